@@ -1,0 +1,328 @@
+"""ctypes binding of libcellula_b200.so (the plain C ABI of include/cellula_b200.h).
+
+This is the Python counterpart of the R `.Call` shim (r-pkg/src/rshim.c): it only converts
+arguments.  There is no CPU fallback anywhere below: if the shared library is missing or no
+B200 is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcellula_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_vp = ctypes.c_void_p
+
+SNN_TYPES = {"rank": 0, "number": 1, "jaccard": 2}
+BUF = dict(libsize_partial=0, gene_acc=1, gram=2, scores=3, knn=4, size_factors=5, logcounts=6)
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in (
+        "h2d_ms", "colsum_ms", "lognorm_ms", "hvg_extract_ms", "gram_ms", "eig_ms", "project_ms",
+        "knn_prep_ms", "knn_tile_ms", "knn_rerank_ms", "snn_revlist_ms", "snn_edges_ms", "d2h_ms")] + [
+        ("kernel_launches", c_i64), ("knn_fallback_queries", c_i64), ("eig_iterations", c_i64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/cellula_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "cb200_init": (c_int, [c_int, c_vp, ctypes.POINTER(c_vp)]),
+    "cb200_free": (c_int, [c_vp]),
+    "cb200_last_error": (ctypes.c_char_p, [c_vp]),
+    "cb200_version": (ctypes.c_char_p, []),
+    "cb200_synchronize": (c_int, [c_vp]),
+    "cb200_stage_timings": (c_int, [c_vp, ctypes.POINTER(Timing)]),
+    "cb200_reset_timings": (c_int, [c_vp]),
+    "cb200_device_ptr": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp), c_i64p]),
+    "cb200_load_csc": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64]),
+    "cb200_load_csc_i32": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64]),
+    "cb200_size_factors_local": (c_int, [c_vp, c_vp]),
+    "cb200_size_factors_finish": (c_int, [c_vp, ctypes.c_double, c_i64, c_vp]),
+    "cb200_size_factors": (c_int, [c_vp, c_vp, c_vp]),
+    "cb200_lognorm_genestats_local": (c_int, [c_vp]),
+    "cb200_genestats_finish": (c_int, [c_vp, c_vp, c_vp]),
+    "cb200_fetch_logcounts": (c_int, [c_vp, c_vp]),
+    "cb200_lognorm_genestats": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cb200_pca_gram_local": (c_int, [c_vp, c_vp, c_int]),
+    "cb200_pca_finish": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "cb200_pca": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "cb200_knn": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp]),
+    "cb200_knn_device": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp]),
+    "cb200_snn": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_i64p,
+                          ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p), ctypes.POINTER(c_f64p)]),
+    "cb200_snn_device": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_i64p,
+                                 ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p), ctypes.POINTER(c_f64p)]),
+    "cb200_snn_resident": (c_int, [c_vp, c_int, c_int, c_i64p]),
+    "cb200_free_edges": (c_int, [c_i32p, c_i32p, c_f64p]),
+    "cb200_synth_counts": (c_int, [c_vp, c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_i64p]),
+    "cb200_export_csc": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+class Cb200Error(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into cellula_b200/libcellula_b200.so (nvcc, in-tree)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise Cb200Error("building libcellula_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Cb200Error(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). cellula_b200 has no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return c_vp(a)
+    return c_vp(a.ctypes.data)
+
+
+class Context:
+    """One cb200_ctx = one GPU (one process per GPU in a multi-GPU job)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = c_vp()
+        L = lib()
+        rc = L.cb200_init(device, c_vp(stream) if stream else None, ctypes.byref(self._h))
+        if rc != 0:
+            raise Cb200Error(L.cb200_last_error(None).decode())
+        self.device = device
+        self.n_genes = self.n_cells = self.nnz = 0
+        self.cell_offset = 0
+        self.n_cells_total = 0
+
+    # -- plumbing -------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise Cb200Error(lib().cb200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value is not None:
+            lib().cb200_free(self._h)
+            self._h = c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def synchronize(self):
+        self._ck(lib().cb200_synchronize(self._h))
+
+    def timings(self) -> dict:
+        t = Timing()
+        self._ck(lib().cb200_stage_timings(self._h, ctypes.byref(t)))
+        return t.as_dict()
+
+    def reset_timings(self):
+        self._ck(lib().cb200_reset_timings(self._h))
+
+    def device_ptr(self, which: str):
+        p, n = c_vp(), c_i64()
+        self._ck(lib().cb200_device_ptr(self._h, BUF[which], ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    # -- a1 -------------------------------------------------------------------------
+    def load_csc(self, n_genes, colptr, rowidx, values, cell_offset=0, n_cells_total=None):
+        colptr = np.ascontiguousarray(colptr)
+        rowidx = np.ascontiguousarray(rowidx, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        n_cells = colptr.size - 1
+        if n_cells_total is None:
+            n_cells_total = n_cells
+        if colptr.dtype == np.int32:
+            fn = lib().cb200_load_csc_i32
+        else:
+            colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+            fn = lib().cb200_load_csc
+        self._ck(fn(self._h, n_genes, n_cells, _ptr(colptr), _ptr(rowidx), _ptr(values), cell_offset,
+                    n_cells_total))
+        self.n_genes, self.n_cells, self.nnz = int(n_genes), int(n_cells), int(values.size)
+        self.cell_offset, self.n_cells_total = int(cell_offset), int(n_cells_total)
+
+    def load_csc_ptrs(self, n_genes, n_cells, nnz, colptr_ptr, rowidx_ptr, values_ptr, cell_offset=0,
+                      n_cells_total=None):
+        """Same, from raw host addresses (pinned torch buffers in bench.py)."""
+        if n_cells_total is None:
+            n_cells_total = n_cells
+        self._ck(lib().cb200_load_csc(self._h, n_genes, n_cells, c_vp(colptr_ptr), c_vp(rowidx_ptr),
+                                      c_vp(values_ptr), cell_offset, n_cells_total))
+        self.n_genes, self.n_cells, self.nnz = int(n_genes), int(n_cells), int(nnz)
+        self.cell_offset, self.n_cells_total = int(cell_offset), int(n_cells_total)
+
+    def synth_counts(self, n_genes, n_cells, nnz_per_cell, seed, cell_offset=0, n_cells_total=None):
+        if n_cells_total is None:
+            n_cells_total = n_cells
+        nnz = c_i64()
+        self._ck(lib().cb200_synth_counts(self._h, n_genes, n_cells, float(nnz_per_cell), seed, cell_offset,
+                                          n_cells_total, ctypes.byref(nnz)))
+        self.n_genes, self.n_cells, self.nnz = int(n_genes), int(n_cells), int(nnz.value)
+        self.cell_offset, self.n_cells_total = int(cell_offset), int(n_cells_total)
+        return self.nnz
+
+    def export_csc(self, colptr=None, rowidx=None, values=None):
+        colptr = np.empty(self.n_cells + 1, dtype=np.int64) if colptr is None else colptr
+        rowidx = np.empty(self.nnz, dtype=np.int32) if rowidx is None else rowidx
+        values = np.empty(self.nnz, dtype=np.float64) if values is None else values
+        self._ck(lib().cb200_export_csc(self._h, _ptr(colptr), _ptr(rowidx), _ptr(values)))
+        return colptr, rowidx, values
+
+    # -- a2 -------------------------------------------------------------------------
+    def size_factors(self, sf_in=None, want=True):
+        sf_in = None if sf_in is None else np.ascontiguousarray(sf_in, dtype=np.float64)
+        out = np.empty(self.n_cells) if want else None
+        self._ck(lib().cb200_size_factors(self._h, _ptr(sf_in), _ptr(out)))
+        return out
+
+    def size_factors_local(self, sf_in=None):
+        sf_in = None if sf_in is None else np.ascontiguousarray(sf_in, dtype=np.float64)
+        self._ck(lib().cb200_size_factors_local(self._h, _ptr(sf_in)))
+
+    def size_factors_finish(self, total, n_cells_total, want=True):
+        out = np.empty(self.n_cells) if want else None
+        self._ck(lib().cb200_size_factors_finish(self._h, float(total), int(n_cells_total), _ptr(out)))
+        return out
+
+    # -- a3 + a4 ----------------------------------------------------------------------
+    def lognorm_genestats(self, want_logx=True, want_stats=True, logx_out=None):
+        logx = logx_out if logx_out is not None else (np.empty(self.nnz) if want_logx else None)
+        mean = np.empty(self.n_genes) if want_stats else None
+        var = np.empty(self.n_genes) if want_stats else None
+        self._ck(lib().cb200_lognorm_genestats(self._h, _ptr(logx), _ptr(mean), _ptr(var)))
+        return logx, mean, var
+
+    def lognorm_genestats_local(self):
+        self._ck(lib().cb200_lognorm_genestats_local(self._h))
+
+    def genestats_finish(self, want=True):
+        mean = np.empty(self.n_genes) if want else None
+        var = np.empty(self.n_genes) if want else None
+        self._ck(lib().cb200_genestats_finish(self._h, _ptr(mean), _ptr(var)))
+        return mean, var
+
+    def fetch_logcounts(self, out=None):
+        out = np.empty(self.nnz) if out is None else out
+        self._ck(lib().cb200_fetch_logcounts(self._h, _ptr(out)))
+        return out
+
+    # -- a7 -------------------------------------------------------------------------
+    def pca(self, hvg_idx, d, want_scores=True, scores_out=None):
+        hvg_idx = np.ascontiguousarray(hvg_idx, dtype=np.int32)
+        self.pca_gram_local(hvg_idx)
+        return self.pca_finish(d, len(hvg_idx), want_scores=want_scores, scores_out=scores_out)
+
+    def pca_gram_local(self, hvg_idx):
+        hvg_idx = np.ascontiguousarray(hvg_idx, dtype=np.int32)
+        self._ck(lib().cb200_pca_gram_local(self._h, _ptr(hvg_idx), len(hvg_idx)))
+
+    def pca_finish(self, d, n_hvg, want_scores=True, scores_out=None):
+        scores = scores_out if scores_out is not None else (
+            np.empty((self.n_cells, d), order="F") if want_scores else None)
+        rotation = np.empty((n_hvg, d), order="F")
+        varexp = np.empty(d)
+        total = ctypes.c_double()
+        self._ck(lib().cb200_pca_finish(self._h, d, _ptr(scores), _ptr(rotation), _ptr(varexp),
+                                        ctypes.cast(ctypes.byref(total), c_vp)))
+        return dict(scores=scores, rotation=rotation, var_explained=varexp, total_var=total.value,
+                    percent_var=100.0 * varexp / total.value)
+
+    # -- a9 -------------------------------------------------------------------------
+    def knn(self, emb, k, q_begin=0, q_end=None, want=True, n_total=None, d=None, out=None):
+        """emb: N x d array (any layout; passed column-major) or None for the resident PCA scores."""
+        if emb is not None:
+            emb = np.asfortranarray(emb, dtype=np.float64)
+            n_total, d = emb.shape
+        q_end = n_total if q_end is None else q_end
+        idx = out if out is not None else (np.empty((q_end - q_begin, k), dtype=np.int32, order="F") if want else None)
+        self._ck(lib().cb200_knn(self._h, _ptr(emb), n_total, d, k, q_begin, q_end, _ptr(idx)))
+        return idx
+
+    def knn_device(self, d_emb_ptr, n_total, d, k, q_begin, q_end, want=True):
+        idx = np.empty((q_end - q_begin, k), dtype=np.int32, order="F") if want else None
+        self._ck(lib().cb200_knn_device(self._h, c_vp(d_emb_ptr), n_total, d, k, q_begin, q_end, _ptr(idx)))
+        return idx
+
+    # -- a10 ------------------------------------------------------------------------
+    def _take_edges(self, ne, pf, pt, pw):
+        m = ne.value
+        if m > 0:
+            f = np.ctypeslib.as_array(pf, shape=(m,)).copy()
+            t = np.ctypeslib.as_array(pt, shape=(m,)).copy()
+            w = np.ctypeslib.as_array(pw, shape=(m,)).copy()
+        else:
+            f, t, w = np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0)
+        lib().cb200_free_edges(pf, pt, pw)
+        return f, t, w
+
+    def snn(self, index, snn_type="rank", j_begin=0, j_end=None, n_total=None, k=None):
+        """index: N x k 1-based (findKNN layout) or None for the resident kNN result."""
+        if index is not None:
+            index = np.asfortranarray(index, dtype=np.int32)
+            n_total, k = index.shape
+        j_end = n_total if j_end is None else j_end
+        ne = c_i64()
+        pf, pt, pw = c_i32p(), c_i32p(), c_f64p()
+        self._ck(lib().cb200_snn(self._h, _ptr(index), n_total, k, SNN_TYPES[snn_type], j_begin, j_end,
+                                 ctypes.byref(ne), ctypes.byref(pf), ctypes.byref(pt), ctypes.byref(pw)))
+        return self._take_edges(ne, pf, pt, pw)
+
+    def snn_device(self, d_index_ptr, n_total, k, snn_type, j_begin, j_end, fetch=True):
+        ne = c_i64()
+        if not fetch:  # edges stay in HBM, only the count comes back
+            self._ck(lib().cb200_snn_device(self._h, c_vp(d_index_ptr), n_total, k, SNN_TYPES[snn_type], j_begin,
+                                            j_end, ctypes.byref(ne), None, None, None))
+            return ne.value
+        pf, pt, pw = c_i32p(), c_i32p(), c_f64p()
+        self._ck(lib().cb200_snn_device(self._h, c_vp(d_index_ptr), n_total, k, SNN_TYPES[snn_type], j_begin,
+                                        j_end, ctypes.byref(ne), ctypes.byref(pf), ctypes.byref(pt),
+                                        ctypes.byref(pw)))
+        return self._take_edges(ne, pf, pt, pw)
+
+    def snn_resident(self, k, snn_type="rank"):
+        ne = c_i64()
+        self._ck(lib().cb200_snn_resident(self._h, k, SNN_TYPES[snn_type], ctypes.byref(ne)))
+        return ne.value

@@ -1,0 +1,248 @@
+// cb200_common.cuh -- context, error handling and small device helpers shared by the
+// kernels of libcellula_b200.so (sm_100a).  See include/cellula_b200.h for the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/cellula_b200.h"
+
+#define CB200_NUM_SM_FALLBACK 148
+
+// ---------------------------------------------------------------------------------------
+// device buffer that grows on demand and is released with the context
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;  // capacity in elements
+    cudaError_t ensure(size_t count)
+    {
+        if (p != nullptr && count <= n)
+            return cudaSuccess;
+        if (p != nullptr) {
+            cudaFree(p);
+            p = nullptr;
+            n = 0;
+        }
+        size_t want = count > 0 ? count : 1;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T));
+        if (e == cudaSuccess)
+            n = want;
+        return e;
+    }
+    void release()
+    {
+        if (p != nullptr)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+enum Cb200Stage {
+    ST_H2D = 0,
+    ST_COLSUM,
+    ST_LOGNORM,
+    ST_HVG_EXTRACT,
+    ST_GRAM,
+    ST_EIG,
+    ST_PROJECT,
+    ST_KNN_PREP,
+    ST_KNN_TILE,
+    ST_KNN_RERANK,
+    ST_SNN_REVLIST,
+    ST_SNN_EDGES,
+    ST_D2H,
+    ST_COUNT_
+};
+
+struct cb200_ctx {
+    int device = 0;
+    int num_sms = CB200_NUM_SM_FALLBACK;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // ---- a1: counts shard (CSC, genes x local cells)
+    int64_t G = 0, N = 0, nnz = 0, cell_offset = 0, N_total = 0;
+    DevBuf<int64_t> colptr;
+    DevBuf<int32_t> rowidx;
+    DevBuf<double> x;
+    bool loaded = false;
+
+    // ---- a2/a3/a4
+    DevBuf<double> libsize;   // [N]
+    DevBuf<double> sf;        // [N]
+    DevBuf<double> part;      // [2]  local sum, local count
+    DevBuf<int> flag;         // [4]  device-side error flags
+    DevBuf<double> logx;      // [nnz]
+    DevBuf<double> gene_acc;  // [2G] sum y, sum y^2
+    DevBuf<double> gene_mean, gene_var;  // [G]
+    bool have_sf = false, have_logx = false, have_genestats = false;
+
+    // ---- a7: PCA
+    int H = 0, d = 0, blk = 0;
+    DevBuf<int32_t> hvg_idx;   // [H]
+    DevBuf<int32_t> slot;      // [G] gene -> hvg slot or -1
+    DevBuf<int32_t> hcnt;      // [N]
+    DevBuf<int64_t> hptr;      // [N+1]
+    DevBuf<int32_t> hslot;     // [nnz_hvg]
+    DevBuf<double> hval;       // [nnz_hvg]
+    int64_t nnz_hvg = 0;
+    DevBuf<double> gram;       // [H*H + H]: upper-triangular accumulation of X^T X, + col sums
+    DevBuf<double> cov;        // [H*H]
+    DevBuf<double> mu;         // [H]
+    DevBuf<double> eq, ew, ey, ex, es, et, etheta, eres, emuv;  // eigen-solver work
+    DevBuf<double> rot;        // [H*d] row-major rotation (V)
+    DevBuf<double> scores;     // [N*d] row-major
+    DevBuf<double> varexp;     // [d]
+    double total_var = 0.0;
+    bool have_gram = false, have_scores = false;
+
+    // ---- a9: kNN
+    DevBuf<double> emb;        // [n_total*d] row-major fp64 (when given from host)
+    DevBuf<double> stage_d;    // staging for column-major <-> row-major conversions
+    DevBuf<float> emb_f;       // [n_total*DP] fp32 padded
+    DevBuf<float> hnorm;       // [n_total]   0.5*|r|^2 (fp32)
+    DevBuf<double> nrm2;       // [n_total]   |r|^2 (fp64)
+    DevBuf<unsigned long long> maxnrm;  // [1] bit pattern of max |r|^2
+    DevBuf<int32_t> cand_idx;  // [nq*KP]
+    DevBuf<float> cand_tau;    // [nq]
+    DevBuf<int32_t> knn;       // [nq*k] row-major 0-based
+    DevBuf<double> knn_dk;     // [nq] exact k-th candidate distance
+    DevBuf<int32_t> fb_list;   // [nq] queries needing the exact scan
+    DevBuf<int32_t> stage_i;   // staging for index layout conversion
+    int64_t knn_nq = 0, knn_ntotal = 0, knn_qbegin = 0;
+    int knn_k = 0;
+    bool have_knn = false;
+
+    // ---- a10: SNN
+    DevBuf<int32_t> index0;    // [n_total*k] row-major 0-based (when given from host)
+    DevBuf<int32_t> rcnt;      // [n_total]
+    DevBuf<int64_t> rptr;      // [n_total+1]
+    DevBuf<int32_t> rcur;      // [n_total]
+    DevBuf<uint32_t> hosts_u;  // unsorted (cell<<8 | rank)
+    DevBuf<uint32_t> hosts;    // sorted by cell within each list
+    DevBuf<int32_t> ecnt;      // [nj]
+    DevBuf<int64_t> eptr;      // [nj+1]
+    DevBuf<int32_t> bcnt;      // [nj*(k+1)] edges of j first met in list i
+    DevBuf<int32_t> efrom, eto;  // [E]
+    DevBuf<double> ew8;          // [E]
+    int64_t n_edges = 0;
+
+    // scan scratch
+    DevBuf<int64_t> scan_blk;
+
+    // ---- timing
+    cudaEvent_t ev[ST_COUNT_][2];
+    bool ev_used[ST_COUNT_];
+    cb200_timing tm;
+};
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+int cb200_fail(cb200_ctx *ctx, const char *fmt, ...);
+
+#define CB_CUDA(ctx, call)                                                                  \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return cb200_fail((ctx), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,   \
+                              cudaGetErrorString(e__));                                     \
+    } while (0)
+
+#define CB_CHECK(ctx, cond, ...)                                                            \
+    do {                                                                                    \
+        if (!(cond))                                                                        \
+            return cb200_fail((ctx), __VA_ARGS__);                                          \
+    } while (0)
+
+#define CB_LAUNCH(ctx)                                                                      \
+    do {                                                                                    \
+        (ctx)->tm.kernel_launches += 1;                                                     \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess)                                                             \
+            return cb200_fail((ctx), "kernel launch failed at %s:%d: %s", __FILE__,         \
+                              __LINE__, cudaGetErrorString(e__));                           \
+    } while (0)
+
+#define CB_TRY(expr)                                                                        \
+    do {                                                                                    \
+        int rc__ = (expr);                                                                  \
+        if (rc__ != 0)                                                                      \
+            return rc__;                                                                    \
+    } while (0)
+
+static inline void cb_stage_begin(cb200_ctx *ctx, int st)
+{
+    cudaEventRecord(ctx->ev[st][0], ctx->stream);
+}
+static inline void cb_stage_end(cb200_ctx *ctx, int st)
+{
+    cudaEventRecord(ctx->ev[st][1], ctx->stream);
+    ctx->ev_used[st] = true;
+}
+
+// exclusive scan of int32 counts into int64 offsets (out has n+1 entries, out[n] = total)
+int cb200_scan_i32_to_i64(cb200_ctx *ctx, const int32_t *d_in, int64_t n, int64_t *d_out);
+
+static inline int cb_grid_for(int64_t work_items, int per_block, int max_blocks)
+{
+    int64_t b = (work_items + per_block - 1) / per_block;
+    if (b < 1)
+        b = 1;
+    if (b > max_blocks)
+        b = max_blocks;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// streaming 64-/128-bit loads that do not pollute L1 (data is touched once)
+__device__ __forceinline__ double ld_stream(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_stream2(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_i(const int *p)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(double *p, double v)
+{
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+#endif

@@ -1,0 +1,387 @@
+// cb200_ctx.cu -- context lifetime, error reporting, stage timing, counts upload (a1) and
+// the device-wide exclusive scan used by the compaction steps.
+#include <cstdarg>
+#include <cstring>
+
+#include "cb200_common.cuh"
+
+static std::string g_init_error;
+
+int cb200_fail(cb200_ctx *ctx, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx != nullptr)
+        ctx->err = buf;
+    else
+        g_init_error = buf;
+    return 1;
+}
+
+extern "C" const char *cb200_version(void) { return "cellula_b200 0.1 sm_100a"; }
+
+extern "C" const char *cb200_last_error(const cb200_ctx *ctx)
+{
+    return ctx != nullptr ? ctx->err.c_str() : g_init_error.c_str();
+}
+
+extern "C" int cb200_init(int device, void *stream, cb200_ctx **out)
+{
+    if (out == nullptr)
+        return cb200_fail(nullptr, "cb200_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return cb200_fail(nullptr, "cb200_init: no CUDA device available (%s); this library has no CPU path",
+                          cudaGetErrorString(e));
+    if (device < 0 || device >= count)
+        return cb200_fail(nullptr, "cb200_init: device %d out of range (have %d)", device, count);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return cb200_fail(nullptr, "cb200_init: cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess)
+        return cb200_fail(nullptr, "cb200_init: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return cb200_fail(nullptr,
+                          "cb200_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                          device, prop.major, prop.minor);
+    cb200_ctx *ctx = new cb200_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (stream != nullptr) {
+        ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+        ctx->own_stream = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return cb200_fail(nullptr, "cb200_init: cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        ctx->own_stream = true;
+    }
+    for (int s = 0; s < ST_COUNT_; ++s) {
+        cudaEventCreate(&ctx->ev[s][0]);
+        cudaEventCreate(&ctx->ev[s][1]);
+        ctx->ev_used[s] = false;
+    }
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    if (ctx->part.ensure(2) != cudaSuccess || ctx->flag.ensure(4) != cudaSuccess ||
+        ctx->maxnrm.ensure(1) != cudaSuccess) {
+        delete ctx;
+        return cb200_fail(nullptr, "cb200_init: device allocation failed");
+    }
+    cudaMemsetAsync(ctx->flag.p, 0, 4 * sizeof(int), ctx->stream);
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int cb200_free(cb200_ctx *ctx)
+{
+    if (ctx == nullptr)
+        return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->colptr.release(); ctx->rowidx.release(); ctx->x.release();
+    ctx->libsize.release(); ctx->sf.release(); ctx->part.release(); ctx->flag.release();
+    ctx->logx.release(); ctx->gene_acc.release(); ctx->gene_mean.release(); ctx->gene_var.release();
+    ctx->hvg_idx.release(); ctx->slot.release(); ctx->hcnt.release(); ctx->hptr.release();
+    ctx->hslot.release(); ctx->hval.release(); ctx->gram.release(); ctx->cov.release();
+    ctx->mu.release(); ctx->eq.release(); ctx->ew.release(); ctx->ey.release(); ctx->ex.release();
+    ctx->es.release(); ctx->et.release(); ctx->etheta.release(); ctx->eres.release();
+    ctx->emuv.release(); ctx->rot.release(); ctx->scores.release(); ctx->varexp.release();
+    ctx->emb.release(); ctx->stage_d.release(); ctx->emb_f.release(); ctx->hnorm.release();
+    ctx->nrm2.release(); ctx->maxnrm.release(); ctx->cand_idx.release(); ctx->cand_tau.release();
+    ctx->knn.release(); ctx->knn_dk.release(); ctx->fb_list.release(); ctx->stage_i.release();
+    ctx->index0.release(); ctx->rcnt.release(); ctx->rptr.release(); ctx->rcur.release();
+    ctx->hosts_u.release(); ctx->hosts.release(); ctx->ecnt.release(); ctx->eptr.release();
+    ctx->bcnt.release(); ctx->efrom.release(); ctx->eto.release(); ctx->ew8.release();
+    ctx->scan_blk.release();
+    for (int s = 0; s < ST_COUNT_; ++s) {
+        cudaEventDestroy(ctx->ev[s][0]);
+        cudaEventDestroy(ctx->ev[s][1]);
+    }
+    if (ctx->own_stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+extern "C" int cb200_synchronize(cb200_ctx *ctx)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int cb200_reset_timings(cb200_ctx *ctx)
+{
+    if (ctx == nullptr)
+        return 1;
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    for (int s = 0; s < ST_COUNT_; ++s)
+        ctx->ev_used[s] = false;
+    return 0;
+}
+
+extern "C" int cb200_stage_timings(cb200_ctx *ctx, cb200_timing *out)
+{
+    if (ctx == nullptr || out == nullptr)
+        return 1;
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double *slots[ST_COUNT_] = {&ctx->tm.h2d_ms,        &ctx->tm.colsum_ms,      &ctx->tm.lognorm_ms,
+                                &ctx->tm.hvg_extract_ms, &ctx->tm.gram_ms,        &ctx->tm.eig_ms,
+                                &ctx->tm.project_ms,     &ctx->tm.knn_prep_ms,    &ctx->tm.knn_tile_ms,
+                                &ctx->tm.knn_rerank_ms,  &ctx->tm.snn_revlist_ms, &ctx->tm.snn_edges_ms,
+                                &ctx->tm.d2h_ms};
+    for (int s = 0; s < ST_COUNT_; ++s) {
+        if (ctx->ev_used[s]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->ev[s][0], ctx->ev[s][1]) == cudaSuccess)
+                *slots[s] = (double)ms;
+        }
+    }
+    *out = ctx->tm;
+    return 0;
+}
+
+extern "C" int cb200_device_ptr(cb200_ctx *ctx, int which, void **ptr, int64_t *bytes)
+{
+    if (ctx == nullptr || ptr == nullptr || bytes == nullptr)
+        return 1;
+    switch (which) {
+    case CB200_BUF_LIBSIZE_PARTIAL: *ptr = ctx->part.p; *bytes = 2 * sizeof(double); break;
+    case CB200_BUF_GENE_ACC: *ptr = ctx->gene_acc.p; *bytes = 2 * ctx->G * (int64_t)sizeof(double); break;
+    case CB200_BUF_GRAM:
+        *ptr = ctx->gram.p;
+        *bytes = ((int64_t)ctx->H * ctx->H) * (int64_t)sizeof(double);
+        break;
+    case CB200_BUF_SCORES: *ptr = ctx->scores.p; *bytes = ctx->N * (int64_t)ctx->d * (int64_t)sizeof(double); break;
+    case CB200_BUF_KNN: *ptr = ctx->knn.p; *bytes = ctx->knn_nq * (int64_t)ctx->knn_k * (int64_t)sizeof(int32_t); break;
+    case CB200_BUF_SIZE_FACTORS: *ptr = ctx->sf.p; *bytes = ctx->N * (int64_t)sizeof(double); break;
+    case CB200_BUF_LOGCOUNTS: *ptr = ctx->logx.p; *bytes = ctx->nnz * (int64_t)sizeof(double); break;
+    default: return cb200_fail(ctx, "cb200_device_ptr: unknown buffer id %d", which);
+    }
+    if (*ptr == nullptr)
+        return cb200_fail(ctx, "cb200_device_ptr: buffer %d has not been produced yet", which);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// a1: counts upload
+// ---------------------------------------------------------------------------------------
+__global__ void k_widen_colptr(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = (int64_t)in[i];
+}
+
+static int load_common(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, int64_t nnz,
+                       const int32_t *rowidx, const double *values, int64_t cell_offset,
+                       int64_t n_cells_total)
+{
+    CB_CHECK(ctx, n_genes > 0 && n_genes < 2147483647LL, "cb200_load_csc: n_genes must be in [1, 2^31)");
+    CB_CHECK(ctx, n_cells > 0, "cb200_load_csc: n_cells must be positive");
+    CB_CHECK(ctx, cell_offset >= 0 && cell_offset + n_cells <= n_cells_total,
+             "cb200_load_csc: shard [%lld, %lld) does not fit n_cells_total=%lld", (long long)cell_offset,
+             (long long)(cell_offset + n_cells), (long long)n_cells_total);
+    ctx->G = n_genes;
+    ctx->N = n_cells;
+    ctx->nnz = nnz;
+    ctx->cell_offset = cell_offset;
+    ctx->N_total = n_cells_total;
+    CB_CUDA(ctx, ctx->rowidx.ensure((size_t)nnz));
+    CB_CUDA(ctx, ctx->x.ensure((size_t)nnz));
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->rowidx.p, rowidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->x.p, values, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    ctx->loaded = true;
+    ctx->have_sf = ctx->have_logx = ctx->have_genestats = ctx->have_gram = ctx->have_scores = false;
+    ctx->have_knn = false;
+    return 0;
+}
+
+extern "C" int cb200_load_csc(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, const int64_t *colptr,
+                              const int32_t *rowidx, const double *values, int64_t cell_offset,
+                              int64_t n_cells_total)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, colptr != nullptr && rowidx != nullptr && values != nullptr, "cb200_load_csc: NULL input");
+    CB_CHECK(ctx, n_cells > 0, "cb200_load_csc: n_cells must be positive");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t base = colptr[0];
+    int64_t nnz = colptr[n_cells] - base;
+    CB_CHECK(ctx, base == 0, "cb200_load_csc: colptr[0] must be 0 (rebase the shard's column pointers)");
+    CB_CHECK(ctx, nnz >= 0, "cb200_load_csc: colptr is not non-decreasing");
+    cb_stage_begin(ctx, ST_H2D);
+    CB_CUDA(ctx, ctx->colptr.ensure((size_t)n_cells + 1));
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->colptr.p, colptr, (size_t)(n_cells + 1) * sizeof(int64_t),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    CB_TRY(load_common(ctx, n_genes, n_cells, nnz, rowidx, values, cell_offset, n_cells_total));
+    cb_stage_end(ctx, ST_H2D);
+    return 0;
+}
+
+extern "C" int cb200_load_csc_i32(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, const int32_t *colptr,
+                                  const int32_t *rowidx, const double *values, int64_t cell_offset,
+                                  int64_t n_cells_total)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, colptr != nullptr && rowidx != nullptr && values != nullptr, "cb200_load_csc_i32: NULL input");
+    CB_CHECK(ctx, n_cells > 0, "cb200_load_csc_i32: n_cells must be positive");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CB_CHECK(ctx, colptr[0] == 0, "cb200_load_csc_i32: p[0] must be 0");
+    int64_t nnz = colptr[n_cells];
+    CB_CHECK(ctx, nnz >= 0, "cb200_load_csc_i32: p is not non-decreasing");
+    cb_stage_begin(ctx, ST_H2D);
+    CB_CUDA(ctx, ctx->colptr.ensure((size_t)n_cells + 1));
+    CB_CUDA(ctx, ctx->stage_i.ensure((size_t)n_cells + 1));
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_i.p, colptr, (size_t)(n_cells + 1) * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    k_widen_colptr<<<(unsigned)((n_cells + 1 + 255) / 256), 256, 0, ctx->stream>>>(ctx->stage_i.p, n_cells + 1,
+                                                                                    ctx->colptr.p);
+    CB_LAUNCH(ctx);
+    CB_TRY(load_common(ctx, n_genes, n_cells, nnz, rowidx, values, cell_offset, n_cells_total));
+    cb_stage_end(ctx, ST_H2D);
+    return 0;
+}
+
+extern "C" int cb200_export_csc(cb200_ctx *ctx, int64_t *colptr, int32_t *rowidx, double *values)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->loaded, "cb200_export_csc: no count matrix in the context");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (colptr != nullptr)
+        CB_CUDA(ctx, cudaMemcpyAsync(colptr, ctx->colptr.p, (size_t)(ctx->N + 1) * sizeof(int64_t),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    if (rowidx != nullptr)
+        CB_CUDA(ctx, cudaMemcpyAsync(rowidx, ctx->rowidx.p, (size_t)ctx->nnz * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    if (values != nullptr)
+        CB_CUDA(ctx, cudaMemcpyAsync(values, ctx->x.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// exclusive scan int32 -> int64 (three launches; n up to a few million)
+// ---------------------------------------------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int64_t block_exclusive_scan_i64(int64_t v, int64_t *total)
+{
+    // blockDim.x == SCAN_THREADS
+    __shared__ int64_t warp_tot[SCAN_THREADS / 32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+            inc += t;
+    }
+    if (lane == 31)
+        warp_tot[w] = inc;
+    __syncthreads();
+    int64_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) {
+        int64_t t = warp_tot[i];
+        if (i < w)
+            base += t;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const int32_t *__restrict__ in, int64_t n,
+                                                                 int64_t *__restrict__ tile_sum)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+        if (idx < n)
+            s += in[idx];
+    }
+    int64_t tot;
+    block_exclusive_scan_i64(s, &tot);
+    if (threadIdx.x == 0)
+        tile_sum[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of the tile sums in place (n_tiles arbitrary)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_offsets(int64_t *__restrict__ tile_sum, int64_t n_tiles,
+                                                                    int64_t *__restrict__ grand_total)
+{
+    int64_t carry = 0;
+    for (int64_t b = 0; b < n_tiles; b += SCAN_THREADS) {
+        int64_t idx = b + threadIdx.x;
+        int64_t v = idx < n_tiles ? tile_sum[idx] : 0;
+        int64_t tot;
+        int64_t ex = block_exclusive_scan_i64(v, &tot);
+        if (idx < n_tiles)
+            tile_sum[idx] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0)
+        *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_finish(const int32_t *__restrict__ in, int64_t n,
+                                                              const int64_t *__restrict__ tile_off,
+                                                              int64_t *__restrict__ out)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t vals[SCAN_ITEMS];
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+        vals[i] = idx < n ? (int64_t)in[idx] : 0;
+        s += vals[i];
+    }
+    int64_t tot;
+    int64_t ex = block_exclusive_scan_i64(s, &tot) + tile_off[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+        if (idx < n)
+            out[idx] = ex;
+        ex += vals[i];
+    }
+}
+
+int cb200_scan_i32_to_i64(cb200_ctx *ctx, const int32_t *d_in, int64_t n, int64_t *d_out)
+{
+    if (n <= 0) {
+        CB_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(int64_t), ctx->stream));
+        return 0;
+    }
+    int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CB_CUDA(ctx, ctx->scan_blk.ensure((size_t)n_tiles + 1));
+    k_scan_tile_sums<<<(unsigned)n_tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, ctx->scan_blk.p);
+    CB_LAUNCH(ctx);
+    k_scan_tile_offsets<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->scan_blk.p, n_tiles, d_out + n);
+    CB_LAUNCH(ctx);
+    k_scan_finish<<<(unsigned)n_tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, ctx->scan_blk.p, d_out);
+    CB_LAUNCH(ctx);
+    return 0;
+}

@@ -1,0 +1,564 @@
+// cb200_knn.cu -- K6: exact Euclidean kNN in PC space.
+//
+// Replaces BiocNeighbors::findKNN(x, k, BNPARAM = KmknnParam(), get.distance = FALSE), the
+// neighbour search inside bluster::makeSNNGraph() that /root/reference/R/
+// makeGraphsAndClusters.R:83-85 (and :125-127, :284) calls.  Contract:
+// for every cell the k nearest other cells ordered by (distance, index), distance =
+// sqrt(sum_t (a_t - b_t)^2) accumulated sequentially in fp64 without FMA contraction.
+//
+// Structure
+//   k_knn_prep      fp64 embedding -> padded fp32 copy, 0.5|r|^2, max |r|^2
+//   k_knn_tiles     128 x 128 distance tiles (norm expansion, key = 0.5|r|^2 - q.r) with a
+//                   fused per-query top-KP selection held in shared memory: the N x N
+//                   distance matrix never exists in HBM.  KP > k candidates are kept.
+//   k_knn_rerank    exact fp64 distances of the KP candidates in the reference's arithmetic,
+//                   sort by (distance, index), emit k; prove with the a-priori error bound of
+//                   the approximate keys that no non-candidate can enter the top k, else
+//   k_knn_exact     flag the query for a full fp64 scan (rare).
+// The result is therefore exact regardless of the precision of the tile kernel.
+#include <cfloat>
+#include <cmath>
+
+#include "cb200_common.cuh"
+
+#define KNN_THREADS 256
+#define KNN_TN 128       // references per tile
+#define KNN_MAX_DP 64    // padded embedding width
+#define KNN_FB_CAP 2048  // candidates the exact-scan fallback can hold per query
+
+__global__ void k_colmajor_to_rowmajor(const double *__restrict__ in, int64_t rows, int cols, double *__restrict__ out)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx < rows * cols) {
+        int64_t r = idx / cols;
+        int c = (int)(idx % cols);
+        out[idx] = in[r + rows * (int64_t)c];
+    }
+}
+
+__global__ void k_knn_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, int DP, float *__restrict__ Ef,
+                           float *__restrict__ hn, double *__restrict__ nrm2, unsigned long long *__restrict__ maxbits)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    double s = 0.0;
+    for (int t = 0; t < d; ++t) {
+        double v = E[i * lde + t];
+        s += v * v;
+        Ef[i * DP + t] = (float)v;
+    }
+    for (int t = d; t < DP; ++t)
+        Ef[i * DP + t] = 0.f;
+    hn[i] = (float)(0.5 * s);
+    nrm2[i] = s;
+    atomicMax(maxbits, (unsigned long long)__double_as_longlong(s));  // s >= 0: bit order == value order
+}
+
+// ---------------------------------------------------------------------------------------
+// warp-wide bitonic sort of 32*EPL (key, idx) pairs, element i = e*32 + lane, ascending by
+// (key, idx)
+// ---------------------------------------------------------------------------------------
+template <typename K>
+__device__ __forceinline__ bool pair_less(K ka, int ia, K kb, int ib)
+{
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+template <typename K, int EPL>
+__device__ __forceinline__ void warp_bitonic_sort(K (&key)[EPL], int (&idx)[EPL], int lane)
+{
+    constexpr int NTOT = 32 * EPL;
+#pragma unroll
+    for (int k = 2; k <= NTOT; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int dj = j >> 5;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    const int pe = e ^ dj;
+                    if (pe > e) {
+                        const bool up = (((e * 32 + lane) & k) == 0);
+                        const bool gt = pair_less<K>(key[pe], idx[pe], key[e], idx[e]);  // v[e] > v[pe]
+                        if (gt == up) {
+                            K tk = key[e];
+                            key[e] = key[pe];
+                            key[pe] = tk;
+                            int ti = idx[e];
+                            idx[e] = idx[pe];
+                            idx[pe] = ti;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    const bool up = (((e * 32 + lane) & k) == 0);
+                    const K ok = __shfl_xor_sync(0xffffffffu, key[e], j);
+                    const int oi = __shfl_xor_sync(0xffffffffu, idx[e], j);
+                    const bool lower = ((lane & j) == 0);
+                    const bool other_less = pair_less<K>(ok, oi, key[e], idx[e]);
+                    // the lower lane of an ascending pair keeps the minimum
+                    const bool take_other = (lower == up) ? other_less : !other_less;
+                    if (take_other) {
+                        key[e] = ok;
+                        idx[e] = oi;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6b: distance tiles + fused top-KP selection (fp32 SIMT tile engine)
+// ---------------------------------------------------------------------------------------
+// Per-row candidate store in shared memory: CAP = 2*KP slots.  A candidate is appended when
+// its key beats the row's threshold tau (the KP-th best key seen so far, +inf until KP have
+// been seen); a row holding more than KP entries is compacted by one warp (bitonic sort,
+// keep KP, refresh tau).  Appends that find the store full are retried after compaction.
+template <int KP, int TM>
+struct KnnSmem {
+    static constexpr int CAP = 2 * KP;
+    static constexpr size_t q_floats = (size_t)KNN_MAX_DP * TM;
+    static constexpr size_t r_floats = (size_t)KNN_MAX_DP * KNN_TN;
+    static constexpr size_t bytes = (q_floats + r_floats + KNN_TN) * sizeof(float) + (size_t)TM * sizeof(float) +
+                                    (size_t)TM * sizeof(int) + (size_t)TM * CAP * (sizeof(float) + sizeof(int));
+};
+
+template <int KP>
+__device__ __forceinline__ void knn_compact_row(float *bkey, int *bidx, int *cnt_p, float *tau_p, int lane, bool force)
+{
+    constexpr int CAP = 2 * KP;
+    constexpr int EPL = CAP / 32;
+    int c = *cnt_p;
+    if (c > CAP)
+        c = CAP;
+    if (!force && c <= KP)
+        return;
+    float key[EPL];
+    int idx[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+        const int p = e * 32 + lane;
+        key[e] = p < c ? bkey[p] : FLT_MAX;
+        idx[e] = p < c ? bidx[p] : 0x7fffffff;
+    }
+    warp_bitonic_sort<float, EPL>(key, idx, lane);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+        const int p = e * 32 + lane;
+        if (p < KP) {
+            bkey[p] = key[e];
+            bidx[p] = idx[e];
+        }
+    }
+    // tau = key at sorted position KP-1 (register (KP-1)/32 of lane 31)
+    const float kth = __shfl_sync(0xffffffffu, key[(KP - 1) / 32], 31);
+    __syncwarp();
+    if (lane == 0) {
+        *cnt_p = c < KP ? c : KP;
+        *tau_p = c >= KP ? kth : FLT_MAX;
+    }
+    __syncwarp();
+}
+
+template <int KP, int TM>
+__global__ void __launch_bounds__(KNN_THREADS, 1)
+k_knn_tiles(const float *__restrict__ Ef, const float *__restrict__ hn, int64_t n, int DP, int64_t q_begin,
+            int64_t q_end, int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau)
+{
+    constexpr int CAP = 2 * KP;
+    constexpr int RPT = TM / 16;  // query rows per thread: 8 (TM=128) or 4 (TM=64)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *Qs = reinterpret_cast<float *>(smem_raw);         // [DP][TM]
+    float *Rs = Qs + (size_t)KNN_MAX_DP * TM;                // [DP][KNN_TN]
+    float *hn_s = Rs + (size_t)KNN_MAX_DP * KNN_TN;          // [KNN_TN]
+    float *tau_s = hn_s + KNN_TN;                            // [TM]
+    int *cnt_s = reinterpret_cast<int *>(tau_s + TM);        // [TM]
+    float *bkey = reinterpret_cast<float *>(cnt_s + TM);     // [TM][CAP]
+    int *bidx = reinterpret_cast<int *>(bkey + (size_t)TM * CAP);  // [TM][CAP]
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t q0 = q_begin + (int64_t)blockIdx.x * TM;
+
+    for (int i = tid; i < TM; i += KNN_THREADS) {
+        tau_s[i] = FLT_MAX;
+        cnt_s[i] = 0;
+    }
+    // query tile, transposed into [t][row]; rows beyond the range are zero
+    const int dp4 = DP >> 2;
+    for (int i = tid; i < TM * dp4; i += KNN_THREADS) {
+        const int row = i % TM, c4 = i / TM;
+        const int64_t g = q0 + row;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < q_end)
+            v = *reinterpret_cast<const float4 *>(Ef + g * DP + c4 * 4);
+        Qs[(c4 * 4 + 0) * TM + row] = v.x;
+        Qs[(c4 * 4 + 1) * TM + row] = v.y;
+        Qs[(c4 * 4 + 2) * TM + row] = v.z;
+        Qs[(c4 * 4 + 3) * TM + row] = v.w;
+    }
+    __syncthreads();
+
+    for (int64_t r0 = 0; r0 < n; r0 += KNN_TN) {
+        for (int i = tid; i < KNN_TN * dp4; i += KNN_THREADS) {
+            const int row = i % KNN_TN, c4 = i / KNN_TN;
+            const int64_t g = r0 + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g < n)
+                v = *reinterpret_cast<const float4 *>(Ef + g * DP + c4 * 4);
+            Rs[(c4 * 4 + 0) * KNN_TN + row] = v.x;
+            Rs[(c4 * 4 + 1) * KNN_TN + row] = v.y;
+            Rs[(c4 * 4 + 2) * KNN_TN + row] = v.z;
+            Rs[(c4 * 4 + 3) * KNN_TN + row] = v.w;
+        }
+        if (tid < KNN_TN)
+            hn_s[tid] = (r0 + tid < n) ? hn[r0 + tid] : FLT_MAX;
+        __syncthreads();
+
+        float acc[RPT][8];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                acc[i][j] = 0.f;
+        for (int t = 0; t < DP; ++t) {
+            float a[RPT], b[8];
+            const float4 a0 = *reinterpret_cast<const float4 *>(Qs + t * TM + ty * 4);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+            if (RPT == 8) {
+                const float4 a1 = *reinterpret_cast<const float4 *>(Qs + t * TM + (TM / 2) + ty * 4);
+                a[RPT - 4] = a1.x; a[RPT - 3] = a1.y; a[RPT - 2] = a1.z; a[RPT - 1] = a1.w;
+            }
+            const float4 b0 = *reinterpret_cast<const float4 *>(Rs + t * KNN_TN + tx * 4);
+            const float4 b1 = *reinterpret_cast<const float4 *>(Rs + t * KNN_TN + 64 + tx * 4);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+            b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+
+        // selection; `done` marks the elements of this thread's micro-tile already stored
+        unsigned long long done = 0ULL;
+        int again;
+        do {
+            int ovf = 0;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const int row = (i < 4) ? (ty * 4 + i) : ((TM / 2) + ty * 4 + (i - 4));
+                const int64_t grow = q0 + row;
+                if (grow >= q_end)
+                    continue;
+                const float tau = tau_s[row];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int bit = i * 8 + j;
+                    if ((done >> bit) & 1ULL)
+                        continue;
+                    const int col = (j < 4) ? (tx * 4 + j) : (64 + tx * 4 + (j - 4));
+                    const int64_t gcol = r0 + col;
+                    const float key = hn_s[col] - acc[i][j];
+                    if (key < tau && gcol < n && gcol != grow) {
+                        const int pos = atomicAdd(&cnt_s[row], 1);
+                        if (pos < CAP) {
+                            bkey[(size_t)row * CAP + pos] = key;
+                            bidx[(size_t)row * CAP + pos] = (int)gcol;
+                            done |= (1ULL << bit);
+                        } else {
+                            ovf = 1;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int row = w; row < TM; row += KNN_THREADS / 32)
+                knn_compact_row<KP>(bkey + (size_t)row * CAP, bidx + (size_t)row * CAP, cnt_s + row, tau_s + row, lane,
+                                    false);
+            again = __syncthreads_or(ovf);
+        } while (again);
+    }
+
+    // final: sort every row's store and write the KP best candidates + the row threshold
+    for (int row = w; row < TM; row += KNN_THREADS / 32) {
+        const int64_t grow = q0 + row;
+        if (grow >= q_end)
+            continue;
+        knn_compact_row<KP>(bkey + (size_t)row * CAP, bidx + (size_t)row * CAP, cnt_s + row, tau_s + row, lane, true);
+        const int c = cnt_s[row];
+        int32_t *out = cand_idx + (grow - q_begin) * KP;
+        for (int p = lane; p < KP; p += 32)
+            out[p] = p < c ? bidx[(size_t)row * CAP + p] : -1;
+        if (lane == 0)
+            cand_tau[grow - q_begin] = tau_s[row];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6c: exact re-rank.  Warp per query.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double exact_dist(const double *__restrict__ a, const double *__restrict__ b, int d)
+{
+    // the reference's arithmetic: sequential fp64, separate multiply and add, then sqrt
+    double acc = 0.0;
+    for (int t = 0; t < d; ++t) {
+        const double dl = __dsub_rn(a[t], b[t]);
+        acc = __dadd_rn(acc, __dmul_rn(dl, dl));
+    }
+    return __dsqrt_rn(acc);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(256)
+k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, int64_t nq, int k,
+             const int32_t *__restrict__ cand_idx, const float *__restrict__ cand_tau, const double *__restrict__ nrm2,
+             const unsigned long long *__restrict__ maxbits, double err_coef, int32_t *__restrict__ knn,
+             double *__restrict__ knn_dk, int32_t *__restrict__ fb_list, int *__restrict__ fb_count)
+{
+    constexpr int EPL = KP / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const double m2 = __longlong_as_double((long long)*maxbits);
+    for (int64_t q = warp0; q < nq; q += nwarps) {
+        const int64_t grow = q_begin + q;
+        const double *qa = E + grow * lde;
+        double key[EPL];
+        int idx[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const int ci = cand_idx[q * KP + e * 32 + lane];
+            if (ci >= 0) {
+                key[e] = exact_dist(qa, E + (int64_t)ci * lde, d);
+                idx[e] = ci;
+            } else {
+                key[e] = DBL_MAX;
+                idx[e] = 0x7fffffff;
+            }
+        }
+        warp_bitonic_sort<double, EPL>(key, idx, lane);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const int p = e * 32 + lane;
+            if (p < k)
+                knn[q * k + p] = idx[e];
+        }
+        // k-th exact distance sits at sorted position k-1
+        double dk = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const double v = __shfl_sync(0xffffffffu, key[e], (k - 1) & 31);
+            if (e == ((k - 1) >> 5))
+                dk = v;
+        }
+        if (lane == 0) {
+            knn_dk[q] = dk;
+            const double nq2 = nrm2[grow];
+            const double ek = 0.5 * dk * dk - 0.5 * nq2;      // exact key of the k-th candidate
+            const double bound = err_coef * (nq2 + m2);       // |approx key - exact key| <= bound
+            const float tau = cand_tau[q];
+            const bool proven = (tau == FLT_MAX) || (ek + bound < (double)tau - bound);
+            if (!proven) {
+                const int pos = atomicAdd(fb_count, 1);
+                fb_list[pos] = (int32_t)q;
+            }
+        }
+    }
+}
+
+// Exact scan for one flagged query per block: every reference whose exact distance is
+// <= the exact distance of the k-th candidate is collected, then ranked by (distance, index).
+__global__ void __launch_bounds__(256)
+k_knn_exact(const double *__restrict__ E, int64_t lde, int d, int64_t n, int64_t q_begin, int k,
+            const int32_t *__restrict__ fb_list, const double *__restrict__ knn_dk, int32_t *__restrict__ knn,
+            int *__restrict__ err_flag)
+{
+    __shared__ double sd[KNN_FB_CAP];
+    __shared__ int si[KNN_FB_CAP];
+    __shared__ int cnt;
+    const int64_t q = fb_list[blockIdx.x];
+    const int64_t grow = q_begin + q;
+    const double thr = knn_dk[q];
+    const double *qa = E + grow * lde;
+    if (threadIdx.x == 0)
+        cnt = 0;
+    __syncthreads();
+    for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
+        if (r == grow)
+            continue;
+        const double dist = exact_dist(qa, E + r * lde, d);
+        if (dist <= thr) {
+            const int pos = atomicAdd(&cnt, 1);
+            if (pos < KNN_FB_CAP) {
+                sd[pos] = dist;
+                si[pos] = (int)r;
+            }
+        }
+    }
+    __syncthreads();
+    const int c = cnt;
+    if (c > KNN_FB_CAP || c < k) {
+        if (threadIdx.x == 0)
+            atomicOr(err_flag, 1);
+        return;
+    }
+    for (int e = threadIdx.x; e < c; e += blockDim.x) {
+        const double de = sd[e];
+        const int ie = si[e];
+        int rank = 0;
+        for (int o = 0; o < c; ++o)
+            rank += pair_less<double>(sd[o], si[o], de, ie) ? 1 : 0;
+        if (rank < k)
+            knn[q * k + rank] = ie;
+    }
+}
+
+// knn (row-major, 0-based) -> column-major 1-based (R layout)
+__global__ void k_knn_to_r_layout(const int32_t *__restrict__ knn, int64_t nq, int k, int32_t *__restrict__ out)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx < nq * k) {
+        int64_t q = idx % nq;
+        int c = (int)(idx / nq);
+        out[idx] = knn[q * k + c] + 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+template <int KP, int TM>
+static int run_tiles_and_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int d, int DP, int k,
+                                int64_t q_begin, int64_t q_end)
+{
+    const int64_t nq = q_end - q_begin;
+    const size_t smem = KnnSmem<KP, TM>::bytes;
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles<KP, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(ctx, ctx->cand_idx.ensure((size_t)nq * KP));
+    CB_CUDA(ctx, ctx->cand_tau.ensure((size_t)nq));
+    cb_stage_begin(ctx, ST_KNN_TILE);
+    const unsigned grid = (unsigned)((nq + TM - 1) / TM);
+    k_knn_tiles<KP, TM><<<grid, KNN_THREADS, smem, ctx->stream>>>(ctx->emb_f.p, ctx->hnorm.p, n, DP, q_begin, q_end,
+                                                                   ctx->cand_idx.p, ctx->cand_tau.p);
+    CB_LAUNCH(ctx);
+    cb_stage_end(ctx, ST_KNN_TILE);
+
+    cb_stage_begin(ctx, ST_KNN_RERANK);
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 2, 0, 2 * sizeof(int), ctx->stream));
+    // fp32 FMA chain of DP terms + input/half-norm roundings, see DESIGN.md "kNN error bound"
+    const double err_coef = ldexp((double)(DP + 8), -24);
+    const int rgrid = cb_grid_for(nq, 8, ctx->num_sms * 16);
+    k_knn_rerank<KP><<<rgrid, 256, 0, ctx->stream>>>(E, lde, d, q_begin, nq, k, ctx->cand_idx.p, ctx->cand_tau.p,
+                                                     ctx->nrm2.p, ctx->maxnrm.p, err_coef, ctx->knn.p, ctx->knn_dk.p,
+                                                     ctx->fb_list.p, ctx->flag.p + 2);
+    CB_LAUNCH(ctx);
+    int h[2] = {0, 0};
+    CB_CUDA(ctx, cudaMemcpyAsync(h, ctx->flag.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->tm.knn_fallback_queries = h[0];
+    if (h[0] > 0) {
+        k_knn_exact<<<h[0], 256, 0, ctx->stream>>>(E, lde, d, n, q_begin, k, ctx->fb_list.p, ctx->knn_dk.p, ctx->knn.p,
+                                                   ctx->flag.p + 3);
+        CB_LAUNCH(ctx);
+        CB_CUDA(ctx, cudaMemcpyAsync(h, ctx->flag.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_CHECK(ctx, h[1] == 0, "cb200_knn: exact-scan fallback overflowed (more than %d ties); result not produced",
+                 KNN_FB_CAP);
+    }
+    cb_stage_end(ctx, ST_KNN_RERANK);
+    return 0;
+}
+
+static int knn_core(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int d, int k, int64_t q_begin,
+                    int64_t q_end, int32_t *index_out)
+{
+    CB_CHECK(ctx, n >= 2, "cb200_knn: need at least 2 points");
+    CB_CHECK(ctx, n < 2147483647LL, "cb200_knn: at most 2^31-2 points");
+    CB_CHECK(ctx, d >= 1 && d <= KNN_MAX_DP, "cb200_knn: 1 <= ndims <= %d required (got %d)", KNN_MAX_DP, d);
+    CB_CHECK(ctx, k >= 1 && (int64_t)k <= n - 1, "cb200_knn: need 1 <= k <= n-1 (k=%d, n=%lld)", k, (long long)n);
+    CB_CHECK(ctx, k <= 112, "cb200_knn: k <= 112 supported (got %d)", k);
+    CB_CHECK(ctx, q_begin >= 0 && q_begin < q_end && q_end <= n, "cb200_knn: bad query range");
+    const int64_t nq = q_end - q_begin;
+    const int DP = (d + 3) & ~3;
+    CB_CUDA(ctx, ctx->emb_f.ensure((size_t)n * DP));
+    CB_CUDA(ctx, ctx->hnorm.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->knn.ensure((size_t)nq * k));
+    CB_CUDA(ctx, ctx->knn_dk.ensure((size_t)nq));
+    CB_CUDA(ctx, ctx->fb_list.ensure((size_t)nq));
+
+    cb_stage_begin(ctx, ST_KNN_PREP);
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, sizeof(unsigned long long), ctx->stream));
+    k_knn_prep<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(E, lde, n, d, DP, ctx->emb_f.p, ctx->hnorm.p,
+                                                                    ctx->nrm2.p, ctx->maxnrm.p);
+    CB_LAUNCH(ctx);
+    cb_stage_end(ctx, ST_KNN_PREP);
+
+    int rc;
+    if (k <= 24)
+        rc = run_tiles_and_rerank<32, 128>(ctx, E, lde, n, d, DP, k, q_begin, q_end);
+    else if (k <= 52)
+        rc = run_tiles_and_rerank<64, 128>(ctx, E, lde, n, d, DP, k, q_begin, q_end);
+    else
+        rc = run_tiles_and_rerank<128, 64>(ctx, E, lde, n, d, DP, k, q_begin, q_end);
+    CB_TRY(rc);
+    ctx->knn_nq = nq;
+    ctx->knn_k = k;
+    ctx->knn_ntotal = n;
+    ctx->knn_qbegin = q_begin;
+    ctx->have_knn = true;
+
+    if (index_out != nullptr) {
+        cb_stage_begin(ctx, ST_D2H);
+        CB_CUDA(ctx, ctx->stage_i.ensure((size_t)nq * k));
+        k_knn_to_r_layout<<<(unsigned)((nq * k + 255) / 256), 256, 0, ctx->stream>>>(ctx->knn.p, nq, k, ctx->stage_i.p);
+        CB_LAUNCH(ctx);
+        CB_CUDA(ctx, cudaMemcpyAsync(index_out, ctx->stage_i.p, (size_t)nq * k * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        cb_stage_end(ctx, ST_D2H);
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+extern "C" int cb200_knn_device(cb200_ctx *ctx, const double *d_emb_rowmajor, int64_t n_total, int d, int k,
+                                int64_t q_begin, int64_t q_end, int32_t *index_out)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, d_emb_rowmajor != nullptr, "cb200_knn_device: NULL embedding");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return knn_core(ctx, d_emb_rowmajor, d, n_total, d, k, q_begin, q_end, index_out);
+}
+
+extern "C" int cb200_knn(cb200_ctx *ctx, const double *emb, int64_t n_total, int d, int k, int64_t q_begin,
+                         int64_t q_end, int32_t *index_out)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (emb == nullptr) {
+        CB_CHECK(ctx, ctx->have_scores, "cb200_knn: no embedding given and no PCA scores in the context");
+        CB_CHECK(ctx, n_total == ctx->N && ctx->N == ctx->N_total,
+                 "cb200_knn: resident scores cover %lld of %lld cells; gather the embedding and use cb200_knn_device",
+                 (long long)ctx->N, (long long)n_total);
+        CB_CHECK(ctx, d <= ctx->d, "cb200_knn: ndims=%d exceeds the %d resident components", d, ctx->d);
+        return knn_core(ctx, ctx->scores.p, ctx->d, n_total, d, k, q_begin, q_end, index_out);
+    }
+    CB_CHECK(ctx, n_total >= 2 && d >= 1, "cb200_knn: bad embedding shape");
+    cb_stage_begin(ctx, ST_H2D);
+    CB_CUDA(ctx, ctx->stage_d.ensure((size_t)n_total * d));
+    CB_CUDA(ctx, ctx->emb.ensure((size_t)n_total * d));
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d.p, emb, (size_t)n_total * d * sizeof(double), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    k_colmajor_to_rowmajor<<<(unsigned)((n_total * d + 255) / 256), 256, 0, ctx->stream>>>(ctx->stage_d.p, n_total, d,
+                                                                                           ctx->emb.p);
+    CB_LAUNCH(ctx);
+    cb_stage_end(ctx, ST_H2D);
+    return knn_core(ctx, ctx->emb.p, d, n_total, d, k, q_begin, q_end, index_out);
+}

@@ -1,0 +1,384 @@
+// cb200_snn.cu -- K7: shared-nearest-neighbour edge weighting.
+//
+// Replaces bluster::neighborsToSNNGraph(index, type) -> libscran build_snn_graph inside
+// bluster::makeSNNGraph(), /root/reference/R/makeGraphsAndClusters.R:83-85 (:125-127, :284).
+// Definition: L_j = [j, nn_1(j) .. nn_k(j)] with ranks 0..k;
+// cells j and h < j are joined when L_j and L_h share an element;
+//   rank    w = max(k - r/2, 1e-6),  r = min over shared s of rank_j(s) + rank_h(s)
+//   number  w = max(|L_j & L_h|, 1e-6)
+//   jaccard w = max(n / (2(k+1) - n), 1e-6),  n = |L_j & L_h|
+//
+// Kernels
+//   k_rev_count / k_rev_fill / k_rev_sort   reverse lists hosts[s] = {(cell, rank)} of all
+//                                           cells whose L contains s, sorted by cell
+//   k_snn_merge<COUNT|EMIT>                 warp per cell j: the k+1 sorted lists
+//                                           hosts[L_j[i]] are merged (lane i holds the head
+//                                           of list i); every distinct h < j is one edge.
+// Edges of cell j are emitted in libscran's order (first encounter while scanning
+// i = 0..k, list i in ascending cell order), i.e. sorted by (first list that holds h, h).
+#include "cb200_common.cuh"
+
+#define SNN_SLOTS 4  // lists per lane: supports k + 1 <= 128
+#define SNN_INF 0xffffffffu
+
+__global__ void k_index_to_rowmajor0(const int32_t *__restrict__ in, int64_t n, int k, int32_t *__restrict__ out,
+                                     int *__restrict__ flag)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx < n * k) {
+        int64_t j = idx / k;
+        int c = (int)(idx % k);
+        int v = in[j + n * (int64_t)c] - 1;
+        if (v < 0 || v >= n)
+            atomicOr(flag, 1);
+        out[idx] = v;
+    }
+}
+
+__global__ void k_rev_count(const int32_t *__restrict__ nn, int64_t n, int k, int32_t *__restrict__ rcnt)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int L = k + 1;
+    if (idx < n * L) {
+        int64_t j = idx / L;
+        int i = (int)(idx % L);
+        int s = i == 0 ? (int)j : nn[j * k + (i - 1)];
+        atomicAdd(rcnt + s, 1);
+    }
+}
+
+__global__ void k_rev_fill(const int32_t *__restrict__ nn, int64_t n, int k, const int64_t *__restrict__ rptr,
+                           int32_t *__restrict__ rcur, uint32_t *__restrict__ hosts_u)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int L = k + 1;
+    if (idx < n * L) {
+        int64_t j = idx / L;
+        int i = (int)(idx % L);
+        int s = i == 0 ? (int)j : nn[j * k + (i - 1)];
+        int pos = atomicAdd(rcur + s, 1);
+        hosts_u[rptr[s] + pos] = ((uint32_t)j << 8) | (uint32_t)i;
+    }
+}
+
+// warp per list: rank sort (entries are unique, so rank = #smaller is a permutation)
+__global__ void __launch_bounds__(256) k_rev_sort(const int64_t *__restrict__ rptr, int64_t n,
+                                                  const uint32_t *__restrict__ hosts_u, uint32_t *__restrict__ hosts)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t s = warp0; s < n; s += nwarps) {
+        const int64_t b = rptr[s];
+        const int len = (int)(rptr[s + 1] - b);
+        if (len <= 32) {
+            const uint32_t mine = lane < len ? hosts_u[b + lane] : SNN_INF;
+            int rank = 0;
+#pragma unroll
+            for (int o = 0; o < 32; ++o) {
+                const uint32_t other = __shfl_sync(0xffffffffu, mine, o);
+                rank += other < mine ? 1 : 0;
+            }
+            if (lane < len)
+                hosts[b + rank] = mine;
+        } else {
+            for (int e = lane; e < len; e += 32) {
+                const uint32_t mine = hosts_u[b + e];
+                int rank = 0;
+                for (int o = 0; o < len; ++o)
+                    rank += hosts_u[b + o] < mine ? 1 : 0;
+                hosts[b + rank] = mine;
+            }
+        }
+    }
+}
+
+// MODE 0: count edges of j (ecnt[j]) and per-list first-encounter counts (bcnt[j][i]).
+// MODE 1: emit edges at eptr[j] + (prefix of bcnt[j][.])[imin] + running index.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
+            const int64_t *__restrict__ rptr, const uint32_t *__restrict__ hosts, int32_t *__restrict__ ecnt,
+            int32_t *__restrict__ bcnt, const int64_t *__restrict__ eptr, int32_t *__restrict__ efrom,
+            int32_t *__restrict__ eto, double *__restrict__ ew)
+{
+    const int lane = threadIdx.x & 31;
+    const int L = k + 1;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t j = j_begin + warp0; j < j_end; j += nwarps) {
+        const int64_t jl = j - j_begin;
+        int64_t ptr[SNN_SLOTS], end[SNN_SLOTS];
+        uint32_t head[SNN_SLOTS];
+        int nfirst[SNN_SLOTS];  // MODE 0: edges first met in my list; MODE 1: next free slot of my bucket
+#pragma unroll
+        for (int u = 0; u < SNN_SLOTS; ++u) {
+            const int i = u * 32 + lane;
+            ptr[u] = 0;
+            end[u] = 0;
+            head[u] = SNN_INF;
+            nfirst[u] = 0;
+            if (i < L) {
+                const int s = i == 0 ? (int)j : nn[j * k + (i - 1)];
+                ptr[u] = rptr[s];
+                end[u] = rptr[s + 1];
+                if (ptr[u] < end[u]) {
+                    const uint32_t hv = hosts[ptr[u]];
+                    head[u] = ((int64_t)(hv >> 8) < j) ? hv : SNN_INF;
+                }
+            }
+        }
+        if (MODE == 1) {
+            // exclusive prefix of the bucket counts over i = 0..k, bucket i = u*32 + lane
+            int carry = 0;
+#pragma unroll
+            for (int u = 0; u < SNN_SLOTS; ++u) {
+                const int i = u * 32 + lane;
+                const int c = i < L ? bcnt[jl * L + i] : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o)
+                        inc += t;
+                }
+                nfirst[u] = carry + inc - c;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        const int64_t ebase = MODE == 1 ? eptr[jl] : 0;
+        int total = 0;
+        while (true) {
+            uint32_t hmin = SNN_INF >> 8;
+#pragma unroll
+            for (int u = 0; u < SNN_SLOTS; ++u)
+                hmin = min(hmin, head[u] >> 8);
+            const uint32_t m = __reduce_min_sync(0xffffffffu, hmin);
+            if (m == (SNN_INF >> 8))
+                break;
+            int rs = 0x7fffffff, nmatch = 0, imin = 0x7fffffff;
+#pragma unroll
+            for (int u = 0; u < SNN_SLOTS; ++u) {
+                if ((head[u] >> 8) == m && head[u] != SNN_INF) {
+                    const int i = u * 32 + lane;
+                    rs = min(rs, i + (int)(head[u] & 0xffu));
+                    imin = min(imin, i);
+                    nmatch += 1;
+                    // advance this list
+                    ptr[u] += 1;
+                    uint32_t hv = SNN_INF;
+                    if (ptr[u] < end[u]) {
+                        hv = hosts[ptr[u]];
+                        if ((int64_t)(hv >> 8) >= j)
+                            hv = SNN_INF;
+                    }
+                    head[u] = hv;
+                }
+            }
+            rs = __reduce_min_sync(0xffffffffu, rs);
+            imin = __reduce_min_sync(0xffffffffu, imin);
+            nmatch = __reduce_add_sync(0xffffffffu, nmatch);
+            // the lane/slot that owns bucket imin
+            const int own_lane = imin & 31, own_u = imin >> 5;
+            if (MODE == 0) {
+#pragma unroll
+                for (int u = 0; u < SNN_SLOTS; ++u)
+                    if (u == own_u && lane == own_lane)
+                        nfirst[u] += 1;
+                total += 1;
+            } else {
+                int slot = 0;
+#pragma unroll
+                for (int u = 0; u < SNN_SLOTS; ++u) {
+                    const int v = __shfl_sync(0xffffffffu, nfirst[u], own_lane);
+                    if (u == own_u) {
+                        slot = v;
+                        if (lane == own_lane)
+                            nfirst[u] += 1;
+                    }
+                }
+                if (lane == 0) {
+                    double wgt;
+                    if (type == CB200_SNN_RANK)
+                        wgt = (double)k - 0.5 * (double)rs;
+                    else if (type == CB200_SNN_NUMBER)
+                        wgt = (double)nmatch;
+                    else
+                        wgt = __ddiv_rn((double)nmatch, (double)(2 * L - nmatch));
+                    if (wgt < 1e-6)
+                        wgt = 1e-6;
+                    const int64_t o = ebase + slot;
+                    efrom[o] = (int32_t)(j + 1);
+                    eto[o] = (int32_t)(m + 1);
+                    ew[o] = wgt;
+                }
+            }
+        }
+        if (MODE == 0) {
+            if (lane == 0)
+                ecnt[jl] = total;
+#pragma unroll
+            for (int u = 0; u < SNN_SLOTS; ++u) {
+                const int i = u * 32 + lane;
+                if (i < L)
+                    bcnt[jl * L + i] = nfirst[u];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static int snn_core(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
+                    int64_t *n_edges)
+{
+    CB_CHECK(ctx, n >= 2 && n < (1LL << 24), "cb200_snn: 2 <= n < 2^24 cells supported (got %lld)", (long long)n);
+    CB_CHECK(ctx, k >= 1 && k + 1 <= 32 * SNN_SLOTS, "cb200_snn: 1 <= k <= %d supported (got %d)", 32 * SNN_SLOTS - 1, k);
+    CB_CHECK(ctx, type >= 0 && type <= 2, "cb200_snn: type must be 0 (rank), 1 (number) or 2 (jaccard)");
+    CB_CHECK(ctx, j_begin >= 0 && j_begin < j_end && j_end <= n, "cb200_snn: bad cell range");
+    const int L = k + 1;
+    const int64_t nj = j_end - j_begin;
+    CB_CUDA(ctx, ctx->rcnt.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->rptr.ensure((size_t)n + 1));
+    CB_CUDA(ctx, ctx->rcur.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->hosts_u.ensure((size_t)n * L));
+    CB_CUDA(ctx, ctx->hosts.ensure((size_t)n * L));
+    CB_CUDA(ctx, ctx->ecnt.ensure((size_t)nj));
+    CB_CUDA(ctx, ctx->eptr.ensure((size_t)nj + 1));
+    CB_CUDA(ctx, ctx->bcnt.ensure((size_t)nj * L));
+
+    cb_stage_begin(ctx, ST_SNN_REVLIST);
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->rcnt.p, 0, (size_t)n * sizeof(int32_t), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->rcur.p, 0, (size_t)n * sizeof(int32_t), ctx->stream));
+    const unsigned g1 = (unsigned)((n * L + 255) / 256);
+    k_rev_count<<<g1, 256, 0, ctx->stream>>>(d_nn, n, k, ctx->rcnt.p);
+    CB_LAUNCH(ctx);
+    CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->rcnt.p, n, ctx->rptr.p));
+    k_rev_fill<<<g1, 256, 0, ctx->stream>>>(d_nn, n, k, ctx->rptr.p, ctx->rcur.p, ctx->hosts_u.p);
+    CB_LAUNCH(ctx);
+    const int g2 = cb_grid_for(n, 8, ctx->num_sms * 16);
+    k_rev_sort<<<g2, 256, 0, ctx->stream>>>(ctx->rptr.p, n, ctx->hosts_u.p, ctx->hosts.p);
+    CB_LAUNCH(ctx);
+    cb_stage_end(ctx, ST_SNN_REVLIST);
+
+    cb_stage_begin(ctx, ST_SNN_EDGES);
+    const int g3 = cb_grid_for(nj, 8, ctx->num_sms * 16);
+    k_snn_merge<0><<<g3, 256, 0, ctx->stream>>>(d_nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
+                                                ctx->ecnt.p, ctx->bcnt.p, nullptr, nullptr, nullptr, nullptr);
+    CB_LAUNCH(ctx);
+    CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->ecnt.p, nj, ctx->eptr.p));
+    int64_t ne = 0;
+    CB_CUDA(ctx, cudaMemcpyAsync(&ne, ctx->eptr.p + nj, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_CUDA(ctx, ctx->efrom.ensure((size_t)ne));
+    CB_CUDA(ctx, ctx->eto.ensure((size_t)ne));
+    CB_CUDA(ctx, ctx->ew8.ensure((size_t)ne));
+    k_snn_merge<1><<<g3, 256, 0, ctx->stream>>>(d_nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
+                                                ctx->ecnt.p, ctx->bcnt.p, ctx->eptr.p, ctx->efrom.p, ctx->eto.p,
+                                                ctx->ew8.p);
+    CB_LAUNCH(ctx);
+    cb_stage_end(ctx, ST_SNN_EDGES);
+    ctx->n_edges = ne;
+    *n_edges = ne;
+    return 0;
+}
+
+static int snn_fetch(cb200_ctx *ctx, int64_t ne, int32_t **from, int32_t **to, double **weight)
+{
+    *from = nullptr;
+    *to = nullptr;
+    *weight = nullptr;
+    const size_t cnt = ne > 0 ? (size_t)ne : 1;
+    CB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(from), cnt * sizeof(int32_t)));
+    CB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(to), cnt * sizeof(int32_t)));
+    CB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(weight), cnt * sizeof(double)));
+    cb_stage_begin(ctx, ST_D2H);
+    if (ne > 0) {
+        CB_CUDA(ctx, cudaMemcpyAsync(*from, ctx->efrom.p, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        CB_CUDA(ctx, cudaMemcpyAsync(*to, ctx->eto.p, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        CB_CUDA(ctx, cudaMemcpyAsync(*weight, ctx->ew8.p, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    }
+    cb_stage_end(ctx, ST_D2H);
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int cb200_free_edges(int32_t *from, int32_t *to, double *weight)
+{
+    if (from != nullptr)
+        cudaFreeHost(from);
+    if (to != nullptr)
+        cudaFreeHost(to);
+    if (weight != nullptr)
+        cudaFreeHost(weight);
+    return 0;
+}
+
+extern "C" int cb200_snn_device(cb200_ctx *ctx, const int32_t *d_index_rowmajor0, int64_t n_total, int k, int type,
+                                int64_t j_begin, int64_t j_end, int64_t *n_edges, int32_t **from, int32_t **to,
+                                double **weight)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, d_index_rowmajor0 != nullptr && n_edges != nullptr, "cb200_snn_device: NULL argument");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CB_TRY(snn_core(ctx, d_index_rowmajor0, n_total, k, type, j_begin, j_end, n_edges));
+    if (from == nullptr || to == nullptr || weight == nullptr) {  // edges stay resident in HBM
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    return snn_fetch(ctx, *n_edges, from, to, weight);
+}
+
+extern "C" int cb200_snn(cb200_ctx *ctx, const int32_t *index, int64_t n_total, int k, int type, int64_t j_begin,
+                         int64_t j_end, int64_t *n_edges, int32_t **from, int32_t **to, double **weight)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, n_edges != nullptr && from != nullptr && to != nullptr && weight != nullptr,
+             "cb200_snn: NULL output argument");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int32_t *d_nn = nullptr;
+    if (index == nullptr) {
+        CB_CHECK(ctx, ctx->have_knn && ctx->knn_nq == n_total && ctx->knn_ntotal == n_total && ctx->knn_k == k,
+                 "cb200_snn: no index given and the resident kNN result does not cover all %lld cells with k=%d",
+                 (long long)n_total, k);
+        d_nn = ctx->knn.p;
+    } else {
+        CB_CHECK(ctx, n_total >= 2 && k >= 1, "cb200_snn: bad index shape");
+        cb_stage_begin(ctx, ST_H2D);
+        CB_CUDA(ctx, ctx->stage_i.ensure((size_t)n_total * k));
+        CB_CUDA(ctx, ctx->index0.ensure((size_t)n_total * k));
+        CB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_i.p, index, (size_t)n_total * k * sizeof(int32_t),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+        k_index_to_rowmajor0<<<(unsigned)((n_total * k + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->stage_i.p, n_total, k, ctx->index0.p, ctx->flag.p);
+        CB_LAUNCH(ctx);
+        cb_stage_end(ctx, ST_H2D);
+        int h_flag = 0;
+        CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_CHECK(ctx, h_flag == 0, "cb200_snn: neighbour index out of range [1, n]");
+        d_nn = ctx->index0.p;
+    }
+    CB_TRY(snn_core(ctx, d_nn, n_total, k, type, j_begin, j_end, n_edges));
+    return snn_fetch(ctx, *n_edges, from, to, weight);
+}
+
+extern "C" int cb200_snn_resident(cb200_ctx *ctx, int k, int type, int64_t *n_edges)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, n_edges != nullptr, "cb200_snn_resident: NULL output argument");
+    CB_CHECK(ctx, ctx->have_knn && ctx->knn_nq == ctx->knn_ntotal && ctx->knn_k == k,
+             "cb200_snn_resident: the resident kNN result does not cover all cells with k=%d", k);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CB_TRY(snn_core(ctx, ctx->knn.p, ctx->knn_ntotal, k, type, 0, ctx->knn_ntotal, n_edges));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

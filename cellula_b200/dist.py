@@ -1,0 +1,178 @@
+"""Cell-sharded execution of the hot path: one process per GPU, `torch.distributed` for the
+plumbing.
+
+Every rank holds a contiguous block of cells (dgCMatrix columns).  The arithmetic of a stage is
+rank-local (libcellula_b200.so through `CudaShard`); between stages this module performs the
+small exchanges the path needs:
+
+    size factors   all-reduce  [sum of library sizes, #cells]           (2 doubles)
+    gene stats     all-reduce  [sum y, sum y^2] per gene                (2 G doubles)
+    PCA            all-reduce  H x H cross-product                      (H^2 doubles)
+                   all-gather  scores (N x d doubles)
+    kNN            all-gather  neighbour index (N x k int32)
+    SNN            none: every rank emits the edges of its own cells j (ascending j), so the
+                   concatenation in rank order is the single-GPU edge list.
+
+`ShardedPipeline` only talks to a *shard backend* (the methods of `CudaShard`) and to
+`torch.distributed`, so the same driver runs on CPU with the gloo backend and a test double as
+backend (tests/test_dist_gloo.py) -- that is how the N>1 host logic is covered without GPUs.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import trendvar
+
+
+def shard_bounds(n_total: int, world: int):
+    """Contiguous, as-equal-as-possible split of [0, n_total) into `world` blocks."""
+    base, rem = divmod(int(n_total), int(world))
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < rem else 0))
+    return bounds
+
+
+def slice_csc(colptr, rowidx, x, c0, c1):
+    """Columns [c0, c1) of a CSC matrix with the column pointers rebased to 0."""
+    colptr = np.asarray(colptr)
+    lo, hi = int(colptr[c0]), int(colptr[c1])
+    return (colptr[c0:c1 + 1] - lo).astype(np.int64), rowidx[lo:hi], x[lo:hi]
+
+
+class _DevView:
+    """Zero-copy torch view of a device buffer owned by the library."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False),
+                                             version=3, strides=None)
+
+
+def device_tensor(ptr, shape, dtype, device):
+    typestr = {torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_DevView(ptr, shape, typestr), device=device)
+
+
+class CudaShard:
+    """Shard backend over one cb200 context (one GPU)."""
+
+    def __init__(self, ctx, device):
+        self.ctx = ctx
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+
+    def _view(self, which, shape, dtype):
+        ptr, _ = self.ctx.device_ptr(which)
+        return device_tensor(ptr, shape, dtype, self.device)
+
+    # K1
+    def libsize_partial(self, sf_in=None):
+        self.ctx.size_factors_local(sf_in)
+        return self._view("libsize_partial", (2,), torch.float64)
+
+    def finish_size_factors(self, total, n_total, want=True):
+        return self.ctx.size_factors_finish(total, n_total, want=want)
+
+    # K2 + K3
+    def gene_acc(self):
+        self.ctx.lognorm_genestats_local()
+        return self._view("gene_acc", (2 * self.ctx.n_genes,), torch.float64)
+
+    def finish_genestats(self):
+        return self.ctx.genestats_finish(want=True)
+
+    def logcounts(self, out=None):
+        return self.ctx.fetch_logcounts(out)
+
+    # K5
+    def gram(self, hvg_idx):
+        self.ctx.pca_gram_local(hvg_idx)
+        h = len(hvg_idx)
+        return self._view("gram", (h * h,), torch.float64)
+
+    def finish_pca(self, d, n_hvg, want_scores=True):
+        res = self.ctx.pca_finish(d, n_hvg, want_scores=want_scores)
+        res["scores_dev"] = self._view("scores", (self.ctx.n_cells, d), torch.float64)
+        return res
+
+    # K6
+    def knn(self, emb_full, k, q_begin, q_end, want=False):
+        n, d = emb_full.shape
+        self.ctx.knn_device(emb_full.data_ptr(), n, d, k, q_begin, q_end, want=want)
+        return self._view("knn", (q_end - q_begin, k), torch.int32)
+
+    # K7
+    def snn(self, knn_full, snn_type, j_begin, j_end, fetch=True):
+        n, k = knn_full.shape
+        return self.ctx.snn_device(knn_full.data_ptr(), n, k, snn_type, j_begin, j_end, fetch=fetch)
+
+
+class ShardedPipeline:
+    """counts shard -> SNN edges of the shard's cells, with the exchanges listed above."""
+
+    def __init__(self, shard, n_total, group=None):
+        self.shard = shard
+        self.n_total = int(n_total)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.bounds = shard_bounds(self.n_total, self.world)
+        self.c0, self.c1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+
+    # -- collectives ---------------------------------------------------------------
+    def _allreduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def _allgather_rows(self, local):
+        """Concatenate row blocks of unequal height in rank order."""
+        if self.world == 1:
+            return local
+        sizes = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
+        mx = max(sizes)
+        pad = local
+        if local.shape[0] < mx:
+            pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            pad[:local.shape[0]] = local
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad.contiguous(), group=self.group)
+        return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0).contiguous()
+
+    # -- stages ----------------------------------------------------------------------
+    def size_factors(self, sf_in=None, want=True):
+        part = self._allreduce(self.shard.libsize_partial(sf_in))
+        tot = part.cpu().numpy()
+        return self.shard.finish_size_factors(float(tot[0]), int(round(float(tot[1]))), want=want)
+
+    def gene_stats(self):
+        self._allreduce(self.shard.gene_acc())
+        return self.shard.finish_genestats()
+
+    def pca(self, hvg_idx, d, want_scores=True):
+        self._allreduce(self.shard.gram(hvg_idx))
+        res = self.shard.finish_pca(d, len(hvg_idx), want_scores=want_scores)
+        res["scores_full_dev"] = self._allgather_rows(res["scores_dev"])
+        return res
+
+    def knn(self, emb_full, k):
+        local = self.shard.knn(emb_full, k, self.c0, self.c1)
+        return self._allgather_rows(local)
+
+    def snn(self, knn_full, snn_type, fetch=True):
+        if fetch:
+            return self.shard.snn(knn_full, snn_type, self.c0, self.c1)
+        return self.shard.snn(knn_full, snn_type, self.c0, self.c1, fetch=False)
+
+    def run(self, ndims=50, hvg_ntop=2000, neighbors=20, snn_type="rank", sf_in=None, want_host=True):
+        """The whole path for this rank's shard.  Returns host results of the shard."""
+        sf = self.size_factors(sf_in, want=want_host)
+        mean, var = self.gene_stats()
+        stats = trendvar.model_gene_var(mean, var)          # replicated host step (R: scran::fitTrendVar)
+        hvgs = trendvar.get_top_hvgs(stats, hvg_ntop)
+        pca = self.pca(hvgs, ndims, want_scores=want_host)
+        knn_full = self.knn(pca["scores_full_dev"], neighbors)
+        edges = self.snn(knn_full, snn_type, fetch=want_host)  # (from, to, w), or the count if resident
+        return dict(sf=sf, mean=mean, var=var, stats=stats, hvgs=hvgs, pca=pca, knn_full=knn_full,
+                    edges=edges)

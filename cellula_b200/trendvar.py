@@ -1,0 +1,226 @@
+"""Host-side mean-variance trend and HVG selection (rows a5/a6 of SURVEY.md section 8).
+
+In the R product these steps stay *unchanged R calls* on the GPU-computed per-gene means and
+variances (`scran::fitTrendVar`, `scran::getTopHVGs`; /root/reference/R/doNormAndReduce.R:88-90,
+r-pkg/R/doNormAndReduce.R).  The Python mirror has no R, so this module supplies the same
+decomposition on the host: G-sized work (~30k points), never on the device.
+
+model_gene_var(mean, var) -> dict(mean, total, tech, bio, p_value, FDR)   (modelGeneVar columns)
+get_top_hvgs(stats, n)    -> 0-based row indices ordered by decreasing bio, bio > 0 only
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+from scipy.special import ndtr
+
+
+def _density_weights(m):
+    """1 / kernel density of the means (Gaussian, bw.nrd0, 512-point grid), mean-scaled."""
+    n = m.size
+    sd = m.std(ddof=1)
+    iqr = np.subtract(*np.percentile(m, [75, 25]))
+    lo = min(sd, iqr / 1.34) or sd or abs(m[0]) or 1.0
+    bw = 0.9 * lo * n ** -0.2
+    grid = np.linspace(m.min() - 3 * bw, m.max() + 3 * bw, 512)
+    dens = np.zeros(512)
+    step = max(1, 4_000_000 // 512)
+    for a in range(0, n, step):
+        z = (grid[:, None] - m[None, a:a + step]) / bw
+        dens += np.exp(-0.5 * z * z).sum(axis=1)
+    dens /= n * bw * math.sqrt(2 * math.pi)
+    w = 1.0 / np.interp(m, grid, dens)
+    return w / w.mean()
+
+
+def _start_values(v, m):
+    order = np.argsort(m, kind="stable")
+    keep = order[:max(1, int(min(100, 0.1 * v.size)))]
+    grad = float(m[keep] @ v[keep]) / float(m[keep] @ m[keep])
+    bgrid = 2.0 ** np.linspace(-5, 5, 10)
+    ngrid = 2.0 ** np.linspace(0, 10, 10)
+    with np.errstate(over="ignore"):
+        mp = m[None, :] ** ngrid[:, None]                                   # [n-grid, genes]
+        pred = grad * bgrid[None, :, None] * m[None, None, :] / (mp[:, None, :] + bgrid[None, :, None])
+        rss = ((v[None, None, :] - pred) ** 2).sum(axis=2)                   # [n-grid, b-grid]
+    i_n, i_b = np.unravel_index(np.argmin(rss), rss.shape)  # first minimum, b fastest: expand.grid order
+    return bgrid[i_b] * grad, bgrid[i_b], ngrid[i_n]
+
+
+def _fit_parametric(v, m, w, tol=1e-9, maxiter=500):
+    """Weighted least squares of v ~ exp(A) m / (m^(1+exp(N)) + exp(B)), damped Gauss-Newton."""
+    a0, b0, n0 = _start_values(v, m)
+    th = np.array([math.log(a0), math.log(b0), math.log(max(n0 - 1.0, 1e-8))])
+    logm = np.log(m)
+
+    def evaluate(t):
+        ea, eb, en = np.exp(t)
+        p = np.exp((1.0 + en) * logm)
+        den = p + eb
+        f = ea * m / den
+        return f, np.column_stack((f, -f * eb / den, -f * p * logm * en / den))
+
+    f, jac = evaluate(th)
+    rss = float(w @ (v - f) ** 2)
+    damp = 1e-3
+    sw = np.sqrt(w)
+    for _ in range(maxiter):
+        r = sw * (v - f)
+        jw = jac * sw[:, None]
+        q, _ = np.linalg.qr(jw)
+        proj = q.T @ r
+        num = float(proj @ proj)
+        if math.sqrt(num / max(float(r @ r) - num, 1e-300)) < tol:
+            break
+        a = jw.T @ jw
+        g = jw.T @ r
+        for _try in range(40):
+            step = np.linalg.solve(a + damp * np.diag(np.diag(a)), g)
+            with np.errstate(over="ignore", invalid="ignore"):
+                f2, jac2 = evaluate(th + step)
+                rss2 = float(w @ (v - f2) ** 2)
+            if np.isfinite(rss2) and rss2 < rss:
+                th, f, jac, rss = th + step, f2, jac2, rss2
+                damp = max(damp / 10.0, 1e-12)
+                break
+            damp *= 10.0
+        else:
+            break
+    return np.exp(th)
+
+
+def _wmedian(x, w):
+    o = np.argsort(x, kind="stable")
+    cw = np.cumsum(w[o])
+    half = 0.5 * cw[-1]
+    i = int(np.searchsorted(cw, half, side="left"))
+    if i + 1 < x.size and cw[i] == half:
+        return 0.5 * (x[o[i]] + x[o[i + 1]])
+    return x[o[i]]
+
+
+def _weighted_lowess(x, y, w, span=0.3, iterations=4, npts=200):
+    """limma::weightedLowess: local linear fits at ~npts seeds over the sorted x, window =
+    nearest points holding span * total weight, tricube kernel, bisquare robustness."""
+    o = np.argsort(x, kind="stable")
+    xs, ys, ws = x[o], y[o], w[o]
+    n = xs.size
+    delta = (xs[-1] - xs[0]) / npts
+    seeds = [0]
+    for i in range(1, n - 1):
+        if xs[i] - xs[seeds[-1]] > delta:
+            seeds.append(i)
+    if n > 1:
+        seeds.append(n - 1)
+    target = span * ws.sum()
+    windows = []
+    for s in seeds:
+        lo = hi = s
+        acc = ws[s]
+        while acc < target and (lo > 0 or hi < n - 1):
+            go_left = hi == n - 1 or (lo > 0 and xs[s] - xs[lo - 1] < xs[hi + 1] - xs[s])
+            if go_left:
+                lo -= 1
+                acc += ws[lo]
+            else:
+                hi += 1
+                acc += ws[hi]
+        dist = max(xs[s] - xs[lo], xs[hi] - xs[s])
+        while lo > 0 and xs[s] - xs[lo - 1] <= dist:
+            lo -= 1
+        while hi < n - 1 and xs[hi + 1] - xs[s] <= dist:
+            hi += 1
+        windows.append((lo, hi + 1, dist))
+    rob = np.ones(n)
+    fitted = ys.copy()
+    sx = xs[seeds]
+    for it in range(iterations):
+        sv = np.empty(len(seeds))
+        for q, (s, (lo, hi, dist)) in enumerate(zip(seeds, windows)):
+            xx, yy = xs[lo:hi], ys[lo:hi]
+            kw = ws[lo:hi] * rob[lo:hi]
+            if dist > 0:
+                u = np.abs(xx - xs[s]) / dist
+                kw = kw * np.where(u < 1, (1 - u ** 3) ** 3, 0.0)
+            tw = kw.sum()
+            if tw <= 0:
+                sv[q] = ys[s]
+                continue
+            xm, ym = (kw @ xx) / tw, (kw @ yy) / tw
+            sxx = kw @ (xx - xm) ** 2
+            if sxx < 1e-12 * max(dist * dist, 1e-300) * tw:
+                sv[q] = ym
+            else:
+                sv[q] = ym + (kw @ ((xx - xm) * (yy - ym))) / sxx * (xs[s] - xm)
+        fitted = np.interp(xs, sx, sv)
+        if it == iterations - 1:
+            break
+        res = np.abs(ys - fitted)
+        cmad = 6.0 * _wmedian(res, ws)
+        if cmad <= 1e-12 * max(res.mean(), 1e-300):
+            break
+        rob = np.where(res < cmad, (1 - (res / cmad) ** 2) ** 2, 0.0)
+    out = np.empty(n)
+    out[o] = fitted
+    return out
+
+
+def fit_trend_var(means, variances, min_mean=0.1):
+    """Returns (trend_function, std_dev) like scran::fitTrendVar(means, vars)."""
+    means = np.asarray(means, dtype=np.float64)
+    variances = np.asarray(variances, dtype=np.float64)
+    ok = np.isfinite(variances) & (variances > 1e-8) & (means >= min_mean)
+    v, m = variances[ok], means[ok]
+    if v.size <= 3:
+        raise ValueError("need at least 4 points for non-linear curve fitting")
+    w = _density_weights(m)
+    ea, eb, en = _fit_parametric(v, m, w)
+
+    def parametric(x):
+        return ea * x / (x ** (1.0 + en) + eb)
+    resid = np.log(v) - np.log(parametric(m))
+    smooth = _weighted_lowess(m, resid, w)
+    ux, inv = np.unique(m, return_inverse=True)
+    uy = np.bincount(inv, weights=smooth) / np.bincount(inv)
+
+    def unscaled(x):
+        return np.exp(np.interp(x, ux, uy)) * parametric(x)
+    left = v / unscaled(m)
+    med = _wmedian(left, w)
+    std_dev = float(_wmedian(np.abs(left / med - 1.0), w) * 1.4826)
+
+    def trend(x):
+        x = np.asarray(x, dtype=np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            t = unscaled(np.maximum(x, 0.0)) * med
+        return np.where(x > 0, t, 0.0)
+    return trend, std_dev
+
+
+def model_gene_var(means, variances):
+    """scran::modelGeneVar's DataFrame columns from per-gene mean / total variance."""
+    means = np.asarray(means, dtype=np.float64)
+    variances = np.asarray(variances, dtype=np.float64)
+    trend, std_dev = fit_trend_var(means, variances)
+    tech = trend(means)
+    bio = variances - tech
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = variances / tech
+    p = np.where(np.isfinite(ratio), ndtr(-(ratio - 1.0) / std_dev), np.nan)
+    fdr = np.full(p.shape, np.nan)
+    valid = np.isfinite(p)
+    if valid.any():
+        pv = p[valid]
+        o = np.argsort(pv, kind="stable")[::-1]
+        adj = np.minimum.accumulate(pv[o] * pv.size / np.arange(pv.size, 0, -1))
+        tmp = np.empty(pv.size)
+        tmp[o] = np.minimum(adj, 1.0)
+        fdr[valid] = tmp
+    return dict(mean=means, total=variances, tech=tech, bio=bio, p_value=p, FDR=fdr)
+
+
+def get_top_hvgs(stats, n):
+    bio = np.asarray(stats["bio"] if isinstance(stats, dict) else stats)
+    keep = np.flatnonzero(np.isfinite(bio) & (bio > 0))
+    return keep[np.argsort(-bio[keep], kind="stable")][:n].astype(np.int32)

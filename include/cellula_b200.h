@@ -1,0 +1,191 @@
+/*
+ * cellula_b200.h -- plain C ABI of libcellula_b200.so
+ *
+ * B200-native (sm_100a) implementation of cellula's data-parallel hot path:
+ *     doNormAndReduce()        /root/reference/R/doNormAndReduce.R:37-109
+ *     makeGraphsAndClusters()  /root/reference/R/makeGraphsAndClusters.R:46-157
+ * from raw counts to the SNN edge list.  The reference is pure R;
+ * the arithmetic it reaches lives in Bioconductor packages.  Each entry point below names
+ * the reference call site (file:line) and the upstream routine it replaces.  The R side
+ * binds these through a .Call shim that only unpacks SEXPs (r-pkg/src/rshim.c,
+ * INTEGRATION.md); the Python mirror binds them through ctypes (cellula_b200/_lib.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is available
+ *     from cb200_last_error(ctx).  Nothing throws or longjmps across this boundary.
+ *   - host input buffers are owned by the caller, read-only, never retained after return.
+ *   - "nullable" output pointers may be NULL when the caller does not need that result
+ *     on the host (it stays resident in HBM for the following stages).
+ *   - one cb200_ctx drives one GPU.  A multi-GPU job is one process (or thread) per GPU,
+ *     each with its own context holding a contiguous shard of cells; the *_local /
+ *     *_finish pairs expose the points where the caller reduces partial results
+ *     (NCCL all-reduce / all-gather on the device pointers from cb200_device_ptr).
+ *     The unsuffixed forms are the single-GPU composition local -> finish.
+ *   - all matrices crossing the boundary use R's layouts: dgCMatrix slots for counts
+ *     (0-based row indices, column pointers), column-major dense matrices, 1-based
+ *     neighbour indices.
+ */
+#ifndef CELLULA_B200_H
+#define CELLULA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cb200_ctx cb200_ctx;
+
+/* SNN weighting schemes: bluster::makeSNNGraph(type=) as passed by
+ * R/makeGraphsAndClusters.R:83-85 (weighting_scheme). */
+enum { CB200_SNN_RANK = 0, CB200_SNN_NUMBER = 1, CB200_SNN_JACCARD = 2 };
+
+/* device buffers a caller may reduce / gather across GPUs (cb200_device_ptr) */
+enum {
+    CB200_BUF_LIBSIZE_PARTIAL = 0, /* double[2]: local sum of library sizes, local #cells    */
+    CB200_BUF_GENE_ACC = 1,        /* double[2*G]: per-gene sum(y), sum(y^2) over local cells */
+    CB200_BUF_GRAM = 2,            /* double[H*H]: local X^T X of the HVG log-counts (upper)  */
+    CB200_BUF_SCORES = 3,          /* double[n_local*d] row-major: local PCA scores           */
+    CB200_BUF_KNN = 4,             /* int32[n_query*k] row-major, 0-based global indices      */
+    CB200_BUF_SIZE_FACTORS = 5,    /* double[n_local]                                         */
+    CB200_BUF_LOGCOUNTS = 6,       /* double[nnz_local]                                       */
+    CB200_BUF_COUNT_ = 7
+};
+
+/* per-stage device times of the most recent call of each stage, milliseconds (CUDA events
+ * on the context's stream), plus launch counts; see cb200_stage_timings */
+typedef struct cb200_timing {
+    double h2d_ms;          /* cb200_load_csc copies                                  */
+    double colsum_ms;       /* K1  k_colsum_csc                                       */
+    double lognorm_ms;      /* K2+K3 k_lognorm_genestats                              */
+    double hvg_extract_ms;  /* K5a HVG sub-matrix extraction                          */
+    double gram_ms;         /* K5b Gram / cross-product                               */
+    double eig_ms;          /* K5c subspace iteration on the H x H covariance         */
+    double project_ms;      /* K5d scores = Xc V                                      */
+    double knn_prep_ms;     /* K6a embedding conversion, norms                        */
+    double knn_tile_ms;     /* K6b distance tiles + fused top-k' selection            */
+    double knn_rerank_ms;   /* K6c exact fp64 re-rank + margin check (+ fallback)     */
+    double snn_revlist_ms;  /* K7a reverse neighbour lists                            */
+    double snn_edges_ms;    /* K7b sorted-intersection edge weighting                 */
+    double d2h_ms;          /* result copies of the last stage that made any          */
+    int64_t kernel_launches; /* kernels of this library launched since cb200_reset_timings */
+    int64_t knn_fallback_queries; /* queries answered by the exact fp64 fallback      */
+    int64_t eig_iterations;
+} cb200_timing;
+
+/* ---- context ------------------------------------------------------------------------ */
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t to run on (e.g.
+ * the caller's current stream so that its own events bracket the work) or NULL to let the
+ * library create one. */
+int cb200_init(int device, void *stream, cb200_ctx **out);
+int cb200_free(cb200_ctx *ctx);
+/* Message of the last failure on this context ("" if none); ctx == NULL returns the
+ * message of the last failed cb200_init. */
+const char *cb200_last_error(const cb200_ctx *ctx);
+/* Library/ABI version and the -gencode it was built for, e.g. "cellula_b200 0.1 sm_100a". */
+const char *cb200_version(void);
+int cb200_synchronize(cb200_ctx *ctx);
+int cb200_stage_timings(cb200_ctx *ctx, cb200_timing *out);
+int cb200_reset_timings(cb200_ctx *ctx);
+/* Device pointer and size in bytes of one of the CB200_BUF_* buffers (valid until the next
+ * stage that reallocates it). */
+int cb200_device_ptr(cb200_ctx *ctx, int which, void **ptr, int64_t *bytes);
+
+/* ---- a1: counts(sce), a dgCMatrix (genes x cells, CSC) -------------------------------
+ * Replaces: the assay every step of R/doNormAndReduce.R:64-97 reads.
+ * colptr is int64[n_cells+1]; cb200_load_csc_i32 takes dgCMatrix's own int32 `p` slot.
+ * rowidx int32[nnz] 0-based gene index, sorted within a column; values double[nnz].
+ * cell_offset / n_cells_total describe the shard: this context holds global cells
+ * [cell_offset, cell_offset + n_cells); single GPU: 0 and n_cells. */
+int cb200_load_csc(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, const int64_t *colptr,
+                   const int32_t *rowidx, const double *values, int64_t cell_offset,
+                   int64_t n_cells_total);
+int cb200_load_csc_i32(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, const int32_t *colptr,
+                       const int32_t *rowidx, const double *values, int64_t cell_offset,
+                       int64_t n_cells_total);
+
+/* ---- a2: size factors ----------------------------------------------------------------
+ * Replaces: scuttle::logNormCounts() -> librarySizeFactors()/sizeFactors() centring,
+ * R/doNormAndReduce.R:78.  sf = ls / mean(ls); a caller-supplied vector (deconvolution
+ * factors from R/doNormAndReduce.R:64-71) is only re-centred.  Fails with
+ * "size factors should be positive" like scuttle. */
+int cb200_size_factors_local(cb200_ctx *ctx, const double *sf_in /* nullable, local cells */);
+int cb200_size_factors_finish(cb200_ctx *ctx, double total, int64_t n_cells_total,
+                              double *sf_out /* nullable, local cells */);
+int cb200_size_factors(cb200_ctx *ctx, const double *sf_in, double *sf_out);
+
+/* ---- a3 + a4: logcounts and per-gene mean / variance ---------------------------------
+ * Replaces: scuttle::normalizeCounts(log=TRUE, pseudo.count=1) (R/doNormAndReduce.R:78)
+ * and scran:::.compute_mean_var inside modelGeneVar() (R/doNormAndReduce.R:88), fused:
+ * logx = log1p(x / sf[col]) / log(2) on the stored non-zeros; mean/var over all cells
+ * with implicit zeros, var with n-1. */
+int cb200_lognorm_genestats_local(cb200_ctx *ctx);
+int cb200_genestats_finish(cb200_ctx *ctx, double *gene_mean /* nullable [G] */,
+                           double *gene_var /* nullable [G] */);
+int cb200_fetch_logcounts(cb200_ctx *ctx, double *logx_out /* [nnz_local] */);
+int cb200_lognorm_genestats(cb200_ctx *ctx, double *logx_out /* nullable */, double *gene_mean,
+                            double *gene_var);
+
+/* ---- a7: PCA on the HVG subset -------------------------------------------------------
+ * Replaces: scater::runPCA(sce, subset_row=hvgs, exprs_values="logcounts",
+ * ncomponents=ndims), R/doNormAndReduce.R:94-97 -> BiocSingular::runPCA.
+ * hvg_idx: 0-based gene rows in getTopHVGs order.  scores column-major n_local x d (U D),
+ * rotation column-major H x d (V), var_explained[d] = D^2/(N-1), total_var = sum of the
+ * HVG column variances (percentVar = 100 var_explained / total_var). */
+int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int n_hvg);
+int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores /* nullable */,
+                     double *rotation /* nullable */, double *var_explained /* nullable */,
+                     double *total_var /* nullable */);
+int cb200_pca(cb200_ctx *ctx, const int32_t *hvg_idx, int n_hvg, int d, double *scores,
+              double *rotation, double *var_explained, double *total_var);
+
+/* ---- a9: exact kNN -------------------------------------------------------------------
+ * Replaces: BiocNeighbors::findKNN(x, k, BNPARAM=KmknnParam(), get.distance=FALSE) inside
+ * bluster::makeSNNGraph(), R/makeGraphsAndClusters.R:83-85 (:125-127, :284).
+ * emb: host, column-major n_total x d (the `space` matrix, :80-81); NULL = use the scores
+ * left in HBM by cb200_pca_finish (single GPU only).  Queries are the global rows
+ * [q_begin, q_end); index_out is column-major (q_end-q_begin) x k, 1-based, each row
+ * ordered by (distance, index) with distance = sqrt(sum (a-b)^2) in fp64, self excluded.
+ * The result is exact: tensor/fp32 distances only nominate candidates, an fp64 re-rank
+ * with a proven error margin (or an fp64 full scan) decides. */
+int cb200_knn(cb200_ctx *ctx, const double *emb, int64_t n_total, int d, int k, int64_t q_begin,
+              int64_t q_end, int32_t *index_out /* nullable */);
+/* Same with the full embedding already in HBM: row-major n_total x d doubles. */
+int cb200_knn_device(cb200_ctx *ctx, const double *d_emb_rowmajor, int64_t n_total, int d, int k,
+                     int64_t q_begin, int64_t q_end, int32_t *index_out /* nullable */);
+
+/* ---- a10: SNN edges ------------------------------------------------------------------
+ * Replaces: bluster::neighborsToSNNGraph(index, type) -> libscran build_snn_graph inside
+ * makeSNNGraph(), R/makeGraphsAndClusters.R:83-85.
+ * index: host, column-major n_total x k, 1-based (findKNN()$index); NULL = use the result
+ * left in HBM by cb200_knn (single GPU, all queries).  Edges are produced for the cells
+ * j in [j_begin, j_end) as (from = j+1, to = h+1, h < j), grouped by j ascending, within
+ * a group ordered as libscran emits them (first encounter).  The arrays are allocated by
+ * the library (pinned host memory); release with cb200_free_edges. */
+int cb200_snn(cb200_ctx *ctx, const int32_t *index, int64_t n_total, int k, int type,
+              int64_t j_begin, int64_t j_end, int64_t *n_edges, int32_t **from, int32_t **to,
+              double **weight);
+/* Same with the full 0-based row-major n_total x k index already in HBM.  from/to/weight may
+ * be NULL: the edges then stay resident in HBM and only the count is returned. */
+int cb200_snn_device(cb200_ctx *ctx, const int32_t *d_index_rowmajor0, int64_t n_total, int k,
+                     int type, int64_t j_begin, int64_t j_end, int64_t *n_edges, int32_t **from,
+                     int32_t **to, double **weight);
+/* Device-only variant: edges stay in HBM (bench "value" leg); returns the count. */
+int cb200_snn_resident(cb200_ctx *ctx, int k, int type, int64_t *n_edges);
+int cb200_free_edges(int32_t *from, int32_t *to, double *weight);
+
+/* ---- synthetic input (bench / test infrastructure, not part of the reference path) ---
+ * Fills the context with a deterministic negative-binomial count matrix with planted
+ * low-rank structure generated on the device, as if by cb200_load_csc.
+ * cb200_export_csc copies it to host buffers so that the same data can be pushed back
+ * through the host-facing calls and handed to the oracle. */
+int cb200_synth_counts(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, double nnz_per_cell,
+                       uint64_t seed, int64_t cell_offset, int64_t n_cells_total,
+                       int64_t *nnz_out);
+int cb200_export_csc(cb200_ctx *ctx, int64_t *colptr, int32_t *rowidx, double *values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLULA_B200_H */

@@ -1,0 +1,580 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+CPU (numpy fp64 + plain C) restatement of the upstream routines that cellula's
+``doNormAndReduce()`` (/root/reference/R/doNormAndReduce.R:57-97) and
+``makeGraphsAndClusters()`` (/root/reference/R/makeGraphsAndClusters.R:80-85) call.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` leg may import this module.  Nothing under ``cellula_b200/``
+imports it; the product path fails loudly without its CUDA library instead.
+
+PARITY UNPINNED.  All arithmetic of the path lives in third-party R/Bioconductor
+packages that are neither vendored in /root/reference nor version-pinned
+(DESCRIPTION:14-50): scuttle (logNormCounts), scran (modelGeneVar, fitTrendVar,
+getTopHVGs), scater/BiocSingular (runPCA), BiocNeighbors/knncolle (findKNN),
+bluster/libscran (makeSNNGraph).  Estimated era Bioconductor 3.20.  The reference holds
+no tests, golden vectors or fixtures and R cannot run in the build
+image, so every function below follows the packages' *published* definitions as
+collected in SURVEY.md 8c.1 and is pinned only by the hand-derived known-answer vectors
+of SURVEY.md 8c.3 (tests/test_oracle_kat.py, tests/golden/kat_*.json).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build_c_oracle(force: bool = False) -> str:
+    """Compile oracle/knn_snn.c -> oracle/liboracle.so (gcc, no FMA contraction)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "knn_snn.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        base = ["/usr/bin/gcc", "-O2", "-fPIC", "-ffp-contract=off", "-std=c11", "-shared",
+                "-o", so, src, "-lm"]
+        try:
+            subprocess.run(base[:5] + ["-fopenmp"] + base[5:], check=True, capture_output=True)
+        except (subprocess.CalledProcessError, FileNotFoundError):
+            subprocess.run(["gcc"] + base[1:], check=True, capture_output=True)
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = ctypes.CDLL(build_c_oracle())
+        i64, i32p, f64p = ctypes.c_int64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)
+        lib.oracle_knn.argtypes = [f64p, i64, ctypes.c_int, ctypes.c_int, i32p, f64p]
+        lib.oracle_knn.restype = ctypes.c_int
+        lib.oracle_snn.argtypes = [i32p, i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(i64),
+                                   ctypes.POINTER(i32p), ctypes.POINTER(i32p), ctypes.POINTER(f64p)]
+        lib.oracle_snn.restype = ctypes.c_int
+        lib.oracle_free.argtypes = [ctypes.c_void_p]
+        lib.oracle_lognorm_genestats.argtypes = [i64, i64, ctypes.POINTER(i64), i32p, f64p, f64p, f64p,
+                                                 f64p, f64p]
+        lib.oracle_lognorm_genestats.restype = ctypes.c_int
+        _LIB = lib
+    return _LIB
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+# ---------------------------------------------------------------------------------------
+# K1/K2: scuttle::logNormCounts  (R/doNormAndReduce.R:78)
+# ---------------------------------------------------------------------------------------
+def library_size_factors(colptr, x, size_factors_in=None):
+    """sf = colSums(counts) / mean(colSums(counts)); a user vector is only re-centred.
+
+    Errors like scuttle does when any factor is non-positive or NA."""
+    colptr = np.asarray(colptr, dtype=np.int64)
+    n = colptr.size - 1
+    if size_factors_in is None:
+        x = np.asarray(x, dtype=np.float64)
+        ls = np.zeros(n)
+        nz = np.diff(colptr) > 0
+        ls[nz] = np.add.reduceat(x, colptr[:-1][nz]) if x.size else 0.0
+        # reduceat on empty trailing segments is handled by the nz mask above
+    else:
+        ls = np.asarray(size_factors_in, dtype=np.float64).copy()
+    sf = ls / ls.mean()
+    if not np.all(np.isfinite(sf)) or np.any(sf <= 0):
+        raise ValueError("size factors should be positive")
+    return sf
+
+
+def log_norm_counts(colptr, x, sf):
+    """logcounts@x = log1p(x / sf[col]) / log(2) on the stored non-zeros (same i/p)."""
+    colptr = np.asarray(colptr, dtype=np.int64)
+    col_of = np.repeat(np.arange(colptr.size - 1), np.diff(colptr))
+    return np.log1p(np.asarray(x, dtype=np.float64) / sf[col_of]) / np.log(2.0)
+
+
+# ---------------------------------------------------------------------------------------
+# K3: scran:::.compute_mean_var  (R/doNormAndReduce.R:88)
+# ---------------------------------------------------------------------------------------
+def gene_mean_var(n_genes, n_cells, rowidx, y):
+    """Per-gene mean and (n-1)-variance over ALL cells, implicit zeros included.
+
+    Two-pass form (exact mean first), mathematically what upstream's Welford computes."""
+    rowidx = np.asarray(rowidx, dtype=np.int64)
+    s = np.bincount(rowidx, weights=y, minlength=n_genes)
+    nnz = np.bincount(rowidx, minlength=n_genes).astype(np.float64)
+    mean = s / n_cells
+    dev = y - mean[rowidx]
+    ss = np.bincount(rowidx, weights=dev * dev, minlength=n_genes)
+    ss += (n_cells - nnz) * mean * mean
+    var = ss / (n_cells - 1) if n_cells > 1 else np.full(n_genes, np.nan)
+    return mean, var
+
+
+def c_lognorm_genestats(n_genes, colptr, rowidx, x, want_logx=True):
+    """Same three steps through oracle/knn_snn.c (single thread, Welford in cell order)."""
+    colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+    rowidx = np.ascontiguousarray(rowidx, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = colptr.size - 1
+    sf = np.empty(n)
+    logx = np.empty(x.size) if want_logx else None
+    mean = np.empty(n_genes)
+    var = np.empty(n_genes)
+    rc = _lib().oracle_lognorm_genestats(
+        n_genes, n, _p(colptr, ctypes.c_int64), _p(rowidx, ctypes.c_int32), _p(x, ctypes.c_double),
+        _p(sf, ctypes.c_double), _p(logx, ctypes.c_double) if want_logx else None,
+        _p(mean, ctypes.c_double), _p(var, ctypes.c_double))
+    if rc == -4:
+        raise ValueError("size factors should be positive")
+    if rc != 0:
+        raise RuntimeError(f"oracle_lognorm_genestats failed: {rc}")
+    return sf, logx, mean, var
+
+
+# ---------------------------------------------------------------------------------------
+# K4: scran::fitTrendVar + modelGeneVar decomposition + getTopHVGs
+#     (R/doNormAndReduce.R:88-90).  Approximate by
+#     construction: stats::nls / limma::weightedLowess / stats::density are restated from
+#     their documentation.  In the R product these stay unchanged R calls.
+# ---------------------------------------------------------------------------------------
+def _bw_nrd0(x):
+    hi = np.std(x, ddof=1)
+    q75, q25 = np.percentile(x, [75, 25])
+    lo = min(hi, (q75 - q25) / 1.34)
+    if lo == 0:
+        lo = hi or abs(x[0]) or 1.0
+    return 0.9 * lo * len(x) ** (-0.2)
+
+
+def _inverse_density_weights(m, adjust=1.0):
+    """scran:::.inverse_density_weights: w = 1/approx(density(m))(m), scaled to mean 1."""
+    bw = _bw_nrd0(m) * adjust
+    lo, hi = m.min() - 3 * bw, m.max() + 3 * bw
+    grid = np.linspace(lo, hi, 512)
+    # Gaussian KDE evaluated on R's default 512-point grid (R bins + FFT; direct sum here)
+    dens = np.empty_like(grid)
+    for a in range(0, 512, 64):
+        z = (grid[a:a + 64, None] - m[None, :]) / bw
+        dens[a:a + 64] = np.exp(-0.5 * z * z).sum(axis=1)
+    dens /= len(m) * bw * np.sqrt(2 * np.pi)
+    w = 1.0 / np.interp(m, grid, dens)
+    return w / w.mean()
+
+
+def _nls_starts(v, m, left_n=100, left_prop=0.1, grid_length=10, b_range=5, n_max=10):
+    o = np.argsort(m, kind="stable")
+    n = len(v)
+    keep = o[:max(1, int(min(left_n, n * left_prop)))]
+    grad = float(np.dot(m[keep], v[keep]) / np.dot(m[keep], m[keep]))  # lm(y ~ 0 + x)
+    b_pts = 2.0 ** np.linspace(-b_range, b_range, grid_length)
+    n_pts = 2.0 ** np.linspace(0, n_max, grid_length)
+    best = (np.inf, None, None)
+    for cur_n in n_pts:          # expand.grid(B=, n=): B varies fastest
+        for cur_b in b_pts:
+            with np.errstate(over="ignore"):
+                rss = float(np.sum((v - grad * cur_b * m / (m ** cur_n + cur_b)) ** 2))
+            if rss < best[0]:
+                best = (rss, cur_b, cur_n)
+    _, b, nn = best
+    return dict(a=b * grad, b=b, n=nn)
+
+
+def _nls_fit(v, m, w, start, maxiter=500, tol=1e-9):
+    """Weighted least squares on v ~ exp(A) m / (m^(1+exp(N)) + exp(B)).
+
+    stats::nls is Gauss-Newton with step halving and the relative-offset stopping rule
+    (tol 1e-5); here the same normal equations are damped (Levenberg-Marquardt) and
+    iterated far past R's tolerance so that two independent implementations land on the
+    same optimum to ~1e-9."""
+    th = np.array([np.log(start["a"]), np.log(start["b"]), np.log(max(start["n"] - 1.0, 1e-8))])
+    lm = np.log(m)
+    sw = np.sqrt(w)
+
+    def model(t):
+        ea, eb, en = np.exp(t[0]), np.exp(t[1]), np.exp(t[2])
+        p = m ** (1.0 + en)
+        den = p + eb
+        f = ea * m / den
+        jac = np.stack([f, -f * eb / den, -f * p * lm * en / den], axis=1)
+        return f, jac
+
+    f, jac = model(th)
+    rss = float(np.sum(w * (v - f) ** 2))
+    damp = 1e-3
+    for _ in range(maxiter):
+        r = sw * (v - f)
+        jw = sw[:, None] * jac
+        q, _ = np.linalg.qr(jw)
+        qtr = q.T @ r
+        crit = np.sqrt(float(qtr @ qtr) / max(float(r @ r) - float(qtr @ qtr), 1e-300))
+        if crit < tol:
+            break
+        a = jw.T @ jw
+        g = jw.T @ r
+        improved = False
+        for _try in range(40):
+            step = np.linalg.solve(a + damp * np.diag(np.diag(a)), g)
+            with np.errstate(over="ignore", invalid="ignore"):
+                f2, jac2 = model(th + step)
+                rss2 = float(np.sum(w * (v - f2) ** 2))
+            if np.isfinite(rss2) and rss2 < rss:
+                th, f, jac, rss = th + step, f2, jac2, rss2
+                damp = max(damp / 10.0, 1e-12)
+                improved = True
+                break
+            damp *= 10.0
+        if not improved:
+            break  # no representable decrease left: converged to rounding level
+    return th
+
+
+def _weighted_median(x, w):
+    o = np.argsort(x, kind="stable")
+    cw = np.cumsum(w[o])
+    half = cw[-1] / 2
+    idx = int(np.searchsorted(cw, half, side="left"))
+    if idx + 1 < len(x) and cw[idx] == half:
+        return 0.5 * (x[o[idx]] + x[o[idx + 1]])
+    return x[o[idx]]
+
+
+def weighted_lowess(x, y, w, span=0.3, iterations=4, npts=200):
+    """limma::weightedLowess restated (sorted-x local linear fits at ~npts seed points,
+    tricube kernel, window sized by span * total weight, bisquare robustness)."""
+    o = np.argsort(x, kind="stable")
+    xs, ys, ws = x[o], y[o], w[o]
+    n = len(xs)
+    delta = (xs[-1] - xs[0]) / npts
+    seeds = [0]
+    last = 0
+    for i in range(1, n - 1):
+        if xs[i] - xs[last] > delta:
+            seeds.append(i)
+            last = i
+    if n > 1:
+        seeds.append(n - 1)
+    seeds = np.array(seeds)
+    span_w = span * ws.sum()
+    cw = np.concatenate([[0.0], np.cumsum(ws)])
+    # window limits per seed: grow towards the nearer neighbour until weight >= span_w
+    lims = []
+    for s in seeds:
+        lo = hi = s
+        cur = ws[s]
+        while cur < span_w and (lo > 0 or hi < n - 1):
+            if lo == 0:
+                hi += 1
+                cur += ws[hi]
+            elif hi == n - 1:
+                lo -= 1
+                cur += ws[lo]
+            elif xs[s] - xs[lo - 1] < xs[hi + 1] - xs[s]:
+                lo -= 1
+                cur += ws[lo]
+            else:
+                hi += 1
+                cur += ws[hi]
+        dist = max(xs[s] - xs[lo], xs[hi] - xs[s])
+        while lo > 0 and xs[s] - xs[lo - 1] <= dist:
+            lo -= 1
+        while hi < n - 1 and xs[hi + 1] - xs[s] <= dist:
+            hi += 1
+        lims.append((lo, hi, dist))
+    del cw
+    rob = np.ones(n)
+    fitted = np.empty(n)
+    for it in range(iterations):
+        sv = np.empty(len(seeds))
+        for q, s in enumerate(seeds):
+            lo, hi, dist = lims[q]
+            xx, yy = xs[lo:hi + 1], ys[lo:hi + 1]
+            if dist <= 0:
+                kw = ws[lo:hi + 1] * rob[lo:hi + 1]
+            else:
+                u = np.abs(xx - xs[s]) / dist
+                kw = np.where(u < 1, (1 - u ** 3) ** 3, 0.0) * ws[lo:hi + 1] * rob[lo:hi + 1]
+            tw = kw.sum()
+            if tw <= 0:
+                sv[q] = ys[s]
+                continue
+            xm = (kw * xx).sum() / tw
+            ym = (kw * yy).sum() / tw
+            var = (kw * (xx - xm) ** 2).sum()
+            if var < 1e-12 * max(dist * dist, 1e-300) * tw:
+                sv[q] = ym
+            else:
+                slope = (kw * (xx - xm) * (yy - ym)).sum() / var
+                sv[q] = ym + slope * (xs[s] - xm)
+        fitted = np.interp(xs, xs[seeds], sv)
+        if it == iterations - 1:
+            break
+        res = np.abs(ys - fitted)
+        cmad = 6.0 * _weighted_median(res, ws)
+        if cmad <= 1e-12 * max(res.mean(), 1e-300):
+            break
+        rob = np.where(res < cmad, (1 - (res / cmad) ** 2) ** 2, 0.0)
+    out = np.empty(n)
+    out[o] = fitted
+    return out
+
+
+@dataclass
+class TrendFit:
+    trend: object
+    std_dev: float
+
+
+def fit_trend_var(means, vars_, min_mean=0.1, parametric=True, lowess=True, density_weights=True):
+    """scran::fitTrendVar(means, vars) with the defaults modelGeneVar uses (row a5)."""
+    means = np.asarray(means, dtype=np.float64)
+    vars_ = np.asarray(vars_, dtype=np.float64)
+    ok = np.isfinite(vars_) & (vars_ > 1e-8) & (means >= min_mean)
+    v, m = vars_[ok], means[ok]
+    if len(v) < 2:
+        raise ValueError("need at least 2 points for non-parametric curve fitting")
+    w = _inverse_density_weights(m) if density_weights else np.ones_like(m)
+    to_fit = np.log(v)
+    left_edge = m.min()
+
+    def paramfun(x):
+        return np.minimum(1.0, x / left_edge)
+
+    if parametric:
+        if len(v) <= 3:
+            raise ValueError("need at least 4 points for non-linear curve fitting")
+        th = _nls_fit(v, m, w, _nls_starts(v, m))
+        ea, eb, en = np.exp(th)
+
+        def paramfun(x):  # noqa: F811
+            return ea * x / (x ** (1.0 + en) + eb)
+        to_fit = to_fit - np.log(paramfun(m))
+    if lowess:
+        lfit = weighted_lowess(m, to_fit, w, span=0.3)
+        o = np.argsort(m, kind="stable")
+        mx, ly = m[o], lfit[o]
+        # approxfun(m, fitted, rule=2); ties averaged like approxfun's default ties=mean
+        ux, inv = np.unique(mx, return_inverse=True)
+        uy = np.bincount(inv, weights=ly) / np.bincount(inv)
+
+        def unscaled(x):
+            return np.exp(np.interp(x, ux, uy)) * paramfun(x)
+    else:
+        unscaled = paramfun
+    leftovers = v / unscaled(m)
+    med = _weighted_median(leftovers, w)
+    std_dev = float(_weighted_median(np.abs(leftovers / med - 1.0), w) * 1.4826)
+
+    def trend(x):
+        x = np.asarray(x, dtype=np.float64)
+        out = unscaled(np.maximum(x, 0.0)) * med
+        return np.where(x > 0, out, 0.0) if np.ndim(out) else out
+    return TrendFit(trend=trend, std_dev=std_dev)
+
+
+def _pnorm_upper(z):
+    from scipy.special import ndtr
+    return ndtr(-z)
+
+
+def model_gene_var(means, vars_):
+    """scran::modelGeneVar decomposition: tech = trend(mean), bio = total - tech,
+    p.value = pnorm(total/tech, mean=1, sd=std.dev, lower=FALSE), FDR = BH."""
+    fit = fit_trend_var(means, vars_)
+    tech = fit.trend(means)
+    bio = vars_ - tech
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = vars_ / tech
+    p = _pnorm_upper((ratio - 1.0) / fit.std_dev)
+    p = np.where(np.isfinite(ratio), p, np.nan)
+    fdr = np.full_like(p, np.nan)
+    okp = np.isfinite(p)
+    if okp.any():
+        pv = p[okp]
+        o = np.argsort(pv, kind="stable")[::-1]
+        n = len(pv)
+        adj = np.minimum.accumulate(pv[o] * n / np.arange(n, 0, -1))
+        tmp = np.empty(n)
+        tmp[o] = np.minimum(adj, 1.0)
+        fdr[okp] = tmp
+    return dict(mean=means, total=vars_, tech=tech, bio=bio, p_value=p, FDR=fdr, std_dev=fit.std_dev)
+
+
+def get_top_hvgs(bio, n):
+    """scran::getTopHVGs(stats, n=n): keep bio > 0, order(bio, decreasing=TRUE) (ties by
+    row index), first n.  Returns 0-based row indices (row a6)."""
+    bio = np.asarray(bio)
+    keep = np.flatnonzero(np.isfinite(bio) & (bio > 0))
+    o = keep[np.argsort(-bio[keep], kind="stable")]
+    return o[:n].astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------
+# K5: scater::runPCA(subset_row = hvgs, exprs_values = "logcounts", ncomponents = d)
+#     (R/doNormAndReduce.R:94-97)
+# ---------------------------------------------------------------------------------------
+def run_pca(n_genes, colptr, rowidx, logx, hvg_idx, d):
+    """Exact truncated SVD of the column-centred (N x H) HVG log-count matrix.
+
+    Returns scores (N x d) = U D, rotation (H x d) = V, var_explained = D^2/(N-1),
+    percent_var = 100 var_explained / sum(column variances)."""
+    import scipy.sparse as sp
+    colptr = np.asarray(colptr, dtype=np.int64)
+    n = colptr.size - 1
+    mat = sp.csc_matrix((logx, np.asarray(rowidx, dtype=np.int64), colptr), shape=(n_genes, n))
+    m = np.asarray(mat.tocsr()[np.asarray(hvg_idx, dtype=np.int64), :].T.todense(), dtype=np.float64)
+    mu = m.mean(axis=0)
+    xc = m - mu
+    total_var = float((xc * xc).sum() / (n - 1))
+    if n >= xc.shape[1]:
+        # eigen-decomposition of the H x H cross-product in fp64 would square the
+        # condition number; use LAPACK SVD (what BiocSingular::ExactParam does).
+        u, s, vt = np.linalg.svd(xc, full_matrices=False)
+    else:
+        u, s, vt = np.linalg.svd(xc, full_matrices=False)
+    scores = u[:, :d] * s[:d]
+    rotation = vt[:d].T
+    var_expl = s[:d] ** 2 / (n - 1)
+    return dict(scores=scores, rotation=rotation, var_explained=var_expl,
+                percent_var=100.0 * var_expl / total_var, total_var=total_var, center=mu)
+
+
+# ---------------------------------------------------------------------------------------
+# K6: BiocNeighbors::findKNN  
+# ---------------------------------------------------------------------------------------
+def find_knn(emb, k, want_dist=False):
+    """Exact kNN through oracle/knn_snn.c.  emb: N x d; returns N x k 1-based int32."""
+    emb_f = np.asfortranarray(emb, dtype=np.float64)
+    n, d = emb_f.shape
+    idx = np.empty((n, k), dtype=np.int32, order="F")
+    dist = np.empty((n, k), dtype=np.float64, order="F") if want_dist else None
+    rc = _lib().oracle_knn(_p(emb_f, ctypes.c_double), n, d, k, _p(idx, ctypes.c_int32),
+                           _p(dist, ctypes.c_double) if want_dist else None)
+    if rc != 0:
+        raise ValueError(f"oracle_knn failed ({rc}): need 1 <= k <= N-1")
+    return (idx, dist) if want_dist else idx
+
+
+def find_knn_numpy(emb, k):
+    """Same contract in numpy, for cross-checking the C oracle on small inputs:
+    sequential fp64 accumulation (numpy never fuses multiply-add), sqrt, (dist, idx) order."""
+    emb = np.asarray(emb, dtype=np.float64)
+    n, d = emb.shape
+    acc = np.zeros((n, n))
+    for t in range(d):
+        delta = emb[:, t][:, None] - emb[:, t][None, :]
+        acc += delta * delta
+    dist = np.sqrt(acc)
+    out = np.empty((n, k), dtype=np.int32)
+    for i in range(n):
+        cand = np.array([j for j in range(n) if j != i])
+        o = np.lexsort((cand, dist[i, cand]))
+        out[i] = cand[o[:k]] + 1
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# K7: bluster::neighborsToSNNGraph  
+# ---------------------------------------------------------------------------------------
+SNN_TYPES = {"rank": 0, "number": 1, "jaccard": 2}
+
+
+def snn_edges(index, snn_type="rank"):
+    """index: N x k 1-based.  Returns (from, to, weight) in emission order (1-based)."""
+    idx = np.asfortranarray(index, dtype=np.int32)
+    n, k = idx.shape
+    ne = ctypes.c_int64(0)
+    pf, pt = ctypes.POINTER(ctypes.c_int32)(), ctypes.POINTER(ctypes.c_int32)()
+    pw = ctypes.POINTER(ctypes.c_double)()
+    rc = _lib().oracle_snn(_p(idx, ctypes.c_int32), n, k, SNN_TYPES[snn_type], ctypes.byref(ne),
+                           ctypes.byref(pf), ctypes.byref(pt), ctypes.byref(pw))
+    if rc != 0:
+        raise ValueError(f"oracle_snn failed ({rc})")
+    m = ne.value
+    f = np.ctypeslib.as_array(pf, shape=(max(m, 1),))[:m].copy()
+    t = np.ctypeslib.as_array(pt, shape=(max(m, 1),))[:m].copy()
+    w = np.ctypeslib.as_array(pw, shape=(max(m, 1),))[:m].copy()
+    for ptr in (pf, pt, pw):
+        _lib().oracle_free(ctypes.cast(ptr, ctypes.c_void_p))
+    return f, t, w
+
+
+def snn_edges_python(index, snn_type="rank"):
+    """Brute-force definition (all pairs), for cross-checking on tiny inputs.
+    Returns a dict {(max, min) 1-based: weight}."""
+    idx = np.asarray(index)
+    n, k = idx.shape
+    lists = [[j] + [int(v) - 1 for v in idx[j]] for j in range(n)]
+    out = {}
+    for j in range(n):
+        for h in range(j):
+            shared = set(lists[j]) & set(lists[h])
+            if not shared:
+                continue
+            if snn_type == "rank":
+                r = min(lists[j].index(s) + lists[h].index(s) for s in shared)
+                wgt = k - r / 2.0
+            elif snn_type == "number":
+                wgt = float(len(shared))
+            else:
+                wgt = len(shared) / (2.0 * (k + 1) - len(shared))
+            out[(j + 1, h + 1)] = max(wgt, 1e-6)
+    return out
+
+
+def canonical_edges(frm, to, w):
+    """(min, max)-sorted edge list, the parity comparison form."""
+    a = np.minimum(frm, to).astype(np.int64)
+    b = np.maximum(frm, to).astype(np.int64)
+    o = np.lexsort((b, a))
+    return a[o], b[o], np.asarray(w)[o]
+
+
+# ---------------------------------------------------------------------------------------
+# whole path (for bench cpu_baseline and the end-to-end parity tests)
+# ---------------------------------------------------------------------------------------
+def pipeline(n_genes, colptr, rowidx, x, ndims=50, hvg_ntop=2000, neighbors=20, snn_type="rank",
+             fast_pca=False):
+    """counts -> SNN graph through the restated steps, in the reference's call order."""
+    sf = library_size_factors(colptr, x)
+    logx = log_norm_counts(colptr, x, sf)
+    n = len(colptr) - 1
+    mean, var = gene_mean_var(n_genes, n, rowidx, logx)
+    stats = model_gene_var(mean, var)
+    hvgs = get_top_hvgs(stats["bio"], hvg_ntop)
+    if fast_pca:
+        pca = run_pca_irlba_like(n_genes, colptr, rowidx, logx, hvgs, ndims)
+    else:
+        pca = run_pca(n_genes, colptr, rowidx, logx, hvgs, ndims)
+    knn = find_knn(pca["scores"], neighbors)
+    frm, to, w = snn_edges(knn, snn_type)
+    return dict(sf=sf, logx=logx, mean=mean, var=var, stats=stats, hvgs=hvgs, pca=pca, knn=knn,
+                edges=(frm, to, w))
+
+
+def run_pca_irlba_like(n_genes, colptr, rowidx, logx, hvg_idx, d):
+    """Truncated SVD by ARPACK on the implicitly centred sparse matrix -- the CPU-baseline
+    stand-in for BiocSingular::IrlbaParam (Lanczos bidiagonalisation)."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import LinearOperator, svds
+    colptr = np.asarray(colptr, dtype=np.int64)
+    n = colptr.size - 1
+    mat = sp.csc_matrix((logx, np.asarray(rowidx, dtype=np.int64), colptr), shape=(n_genes, n))
+    m = mat.tocsr()[np.asarray(hvg_idx, dtype=np.int64), :].T.tocsr()  # N x H
+    mu = np.asarray(m.mean(axis=0)).ravel()
+    ones = np.ones(n)
+    op = LinearOperator(m.shape, dtype=np.float64,
+                        matvec=lambda v: m @ v - ones * float(mu @ np.ravel(v)),
+                        rmatvec=lambda u: m.T @ u - mu * float(np.ravel(u).sum()))
+    rng = np.random.default_rng(0)
+    u, s, vt = svds(op, k=d, v0=rng.standard_normal(min(m.shape)), tol=1e-10)
+    o = np.argsort(-s)
+    u, s, vt = u[:, o], s[o], vt[o]
+    sq = np.asarray(m.multiply(m).sum(axis=0)).ravel()
+    total_var = float((sq - n * mu * mu).sum() / (n - 1))
+    var_expl = s ** 2 / (n - 1)
+    return dict(scores=u * s, rotation=vt.T, var_explained=var_expl,
+                percent_var=100.0 * var_expl / total_var, total_var=total_var, center=mu)

@@ -1,0 +1,77 @@
+"""GPU parity, stage K6 (exact kNN): neighbour indices must be bit-exact against the oracle's
+(distance, index) ordering, including ties, duplicates and every supported k."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cellula_b200
+from cellula_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+
+
+def test_kat_knn(gpu_ctx):
+    x = np.asarray(KAT["snn1"]["x"], dtype=np.float64)[:, None]
+    assert gpu_ctx.knn(x, 2).tolist() == KAT["snn1"]["knn"]
+    x = np.asarray(KAT["knn_tie"]["x"], dtype=np.float64)[:, None]
+    assert gpu_ctx.knn(x, 1).tolist() == KAT["knn_tie"]["knn"]
+
+
+@pytest.mark.parametrize("n,d,k", [(3000, 50, 20), (3000, 50, 10), (2500, 30, 30), (2000, 50, 100),
+                                   (1500, 7, 5), (777, 1, 3), (4097, 64, 24), (129, 50, 52)])
+def test_knn_bit_exact_random(gpu_ctx, n, d, k):
+    emb = synth.make_embedding(n, d, seed=n + d + k)
+    got = gpu_ctx.knn(emb, k)
+    assert got.dtype == np.int32 and got.shape == (n, k)
+    assert np.array_equal(got, O.find_knn(emb, k))
+
+
+def test_knn_bit_exact_20k(gpu_ctx):
+    emb = synth.make_embedding(20000, 50, seed=99)
+    assert np.array_equal(gpu_ctx.knn(emb, 20), O.find_knn(emb, 20))
+
+
+def test_knn_integer_lattice_ties(gpu_ctx):
+    """Massive exact ties: neighbours must come out in index order within equal distances.
+    Also forces the margin test to fail, so the exact-scan fallback is exercised."""
+    rng = np.random.default_rng(5)
+    emb = rng.integers(-2, 3, size=(1500, 4)).astype(np.float64)
+    got = gpu_ctx.knn(emb, 15)
+    assert np.array_equal(got, O.find_knn(emb, 15))
+    assert gpu_ctx.timings()["knn_fallback_queries"] > 0
+
+
+def test_knn_duplicates(gpu_ctx):
+    emb = synth.make_embedding(600, 10, seed=1)
+    emb[100:140] = emb[100]          # 40 identical cells
+    emb[300] = emb[7]
+    got = gpu_ctx.knn(emb, 12)
+    assert np.array_equal(got, O.find_knn(emb, 12))
+    assert all(i + 1 not in got[i] for i in range(600))
+
+
+def test_knn_query_range(gpu_ctx):
+    emb = synth.make_embedding(2000, 20, seed=2)
+    full = O.find_knn(emb, 10)
+    part = gpu_ctx.knn(emb, 10, q_begin=513, q_end=1400)
+    assert np.array_equal(part, full[513:1400])
+
+
+def test_knn_scale_invariance_of_exactness(gpu_ctx):
+    """Large offsets make the norm expansion lossy in fp32; the result must stay exact."""
+    emb = synth.make_embedding(1500, 20, seed=4) + 1000.0
+    assert np.array_equal(gpu_ctx.knn(emb, 10), O.find_knn(emb, 10))
+
+
+def test_knn_argument_errors(gpu_ctx):
+    emb = synth.make_embedding(50, 5, seed=3)
+    with pytest.raises(cellula_b200.Cb200Error, match="k <= n-1"):
+        gpu_ctx.knn(emb, 50)
+    with pytest.raises(cellula_b200.Cb200Error, match="k <= 112"):
+        gpu_ctx.knn(synth.make_embedding(300, 5, seed=3), 120)
+    with pytest.raises(cellula_b200.Cb200Error, match="ndims"):
+        gpu_ctx.knn(synth.make_embedding(100, 70, seed=3), 5)

@@ -1,0 +1,97 @@
+"""GPU parity, stages K1-K3 (size factors, logcounts, per-gene mean/variance) through the C ABI
+against the oracle.  north_star tolerance: 1e-6 relative; asserted much tighter."""
+import numpy as np
+import pytest
+
+import cellula_b200
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def run_norm(ctx, d, colptr_dtype=np.int64):
+    ctx.load_csc(d["n_genes"], d["colptr"].astype(colptr_dtype), d["rowidx"], d["x"])
+    sf = ctx.size_factors()
+    logx, mean, var = ctx.lognorm_genestats()
+    return sf, logx, mean, var
+
+
+def check_against_oracle(d, sf, logx, mean, var):
+    o_sf = O.library_size_factors(d["colptr"], d["x"])
+    o_logx = O.log_norm_counts(d["colptr"], d["x"], o_sf)
+    o_mean, o_var = O.gene_mean_var(d["n_genes"], len(d["colptr"]) - 1, d["rowidx"], o_logx)
+    assert rel(sf, o_sf) <= 1e-13
+    assert rel(logx, o_logx) <= 1e-12          # contract: 1e-6
+    assert np.allclose(mean, o_mean, rtol=1e-11, atol=1e-300)   # contract: 1e-6
+    assert np.allclose(var, o_var, rtol=1e-9, atol=1e-18)
+    assert np.all(var >= 0)
+
+
+def test_norm_small(gpu_ctx, small_counts):
+    check_against_oracle(small_counts, *run_norm(gpu_ctx, small_counts))
+
+
+def test_norm_int32_colptr_like_dgcmatrix(gpu_ctx, small_counts):
+    check_against_oracle(small_counts, *run_norm(gpu_ctx, small_counts, np.int32))
+
+
+def test_norm_kat(gpu_ctx):
+    # KAT-NORM-1 / KAT-VAR-1 of SURVEY.md 8c.3: column sums 2, 4, 6; count 3 in the first column
+    colptr = np.array([0, 2, 3, 5], dtype=np.int64)
+    rowidx = np.array([0, 1, 0, 0, 1], dtype=np.int32)
+    x = np.array([3.0, -1.0 + 0.0, 4.0, 5.0, 1.0])
+    x[1] = -1.0  # (3 + -1 = 2): values need not be counts for the arithmetic
+    gpu_ctx.load_csc(2, colptr, rowidx, x)
+    sf = gpu_ctx.size_factors()
+    assert np.allclose(sf, [0.5, 1.0, 1.5], rtol=0, atol=1e-16)
+    logx, _, _ = gpu_ctx.lognorm_genestats()
+    assert abs(logx[0] - 2.807354922057604) < 1e-14
+
+
+def test_ragged_columns_and_alignment(gpu_ctx):
+    """Column lengths 1..70 at every start parity: exercises the 128-bit head/tail handling."""
+    rng = np.random.default_rng(3)
+    lens = np.concatenate([np.arange(1, 71), rng.integers(1, 9, 300), [257, 1, 2, 3, 511]])
+    colptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    G = 600
+    rowidx = np.concatenate([np.sort(rng.choice(G, n, replace=False)) for n in lens]).astype(np.int32)
+    x = rng.integers(1, 50, colptr[-1]).astype(np.float64)
+    d = dict(n_genes=G, colptr=colptr, rowidx=rowidx, x=x)
+    check_against_oracle(d, *run_norm(gpu_ctx, d))
+
+
+def test_genes_without_counts_have_zero_stats(gpu_ctx, small_counts):
+    d = dict(small_counts)
+    d["n_genes"] = small_counts["n_genes"] + 37  # trailing all-zero genes
+    sf, logx, mean, var = run_norm(gpu_ctx, d)
+    assert np.all(mean[-37:] == 0) and np.all(var[-37:] == 0)
+    check_against_oracle(d, sf, logx, mean, var)
+
+
+def test_user_size_factors_are_recentred(gpu_ctx, small_counts):
+    d = small_counts
+    rng = np.random.default_rng(0)
+    user = rng.uniform(0.2, 3.0, d["n_cells"])
+    gpu_ctx.load_csc(d["n_genes"], d["colptr"], d["rowidx"], d["x"])
+    sf = gpu_ctx.size_factors(user)
+    assert np.allclose(sf, user / user.mean(), rtol=1e-14)
+    logx, _, _ = gpu_ctx.lognorm_genestats()
+    assert rel(logx, O.log_norm_counts(d["colptr"], d["x"], user / user.mean())) <= 1e-12
+
+
+def test_empty_cell_fails_like_scuttle(gpu_ctx):
+    colptr = np.array([0, 2, 2, 3], dtype=np.int64)  # second cell has no counts
+    gpu_ctx.load_csc(4, colptr, np.array([0, 1, 2], dtype=np.int32), np.array([1.0, 2.0, 3.0]))
+    with pytest.raises(cellula_b200.Cb200Error, match="size factors should be positive"):
+        gpu_ctx.size_factors()
+
+
+def test_stage_order_is_enforced(gpu_ctx, small_counts):
+    d = small_counts
+    gpu_ctx.load_csc(d["n_genes"], d["colptr"], d["rowidx"], d["x"])
+    with pytest.raises(cellula_b200.Cb200Error, match="size factors have not been computed"):
+        gpu_ctx.lognorm_genestats()

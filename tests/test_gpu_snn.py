@@ -1,0 +1,83 @@
+"""GPU parity, stage K7 (SNN edge weighting): edges and weights bit-exact against the oracle,
+in canonical form and in emission order, for rank / number / jaccard."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cellula_b200
+from cellula_b200 import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+SCHEMES = ["rank", "number", "jaccard"]
+
+
+def assert_same_edges(got, want):
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)                      # same order (libscran emission order)
+    cg, cw = O.canonical_edges(*got), O.canonical_edges(*want)
+    for g, w in zip(cg, cw):
+        assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_kat_snn(gpu_ctx, scheme):
+    knn = np.asarray(KAT["snn1"]["knn"], dtype=np.int32)
+    f, t, w = gpu_ctx.snn(knn, scheme)
+    want = sorted((min(a, b), max(a, b), float(c)) for a, b, c in KAT["snn1"]["edges"][scheme])
+    got = sorted((min(a, b), max(a, b), float(c)) for a, b, c in zip(f.tolist(), t.tolist(), w.tolist()))
+    assert [g[:2] for g in got] == [x[:2] for x in want]
+    assert np.allclose([g[2] for g in got], [x[2] for x in want], rtol=0, atol=1e-15)
+    assert [[a, b] for a, b in zip(f.tolist(), t.tolist())] == KAT["snn1"]["emission_order_8c1_7"]["pairs"]
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("n,k", [(3000, 10), (3000, 20), (2000, 30), (1200, 100), (500, 1), (64, 40)])
+def test_snn_bit_exact(gpu_ctx, scheme, n, k):
+    knn = O.find_knn(synth.make_embedding(n, 20, seed=n + k), k)
+    assert_same_edges(gpu_ctx.snn(knn, scheme), O.snn_edges(knn, scheme))
+
+
+def test_snn_hub_cells(gpu_ctx):
+    """A few cells sit in thousands of neighbour lists: long reverse lists."""
+    rng = np.random.default_rng(8)
+    n, k = 6000, 10
+    knn = np.empty((n, k), dtype=np.int32)
+    for j in range(n):
+        cand = np.setdiff1d(np.concatenate([np.arange(5), rng.choice(n, 30, replace=False)]), [j],
+                            assume_unique=False)
+        hubs = [c for c in range(5) if c != j][:4]
+        rest = [c for c in cand if c not in hubs][:k - len(hubs)]
+        knn[j] = np.array(hubs + rest) + 1
+    for scheme in SCHEMES:
+        assert_same_edges(gpu_ctx.snn(knn, scheme), O.snn_edges(knn, scheme))
+
+
+def test_snn_cell_range_shards_concatenate(gpu_ctx):
+    knn = O.find_knn(synth.make_embedding(2500, 20, seed=6), 15)
+    want = O.snn_edges(knn, "rank")
+    parts = [gpu_ctx.snn(knn, "rank", j_begin=a, j_end=b) for a, b in [(0, 700), (700, 1301), (1301, 2500)]]
+    got = tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+    assert_same_edges(got, want)
+
+
+def test_snn_resident_knn_equals_host_index(gpu_ctx):
+    emb = synth.make_embedding(3000, 30, seed=12)
+    knn = gpu_ctx.knn(emb, 20)
+    a = gpu_ctx.snn(None, "jaccard", n_total=3000, k=20)     # uses the kNN left in HBM
+    b = gpu_ctx.snn(knn, "jaccard")
+    assert_same_edges(a, b)
+    assert gpu_ctx.snn_resident(20, "jaccard") == len(b[0])
+
+
+def test_snn_argument_errors(gpu_ctx):
+    knn = O.find_knn(synth.make_embedding(100, 5, seed=1), 5)
+    bad = knn.copy()
+    bad[3, 2] = 101
+    with pytest.raises(cellula_b200.Cb200Error, match="out of range"):
+        gpu_ctx.snn(bad, "rank")
+    with pytest.raises(KeyError):
+        gpu_ctx.snn(knn, "cosine")

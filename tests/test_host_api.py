@@ -1,0 +1,80 @@
+"""Host-side mirror of the reference entry points: argument validation and error text follow
+/root/reference/R/doNormAndReduce.R:45-53 and R/makeGraphsAndClusters.R:65-72.  These checks
+fire before any device work, so they run without a GPU."""
+import numpy as np
+import pytest
+
+import cellula_b200 as cb
+from cellula_b200 import trendvar
+from cellula_b200.dist import shard_bounds, slice_csc
+
+
+def tiny_sce():
+    return cb.SingleCellExperiment.from_counts([0, 1, 2], [0, 1], [1.0, 2.0], n_genes=3)
+
+
+def test_donormandreduce_validation():
+    with pytest.raises(TypeError, match="must provide a SingleCellExperiment object"):
+        cb.doNormAndReduce(object())
+    with pytest.raises(ValueError, match="batch column not found in the colData of the object"):
+        cb.doNormAndReduce(tiny_sce(), batch="nope")
+    with pytest.raises(ValueError, match="hvg_ntop cannot be higher than the number of features"):
+        cb.doNormAndReduce(tiny_sce(), hvg_ntop=10)
+    sce = tiny_sce()
+    sce.colData["batch"] = ["a", "b"]
+    with pytest.raises(NotImplementedError, match="batch-aware path is not implemented"):
+        cb.doNormAndReduce(sce, batch="batch", hvg_ntop=2)
+
+
+def test_makegraphsandclusters_validation():
+    with pytest.raises(TypeError, match="must provide a SingleCellExperiment object"):
+        cb.makeGraphsAndClusters(42)
+    sce = tiny_sce()
+    with pytest.raises(ValueError, match='must be one of "leiden" or "louvain"'):
+        cb.makeGraphsAndClusters(sce, method="walktrap")
+    with pytest.raises(ValueError, match='must be one of "jaccard", "rank", or "number"'):
+        cb.makeGraphsAndClusters(sce, weighting_scheme="cosine")
+    with pytest.raises(ValueError, match="there are no dimensionality reductions"):
+        cb.makeGraphsAndClusters(sce)
+    sce.reducedDims["PCA"] = np.zeros((2, 2))
+    with pytest.raises(ValueError, match="the dr name supplied was not found"):
+        cb.makeGraphsAndClusters(sce, dr="UMAP")
+
+
+def test_signatures_match_reference_defaults():
+    import inspect
+    s = inspect.signature(cb.doNormAndReduce).parameters
+    assert list(s) == ["sce", "batch", "name", "ndims", "hvg_ntop", "umap_seed", "verbose", "parallel_param"]
+    assert (s["ndims"].default, s["hvg_ntop"].default, s["umap_seed"].default) == (20, 2000, 11)
+    g = inspect.signature(cb.makeGraphsAndClusters).parameters
+    assert list(g) == ["sce", "neighbors", "weighting_scheme", "sweep_on", "method", "k", "dr", "ndims",
+                       "calculate_modularity", "calculate_silhouette", "leiden_iterations", "save_graphs",
+                       "prefix", "verbose"]
+    assert (g["neighbors"].default, g["weighting_scheme"].default, g["ndims"].default) == (10, "jaccard", 20)
+
+
+def test_shard_bounds_and_slicing():
+    assert shard_bounds(10, 3) == [0, 4, 7, 10]
+    assert shard_bounds(8, 8) == list(range(9))
+    colptr = np.array([0, 2, 2, 5, 6])
+    rowidx = np.arange(6, dtype=np.int32)
+    x = np.arange(6, dtype=float)
+    p, i, v = slice_csc(colptr, rowidx, x, 1, 3)
+    assert p.tolist() == [0, 0, 3] and i.tolist() == [2, 3, 4] and v.tolist() == [2.0, 3.0, 4.0]
+
+
+def test_host_trend_agrees_with_oracle_restatement(small_counts):
+    """The package's host-side HVG step and the oracle's restatement are written separately;
+    fed the same means/variances they must pick the same HVGs in the same order."""
+    from oracle import oracle as O
+    d = small_counts
+    sf = O.library_size_factors(d["colptr"], d["x"])
+    lx = O.log_norm_counts(d["colptr"], d["x"], sf)
+    mean, var = O.gene_mean_var(d["n_genes"], d["n_cells"], d["rowidx"], lx)
+    a = trendvar.model_gene_var(mean, var)
+    b = O.model_gene_var(mean, var)
+    assert np.allclose(a["tech"], b["tech"], rtol=1e-7, atol=1e-12)
+    assert np.array_equal(trendvar.get_top_hvgs(a, 800), O.get_top_hvgs(b["bio"], 800))
+    # trend properties: positive where the mean is positive, zero at zero
+    tr, sd = trendvar.fit_trend_var(mean, var)
+    assert sd > 0 and tr(np.array([0.0]))[0] == 0.0 and np.all(tr(np.linspace(0.01, 5, 50)) > 0)
