@@ -61,7 +61,10 @@ def _fit_parametric(v, m, w, tol=1e-9, maxiter=500):
         f = ea * m / den
         return f, np.column_stack((f, -f * eb / den, -f * p * logm * en / den))
 
-    f, jac = evaluate(th)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        f, jac = evaluate(th)
+    if not (np.all(np.isfinite(f)) and np.all(np.isfinite(jac))):
+        return np.exp(th)  # scran keeps the grid-search start values when nls() cannot run
     rss = float(w @ (v - f) ** 2)
     damp = 1e-3
     sw = np.sqrt(w)
@@ -76,11 +79,15 @@ def _fit_parametric(v, m, w, tol=1e-9, maxiter=500):
         a = jw.T @ jw
         g = jw.T @ r
         for _try in range(40):
-            step = np.linalg.solve(a + damp * np.diag(np.diag(a)), g)
-            with np.errstate(over="ignore", invalid="ignore"):
+            try:
+                step = np.linalg.solve(a + damp * np.diag(np.diag(a) + 1e-300), g)
+            except np.linalg.LinAlgError:
+                damp *= 10.0
+                continue
+            with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
                 f2, jac2 = evaluate(th + step)
                 rss2 = float(w @ (v - f2) ** 2)
-            if np.isfinite(rss2) and rss2 < rss:
+            if np.isfinite(rss2) and rss2 < rss and np.all(np.isfinite(jac2)):
                 th, f, jac, rss = th + step, f2, jac2, rss2
                 damp = max(damp / 10.0, 1e-12)
                 break

@@ -202,7 +202,10 @@ def _nls_fit(v, m, w, start, maxiter=500, tol=1e-9):
         jac = np.stack([f, -f * eb / den, -f * p * lm * en / den], axis=1)
         return f, jac
 
-    f, jac = model(th)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        f, jac = model(th)
+    if not (np.all(np.isfinite(f)) and np.all(np.isfinite(jac))):
+        return th  # scran keeps the grid-search start values when nls() cannot run
     rss = float(np.sum(w * (v - f) ** 2))
     damp = 1e-3
     for _ in range(maxiter):
@@ -217,11 +220,15 @@ def _nls_fit(v, m, w, start, maxiter=500, tol=1e-9):
         g = jw.T @ r
         improved = False
         for _try in range(40):
-            step = np.linalg.solve(a + damp * np.diag(np.diag(a)), g)
-            with np.errstate(over="ignore", invalid="ignore"):
+            try:
+                step = np.linalg.solve(a + damp * np.diag(np.diag(a) + 1e-300), g)
+            except np.linalg.LinAlgError:
+                damp *= 10.0
+                continue
+            with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
                 f2, jac2 = model(th + step)
                 rss2 = float(np.sum(w * (v - f2) ** 2))
-            if np.isfinite(rss2) and rss2 < rss:
+            if np.isfinite(rss2) and rss2 < rss and np.all(np.isfinite(jac2)):
                 th, f, jac, rss = th + step, f2, jac2, rss2
                 damp = max(damp / 10.0, 1e-12)
                 improved = True

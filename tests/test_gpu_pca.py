@@ -48,7 +48,9 @@ def test_pca_matches_oracle_svd(gpu_ctx, small_counts, small_oracle, ndims):
 def test_pca_sign_convention_is_deterministic(gpu_ctx, small_counts, small_oracle):
     a = run_to_pca(gpu_ctx, small_counts, small_oracle["hvgs"], 6)
     b = run_to_pca(gpu_ctx, small_counts, small_oracle["hvgs"], 6)
-    assert np.array_equal(a["rotation"], b["rotation"])
+    # the cross-product is accumulated with fp64 reductions in L2 (order varies run to run), so
+    # two runs agree to rounding, and the sign rule makes them agree in sign as well
+    assert np.allclose(a["rotation"], b["rotation"], rtol=0, atol=1e-9)
     j = np.argmax(np.abs(a["rotation"]), axis=0)
     assert np.all(a["rotation"][j, np.arange(6)] > 0)
 
