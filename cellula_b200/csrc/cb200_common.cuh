@@ -108,6 +108,7 @@ struct cb200_ctx {
     DevBuf<double> emb;        // [n_total*d] row-major fp64 (when given from host)
     DevBuf<double> stage_d;    // staging for column-major <-> row-major conversions
     DevBuf<float> emb_f;       // [n_total*DP] fp32 padded
+    DevBuf<unsigned char> knn_img;  // tensor-core operand image of the references (cb200_knn_tc.cu)
     DevBuf<float> hnorm;       // [n_total]   0.5*|r|^2 (fp32)
     DevBuf<double> nrm2;       // [n_total]   |r|^2 (fp64)
     DevBuf<unsigned long long> maxnrm;  // [1] bit pattern of max |r|^2

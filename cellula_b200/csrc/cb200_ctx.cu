@@ -95,7 +95,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->mu.release(); ctx->eq.release(); ctx->ew.release(); ctx->ey.release(); ctx->ex.release();
     ctx->es.release(); ctx->et.release(); ctx->etheta.release(); ctx->eres.release();
     ctx->emuv.release(); ctx->rot.release(); ctx->scores.release(); ctx->varexp.release();
-    ctx->emb.release(); ctx->stage_d.release(); ctx->emb_f.release(); ctx->hnorm.release();
+    ctx->emb.release(); ctx->stage_d.release(); ctx->emb_f.release(); ctx->knn_img.release(); ctx->hnorm.release();
     ctx->nrm2.release(); ctx->maxnrm.release(); ctx->cand_idx.release(); ctx->cand_tau.release();
     ctx->knn.release(); ctx->knn_dk.release(); ctx->fb_list.release(); ctx->stage_i.release();
     ctx->index0.release(); ctx->rcnt.release(); ctx->rptr.release(); ctx->rcur.release();

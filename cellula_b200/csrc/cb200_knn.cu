@@ -19,7 +19,11 @@
 #include <cfloat>
 #include <cmath>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "cb200_common.cuh"
+#include "cb200_knn_tc.cuh"
 
 #define KNN_THREADS 256
 #define KNN_TN 128       // references per tile
@@ -53,62 +57,6 @@ __global__ void k_knn_prep(const double *__restrict__ E, int64_t lde, int64_t n,
     hn[i] = (float)(0.5 * s);
     nrm2[i] = s;
     atomicMax(maxbits, (unsigned long long)__double_as_longlong(s));  // s >= 0: bit order == value order
-}
-
-// ---------------------------------------------------------------------------------------
-// warp-wide bitonic sort of 32*EPL (key, idx) pairs, element i = e*32 + lane, ascending by
-// (key, idx)
-// ---------------------------------------------------------------------------------------
-template <typename K>
-__device__ __forceinline__ bool pair_less(K ka, int ia, K kb, int ib)
-{
-    return ka < kb || (ka == kb && ia < ib);
-}
-
-template <typename K, int EPL>
-__device__ __forceinline__ void warp_bitonic_sort(K (&key)[EPL], int (&idx)[EPL], int lane)
-{
-    constexpr int NTOT = 32 * EPL;
-#pragma unroll
-    for (int k = 2; k <= NTOT; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int dj = j >> 5;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) {
-                    const int pe = e ^ dj;
-                    if (pe > e) {
-                        const bool up = (((e * 32 + lane) & k) == 0);
-                        const bool gt = pair_less<K>(key[pe], idx[pe], key[e], idx[e]);  // v[e] > v[pe]
-                        if (gt == up) {
-                            K tk = key[e];
-                            key[e] = key[pe];
-                            key[pe] = tk;
-                            int ti = idx[e];
-                            idx[e] = idx[pe];
-                            idx[pe] = ti;
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) {
-                    const bool up = (((e * 32 + lane) & k) == 0);
-                    const K ok = __shfl_xor_sync(0xffffffffu, key[e], j);
-                    const int oi = __shfl_xor_sync(0xffffffffu, idx[e], j);
-                    const bool lower = ((lane & j) == 0);
-                    const bool other_less = pair_less<K>(ok, oi, key[e], idx[e]);
-                    // the lower lane of an ascending pair keeps the minimum
-                    const bool take_other = (lower == up) ? other_less : !other_less;
-                    if (take_other) {
-                        key[e] = ok;
-                        idx[e] = oi;
-                    }
-                }
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -316,7 +264,7 @@ __device__ __forceinline__ double exact_dist(const double *__restrict__ a, const
 template <int KP>
 __global__ void __launch_bounds__(256)
 k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, int64_t nq, int k,
-             const int32_t *__restrict__ cand_idx, const float *__restrict__ cand_tau, const double *__restrict__ nrm2,
+             const int32_t *__restrict__ cand_idx, const float *__restrict__ cand_tau, int ntau, const double *__restrict__ nrm2,
              const unsigned long long *__restrict__ maxbits, double err_coef, int32_t *__restrict__ knn,
              double *__restrict__ knn_dk, int32_t *__restrict__ fb_list, int *__restrict__ fb_count)
 {
@@ -361,7 +309,10 @@ k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, 
             const double nq2 = nrm2[grow];
             const double ek = 0.5 * dk * dk - 0.5 * nq2;      // exact key of the k-th candidate
             const double bound = err_coef * (nq2 + m2);       // |approx key - exact key| <= bound
-            const float tau = cand_tau[q];
+            // every non-candidate has an approximate key >= the smallest of the ntau thresholds
+            float tau = cand_tau[q * ntau];
+            for (int u = 1; u < ntau; ++u)
+                tau = fminf(tau, cand_tau[q * ntau + u]);
             const bool proven = (tau == FLT_MAX) || (ek + bound < (double)tau - bound);
             if (!proven) {
                 const int pos = atomicAdd(fb_count, 1);
@@ -433,8 +384,7 @@ __global__ void k_knn_to_r_layout(const int32_t *__restrict__ knn, int64_t nq, i
 // host side
 // ---------------------------------------------------------------------------------------
 template <int KP, int TM>
-static int run_tiles_and_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int d, int DP, int k,
-                                int64_t q_begin, int64_t q_end)
+static int run_tiles_simt(cb200_ctx *ctx, int64_t n, int DP, int64_t q_begin, int64_t q_end)
 {
     const int64_t nq = q_end - q_begin;
     const size_t smem = KnnSmem<KP, TM>::bytes;
@@ -447,19 +397,24 @@ static int run_tiles_and_rerank(cb200_ctx *ctx, const double *E, int64_t lde, in
                                                                    ctx->cand_idx.p, ctx->cand_tau.p);
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_KNN_TILE);
+    return 0;
+}
 
+template <int KP>
+static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int d, int k, int64_t q_begin,
+                      int64_t nq, double err_coef, int ntau)
+{
     cb_stage_begin(ctx, ST_KNN_RERANK);
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 2, 0, 2 * sizeof(int), ctx->stream));
-    // fp32 FMA chain of DP terms + input/half-norm roundings, see DESIGN.md "kNN error bound"
-    const double err_coef = ldexp((double)(DP + 8), -24);
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 2, 0, sizeof(int), ctx->stream));
     const int rgrid = cb_grid_for(nq, 8, ctx->num_sms * 16);
     k_knn_rerank<KP><<<rgrid, 256, 0, ctx->stream>>>(E, lde, d, q_begin, nq, k, ctx->cand_idx.p, ctx->cand_tau.p,
-                                                     ctx->nrm2.p, ctx->maxnrm.p, err_coef, ctx->knn.p, ctx->knn_dk.p,
+                                                     ntau, ctx->nrm2.p, ctx->maxnrm.p, err_coef, ctx->knn.p, ctx->knn_dk.p,
                                                      ctx->fb_list.p, ctx->flag.p + 2);
     CB_LAUNCH(ctx);
     int h[2] = {0, 0};
     CB_CUDA(ctx, cudaMemcpyAsync(h, ctx->flag.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_CHECK(ctx, (h[1] & 4) == 0, "cb200_knn: tensor-core tile kernel timed out on a barrier (protocol error)");
     ctx->tm.knn_fallback_queries = h[0];
     if (h[0] > 0) {
         k_knn_exact<<<h[0], 256, 0, ctx->stream>>>(E, lde, d, n, q_begin, k, ctx->fb_list.p, ctx->knn_dk.p, ctx->knn.p,
@@ -467,8 +422,8 @@ static int run_tiles_and_rerank(cb200_ctx *ctx, const double *E, int64_t lde, in
         CB_LAUNCH(ctx);
         CB_CUDA(ctx, cudaMemcpyAsync(h, ctx->flag.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        CB_CHECK(ctx, h[1] == 0, "cb200_knn: exact-scan fallback overflowed (more than %d ties); result not produced",
-                 KNN_FB_CAP);
+        CB_CHECK(ctx, (h[1] & 1) == 0,
+                 "cb200_knn: exact-scan fallback overflowed (more than %d ties); result not produced", KNN_FB_CAP);
     }
     cb_stage_end(ctx, ST_KNN_RERANK);
     return 0;
@@ -484,29 +439,51 @@ static int knn_core(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int
     CB_CHECK(ctx, k <= 112, "cb200_knn: k <= 112 supported (got %d)", k);
     CB_CHECK(ctx, q_begin >= 0 && q_begin < q_end && q_end <= n, "cb200_knn: bad query range");
     const int64_t nq = q_end - q_begin;
-    const int DP = (d + 3) & ~3;
-    CB_CUDA(ctx, ctx->emb_f.ensure((size_t)n * DP));
-    CB_CUDA(ctx, ctx->hnorm.ensure((size_t)n));
-    CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
     CB_CUDA(ctx, ctx->knn.ensure((size_t)nq * k));
     CB_CUDA(ctx, ctx->knn_dk.ensure((size_t)nq));
     CB_CUDA(ctx, ctx->fb_list.ensure((size_t)nq));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
 
-    cb_stage_begin(ctx, ST_KNN_PREP);
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, sizeof(unsigned long long), ctx->stream));
-    k_knn_prep<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(E, lde, n, d, DP, ctx->emb_f.p, ctx->hnorm.p,
-                                                                    ctx->nrm2.p, ctx->maxnrm.p);
-    CB_LAUNCH(ctx);
-    cb_stage_end(ctx, ST_KNN_PREP);
-
-    int rc;
-    if (k <= 24)
-        rc = run_tiles_and_rerank<32, 128>(ctx, E, lde, n, d, DP, k, q_begin, q_end);
-    else if (k <= 52)
-        rc = run_tiles_and_rerank<64, 128>(ctx, E, lde, n, d, DP, k, q_begin, q_end);
+    // tile engine: tensor cores (tcgen05) whenever the shape allows; CB200_KNN_ENGINE=simt forces the
+    // fp32 CUDA-core engine (kept for d > 61 or k > 52, and as the cross-check in the tests)
+    const char *eng = getenv("CB200_KNN_ENGINE");
+    const bool want_simt = eng != nullptr && strcmp(eng, "simt") == 0;
+    const bool use_tc = !want_simt && cb200_knn_tc_supported(d, k);
+    int KP = 0, ntau = 1;
+    double err_coef = 0.0;
+    ctx->tm.knn_engine = use_tc ? 2 : 1;
+    if (use_tc) {
+        CB_TRY(cb200_knn_tiles_tc(ctx, E, lde, n, d, k, q_begin, q_end, &KP, &ntau, &err_coef));
+    } else {
+        const int DP = (d + 3) & ~3;
+        CB_CUDA(ctx, ctx->emb_f.ensure((size_t)n * DP));
+        CB_CUDA(ctx, ctx->hnorm.ensure((size_t)n));
+        CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
+        cb_stage_begin(ctx, ST_KNN_PREP);
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, sizeof(unsigned long long), ctx->stream));
+        k_knn_prep<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(E, lde, n, d, DP, ctx->emb_f.p, ctx->hnorm.p,
+                                                                        ctx->nrm2.p, ctx->maxnrm.p);
+        CB_LAUNCH(ctx);
+        cb_stage_end(ctx, ST_KNN_PREP);
+        // fp32 FMA chain of DP terms + input/half-norm roundings, see DESIGN.md "kNN error bound"
+        err_coef = ldexp((double)(DP + 8), -24);
+        if (k <= 24) {
+            KP = 32;
+            CB_TRY((run_tiles_simt<32, 128>(ctx, n, DP, q_begin, q_end)));
+        } else if (k <= 52) {
+            KP = 64;
+            CB_TRY((run_tiles_simt<64, 128>(ctx, n, DP, q_begin, q_end)));
+        } else {
+            KP = 128;
+            CB_TRY((run_tiles_simt<128, 64>(ctx, n, DP, q_begin, q_end)));
+        }
+    }
+    if (KP == 32)
+        CB_TRY(run_rerank<32>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau));
+    else if (KP == 64)
+        CB_TRY(run_rerank<64>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau));
     else
-        rc = run_tiles_and_rerank<128, 64>(ctx, E, lde, n, d, DP, k, q_begin, q_end);
-    CB_TRY(rc);
+        CB_TRY(run_rerank<128>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau));
     ctx->knn_nq = nq;
     ctx->knn_k = k;
     ctx->knn_ntotal = n;

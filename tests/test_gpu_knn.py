@@ -1,5 +1,6 @@
 """GPU parity, stage K6 (exact kNN): neighbour indices must be bit-exact against the oracle's
-(distance, index) ordering, including ties, duplicates and every supported k."""
+(distance, index) ordering, including ties, duplicates and every supported k -- with both tile
+engines (tcgen05 tensor cores, fp32 CUDA cores)."""
 import json
 import os
 
@@ -12,40 +13,66 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+ENGINE_ID = {"simt": 1, "tc": 2}
 
 
-def test_kat_knn(gpu_ctx):
+@pytest.fixture(params=["tc", "simt"])
+def engine(request, monkeypatch):
+    monkeypatch.setenv("CB200_KNN_ENGINE", request.param)
+    return request.param
+
+
+def test_kat_knn(gpu_ctx, engine):
     x = np.asarray(KAT["snn1"]["x"], dtype=np.float64)[:, None]
     assert gpu_ctx.knn(x, 2).tolist() == KAT["snn1"]["knn"]
+    assert gpu_ctx.timings()["knn_engine"] == ENGINE_ID[engine]
     x = np.asarray(KAT["knn_tie"]["x"], dtype=np.float64)[:, None]
     assert gpu_ctx.knn(x, 1).tolist() == KAT["knn_tie"]["knn"]
 
 
-@pytest.mark.parametrize("n,d,k", [(3000, 50, 20), (3000, 50, 10), (2500, 30, 30), (2000, 50, 100),
-                                   (1500, 7, 5), (777, 1, 3), (4097, 64, 24), (129, 50, 52)])
-def test_knn_bit_exact_random(gpu_ctx, n, d, k):
+@pytest.mark.parametrize("n,d,k", [(3000, 50, 20), (3000, 50, 10), (2500, 30, 30), (1500, 7, 5), (777, 1, 3),
+                                   (4097, 61, 24), (129, 50, 52), (128, 16, 40), (257, 3, 25)])
+def test_knn_bit_exact_random(gpu_ctx, engine, n, d, k):
     emb = synth.make_embedding(n, d, seed=n + d + k)
     got = gpu_ctx.knn(emb, k)
+    assert gpu_ctx.timings()["knn_engine"] == ENGINE_ID[engine]
     assert got.dtype == np.int32 and got.shape == (n, k)
-    assert np.array_equal(got, O.find_knn(emb, k))
+    want = O.find_knn(emb, k)
+    bad = np.flatnonzero((got != want).any(axis=1))
+    assert bad.size == 0, (bad[:10], got[bad[:3]], want[bad[:3]])
 
 
-def test_knn_bit_exact_20k(gpu_ctx):
+@pytest.mark.parametrize("n,d,k", [(2000, 50, 100), (4097, 64, 24), (900, 62, 10), (700, 20, 53)])
+def test_knn_shapes_only_the_simt_engine_takes(gpu_ctx, n, d, k):
+    emb = synth.make_embedding(n, d, seed=n + d + k)
+    assert np.array_equal(gpu_ctx.knn(emb, k), O.find_knn(emb, k))
+    assert gpu_ctx.timings()["knn_engine"] == 1
+
+
+def test_knn_bit_exact_20k(gpu_ctx, engine):
     emb = synth.make_embedding(20000, 50, seed=99)
-    assert np.array_equal(gpu_ctx.knn(emb, 20), O.find_knn(emb, 20))
+    got, want = gpu_ctx.knn(emb, 20), O.find_knn(emb, 20)
+    bad = np.flatnonzero((got != want).any(axis=1))
+    assert bad.size == 0, (bad.size, bad[:10])
+    # the margin test must prove (nearly) every query without the exact-scan fallback
+    assert gpu_ctx.timings()["knn_fallback_queries"] <= 20
 
 
-def test_knn_integer_lattice_ties(gpu_ctx):
+def test_knn_integer_lattice_ties(gpu_ctx, engine):
     """Massive exact ties: neighbours must come out in index order within equal distances.
     Also forces the margin test to fail, so the exact-scan fallback is exercised."""
     rng = np.random.default_rng(5)
     emb = rng.integers(-2, 3, size=(1500, 4)).astype(np.float64)
     got = gpu_ctx.knn(emb, 15)
     assert np.array_equal(got, O.find_knn(emb, 15))
+    # 9 distinct positions, ~440 copies of each: far more exact ties than candidates are kept
+    emb = rng.integers(-1, 2, size=(4000, 2)).astype(np.float64)
+    got = gpu_ctx.knn(emb, 15)
+    assert np.array_equal(got, O.find_knn(emb, 15))
     assert gpu_ctx.timings()["knn_fallback_queries"] > 0
 
 
-def test_knn_duplicates(gpu_ctx):
+def test_knn_duplicates(gpu_ctx, engine):
     emb = synth.make_embedding(600, 10, seed=1)
     emb[100:140] = emb[100]          # 40 identical cells
     emb[300] = emb[7]
@@ -54,17 +81,28 @@ def test_knn_duplicates(gpu_ctx):
     assert all(i + 1 not in got[i] for i in range(600))
 
 
-def test_knn_query_range(gpu_ctx):
+def test_knn_query_range(gpu_ctx, engine):
     emb = synth.make_embedding(2000, 20, seed=2)
     full = O.find_knn(emb, 10)
     part = gpu_ctx.knn(emb, 10, q_begin=513, q_end=1400)
     assert np.array_equal(part, full[513:1400])
 
 
-def test_knn_scale_invariance_of_exactness(gpu_ctx):
-    """Large offsets make the norm expansion lossy in fp32; the result must stay exact."""
-    emb = synth.make_embedding(1500, 20, seed=4) + 1000.0
+@pytest.mark.parametrize("shift,scale", [(1000.0, 1.0), (0.0, 1e-6), (0.0, 1e5), (-3e4, 7.0)])
+def test_knn_exact_under_offsets_and_scales(gpu_ctx, engine, shift, scale):
+    """Large offsets make the norm expansion lossy, tiny/huge values stress the fp16 split;
+    the result must stay exact (through the margin test / fallback)."""
+    emb = synth.make_embedding(1500, 20, seed=4) * scale + shift
     assert np.array_equal(gpu_ctx.knn(emb, 10), O.find_knn(emb, 10))
+
+
+def test_knn_engines_agree_on_candidates_quality(gpu_ctx, monkeypatch):
+    """Both engines must need (almost) no fallback on well-separated data."""
+    emb = synth.make_embedding(6000, 50, seed=21)
+    for eng in ("tc", "simt"):
+        monkeypatch.setenv("CB200_KNN_ENGINE", eng)
+        gpu_ctx.knn(emb, 20, want=False)
+        assert gpu_ctx.timings()["knn_fallback_queries"] <= 6, eng
 
 
 def test_knn_argument_errors(gpu_ctx):
