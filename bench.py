@@ -136,7 +136,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cellula_b200", choices=["cellula_b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("CB200_WORKLOAD", "cfg2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("CB200_WORKLOAD", "cfg3"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=20000, help="cells in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -218,15 +218,31 @@ def main():
         x_h = torch.empty(nnz, dtype=torch.float64).pin_memory()
         ctx.export_csc(colptr_h.numpy(), rowidx_h.numpy(), x_h.numpy())
         logx_h = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        scores_h = torch.empty(n_local * w["ndims"], dtype=torch.float64).pin_memory()
+        knn_h = torch.empty((n_local, w["k"]), dtype=torch.int32).pin_memory()
+        cap = int(1.05 * n_edges_local) + 1024
+        ebuf = [torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory(),
+                torch.empty(cap, dtype=torch.float64).pin_memory()]
+
+        def edge_buffers(ne):
+            if ne > ebuf[0].numel():  # grow (not expected: same data every step)
+                ebuf[0] = torch.empty(ne, dtype=torch.int32).pin_memory()
+                ebuf[1] = torch.empty(ne, dtype=torch.int32).pin_memory()
+                ebuf[2] = torch.empty(ne, dtype=torch.float64).pin_memory()
+            return ebuf[0].numpy(), ebuf[1].numpy(), ebuf[2].numpy()
+
+        scores_np = scores_h.numpy().reshape((n_local, w["ndims"]), order="F")
         h2d = colptr_h.numel() * 8 + rowidx_h.numel() * 4 + x_h.numel() * 8 + HVG_NTOP * 4
         d2h_box = [0]
 
         def e2e_step():
             ctx.load_csc_ptrs(w["genes"], n_local, nnz, colptr_h.data_ptr(), rowidx_h.data_ptr(), x_h.data_ptr(),
                               cell_offset=c0, n_cells_total=w["cells"])
-            r = pipe.run(ndims=w["ndims"], hvg_ntop=HVG_NTOP, neighbors=w["k"], snn_type=w["scheme"], want_host=True)
+            r = pipe.run(ndims=w["ndims"], hvg_ntop=HVG_NTOP, neighbors=w["k"], snn_type=w["scheme"], want_host=True,
+                         scores_out=scores_np, edge_buffers=edge_buffers)
             ctx.fetch_logcounts(logx_h.numpy())
-            knn_local = r["knn_full"][c0:c1].cpu()
+            knn_h.copy_(r["knn_full"][c0:c1], non_blocking=False)
+            knn_local = knn_h
             f, t, wt = r["edges"]
             d2h_box[0] = (n_local * 8 + nnz * 8 + 2 * w["genes"] * 8 + n_local * w["ndims"] * 8 +
                           HVG_NTOP * w["ndims"] * 8 + knn_local.numel() * 4 + f.size * 4 + t.size * 4 + wt.size * 8)

@@ -68,6 +68,7 @@ SIGNATURES = {
                                  ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p), ctypes.POINTER(c_f64p)]),
     "cb200_snn_resident": (c_int, [c_vp, c_int, c_int, c_i64p]),
     "cb200_free_edges": (c_int, [c_i32p, c_i32p, c_f64p]),
+    "cb200_fetch_edges": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cb200_synth_counts": (c_int, [c_vp, c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_i64p]),
     "cb200_export_csc": (c_int, [c_vp, c_vp, c_vp, c_vp]),
 }
@@ -322,6 +323,14 @@ class Context:
                                         j_end, ctypes.byref(ne), ctypes.byref(pf), ctypes.byref(pt),
                                         ctypes.byref(pw)))
         return self._take_edges(ne, pf, pt, pw)
+
+    def fetch_edges(self, n_edges, frm=None, to=None, weight=None):
+        """Edges of the last snn* call into caller-owned (e.g. pinned) arrays."""
+        frm = np.empty(n_edges, np.int32) if frm is None else frm
+        to = np.empty(n_edges, np.int32) if to is None else to
+        weight = np.empty(n_edges, np.float64) if weight is None else weight
+        self._ck(lib().cb200_fetch_edges(self._h, n_edges, _ptr(frm), _ptr(to), _ptr(weight)))
+        return frm[:n_edges], to[:n_edges], weight[:n_edges]
 
     def snn_resident(self, k, snn_type="rank"):
         ne = c_i64()

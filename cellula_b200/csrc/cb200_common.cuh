@@ -87,7 +87,9 @@ struct cb200_ctx {
 
     // ---- a7: PCA
     int H = 0, d = 0, blk = 0;
-    DevBuf<int32_t> hvg_idx;   // [H]
+    DevBuf<int32_t> hvg_idx;   // [H] genes of the slots, ascending
+    DevBuf<int32_t> hvg_perm;  // [H] slot of the caller's h-th HVG
+    DevBuf<uint16_t> hbptr;    // [N*(nb+1)] block boundaries of the per-cell HVG entries
     DevBuf<int32_t> slot;      // [G] gene -> hvg slot or -1
     DevBuf<int32_t> hcnt;      // [N]
     DevBuf<int64_t> hptr;      // [N+1]

@@ -10,7 +10,10 @@
 // GPUs by the caller), centre it with the gene means already known from K3, take the top d
 // eigenpairs of the covariance by Chebyshev-filtered block subspace iteration with
 // Rayleigh-Ritz (fp64, no cuSOLVER), then project: scores = X V - 1 (mu^T V).
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "cb200_common.cuh"
@@ -109,6 +112,125 @@ k_gram_sparse(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslo
                 atomicAdd(gram + (int64_t)r * H + cc, va * vb);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K5b (v2): tiled sparse cross-product.  HVG slots are numbered in ascending gene order, so the
+// entries of a cell are sorted by slot and the entries that fall into a block of GB_BS slots are
+// contiguous; bptr[c][blk] (uint16, relative to hptr[c]) marks the block boundaries.  A CTA owns
+// one GB_BS x GB_BS tile (I <= J) of X^T X for a slice of the cells, accumulates the outer products
+// of the I- and J-entries of every cell in shared memory (fp64 shared atomics), and flushes the
+// tile once with fp64 reductions to L2.  Exact fp64 products; no dense operand is ever formed.
+// ---------------------------------------------------------------------------------------
+#define GB_BS 64
+
+// warp per cell, lane per block: first entry with slot >= blk*GB_BS (binary search)
+__global__ void __launch_bounds__(256)
+k_hvg_blockptr(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, int64_t n_cols, int nb,
+               uint16_t *__restrict__ bptr)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = warp0; c < n_cols; c += nwarps) {
+        const int64_t b = hptr[c];
+        const int m = (int)(hptr[c + 1] - b);
+        for (int blk = lane; blk <= nb; blk += 32) {
+            const int target = blk * GB_BS;
+            int lo = 0, hi = m;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (hslot[b + mid] < target)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            bptr[c * (nb + 1) + blk] = (uint16_t)lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gram_tiled(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, const double *__restrict__ hval,
+             const uint16_t *__restrict__ bptr, int64_t n_cols, int nb, int H, double *__restrict__ gram)
+{
+    __shared__ double T[GB_BS][GB_BS + 1];
+    // blockIdx.x enumerates the tiles (I <= J) in row-major order of the upper triangle
+    int I = 0, rem = blockIdx.x;
+    while (rem >= nb - I) {
+        rem -= nb - I;
+        ++I;
+    }
+    const int J = I + rem;
+    for (int i = threadIdx.x; i < GB_BS * (GB_BS + 1); i += blockDim.x)
+        (&T[0][0])[i] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t per = (n_cols + gridDim.y - 1) / gridDim.y;
+    const int64_t c_begin = (int64_t)blockIdx.y * per;
+    const int64_t c_end = c_begin + per < n_cols ? c_begin + per : n_cols;
+    const int stride = nb + 1;
+    for (int64_t c = c_begin + w; c < c_end; c += nw) {
+        const uint16_t *bp = bptr + c * stride;
+        const int i0 = bp[I], i1 = bp[I + 1], j0 = bp[J], j1 = bp[J + 1];
+        const int nI = i1 - i0, nJ = j1 - j0;
+        if (nI == 0 || nJ == 0)
+            continue;
+        const int64_t base = hptr[c];
+        for (int ja = 0; ja < nJ; ja += 32) {
+            const int nbj = nJ - ja < 32 ? nJ - ja : 32;
+            int sJ = 0;
+            double vJ = 0.0;
+            if (lane < nbj) {
+                sJ = hslot[base + j0 + ja + lane] - J * GB_BS;
+                vJ = hval[base + j0 + ja + lane];
+            }
+            // lanes are split into G groups of nbp (a power of two >= nbj) lanes: group g takes I-entry
+            // ia + g, lane (l % nbp) takes the J-entry
+            int nbp = 1;
+            while (nbp < nbj)
+                nbp <<= 1;
+            const int G = 32 / nbp;
+            const int gsel = lane / nbp, bsel = lane & (nbp - 1);
+            const double vb = __shfl_sync(0xffffffffu, vJ, bsel);
+            const int sb = __shfl_sync(0xffffffffu, sJ, bsel);
+            for (int ia = 0; ia < nI; ia += 32) {
+                const int nai = nI - ia < 32 ? nI - ia : 32;
+                int sI = 0;
+                double vI = 0.0;
+                if (lane < nai) {
+                    sI = hslot[base + i0 + ia + lane] - I * GB_BS;
+                    vI = hval[base + i0 + ia + lane];
+                }
+                for (int a0 = 0; a0 < nai; a0 += G) {
+                    const int a = a0 + gsel;
+                    const double va = __shfl_sync(0xffffffffu, vI, a & 31);
+                    const int sa = __shfl_sync(0xffffffffu, sI, a & 31);
+                    if (a < nai && bsel < nbj && (I != J || sa <= sb))
+                        atomicAdd(&T[sa][sb], va * vb);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < GB_BS * GB_BS; i += blockDim.x) {
+        const int r = i / GB_BS, cc = i % GB_BS;
+        const int gr = I * GB_BS + r, gc = J * GB_BS + cc;
+        const double v = T[r][cc];
+        if (gr < H && gc < H && v != 0.0)
+            atomicAdd(gram + (int64_t)gr * H + gc, v);
+    }
+}
+
+// rotation in the caller's HVG order, column-major: out[h + H*j] = rot[perm[h]*d + j]
+__global__ void k_rotation_out(const double *__restrict__ rot, const int32_t *__restrict__ perm, int H, int d,
+                               double *__restrict__ out)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx < (int64_t)H * d) {
+        const int h = (int)(idx % H), j = (int)(idx / H);
+        out[idx] = rot[(int64_t)perm[h] * d + j];
     }
 }
 
@@ -678,6 +800,17 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int H = n_hvg;
     ctx->H = H;
+    // Device-side slots are numbered in ascending gene order (entries of a cell then come sorted by
+    // slot); perm[h] = slot of the caller's h-th HVG, used when the rotation is handed back.
+    std::vector<int32_t> order((size_t)H), sorted_genes((size_t)H), perm((size_t)H);
+    for (int h = 0; h < H; ++h)
+        order[h] = h;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hvg_idx[a] < hvg_idx[b]; });
+    for (int s = 0; s < H; ++s) {
+        sorted_genes[s] = hvg_idx[order[s]];
+        perm[order[s]] = s;
+    }
+    CB_CUDA(ctx, ctx->hvg_perm.ensure((size_t)H));
     CB_CUDA(ctx, ctx->hvg_idx.ensure((size_t)H));
     CB_CUDA(ctx, ctx->slot.ensure((size_t)ctx->G));
     CB_CUDA(ctx, ctx->mu.ensure((size_t)H));
@@ -686,8 +819,11 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     CB_CUDA(ctx, ctx->gram.ensure((size_t)H * H));
 
     cb_stage_begin(ctx, ST_HVG_EXTRACT);
-    CB_CUDA(ctx, cudaMemcpyAsync(ctx->hvg_idx.p, hvg_idx, (size_t)H * sizeof(int32_t), cudaMemcpyHostToDevice,
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->hvg_idx.p, sorted_genes.data(), (size_t)H * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->hvg_perm.p, perm.data(), (size_t)H * sizeof(int32_t), cudaMemcpyHostToDevice,
                                  ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
     k_fill_i32<<<(unsigned)((ctx->G + 255) / 256), 256, 0, ctx->stream>>>(ctx->slot.p, ctx->G, -1);
     CB_LAUNCH(ctx);
     k_build_slot<<<(H + 255) / 256, 256, 0, ctx->stream>>>(ctx->hvg_idx.p, H, ctx->slot.p, ctx->gene_mean.p,
@@ -707,12 +843,33 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     k_hvg_fill<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->logx.p, ctx->slot.p, ctx->N,
                                               ctx->hptr.p, ctx->hslot.p, ctx->hval.p);
     CB_LAUNCH(ctx);
+    const int nb = (H + GB_BS - 1) / GB_BS;
+    CB_CUDA(ctx, ctx->hbptr.ensure((size_t)ctx->N * (nb + 1)));
+    k_hvg_blockptr<<<grid, 256, 0, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->N, nb, ctx->hbptr.p);
+    CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_HVG_EXTRACT);
 
     cb_stage_begin(ctx, ST_GRAM);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->gram.p, 0, (size_t)H * H * sizeof(double), ctx->stream));
-    k_gram_sparse<<<grid, 256, 0, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p, ctx->N, H, ctx->gram.p);
-    CB_LAUNCH(ctx);
+    const char *geng = getenv("CB200_GRAM_ENGINE");
+    if (geng != nullptr && strcmp(geng, "atomic") == 0) {
+        // v1 (kept as a cross-check): one fp64 L2 reduction per product
+        k_gram_sparse<<<grid, 256, 0, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p, ctx->N, H, ctx->gram.p);
+        CB_LAUNCH(ctx);
+    } else {
+        // a cell holds at most 65535 HVG entries by construction (H <= 32767)
+        const int n_tiles = nb * (nb + 1) / 2;
+        int ysplit = (int)((4LL * ctx->num_sms + n_tiles - 1) / n_tiles);  // >= 4 CTAs per SM in flight
+        const int64_t max_split = (ctx->N + 255) / 256;
+        if (ysplit > max_split)
+            ysplit = (int)max_split;
+        if (ysplit < 1)
+            ysplit = 1;
+        dim3 ggrid((unsigned)n_tiles, (unsigned)ysplit);
+        k_gram_tiled<<<ggrid, 256, 0, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p, ctx->hbptr.p, ctx->N, nb,
+                                                     H, ctx->gram.p);
+        CB_LAUNCH(ctx);
+    }
     cb_stage_end(ctx, ST_GRAM);
     ctx->have_gram = true;
     ctx->have_scores = false;
@@ -870,8 +1027,8 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (rotation != nullptr) {
-        k_rowmajor_to_colmajor<<<(unsigned)(((int64_t)H * d + 255) / 256), 256, 0, ctx->stream>>>(ctx->rot.p, H, d,
-                                                                                                 ctx->stage_d.p);
+        k_rotation_out<<<(unsigned)(((int64_t)H * d + 255) / 256), 256, 0, ctx->stream>>>(ctx->rot.p, ctx->hvg_perm.p,
+                                                                                        H, d, ctx->stage_d.p);
         CB_LAUNCH(ctx);
         CB_CUDA(ctx, cudaMemcpyAsync(rotation, ctx->stage_d.p, (size_t)H * d * sizeof(double), cudaMemcpyDeviceToHost,
                                      ctx->stream));

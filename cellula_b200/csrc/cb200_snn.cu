@@ -307,6 +307,30 @@ static int snn_fetch(cb200_ctx *ctx, int64_t ne, int32_t **from, int32_t **to, d
     return 0;
 }
 
+// Copies the edges left in HBM by the last cb200_snn* call into caller-owned buffers (R vectors,
+// pinned staging, ...): no allocation, no intermediate copy.
+extern "C" int cb200_fetch_edges(cb200_ctx *ctx, int64_t n_edges, int32_t *from, int32_t *to, double *weight)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, n_edges == ctx->n_edges, "cb200_fetch_edges: the context holds %lld edges, not %lld",
+             (long long)ctx->n_edges, (long long)n_edges);
+    CB_CHECK(ctx, from != nullptr && to != nullptr && weight != nullptr, "cb200_fetch_edges: NULL output");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_stage_begin(ctx, ST_D2H);
+    if (n_edges > 0) {
+        CB_CUDA(ctx, cudaMemcpyAsync(from, ctx->efrom.p, (size_t)n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        CB_CUDA(ctx, cudaMemcpyAsync(to, ctx->eto.p, (size_t)n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        CB_CUDA(ctx, cudaMemcpyAsync(weight, ctx->ew8.p, (size_t)n_edges * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    }
+    cb_stage_end(ctx, ST_D2H);
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" int cb200_free_edges(int32_t *from, int32_t *to, double *weight)
 {
     if (from != nullptr)

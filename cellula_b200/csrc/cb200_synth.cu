@@ -177,20 +177,40 @@ extern "C" int cb200_synth_counts(cb200_ctx *ctx, int64_t n_genes, int64_t n_cel
         else
             hi = mid;
     }
-    const float off = (float)(0.5 * (lo + hi));
+    float off = (float)(0.5 * (lo + hi));
 
     ctx->G = n_genes;
     ctx->N = n_cells;
     ctx->cell_offset = cell_offset;
     ctx->N_total = n_cells_total;
-    CB_CUDA(ctx, ctx->colptr.ensure((size_t)n_cells + 1));
-    CB_CUDA(ctx, ctx->hcnt.ensure((size_t)n_cells));
+    // The neutral-cell calibration ignores the factor / depth variance: correct the offset with a
+    // few count passes over a fixed probe -- the first min(N_total, 16384) cells of the *global*
+    // matrix -- until the realised mean is within 1% of the request.  The probe does not depend on
+    // the shard, so every rank derives the same offset and the shards tile one matrix.
+    const int64_t n_probe = n_cells_total < 16384 ? n_cells_total : 16384;
+    const int64_t n_buf = n_cells > n_probe ? n_cells : n_probe;
+    CB_CUDA(ctx, ctx->colptr.ensure((size_t)n_buf + 1));
+    CB_CUDA(ctx, ctx->hcnt.ensure((size_t)n_buf));
+    int64_t nnz = 0;
+    const int pgrid = cb_grid_for(n_probe, 8, ctx->num_sms * 8);
+    for (int pass = 0; pass < 6; ++pass) {
+        k_synth_cells<0><<<pgrid, 256, 0, ctx->stream>>>(n_genes, n_probe, 0, seed, off, P, ctx->hcnt.p, nullptr,
+                                                         nullptr, nullptr);
+        CB_LAUNCH(ctx);
+        CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->hcnt.p, n_probe, ctx->colptr.p));
+        CB_CUDA(ctx, cudaMemcpyAsync(&nnz, ctx->colptr.p + n_probe, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const double actual = (double)nnz / (double)n_probe;
+        if (fabs(actual / nnz_per_cell - 1.0) < 0.01)
+            break;
+        off += (float)(1.3 * log(nnz_per_cell / actual));
+    }
     const int grid = cb_grid_for(n_cells, 8, ctx->num_sms * 8);
     k_synth_cells<0><<<grid, 256, 0, ctx->stream>>>(n_genes, n_cells, cell_offset, seed, off, P, ctx->hcnt.p, nullptr,
                                                     nullptr, nullptr);
     CB_LAUNCH(ctx);
     CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->hcnt.p, n_cells, ctx->colptr.p));
-    int64_t nnz = 0;
     CB_CUDA(ctx, cudaMemcpyAsync(&nnz, ctx->colptr.p + n_cells, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->nnz = nnz;

@@ -91,8 +91,8 @@ class CudaShard:
         h = len(hvg_idx)
         return self._view("gram", (h * h,), torch.float64)
 
-    def finish_pca(self, d, n_hvg, want_scores=True):
-        res = self.ctx.pca_finish(d, n_hvg, want_scores=want_scores)
+    def finish_pca(self, d, n_hvg, want_scores=True, scores_out=None):
+        res = self.ctx.pca_finish(d, n_hvg, want_scores=want_scores, scores_out=scores_out)
         res["scores_dev"] = self._view("scores", (self.ctx.n_cells, d), torch.float64)
         return res
 
@@ -103,8 +103,13 @@ class CudaShard:
         return self._view("knn", (q_end - q_begin, k), torch.int32)
 
     # K7
-    def snn(self, knn_full, snn_type, j_begin, j_end, fetch=True):
+    def snn(self, knn_full, snn_type, j_begin, j_end, fetch=True, edge_buffers=None):
         n, k = knn_full.shape
+        if fetch and edge_buffers is not None:
+            # count first, then copy straight into the caller's (pinned) arrays
+            ne = self.ctx.snn_device(knn_full.data_ptr(), n, k, snn_type, j_begin, j_end, fetch=False)
+            f, t, w = edge_buffers(ne)
+            return self.ctx.fetch_edges(ne, f, t, w)
         return self.ctx.snn_device(knn_full.data_ptr(), n, k, snn_type, j_begin, j_end, fetch=fetch)
 
 
@@ -150,9 +155,12 @@ class ShardedPipeline:
         self._allreduce(self.shard.gene_acc())
         return self.shard.finish_genestats()
 
-    def pca(self, hvg_idx, d, want_scores=True):
+    def pca(self, hvg_idx, d, want_scores=True, scores_out=None):
         self._allreduce(self.shard.gram(hvg_idx))
-        res = self.shard.finish_pca(d, len(hvg_idx), want_scores=want_scores)
+        if scores_out is not None:
+            res = self.shard.finish_pca(d, len(hvg_idx), want_scores=True, scores_out=scores_out)
+        else:
+            res = self.shard.finish_pca(d, len(hvg_idx), want_scores=want_scores)
         res["scores_full_dev"] = self._allgather_rows(res["scores_dev"])
         return res
 
@@ -160,19 +168,25 @@ class ShardedPipeline:
         local = self.shard.knn(emb_full, k, self.c0, self.c1)
         return self._allgather_rows(local)
 
-    def snn(self, knn_full, snn_type, fetch=True):
+    def snn(self, knn_full, snn_type, fetch=True, edge_buffers=None):
+        if fetch and edge_buffers is not None:
+            return self.shard.snn(knn_full, snn_type, self.c0, self.c1, fetch=True, edge_buffers=edge_buffers)
         if fetch:
             return self.shard.snn(knn_full, snn_type, self.c0, self.c1)
         return self.shard.snn(knn_full, snn_type, self.c0, self.c1, fetch=False)
 
-    def run(self, ndims=50, hvg_ntop=2000, neighbors=20, snn_type="rank", sf_in=None, want_host=True):
-        """The whole path for this rank's shard.  Returns host results of the shard."""
+    def run(self, ndims=50, hvg_ntop=2000, neighbors=20, snn_type="rank", sf_in=None, want_host=True,
+            scores_out=None, edge_buffers=None):
+        """The whole path for this rank's shard.  Returns host results of the shard.
+        scores_out: optional column-major (n_local x ndims) host array (e.g. pinned) for the scores;
+        edge_buffers: optional callable n_edges -> (from, to, weight) host arrays to fill."""
         sf = self.size_factors(sf_in, want=want_host)
         mean, var = self.gene_stats()
         stats = trendvar.model_gene_var(mean, var)          # replicated host step (R: scran::fitTrendVar)
         hvgs = trendvar.get_top_hvgs(stats, hvg_ntop)
-        pca = self.pca(hvgs, ndims, want_scores=want_host)
+        pca = self.pca(hvgs, ndims, want_scores=want_host, scores_out=scores_out if want_host else None)
         knn_full = self.knn(pca["scores_full_dev"], neighbors)
-        edges = self.snn(knn_full, snn_type, fetch=want_host)  # (from, to, w), or the count if resident
+        # (from, to, w), or the count if resident
+        edges = self.snn(knn_full, snn_type, fetch=want_host, edge_buffers=edge_buffers)
         return dict(sf=sf, mean=mean, var=var, stats=stats, hvgs=hvgs, pca=pca, knn_full=knn_full,
                     edges=edges)

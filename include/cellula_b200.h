@@ -175,6 +175,9 @@ int cb200_snn_device(cb200_ctx *ctx, const int32_t *d_index_rowmajor0, int64_t n
 /* Device-only variant: edges stay in HBM (bench "value" leg); returns the count. */
 int cb200_snn_resident(cb200_ctx *ctx, int k, int type, int64_t *n_edges);
 int cb200_free_edges(int32_t *from, int32_t *to, double *weight);
+/* Copies the n_edges edges left in HBM by the last cb200_snn / cb200_snn_device / cb200_snn_resident
+ * call into caller-owned arrays (what the R shim does with freshly allocated R vectors). */
+int cb200_fetch_edges(cb200_ctx *ctx, int64_t n_edges, int32_t *from, int32_t *to, double *weight);
 
 /* ---- synthetic input (bench / test infrastructure, not part of the reference path) ---
  * Fills the context with a deterministic negative-binomial count matrix with planted

@@ -132,17 +132,13 @@ SEXP cb200r_snn_graph(SEXP sctx, SEXP space, SEXP k, SEXP type)
     int d = Rf_ncols(space), kk = Rf_asInteger(k);
     CB_OK(ctx, cb200_knn(ctx, REAL(space), n, d, kk, 0, n, NULL));
     int64_t ne = 0;
-    int32_t *from = NULL, *to = NULL;
-    double *w = NULL;
-    CB_OK(ctx, cb200_snn(ctx, NULL, n, kk, Rf_asInteger(type), 0, n, &ne, &from, &to, &w));
+    CB_OK(ctx, cb200_snn_resident(ctx, kk, Rf_asInteger(type), &ne));  /* edges stay in HBM */
     SEXP sf = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)ne)), st = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)ne));
     SEXP sw = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)ne));
-    for (int64_t e = 0; e < ne; ++e) {
-        INTEGER(sf)[e] = from[e];
-        INTEGER(st)[e] = to[e];
-        REAL(sw)[e] = w[e];
+    if (cb200_fetch_edges(ctx, ne, INTEGER(sf), INTEGER(st), REAL(sw)) != 0) { /* straight into the R vectors */
+        UNPROTECT(3);
+        Rf_error("%s", cb200_last_error(ctx));
     }
-    cb200_free_edges(from, to, w);
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)), nm = PROTECT(Rf_allocVector(STRSXP, 3));
     SET_VECTOR_ELT(out, 0, sf);
     SET_VECTOR_ELT(out, 1, st);

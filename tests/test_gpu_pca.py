@@ -45,6 +45,16 @@ def test_pca_matches_oracle_svd(gpu_ctx, small_counts, small_oracle, ndims):
     gpu_ctx.timings()["eig_iterations"] > 0
 
 
+def test_gram_engines_agree(gpu_ctx, small_counts, small_oracle, monkeypatch):
+    """The tiled shared-memory cross-product and the plain L2-reduction one are the same sums."""
+    a = run_to_pca(gpu_ctx, small_counts, small_oracle["hvgs"], 8)
+    monkeypatch.setenv("CB200_GRAM_ENGINE", "atomic")
+    b = run_to_pca(gpu_ctx, small_counts, small_oracle["hvgs"], 8)
+    assert np.allclose(a["var_explained"], b["var_explained"], rtol=1e-10)
+    assert np.allclose(a["rotation"], b["rotation"], atol=1e-8)
+    assert np.allclose(a["scores"], b["scores"], atol=1e-7 * np.abs(a["scores"]).max())
+
+
 def test_pca_sign_convention_is_deterministic(gpu_ctx, small_counts, small_oracle):
     a = run_to_pca(gpu_ctx, small_counts, small_oracle["hvgs"], 6)
     b = run_to_pca(gpu_ctx, small_counts, small_oracle["hvgs"], 6)

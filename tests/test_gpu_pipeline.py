@@ -126,5 +126,5 @@ def test_cfg2_sized_properties(gpu_ctx):
     have = set(key[np.isin(f, probe + 1) | np.isin(t, probe + 1)].tolist())
     for j in probe[:300]:
         for h in knn[j]:
-            a, b = max(j + 1, h), min(j + 1, h)
+            a, b = int(max(j + 1, h)), int(min(j + 1, h))
             assert a * (n + 1) + b in have
