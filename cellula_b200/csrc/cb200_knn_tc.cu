@@ -69,14 +69,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin
             : "memory");
         if (ok)
             return;
-        if (spin > (1u << 24)) {
+        if (spin > (1u << 20)) {
             atomicOr(err_flag, 4);
             __threadfence();
             asm volatile("trap;");
@@ -449,12 +449,18 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     }
                 }
             };
-            uint32_t ra[32];
+            // two register buffers: the TMEM load of the next chunk is in flight while one is scanned
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(tcol, ra);
 #pragma unroll 1
-            for (int ch = 0; ch < TC_N / 32; ++ch) {
-                tmem_ld32_issue(tcol + (uint32_t)(ch * 32), ra);
+            for (int p2 = 0; p2 < TC_N / 64; ++p2) {
                 tmem_ld_wait();
-                scan_chunk(ra, r0 + ch * 32);
+                tmem_ld32_issue(tcol + (uint32_t)(p2 * 64 + 32), rb);
+                scan_chunk(ra, r0 + p2 * 64);
+                tmem_ld_wait();
+                if (p2 + 1 < TC_N / 64)
+                    tmem_ld32_issue(tcol + (uint32_t)((p2 + 1) * 64), ra);
+                scan_chunk(rb, r0 + p2 * 64 + 32);
             }
             tc_fence_before();
             __syncwarp();
