@@ -89,6 +89,7 @@ struct cb200_ctx {
     int H = 0, d = 0, blk = 0;
     DevBuf<int32_t> hvg_idx;   // [H] genes of the slots, ascending
     DevBuf<int32_t> hvg_perm;  // [H] slot of the caller's h-th HVG
+    DevBuf<unsigned char> gram_img;  // int8 digit planes of the HVG matrix (cb200_gram_tc.cu)
     DevBuf<uint16_t> hbptr;    // [N*(nb+1)] block boundaries of the per-cell HVG entries
     DevBuf<int32_t> slot;      // [G] gene -> hvg slot or -1
     DevBuf<int32_t> hcnt;      // [N]

@@ -90,7 +90,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->colptr.release(); ctx->rowidx.release(); ctx->x.release();
     ctx->libsize.release(); ctx->sf.release(); ctx->part.release(); ctx->flag.release();
     ctx->logx.release(); ctx->gene_acc.release(); ctx->gene_mean.release(); ctx->gene_var.release();
-    ctx->hvg_idx.release(); ctx->hvg_perm.release(); ctx->hbptr.release(); ctx->slot.release(); ctx->hcnt.release(); ctx->hptr.release();
+    ctx->hvg_idx.release(); ctx->hvg_perm.release(); ctx->hbptr.release(); ctx->gram_img.release(); ctx->slot.release(); ctx->hcnt.release(); ctx->hptr.release();
     ctx->hslot.release(); ctx->hval.release(); ctx->gram.release(); ctx->cov.release();
     ctx->mu.release(); ctx->eq.release(); ctx->ew.release(); ctx->ey.release(); ctx->ex.release();
     ctx->es.release(); ctx->et.release(); ctx->etheta.release(); ctx->eres.release();

@@ -1,0 +1,307 @@
+// cb200_gram_tc.cu -- K5b on the tensor cores: the H x H cross-product X^T X of the HVG log-counts
+// with tcgen05.mma kind::i8 and an error-free digit splitting, so that the result keeps fp64-grade
+// accuracy (the eigenvectors of near-degenerate PCs do not survive an fp32-accumulated product).
+//
+// Arithmetic.  Every log-count y (0 <= y < 32) is rounded to a 24-bit fixed-point integer
+// q = round(y 2^19) = d0 + d1 2^8 + d2 2^16 with 8-bit digits.  Then
+//        sum_c q_ci q_cj = sum_{p,p'} 2^{8(p+p')} sum_c d_p(c,i) d_p'(c,j)
+// and each inner sum is an unsigned 8-bit GEMM with int32 accumulation, which the tensor core does
+// *exactly* as long as it stays below 2^31: the five orders o = p + p' get separate TMEM
+// accumulators (at most 3 digit pairs x 255^2 per cell) which are flushed into fp64 every
+// GT_FLUSH_CHUNKS x 128 cells.  The only error left is the input rounding (2^-20 absolute, zero-mean
+// and uncorrelated with the data), whose effect on the covariance is ~1e-9 relative.
+//
+// Operands.  k_gram_img densifies the sparse HVG sub-matrix into digit planes in the shared-memory
+// operand layout of tcgen05 (K-major, 128-byte swizzle; K = cells): for gene tile g (128 genes) and
+// cell chunk c (128 cells) three 16 KB planes.  A CTA of k_gram_tc owns a 128 x 64 output tile (I, J)
+// for a slice of the chunks: per chunk one 48 KB + three 8 KB bulk copies, 9 digit products x 4
+// tcgen05.mma (M = 128, N = 64, K = 32).  Warp roles: 0 = bulk-copy producer, 1 = MMA issuer,
+// 2-5 = flush (TMEM -> fp64 -> RED.ADD.F64 into the H x H buffer).
+#include <cstdlib>
+#include <cstring>
+
+#include "cb200_common.cuh"
+#include "cb200_tc.cuh"
+
+using namespace cb200tc;
+
+namespace {
+constexpr int GT_M = 128;            // genes per A tile (UMMA M)
+constexpr int GT_N = 64;             // genes per B tile (UMMA N)
+constexpr int GT_KC = 128;           // cells per chunk = bytes per operand row
+constexpr int GT_PLANES = 3;
+constexpr int GT_PLANE_BYTES = GT_M * GT_KC;             // 16 KB
+constexpr int GT_TILE_BYTES = GT_PLANES * GT_PLANE_BYTES; // 48 KB per (gene tile, chunk)
+constexpr int GT_B_BYTES = GT_N * GT_KC;                  // 8 KB: half a plane
+constexpr int GT_STAGE_BYTES = GT_TILE_BYTES + GT_PLANES * GT_B_BYTES;  // 72 KB
+constexpr int GT_STAGES = 3;
+constexpr int GT_ORDERS = 2 * GT_PLANES - 1;              // 5 accumulators of GT_N columns
+constexpr uint32_t GT_TMEM_COLS = 512;                    // 5 x 64 = 320 -> next power of two
+constexpr int GT_FLUSH_CHUNKS = 80;                       // 3 * 255^2 * 128 * 80 < 2^31
+constexpr int GT_THREADS = 192;
+constexpr int GT_SCALE_BITS = 19;                         // q = round(y 2^19) < 2^24 for y < 32
+constexpr int GT_QUAD = 4;                                // gene tiles built per CTA of k_gram_img
+// instruction descriptor: c = S32 (2) at [4,6), a = b = unsigned 8 bit (0), K-major, N>>3, M>>4
+constexpr uint32_t GT_IDESC = (2u << 4) | ((uint32_t)(GT_N >> 3) << 17) | ((uint32_t)(GT_M >> 4) << 24);
+}  // namespace
+
+// max of the HVG values (bit pattern of a non-negative double orders like an integer)
+__global__ void k_gram_maxval(const double *__restrict__ v, int64_t n, unsigned long long *__restrict__ maxbits)
+{
+    double m = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0)
+        atomicMax(maxbits, (unsigned long long)__double_as_longlong(m));
+}
+
+// Digit planes of GT_QUAD gene tiles for one chunk of 128 cells, built in shared memory and written
+// out with coalesced 16-byte stores.  bptr: block boundaries (blocks of 64 slots) of the per-cell
+// entries, as produced by k_hvg_blockptr.
+__global__ void __launch_bounds__(256)
+k_gram_img(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, const double *__restrict__ hval,
+           const uint16_t *__restrict__ bptr, int64_t n_cells, int nb, int n_gt, int64_t n_chunks,
+           unsigned char *__restrict__ img)
+{
+    extern __shared__ __align__(16) unsigned char sm[];  // GT_QUAD x 48 KB
+    const int64_t kc = blockIdx.x;
+    const int gt0 = blockIdx.y * GT_QUAD;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint4 *sm4 = reinterpret_cast<uint4 *>(sm);
+    for (int i = tid; i < GT_QUAD * GT_TILE_BYTES / 16; i += blockDim.x)
+        sm4[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const int blk0 = gt0 * (GT_M / 64);
+    int blk1 = (gt0 + GT_QUAD) * (GT_M / 64);
+    if (blk1 > nb)
+        blk1 = nb;
+    const double scale = (double)(1 << GT_SCALE_BITS);
+    for (int cc = w; cc < GT_KC; cc += 8) {
+        const int64_t c = kc * GT_KC + cc;
+        if (c >= n_cells)
+            break;
+        const uint16_t *bp = bptr + c * (nb + 1);
+        const int64_t base = hptr[c];
+        const int e0 = bp[blk0], e1 = bp[blk1];
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int s = hslot[base + e];
+            double qd = rint(hval[base + e] * scale);
+            if (qd > 16777215.0)
+                qd = 16777215.0;
+            const uint32_t q = (uint32_t)qd;
+            const int lt = s / GT_M - gt0, row = s % GT_M;
+            unsigned char *t = sm + (size_t)lt * GT_TILE_BYTES + swz_offset(row, cc);
+            t[0] = (unsigned char)(q & 255u);
+            t[GT_PLANE_BYTES] = (unsigned char)((q >> 8) & 255u);
+            t[2 * GT_PLANE_BYTES] = (unsigned char)(q >> 16);
+        }
+    }
+    __syncthreads();
+    for (int lt = 0; lt < GT_QUAD; ++lt) {
+        if (gt0 + lt >= n_gt)
+            break;
+        uint4 *dst = reinterpret_cast<uint4 *>(img + ((size_t)(gt0 + lt) * n_chunks + kc) * GT_TILE_BYTES);
+        const uint4 *src = reinterpret_cast<const uint4 *>(sm + (size_t)lt * GT_TILE_BYTES);
+        for (int i = tid; i < GT_TILE_BYTES / 16; i += blockDim.x)
+            dst[i] = src[i];
+    }
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int H, double *__restrict__ gram,
+          int *__restrict__ err_flag)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)GT_STAGES * GT_STAGE_BYTES);
+    uint64_t *full = bars;                 // [GT_STAGES]
+    uint64_t *empty = bars + GT_STAGES;    // [GT_STAGES]
+    uint64_t *tfull = bars + 2 * GT_STAGES;
+    uint64_t *tempty = tfull + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 1);
+
+    // tile (I, J): 128 rows starting at I*128, 64 columns starting at J*64, J*64 >= I*128
+    const int n_gn = n_gt * (GT_M / GT_N);
+    int I = 0, rem = blockIdx.x;
+    while (rem >= n_gn - 2 * I) {
+        rem -= n_gn - 2 * I;
+        ++I;
+    }
+    const int J = 2 * I + rem;
+    const int gtB = J / 2, halfB = J & 1;
+    const int64_t per = (n_chunks + gridDim.y - 1) / gridDim.y;
+    const int64_t kc0 = (int64_t)blockIdx.y * per;
+    const int64_t kc1 = kc0 + per < n_chunks ? kc0 + per : n_chunks;
+    const int64_t nk = kc1 > kc0 ? kc1 - kc0 : 0;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < GT_STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0)
+        tmem_alloc(tmem_slot, GT_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_flush = (nk + GT_FLUSH_CHUNKS - 1) / GT_FLUSH_CHUNKS;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int64_t t = 0; t < nk; ++t) {
+                const int s = (int)(t % GT_STAGES);
+                const uint32_t ph = (uint32_t)((t / GT_STAGES) & 1);
+                mbar_wait(empty + s, ph ^ 1u, err_flag);
+                mbar_expect_tx(full + s, GT_STAGE_BYTES);
+                unsigned char *st = smem + (size_t)s * GT_STAGE_BYTES;
+                const unsigned char *a = img + ((size_t)I * n_chunks + (kc0 + t)) * GT_TILE_BYTES;
+                const unsigned char *b = img + ((size_t)gtB * n_chunks + (kc0 + t)) * GT_TILE_BYTES + halfB * GT_B_BYTES;
+                bulk_g2s(st, a, GT_TILE_BYTES, full + s);
+#pragma unroll
+                for (int p = 0; p < GT_PLANES; ++p)
+                    bulk_g2s(st + GT_TILE_BYTES + p * GT_B_BYTES, b + (size_t)p * GT_PLANE_BYTES, GT_B_BYTES, full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int64_t f = 0; f < n_flush; ++f) {
+                // the flush warps must have drained the accumulators of the previous period
+                mbar_wait(tempty, (uint32_t)((f & 1) ^ 1), err_flag);
+                tc_fence_after();
+                uint32_t accf[GT_ORDERS];
+#pragma unroll
+                for (int o = 0; o < GT_ORDERS; ++o)
+                    accf[o] = 0;
+                const int64_t t0 = f * GT_FLUSH_CHUNKS;
+                const int64_t t1 = t0 + GT_FLUSH_CHUNKS < nk ? t0 + GT_FLUSH_CHUNKS : nk;
+                for (int64_t t = t0; t < t1; ++t) {
+                    const int s = (int)(t % GT_STAGES);
+                    const uint32_t ph = (uint32_t)((t / GT_STAGES) & 1);
+                    mbar_wait(full + s, ph, err_flag);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * GT_STAGE_BYTES);
+                    const uint32_t sb = sa + GT_TILE_BYTES;
+#pragma unroll
+                    for (int p = 0; p < GT_PLANES; ++p) {
+#pragma unroll
+                        for (int q = 0; q < GT_PLANES; ++q) {
+#pragma unroll
+                            for (int kk = 0; kk < GT_KC / 32; ++kk) {
+                                umma_i8(tmem_base + (uint32_t)((p + q) * GT_N),
+                                        make_desc(sa + p * GT_PLANE_BYTES + kk * 32),
+                                        make_desc(sb + q * GT_B_BYTES + kk * 32), GT_IDESC, accf[p + q]);
+                                accf[p + q] = 1;
+                            }
+                        }
+                    }
+                    umma_commit(empty + s);
+                }
+                umma_commit(tfull);
+            }
+        }
+    } else {
+        // ===== flush: thread = output row; fp64 combination of the five exact integer sums =====
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int grow = I * GT_M + row;
+        const double unscale = 1.0 / ((double)(1 << GT_SCALE_BITS) * (double)(1 << GT_SCALE_BITS));
+        for (int64_t f = 0; f < n_flush; ++f) {
+            mbar_wait(tfull, (uint32_t)(f & 1), err_flag);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < GT_N / 32; ++half) {
+                double acc[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    acc[c] = 0.0;
+#pragma unroll
+                for (int o = 0; o < GT_ORDERS; ++o) {
+                    uint32_t r[32];
+                    tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(o * GT_N + half * 32), r);
+                    tmem_ld_wait();
+                    const double wgt = (double)(1ull << (8 * o));  // 2^(8 o)
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        acc[c] += (double)(int)r[c] * wgt;
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int gcol = J * GT_N + half * 32 + c;
+                    if (grow < H && gcol < H && gcol >= grow && acc[c] != 0.0)
+                        atomicAdd(gram + (int64_t)grow * H + gcol, acc[c] * unscale);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        tmem_dealloc(tmem_base, GT_TMEM_COLS);
+}
+
+// Adds the local X^T X (upper triangle) of the HVG sub-matrix held by the context into ctx->gram,
+// which the caller has zeroed.  Returns 1 in *used when the tensor-core path applied (all values
+// below 32), 0 when the caller has to use the fp64 kernels instead.
+int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used)
+{
+    *used = 0;
+    const int H = ctx->H;
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, sizeof(unsigned long long), ctx->stream));
+    if (ctx->nnz_hvg > 0) {
+        k_gram_maxval<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->hval.p, ctx->nnz_hvg, ctx->maxnrm.p);
+        CB_LAUNCH(ctx);
+    }
+    unsigned long long bits = 0;
+    CB_CUDA(ctx, cudaMemcpyAsync(&bits, ctx->maxnrm.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double mx;
+    memcpy(&mx, &bits, sizeof(double));
+    if (!(mx < 31.99))
+        return 0;  // outside the fixed-point range: fp64 path
+    const int n_gt = (H + GT_M - 1) / GT_M;
+    const int64_t n_chunks = (ctx->N + GT_KC - 1) / GT_KC;
+    CB_CUDA(ctx, ctx->gram_img.ensure((size_t)n_gt * n_chunks * GT_TILE_BYTES));
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_img, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GT_QUAD * GT_TILE_BYTES));
+    dim3 igrid((unsigned)n_chunks, (unsigned)((n_gt + GT_QUAD - 1) / GT_QUAD));
+    k_gram_img<<<igrid, 256, GT_QUAD * GT_TILE_BYTES, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p,
+                                                                      ctx->hbptr.p, ctx->N, nb, n_gt, n_chunks,
+                                                                      ctx->gram_img.p);
+    CB_LAUNCH(ctx);
+
+    const int n_gn = n_gt * (GT_M / GT_N);
+    int n_pairs = 0;
+    for (int i = 0; i < n_gt; ++i)
+        n_pairs += n_gn - 2 * i;
+    // enough CTAs to fill the machine a few times, but at least ~32 chunks per CTA
+    int64_t ksplit = (6LL * ctx->num_sms + n_pairs - 1) / n_pairs;
+    const int64_t max_split = (n_chunks + 31) / 32;
+    if (ksplit > max_split)
+        ksplit = max_split;
+    if (ksplit < 1)
+        ksplit = 1;
+    const size_t smem = (size_t)GT_STAGES * GT_STAGE_BYTES + (2 * GT_STAGES + 2) * 8 + 16;
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
+    dim3 grid((unsigned)n_pairs, (unsigned)ksplit);
+    k_gram_tc<<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, ctx->gram.p, ctx->flag.p + 3);
+    CB_LAUNCH(ctx);
+    int h_flag = 0;
+    CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, ctx->flag.p + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_CHECK(ctx, (h_flag & 4) == 0, "cb200_pca: tensor-core cross-product kernel timed out on a barrier");
+    *used = 1;
+    return 0;
+}

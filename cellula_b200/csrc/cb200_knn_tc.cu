@@ -29,6 +29,9 @@
 
 #include "cb200_common.cuh"
 #include "cb200_knn_tc.cuh"
+#include "cb200_tc.cuh"
+
+using namespace cb200tc;
 
 namespace {
 
@@ -41,117 +44,9 @@ constexpr int TC_TILE_BYTES = 2 * TC_PART_BYTES; // hi + lo
 // SETS epilogue warp sets of 4 warps each, one per TMEM accumulator stage (SETS x 128 columns)
 __host__ __device__ constexpr int tc_threads(int sets) { return 64 + sets * 128; }
 
-__host__ __device__ inline uint32_t swz_offset(int row, int kbyte)
-{
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((kbyte >> 4) ^ (row & 7)) & 7) << 4) + (kbyte & 15));
-}
-
-// ---- PTX wrappers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded wait: a protocol error must fault, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err_flag)
-{
-    const uint32_t addr = smem_u32(bar);
-    for (uint32_t spin = 0;; ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin
-            : "memory");
-        if (ok)
-            return;
-        if (spin > (1u << 20)) {
-            atomicOr(err_flag, 4);
-            __threadfence();
-            asm volatile("trap;");
-        }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B
-// between 8-row groups | version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=b=F16 (0), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-
-// asynchronous TMEM -> register load of 32 consecutive fp32 columns of this thread's lane;
-// the registers are valid after tmem_ld_wait()
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // fp64 coordinate (already scaled) -> (hi, lo) fp16 pair
 __device__ __forceinline__ void split_h(double x, __half &hi, __half &lo)
@@ -449,18 +344,14 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     }
                 }
             };
-            // two register buffers: the TMEM load of the next chunk is in flight while one is scanned
-            uint32_t ra[32], rb[32];
-            tmem_ld32_issue(tcol, ra);
+            // one register buffer: a second one (load of chunk ch+1 in flight while ch is scanned) was
+            // measured 2.4x slower -- the doubled slow-path code thrashes the instruction cache
+            uint32_t ra[32];
 #pragma unroll 1
-            for (int p2 = 0; p2 < TC_N / 64; ++p2) {
+            for (int ch = 0; ch < TC_N / 32; ++ch) {
+                tmem_ld32_issue(tcol + (uint32_t)(ch * 32), ra);
                 tmem_ld_wait();
-                tmem_ld32_issue(tcol + (uint32_t)(p2 * 64 + 32), rb);
-                scan_chunk(ra, r0 + p2 * 64);
-                tmem_ld_wait();
-                if (p2 + 1 < TC_N / 64)
-                    tmem_ld32_issue(tcol + (uint32_t)((p2 + 1) * 64), ra);
-                scan_chunk(rb, r0 + p2 * 64 + 32);
+                scan_chunk(ra, r0 + ch * 32);
             }
             tc_fence_before();
             __syncwarp();

@@ -18,6 +18,8 @@
 
 #include "cb200_common.cuh"
 
+int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used);  // cb200_gram_tc.cu
+
 // ---------------------------------------------------------------------------------------
 // K5a: HVG sub-matrix extraction
 // ---------------------------------------------------------------------------------------
@@ -851,8 +853,16 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
 
     cb_stage_begin(ctx, ST_GRAM);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->gram.p, 0, (size_t)H * H * sizeof(double), ctx->stream));
+    // engine: tensor cores (error-free int8 digit products) by default; CB200_GRAM_ENGINE=tiled|atomic
+    // selects the exact fp64 kernels (also used when a value is outside the fixed-point range)
     const char *geng = getenv("CB200_GRAM_ENGINE");
-    if (geng != nullptr && strcmp(geng, "atomic") == 0) {
+    int used_tc = 0;
+    if ((geng == nullptr && ctx->N >= 1024) || (geng != nullptr && strcmp(geng, "tc") == 0))
+        CB_TRY(cb200_gram_tc(ctx, nb, &used_tc));
+    ctx->tm.gram_engine = used_tc ? 3 : ((geng != nullptr && strcmp(geng, "atomic") == 0) ? 1 : 2);
+    if (used_tc) {
+        // done
+    } else if (geng != nullptr && strcmp(geng, "atomic") == 0) {
         // v1 (kept as a cross-check): one fp64 L2 reduction per product
         k_gram_sparse<<<grid, 256, 0, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p, ctx->N, H, ctx->gram.p);
         CB_LAUNCH(ctx);

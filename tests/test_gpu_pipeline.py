@@ -29,7 +29,7 @@ def test_api_end_to_end_against_oracle(small_counts, small_oracle):
     sign = np.sign(np.sum(np.asarray(pca) * want, axis=0))
     err = np.abs(np.asarray(pca) * sign - want).max(axis=0) / np.abs(want).max(axis=0)
     assert err.max() <= 1e-4
-    assert np.allclose(pca.attrs["percentVar"], ref["pca"]["percent_var"], rtol=1e-7)
+    assert np.allclose(pca.attrs["percentVar"], ref["pca"]["percent_var"], rtol=1e-6)
 
     sce = cb.makeGraphsAndClusters(sce, neighbors=10, weighting_scheme="rank", ndims=20, save_graphs=True)
     g = sce.metadata["SNN_10_rank"]
@@ -108,7 +108,7 @@ def test_cfg2_sized_properties(gpu_ctx):
     pca = gpu_ctx.pca(hv, nd)
     sc = pca["scores"]
     assert np.allclose(sc.mean(axis=0), 0, atol=1e-9 * np.abs(sc).max())
-    assert np.allclose(sc.var(axis=0, ddof=1), pca["var_explained"], rtol=1e-8)
+    assert np.allclose(sc.var(axis=0, ddof=1), pca["var_explained"], rtol=1e-6)
     gram = sc.T @ sc                                                  # scores are orthogonal (U D)
     off = gram - np.diag(np.diag(gram))
     assert np.abs(off).max() <= 1e-6 * np.diag(gram).max()
