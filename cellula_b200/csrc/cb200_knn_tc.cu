@@ -178,7 +178,7 @@ template <int KP, int SETS, int STAGES>
 __global__ void __launch_bounds__(tc_threads(SETS), 1)
 k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, const unsigned char *__restrict__ img,
                int64_t n, int64_t q_begin, int64_t q_end, float key_unscale, int32_t *__restrict__ cand_idx,
-               float *__restrict__ cand_tau, int *__restrict__ err_flag)
+               float *__restrict__ cand_tau, int *__restrict__ err_flag, int mode)
 {
     constexpr int EPL = KP / 32;
     constexpr int TC_SETS = SETS, TC_ACC_STAGES = SETS, TC_THREADS = tc_threads(SETS);
@@ -194,6 +194,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     uint64_t *tfull = bars + 2 * STAGES;         // [TC_ACC_STAGES]
     uint64_t *tempty = tfull + TC_ACC_STAGES;    // [TC_ACC_STAGES]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + TC_ACC_STAGES);
+    float *thr_sh = reinterpret_cast<float *>(tmem_slot + 4);  // [SETS][TC_M] thresholds published by the sets
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q0 = q_begin + (int64_t)blockIdx.x * TC_M;
@@ -224,6 +225,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         lkey[i] = FLT_MAX;
         lidx[i] = 0x7fffffff;
     }
+    for (int i = tid; i < TC_SETS * TC_M; i += TC_THREADS)
+        thr_sh[i] = -FLT_MAX;
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full + s, 1);
@@ -299,6 +302,14 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             mbar_wait(tfull + set, aph, err_flag);
             tc_fence_after();
             const int64_t r0 = t * TC_N;
+            // A reference that does not beat the 32nd best of ANY set cannot be among the 32 best
+            // overall: take the tightest threshold any set has published for this row (stale reads
+            // only cost extra hits; the union of the per-set lists still holds the global top 32).
+            if (thr != FLT_MAX) {
+#pragma unroll
+                for (int s2 = 0; s2 < TC_SETS; ++s2)
+                    thr = fmaxf(thr, thr_sh[s2 * TC_M + row]);
+            }
             // Scan of 32 accumulator columns held in registers.  Fast path: 3-input max tree + one
             // vote.  Slow path (some lane beats its threshold): 32 independent ballots give the hit
             // lanes of every column; each hit is inserted into its row's sorted list by the whole
@@ -316,7 +327,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     g[j] = fmaxf(fmaxf(a0, a1), a2);
                 }
                 const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-                if (!__any_sync(0xffffffffu, m > thr))
+                if (!__any_sync(0xffffffffu, m > thr) || (mode & 8))
                     return;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -333,12 +344,14 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                             const float othr = __shfl_sync(0xffffffffu, thr, owner);
                             const int64_t gcol = c0 + i;
                             const int64_t og = q0 + quarter * 32 + owner;
-                            if (val > othr && gcol < n && gcol != og) {
+                            if (val > othr && gcol < n && gcol != og && !(mode & 16)) {
                                 const float kth = tc_insert<EPL>(set_key + (size_t)(quarter * 32 + owner) * KP,
                                                                  set_idx + (size_t)(quarter * 32 + owner) * KP, -val,
                                                                  (int)gcol, lane);
-                                if (lane == owner)
-                                    thr = (kth == FLT_MAX) ? -FLT_MAX : -kth;
+                                if (lane == owner && kth != FLT_MAX) {
+                                    thr = fmaxf(thr, -kth);
+                                    thr_sh[set * TC_M + row] = -kth;
+                                }
                             }
                         }
                     }
@@ -348,10 +361,13 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             // measured 2.4x slower -- the doubled slow-path code thrashes the instruction cache
             uint32_t ra[32];
 #pragma unroll 1
-            for (int ch = 0; ch < TC_N / 32; ++ch) {
-                tmem_ld32_issue(tcol + (uint32_t)(ch * 32), ra);
-                tmem_ld_wait();
-                scan_chunk(ra, r0 + ch * 32);
+            for (int ch = 0; ch < ((mode & 2) ? 2 : TC_N / 32); ++ch) {
+                if (!(mode & 4)) {
+                    tmem_ld32_issue(tcol + (uint32_t)(ch * 32), ra);
+                    tmem_ld_wait();
+                }
+                if (!(mode & 1))
+                    scan_chunk(ra, r0 + ch * 32);
             }
             tc_fence_before();
             __syncwarp();
@@ -387,7 +403,7 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
                      int64_t q_end)
 {
     const size_t smem = (size_t)TC_TILE_BYTES * (1 + STAGES) + (size_t)SETS * TC_M * KP * 8 +
-                        (size_t)(2 * STAGES + 2 * SETS) * 8 + 16;
+                        (size_t)(2 * STAGES + 2 * SETS) * 8 + 16 + (size_t)SETS * TC_M * 4;
     CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, SETS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     const int64_t nq = q_end - q_begin;
@@ -395,7 +411,7 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
     const float key_unscale = (float)(1.0 / (scale * scale));
     k_knn_tiles_tc<KP, SETS, STAGES><<<grid, tc_threads(SETS), smem, ctx->stream>>>(
         E, lde, d, scale, ctx->knn_img.p, n, q_begin, q_end, key_unscale, ctx->cand_idx.p, ctx->cand_tau.p,
-        ctx->flag.p + 3);
+        ctx->flag.p + 3, getenv("CB200_TC_MODE") ? atoi(getenv("CB200_TC_MODE")) : 0);
     CB_LAUNCH(ctx);
     return 0;
 }
