@@ -239,8 +239,7 @@ def main():
             ctx.load_csc_ptrs(w["genes"], n_local, nnz, colptr_h.data_ptr(), rowidx_h.data_ptr(), x_h.data_ptr(),
                               cell_offset=c0, n_cells_total=w["cells"])
             r = pipe.run(ndims=w["ndims"], hvg_ntop=HVG_NTOP, neighbors=w["k"], snn_type=w["scheme"], want_host=True,
-                         scores_out=scores_np, edge_buffers=edge_buffers)
-            ctx.fetch_logcounts(logx_h.numpy())
+                         scores_out=scores_np, edge_buffers=edge_buffers, logx_out=logx_h.numpy())
             knn_h.copy_(r["knn_full"][c0:c1], non_blocking=False)
             knn_local = knn_h
             f, t, wt = r["edges"]

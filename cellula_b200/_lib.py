@@ -56,6 +56,8 @@ SIGNATURES = {
     "cb200_lognorm_genestats_local": (c_int, [c_vp]),
     "cb200_genestats_finish": (c_int, [c_vp, c_vp, c_vp]),
     "cb200_fetch_logcounts": (c_int, [c_vp, c_vp]),
+    "cb200_fetch_logcounts_async": (c_int, [c_vp, c_vp]),
+    "cb200_wait_copies": (c_int, [c_vp]),
     "cb200_lognorm_genestats": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cb200_pca_gram_local": (c_int, [c_vp, c_vp, c_int]),
     "cb200_pca_finish": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -250,6 +252,12 @@ class Context:
         out = np.empty(self.nnz) if out is None else out
         self._ck(lib().cb200_fetch_logcounts(self._h, _ptr(out)))
         return out
+
+    def fetch_logcounts_async(self, out):
+        self._ck(lib().cb200_fetch_logcounts_async(self._h, _ptr(out)))
+
+    def wait_copies(self):
+        self._ck(lib().cb200_wait_copies(self._h))
 
     # -- a7 -------------------------------------------------------------------------
     def pca(self, hvg_idx, d, want_scores=True, scores_out=None):

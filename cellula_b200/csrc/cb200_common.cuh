@@ -66,6 +66,8 @@ struct cb200_ctx {
     int num_sms = CB200_NUM_SM_FALLBACK;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // asynchronous result copies (cb200_fetch_logcounts_async)
+    cudaEvent_t copy_event = nullptr;
     std::string err;
 
     // ---- a1: counts shard (CSC, genes x local cells)

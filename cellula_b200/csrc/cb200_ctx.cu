@@ -106,6 +106,11 @@ extern "C" int cb200_free(cb200_ctx *ctx)
         cudaEventDestroy(ctx->ev[s][0]);
         cudaEventDestroy(ctx->ev[s][1]);
     }
+    if (ctx->copy_stream != nullptr) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        cudaEventDestroy(ctx->copy_event);
+    }
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -261,6 +261,36 @@ extern "C" int cb200_fetch_logcounts(cb200_ctx *ctx, double *logx_out)
     return 0;
 }
 
+// Asynchronous variant: the copy runs on the context's copy stream behind the kernel that produced
+// the logcounts, so it overlaps the following stages (PCA, kNN, SNN).  logx_out should be pinned.
+// cb200_wait_copies() blocks until it has landed.
+extern "C" int cb200_fetch_logcounts_async(cb200_ctx *ctx, double *logx_out)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->have_logx, "cb200_fetch_logcounts_async: logcounts have not been computed");
+    CB_CHECK(ctx, logx_out != nullptr, "cb200_fetch_logcounts_async: NULL output");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->copy_stream == nullptr) {
+        CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+    }
+    CB_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->stream));
+    CB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+    CB_CUDA(ctx, cudaMemcpyAsync(logx_out, ctx->logx.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->copy_stream));
+    return 0;
+}
+
+extern "C" int cb200_wait_copies(cb200_ctx *ctx)
+{
+    if (ctx == nullptr)
+        return 1;
+    if (ctx->copy_stream != nullptr)
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return 0;
+}
+
 extern "C" int cb200_lognorm_genestats(cb200_ctx *ctx, double *logx_out, double *gene_mean, double *gene_var)
 {
     if (ctx == nullptr)

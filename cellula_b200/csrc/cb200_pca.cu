@@ -963,7 +963,8 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
     CB_TRY(chol_qr(ctx, Y2, H, b, Q));
 
     const int max_outer = 300;
-    const double tol = 1e-9;
+    const double tol = 2e-9;
+    int degree = 3;  // Chebyshev filter degree between Rayleigh-Ritz steps
     std::vector<double> th((size_t)b), res((size_t)b);
     int it = 0;
     bool converged = false;
@@ -993,7 +994,7 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
             converged = true;
             break;
         }
-        // degree-2 Chebyshev filter damping [0, cut]; cut = smallest Ritz value of the block
+        // Chebyshev filter (degree 3, or 2) damping [0, cut]; cut = smallest Ritz value of the block
         double cut = th[b - 1];
         if (!(cut > 1e-12 * th[0]))
             cut = 1e-12 * th[0];
@@ -1003,10 +1004,27 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
         CB_LAUNCH(ctx);
         // X2 = 2 (C X1 - c X1)/e - Q -> Q buffer
         CB_TRY(launch_gemm(ctx, H, b, H, C, H, 1, W, b, 1, 2.0 / ee, W, -2.0 * cc / ee, Y1, -1.0, Q, b));
-        k_colnorm_scale<<<b, 256, 0, ctx->stream>>>(Q, H, b);
+        double *filtered = Q;
+        if (degree >= 3) {
+            // X3 = 2 (C X2 - c X2)/e - X1 -> Y2 buffer (C Q is no longer needed)
+            CB_TRY(launch_gemm(ctx, H, b, H, C, H, 1, Q, b, 1, 2.0 / ee, Q, -2.0 * cc / ee, W, -1.0, Y2, b));
+            filtered = Y2;
+        }
+        k_colnorm_scale<<<b, 256, 0, ctx->stream>>>(filtered, H, b);
         CB_LAUNCH(ctx);
-        CB_TRY(chol_qr(ctx, Q, H, b, W));
+        CB_TRY(chol_qr(ctx, filtered, H, b, W));
         CB_TRY(chol_qr(ctx, W, H, b, Q));
+        if (degree >= 3) {
+            // a floored Cholesky pivot means the degree-3 block was too ill-conditioned for
+            // Cholesky-QR: continue with the gentler degree-2 filter
+            int h_piv = 0;
+            CB_CUDA(ctx, cudaMemcpyAsync(&h_piv, ctx->flag.p + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h_piv != 0) {
+                degree = 2;
+                CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 1, 0, sizeof(int), ctx->stream));
+            }
+        }
     }
     ctx->tm.eig_iterations = it + (converged ? 1 : 0);
     // Ritz vectors of the last Rayleigh-Ritz step are in Y1, values in th

@@ -85,6 +85,12 @@ class CudaShard:
     def logcounts(self, out=None):
         return self.ctx.fetch_logcounts(out)
 
+    def logcounts_async(self, out):
+        self.ctx.fetch_logcounts_async(out)
+
+    def wait_copies(self):
+        self.ctx.wait_copies()
+
     # K5
     def gram(self, hvg_idx):
         self.ctx.pca_gram_local(hvg_idx)
@@ -176,17 +182,22 @@ class ShardedPipeline:
         return self.shard.snn(knn_full, snn_type, self.c0, self.c1, fetch=False)
 
     def run(self, ndims=50, hvg_ntop=2000, neighbors=20, snn_type="rank", sf_in=None, want_host=True,
-            scores_out=None, edge_buffers=None):
+            scores_out=None, edge_buffers=None, logx_out=None):
         """The whole path for this rank's shard.  Returns host results of the shard.
         scores_out: optional column-major (n_local x ndims) host array (e.g. pinned) for the scores;
-        edge_buffers: optional callable n_edges -> (from, to, weight) host arrays to fill."""
+        edge_buffers: optional callable n_edges -> (from, to, weight) host arrays to fill;
+        logx_out: optional pinned array for the logcounts, copied out behind the following stages."""
         sf = self.size_factors(sf_in, want=want_host)
         mean, var = self.gene_stats()
+        if logx_out is not None:
+            self.shard.logcounts_async(logx_out)            # overlaps the trend fit, PCA, kNN and SNN
         stats = trendvar.model_gene_var(mean, var)          # replicated host step (R: scran::fitTrendVar)
         hvgs = trendvar.get_top_hvgs(stats, hvg_ntop)
         pca = self.pca(hvgs, ndims, want_scores=want_host, scores_out=scores_out if want_host else None)
         knn_full = self.knn(pca["scores_full_dev"], neighbors)
         # (from, to, w), or the count if resident
         edges = self.snn(knn_full, snn_type, fetch=want_host, edge_buffers=edge_buffers)
+        if logx_out is not None:
+            self.shard.wait_copies()
         return dict(sf=sf, mean=mean, var=var, stats=stats, hvgs=hvgs, pca=pca, knn_full=knn_full,
                     edges=edges)

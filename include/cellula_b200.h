@@ -126,6 +126,10 @@ int cb200_lognorm_genestats_local(cb200_ctx *ctx);
 int cb200_genestats_finish(cb200_ctx *ctx, double *gene_mean /* nullable [G] */,
                            double *gene_var /* nullable [G] */);
 int cb200_fetch_logcounts(cb200_ctx *ctx, double *logx_out /* [nnz_local] */);
+/* Same copy issued on the context's copy stream so that it overlaps the following stages;
+ * logx_out should be page-locked.  cb200_wait_copies blocks until such copies have landed. */
+int cb200_fetch_logcounts_async(cb200_ctx *ctx, double *logx_out /* [nnz_local] */);
+int cb200_wait_copies(cb200_ctx *ctx);
 int cb200_lognorm_genestats(cb200_ctx *ctx, double *logx_out /* nullable */, double *gene_mean,
                             double *gene_var);
 
