@@ -1,0 +1,151 @@
+// cb200_host.cu -- host-side helper of the Python mirror (no device code): the weighted lowess
+// that scran::fitTrendVar runs on the per-gene (mean, log-variance residual) points.  In the R
+// product this stays limma::weightedLowess inside the unchanged scran call; the Python mirror
+// (cellula_b200/trendvar.py) has no R and would otherwise spend ~0.2 s per call in interpreted loops.
+// Same algorithm as trendvar.py's reference loops: local linear fits at ~npts seed points over the
+// sorted x, window = nearest points holding span * total weight, tricube kernel, bisquare
+// robustness iterations, linear interpolation between the seeds.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+#include "../../include/cellula_b200.h"
+
+static double weighted_median(const std::vector<double> &x, const double *w, std::vector<int> &order)
+{
+    const int n = (int)x.size();
+    order.resize(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return x[a] < x[b]; });
+    double total = 0.0;
+    for (int i = 0; i < n; ++i)
+        total += w[order[i]];
+    const double half = 0.5 * total;
+    double cw = 0.0;
+    for (int i = 0; i < n; ++i) {
+        cw += w[order[i]];
+        if (cw >= half) {
+            if (cw == half && i + 1 < n)
+                return 0.5 * (x[order[i]] + x[order[i + 1]]);
+            return x[order[i]];
+        }
+    }
+    return x[order[n - 1]];
+}
+
+// xs must be sorted ascending.  fitted_out[n].  Returns 0.
+extern "C" int cb200_host_weighted_lowess(int64_t n64, const double *xs, const double *ys, const double *ws, double span,
+                                          int iterations, int npts, double *fitted_out)
+{
+    const int n = (int)n64;
+    if (n < 1 || xs == nullptr || ys == nullptr || ws == nullptr || fitted_out == nullptr)
+        return 1;
+    const double delta = (xs[n - 1] - xs[0]) / npts;
+    std::vector<int> seeds(1, 0);
+    for (int i = 1; i < n - 1; ++i)
+        if (xs[i] - xs[seeds.back()] > delta)
+            seeds.push_back(i);
+    if (n > 1)
+        seeds.push_back(n - 1);
+    const int ns = (int)seeds.size();
+    double total = 0.0;
+    for (int i = 0; i < n; ++i)
+        total += ws[i];
+    const double target = span * total;
+    std::vector<int> lo(ns), hi(ns);
+    std::vector<double> dist(ns);
+    for (int q = 0; q < ns; ++q) {
+        const int s = seeds[q];
+        int l = s, h = s;
+        double acc = ws[s];
+        while (acc < target && (l > 0 || h < n - 1)) {
+            const bool go_left = h == n - 1 || (l > 0 && xs[s] - xs[l - 1] < xs[h + 1] - xs[s]);
+            if (go_left)
+                acc += ws[--l];
+            else
+                acc += ws[++h];
+        }
+        const double d = std::max(xs[s] - xs[l], xs[h] - xs[s]);
+        while (l > 0 && xs[s] - xs[l - 1] <= d)
+            --l;
+        while (h < n - 1 && xs[h + 1] - xs[s] <= d)
+            ++h;
+        lo[q] = l;
+        hi[q] = h + 1;
+        dist[q] = d;
+    }
+    std::vector<double> rob(n, 1.0), sv(ns), res(n);
+    std::vector<int> order;
+    for (int i = 0; i < n; ++i)
+        fitted_out[i] = ys[i];
+    for (int it = 0; it < iterations; ++it) {
+        for (int q = 0; q < ns; ++q) {
+            const int s = seeds[q];
+            const double d = dist[q];
+            double tw = 0.0, sx = 0.0, sy = 0.0;
+            for (int i = lo[q]; i < hi[q]; ++i) {
+                double k = ws[i] * rob[i];
+                if (d > 0.0) {
+                    const double u = std::fabs(xs[i] - xs[s]) / d;
+                    const double t = 1.0 - u * u * u;
+                    k *= (u < 1.0) ? t * t * t : 0.0;
+                }
+                tw += k;
+                sx += k * xs[i];
+                sy += k * ys[i];
+            }
+            if (!(tw > 0.0)) {
+                sv[q] = ys[s];
+                continue;
+            }
+            const double xm = sx / tw, ym = sy / tw;
+            double sxx = 0.0, sxy = 0.0;
+            for (int i = lo[q]; i < hi[q]; ++i) {
+                double k = ws[i] * rob[i];
+                if (d > 0.0) {
+                    const double u = std::fabs(xs[i] - xs[s]) / d;
+                    const double t = 1.0 - u * u * u;
+                    k *= (u < 1.0) ? t * t * t : 0.0;
+                }
+                const double dx = xs[i] - xm;
+                sxx += k * dx * dx;
+                sxy += k * dx * (ys[i] - ym);
+            }
+            if (sxx < 1e-12 * std::max(d * d, 1e-300) * tw)
+                sv[q] = ym;
+            else
+                sv[q] = ym + sxy / sxx * (xs[s] - xm);
+        }
+        // linear interpolation between the seeds (xs[seeds] is strictly increasing except for ties)
+        int q = 0;
+        for (int i = 0; i < n; ++i) {
+            while (q + 1 < ns - 1 && xs[i] > xs[seeds[q + 1]])
+                ++q;
+            const double x0 = xs[seeds[q]], x1 = xs[seeds[std::min(q + 1, ns - 1)]];
+            if (ns == 1 || x1 <= x0 || xs[i] <= x0)
+                fitted_out[i] = (xs[i] <= x0 || ns == 1) ? sv[q] : sv[std::min(q + 1, ns - 1)];
+            else if (xs[i] >= x1)
+                fitted_out[i] = sv[q + 1];
+            else
+                fitted_out[i] = sv[q] + (sv[q + 1] - sv[q]) * (xs[i] - x0) / (x1 - x0);
+        }
+        if (it == iterations - 1)
+            break;
+        double rmean = 0.0;
+        for (int i = 0; i < n; ++i) {
+            res[i] = std::fabs(ys[i] - fitted_out[i]);
+            rmean += res[i];
+        }
+        rmean /= n;
+        const double cmad = 6.0 * weighted_median(res, ws, order);
+        if (cmad <= 1e-12 * std::max(rmean, 1e-300))
+            break;
+        for (int i = 0; i < n; ++i) {
+            const double r = res[i] / cmad;
+            rob[i] = res[i] < cmad ? (1.0 - r * r) * (1.0 - r * r) : 0.0;
+        }
+    }
+    return 0;
+}

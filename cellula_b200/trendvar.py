@@ -107,12 +107,30 @@ def _wmedian(x, w):
     return x[o[i]]
 
 
+def _native_lowess():
+    """cb200_host_weighted_lowess from the shared library, or None when it has not been built."""
+    try:
+        from . import _lib
+        return _lib.lib().cb200_host_weighted_lowess
+    except Exception:
+        return None
+
+
 def _weighted_lowess(x, y, w, span=0.3, iterations=4, npts=200):
     """limma::weightedLowess: local linear fits at ~npts seeds over the sorted x, window =
     nearest points holding span * total weight, tricube kernel, bisquare robustness."""
     o = np.argsort(x, kind="stable")
-    xs, ys, ws = x[o], y[o], w[o]
+    xs, ys, ws = np.ascontiguousarray(x[o]), np.ascontiguousarray(y[o]), np.ascontiguousarray(w[o])
     n = xs.size
+    native = _native_lowess()
+    if native is not None:   # same algorithm in C++ (csrc/cb200_host.cu); the loops below are its definition
+        fitted = np.empty(n)
+        rc = native(n, xs.ctypes.data, ys.ctypes.data, ws.ctypes.data, float(span), int(iterations), int(npts),
+                    fitted.ctypes.data)
+        if rc == 0:
+            out = np.empty(n)
+            out[o] = fitted
+            return out
     delta = (xs[-1] - xs[0]) / npts
     seeds = [0]
     for i in range(1, n - 1):

@@ -194,6 +194,12 @@ int cb200_synth_counts(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, double 
                        int64_t *nnz_out);
 int cb200_export_csc(cb200_ctx *ctx, int64_t *colptr, int32_t *rowidx, double *values);
 
+/* ---- host-side helper of the Python mirror (no device work, not part of the reference FFI) ----
+ * limma::weightedLowess as scran::fitTrendVar uses it, on x sorted ascending.  The R package keeps
+ * calling scran/limma; cellula_b200/trendvar.py uses this instead of interpreted loops. */
+int cb200_host_weighted_lowess(int64_t n, const double *x_sorted, const double *y, const double *w, double span,
+                               int iterations, int npts, double *fitted_out);
+
 #ifdef __cplusplus
 }
 #endif
