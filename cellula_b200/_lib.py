@@ -32,7 +32,8 @@ class Timing(ctypes.Structure):
         "h2d_ms", "colsum_ms", "lognorm_ms", "hvg_extract_ms", "gram_ms", "eig_ms", "project_ms",
         "knn_prep_ms", "knn_tile_ms", "knn_rerank_ms", "snn_revlist_ms", "snn_edges_ms", "d2h_ms")] + [
         ("kernel_launches", c_i64), ("knn_fallback_queries", c_i64), ("eig_iterations", c_i64),
-        ("gram_engine", c_i64), ("knn_engine", c_i64)]
+        ("gram_engine", c_i64), ("knn_tiles_scanned", c_i64), ("knn_tiles_total", c_i64),
+        ("knn_engine", c_i64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -113,6 +113,10 @@ struct cb200_ctx {
     DevBuf<double> emb;        // [n_total*d] row-major fp64 (when given from host)
     DevBuf<double> stage_d;    // staging for column-major <-> row-major conversions
     DevBuf<float> emb_f;       // [n_total*DP] fp32 padded
+    DevBuf<int32_t> knn_perm, knn_bkt, knn_hist, knn_qlist, knn_qpos;  // PC-1 ordering of the references
+    DevBuf<unsigned long long> knn_cursor;
+    DevBuf<int64_t> knn_qoff;
+    DevBuf<float> knn_tile_lo, knn_tile_hi;  // PC-1 interval of every reference tile
     DevBuf<unsigned char> knn_img;  // tensor-core operand image of the references (cb200_knn_tc.cu)
     DevBuf<float> hnorm;       // [n_total]   0.5*|r|^2 (fp32)
     DevBuf<double> nrm2;       // [n_total]   |r|^2 (fp64)

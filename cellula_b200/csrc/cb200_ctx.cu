@@ -72,7 +72,7 @@ extern "C" int cb200_init(int device, void *stream, cb200_ctx **out)
     }
     memset(&ctx->tm, 0, sizeof(ctx->tm));
     if (ctx->part.ensure(2) != cudaSuccess || ctx->flag.ensure(4) != cudaSuccess ||
-        ctx->maxnrm.ensure(1) != cudaSuccess) {
+        ctx->maxnrm.ensure(4) != cudaSuccess) {
         delete ctx;
         return cb200_fail(nullptr, "cb200_init: device allocation failed");
     }
@@ -95,7 +95,9 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->mu.release(); ctx->eq.release(); ctx->ew.release(); ctx->ey.release(); ctx->ex.release();
     ctx->es.release(); ctx->et.release(); ctx->etheta.release(); ctx->eres.release();
     ctx->emuv.release(); ctx->rot.release(); ctx->scores.release(); ctx->varexp.release();
-    ctx->emb.release(); ctx->stage_d.release(); ctx->emb_f.release(); ctx->knn_img.release(); ctx->hnorm.release();
+    ctx->emb.release(); ctx->stage_d.release(); ctx->emb_f.release(); ctx->knn_img.release(); ctx->knn_perm.release(); ctx->knn_bkt.release(); ctx->knn_hist.release();
+    ctx->knn_qlist.release(); ctx->knn_qpos.release(); ctx->knn_cursor.release(); ctx->knn_qoff.release();
+    ctx->knn_tile_lo.release(); ctx->knn_tile_hi.release(); ctx->hnorm.release();
     ctx->nrm2.release(); ctx->maxnrm.release(); ctx->cand_idx.release(); ctx->cand_tau.release();
     ctx->knn.release(); ctx->knn_dk.release(); ctx->fb_list.release(); ctx->stage_i.release();
     ctx->index0.release(); ctx->rcnt.release(); ctx->rptr.release(); ctx->rcur.release();

@@ -265,8 +265,9 @@ template <int KP>
 __global__ void __launch_bounds__(256)
 k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, int64_t nq, int k,
              const int32_t *__restrict__ cand_idx, const float *__restrict__ cand_tau, int ntau, const double *__restrict__ nrm2,
-             const unsigned long long *__restrict__ maxbits, double err_coef, int32_t *__restrict__ knn,
-             double *__restrict__ knn_dk, int32_t *__restrict__ fb_list, int *__restrict__ fb_count)
+             const unsigned long long *__restrict__ maxbits, double err_coef, const int32_t *__restrict__ qlist,
+             int32_t *__restrict__ knn, double *__restrict__ knn_dk, int32_t *__restrict__ fb_list,
+             int *__restrict__ fb_count)
 {
     constexpr int EPL = KP / 32;
     const int lane = threadIdx.x & 31;
@@ -274,7 +275,9 @@ k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, 
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const double m2 = __longlong_as_double((long long)*maxbits);
     for (int64_t q = warp0; q < nq; q += nwarps) {
-        const int64_t grow = q_begin + q;
+        // q runs over the candidate records; the tensor-core engine orders them by PC 1 (qlist)
+        const int64_t grow = qlist != nullptr ? (int64_t)qlist[q] : q_begin + q;
+        const int64_t orow = grow - q_begin;   // row of the result
         const double *qa = E + grow * lde;
         double key[EPL];
         int idx[EPL];
@@ -294,7 +297,7 @@ k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, 
         for (int e = 0; e < EPL; ++e) {
             const int p = e * 32 + lane;
             if (p < k)
-                knn[q * k + p] = idx[e];
+                knn[orow * k + p] = idx[e];
         }
         // k-th exact distance sits at sorted position k-1
         double dk = 0.0;
@@ -305,7 +308,7 @@ k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, 
                 dk = v;
         }
         if (lane == 0) {
-            knn_dk[q] = dk;
+            knn_dk[orow] = dk;
             const double nq2 = nrm2[grow];
             const double ek = 0.5 * dk * dk - 0.5 * nq2;      // exact key of the k-th candidate
             const double bound = err_coef * (nq2 + m2);       // |approx key - exact key| <= bound
@@ -316,7 +319,7 @@ k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, 
             const bool proven = (tau == FLT_MAX) || (ek + bound < (double)tau - bound);
             if (!proven) {
                 const int pos = atomicAdd(fb_count, 1);
-                fb_list[pos] = (int32_t)q;
+                fb_list[pos] = (int32_t)orow;
             }
         }
     }
@@ -402,13 +405,13 @@ static int run_tiles_simt(cb200_ctx *ctx, int64_t n, int DP, int64_t q_begin, in
 
 template <int KP>
 static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int d, int k, int64_t q_begin,
-                      int64_t nq, double err_coef, int ntau)
+                      int64_t nq, double err_coef, int ntau, const int32_t *qlist)
 {
     cb_stage_begin(ctx, ST_KNN_RERANK);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 2, 0, sizeof(int), ctx->stream));
     const int rgrid = cb_grid_for(nq, 8, ctx->num_sms * 16);
     k_knn_rerank<KP><<<rgrid, 256, 0, ctx->stream>>>(E, lde, d, q_begin, nq, k, ctx->cand_idx.p, ctx->cand_tau.p,
-                                                     ntau, ctx->nrm2.p, ctx->maxnrm.p, err_coef, ctx->knn.p, ctx->knn_dk.p,
+                                                     ntau, ctx->nrm2.p, ctx->maxnrm.p, err_coef, qlist, ctx->knn.p, ctx->knn_dk.p,
                                                      ctx->fb_list.p, ctx->flag.p + 2);
     CB_LAUNCH(ctx);
     int h[2] = {0, 0};
@@ -416,6 +419,15 @@ static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, i
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     CB_CHECK(ctx, (h[1] & 4) == 0, "cb200_knn: tensor-core tile kernel timed out on a barrier (protocol error)");
     ctx->tm.knn_fallback_queries = h[0];
+    if (qlist != nullptr) {  // tensor-core engine: how much of the N x N tile grid survived the PC-1 pruning
+        unsigned long long done = 0;
+        CB_CUDA(ctx, cudaMemcpyAsync(&done, ctx->maxnrm.p + 3, sizeof(done), cudaMemcpyDeviceToHost, ctx->stream));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->tm.knn_tiles_scanned = (int64_t)done;
+        ctx->tm.knn_tiles_total = ((nq + 127) / 128) * ((n + 127) / 128);
+    } else {
+        ctx->tm.knn_tiles_scanned = ctx->tm.knn_tiles_total = ((nq + 127) / 128) * ((n + 127) / 128);
+    }
     if (h[0] > 0) {
         k_knn_exact<<<h[0], 256, 0, ctx->stream>>>(E, lde, d, n, q_begin, k, ctx->fb_list.p, ctx->knn_dk.p, ctx->knn.p,
                                                    ctx->flag.p + 3);
@@ -451,9 +463,10 @@ static int knn_core(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int
     const bool use_tc = !want_simt && cb200_knn_tc_supported(d, k);
     int KP = 0, ntau = 1;
     double err_coef = 0.0;
+    const int32_t *qlist = nullptr;  // order of the candidate records (tensor-core engine: sorted by PC 1)
     ctx->tm.knn_engine = use_tc ? 2 : 1;
     if (use_tc) {
-        CB_TRY(cb200_knn_tiles_tc(ctx, E, lde, n, d, k, q_begin, q_end, &KP, &ntau, &err_coef));
+        CB_TRY(cb200_knn_tiles_tc(ctx, E, lde, n, d, k, q_begin, q_end, &KP, &ntau, &qlist, &err_coef));
     } else {
         const int DP = (d + 3) & ~3;
         CB_CUDA(ctx, ctx->emb_f.ensure((size_t)n * DP));
@@ -479,11 +492,11 @@ static int knn_core(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int
         }
     }
     if (KP == 32)
-        CB_TRY(run_rerank<32>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau));
+        CB_TRY(run_rerank<32>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau, qlist));
     else if (KP == 64)
-        CB_TRY(run_rerank<64>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau));
+        CB_TRY(run_rerank<64>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau, qlist));
     else
-        CB_TRY(run_rerank<128>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau));
+        CB_TRY(run_rerank<128>(ctx, E, lde, n, d, k, q_begin, nq, err_coef, ntau, qlist));
     ctx->knn_nq = nq;
     ctx->knn_k = k;
     ctx->knn_ntotal = n;

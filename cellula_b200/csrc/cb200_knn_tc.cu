@@ -19,9 +19,18 @@
 // in HBM is stored tile by tile in exactly this layout (hi part then lo part, 32 KB per 128
 // points), so one cp.async.bulk moves a whole stage.
 //
-// Warp roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected lane),
-// warps 2-5 / 6-9 = two epilogue sets, one per TMEM accumulator stage (even / odd reference tiles);
-// within a set warp w owns TMEM lane quarter w % 4 and a thread is one query row.
+// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one elected lane), then SETS epilogue
+// sets of 4 warps, one per TMEM accumulator stage; within a set warp w owns TMEM lane quarter w % 4 and
+// a thread is one query row.
+//
+// Pruning (exact).  The points are ordered by their first coordinate (PC 1, the direction of largest
+// variance) with a counting sort, so a query tile is a narrow PC-1 interval and reference tile t covers
+// [lo_t, hi_t].  Since d(q, r) >= |q_1 - r_1|, a tile whose PC-1 interval is farther from every row of
+// the query tile than that row's current KP-th candidate distance cannot contribute.  The producer
+// walks outwards from the query tile's own position (t0, t0+1, t0-1, ...) and stops a direction for
+// good once the epilogue warps report that nothing beyond is within reach -- the MMA and epilogue work
+// of those tiles is never issued.  The bound uses exact quantities only (rounded outwards), so the
+// pruned references satisfy key_exact >= threshold and the margin proof of k_knn_rerank still holds.
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -58,29 +67,118 @@ __device__ __forceinline__ void split_h(double x, __half &hi, __half &lo)
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// reference image: one thread per point
+// ordering by the first coordinate: counting sort into 2^16 buckets
 // ---------------------------------------------------------------------------------------
-__global__ void k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, double scale,
-                              unsigned char *__restrict__ img, double *__restrict__ nrm2,
-                              unsigned long long *__restrict__ maxbits)
+#define TC_BUCKETS 65536
+
+// order-preserving map double -> uint64
+__device__ __forceinline__ unsigned long long ord_bits(double v)
+{
+    const long long b = __double_as_longlong(v);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ULL);
+}
+
+// max |x| over the embedding and min / max of the first coordinate
+__global__ void k_knn_tc_ranges(const double *__restrict__ E, int64_t lde, int64_t n, int d,
+                                unsigned long long *__restrict__ out3)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t n_pad = ((n + TC_N - 1) / TC_N) * TC_N;
-    if (i >= n_pad)
-        return;
-    unsigned char *tile = img + (i / TC_N) * (int64_t)TC_TILE_BYTES;
-    const int row = (int)(i % TC_N);
+    double m = 0.0;
+    unsigned long long lo = ~0ULL, hi = 0ULL;
+    if (i < n) {
+        for (int t = 0; t < d; ++t)
+            m = fmax(m, fabs(E[i * lde + t]));
+        lo = hi = ord_bits(E[i * lde]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m > 0.0)
+            atomicMax(out3, (unsigned long long)__double_as_longlong(m));
+        atomicMin(out3 + 1, lo);
+        atomicMax(out3 + 2, hi);
+    }
+}
+
+__global__ void k_knn_tc_bucket(const double *__restrict__ E, int64_t lde, int64_t n, double lo, double inv_width,
+                                int32_t *__restrict__ bkt, int32_t *__restrict__ hist)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        double f = (E[i * lde] - lo) * inv_width;
+        int b = (int)f;
+        b = b < 0 ? 0 : (b >= TC_BUCKETS ? TC_BUCKETS - 1 : b);
+        bkt[i] = b;
+        atomicAdd(hist + b, 1);
+    }
+}
+
+// perm[sorted position] = original index (order inside a bucket is arbitrary: tile bounds are taken
+// from the actual values, and every tie-break of the final result uses original indices)
+__global__ void k_knn_tc_scatter(const int32_t *__restrict__ bkt, int64_t n, unsigned long long *__restrict__ cursor,
+                                 int32_t *__restrict__ perm)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        const unsigned long long pos = atomicAdd(cursor + bkt[i], 1ULL);
+        perm[pos] = (int32_t)i;
+    }
+}
+
+// queries of [q_begin, q_end) in sorted order: flag, (scan), scatter
+__global__ void k_knn_tc_qflag(const int32_t *__restrict__ perm, int64_t n, int64_t q_begin, int64_t q_end,
+                               int32_t *__restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n)
+        flag[i] = (perm[i] >= q_begin && perm[i] < q_end) ? 1 : 0;
+}
+__global__ void k_knn_tc_qscatter(const int32_t *__restrict__ perm, const int32_t *__restrict__ flag,
+                                  const int64_t *__restrict__ off, int64_t n, int32_t *__restrict__ qlist,
+                                  int32_t *__restrict__ qpos)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) {
+        qlist[off[i]] = perm[i];
+        qpos[off[i]] = (int32_t)i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// reference image in sorted order: one block = one tile of 128 points, one thread per point
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, double scale,
+              const int32_t *__restrict__ perm, unsigned char *__restrict__ img, double *__restrict__ nrm2,
+              unsigned long long *__restrict__ maxbits, float *__restrict__ tile_lo, float *__restrict__ tile_hi)
+{
+    __shared__ float smin[4], smax[4];
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // sorted position
+    unsigned char *tile = img + (int64_t)blockIdx.x * TC_TILE_BYTES;
+    const int row = threadIdx.x;
     __half *hi_base = reinterpret_cast<__half *>(tile);
     __half *lo_base = reinterpret_cast<__half *>(tile + TC_PART_BYTES);
+    const int64_t src = i < n ? (int64_t)perm[i] : -1;
     double s = 0.0, sp = 0.0;
+    float c0lo = FLT_MAX, c0hi = -FLT_MAX;
     for (int t = 0; t < TC_K; ++t) {
         __half h = __float2half(0.f), l = __float2half(0.f);
-        if (i < n && t < d) {
-            const double v = E[i * lde + t];
+        if (src >= 0 && t < d) {
+            const double v = E[src * lde + t];
             s += v * v;
             const double vs = v * scale;
             sp += vs * vs;
             split_h(vs, h, l);
+            if (t == 0) {  // bounds of the scaled first coordinate, one ulp outwards
+                const float f = (float)vs;
+                c0lo = nextafterf(f, -FLT_MAX);
+                c0hi = nextafterf(f, FLT_MAX);
+            }
         }
         const uint32_t off = swz_offset(row, t * 2);
         *reinterpret_cast<__half *>(reinterpret_cast<unsigned char *>(hi_base) + off) = h;
@@ -88,14 +186,14 @@ __global__ void k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t
     }
     // -0.5|r'|^2 in the three spare K columns of the hi part
     __half a1, a2, a3;
-    if (i < n) {
+    if (src >= 0) {
         const double hn = 0.5 * sp;
         a1 = __double2half(hn * (1.0 / 4096.0));
         const double r1 = hn - (double)__half2float(a1) * 4096.0;
         a2 = __double2half(r1);
         const double r2 = r1 - (double)__half2float(a2);
         a3 = __double2half(r2 * 4096.0);
-        nrm2[i] = s;
+        nrm2[src] = s;
         atomicMax(maxbits, (unsigned long long)__double_as_longlong(s));
     } else {
         a1 = __float2half(65504.f);  // padding rows: T = -2.7e8, never selected
@@ -106,22 +204,21 @@ __global__ void k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t
     *reinterpret_cast<__half *>(hb + swz_offset(row, (d + 0) * 2)) = __hneg(a1);
     *reinterpret_cast<__half *>(hb + swz_offset(row, (d + 1) * 2)) = __hneg(a2);
     *reinterpret_cast<__half *>(hb + swz_offset(row, (d + 2) * 2)) = __hneg(a3);
-}
-
-// max |x| over the embedding (bit pattern of a non-negative double orders like an integer)
-__global__ void k_knn_tc_maxabs(const double *__restrict__ E, int64_t lde, int64_t n, int d,
-                                unsigned long long *__restrict__ maxbits)
-{
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    double m = 0.0;
-    if (i < n)
-        for (int t = 0; t < d; ++t)
-            m = fmax(m, fabs(E[i * lde + t]));
+    // PC-1 interval of the tile
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.0)
-        atomicMax(maxbits, (unsigned long long)__double_as_longlong(m));
+    for (int o = 16; o > 0; o >>= 1) {
+        c0lo = fminf(c0lo, __shfl_xor_sync(0xffffffffu, c0lo, o));
+        c0hi = fmaxf(c0hi, __shfl_xor_sync(0xffffffffu, c0hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        smin[threadIdx.x >> 5] = c0lo;
+        smax[threadIdx.x >> 5] = c0hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tile_lo[blockIdx.x] = fminf(fminf(smin[0], smin[1]), fminf(smin[2], smin[3]));
+        tile_hi[blockIdx.x] = fmaxf(fmaxf(smax[0], smax[1]), fmaxf(smax[2], smax[3]));
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -171,14 +268,19 @@ __device__ __noinline__ float tc_insert(float *lkey, int *lidx, float nk, int ni
 }
 
 // Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, then SETS epilogue sets of 4 warps;
-// set s takes the reference tiles t = s (mod SETS) from accumulator stage s.  Within a set warp w
-// owns TMEM lane quarter w % 4; a thread is one query row.  Each set keeps its own sorted top-KP
-// list per row, so a query ends with SETS*KP candidates and SETS thresholds.
+// the n-th tile of the (pruned, outward) tile sequence goes to set n % SETS through accumulator
+// stage n % SETS.  Within a set warp w owns TMEM lane quarter w % 4; a thread is one query row.  Each
+// set keeps its own sorted top-KP list per row, so a query ends with SETS*KP candidates and SETS
+// thresholds.
+constexpr int TC_RING = 16;  // tile ids of the sequence in flight (producer -> MMA -> epilogue)
+
 template <int KP, int SETS, int STAGES>
 __global__ void __launch_bounds__(tc_threads(SETS), 1)
 k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, const unsigned char *__restrict__ img,
-               int64_t n, int64_t q_begin, int64_t q_end, float key_unscale, int32_t *__restrict__ cand_idx,
-               float *__restrict__ cand_tau, int *__restrict__ err_flag, int mode)
+               int64_t n, int64_t nq, const int32_t *__restrict__ qlist, const int32_t *__restrict__ qpos,
+               const int32_t *__restrict__ perm, const float *__restrict__ tile_lo, const float *__restrict__ tile_hi,
+               float key_unscale, int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau,
+               int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done)
 {
     constexpr int EPL = KP / 32;
     constexpr int TC_SETS = SETS, TC_ACC_STAGES = SETS, TC_THREADS = tc_threads(SETS);
@@ -186,8 +288,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *q_img = smem;                                   // 32 KB: Q hi | Q lo
     unsigned char *r_img = smem + TC_TILE_BYTES;                   // STAGES x 32 KB
-    float *lkey = reinterpret_cast<float *>(r_img + (size_t)STAGES * TC_TILE_BYTES);  // [2][TC_M][KP]
-    int *lidx = reinterpret_cast<int *>(lkey + (size_t)TC_SETS * TC_M * KP);          // [2][TC_M][KP]
+    float *lkey = reinterpret_cast<float *>(r_img + (size_t)STAGES * TC_TILE_BYTES);  // [SETS][TC_M][KP]
+    int *lidx = reinterpret_cast<int *>(lkey + (size_t)TC_SETS * TC_M * KP);          // [SETS][TC_M][KP]
     uint64_t *bars = reinterpret_cast<uint64_t *>(lidx + (size_t)TC_SETS * TC_M * KP);
     uint64_t *full = bars;                       // [STAGES]
     uint64_t *empty = bars + STAGES;             // [STAGES]
@@ -195,18 +297,22 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     uint64_t *tempty = tfull + TC_ACC_STAGES;    // [TC_ACC_STAGES]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + TC_ACC_STAGES);
     float *thr_sh = reinterpret_cast<float *>(tmem_slot + 4);  // [SETS][TC_M] thresholds published by the sets
+    volatile float *reach_r = thr_sh + TC_SETS * TC_M;         // [SETS*4] largest PC-1 value a warp still needs
+    volatile float *reach_l = reach_r + TC_SETS * 4;           // [SETS*4] smallest PC-1 value a warp still needs
+    volatile int *seq_tile = reinterpret_cast<volatile int *>(reach_l + TC_SETS * 4);  // [TC_RING]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t q0 = q_begin + (int64_t)blockIdx.x * TC_M;
+    const int64_t ql0 = (int64_t)blockIdx.x * TC_M;   // first entry of the (sorted) query list
     const int64_t n_tiles = (n + TC_N - 1) / TC_N;
 
     // ---- one-time setup ------------------------------------------------------------------
     // query operand image (generic-proxy stores, made visible to the async proxy below)
     for (int i = tid; i < TC_M * TC_K; i += TC_THREADS) {
         const int row = i / TC_K, t = i % TC_K;
-        const int64_t g = q0 + row;
+        const int64_t ql = ql0 + row;
         __half h = __float2half(0.f), l = __float2half(0.f);
-        if (g < q_end) {
+        if (ql < nq) {
+            const int64_t g = qlist[ql];
             if (t < d) {
                 split_h(E[g * lde + t] * scale, h, l);
             } else if (t == d) {
@@ -227,6 +333,10 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     }
     for (int i = tid; i < TC_SETS * TC_M; i += TC_THREADS)
         thr_sh[i] = -FLT_MAX;
+    if (tid < TC_SETS * 4) {
+        reach_r[tid] = FLT_MAX;    // nothing can be pruned before thresholds exist
+        reach_l[tid] = -FLT_MAX;
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full + s, 1);
@@ -247,28 +357,70 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== producer: one 32 KB bulk copy per reference tile =====
+        // ===== producer: walks the reference tiles outwards from the query tile's own position =====
         if (lane == 0) {
-            for (int64_t t = 0; t < n_tiles; ++t) {
-                const int s = (int)(t % STAGES);
-                const uint32_t ph = (uint32_t)((t / STAGES) & 1);
+            const int64_t nvalid = nq - ql0 < TC_M ? nq - ql0 : TC_M;
+            const int64_t qmid = ql0 + nvalid / 2;
+            const int64_t tc = (qpos != nullptr ? (int64_t)qpos[qmid] : qmid) / TC_N;
+            int64_t tr = tc, tl = tc - 1, seq = 0;
+            bool right_done = false, left_done = false, take_right = true;
+            while (true) {
+                float rr = -FLT_MAX, rl = FLT_MAX;
+#pragma unroll
+                for (int w2 = 0; w2 < TC_SETS * 4; ++w2) {
+                    rr = fmaxf(rr, reach_r[w2]);
+                    rl = fminf(rl, reach_l[w2]);
+                }
+                if (tr >= n_tiles || (!right_done && tile_lo[tr] > rr))
+                    right_done = true;
+                if (tl < 0 || (!left_done && tile_hi[tl] < rl))
+                    left_done = true;
+                if (right_done && left_done)
+                    break;
+                const bool go_right = right_done ? false : (left_done ? true : take_right);
+                take_right = !go_right;
+                const int64_t t = go_right ? tr++ : tl--;
+                const int s = (int)(seq % STAGES);
+                const uint32_t ph = (uint32_t)((seq / STAGES) & 1);
                 mbar_wait(empty + s, ph ^ 1u, err_flag);
+                seq_tile[seq % TC_RING] = (int)t;
                 mbar_expect_tx(full + s, TC_TILE_BYTES);
                 bulk_g2s(r_img + (size_t)s * TC_TILE_BYTES, img + t * (int64_t)TC_TILE_BYTES, TC_TILE_BYTES, full + s);
+                ++seq;
             }
+            // end of the sequence
+            const int s = (int)(seq % STAGES);
+            mbar_wait(empty + s, (uint32_t)((seq / STAGES) & 1) ^ 1u, err_flag);
+            seq_tile[seq % TC_RING] = -1;
+            __threadfence_block();
+            mbar_arrive(full + s);
+            atomicAdd(tiles_done, (unsigned long long)seq);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t qh = smem_u32(q_img), ql = smem_u32(q_img + TC_PART_BYTES);
-            for (int64_t t = 0; t < n_tiles; ++t) {
-                const int s = (int)(t % STAGES);
-                const uint32_t ph = (uint32_t)((t / STAGES) & 1);
-                const int a = (int)(t % TC_ACC_STAGES);
-                const uint32_t aph = (uint32_t)((t / TC_ACC_STAGES) & 1);
+            for (int64_t seq = 0;; ++seq) {
+                const int s = (int)(seq % STAGES);
+                const uint32_t ph = (uint32_t)((seq / STAGES) & 1);
+                const int a = (int)(seq % TC_ACC_STAGES);
+                const uint32_t aph = (uint32_t)((seq / TC_ACC_STAGES) & 1);
                 mbar_wait(tempty + a, aph ^ 1u, err_flag);
                 mbar_wait(full + s, ph, err_flag);
                 tc_fence_after();
+                if (seq_tile[seq % TC_RING] < 0) {
+                    // wake every epilogue set with the end marker at its next sequence slot
+                    for (int j = 0; j < TC_SETS; ++j) {
+                        const int64_t sq = seq + j;
+                        const int a2 = (int)(sq % TC_ACC_STAGES);
+                        if (j > 0)
+                            mbar_wait(tempty + a2, (uint32_t)((sq / TC_ACC_STAGES) & 1) ^ 1u, err_flag);
+                        seq_tile[sq % TC_RING] = -1;
+                        __threadfence_block();
+                        mbar_arrive(tfull + a2);
+                    }
+                    break;
+                }
                 const uint32_t rh = smem_u32(r_img + (size_t)s * TC_TILE_BYTES), rl = rh + TC_PART_BYTES;
                 const uint32_t dcol = tmem_base + (uint32_t)(a * TC_N);
                 uint32_t acc = 0;
@@ -289,33 +441,50 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         }
     } else {
         // ===== epilogue: thread = query row (TMEM lane), fused top-KP selection =====
-        const int set = (warp - 2) >> 2;           // 0: even tiles / accumulator 0, 1: odd tiles / accumulator 1
+        const int set = (warp - 2) >> 2;           // accumulator stage / sequence residue of this set
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;
-        const int64_t grow = q0 + row;
+        const int64_t myql = ql0 + row;
+        const bool active = myql < nq;
         float *set_key = lkey + (size_t)set * TC_M * KP;
         int *set_idx = lidx + (size_t)set * TC_M * KP;
-        float thr = (grow < q_end) ? -FLT_MAX : FLT_MAX;  // T must exceed thr; rows past the range never select
+        float thr = active ? -FLT_MAX : FLT_MAX;   // T must exceed thr; rows past the list never select
+        // exact quantities of this row for the pruning bound, rounded so that the reach only grows
+        int my_pos = -1;                           // sorted position of the query itself (self-exclusion)
+        float q1 = 0.f, qn = 0.f;                  // scaled first coordinate, 0.5 |q'|^2 (rounded up)
+        if (active) {
+            const int64_t g = qlist[myql];
+            my_pos = qpos != nullptr ? qpos[myql] : (int)myql;
+            double sp = 0.0;
+            for (int t = 0; t < d; ++t) {
+                const double vs = E[g * lde + t] * scale;
+                sp += vs * vs;
+            }
+            q1 = (float)(E[g * lde] * scale);
+            qn = nextafterf((float)(0.5 * sp), FLT_MAX);
+        }
         const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * TC_N);
-        for (int64_t t = set; t < n_tiles; t += TC_SETS) {
-            const uint32_t aph = (uint32_t)((t / TC_ACC_STAGES) & 1);
+        for (int64_t seq = set;; seq += TC_SETS) {
+            const uint32_t aph = (uint32_t)((seq / TC_ACC_STAGES) & 1);
             mbar_wait(tfull + set, aph, err_flag);
             tc_fence_after();
-            const int64_t r0 = t * TC_N;
-            // A reference that does not beat the 32nd best of ANY set cannot be among the 32 best
+            const int t = seq_tile[seq % TC_RING];
+            if (t < 0)
+                break;
+            const int64_t r0 = (int64_t)t * TC_N;
+            // A reference that does not beat the KP-th best of ANY set cannot be among the KP best
             // overall: take the tightest threshold any set has published for this row (stale reads
-            // only cost extra hits; the union of the per-set lists still holds the global top 32).
-            if (thr != FLT_MAX) {
+            // only cost extra hits; the union of the per-set lists still holds the global top KP).
+            if (active) {
 #pragma unroll
                 for (int s2 = 0; s2 < TC_SETS; ++s2)
                     thr = fmaxf(thr, thr_sh[s2 * TC_M + row]);
             }
             // Scan of 32 accumulator columns held in registers.  Fast path: 3-input max tree + one
-            // vote.  Slow path (some lane beats its threshold): 32 independent ballots give the hit
-            // lanes of every column; each hit is inserted into its row's sorted list by the whole
-            // warp (tc_insert), which also yields the row's exact new threshold.
+            // vote.  Slow path (some lane beats its threshold): group votes, then per-column ballots;
+            // each hit is inserted into its row's sorted list by the whole warp (tc_insert), which
+            // also yields the row's exact new threshold.
             auto scan_chunk = [&](uint32_t(&r)[32], int64_t c0) {
-                // maxima of the four 8-column groups, then of the chunk
                 float g[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -327,7 +496,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     g[j] = fmaxf(fmaxf(a0, a1), a2);
                 }
                 const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-                if (!__any_sync(0xffffffffu, m > thr) || (mode & 8))
+                if (!__any_sync(0xffffffffu, m > thr))
                     return;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -342,9 +511,9 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                             c &= c - 1;
                             const float val = __shfl_sync(0xffffffffu, __uint_as_float(r[i]), owner);
                             const float othr = __shfl_sync(0xffffffffu, thr, owner);
+                            const int opos = __shfl_sync(0xffffffffu, my_pos, owner);
                             const int64_t gcol = c0 + i;
-                            const int64_t og = q0 + quarter * 32 + owner;
-                            if (val > othr && gcol < n && gcol != og && !(mode & 16)) {
+                            if (val > othr && gcol < n && gcol != opos) {
                                 const float kth = tc_insert<EPL>(set_key + (size_t)(quarter * 32 + owner) * KP,
                                                                  set_idx + (size_t)(quarter * 32 + owner) * KP, -val,
                                                                  (int)gcol, lane);
@@ -361,32 +530,51 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             // measured 2.4x slower -- the doubled slow-path code thrashes the instruction cache
             uint32_t ra[32];
 #pragma unroll 1
-            for (int ch = 0; ch < ((mode & 2) ? 2 : TC_N / 32); ++ch) {
-                if (!(mode & 4)) {
-                    tmem_ld32_issue(tcol + (uint32_t)(ch * 32), ra);
-                    tmem_ld_wait();
-                }
-                if (!(mode & 1))
-                    scan_chunk(ra, r0 + ch * 32);
+            for (int ch = 0; ch < TC_N / 32; ++ch) {
+                tmem_ld32_issue(tcol + (uint32_t)(ch * 32), ra);
+                tmem_ld_wait();
+                scan_chunk(ra, r0 + ch * 32);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(tempty + set);
+            // how far along PC 1 this warp's rows can still find a candidate: d <= sqrt(2 (key_thr + qn))
+            float rr = -FLT_MAX, rl = FLT_MAX;
+            if (active) {
+                if (thr == -FLT_MAX) {
+                    rr = FLT_MAX;
+                    rl = -FLT_MAX;
+                } else {
+                    const float d2 = fmaxf(2.0f * (qn - thr), 0.f);           // key_thr = -thr
+                    const float reach = sqrtf(d2) * 1.000002f + fabsf(q1) * 4.8e-7f + 1e-30f;
+                    rr = q1 + reach;
+                    rl = q1 - reach;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                rr = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, o));
+                rl = fminf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+            }
+            if (lane == 0) {
+                reach_r[warp - 2] = rr;
+                reach_l[warp - 2] = rl;
+            }
         }
-        // final: the lists are sorted; write this set's KP candidates and threshold of every row
-        // (key space, unscaled: key = 0.5 d^2 - 0.5 |q|^2)
+        // final: the lists are sorted; write this set's KP candidates (original indices) and the
+        // threshold of every row (key space, unscaled: key = 0.5 d^2 - 0.5 |q|^2)
         __syncwarp();
-        if (grow < q_end) {
+        if (active) {
             const float *rk = set_key + (size_t)row * KP;
             const int *ri = set_idx + (size_t)row * KP;
-            int32_t *out = cand_idx + (grow - q_begin) * (int64_t)(TC_SETS * KP) + set * KP;
+            int32_t *out = cand_idx + myql * (int64_t)(TC_SETS * KP) + set * KP;
             for (int p = 0; p < KP; ++p) {
                 const int v = ri[p];
-                out[p] = v == 0x7fffffff ? -1 : v;
+                out[p] = v == 0x7fffffff ? -1 : perm[v];
             }
             const float kth = rk[KP - 1];
-            cand_tau[(grow - q_begin) * TC_SETS + set] = (kth == FLT_MAX) ? FLT_MAX : kth * key_unscale;
+            cand_tau[myql * TC_SETS + set] = (kth == FLT_MAX) ? FLT_MAX : kth * key_unscale;
         }
     }
     tc_fence_before();
@@ -399,50 +587,70 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 // host side
 // ---------------------------------------------------------------------------------------
 template <int KP, int SETS, int STAGES>
-static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double scale, int64_t n, int64_t q_begin,
-                     int64_t q_end)
+static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double scale, int64_t n, int64_t nq,
+                     const int32_t *qlist, const int32_t *qpos)
 {
     const size_t smem = (size_t)TC_TILE_BYTES * (1 + STAGES) + (size_t)SETS * TC_M * KP * 8 +
-                        (size_t)(2 * STAGES + 2 * SETS) * 8 + 16 + (size_t)SETS * TC_M * 4;
+                        (size_t)(2 * STAGES + 2 * SETS) * 8 + 16 + (size_t)SETS * TC_M * 4 + (size_t)SETS * 4 * 8 +
+                        (size_t)TC_RING * 4;
     CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, SETS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-    const int64_t nq = q_end - q_begin;
     const unsigned grid = (unsigned)((nq + TC_M - 1) / TC_M);
     const float key_unscale = (float)(1.0 / (scale * scale));
     k_knn_tiles_tc<KP, SETS, STAGES><<<grid, tc_threads(SETS), smem, ctx->stream>>>(
-        E, lde, d, scale, ctx->knn_img.p, n, q_begin, q_end, key_unscale, ctx->cand_idx.p, ctx->cand_tau.p,
-        ctx->flag.p + 3, getenv("CB200_TC_MODE") ? atoi(getenv("CB200_TC_MODE")) : 0);
+        E, lde, d, scale, ctx->knn_img.p, n, nq, qlist, qpos, ctx->knn_perm.p, ctx->knn_tile_lo.p, ctx->knn_tile_hi.p,
+        key_unscale, ctx->cand_idx.p, ctx->cand_tau.p, ctx->flag.p + 3, ctx->maxnrm.p + 3);
     CB_LAUNCH(ctx);
     return 0;
 }
 
 bool cb200_knn_tc_supported(int d, int k) { return d + 3 <= TC_K && k <= 52; }
 
-// Builds the reference image and runs the tensor-core tile kernel; fills ctx->cand_idx /
-// ctx->cand_tau, ctx->nrm2, ctx->maxnrm.  *kp_out = candidates kept per query, *ntau_out =
-// thresholds per query (every non-candidate has key >= the smallest of them),
-// *err_coef_out = coefficient of the a-priori key error bound.
+// Orders the references by their first coordinate, builds the operand image and runs the
+// tensor-core tile kernel; fills ctx->cand_idx / ctx->cand_tau (indexed by position in the sorted
+// query list), ctx->nrm2, ctx->maxnrm.  *kp_out = candidates kept per query, *ntau_out = thresholds
+// per query (every non-candidate has key >= the smallest of them), *qlist_out = original index of
+// every entry of the query list (device), *err_coef_out = coefficient of the a-priori key error bound.
 int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int d, int k, int64_t q_begin,
-                       int64_t q_end, int *kp_out, int *ntau_out, double *err_coef_out)
+                       int64_t q_end, int *kp_out, int *ntau_out, const int32_t **qlist_out, double *err_coef_out)
 {
     const int64_t nq = q_end - q_begin;
     const int64_t n_tiles = (n + TC_N - 1) / TC_N;
     const int KP = k <= 24 ? 32 : 64;
+    const int SETS = KP == 32 ? 4 : 2;
     CB_CUDA(ctx, ctx->knn_img.ensure((size_t)n_tiles * TC_TILE_BYTES));
     CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
-    const int SETS = KP == 32 ? 4 : 2;
     CB_CUDA(ctx, ctx->cand_idx.ensure((size_t)nq * SETS * KP));
     CB_CUDA(ctx, ctx->cand_tau.ensure((size_t)nq * SETS));
+    CB_CUDA(ctx, ctx->knn_perm.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->knn_bkt.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->knn_hist.ensure((size_t)TC_BUCKETS));
+    CB_CUDA(ctx, ctx->knn_cursor.ensure((size_t)TC_BUCKETS + 1));
+    CB_CUDA(ctx, ctx->knn_tile_lo.ensure((size_t)n_tiles));
+    CB_CUDA(ctx, ctx->knn_tile_hi.ensure((size_t)n_tiles));
+    CB_CUDA(ctx, ctx->maxnrm.ensure(4));
 
     cb_stage_begin(ctx, ST_KNN_PREP);
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, sizeof(unsigned long long), ctx->stream));
-    k_knn_tc_maxabs<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(E, lde, n, d, ctx->maxnrm.p);
+    // ranges: [0] max |x| bits, [1] min of coordinate 0 (ordered bits), [2] max of coordinate 0
+    {
+        unsigned long long init[4] = {0ULL, ~0ULL, 0ULL, 0ULL};
+        CB_CUDA(ctx, cudaMemcpyAsync(ctx->maxnrm.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const unsigned g256 = (unsigned)((n + 255) / 256);
+    k_knn_tc_ranges<<<g256, 256, 0, ctx->stream>>>(E, lde, n, d, ctx->maxnrm.p);
     CB_LAUNCH(ctx);
-    unsigned long long bits = 0;
-    CB_CUDA(ctx, cudaMemcpyAsync(&bits, ctx->maxnrm.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long r3[3];
+    CB_CUDA(ctx, cudaMemcpyAsync(r3, ctx->maxnrm.p, sizeof(r3), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    auto unord = [](unsigned long long u) {
+        const unsigned long long b = (u & 0x8000000000000000ULL) ? (u & 0x7fffffffffffffffULL) : ~u;
+        double v;
+        memcpy(&v, &b, sizeof(v));
+        return v;
+    };
     double maxabs;
-    memcpy(&maxabs, &bits, sizeof(double));
+    memcpy(&maxabs, &r3[0], sizeof(double));
+    const double c0min = unord(r3[1]), c0max = unord(r3[2]);
     CB_CHECK(ctx, maxabs == maxabs && maxabs < 1e300, "cb200_knn: embedding contains non-finite values");
     // power-of-two scale: max |x'| in [256, 512)
     double scale = 1.0;
@@ -451,22 +659,48 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
         frexp(maxabs, &e);          // maxabs = f * 2^e, f in [0.5, 1)
         scale = ldexp(1.0, 9 - e);  // maxabs * scale in [256, 512)
     }
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, sizeof(unsigned long long), ctx->stream));
-    const int64_t n_pad = n_tiles * TC_N;
-    k_knn_tc_prep<<<(unsigned)((n_pad + 127) / 128), 128, 0, ctx->stream>>>(E, lde, n, d, scale, ctx->knn_img.p,
-                                                                           ctx->nrm2.p, ctx->maxnrm.p);
+    // counting sort by the first coordinate
+    const double width = c0max - c0min;
+    const double inv_width = width > 0.0 ? (double)TC_BUCKETS / width * (1.0 - 1e-12) : 0.0;
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->knn_hist.p, 0, TC_BUCKETS * sizeof(int32_t), ctx->stream));
+    k_knn_tc_bucket<<<g256, 256, 0, ctx->stream>>>(E, lde, n, c0min, inv_width, ctx->knn_bkt.p, ctx->knn_hist.p);
     CB_LAUNCH(ctx);
+    CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->knn_hist.p, TC_BUCKETS, reinterpret_cast<int64_t *>(ctx->knn_cursor.p)));
+    k_knn_tc_scatter<<<g256, 256, 0, ctx->stream>>>(ctx->knn_bkt.p, n, ctx->knn_cursor.p, ctx->knn_perm.p);
+    CB_LAUNCH(ctx);
+    // image, norms, tile intervals (maxnrm[0] becomes max |r|^2)
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    k_knn_tc_prep<<<(unsigned)n_tiles, 128, 0, ctx->stream>>>(E, lde, n, d, scale, ctx->knn_perm.p, ctx->knn_img.p,
+                                                              ctx->nrm2.p, ctx->maxnrm.p, ctx->knn_tile_lo.p,
+                                                              ctx->knn_tile_hi.p);
+    CB_LAUNCH(ctx);
+    // the query list: the cells of [q_begin, q_end) in sorted order
+    const int32_t *qlist = ctx->knn_perm.p, *qpos = nullptr;
+    if (!(q_begin == 0 && q_end == n)) {
+        CB_CUDA(ctx, ctx->knn_qlist.ensure((size_t)nq));
+        CB_CUDA(ctx, ctx->knn_qpos.ensure((size_t)nq));
+        CB_CUDA(ctx, ctx->knn_qoff.ensure((size_t)n + 1));
+        k_knn_tc_qflag<<<g256, 256, 0, ctx->stream>>>(ctx->knn_perm.p, n, q_begin, q_end, ctx->knn_bkt.p);
+        CB_LAUNCH(ctx);
+        CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->knn_bkt.p, n, ctx->knn_qoff.p));
+        k_knn_tc_qscatter<<<g256, 256, 0, ctx->stream>>>(ctx->knn_perm.p, ctx->knn_bkt.p, ctx->knn_qoff.p, n,
+                                                         ctx->knn_qlist.p, ctx->knn_qpos.p);
+        CB_LAUNCH(ctx);
+        qlist = ctx->knn_qlist.p;
+        qpos = ctx->knn_qpos.p;
+    }
     cb_stage_end(ctx, ST_KNN_PREP);
 
     cb_stage_begin(ctx, ST_KNN_TILE);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     if (KP == 32)
-        CB_TRY((launch_tc<32, 4, 2>(ctx, E, lde, d, scale, n, q_begin, q_end)));
+        CB_TRY((launch_tc<32, 4, 2>(ctx, E, lde, d, scale, n, nq, qlist, qpos)));
     else
-        CB_TRY((launch_tc<64, 2, 2>(ctx, E, lde, d, scale, n, q_begin, q_end)));
+        CB_TRY((launch_tc<64, 2, 2>(ctx, E, lde, d, scale, n, nq, qlist, qpos)));
     cb_stage_end(ctx, ST_KNN_TILE);
     *kp_out = SETS * KP;  // candidates per query: one sorted list per epilogue set
     *ntau_out = SETS;
+    *qlist_out = qlist;
     // split (3.1 * 2^-22) + fp32 accumulation of <= 195 products (2^-23 each, truncation assumed)
     *err_coef_out = ldexp(1.0, -15);
     return 0;

@@ -64,4 +64,4 @@ __device__ __forceinline__ void warp_bitonic_sort(K (&key)[EPL], int (&idx)[EPL]
 // tensor-core tile engine (cb200_knn_tc.cu)
 bool cb200_knn_tc_supported(int d, int k);
 int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int d, int k, int64_t q_begin,
-                       int64_t q_end, int *kp_out, int *ntau_out, double *err_coef_out);
+                       int64_t q_end, int *kp_out, int *ntau_out, const int32_t **qlist_out, double *err_coef_out);

@@ -72,6 +72,8 @@ typedef struct cb200_timing {
     int64_t knn_fallback_queries; /* queries answered by the exact fp64 fallback      */
     int64_t eig_iterations;
     int64_t gram_engine;    /* cross-product engine of the last PCA: 1 = fp64 L2 reductions, 2 = fp64 shared-memory tiles, 3 = tcgen05 int8 digits */
+    int64_t knn_tiles_scanned; /* 128 x 128 distance tiles computed by the last kNN call ...          */
+    int64_t knn_tiles_total;   /* ... out of this many (the rest was pruned on the PC-1 bound)          */
     int64_t knn_engine;     /* tile engine of the last kNN call: 1 = fp32 CUDA cores, 2 = tcgen05 tensor cores */
 } cb200_timing;
 
