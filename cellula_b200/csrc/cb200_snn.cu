@@ -18,7 +18,7 @@
 // i = 0..k, list i in ascending cell order), i.e. sorted by (first list that holds h, h).
 #include "cb200_common.cuh"
 
-#define SNN_SLOTS 4  // lists per lane: supports k + 1 <= 128
+#define SNN_SLOTS 4  // at most 4 lists per lane: supports k + 1 <= 128
 #define SNN_INF 0xffffffffu
 
 __global__ void k_index_to_rowmajor0(const int32_t *__restrict__ in, int64_t n, int k, int32_t *__restrict__ out,
@@ -95,44 +95,82 @@ __global__ void __launch_bounds__(256) k_rev_sort(const int64_t *__restrict__ rp
 
 // MODE 0: count edges of j (ecnt[j]) and per-list first-encounter counts (bcnt[j][i]).
 // MODE 1: emit edges at eptr[j] + (prefix of bcnt[j][.])[imin] + running index.
-template <int MODE>
+// SLOTS lists per lane (k + 1 <= 32 * SLOTS).  Each lane stages the next SNN_CHUNK(SLOTS) entries
+// of its lists in shared memory (loads issued back to back), so the merge loop -- one warp-min
+// (redux.sync) and one shared-memory read per output edge -- has no dependent global load inside.
+#define SNN_SMEM_WORDS 1056  // per warp: 32 lanes x (32 + 1 pad) words
+template <int SLOTS>
+struct SnnChunk {
+    static constexpr int value = 32 / SLOTS;  // entries staged per list
+};
+
+template <int MODE, int SLOTS>
 __global__ void __launch_bounds__(256)
 k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
             const int64_t *__restrict__ rptr, const uint32_t *__restrict__ hosts, int32_t *__restrict__ ecnt,
             int32_t *__restrict__ bcnt, const int64_t *__restrict__ eptr, int32_t *__restrict__ efrom,
             int32_t *__restrict__ eto, double *__restrict__ ew)
 {
-    const int lane = threadIdx.x & 31;
+    constexpr int CH = SnnChunk<SLOTS>::value;
+    __shared__ uint32_t stage[8][SNN_SMEM_WORDS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t *mine = stage[w] + lane * 33;  // this lane's SLOTS x CH staged entries (+1 pad: no bank conflicts)
     const int L = k + 1;
-    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t j = j_begin + warp0; j < j_end; j += nwarps) {
         const int64_t jl = j - j_begin;
-        int64_t ptr[SNN_SLOTS], end[SNN_SLOTS];
-        uint32_t head[SNN_SLOTS];
-        int nfirst[SNN_SLOTS];  // MODE 0: edges first met in my list; MODE 1: next free slot of my bucket
+        int64_t gptr[SLOTS], gend[SLOTS];   // next entry not yet staged / end of the list
+        int hpos[SLOTS], hcnt[SLOTS];       // position in / size of the staged chunk
+        uint32_t head[SLOTS];
+        int nfirst[SLOTS];  // MODE 0: edges first met in my list; MODE 1: next free slot of my bucket
+        auto refill = [&](int u) {
+            // stage the next CH entries of list u (independent loads, one latency)
+            int c = 0;
 #pragma unroll
-        for (int u = 0; u < SNN_SLOTS; ++u) {
+            for (int e = 0; e < CH; ++e) {
+                if (gptr[u] + e < gend[u]) {
+                    mine[u * CH + e] = hosts[gptr[u] + e];
+                    c = e + 1;
+                }
+            }
+            gptr[u] += c;
+            hcnt[u] = c;
+            hpos[u] = 0;
+        };
+        auto load_head = [&](int u) {
+            if (hpos[u] == hcnt[u] && gptr[u] < gend[u])
+                refill(u);
+            uint32_t hv = SNN_INF;
+            if (hpos[u] < hcnt[u]) {
+                hv = mine[u * CH + hpos[u]];
+                if ((int64_t)(hv >> 8) >= j) {  // sorted by cell: nothing further can precede j
+                    hv = SNN_INF;
+                    gptr[u] = gend[u];
+                    hcnt[u] = hpos[u];
+                }
+            }
+            head[u] = hv;
+        };
+#pragma unroll
+        for (int u = 0; u < SLOTS; ++u) {
             const int i = u * 32 + lane;
-            ptr[u] = 0;
-            end[u] = 0;
-            head[u] = SNN_INF;
+            gptr[u] = 0;
+            gend[u] = 0;
+            hpos[u] = hcnt[u] = 0;
             nfirst[u] = 0;
             if (i < L) {
                 const int s = i == 0 ? (int)j : nn[j * k + (i - 1)];
-                ptr[u] = rptr[s];
-                end[u] = rptr[s + 1];
-                if (ptr[u] < end[u]) {
-                    const uint32_t hv = hosts[ptr[u]];
-                    head[u] = ((int64_t)(hv >> 8) < j) ? hv : SNN_INF;
-                }
+                gptr[u] = rptr[s];
+                gend[u] = rptr[s + 1];
             }
+            load_head(u);
         }
         if (MODE == 1) {
             // exclusive prefix of the bucket counts over i = 0..k, bucket i = u*32 + lane
             int carry = 0;
 #pragma unroll
-            for (int u = 0; u < SNN_SLOTS; ++u) {
+            for (int u = 0; u < SLOTS; ++u) {
                 const int i = u * 32 + lane;
                 const int c = i < L ? bcnt[jl * L + i] : 0;
                 int inc = c;
@@ -151,28 +189,21 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
         while (true) {
             uint32_t hmin = SNN_INF >> 8;
 #pragma unroll
-            for (int u = 0; u < SNN_SLOTS; ++u)
+            for (int u = 0; u < SLOTS; ++u)
                 hmin = min(hmin, head[u] >> 8);
             const uint32_t m = __reduce_min_sync(0xffffffffu, hmin);
             if (m == (SNN_INF >> 8))
                 break;
             int rs = 0x7fffffff, nmatch = 0, imin = 0x7fffffff;
 #pragma unroll
-            for (int u = 0; u < SNN_SLOTS; ++u) {
+            for (int u = 0; u < SLOTS; ++u) {
                 if ((head[u] >> 8) == m && head[u] != SNN_INF) {
                     const int i = u * 32 + lane;
                     rs = min(rs, i + (int)(head[u] & 0xffu));
                     imin = min(imin, i);
                     nmatch += 1;
-                    // advance this list
-                    ptr[u] += 1;
-                    uint32_t hv = SNN_INF;
-                    if (ptr[u] < end[u]) {
-                        hv = hosts[ptr[u]];
-                        if ((int64_t)(hv >> 8) >= j)
-                            hv = SNN_INF;
-                    }
-                    head[u] = hv;
+                    hpos[u] += 1;
+                    load_head(u);
                 }
             }
             rs = __reduce_min_sync(0xffffffffu, rs);
@@ -182,14 +213,14 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
             const int own_lane = imin & 31, own_u = imin >> 5;
             if (MODE == 0) {
 #pragma unroll
-                for (int u = 0; u < SNN_SLOTS; ++u)
+                for (int u = 0; u < SLOTS; ++u)
                     if (u == own_u && lane == own_lane)
                         nfirst[u] += 1;
                 total += 1;
             } else {
                 int slot = 0;
 #pragma unroll
-                for (int u = 0; u < SNN_SLOTS; ++u) {
+                for (int u = 0; u < SLOTS; ++u) {
                     const int v = __shfl_sync(0xffffffffu, nfirst[u], own_lane);
                     if (u == own_u) {
                         slot = v;
@@ -218,13 +249,32 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
             if (lane == 0)
                 ecnt[jl] = total;
 #pragma unroll
-            for (int u = 0; u < SNN_SLOTS; ++u) {
+            for (int u = 0; u < SLOTS; ++u) {
                 const int i = u * 32 + lane;
                 if (i < L)
                     bcnt[jl * L + i] = nfirst[u];
             }
         }
     }
+}
+
+template <int MODE>
+static void launch_snn_merge(cb200_ctx *ctx, int grid, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin,
+                             int64_t j_end)
+{
+    const int32_t *nn = d_nn;
+    if (k + 1 <= 32)
+        k_snn_merge<MODE, 1><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
+                                                           ctx->ecnt.p, ctx->bcnt.p, ctx->eptr.p, ctx->efrom.p,
+                                                           ctx->eto.p, ctx->ew8.p);
+    else if (k + 1 <= 64)
+        k_snn_merge<MODE, 2><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
+                                                           ctx->ecnt.p, ctx->bcnt.p, ctx->eptr.p, ctx->efrom.p,
+                                                           ctx->eto.p, ctx->ew8.p);
+    else
+        k_snn_merge<MODE, 4><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
+                                                           ctx->ecnt.p, ctx->bcnt.p, ctx->eptr.p, ctx->efrom.p,
+                                                           ctx->eto.p, ctx->ew8.p);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -264,8 +314,7 @@ static int snn_core(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int t
 
     cb_stage_begin(ctx, ST_SNN_EDGES);
     const int g3 = cb_grid_for(nj, 8, ctx->num_sms * 16);
-    k_snn_merge<0><<<g3, 256, 0, ctx->stream>>>(d_nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                ctx->ecnt.p, ctx->bcnt.p, nullptr, nullptr, nullptr, nullptr);
+    launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end);
     CB_LAUNCH(ctx);
     CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->ecnt.p, nj, ctx->eptr.p));
     int64_t ne = 0;
@@ -274,9 +323,7 @@ static int snn_core(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int t
     CB_CUDA(ctx, ctx->efrom.ensure((size_t)ne));
     CB_CUDA(ctx, ctx->eto.ensure((size_t)ne));
     CB_CUDA(ctx, ctx->ew8.ensure((size_t)ne));
-    k_snn_merge<1><<<g3, 256, 0, ctx->stream>>>(d_nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                ctx->ecnt.p, ctx->bcnt.p, ctx->eptr.p, ctx->efrom.p, ctx->eto.p,
-                                                ctx->ew8.p);
+    launch_snn_merge<1>(ctx, g3, d_nn, n, k, type, j_begin, j_end);
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_SNN_EDGES);
     ctx->n_edges = ne;
