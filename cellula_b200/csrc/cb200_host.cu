@@ -149,3 +149,30 @@ extern "C" int cb200_host_weighted_lowess(int64_t n64, const double *xs, const d
     }
     return 0;
 }
+
+// Gaussian kernel density of m[0..n) on a uniform grid of `ng` points from lo to hi with bandwidth bw
+// (direct sum, what trendvar._density_weights evaluates with numpy): dens_out[ng].
+extern "C" int cb200_host_gauss_kde(int64_t n, const double *m, double bw, double lo, double hi, int ng,
+                                    double *dens_out)
+{
+    if (n < 1 || ng < 2 || m == nullptr || dens_out == nullptr || !(bw > 0.0))
+        return 1;
+    const double step = (hi - lo) / (ng - 1);
+    std::vector<double> acc((size_t)ng, 0.0);
+    const double inv = 1.0 / bw;
+    for (int64_t j = 0; j < n; ++j) {
+        const double mj = m[j];
+        // exp(-0.5 z^2) < 2e-16 beyond |z| = 8.5: those terms cannot change a double-precision sum
+        int i0 = (int)std::floor((mj - 8.5 * bw - lo) / step), i1 = (int)std::ceil((mj + 8.5 * bw - lo) / step);
+        i0 = i0 < 0 ? 0 : i0;
+        i1 = i1 > ng - 1 ? ng - 1 : i1;
+        for (int i = i0; i <= i1; ++i) {
+            const double z = ((lo + step * i) - mj) * inv;
+            acc[i] += std::exp(-0.5 * z * z);
+        }
+    }
+    const double norm = 1.0 / ((double)n * bw * 2.5066282746310002);  // sqrt(2 pi)
+    for (int i = 0; i < ng; ++i)
+        dens_out[i] = acc[i] * norm;
+    return 0;
+}

@@ -86,8 +86,10 @@ __global__ void k_knn_tc_ranges(const double *__restrict__ E, int64_t lde, int64
     double m = 0.0;
     unsigned long long lo = ~0ULL, hi = 0ULL;
     if (i < n) {
-        for (int t = 0; t < d; ++t)
-            m = fmax(m, fabs(E[i * lde + t]));
+        for (int t = 0; t < d; ++t) {
+            const double v = E[i * lde + t];
+            m = (v != v) ? 1.0 / 0.0 : fmax(m, fabs(v));  // NaN must not slip through fmax
+        }
         lo = hi = ord_bits(E[i * lde]);
     }
 #pragma unroll

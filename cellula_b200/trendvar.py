@@ -16,6 +16,19 @@ import numpy as np
 from scipy.special import ndtr
 
 
+def _native(name):
+    """A host helper of the shared library (csrc/cb200_host.cu), or None when it has not been built."""
+    try:
+        from . import _lib
+        return getattr(_lib.lib(), name)
+    except Exception:
+        return None
+
+
+def _native_lowess():
+    return _native("cb200_host_weighted_lowess")
+
+
 def _density_weights(m):
     """1 / kernel density of the means (Gaussian, bw.nrd0, 512-point grid), mean-scaled."""
     n = m.size
@@ -23,13 +36,22 @@ def _density_weights(m):
     iqr = np.subtract(*np.percentile(m, [75, 25]))
     lo = min(sd, iqr / 1.34) or sd or abs(m[0]) or 1.0
     bw = 0.9 * lo * n ** -0.2
-    grid = np.linspace(m.min() - 3 * bw, m.max() + 3 * bw, 512)
-    dens = np.zeros(512)
-    step = max(1, 4_000_000 // 512)
-    for a in range(0, n, step):
-        z = (grid[:, None] - m[None, a:a + step]) / bw
-        dens += np.exp(-0.5 * z * z).sum(axis=1)
-    dens /= n * bw * math.sqrt(2 * math.pi)
+    lo_g, hi_g = m.min() - 3 * bw, m.max() + 3 * bw
+    grid = np.linspace(lo_g, hi_g, 512)
+    dens = None
+    native = _native("cb200_host_gauss_kde")
+    if native is not None:
+        mc = np.ascontiguousarray(m)
+        out = np.empty(512)
+        if native(n, mc.ctypes.data, float(bw), float(lo_g), float(hi_g), 512, out.ctypes.data) == 0:
+            dens = out
+    if dens is None:
+        dens = np.zeros(512)
+        step = max(1, 4_000_000 // 512)
+        for a in range(0, n, step):
+            z = (grid[:, None] - m[None, a:a + step]) / bw
+            dens += np.exp(-0.5 * z * z).sum(axis=1)
+        dens /= n * bw * math.sqrt(2 * math.pi)
     w = 1.0 / np.interp(m, grid, dens)
     return w / w.mean()
 
@@ -105,15 +127,6 @@ def _wmedian(x, w):
     if i + 1 < x.size and cw[i] == half:
         return 0.5 * (x[o[i]] + x[o[i + 1]])
     return x[o[i]]
-
-
-def _native_lowess():
-    """cb200_host_weighted_lowess from the shared library, or None when it has not been built."""
-    try:
-        from . import _lib
-        return _lib.lib().cb200_host_weighted_lowess
-    except Exception:
-        return None
 
 
 def _weighted_lowess(x, y, w, span=0.3, iterations=4, npts=200):

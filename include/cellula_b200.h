@@ -201,6 +201,8 @@ int cb200_export_csc(cb200_ctx *ctx, int64_t *colptr, int32_t *rowidx, double *v
  * calling scran/limma; cellula_b200/trendvar.py uses this instead of interpreted loops. */
 int cb200_host_weighted_lowess(int64_t n, const double *x_sorted, const double *y, const double *w, double span,
                                int iterations, int npts, double *fitted_out);
+/* Gaussian kernel density of m[0..n) on `ng` uniform grid points in [lo, hi] (stats::density stand-in). */
+int cb200_host_gauss_kde(int64_t n, const double *m, double bw, double lo, double hi, int ng, double *dens_out);
 
 #ifdef __cplusplus
 }

@@ -105,6 +105,49 @@ def test_knn_engines_agree_on_candidates_quality(gpu_ctx, monkeypatch):
         assert gpu_ctx.timings()["knn_fallback_queries"] <= 6, eng
 
 
+def test_knn_degenerate_first_coordinate(gpu_ctx, engine):
+    """The tensor-core engine orders and prunes by the first coordinate: constant, two-valued and
+    outlier-ridden first coordinates must not change the (exact) result."""
+    rng = np.random.default_rng(9)
+    emb = synth.make_embedding(2000, 12, seed=8)
+    for mutate in ("const", "binary", "outlier"):
+        e = emb.copy()
+        if mutate == "const":
+            e[:, 0] = 3.25
+        elif mutate == "binary":
+            e[:, 0] = rng.integers(0, 2, 2000) * 50.0
+        else:
+            e[::400, 0] = 1e6
+        assert np.array_equal(gpu_ctx.knn(e, 10), O.find_knn(e, 10)), mutate
+
+
+def test_knn_rejects_non_finite(gpu_ctx):
+    emb = synth.make_embedding(500, 8, seed=8)
+    emb[17, 3] = np.nan
+    with pytest.raises(cellula_b200.Cb200Error, match="non-finite"):
+        gpu_ctx.knn(emb, 5)
+
+
+def test_knn_pruning_reports_tiles(gpu_ctx):
+    """Well-separated clusters along the first coordinate: most of the tile grid must be pruned."""
+    rng = np.random.default_rng(3)
+    emb = rng.standard_normal((40000, 10))
+    emb[:, 0] += np.repeat(np.arange(40) * 40.0, 1000)       # 40 slabs far apart in PC 1
+    emb = emb[rng.permutation(40000)]
+    got = gpu_ctx.knn(emb, 10)
+    t = gpu_ctx.timings()
+    assert t["knn_engine"] == 2 and t["knn_tiles_scanned"] < 0.2 * t["knn_tiles_total"], t
+    q = rng.choice(40000, 200, replace=False)
+    acc = np.zeros((200, 40000))
+    for c in range(10):
+        dlt = emb[q, c][:, None] - emb[None, :, c]
+        acc += dlt * dlt
+    dist = np.sqrt(acc)
+    dist[np.arange(200), q] = np.inf
+    want = np.array([np.lexsort((np.arange(40000), dist[r]))[:10] + 1 for r in range(200)], dtype=np.int32)
+    assert np.array_equal(got[q], want)
+
+
 def test_knn_argument_errors(gpu_ctx):
     emb = synth.make_embedding(50, 5, seed=3)
     with pytest.raises(cellula_b200.Cb200Error, match="k <= n-1"):
