@@ -176,3 +176,124 @@ extern "C" int cb200_host_gauss_kde(int64_t n, const double *m, double bw, doubl
         dens_out[i] = acc[i] * norm;
     return 0;
 }
+
+// Weighted least squares of v ~ exp(A) m / (m^(1+exp(N)) + exp(B)) (the parametric part of
+// scran::fitTrendVar), damped Gauss-Newton from theta = (A, B, N); same iteration as
+// trendvar._fit_parametric.  theta is updated in place.  Returns 0, or 2 when the start point is not
+// finite (the caller keeps the start values, as scran does when nls() fails).
+static bool solve3(const double a[3][3], const double g[3], double x[3])
+{
+    double m[3][4];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            m[i][j] = a[i][j];
+        m[i][3] = g[i];
+    }
+    for (int c = 0; c < 3; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 3; ++r)
+            if (std::fabs(m[r][c]) > std::fabs(m[piv][c]))
+                piv = r;
+        if (!(std::fabs(m[piv][c]) > 0.0) || !std::isfinite(m[piv][c]))
+            return false;
+        for (int j = 0; j < 4; ++j)
+            std::swap(m[c][j], m[piv][j]);
+        for (int r = c + 1; r < 3; ++r) {
+            const double f = m[r][c] / m[c][c];
+            for (int j = c; j < 4; ++j)
+                m[r][j] -= f * m[c][j];
+        }
+    }
+    for (int c = 2; c >= 0; --c) {
+        double t = m[c][3];
+        for (int j = c + 1; j < 3; ++j)
+            t -= m[c][j] * x[j];
+        x[c] = t / m[c][c];
+    }
+    return std::isfinite(x[0]) && std::isfinite(x[1]) && std::isfinite(x[2]);
+}
+
+extern "C" int cb200_host_nls_trend(int64_t n64, const double *v, const double *m, const double *w, double *theta,
+                                    double tol, int maxiter)
+{
+    const int n = (int)n64;
+    if (n < 4 || v == nullptr || m == nullptr || w == nullptr || theta == nullptr)
+        return 1;
+    std::vector<double> logm(n), f(n), f2(n), j0(n), j1(n), j2(n), k0(n), k1(n), k2(n);
+    for (int i = 0; i < n; ++i)
+        logm[i] = std::log(m[i]);
+    auto evaluate = [&](const double *t, std::vector<double> &ff, std::vector<double> &a0, std::vector<double> &a1,
+                        std::vector<double> &a2, double &rss) {
+        const double ea = std::exp(t[0]), eb = std::exp(t[1]), en = std::exp(t[2]);
+        rss = 0.0;
+        bool ok = true;
+        for (int i = 0; i < n; ++i) {
+            const double p = std::exp((1.0 + en) * logm[i]);
+            const double den = p + eb;
+            const double fi = ea * m[i] / den;
+            ff[i] = fi;
+            a0[i] = fi;
+            a1[i] = -fi * eb / den;
+            a2[i] = -fi * p * logm[i] * en / den;
+            const double r = v[i] - fi;
+            rss += w[i] * r * r;
+            ok = ok && std::isfinite(fi) && std::isfinite(a1[i]) && std::isfinite(a2[i]);
+        }
+        return ok && std::isfinite(rss);
+    };
+    double rss;
+    if (!evaluate(theta, f, j0, j1, j2, rss))
+        return 2;
+    double damp = 1e-3;
+    for (int it = 0; it < maxiter; ++it) {
+        double a[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, g[3] = {0, 0, 0}, rr = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double jr[3] = {j0[i], j1[i], j2[i]};
+            const double r = v[i] - f[i];
+            rr += w[i] * r * r;
+            for (int p = 0; p < 3; ++p) {
+                g[p] += w[i] * jr[p] * r;
+                for (int q = 0; q < 3; ++q)
+                    a[p][q] += w[i] * jr[p] * jr[q];
+            }
+        }
+        // relative-offset criterion: |Q^T r|^2 = g^T (J^T W J)^-1 g
+        double x[3];
+        if (solve3(a, g, x)) {
+            const double num = g[0] * x[0] + g[1] * x[1] + g[2] * x[2];
+            if (std::sqrt(num / std::max(rr - num, 1e-300)) < tol)
+                break;
+        }
+        bool improved = false;
+        for (int tr = 0; tr < 40; ++tr) {
+            double ad[3][3];
+            for (int p = 0; p < 3; ++p)
+                for (int q = 0; q < 3; ++q)
+                    ad[p][q] = a[p][q] + (p == q ? damp * (a[p][p] + 1e-300) : 0.0);
+            double step[3];
+            if (!solve3(ad, g, step)) {
+                damp *= 10.0;
+                continue;
+            }
+            const double t2[3] = {theta[0] + step[0], theta[1] + step[1], theta[2] + step[2]};
+            double rss2;
+            if (evaluate(t2, f2, k0, k1, k2, rss2) && rss2 < rss) {
+                theta[0] = t2[0];
+                theta[1] = t2[1];
+                theta[2] = t2[2];
+                f.swap(f2);
+                j0.swap(k0);
+                j1.swap(k1);
+                j2.swap(k2);
+                rss = rss2;
+                damp = std::max(damp / 10.0, 1e-12);
+                improved = true;
+                break;
+            }
+            damp *= 10.0;
+        }
+        if (!improved)
+            break;
+    }
+    return 0;
+}

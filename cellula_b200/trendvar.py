@@ -74,6 +74,13 @@ def _fit_parametric(v, m, w, tol=1e-9, maxiter=500):
     """Weighted least squares of v ~ exp(A) m / (m^(1+exp(N)) + exp(B)), damped Gauss-Newton."""
     a0, b0, n0 = _start_values(v, m)
     th = np.array([math.log(a0), math.log(b0), math.log(max(n0 - 1.0, 1e-8))])
+    native = _native("cb200_host_nls_trend")
+    if native is not None:   # same iteration in C++ (csrc/cb200_host.cu)
+        vc, mc, wc = np.ascontiguousarray(v), np.ascontiguousarray(m), np.ascontiguousarray(w)
+        tc = th.copy()
+        rc = native(v.size, vc.ctypes.data, mc.ctypes.data, wc.ctypes.data, tc.ctypes.data, float(tol), int(maxiter))
+        if rc in (0, 2):
+            return np.exp(tc)
     logm = np.log(m)
 
     def evaluate(t):

@@ -202,6 +202,10 @@ int cb200_export_csc(cb200_ctx *ctx, int64_t *colptr, int32_t *rowidx, double *v
 int cb200_host_weighted_lowess(int64_t n, const double *x_sorted, const double *y, const double *w, double span,
                                int iterations, int npts, double *fitted_out);
 /* Gaussian kernel density of m[0..n) on `ng` uniform grid points in [lo, hi] (stats::density stand-in). */
+/* Parametric mean-variance trend of scran::fitTrendVar: weighted least squares of
+ * v ~ exp(A) m / (m^(1+exp(N)) + exp(B)), theta = (A, B, N) updated in place from its start value. */
+int cb200_host_nls_trend(int64_t n, const double *v, const double *m, const double *w, double *theta, double tol,
+                         int maxiter);
 int cb200_host_gauss_kde(int64_t n, const double *m, double bw, double lo, double hi, int ng, double *dens_out);
 
 #ifdef __cplusplus
