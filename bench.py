@@ -209,6 +209,9 @@ def main():
     n_edges_local = int(res["edges"])
     fallback_q = tm["knn_fallback_queries"]
     eig_iters = tm["eig_iterations"]
+    tiles_scanned, tiles_total = tm["knn_tiles_scanned"], tm["knn_tiles_total"]
+    engines = dict(gram={1: "fp64-l2-red", 2: "fp64-smem-tiles", 3: "tcgen05-int8-digits"}.get(tm["gram_engine"]),
+                   knn={1: "fp32-cuda-cores", 2: "tcgen05-fp16-split"}.get(tm["knn_engine"]))
 
     # ---- e2e leg: host buffers in, host results out, through the C ABI ----
     e2e = None
@@ -280,12 +283,20 @@ def main():
     if rank == 0:
         peaks = read_peaks()
         stage_ms = {k: v / args.steps for k, v in stage_sum.items()}
-        # dominant kernel: the kNN distance-tile kernel (k_knn_tiles): 2 * n_query * N * d flop per launch
+        # dominant kernel: the kNN distance-tile kernel (k_knn_tiles_tc): ALGORITHMIC work 2 * n_query * N * d flop
+        # per launch (the full distance matrix; tiles skipped by the exact PC-1 bound still count as answered)
         flop = 2.0 * n_local * w["cells"] * w["ndims"]
         knn_ms = stage_ms["knn_tile_ms"]
         achieved_tf = flop / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else 0.0
-        roofline = dict(bound="tensor", kernel="k_knn_tiles", achieved=achieved_tf, peak=peaks["tf_sustained"],
-                        unit="TFLOP/s", frac=achieved_tf / peaks["tf_sustained"], traffic=None,
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu capture of this kernel, when it matches this run
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_knn_tiles_tc"]
+            if tj["workload"] == args.workload and tj["n_gpus"] == world:
+                traffic = tj["bytes_per_launch"]
+        except Exception:
+            traffic = None
+        roofline = dict(bound="tensor", kernel="k_knn_tiles_tc", achieved=achieved_tf, peak=peaks["tf_sustained"],
+                        unit="TFLOP/s", frac=achieved_tf / peaks["tf_sustained"], traffic=traffic,
                         peak_source=peaks["source"] + " bf16 sustained",
                         share_of_step=knn_ms / dev_ms if dev_ms > 0 else None)
         # memory-bound stages against the measured HBM copy bandwidth (algorithmic bytes)
@@ -301,7 +312,8 @@ def main():
                     config=dict(workload=args.workload, **w, hvg_ntop=HVG_NTOP, nnz_local=nnz, n_edges=n_edges,
                                 l2="inputs larger than L2 (no flush)", parallelism=f"cells sharded x{world}",
                                 knn_fallback_queries=int(fallback_q), eig_iterations=int(eig_iters),
-                                size_factors="library"),
+                                knn_tiles_scanned_rank0=int(tiles_scanned), knn_tiles_total_rank0=int(tiles_total),
+                                engines=engines, size_factors="library"),
                     clocks=sampler.summary(), gpu_launches=launches_all // max(args.steps, 1) * args.steps,
                     stage_ms=stage_ms, hbm_stages=hbm, roofline=roofline)
         if e2e:
