@@ -113,10 +113,19 @@ struct cb200_ctx {
     DevBuf<double> emb;        // [n_total*d] row-major fp64 (when given from host)
     DevBuf<double> stage_d;    // staging for column-major <-> row-major conversions
     DevBuf<float> emb_f;       // [n_total*DP] fp32 padded
-    DevBuf<int32_t> knn_perm, knn_bkt, knn_hist, knn_qlist, knn_qpos;  // PC-1 ordering of the references
+    DevBuf<int32_t> knn_perm, knn_bkt, knn_hist, knn_qlist, knn_qpos;  // cluster ordering of the references
     DevBuf<unsigned long long> knn_cursor;
     DevBuf<int64_t> knn_qoff;
-    DevBuf<float> knn_tile_lo, knn_tile_hi;  // PC-1 interval of every reference tile
+    DevBuf<float> knn_tile_lo, knn_tile_hi;  // range of the distance to the cluster centre over every reference tile
+    DevBuf<double> knn_cen, knn_km_sums;     // [C*d] cluster centres (scaled units), Lloyd accumulators
+    DevBuf<unsigned long long> knn_km_cnt;   // [C]
+    DevBuf<float> knn_dqc;                   // [n*C] distance of every point to every cluster centre
+    DevBuf<int32_t> knn_cl;                  // [n] cluster of every point
+    DevBuf<float> knn_rho;                   // [n] distance to the own cluster centre
+    DevBuf<unsigned int> knn_cl_rhomax;      // [C] float bits of the largest rho of the cluster
+    DevBuf<int32_t> knn_cl_tile_begin;       // [C+1] first (padded) tile of every cluster
+    DevBuf<int64_t> knn_pad_before;          // [C] padding positions ahead of the cluster
+    DevBuf<uint16_t> knn_cl_order;           // [C*C] clusters by ascending centre distance from cluster h
     DevBuf<unsigned char> knn_img;  // tensor-core operand image of the references (cb200_knn_tc.cu)
     DevBuf<float> hnorm;       // [n_total]   0.5*|r|^2 (fp32)
     DevBuf<double> nrm2;       // [n_total]   |r|^2 (fp64)

@@ -98,6 +98,9 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->emb.release(); ctx->stage_d.release(); ctx->emb_f.release(); ctx->knn_img.release(); ctx->knn_perm.release(); ctx->knn_bkt.release(); ctx->knn_hist.release();
     ctx->knn_qlist.release(); ctx->knn_qpos.release(); ctx->knn_cursor.release(); ctx->knn_qoff.release();
     ctx->knn_tile_lo.release(); ctx->knn_tile_hi.release(); ctx->hnorm.release();
+    ctx->knn_cen.release(); ctx->knn_km_sums.release(); ctx->knn_km_cnt.release(); ctx->knn_dqc.release();
+    ctx->knn_cl.release(); ctx->knn_rho.release(); ctx->knn_cl_rhomax.release(); ctx->knn_cl_tile_begin.release();
+    ctx->knn_pad_before.release(); ctx->knn_cl_order.release();
     ctx->nrm2.release(); ctx->maxnrm.release(); ctx->cand_idx.release(); ctx->cand_tau.release();
     ctx->knn.release(); ctx->knn_dk.release(); ctx->fb_list.release(); ctx->stage_i.release();
     ctx->index0.release(); ctx->rcnt.release(); ctx->rptr.release(); ctx->rcur.release();

@@ -23,14 +23,17 @@
 // sets of 4 warps, one per TMEM accumulator stage; within a set warp w owns TMEM lane quarter w % 4 and
 // a thread is one query row.
 //
-// Pruning (exact).  The points are ordered by their first coordinate (PC 1, the direction of largest
-// variance) with a counting sort, so a query tile is a narrow PC-1 interval and reference tile t covers
-// [lo_t, hi_t].  Since d(q, r) >= |q_1 - r_1|, a tile whose PC-1 interval is farther from every row of
-// the query tile than that row's current KP-th candidate distance cannot contribute.  The producer
-// walks outwards from the query tile's own position (t0, t0+1, t0-1, ...) and stops a direction for
-// good once the epilogue warps report that nothing beyond is within reach -- the MMA and epilogue work
-// of those tiles is never issued.  The bound uses exact quantities only (rounded outwards), so the
-// pruned references satisfy key_exact >= threshold and the margin proof of k_knn_rerank still holds.
+// Pruning (exact).  The references are partitioned into C clusters (a few Lloyd iterations on a
+// sample; any partition is valid) and sorted by (cluster, rho = distance to the cluster centre);
+// clusters are padded to whole tiles, so tile t belongs to one cluster j and covers rho in
+// [lo_t, hi_t].  By the triangle inequality d(q, r) >= |d(q, c_j) - rho_r|, so a tile can hold a
+// candidate of row q only if  d(q, c_j) - reach_q <= hi_t  and  d(q, c_j) + reach_q >= lo_t, where
+// reach_q is the distance of the row's current KP-th candidate.  d(q, c_j) comes from a table
+// computed in fp64 (k_knn_tc_assign).  The producer warp (lane = 4 query rows) visits the clusters
+// by ascending centre distance from the query tile's own cluster -- the thresholds settle inside
+// the first cluster -- and stages only the tiles some row can still reach; the MMA and epilogue work
+// of the others is never issued.  All quantities are rounded outwards, so the pruned references
+// satisfy key_exact >= threshold and the margin proof of k_knn_rerank still holds.
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -67,96 +70,242 @@ __device__ __forceinline__ void split_h(double x, __half &hi, __half &lo)
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// ordering by the first coordinate: counting sort into 2^16 buckets
+// ordering of the references: C clusters (a few Lloyd iterations on a strided sample), points
+// sorted by (cluster, distance to the cluster centre) with a counting sort into 2^16 buckets,
+// every cluster padded to whole tiles
 // ---------------------------------------------------------------------------------------
 #define TC_BUCKETS 65536
+#define TC_MAXC 1024       // clusters at most
+#define TC_KM_CHUNK 32     // centres staged per pass of k_knn_tc_assign
+#define TC_KM_J 8          // centres per register block
 
-// order-preserving map double -> uint64
-__device__ __forceinline__ unsigned long long ord_bits(double v)
-{
-    const long long b = __double_as_longlong(v);
-    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ULL);
-}
-
-// max |x| over the embedding and min / max of the first coordinate
+// max |x| over the embedding
 __global__ void k_knn_tc_ranges(const double *__restrict__ E, int64_t lde, int64_t n, int d,
-                                unsigned long long *__restrict__ out3)
+                                unsigned long long *__restrict__ out)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     double m = 0.0;
-    unsigned long long lo = ~0ULL, hi = 0ULL;
     if (i < n) {
         for (int t = 0; t < d; ++t) {
             const double v = E[i * lde + t];
             m = (v != v) ? 1.0 / 0.0 : fmax(m, fabs(v));  // NaN must not slip through fmax
         }
-        lo = hi = ord_bits(E[i * lde]);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 16; o > 0; o >>= 1)
         m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
-        lo = l2 < lo ? l2 : lo;
-        hi = h2 > hi ? h2 : hi;
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (m > 0.0)
-            atomicMax(out3, (unsigned long long)__double_as_longlong(m));
-        atomicMin(out3 + 1, lo);
-        atomicMax(out3 + 2, hi);
+    if ((threadIdx.x & 31) == 0 && m > 0.0)
+        atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// initial centres: C points taken at equal strides (scaled units)
+__global__ void k_knn_tc_km_init(const double *__restrict__ E, int64_t lde, int64_t n, int d, double scale, int C,
+                                 double *__restrict__ cen)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < C * d) {
+        const int j = idx / d, t = idx % d;
+        const int64_t i = (int64_t)(((2 * (int64_t)j + 1) * n) / (2 * (int64_t)C));
+        cen[idx] = E[i * lde + t] * scale;
     }
 }
 
-__global__ void k_knn_tc_bucket(const double *__restrict__ E, int64_t lde, int64_t n, double lo, double inv_width,
-                                int32_t *__restrict__ bkt, int32_t *__restrict__ hist)
+// Distances of the points i = m*stride (m < M) to all C centres in fp64 (scaled units).
+// FINAL = false: one Lloyd step (accumulate the points of every cluster).
+// FINAL = true : write the distance table dqc[i*C + j] (fp32, round to nearest), the cluster of
+//                every point (ties -> lowest j), its distance rho to that centre and the largest
+//                rho of every cluster.
+template <bool FINAL>
+__global__ void __launch_bounds__(128)
+k_knn_tc_assign(const double *__restrict__ E, int64_t lde, int64_t n, int d, double scale, int64_t stride, int64_t M,
+                int C, const double *__restrict__ cen, double *__restrict__ sums, unsigned long long *__restrict__ cnts,
+                float *__restrict__ dqc, int32_t *__restrict__ cl, float *__restrict__ rho,
+                unsigned int *__restrict__ cl_rhomax)
+{
+    __shared__ __align__(16) double cs[TC_K][TC_KM_CHUNK];  // centre chunk, [t][j]
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = m * stride;
+    const bool valid = m < M && i < n;
+    double x[TC_K];
+#pragma unroll
+    for (int t = 0; t < TC_K; ++t)
+        x[t] = (valid && t < d) ? E[i * lde + t] * scale : 0.0;
+    double best = 1.0 / 0.0;
+    int bj = 0;
+    for (int j0 = 0; j0 < C; j0 += TC_KM_CHUNK) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < TC_K * TC_KM_CHUNK; e += blockDim.x) {
+            const int jj = e % TC_KM_CHUNK, t = e / TC_KM_CHUNK;
+            cs[t][jj] = (j0 + jj < C && t < d) ? cen[(size_t)(j0 + jj) * d + t] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int jb = 0; jb < TC_KM_CHUNK && j0 + jb < C; jb += TC_KM_J) {
+            double acc[TC_KM_J];
+#pragma unroll
+            for (int u = 0; u < TC_KM_J; ++u)
+                acc[u] = 0.0;
+#pragma unroll
+            for (int t = 0; t < TC_K; ++t) {
+                if (t < d) {
+#pragma unroll
+                    for (int u = 0; u < TC_KM_J; u += 2) {
+                        const double2 c2 = *reinterpret_cast<const double2 *>(&cs[t][jb + u]);
+                        const double d0 = x[t] - c2.x, d1 = x[t] - c2.y;
+                        acc[u] = fma(d0, d0, acc[u]);
+                        acc[u + 1] = fma(d1, d1, acc[u + 1]);
+                    }
+                }
+            }
+            float f[TC_KM_J];
+#pragma unroll
+            for (int u = 0; u < TC_KM_J; ++u) {
+                const double dist = sqrt(acc[u]);
+                f[u] = (float)dist;
+                if (j0 + jb + u < C && dist < best) {
+                    best = dist;
+                    bj = j0 + jb + u;
+                }
+            }
+            if (FINAL && valid) {
+                float *out = dqc + (size_t)i * C + j0 + jb;
+                if (j0 + jb + TC_KM_J <= C && (C & 3) == 0) {
+                    *reinterpret_cast<float4 *>(out) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4 *>(out + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < TC_KM_J; ++u)
+                        if (j0 + jb + u < C)
+                            out[u] = f[u];
+                }
+            }
+        }
+    }
+    if (!valid)
+        return;
+    if (FINAL) {
+        cl[i] = bj;
+        const float r = (float)best;
+        rho[i] = r;
+        atomicMax(cl_rhomax + bj, __float_as_uint(r));  // r >= 0: the bit patterns are ordered
+    } else {
+        atomicAdd(cnts + bj, 1ULL);
+#pragma unroll
+        for (int t = 0; t < TC_K; ++t)
+            if (t < d)
+                atomicAdd(sums + (size_t)bj * d + t, x[t]);
+    }
+}
+
+// centres <- mean of the assigned sample points (an empty cluster keeps its centre)
+__global__ void k_knn_tc_km_update(int C, int d, const double *__restrict__ sums,
+                                   const unsigned long long *__restrict__ cnts, double *__restrict__ cen)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < C * d) {
+        const unsigned long long c = cnts[idx / d];
+        if (c > 0)
+            cen[idx] = sums[idx] / (double)c;
+    }
+}
+
+// bucket = cluster * B + bin of rho within [0, rhomax of the cluster]
+__global__ void k_knn_tc_bucket(int64_t n, int B, const int32_t *__restrict__ cl, const float *__restrict__ rho,
+                                const unsigned int *__restrict__ cl_rhomax, int32_t *__restrict__ bkt,
+                                int32_t *__restrict__ hist)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) {
-        double f = (E[i * lde] - lo) * inv_width;
-        int b = (int)f;
-        b = b < 0 ? 0 : (b >= TC_BUCKETS ? TC_BUCKETS - 1 : b);
-        bkt[i] = b;
-        atomicAdd(hist + b, 1);
+        const int c = cl[i];
+        const float rm = __uint_as_float(cl_rhomax[c]);
+        int b = rm > 0.f ? (int)(rho[i] / rm * (float)B) : 0;
+        b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+        const int bk = c * B + b;
+        bkt[i] = bk;
+        atomicAdd(hist + bk, 1);
     }
 }
 
-// perm[sorted position] = original index (order inside a bucket is arbitrary: tile bounds are taken
-// from the actual values, and every tie-break of the final result uses original indices)
-__global__ void k_knn_tc_scatter(const int32_t *__restrict__ bkt, int64_t n, unsigned long long *__restrict__ cursor,
+// every cluster starts on a tile boundary: first tile of every cluster and the number of padding
+// positions ahead of it (one thread; C <= 256)
+__global__ void k_knn_tc_layout(int C, int B, const unsigned long long *__restrict__ cursor,
+                                int32_t *__restrict__ cl_tile_begin, int64_t *__restrict__ pad_before)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int64_t tiles = 0;
+        for (int c = 0; c < C; ++c) {
+            const int64_t p0 = (int64_t)cursor[(size_t)c * B], p1 = (int64_t)cursor[(size_t)(c + 1) * B];
+            cl_tile_begin[c] = (int32_t)tiles;
+            pad_before[c] = tiles * TC_N - p0;
+            tiles += (p1 - p0 + TC_N - 1) / TC_N;
+        }
+        cl_tile_begin[C] = (int32_t)tiles;
+    }
+}
+
+// perm[sorted position] = original index, -1 at the padding positions (order inside a bucket is
+// arbitrary: tile bounds are taken from the actual values, and every tie-break of the final result
+// uses original indices)
+__global__ void k_knn_tc_scatter(const int32_t *__restrict__ bkt, int64_t n, int B,
+                                 unsigned long long *__restrict__ cursor, const int64_t *__restrict__ pad_before,
                                  int32_t *__restrict__ perm)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) {
-        const unsigned long long pos = atomicAdd(cursor + bkt[i], 1ULL);
-        perm[pos] = (int32_t)i;
+        const int bk = bkt[i];
+        const unsigned long long pos = atomicAdd(cursor + bk, 1ULL);
+        perm[(int64_t)pos + pad_before[bk / B]] = (int32_t)i;
+    }
+}
+
+// clusters by ascending centre distance from cluster h (block h)
+__global__ void __launch_bounds__(TC_MAXC)
+k_knn_tc_corder(int C, int d, const double *__restrict__ cen, uint16_t *__restrict__ order)
+{
+    __shared__ double dist[TC_MAXC];
+    const int h = blockIdx.x, j = threadIdx.x;
+    double s = 0.0;
+    if (j < C) {
+        for (int t = 0; t < d; ++t) {
+            const double df = cen[(size_t)h * d + t] - cen[(size_t)j * d + t];
+            s += df * df;
+        }
+        dist[j] = s;
+    }
+    __syncthreads();
+    if (j < C) {
+        int rank = 0;
+        for (int o = 0; o < C; ++o)
+            rank += (dist[o] < s || (dist[o] == s && o < j)) ? 1 : 0;
+        order[(size_t)h * C + rank] = (uint16_t)j;
     }
 }
 
 // queries of [q_begin, q_end) in sorted order: flag, (scan), scatter
-__global__ void k_knn_tc_qflag(const int32_t *__restrict__ perm, int64_t n, int64_t q_begin, int64_t q_end,
+__global__ void k_knn_tc_qflag(const int32_t *__restrict__ perm, int64_t npos, int64_t q_begin, int64_t q_end,
                                int32_t *__restrict__ flag)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n)
+    if (i < npos)
         flag[i] = (perm[i] >= q_begin && perm[i] < q_end) ? 1 : 0;
 }
 __global__ void k_knn_tc_qscatter(const int32_t *__restrict__ perm, const int32_t *__restrict__ flag,
-                                  const int64_t *__restrict__ off, int64_t n, int32_t *__restrict__ qlist,
+                                  const int64_t *__restrict__ off, int64_t npos, int32_t *__restrict__ qlist,
                                   int32_t *__restrict__ qpos)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n && flag[i]) {
+    if (i < npos && flag[i]) {
         qlist[off[i]] = perm[i];
         qpos[off[i]] = (int32_t)i;
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// reference image in sorted order: one block = one tile of 128 points, one thread per point
+// reference image in sorted order: one block = one tile of 128 positions, one thread per point
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, double scale,
-              const int32_t *__restrict__ perm, unsigned char *__restrict__ img, double *__restrict__ nrm2,
+k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, const int32_t *__restrict__ perm,
+              const float *__restrict__ rho, unsigned char *__restrict__ img, double *__restrict__ nrm2,
               unsigned long long *__restrict__ maxbits, float *__restrict__ tile_lo, float *__restrict__ tile_hi)
 {
     __shared__ float smin[4], smax[4];
@@ -165,9 +314,8 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, doubl
     const int row = threadIdx.x;
     __half *hi_base = reinterpret_cast<__half *>(tile);
     __half *lo_base = reinterpret_cast<__half *>(tile + TC_PART_BYTES);
-    const int64_t src = i < n ? (int64_t)perm[i] : -1;
+    const int64_t src = (int64_t)perm[i];  // -1: padding position
     double s = 0.0, sp = 0.0;
-    float c0lo = FLT_MAX, c0hi = -FLT_MAX;
     for (int t = 0; t < TC_K; ++t) {
         __half h = __float2half(0.f), l = __float2half(0.f);
         if (src >= 0 && t < d) {
@@ -176,11 +324,6 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, doubl
             const double vs = v * scale;
             sp += vs * vs;
             split_h(vs, h, l);
-            if (t == 0) {  // bounds of the scaled first coordinate, one ulp outwards
-                const float f = (float)vs;
-                c0lo = nextafterf(f, -FLT_MAX);
-                c0hi = nextafterf(f, FLT_MAX);
-            }
         }
         const uint32_t off = swz_offset(row, t * 2);
         *reinterpret_cast<__half *>(reinterpret_cast<unsigned char *>(hi_base) + off) = h;
@@ -188,6 +331,7 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, doubl
     }
     // -0.5|r'|^2 in the three spare K columns of the hi part
     __half a1, a2, a3;
+    float rlo = INFINITY, rhi = -INFINITY;  // an all-padding tile is never needed
     if (src >= 0) {
         const double hn = 0.5 * sp;
         a1 = __double2half(hn * (1.0 / 4096.0));
@@ -197,8 +341,12 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, doubl
         a3 = __double2half(r2 * 4096.0);
         nrm2[src] = s;
         atomicMax(maxbits, (unsigned long long)__double_as_longlong(s));
+        // distance to the cluster centre, one fp32 ulp outwards (the table holds round-to-nearest values)
+        const float r = rho[src];
+        rlo = fmaxf(nextafterf(r, -FLT_MAX), 0.f);
+        rhi = nextafterf(r, FLT_MAX);
     } else {
-        a1 = __float2half(65504.f);  // padding rows: T = -2.7e8, never selected
+        a1 = __float2half(65504.f);  // padding rows: T = -2.7e8, below every real reference
         a2 = __float2half(0.f);
         a3 = __float2half(0.f);
     }
@@ -206,15 +354,14 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int64_t n, int d, doubl
     *reinterpret_cast<__half *>(hb + swz_offset(row, (d + 0) * 2)) = __hneg(a1);
     *reinterpret_cast<__half *>(hb + swz_offset(row, (d + 1) * 2)) = __hneg(a2);
     *reinterpret_cast<__half *>(hb + swz_offset(row, (d + 2) * 2)) = __hneg(a3);
-    // PC-1 interval of the tile
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        c0lo = fminf(c0lo, __shfl_xor_sync(0xffffffffu, c0lo, o));
-        c0hi = fmaxf(c0hi, __shfl_xor_sync(0xffffffffu, c0hi, o));
+        rlo = fminf(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+        rhi = fmaxf(rhi, __shfl_xor_sync(0xffffffffu, rhi, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        smin[threadIdx.x >> 5] = c0lo;
-        smax[threadIdx.x >> 5] = c0hi;
+        smin[threadIdx.x >> 5] = rlo;
+        smax[threadIdx.x >> 5] = rhi;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -279,10 +426,12 @@ constexpr int TC_RING = 16;  // tile ids of the sequence in flight (producer -> 
 template <int KP, int SETS, int STAGES>
 __global__ void __launch_bounds__(tc_threads(SETS), 1)
 k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, const unsigned char *__restrict__ img,
-               int64_t n, int64_t nq, const int32_t *__restrict__ qlist, const int32_t *__restrict__ qpos,
-               const int32_t *__restrict__ perm, const float *__restrict__ tile_lo, const float *__restrict__ tile_hi,
-               float key_unscale, int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau,
-               int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done)
+               int64_t nq, const int32_t *__restrict__ qlist, const int32_t *__restrict__ qpos,
+               const int32_t *__restrict__ perm, int C, const float *__restrict__ dqc, const int32_t *__restrict__ cl,
+               const uint16_t *__restrict__ cl_order, const int32_t *__restrict__ cl_tile_begin,
+               const unsigned int *__restrict__ cl_rhomax, const float *__restrict__ tile_lo,
+               const float *__restrict__ tile_hi, float key_unscale, int32_t *__restrict__ cand_idx,
+               float *__restrict__ cand_tau, int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done)
 {
     constexpr int EPL = KP / 32;
     constexpr int TC_SETS = SETS, TC_ACC_STAGES = SETS, TC_THREADS = tc_threads(SETS);
@@ -298,14 +447,11 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     uint64_t *tfull = bars + 2 * STAGES;         // [TC_ACC_STAGES]
     uint64_t *tempty = tfull + TC_ACC_STAGES;    // [TC_ACC_STAGES]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + TC_ACC_STAGES);
-    float *thr_sh = reinterpret_cast<float *>(tmem_slot + 4);  // [SETS][TC_M] thresholds published by the sets
-    volatile float *reach_r = thr_sh + TC_SETS * TC_M;         // [SETS*4] largest PC-1 value a warp still needs
-    volatile float *reach_l = reach_r + TC_SETS * 4;           // [SETS*4] smallest PC-1 value a warp still needs
-    volatile int *seq_tile = reinterpret_cast<volatile int *>(reach_l + TC_SETS * 4);  // [TC_RING]
+    volatile float *thr_sh = reinterpret_cast<volatile float *>(tmem_slot + 4);  // [SETS][TC_M] thresholds published by the sets
+    volatile int *seq_tile = reinterpret_cast<volatile int *>(const_cast<float *>(thr_sh) + TC_SETS * TC_M);  // [TC_RING]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ql0 = (int64_t)blockIdx.x * TC_M;   // first entry of the (sorted) query list
-    const int64_t n_tiles = (n + TC_N - 1) / TC_N;
 
     // ---- one-time setup ------------------------------------------------------------------
     // query operand image (generic-proxy stores, made visible to the async proxy below)
@@ -335,10 +481,6 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     }
     for (int i = tid; i < TC_SETS * TC_M; i += TC_THREADS)
         thr_sh[i] = -FLT_MAX;
-    if (tid < TC_SETS * 4) {
-        reach_r[tid] = FLT_MAX;    // nothing can be pruned before thresholds exist
-        reach_l[tid] = -FLT_MAX;
-    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full + s, 1);
@@ -359,45 +501,121 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== producer: walks the reference tiles outwards from the query tile's own position =====
-        if (lane == 0) {
-            const int64_t nvalid = nq - ql0 < TC_M ? nq - ql0 : TC_M;
-            const int64_t qmid = ql0 + nvalid / 2;
-            const int64_t tc = (qpos != nullptr ? (int64_t)qpos[qmid] : qmid) / TC_N;
-            int64_t tr = tc, tl = tc - 1, seq = 0;
-            bool right_done = false, left_done = false, take_right = true;
-            while (true) {
-                float rr = -FLT_MAX, rl = FLT_MAX;
+        // ===== producer: visits the clusters by ascending centre distance from the query tile's own
+        // cluster and stages only the tiles some row can still reach (whole warp: lane = 4 query rows) =====
+        constexpr float EPS = 3e-7f;
+        int64_t g[4];
+        float qn[4], dlo[4], dhi[4], lo[4], hi[4];
 #pragma unroll
-                for (int w2 = 0; w2 < TC_SETS * 4; ++w2) {
-                    rr = fmaxf(rr, reach_r[w2]);
-                    rl = fminf(rl, reach_l[w2]);
+        for (int u = 0; u < 4; ++u) {
+            const int64_t ql = ql0 + u * 32 + lane;
+            g[u] = ql < nq ? (int64_t)qlist[ql] : -1;
+            qn[u] = 0.f;
+            if (g[u] >= 0) {
+                double sp = 0.0;
+                for (int t = 0; t < d; ++t) {
+                    const double vs = E[g[u] * lde + t] * scale;
+                    sp += vs * vs;
                 }
-                if (tr >= n_tiles || (!right_done && tile_lo[tr] > rr))
-                    right_done = true;
-                if (tl < 0 || (!left_done && tile_hi[tl] < rl))
-                    left_done = true;
-                if (right_done && left_done)
-                    break;
-                const bool go_right = right_done ? false : (left_done ? true : take_right);
-                take_right = !go_right;
-                const int64_t t = go_right ? tr++ : tl--;
-                const int s = (int)(seq % STAGES);
-                const uint32_t ph = (uint32_t)((seq / STAGES) & 1);
-                mbar_wait(empty + s, ph ^ 1u, err_flag);
-                seq_tile[seq % TC_RING] = (int)t;
-                mbar_expect_tx(full + s, TC_TILE_BYTES);
-                bulk_g2s(r_img + (size_t)s * TC_TILE_BYTES, img + t * (int64_t)TC_TILE_BYTES, TC_TILE_BYTES, full + s);
-                ++seq;
+                qn[u] = nextafterf((float)(0.5 * sp), FLT_MAX);
             }
-            // end of the sequence
+            dlo[u] = INFINITY;   // rows past the list need nothing
+            dhi[u] = -INFINITY;
+            lo[u] = INFINITY;
+            hi[u] = -INFINITY;
+        }
+        const int64_t nvalid = nq - ql0 < TC_M ? nq - ql0 : TC_M;
+        const int home = cl[qlist[ql0 + nvalid / 2]];
+        const uint16_t *order = cl_order + (size_t)home * C;
+        int64_t seq = 0;
+        int oi = 0, t = 0, te = 0, tb32 = 0;
+        float blo = 0.f, bhi = 0.f;   // bounds of tile tb32 + lane
+        float crmax = 0.f;
+        while (true) {
             const int s = (int)(seq % STAGES);
-            mbar_wait(empty + s, (uint32_t)((seq / STAGES) & 1) ^ 1u, err_flag);
+            if (lane == 0)
+                mbar_wait(empty + s, (uint32_t)((seq / STAGES) & 1) ^ 1u, err_flag);
+            __syncwarp();
+            // how far every row can still find a candidate: d <= sqrt(2 (key_thr + qn)), rounded up
+            float reach[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float thr = -FLT_MAX;
+#pragma unroll
+                for (int s2 = 0; s2 < TC_SETS; ++s2)
+                    thr = fmaxf(thr, thr_sh[s2 * TC_M + u * 32 + lane]);
+                reach[u] = thr == -FLT_MAX ? INFINITY
+                                           : sqrtf(fmaxf(2.0f * (qn[u] - thr), 0.f)) * 1.000002f + 1e-30f;
+                if (g[u] >= 0) {
+                    lo[u] = dlo[u] - reach[u];
+                    hi[u] = dhi[u] + reach[u];
+                }
+            }
+            bool found = false;
+            while (true) {
+                if (t >= te) {  // next cluster
+                    if (oi >= C)
+                        break;
+                    const int j = order[oi++];
+                    t = cl_tile_begin[j];
+                    te = cl_tile_begin[j + 1];
+                    if (t >= te)
+                        continue;
+                    crmax = __uint_as_float(cl_rhomax[j]) * (1.f + EPS);
+                    bool need = false;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (g[u] >= 0) {
+                            const float dq = dqc[(size_t)g[u] * C + j];
+                            dlo[u] = dq * (1.f - EPS);
+                            dhi[u] = dq * (1.f + EPS);
+                            lo[u] = dlo[u] - reach[u];
+                            hi[u] = dhi[u] + reach[u];
+                            need |= lo[u] <= crmax;
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, need)) {
+                        t = te;
+                        continue;
+                    }
+                    tb32 = t - 32;  // forces a load of the tile bounds below
+                }
+                if (t >= tb32 + 32) {
+                    tb32 = t;
+                    const int tt = t + lane;
+                    blo = tt < te ? tile_lo[tt] : INFINITY;
+                    bhi = tt < te ? tile_hi[tt] : -INFINITY;
+                }
+                const float a = __shfl_sync(0xffffffffu, blo, t - tb32);
+                const float b = __shfl_sync(0xffffffffu, bhi, t - tb32);
+                bool need = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    need |= (lo[u] <= b) && (hi[u] >= a);
+                if (__any_sync(0xffffffffu, need)) {
+                    found = true;
+                    break;
+                }
+                ++t;
+            }
+            if (!found)
+                break;
+            if (lane == 0) {
+                seq_tile[seq % TC_RING] = t;
+                mbar_expect_tx(full + s, TC_TILE_BYTES);
+                bulk_g2s(r_img + (size_t)s * TC_TILE_BYTES, img + (int64_t)t * TC_TILE_BYTES, TC_TILE_BYTES, full + s);
+            }
+            ++t;
+            ++seq;
+        }
+        // end of the sequence (the empty slot of stage seq % STAGES has been waited for above)
+        if (lane == 0) {
             seq_tile[seq % TC_RING] = -1;
             __threadfence_block();
-            mbar_arrive(full + s);
+            mbar_arrive(full + (int)(seq % STAGES));
             atomicAdd(tiles_done, (unsigned long long)seq);
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
@@ -451,20 +669,9 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         float *set_key = lkey + (size_t)set * TC_M * KP;
         int *set_idx = lidx + (size_t)set * TC_M * KP;
         float thr = active ? -FLT_MAX : FLT_MAX;   // T must exceed thr; rows past the list never select
-        // exact quantities of this row for the pruning bound, rounded so that the reach only grows
         int my_pos = -1;                           // sorted position of the query itself (self-exclusion)
-        float q1 = 0.f, qn = 0.f;                  // scaled first coordinate, 0.5 |q'|^2 (rounded up)
-        if (active) {
-            const int64_t g = qlist[myql];
-            my_pos = qpos != nullptr ? qpos[myql] : (int)myql;
-            double sp = 0.0;
-            for (int t = 0; t < d; ++t) {
-                const double vs = E[g * lde + t] * scale;
-                sp += vs * vs;
-            }
-            q1 = (float)(E[g * lde] * scale);
-            qn = nextafterf((float)(0.5 * sp), FLT_MAX);
-        }
+        if (active)
+            my_pos = qpos[myql];
         const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * TC_N);
         for (int64_t seq = set;; seq += TC_SETS) {
             const uint32_t aph = (uint32_t)((seq / TC_ACC_STAGES) & 1);
@@ -515,7 +722,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                             const float othr = __shfl_sync(0xffffffffu, thr, owner);
                             const int opos = __shfl_sync(0xffffffffu, my_pos, owner);
                             const int64_t gcol = c0 + i;
-                            if (val > othr && gcol < n && gcol != opos) {
+                            if (val > othr && gcol != opos) {
                                 const float kth = tc_insert<EPL>(set_key + (size_t)(quarter * 32 + owner) * KP,
                                                                  set_idx + (size_t)(quarter * 32 + owner) * KP, -val,
                                                                  (int)gcol, lane);
@@ -541,28 +748,6 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(tempty + set);
-            // how far along PC 1 this warp's rows can still find a candidate: d <= sqrt(2 (key_thr + qn))
-            float rr = -FLT_MAX, rl = FLT_MAX;
-            if (active) {
-                if (thr == -FLT_MAX) {
-                    rr = FLT_MAX;
-                    rl = -FLT_MAX;
-                } else {
-                    const float d2 = fmaxf(2.0f * (qn - thr), 0.f);           // key_thr = -thr
-                    const float reach = sqrtf(d2) * 1.000002f + fabsf(q1) * 4.8e-7f + 1e-30f;
-                    rr = q1 + reach;
-                    rl = q1 - reach;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                rr = fmaxf(rr, __shfl_xor_sync(0xffffffffu, rr, o));
-                rl = fminf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
-            }
-            if (lane == 0) {
-                reach_r[warp - 2] = rr;
-                reach_l[warp - 2] = rl;
-            }
         }
         // final: the lists are sorted; write this set's KP candidates (original indices) and the
         // threshold of every row (key space, unscaled: key = 0.5 d^2 - 0.5 |q|^2)
@@ -589,70 +774,91 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 // host side
 // ---------------------------------------------------------------------------------------
 template <int KP, int SETS, int STAGES>
-static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double scale, int64_t n, int64_t nq,
-                     const int32_t *qlist, const int32_t *qpos)
+static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double scale, int64_t nq, int C)
 {
     const size_t smem = (size_t)TC_TILE_BYTES * (1 + STAGES) + (size_t)SETS * TC_M * KP * 8 +
-                        (size_t)(2 * STAGES + 2 * SETS) * 8 + 16 + (size_t)SETS * TC_M * 4 + (size_t)SETS * 4 * 8 +
-                        (size_t)TC_RING * 4;
+                        (size_t)(2 * STAGES + 2 * SETS) * 8 + 16 + (size_t)SETS * TC_M * 4 + (size_t)TC_RING * 4;
     CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, SETS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     const unsigned grid = (unsigned)((nq + TC_M - 1) / TC_M);
     const float key_unscale = (float)(1.0 / (scale * scale));
     k_knn_tiles_tc<KP, SETS, STAGES><<<grid, tc_threads(SETS), smem, ctx->stream>>>(
-        E, lde, d, scale, ctx->knn_img.p, n, nq, qlist, qpos, ctx->knn_perm.p, ctx->knn_tile_lo.p, ctx->knn_tile_hi.p,
-        key_unscale, ctx->cand_idx.p, ctx->cand_tau.p, ctx->flag.p + 3, ctx->maxnrm.p + 3);
+        E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, C, ctx->knn_dqc.p,
+        ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p, ctx->knn_tile_lo.p,
+        ctx->knn_tile_hi.p, key_unscale, ctx->cand_idx.p, ctx->cand_tau.p, ctx->flag.p + 3, ctx->maxnrm.p + 3);
     CB_LAUNCH(ctx);
     return 0;
 }
 
 bool cb200_knn_tc_supported(int d, int k) { return d + 3 <= TC_K && k <= 52; }
 
-// Orders the references by their first coordinate, builds the operand image and runs the
-// tensor-core tile kernel; fills ctx->cand_idx / ctx->cand_tau (indexed by position in the sorted
-// query list), ctx->nrm2, ctx->maxnrm.  *kp_out = candidates kept per query, *ntau_out = thresholds
-// per query (every non-candidate has key >= the smallest of them), *qlist_out = original index of
-// every entry of the query list (device), *err_coef_out = coefficient of the a-priori key error bound.
+// number of clusters of the reference ordering: about one per 512 points (4 tiles), at most 256
+// (CB200_KNN_CLUSTERS overrides, up to TC_MAXC; any value gives the same, exact, result)
+static int tc_num_clusters(int64_t n)
+{
+    int64_t c = n / 512;
+    if (c > 256)
+        c = 256;
+    const char *e = getenv("CB200_KNN_CLUSTERS");
+    if (e != nullptr && atoi(e) > 0)
+        c = atoi(e);
+    if (c > TC_MAXC)
+        c = TC_MAXC;
+    if (c > n / 2)
+        c = n / 2;
+    if (c < 1)
+        c = 1;
+    return (int)c;
+}
+
+// Clusters and orders the references, builds the operand image and runs the tensor-core tile
+// kernel; fills ctx->cand_idx / ctx->cand_tau (indexed by position in the sorted query list),
+// ctx->nrm2, ctx->maxnrm.  *kp_out = candidates kept per query, *ntau_out = thresholds per query
+// (every non-candidate has key >= the smallest of them), *qlist_out = original index of every entry
+// of the query list (device), *err_coef_out = coefficient of the a-priori key error bound.
 int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int d, int k, int64_t q_begin,
                        int64_t q_end, int *kp_out, int *ntau_out, const int32_t **qlist_out, double *err_coef_out)
 {
     const int64_t nq = q_end - q_begin;
-    const int64_t n_tiles = (n + TC_N - 1) / TC_N;
+    const int C = tc_num_clusters(n);
+    const int B = TC_BUCKETS / C;
+    const int64_t n_tiles_cap = (n + TC_N - 1) / TC_N + C;  // every cluster is padded to whole tiles
+    const int64_t npos = n_tiles_cap * TC_N;
     const int KP = k <= 24 ? 32 : 64;
     const int SETS = KP == 32 ? 4 : 2;
-    CB_CUDA(ctx, ctx->knn_img.ensure((size_t)n_tiles * TC_TILE_BYTES));
+    CB_CUDA(ctx, ctx->knn_img.ensure((size_t)n_tiles_cap * TC_TILE_BYTES));
     CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
     CB_CUDA(ctx, ctx->cand_idx.ensure((size_t)nq * SETS * KP));
     CB_CUDA(ctx, ctx->cand_tau.ensure((size_t)nq * SETS));
-    CB_CUDA(ctx, ctx->knn_perm.ensure((size_t)n));
-    CB_CUDA(ctx, ctx->knn_bkt.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->knn_perm.ensure((size_t)npos));
+    CB_CUDA(ctx, ctx->knn_bkt.ensure((size_t)npos));
     CB_CUDA(ctx, ctx->knn_hist.ensure((size_t)TC_BUCKETS));
     CB_CUDA(ctx, ctx->knn_cursor.ensure((size_t)TC_BUCKETS + 1));
-    CB_CUDA(ctx, ctx->knn_tile_lo.ensure((size_t)n_tiles));
-    CB_CUDA(ctx, ctx->knn_tile_hi.ensure((size_t)n_tiles));
+    CB_CUDA(ctx, ctx->knn_tile_lo.ensure((size_t)n_tiles_cap));
+    CB_CUDA(ctx, ctx->knn_tile_hi.ensure((size_t)n_tiles_cap));
     CB_CUDA(ctx, ctx->maxnrm.ensure(4));
+    CB_CUDA(ctx, ctx->knn_cen.ensure((size_t)C * d));
+    CB_CUDA(ctx, ctx->knn_km_sums.ensure((size_t)C * d));
+    CB_CUDA(ctx, ctx->knn_km_cnt.ensure((size_t)C));
+    CB_CUDA(ctx, ctx->knn_dqc.ensure((size_t)n * C));
+    CB_CUDA(ctx, ctx->knn_cl.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->knn_rho.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->knn_cl_rhomax.ensure((size_t)C));
+    CB_CUDA(ctx, ctx->knn_cl_tile_begin.ensure((size_t)C + 1));
+    CB_CUDA(ctx, ctx->knn_pad_before.ensure((size_t)C));
+    CB_CUDA(ctx, ctx->knn_cl_order.ensure((size_t)C * C));
+    CB_CUDA(ctx, ctx->knn_qlist.ensure((size_t)nq));
+    CB_CUDA(ctx, ctx->knn_qpos.ensure((size_t)nq));
+    CB_CUDA(ctx, ctx->knn_qoff.ensure((size_t)npos + 1));
 
     cb_stage_begin(ctx, ST_KNN_PREP);
-    // ranges: [0] max |x| bits, [1] min of coordinate 0 (ordered bits), [2] max of coordinate 0
-    {
-        unsigned long long init[4] = {0ULL, ~0ULL, 0ULL, 0ULL};
-        CB_CUDA(ctx, cudaMemcpyAsync(ctx->maxnrm.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     const unsigned g256 = (unsigned)((n + 255) / 256);
     k_knn_tc_ranges<<<g256, 256, 0, ctx->stream>>>(E, lde, n, d, ctx->maxnrm.p);
     CB_LAUNCH(ctx);
-    unsigned long long r3[3];
-    CB_CUDA(ctx, cudaMemcpyAsync(r3, ctx->maxnrm.p, sizeof(r3), cudaMemcpyDeviceToHost, ctx->stream));
+    double maxabs = 0.0;
+    CB_CUDA(ctx, cudaMemcpyAsync(&maxabs, ctx->maxnrm.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    auto unord = [](unsigned long long u) {
-        const unsigned long long b = (u & 0x8000000000000000ULL) ? (u & 0x7fffffffffffffffULL) : ~u;
-        double v;
-        memcpy(&v, &b, sizeof(v));
-        return v;
-    };
-    double maxabs;
-    memcpy(&maxabs, &r3[0], sizeof(double));
-    const double c0min = unord(r3[1]), c0max = unord(r3[2]);
     CB_CHECK(ctx, maxabs == maxabs && maxabs < 1e300, "cb200_knn: embedding contains non-finite values");
     // power-of-two scale: max |x'| in [256, 512)
     double scale = 1.0;
@@ -661,48 +867,69 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
         frexp(maxabs, &e);          // maxabs = f * 2^e, f in [0.5, 1)
         scale = ldexp(1.0, 9 - e);  // maxabs * scale in [256, 512)
     }
-    // counting sort by the first coordinate
-    const double width = c0max - c0min;
-    const double inv_width = width > 0.0 ? (double)TC_BUCKETS / width * (1.0 - 1e-12) : 0.0;
+    // clusters: Lloyd iterations on a strided sample of at most 65536 points, then the distance table
+    const unsigned gcd = (unsigned)((C * d + 255) / 256);
+    k_knn_tc_km_init<<<gcd, 256, 0, ctx->stream>>>(E, lde, n, d, scale, C, ctx->knn_cen.p);
+    CB_LAUNCH(ctx);
+    if (C > 1) {
+        const int64_t stride = n > 65536 ? n / 65536 : 1;
+        const int64_t M = (n + stride - 1) / stride;
+        for (int it = 0; it < 4; ++it) {
+            CB_CUDA(ctx, cudaMemsetAsync(ctx->knn_km_sums.p, 0, (size_t)C * d * sizeof(double), ctx->stream));
+            CB_CUDA(ctx, cudaMemsetAsync(ctx->knn_km_cnt.p, 0, (size_t)C * sizeof(unsigned long long), ctx->stream));
+            k_knn_tc_assign<false><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(
+                E, lde, n, d, scale, stride, M, C, ctx->knn_cen.p, ctx->knn_km_sums.p, ctx->knn_km_cnt.p, nullptr, nullptr,
+                nullptr, nullptr);
+            CB_LAUNCH(ctx);
+            k_knn_tc_km_update<<<gcd, 256, 0, ctx->stream>>>(C, d, ctx->knn_km_sums.p, ctx->knn_km_cnt.p, ctx->knn_cen.p);
+            CB_LAUNCH(ctx);
+        }
+    }
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->knn_cl_rhomax.p, 0, (size_t)C * sizeof(unsigned int), ctx->stream));
+    k_knn_tc_assign<true><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+        E, lde, n, d, scale, 1, n, C, ctx->knn_cen.p, nullptr, nullptr, ctx->knn_dqc.p, ctx->knn_cl.p, ctx->knn_rho.p,
+        ctx->knn_cl_rhomax.p);
+    CB_LAUNCH(ctx);
+    k_knn_tc_corder<<<C, TC_MAXC, 0, ctx->stream>>>(C, d, ctx->knn_cen.p, ctx->knn_cl_order.p);
+    CB_LAUNCH(ctx);
+    // counting sort by (cluster, rho bin), clusters padded to whole tiles
     CB_CUDA(ctx, cudaMemsetAsync(ctx->knn_hist.p, 0, TC_BUCKETS * sizeof(int32_t), ctx->stream));
-    k_knn_tc_bucket<<<g256, 256, 0, ctx->stream>>>(E, lde, n, c0min, inv_width, ctx->knn_bkt.p, ctx->knn_hist.p);
+    k_knn_tc_bucket<<<g256, 256, 0, ctx->stream>>>(n, B, ctx->knn_cl.p, ctx->knn_rho.p, ctx->knn_cl_rhomax.p,
+                                                   ctx->knn_bkt.p, ctx->knn_hist.p);
     CB_LAUNCH(ctx);
     CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->knn_hist.p, TC_BUCKETS, reinterpret_cast<int64_t *>(ctx->knn_cursor.p)));
-    k_knn_tc_scatter<<<g256, 256, 0, ctx->stream>>>(ctx->knn_bkt.p, n, ctx->knn_cursor.p, ctx->knn_perm.p);
+    k_knn_tc_layout<<<1, 32, 0, ctx->stream>>>(C, B, ctx->knn_cursor.p, ctx->knn_cl_tile_begin.p, ctx->knn_pad_before.p);
     CB_LAUNCH(ctx);
-    // image, norms, tile intervals (maxnrm[0] becomes max |r|^2)
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->knn_perm.p, 0xFF, (size_t)npos * sizeof(int32_t), ctx->stream));
+    k_knn_tc_scatter<<<g256, 256, 0, ctx->stream>>>(ctx->knn_bkt.p, n, B, ctx->knn_cursor.p, ctx->knn_pad_before.p,
+                                                    ctx->knn_perm.p);
+    CB_LAUNCH(ctx);
+    // image, norms, tile bounds (maxnrm[0] becomes max |r|^2)
     CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    k_knn_tc_prep<<<(unsigned)n_tiles, 128, 0, ctx->stream>>>(E, lde, n, d, scale, ctx->knn_perm.p, ctx->knn_img.p,
-                                                              ctx->nrm2.p, ctx->maxnrm.p, ctx->knn_tile_lo.p,
-                                                              ctx->knn_tile_hi.p);
+    k_knn_tc_prep<<<(unsigned)n_tiles_cap, 128, 0, ctx->stream>>>(E, lde, d, scale, ctx->knn_perm.p, ctx->knn_rho.p,
+                                                                  ctx->knn_img.p, ctx->nrm2.p, ctx->maxnrm.p,
+                                                                  ctx->knn_tile_lo.p, ctx->knn_tile_hi.p);
     CB_LAUNCH(ctx);
-    // the query list: the cells of [q_begin, q_end) in sorted order
-    const int32_t *qlist = ctx->knn_perm.p, *qpos = nullptr;
-    if (!(q_begin == 0 && q_end == n)) {
-        CB_CUDA(ctx, ctx->knn_qlist.ensure((size_t)nq));
-        CB_CUDA(ctx, ctx->knn_qpos.ensure((size_t)nq));
-        CB_CUDA(ctx, ctx->knn_qoff.ensure((size_t)n + 1));
-        k_knn_tc_qflag<<<g256, 256, 0, ctx->stream>>>(ctx->knn_perm.p, n, q_begin, q_end, ctx->knn_bkt.p);
-        CB_LAUNCH(ctx);
-        CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->knn_bkt.p, n, ctx->knn_qoff.p));
-        k_knn_tc_qscatter<<<g256, 256, 0, ctx->stream>>>(ctx->knn_perm.p, ctx->knn_bkt.p, ctx->knn_qoff.p, n,
-                                                         ctx->knn_qlist.p, ctx->knn_qpos.p);
-        CB_LAUNCH(ctx);
-        qlist = ctx->knn_qlist.p;
-        qpos = ctx->knn_qpos.p;
-    }
+    // the query list: the cells of [q_begin, q_end) in sorted order, with their sorted positions
+    const unsigned gpos = (unsigned)((npos + 255) / 256);
+    k_knn_tc_qflag<<<gpos, 256, 0, ctx->stream>>>(ctx->knn_perm.p, npos, q_begin, q_end, ctx->knn_bkt.p);
+    CB_LAUNCH(ctx);
+    CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->knn_bkt.p, npos, ctx->knn_qoff.p));
+    k_knn_tc_qscatter<<<gpos, 256, 0, ctx->stream>>>(ctx->knn_perm.p, ctx->knn_bkt.p, ctx->knn_qoff.p, npos,
+                                                     ctx->knn_qlist.p, ctx->knn_qpos.p);
+    CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_KNN_PREP);
 
     cb_stage_begin(ctx, ST_KNN_TILE);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     if (KP == 32)
-        CB_TRY((launch_tc<32, 4, 2>(ctx, E, lde, d, scale, n, nq, qlist, qpos)));
+        CB_TRY((launch_tc<32, 4, 2>(ctx, E, lde, d, scale, nq, C)));
     else
-        CB_TRY((launch_tc<64, 2, 2>(ctx, E, lde, d, scale, n, nq, qlist, qpos)));
+        CB_TRY((launch_tc<64, 2, 2>(ctx, E, lde, d, scale, nq, C)));
     cb_stage_end(ctx, ST_KNN_TILE);
     *kp_out = SETS * KP;  // candidates per query: one sorted list per epilogue set
     *ntau_out = SETS;
-    *qlist_out = qlist;
+    *qlist_out = ctx->knn_qlist.p;
     // split (3.1 * 2^-22) + fp32 accumulation of <= 195 products (2^-23 each, truncation assumed)
     *err_coef_out = ldexp(1.0, -15);
     return 0;

@@ -106,8 +106,8 @@ def test_knn_engines_agree_on_candidates_quality(gpu_ctx, monkeypatch):
 
 
 def test_knn_degenerate_first_coordinate(gpu_ctx, engine):
-    """The tensor-core engine orders and prunes by the first coordinate: constant, two-valued and
-    outlier-ridden first coordinates must not change the (exact) result."""
+    """Constant, two-valued and outlier-ridden coordinates (degenerate clusters, a scale set by a few
+    outliers) must not change the (exact) result."""
     rng = np.random.default_rng(9)
     emb = synth.make_embedding(2000, 12, seed=8)
     for mutate in ("const", "binary", "outlier"):
@@ -121,6 +121,48 @@ def test_knn_degenerate_first_coordinate(gpu_ctx, engine):
         assert np.array_equal(gpu_ctx.knn(e, 10), O.find_knn(e, 10)), mutate
 
 
+@pytest.mark.parametrize("clusters", [1, 2, 7, 23, 256])
+def test_knn_any_cluster_count_is_exact(gpu_ctx, monkeypatch, clusters):
+    """The tensor-core engine orders the references by (cluster, distance to the cluster centre) and
+    skips tiles by the triangle inequality; the number of clusters must never change the result --
+    random data, a query sub-range, duplicates and a tie-heavy lattice."""
+    monkeypatch.setenv("CB200_KNN_ENGINE", "tc")
+    monkeypatch.setenv("CB200_KNN_CLUSTERS", str(clusters))
+    emb = synth.make_embedding(3000, 50, seed=77)
+    want = O.find_knn(emb, 20)
+    assert np.array_equal(gpu_ctx.knn(emb, 20), want)
+    assert gpu_ctx.timings()["knn_engine"] == 2
+    assert np.array_equal(gpu_ctx.knn(emb, 20, q_begin=1000, q_end=1777), want[1000:1777])
+    emb[100:140] = emb[100]
+    assert np.array_equal(gpu_ctx.knn(emb, 12), O.find_knn(emb, 12))
+    rng = np.random.default_rng(5)
+    lat = rng.integers(-2, 3, size=(1500, 4)).astype(np.float64)
+    assert np.array_equal(gpu_ctx.knn(lat, 15), O.find_knn(lat, 15))
+    same = np.ones((700, 6))                      # every point identical: all distances tie at 0
+    assert np.array_equal(gpu_ctx.knn(same, 9), O.find_knn(same, 9))
+
+
+def test_knn_cluster_pruning_on_blobs(gpu_ctx, monkeypatch):
+    """40 Gaussian blobs in 50 dimensions: most of the tile grid must be skipped, exactly."""
+    monkeypatch.setenv("CB200_KNN_ENGINE", "tc")
+    emb = synth.make_embedding(60000, 50, seed=31)
+    got = gpu_ctx.knn(emb, 20)
+    t = gpu_ctx.timings()
+    assert t["knn_tiles_scanned"] < 0.35 * t["knn_tiles_total"], t
+    assert t["knn_fallback_queries"] <= 20
+    q = np.random.default_rng(1).choice(60000, 300, replace=False)
+    sub = O.find_knn_queries(emb, q, 20) if hasattr(O, "find_knn_queries") else None
+    if sub is None:
+        acc = np.zeros((300, 60000))
+        for c in range(50):                       # the reference's summation order
+            dlt = emb[q, c][:, None] - emb[None, :, c]
+            acc += dlt * dlt
+        dist = np.sqrt(acc)
+        dist[np.arange(300), q] = np.inf
+        sub = np.array([np.lexsort((np.arange(60000), dist[r]))[:20] + 1 for r in range(300)], dtype=np.int32)
+    assert np.array_equal(got[q], sub)
+
+
 def test_knn_rejects_non_finite(gpu_ctx):
     emb = synth.make_embedding(500, 8, seed=8)
     emb[17, 3] = np.nan
@@ -129,7 +171,7 @@ def test_knn_rejects_non_finite(gpu_ctx):
 
 
 def test_knn_pruning_reports_tiles(gpu_ctx):
-    """Well-separated clusters along the first coordinate: most of the tile grid must be pruned."""
+    """Well-separated slabs along the first coordinate: most of the tile grid must be pruned."""
     rng = np.random.default_rng(3)
     emb = rng.standard_normal((40000, 10))
     emb[:, 0] += np.repeat(np.arange(40) * 40.0, 1000)       # 40 slabs far apart in PC 1
