@@ -53,8 +53,6 @@ constexpr int TC_K = 64;         // padded K (fp16 elements): 128-byte rows
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_PART_BYTES = TC_N * TC_K * 2;   // 16 KB: one fp16 part of a tile
 constexpr int TC_TILE_BYTES = 2 * TC_PART_BYTES; // hi + lo
-// SETS epilogue warp sets of 4 warps each, one per TMEM accumulator stage (SETS x 128 columns)
-__host__ __device__ constexpr int tc_threads(int sets) { return 64 + sets * 128; }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=b=F16 (0), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
@@ -373,82 +371,68 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, co
 // ---------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------
-// Warp-cooperative insertion of (nk, ni) into one row's candidate list: KP = 32*EPL entries sorted
-// ascending by (key, idx) in shared memory, element p held by lane p % 32 in register p / 32.
-// Returns the new KP-th key.  ~10 + 12*EPL instructions; out of line to keep the epilogue compact.
-template <int EPL>
-__device__ __noinline__ float tc_insert(float *lkey, int *lidx, float nk, int ni, int lane)
-{
-    float k[EPL];
-    int ix[EPL];
-    int pos = 0;
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-        k[e] = lkey[e * 32 + lane];
-        ix[e] = lidx[e * 32 + lane];
-        pos += __popc(__ballot_sync(0xffffffffu, pair_less<float>(k[e], ix[e], nk, ni)));
-    }
-#pragma unroll
-    for (int e = EPL - 1; e >= 0; --e) {
-        const int p = e * 32 + lane;
-        float uk = __shfl_up_sync(0xffffffffu, k[e], 1);
-        int ui = __shfl_up_sync(0xffffffffu, ix[e], 1);
-        if (e > 0) {
-            const float lk = __shfl_sync(0xffffffffu, k[e - 1], 31);
-            const int li = __shfl_sync(0xffffffffu, ix[e - 1], 31);
-            if (lane == 0) {
-                uk = lk;
-                ui = li;
-            }
-        }
-        if (p > pos) {
-            k[e] = uk;
-            ix[e] = ui;
-        } else if (p == pos) {
-            k[e] = nk;
-            ix[e] = ni;
-        }
-        lkey[p] = k[e];
-        lidx[p] = ix[e];
-    }
-    const float kth = __shfl_sync(0xffffffffu, k[EPL - 1], 31);
-    __syncwarp();
-    return kth;
-}
+// Warp roles: warp 0 = bulk-copy producer (+ pruning tests), warp 1 = MMA issuer, warps 2..9 = two
+// scanner sets of 4 warps (the n-th tile of the sequence goes to set n % 2 through accumulator stage
+// n % 4; within a set warp w owns TMEM lane quarter w % 4 and a thread is one query row), warps
+// 10..13 = inserters, again one thread per query row.
+//
+// Scanners only compare: 3-input max tree over 32 accumulator columns + one vote; a column that beats
+// the row's published threshold is pushed as (value, sorted position) into the ring of (set, row) --
+// single producer, single consumer, no atomics: a slot carries the lap parity of its position, so
+// the consumer can tell a written slot from a stale one without resetting it, and the producer may
+// write position p once head > p - QCAP.  The inserter thread of a row keeps ONE binary min-heap of
+// the KP best candidates in shared memory ([entry][row]: a lane always hits its own bank); the root
+// is the row's threshold, published after every change.  Candidates leave unsorted (k_knn_rerank
+// sorts by exact distance).
+constexpr int TC_RING = 16;  // tile ids of the sequence in flight (producer -> MMA -> scanners)
+constexpr int TC_SCAN_SETS = 2;
+constexpr int TC_ACC_STAGES = 4;
+constexpr int TC_POS_BITS = 27;  // sorted positions in a ring entry
+constexpr int TC_THREADS = 64 + TC_SCAN_SETS * 128 + 128;
 
-// Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer, then SETS epilogue sets of 4 warps;
-// the n-th tile of the (pruned, outward) tile sequence goes to set n % SETS through accumulator
-// stage n % SETS.  Within a set warp w owns TMEM lane quarter w % 4; a thread is one query row.  Each
-// set keeps its own sorted top-KP list per row, so a query ends with SETS*KP candidates and SETS
-// thresholds.
-constexpr int TC_RING = 16;  // tile ids of the sequence in flight (producer -> MMA -> epilogue)
+template <int KP, int STAGES, int QCAP>
+struct TcSmem {
+    static constexpr size_t q_img = 0;
+    static constexpr size_t r_img = q_img + TC_TILE_BYTES;
+    static constexpr size_t hk = r_img + (size_t)STAGES * TC_TILE_BYTES;    // [KP][TC_M] heap keys (T values)
+    static constexpr size_t hi = hk + (size_t)TC_M * KP * 4;                // [KP][TC_M] sorted positions
+    static constexpr size_t ring = hi + (size_t)TC_M * KP * 4;              // [SETS][QCAP][TC_M] uint2
+    static constexpr size_t bars = ring + (size_t)TC_SCAN_SETS * QCAP * TC_M * 8;  // full/empty[STAGES], tfull/tempty[ACC]
+    static constexpr size_t thr_sh = bars + (size_t)(2 * STAGES + 2 * TC_ACC_STAGES) * 8;  // [TC_M] float
+    static constexpr size_t qhead = thr_sh + TC_M * 4;                      // [SETS][TC_M]
+    static constexpr size_t misc = qhead + TC_SCAN_SETS * TC_M * 4;         // tmem slot, scan_done
+    static constexpr size_t seq_tile = misc + 16;                           // [TC_RING]
+    static constexpr size_t bytes = seq_tile + TC_RING * 4;
+};
 
-template <int KP, int SETS, int STAGES>
-__global__ void __launch_bounds__(tc_threads(SETS), 1)
+template <int KP, int STAGES, int QCAP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, const unsigned char *__restrict__ img,
                int64_t nq, const int32_t *__restrict__ qlist, const int32_t *__restrict__ qpos,
                const int32_t *__restrict__ perm, int C, const float *__restrict__ dqc, const int32_t *__restrict__ cl,
                const uint16_t *__restrict__ cl_order, const int32_t *__restrict__ cl_tile_begin,
                const unsigned int *__restrict__ cl_rhomax, const float *__restrict__ tile_lo,
-               const float *__restrict__ tile_hi, float key_unscale, int32_t *__restrict__ cand_idx,
+               const float *__restrict__ tile_hi, float key_unscale, int cand_stride, int32_t *__restrict__ cand_idx,
                float *__restrict__ cand_tau, int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done)
 {
-    constexpr int EPL = KP / 32;
-    constexpr int TC_SETS = SETS, TC_ACC_STAGES = SETS, TC_THREADS = tc_threads(SETS);
-    constexpr uint32_t TC_TMEM_COLS = SETS * TC_N;  // 256 or 512 (power of two)
+    using L = TcSmem<KP, STAGES, QCAP>;
+    constexpr uint32_t TC_TMEM_COLS = TC_ACC_STAGES * TC_N;  // 512
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *q_img = smem;                                   // 32 KB: Q hi | Q lo
-    unsigned char *r_img = smem + TC_TILE_BYTES;                   // STAGES x 32 KB
-    float *lkey = reinterpret_cast<float *>(r_img + (size_t)STAGES * TC_TILE_BYTES);  // [SETS][TC_M][KP]
-    int *lidx = reinterpret_cast<int *>(lkey + (size_t)TC_SETS * TC_M * KP);          // [SETS][TC_M][KP]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(lidx + (size_t)TC_SETS * TC_M * KP);
+    unsigned char *q_img = smem + L::q_img;                                // 32 KB: Q hi | Q lo
+    unsigned char *r_img = smem + L::r_img;                                // STAGES x 32 KB
+    float *hk = reinterpret_cast<float *>(smem + L::hk);
+    int *hi_ = reinterpret_cast<int *>(smem + L::hi);
+    uint2 *ring = reinterpret_cast<uint2 *>(smem + L::ring);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bars);
     uint64_t *full = bars;                       // [STAGES]
     uint64_t *empty = bars + STAGES;             // [STAGES]
     uint64_t *tfull = bars + 2 * STAGES;         // [TC_ACC_STAGES]
     uint64_t *tempty = tfull + TC_ACC_STAGES;    // [TC_ACC_STAGES]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + TC_ACC_STAGES);
-    volatile float *thr_sh = reinterpret_cast<volatile float *>(tmem_slot + 4);  // [SETS][TC_M] thresholds published by the sets
-    volatile int *seq_tile = reinterpret_cast<volatile int *>(const_cast<float *>(thr_sh) + TC_SETS * TC_M);  // [TC_RING]
+    volatile float *thr_sh = reinterpret_cast<volatile float *>(smem + L::thr_sh);
+    volatile unsigned int *qhead = reinterpret_cast<volatile unsigned int *>(smem + L::qhead);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::misc);
+    unsigned int *scan_done = reinterpret_cast<unsigned int *>(smem + L::misc + 4);
+    volatile int *seq_tile = reinterpret_cast<volatile int *>(smem + L::seq_tile);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ql0 = (int64_t)blockIdx.x * TC_M;   // first entry of the (sorted) query list
@@ -475,12 +459,14 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         *reinterpret_cast<__half *>(q_img + off) = h;
         *reinterpret_cast<__half *>(q_img + TC_PART_BYTES + off) = l;
     }
-    for (int i = tid; i < TC_SETS * TC_M * KP; i += TC_THREADS) {
-        lkey[i] = FLT_MAX;
-        lidx[i] = 0x7fffffff;
-    }
-    for (int i = tid; i < TC_SETS * TC_M; i += TC_THREADS)
-        thr_sh[i] = -FLT_MAX;
+    for (int i = tid; i < TC_SCAN_SETS * QCAP * TC_M; i += TC_THREADS)
+        ring[i] = make_uint2(0u, 0x80000000u);  // parity of lap -1
+    for (int i = tid; i < TC_M; i += TC_THREADS)
+        thr_sh[i] = (ql0 + i < nq) ? -FLT_MAX : FLT_MAX;  // rows past the list never select
+    for (int i = tid; i < TC_SCAN_SETS * TC_M; i += TC_THREADS)
+        qhead[i] = 0u;
+    if (tid == 0)
+        *scan_done = 0u;
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full + s, 1);
@@ -488,7 +474,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         }
         for (int a = 0; a < TC_ACC_STAGES; ++a) {
             mbar_init(tfull + a, 1);
-            mbar_init(tempty + a, 4);  // one arrival per epilogue warp of the set
+            mbar_init(tempty + a, 4);  // one arrival per scanner warp of the set
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -540,10 +526,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             float reach[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                float thr = -FLT_MAX;
-#pragma unroll
-                for (int s2 = 0; s2 < TC_SETS; ++s2)
-                    thr = fmaxf(thr, thr_sh[s2 * TC_M + u * 32 + lane]);
+                const float thr = thr_sh[u * 32 + lane];
                 reach[u] = thr == -FLT_MAX ? INFINITY
                                            : sqrtf(fmaxf(2.0f * (qn[u] - thr), 0.f)) * 1.000002f + 1e-30f;
                 if (g[u] >= 0) {
@@ -629,8 +612,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 mbar_wait(full + s, ph, err_flag);
                 tc_fence_after();
                 if (seq_tile[seq % TC_RING] < 0) {
-                    // wake every epilogue set with the end marker at its next sequence slot
-                    for (int j = 0; j < TC_SETS; ++j) {
+                    // wake every scanner set with the end marker at its next sequence slot
+                    for (int j = 0; j < TC_SCAN_SETS; ++j) {
                         const int64_t sq = seq + j;
                         const int a2 = (int)(sq % TC_ACC_STAGES);
                         if (j > 0)
@@ -659,41 +642,33 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 umma_commit(tfull + a);   // accumulator complete
             }
         }
-    } else {
-        // ===== epilogue: thread = query row (TMEM lane), fused top-KP selection =====
-        const int set = (warp - 2) >> 2;           // accumulator stage / sequence residue of this set
+    } else if (warp < 2 + TC_SCAN_SETS * 4) {
+        // ===== scanners: thread = query row (TMEM lane) =====
+        const int set = (warp - 2) >> 2;           // sequence residue of this set
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;
         const int64_t myql = ql0 + row;
         const bool active = myql < nq;
-        float *set_key = lkey + (size_t)set * TC_M * KP;
-        int *set_idx = lidx + (size_t)set * TC_M * KP;
-        float thr = active ? -FLT_MAX : FLT_MAX;   // T must exceed thr; rows past the list never select
-        int my_pos = -1;                           // sorted position of the query itself (self-exclusion)
-        if (active)
-            my_pos = qpos[myql];
-        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * TC_N);
-        for (int64_t seq = set;; seq += TC_SETS) {
-            const uint32_t aph = (uint32_t)((seq / TC_ACC_STAGES) & 1);
-            mbar_wait(tfull + set, aph, err_flag);
+        const int my_pos = active ? qpos[myql] : -1;   // sorted position of the query itself (self-exclusion)
+        const uint32_t ring_addr = smem_u32(ring + (size_t)set * QCAP * TC_M + row);  // slot s at + s*TC_M*8
+        volatile unsigned int *myhead = qhead + set * TC_M + row;
+        unsigned tail = 0u;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int64_t seq = set;; seq += TC_SCAN_SETS) {
+            const int a = (int)(seq % TC_ACC_STAGES);
+            mbar_wait(tfull + a, (uint32_t)((seq / TC_ACC_STAGES) & 1), err_flag);
             tc_fence_after();
             const int t = seq_tile[seq % TC_RING];
             if (t < 0)
                 break;
-            const int64_t r0 = (int64_t)t * TC_N;
-            // A reference that does not beat the KP-th best of ANY set cannot be among the KP best
-            // overall: take the tightest threshold any set has published for this row (stale reads
-            // only cost extra hits; the union of the per-set lists still holds the global top KP).
-            if (active) {
-#pragma unroll
-                for (int s2 = 0; s2 < TC_SETS; ++s2)
-                    thr = fmaxf(thr, thr_sh[s2 * TC_M + row]);
-            }
-            // Scan of 32 accumulator columns held in registers.  Fast path: 3-input max tree + one
-            // vote.  Slow path (some lane beats its threshold): group votes, then per-column ballots;
-            // each hit is inserted into its row's sorted list by the whole warp (tc_insert), which
-            // also yields the row's exact new threshold.
-            auto scan_chunk = [&](uint32_t(&r)[32], int64_t c0) {
+            const int r0 = t * TC_N;
+            const uint32_t tcol = tbase + (uint32_t)(a * TC_N);
+            uint32_t r[32];
+#pragma unroll 1
+            for (int ch = 0; ch < TC_N / 32; ++ch) {
+                tmem_ld32_issue(tcol + (uint32_t)(ch * 32), r);
+                const float thr = thr_sh[row];     // stale reads only cost extra pushes
+                tmem_ld_wait();
                 float g[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -706,62 +681,139 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 }
                 const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
                 if (!__any_sync(0xffffffffu, m > thr))
-                    return;
+                    continue;
+                if (m > thr) {  // this row has at least one hit among the 32 columns
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (!__any_sync(0xffffffffu, g[j] > thr))
-                        continue;
-#pragma unroll
-                    for (int ii = 0; ii < 8; ++ii) {
-                        const int i = 8 * j + ii;
-                        unsigned c = __ballot_sync(0xffffffffu, __uint_as_float(r[i]) > thr);
-                        while (c) {
-                            const int owner = __ffs(c) - 1;
-                            c &= c - 1;
-                            const float val = __shfl_sync(0xffffffffu, __uint_as_float(r[i]), owner);
-                            const float othr = __shfl_sync(0xffffffffu, thr, owner);
-                            const int opos = __shfl_sync(0xffffffffu, my_pos, owner);
-                            const int64_t gcol = c0 + i;
-                            if (val > othr && gcol != opos) {
-                                const float kth = tc_insert<EPL>(set_key + (size_t)(quarter * 32 + owner) * KP,
-                                                                 set_idx + (size_t)(quarter * 32 + owner) * KP, -val,
-                                                                 (int)gcol, lane);
-                                if (lane == owner && kth != FLT_MAX) {
-                                    thr = fmaxf(thr, -kth);
-                                    thr_sh[set * TC_M + row] = -kth;
+                    for (int i = 0; i < 32; ++i) {
+                        const int gcol = r0 + ch * 32 + i;
+                        if (__uint_as_float(r[i]) > thr && gcol != my_pos) {
+                            for (uint32_t spin = 0; (int)(tail - *myhead) >= QCAP; ++spin) {
+                                if (spin > (1u << 24)) {
+                                    atomicOr(err_flag, 4);
+                                    __threadfence();
+                                    asm volatile("trap;");
                                 }
                             }
+                            const unsigned meta = (((tail / QCAP) & 1u) << 31) | (unsigned)gcol;
+                            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(
+                                             ring_addr + (uint32_t)((tail % QCAP) * TC_M * 8)),
+                                         "r"(r[i]), "r"(meta)
+                                         : "memory");
+                            ++tail;
                         }
                     }
                 }
-            };
-            // one register buffer: a second one (load of chunk ch+1 in flight while ch is scanned) was
-            // measured 2.4x slower -- the doubled slow-path code thrashes the instruction cache
-            uint32_t ra[32];
-#pragma unroll 1
-            for (int ch = 0; ch < TC_N / 32; ++ch) {
-                tmem_ld32_issue(tcol + (uint32_t)(ch * 32), ra);
-                tmem_ld_wait();
-                scan_chunk(ra, r0 + ch * 32);
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0)
-                mbar_arrive(tempty + set);
+                mbar_arrive(tempty + a);
         }
-        // final: the lists are sorted; write this set's KP candidates (original indices) and the
-        // threshold of every row (key space, unscaled: key = 0.5 d^2 - 0.5 |q|^2)
         __syncwarp();
-        if (active) {
-            const float *rk = set_key + (size_t)row * KP;
-            const int *ri = set_idx + (size_t)row * KP;
-            int32_t *out = cand_idx + myql * (int64_t)(TC_SETS * KP) + set * KP;
-            for (int p = 0; p < KP; ++p) {
-                const int v = ri[p];
-                out[p] = v == 0x7fffffff ? -1 : perm[v];
+        if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(scan_done, 1u);
+        }
+    } else {
+        // ===== inserters: thread = query row; binary min-heap of the KP largest T in shared memory =====
+        const int row = tid - (64 + TC_SCAN_SETS * 128);
+        float *mk = hk + row;   // entry e at mk[e * TC_M]
+        int *mi = hi_ + row;
+        unsigned head[TC_SCAN_SETS];
+        uint32_t raddr[TC_SCAN_SETS];
+#pragma unroll
+        for (int s2 = 0; s2 < TC_SCAN_SETS; ++s2) {
+            head[s2] = 0u;
+            raddr[s2] = smem_u32(ring + (size_t)s2 * QCAP * TC_M + row);
+        }
+        int cnt = 0;            // entries held; the heap is filled from the back (no sifting: parents are empty)
+        float root = -FLT_MAX;
+        bool done_seen = false;
+        while (true) {
+            bool got = false;
+#pragma unroll
+            for (int s2 = 0; s2 < TC_SCAN_SETS; ++s2) {
+                unsigned ex, ey;
+                asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(ex), "=r"(ey)
+                             : "r"(raddr[s2] + (uint32_t)((head[s2] % QCAP) * TC_M * 8))
+                             : "memory");
+                if ((ey >> 31) != ((head[s2] / QCAP) & 1u))
+                    continue;
+                got = true;
+                ++head[s2];
+                qhead[s2 * TC_M + row] = head[s2];
+                const float val = __uint_as_float(ex);
+                const int pos = (int)(ey & ((1u << TC_POS_BITS) - 1u));
+                if (cnt < KP) {
+                    const int e = KP - 1 - cnt;
+                    mk[e * TC_M] = val;
+                    mi[e * TC_M] = pos;
+                    if (++cnt == KP) {
+                        // heapify: Floyd, parents from the last one down
+                        for (int st = KP / 2 - 1; st >= 0; --st) {
+                            float v = mk[st * TC_M];
+                            int vp = mi[st * TC_M];
+                            int i = st;
+                            while (true) {
+                                const int l = 2 * i + 1;
+                                if (l >= KP)
+                                    break;
+                                const float kl = mk[l * TC_M];
+                                const float kr = (l + 1 < KP) ? mk[(l + 1) * TC_M] : FLT_MAX;
+                                const int c = kl <= kr ? l : l + 1;
+                                const float kc = fminf(kl, kr);
+                                if (v <= kc)
+                                    break;
+                                mk[i * TC_M] = kc;
+                                mi[i * TC_M] = mi[c * TC_M];
+                                i = c;
+                            }
+                            mk[i * TC_M] = v;
+                            mi[i * TC_M] = vp;
+                        }
+                        root = mk[0];
+                        thr_sh[row] = root;
+                    }
+                } else if (val > root) {
+                    int i = 0;
+                    while (true) {  // sift the new value down from the root
+                        const int l = 2 * i + 1;
+                        if (l >= KP)
+                            break;
+                        const float kl = mk[l * TC_M];
+                        const float kr = (l + 1 < KP) ? mk[(l + 1) * TC_M] : FLT_MAX;
+                        const int c = kl <= kr ? l : l + 1;
+                        const float kc = fminf(kl, kr);
+                        if (val <= kc)
+                            break;
+                        mk[i * TC_M] = kc;
+                        mi[i * TC_M] = mi[c * TC_M];
+                        i = c;
+                    }
+                    mk[i * TC_M] = val;
+                    mi[i * TC_M] = pos;
+                    root = mk[0];
+                    thr_sh[row] = root;
+                }
             }
-            const float kth = rk[KP - 1];
-            cand_tau[myql * TC_SETS + set] = (kth == FLT_MAX) ? FLT_MAX : kth * key_unscale;
+            if (!__any_sync(0xffffffffu, got)) {
+                if (done_seen)
+                    break;
+                done_seen = *reinterpret_cast<volatile unsigned int *>(scan_done) == (unsigned)(TC_SCAN_SETS * 4);
+                if (!done_seen)
+                    __nanosleep(32);
+            }
+        }
+        // final: candidates (original indices, unsorted) and the row threshold in key space, unscaled:
+        // key = 0.5 d^2 - 0.5 |q|^2 = -T
+        const int64_t myql = ql0 + row;
+        if (myql < nq) {
+            int32_t *out = cand_idx + myql * (int64_t)cand_stride;
+            for (int p = 0; p < cand_stride; ++p)
+                out[p] = (p < KP && p >= KP - cnt) ? perm[mi[p * TC_M]] : -1;
+            cand_tau[myql] = (cnt < KP) ? FLT_MAX : -root * key_unscale;
         }
     }
     tc_fence_before();
@@ -773,19 +825,21 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-template <int KP, int SETS, int STAGES>
-static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double scale, int64_t nq, int C)
+template <int KP, int STAGES, int QCAP>
+static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double scale, int64_t nq, int C,
+                     int cand_stride)
 {
-    const size_t smem = (size_t)TC_TILE_BYTES * (1 + STAGES) + (size_t)SETS * TC_M * KP * 8 +
-                        (size_t)(2 * STAGES + 2 * SETS) * 8 + 16 + (size_t)SETS * TC_M * 4 + (size_t)TC_RING * 4;
-    CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, SETS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = TcSmem<KP, STAGES, QCAP>::bytes;
+    static_assert(TcSmem<KP, STAGES, QCAP>::bytes <= 232448, "shared memory budget");
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, STAGES, QCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     const unsigned grid = (unsigned)((nq + TC_M - 1) / TC_M);
     const float key_unscale = (float)(1.0 / (scale * scale));
-    k_knn_tiles_tc<KP, SETS, STAGES><<<grid, tc_threads(SETS), smem, ctx->stream>>>(
+    k_knn_tiles_tc<KP, STAGES, QCAP><<<grid, TC_THREADS, smem, ctx->stream>>>(
         E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, C, ctx->knn_dqc.p,
         ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p, ctx->knn_tile_lo.p,
-        ctx->knn_tile_hi.p, key_unscale, ctx->cand_idx.p, ctx->cand_tau.p, ctx->flag.p + 3, ctx->maxnrm.p + 3);
+        ctx->knn_tile_hi.p, key_unscale, cand_stride, ctx->cand_idx.p, ctx->cand_tau.p, ctx->flag.p + 3,
+        ctx->maxnrm.p + 3);
     CB_LAUNCH(ctx);
     return 0;
 }
@@ -824,12 +878,14 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     const int B = TC_BUCKETS / C;
     const int64_t n_tiles_cap = (n + TC_N - 1) / TC_N + C;  // every cluster is padded to whole tiles
     const int64_t npos = n_tiles_cap * TC_N;
-    const int KP = k <= 24 ? 32 : 64;
-    const int SETS = KP == 32 ? 4 : 2;
+    // candidates kept per query (one list): enough beyond k for the margin proof of k_knn_rerank;
+    // the candidate records are padded to 128 entries (the re-rank sorts a power of two)
+    const int KP = k <= 24 ? 96 : 120;
+    const int CAND = 128;
     CB_CUDA(ctx, ctx->knn_img.ensure((size_t)n_tiles_cap * TC_TILE_BYTES));
     CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
-    CB_CUDA(ctx, ctx->cand_idx.ensure((size_t)nq * SETS * KP));
-    CB_CUDA(ctx, ctx->cand_tau.ensure((size_t)nq * SETS));
+    CB_CUDA(ctx, ctx->cand_idx.ensure((size_t)nq * CAND));
+    CB_CUDA(ctx, ctx->cand_tau.ensure((size_t)nq));
     CB_CUDA(ctx, ctx->knn_perm.ensure((size_t)npos));
     CB_CUDA(ctx, ctx->knn_bkt.ensure((size_t)npos));
     CB_CUDA(ctx, ctx->knn_hist.ensure((size_t)TC_BUCKETS));
@@ -922,13 +978,14 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
 
     cb_stage_begin(ctx, ST_KNN_TILE);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
-    if (KP == 32)
-        CB_TRY((launch_tc<32, 4, 2>(ctx, E, lde, d, scale, nq, C)));
+    CB_CHECK(ctx, npos < (1LL << TC_POS_BITS), "cb200_knn: at most 2^27 points on the tensor-core engine");
+    if (KP == 96)
+        CB_TRY((launch_tc<96, 2, 8>(ctx, E, lde, d, scale, nq, C, CAND)));
     else
-        CB_TRY((launch_tc<64, 2, 2>(ctx, E, lde, d, scale, nq, C)));
+        CB_TRY((launch_tc<120, 2, 4>(ctx, E, lde, d, scale, nq, C, CAND)));
     cb_stage_end(ctx, ST_KNN_TILE);
-    *kp_out = SETS * KP;  // candidates per query: one sorted list per epilogue set
-    *ntau_out = SETS;
+    *kp_out = CAND;
+    *ntau_out = 1;
     *qlist_out = ctx->knn_qlist.p;
     // split (3.1 * 2^-22) + fp32 accumulation of <= 195 products (2^-23 each, truncation assumed)
     *err_coef_out = ldexp(1.0, -15);
