@@ -261,7 +261,9 @@ def main():
         e1.record(stream)
         barrier()
         e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps
-        e2e = dict(ms=e2e_ms, h2d=h2d, d2h=d2h_box[0])
+        tme = ctx.timings()
+        e2e = dict(ms=e2e_ms, h2d=h2d, d2h=d2h_box[0],
+                   stage_ms={k: tme[k] for k in ["h2d_ms", "d2h_ms"] + stage_keys} | {"host_marks_ms": pipe.last_marks})
 
     # ---- max over ranks ----
     vals = torch.tensor([dev_ms, e2e["ms"] if e2e else 0.0, float(n_edges_local), float(launches),
@@ -318,7 +320,8 @@ def main():
                     stage_ms=stage_ms, hbm_stages=hbm, roofline=roofline)
         if e2e:
             line["e2e"] = dict(value=w["cells"] / (e2e_ms * 1e-3), unit="cells/s", ms_per_step=e2e_ms,
-                               h2d_bytes_per_step=h2d_all, d2h_bytes_per_step=d2h_all)
+                               h2d_bytes_per_step=h2d_all, d2h_bytes_per_step=d2h_all,
+                               last_step_stage_ms_rank0=e2e.get("stage_ms"))
         if world == 1 and not args.no_cpu_baseline:
             n_sample = min(w["cells"], args.cpu_sample)
             d = host_sample(w, n_sample)

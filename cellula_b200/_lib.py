@@ -70,6 +70,8 @@ SIGNATURES = {
     "cb200_snn_device": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_i64p,
                                  ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p), ctypes.POINTER(c_f64p)]),
     "cb200_snn_resident": (c_int, [c_vp, c_int, c_int, c_i64p]),
+    "cb200_snn_count_device": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_i64p]),
+    "cb200_snn_emit": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cb200_free_edges": (c_int, [c_i32p, c_i32p, c_f64p]),
     "cb200_fetch_edges": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cb200_synth_counts": (c_int, [c_vp, c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_i64p]),
@@ -335,6 +337,25 @@ class Context:
                                         j_end, ctypes.byref(ne), ctypes.byref(pf), ctypes.byref(pt),
                                         ctypes.byref(pw)))
         return self._take_edges(ne, pf, pt, pw)
+
+    def snn_count_device(self, d_index_ptr, n_total, k, snn_type, j_begin, j_end):
+        """Phase 1 of the two-phase SNN call: number of edges the cells [j_begin, j_end) will emit."""
+        ne = c_i64()
+        self._ck(lib().cb200_snn_count_device(self._h, c_vp(d_index_ptr), n_total, k, SNN_TYPES[snn_type], j_begin,
+                                              j_end, ctypes.byref(ne)))
+        return ne.value
+
+    def snn_emit(self, n_edges, frm=None, to=None, weight=None, resident=False):
+        """Phase 2: emit the counted edges into caller-owned arrays (copies overlap the emission)."""
+        if resident:
+            self._ck(lib().cb200_snn_emit(self._h, None, None, None))
+            return n_edges
+        frm = np.empty(n_edges, np.int32) if frm is None else frm
+        to = np.empty(n_edges, np.int32) if to is None else to
+        weight = np.empty(n_edges, np.float64) if weight is None else weight
+        assert frm.size >= n_edges and to.size >= n_edges and weight.size >= n_edges
+        self._ck(lib().cb200_snn_emit(self._h, _ptr(frm), _ptr(to), _ptr(weight)))
+        return frm[:n_edges], to[:n_edges], weight[:n_edges]
 
     def fetch_edges(self, n_edges, frm=None, to=None, weight=None):
         """Edges of the last snn* call into caller-owned (e.g. pinned) arrays."""

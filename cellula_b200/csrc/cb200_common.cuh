@@ -12,6 +12,7 @@
 #include "../../include/cellula_b200.h"
 
 #define CB200_NUM_SM_FALLBACK 148
+#define CB200_PIN_SCRATCH (1u << 20)
 
 // ---------------------------------------------------------------------------------------
 // device buffer that grows on demand and is released with the context
@@ -66,8 +67,8 @@ struct cb200_ctx {
     int num_sms = CB200_NUM_SM_FALLBACK;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t copy_stream = nullptr;  // asynchronous result copies (cb200_fetch_logcounts_async)
-    cudaEvent_t copy_event = nullptr;
+    unsigned char *pin_scratch = nullptr;  // pinned staging of cb200_read_back (CB200_PIN_SCRATCH bytes)
+    struct CopyWorker *copier = nullptr;  // paced background device->host copies (cb200_ctx.cu)
     std::string err;
 
     // ---- a1: counts shard (CSC, genes x local cells)
@@ -153,6 +154,12 @@ struct cb200_ctx {
     DevBuf<int32_t> efrom, eto;  // [E]
     DevBuf<double> ew8;          // [E]
     int64_t n_edges = 0;
+    DevBuf<int64_t> snn_bounds;    // chunk boundaries of the emission pass (device) ...
+    int64_t *snn_bounds_h = nullptr;  // ... and their pinned host copy
+    const int32_t *snn_nn = nullptr;  // the counted range (between cb200_snn_count_device and cb200_snn_emit)
+    int64_t snn_n = 0, snn_jbegin = 0, snn_jend = 0;
+    int snn_k = 0, snn_type = 0;
+    bool snn_counted = false;
 
     // scan scratch
     DevBuf<int64_t> scan_blk;
@@ -198,6 +205,20 @@ int cb200_fail(cb200_ctx *ctx, const char *fmt, ...);
             return rc__;                                                                    \
     } while (0)
 
+// CB200_TRACE=1: host wall-clock marks on stderr (debugging aid for the overlap of copies and stages)
+#include <chrono>
+#include <cstdlib>
+static inline void cb_trace(const char *label)
+{
+    static const bool on = getenv("CB200_TRACE") != nullptr;
+    if (!on)
+        return;
+    static auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[cb200 %10.3f ms] %s\n", ms, label);
+}
+#define CB_TRACE(label) cb_trace(label)
+
 static inline void cb_stage_begin(cb200_ctx *ctx, int st)
 {
     cudaEventRecord(ctx->ev[st][0], ctx->stream);
@@ -207,6 +228,23 @@ static inline void cb_stage_end(cb200_ctx *ctx, int st)
     cudaEventRecord(ctx->ev[st][1], ctx->stream);
     ctx->ev_used[st] = true;
 }
+
+// Background device->host copy of `bytes` from src (device) to dst (host, ideally pinned), ordered
+// behind everything submitted to ctx->stream so far.  A worker thread feeds the copy engine a few
+// small chunks at a time, so the short synchronous result reads of the following stages are never
+// queued behind one multi-gigabyte transfer.  cb200_copies_wait() blocks until all jobs have landed.
+int cb200_copy_async(cb200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int cb200_copies_wait(cb200_ctx *ctx);
+void cb200_copies_shutdown(cb200_ctx *ctx);
+
+// Small synchronous transfers (flags, counters, a few KB of statistics or indices) that do NOT go
+// through the copy engines: a kernel moves the bytes between device memory and a pinned, device-
+// mapped scratch buffer over PCIe.  A copy-engine transfer issued while a background copy is in
+// flight waits until that stream's queue runs dry (measured: a 4-byte read behind a 4.8 GB copy
+// took 66 ms), which would serialise the stages behind the logcounts copy-out.  Both calls leave
+// the stream idle.  Above CB200_PIN_SCRATCH/2 bytes they fall back to a plain cudaMemcpyAsync.
+int cb200_read_back(cb200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int cb200_write_small(cb200_ctx *ctx, void *dev_dst, const void *src, size_t bytes);
 
 // exclusive scan of int32 counts into int64 offsets (out has n+1 entries, out[n] = total)
 int cb200_scan_i32_to_i64(cb200_ctx *ctx, const int32_t *d_in, int64_t n, int64_t *d_out);

@@ -3,6 +3,12 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
 #include "cb200_common.cuh"
 
 static std::string g_init_error;
@@ -77,6 +83,11 @@ extern "C" int cb200_init(int device, void *stream, cb200_ctx **out)
         return cb200_fail(nullptr, "cb200_init: device allocation failed");
     }
     cudaMemsetAsync(ctx->flag.p, 0, 4 * sizeof(int), ctx->stream);
+    if (cudaMallocHost(reinterpret_cast<void **>(&ctx->snn_bounds_h), 64 * sizeof(int64_t)) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void **>(&ctx->pin_scratch), CB200_PIN_SCRATCH) != cudaSuccess) {
+        delete ctx;
+        return cb200_fail(nullptr, "cb200_init: pinned allocation failed");
+    }
     *out = ctx;
     return 0;
 }
@@ -106,20 +117,208 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->index0.release(); ctx->rcnt.release(); ctx->rptr.release(); ctx->rcur.release();
     ctx->hosts_u.release(); ctx->hosts.release(); ctx->ecnt.release(); ctx->eptr.release();
     ctx->bcnt.release(); ctx->efrom.release(); ctx->eto.release(); ctx->ew8.release();
-    ctx->scan_blk.release();
+    ctx->scan_blk.release(); ctx->snn_bounds.release();
+    if (ctx->snn_bounds_h != nullptr)
+        cudaFreeHost(ctx->snn_bounds_h);
+    if (ctx->pin_scratch != nullptr)
+        cudaFreeHost(ctx->pin_scratch);
     for (int s = 0; s < ST_COUNT_; ++s) {
         cudaEventDestroy(ctx->ev[s][0]);
         cudaEventDestroy(ctx->ev[s][1]);
     }
-    if (ctx->copy_stream != nullptr) {
-        cudaStreamSynchronize(ctx->copy_stream);
-        cudaStreamDestroy(ctx->copy_stream);
-        cudaEventDestroy(ctx->copy_event);
-    }
+    cb200_copies_shutdown(ctx);
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
+}
+
+// bytes: word copies when everything is 8- or 4-byte aligned, else byte by byte
+__global__ void k_copy_bytes(void *__restrict__ dst, const void *__restrict__ src, size_t bytes)
+{
+    const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+    const size_t align = (size_t)dst | (size_t)src | bytes;
+    if ((align & 7) == 0) {
+        for (size_t i = i0; i < bytes / 8; i += step)
+            static_cast<unsigned long long *>(dst)[i] = static_cast<const unsigned long long *>(src)[i];
+    } else if ((align & 3) == 0) {
+        for (size_t i = i0; i < bytes / 4; i += step)
+            static_cast<unsigned int *>(dst)[i] = static_cast<const unsigned int *>(src)[i];
+    } else {
+        for (size_t i = i0; i < bytes; i += step)
+            static_cast<unsigned char *>(dst)[i] = static_cast<const unsigned char *>(src)[i];
+    }
+}
+
+int cb200_read_back(cb200_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0)
+        return 0;
+    if (bytes <= CB200_PIN_SCRATCH / 2) {
+        const unsigned grid = (unsigned)((bytes / 8 + 255) / 256 > 64 ? 64 : (bytes / 8 + 255) / 256 + 1);
+        k_copy_bytes<<<grid, 256, 0, ctx->stream>>>(ctx->pin_scratch, src, bytes);
+        CB_LAUNCH(ctx);
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(dst, ctx->pin_scratch, bytes);
+        return 0;
+    }
+    CB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int cb200_write_small(cb200_ctx *ctx, void *dev_dst, const void *src, size_t bytes)
+{
+    if (bytes == 0)
+        return 0;
+    if (bytes <= CB200_PIN_SCRATCH / 2) {
+        unsigned char *stage = ctx->pin_scratch + CB200_PIN_SCRATCH / 2;
+        memcpy(stage, src, bytes);
+        const unsigned grid = (unsigned)((bytes / 8 + 255) / 256 > 64 ? 64 : (bytes / 8 + 255) / 256 + 1);
+        k_copy_bytes<<<grid, 256, 0, ctx->stream>>>(dev_dst, stage, bytes);
+        CB_LAUNCH(ctx);
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    CB_CUDA(ctx, cudaMemcpyAsync(dev_dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// paced background device->host copies
+// ---------------------------------------------------------------------------------------
+struct CopyJob {
+    void *dst;
+    const void *src;
+    size_t bytes;
+    cudaEvent_t after;
+};
+struct CopyWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::deque<CopyJob> q;
+    bool stop = false;
+    int pending = 0;
+    cudaError_t err = cudaSuccess;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
+};
+static constexpr size_t COPY_CHUNK = 32u << 20;  // 0.6 ms of PCIe; ONE chunk in flight: the copy engine serves another
+                                                 // stream's transfer only when this stream's queue has run dry
+
+// Waits for an event without sitting in a blocking driver call (which would hold up the API calls
+// of the thread that runs the pipeline).
+static cudaError_t poll_event(cudaEvent_t ev)
+{
+    for (;;) {
+        const cudaError_t e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady)
+            return e;
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+}
+
+static void copy_worker_main(CopyWorker *w)
+{
+    cudaSetDevice(w->device);
+    for (;;) {
+        CopyJob job;
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return w->stop || !w->q.empty(); });
+            if (w->q.empty())
+                return;
+            job = w->q.front();
+            w->q.pop_front();
+        }
+        cudaError_t e = cudaStreamWaitEvent(w->stream, job.after, 0);
+        size_t i = 0;
+        for (size_t off = 0; off < job.bytes && e == cudaSuccess; off += COPY_CHUNK, ++i) {
+            const size_t nb = job.bytes - off < COPY_CHUNK ? job.bytes - off : COPY_CHUNK;
+            if (i >= 1)
+                e = poll_event(w->chunk_ev[(i - 1) & 1]);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(static_cast<char *>(job.dst) + off, static_cast<const char *>(job.src) + off, nb,
+                                    cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess)
+                e = cudaEventRecord(w->chunk_ev[i & 1], w->stream);
+        }
+        if (i >= 1 && e == cudaSuccess)
+            e = poll_event(w->chunk_ev[(i - 1) & 1]);
+        cudaEventDestroy(job.after);
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            if (e != cudaSuccess && w->err == cudaSuccess)
+                w->err = e;
+            w->pending -= 1;
+        }
+        w->cv_done.notify_all();
+    }
+}
+
+int cb200_copy_async(cb200_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (ctx->copier == nullptr) {
+        CopyWorker *w = new CopyWorker();
+        w->device = ctx->device;
+        cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+            e = cudaEventCreateWithFlags(&w->chunk_ev[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            delete w;
+            return cb200_fail(ctx, "cb200_copy_async: %s", cudaGetErrorString(e));
+        }
+        w->th = std::thread(copy_worker_main, w);
+        ctx->copier = w;
+    }
+    CopyJob job{dst, src, bytes, nullptr};
+    CB_CUDA(ctx, cudaEventCreateWithFlags(&job.after, cudaEventDisableTiming));
+    CB_CUDA(ctx, cudaEventRecord(job.after, ctx->stream));
+    {
+        std::lock_guard<std::mutex> lk(ctx->copier->mu);
+        ctx->copier->q.push_back(job);
+        ctx->copier->pending += 1;
+    }
+    ctx->copier->cv.notify_one();
+    return 0;
+}
+
+int cb200_copies_wait(cb200_ctx *ctx)
+{
+    CopyWorker *w = ctx->copier;
+    if (w == nullptr)
+        return 0;
+    cudaError_t e;
+    {
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->cv_done.wait(lk, [&] { return w->pending == 0; });
+        e = w->err;
+        w->err = cudaSuccess;
+    }
+    CB_CHECK(ctx, e == cudaSuccess, "background copy failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+void cb200_copies_shutdown(cb200_ctx *ctx)
+{
+    CopyWorker *w = ctx->copier;
+    if (w == nullptr)
+        return;
+    {
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->cv_done.wait(lk, [&] { return w->pending == 0; });
+        w->stop = true;
+    }
+    w->cv.notify_all();
+    w->th.join();
+    cudaStreamDestroy(w->stream);
+    cudaEventDestroy(w->chunk_ev[0]);
+    cudaEventDestroy(w->chunk_ev[1]);
+    delete w;
+    ctx->copier = nullptr;
 }
 
 extern "C" int cb200_synchronize(cb200_ctx *ctx)

@@ -264,8 +264,8 @@ int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used)
         CB_LAUNCH(ctx);
     }
     unsigned long long bits = 0;
-    CB_CUDA(ctx, cudaMemcpyAsync(&bits, ctx->maxnrm.p, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(cb200_read_back(ctx, &bits, ctx->maxnrm.p, sizeof(bits)));
+    CB_TRACE("gram_tc: maxval read");
     double mx;
     memcpy(&mx, &bits, sizeof(double));
     if (!(mx < 31.99))
@@ -295,12 +295,12 @@ int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used)
     const size_t smem = (size_t)GT_STAGES * GT_STAGE_BYTES + (2 * GT_STAGES + 2) * 8 + 16;
     CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
+    CB_TRACE("gram_tc: img launched");
     dim3 grid((unsigned)n_pairs, (unsigned)ksplit);
     k_gram_tc<<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, ctx->gram.p, ctx->flag.p + 3);
     CB_LAUNCH(ctx);
     int h_flag = 0;
-    CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, ctx->flag.p + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p + 3, sizeof(int)));
     CB_CHECK(ctx, (h_flag & 4) == 0, "cb200_pca: tensor-core cross-product kernel timed out on a barrier");
     *used = 1;
     return 0;

@@ -415,14 +415,12 @@ static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, i
                                                      ctx->fb_list.p, ctx->flag.p + 2);
     CB_LAUNCH(ctx);
     int h[2] = {0, 0};
-    CB_CUDA(ctx, cudaMemcpyAsync(h, ctx->flag.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(cb200_read_back(ctx, h, ctx->flag.p + 2, 2 * sizeof(int)));
     CB_CHECK(ctx, (h[1] & 4) == 0, "cb200_knn: tensor-core tile kernel timed out on a barrier (protocol error)");
     ctx->tm.knn_fallback_queries = h[0];
     if (qlist != nullptr) {  // tensor-core engine: how much of the N x N tile grid survived the PC-1 pruning
         unsigned long long done = 0;
-        CB_CUDA(ctx, cudaMemcpyAsync(&done, ctx->maxnrm.p + 3, sizeof(done), cudaMemcpyDeviceToHost, ctx->stream));
-        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_TRY(cb200_read_back(ctx, &done, ctx->maxnrm.p + 3, sizeof(done)));
         ctx->tm.knn_tiles_scanned = (int64_t)done;
         ctx->tm.knn_tiles_total = ((nq + 127) / 128) * ((n + 127) / 128);
     } else {
@@ -432,8 +430,7 @@ static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, i
         k_knn_exact<<<h[0], 256, 0, ctx->stream>>>(E, lde, d, n, q_begin, k, ctx->fb_list.p, ctx->knn_dk.p, ctx->knn.p,
                                                    ctx->flag.p + 3);
         CB_LAUNCH(ctx);
-        CB_CUDA(ctx, cudaMemcpyAsync(h, ctx->flag.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_TRY(cb200_read_back(ctx, h, ctx->flag.p + 2, 2 * sizeof(int)));
         CB_CHECK(ctx, (h[1] & 1) == 0,
                  "cb200_knn: exact-scan fallback overflowed (more than %d ties); result not produced", KNN_FB_CAP);
     }

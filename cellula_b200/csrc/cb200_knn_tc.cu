@@ -913,8 +913,7 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     k_knn_tc_ranges<<<g256, 256, 0, ctx->stream>>>(E, lde, n, d, ctx->maxnrm.p);
     CB_LAUNCH(ctx);
     double maxabs = 0.0;
-    CB_CUDA(ctx, cudaMemcpyAsync(&maxabs, ctx->maxnrm.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(cb200_read_back(ctx, &maxabs, ctx->maxnrm.p, sizeof(double)));
     CB_CHECK(ctx, maxabs == maxabs && maxabs < 1e300, "cb200_knn: embedding contains non-finite values");
     // power-of-two scale: max |x'| in [256, 512)
     double scale = 1.0;

@@ -126,9 +126,7 @@ extern "C" int cb200_size_factors_finish(cb200_ctx *ctx, double total, int64_t n
     int h_flag = 0;
     CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (sf_out != nullptr)
-        CB_CUDA(ctx, cudaMemcpyAsync(sf_out, ctx->sf.p, (size_t)ctx->N * sizeof(double), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_TRY(cb200_read_back(ctx, sf_out, ctx->sf.p, (size_t)ctx->N * sizeof(double)));
     CB_CHECK(ctx, h_flag == 0, "size factors should be positive");
     ctx->have_sf = true;
     return 0;
@@ -140,8 +138,7 @@ extern "C" int cb200_size_factors(cb200_ctx *ctx, const double *sf_in, double *s
         return 1;
     CB_TRY(cb200_size_factors_local(ctx, sf_in));
     double part[2];
-    CB_CUDA(ctx, cudaMemcpyAsync(part, ctx->part.p, sizeof(part), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(cb200_read_back(ctx, part, ctx->part.p, sizeof(part)));
     return cb200_size_factors_finish(ctx, part[0], ctx->N, sf_out);
 }
 
@@ -235,13 +232,9 @@ extern "C" int cb200_genestats_finish(cb200_ctx *ctx, double *gene_mean, double 
         ctx->gene_acc.p, ctx->gene_acc.p + ctx->G, ctx->G, (double)ctx->N_total, ctx->gene_mean.p, ctx->gene_var.p);
     CB_LAUNCH(ctx);
     if (gene_mean != nullptr)
-        CB_CUDA(ctx, cudaMemcpyAsync(gene_mean, ctx->gene_mean.p, (size_t)ctx->G * sizeof(double),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
+        CB_TRY(cb200_read_back(ctx, gene_mean, ctx->gene_mean.p, (size_t)ctx->G * sizeof(double)));
     if (gene_var != nullptr)
-        CB_CUDA(ctx, cudaMemcpyAsync(gene_var, ctx->gene_var.p, (size_t)ctx->G * sizeof(double),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-    if (gene_mean != nullptr || gene_var != nullptr)
-        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_TRY(cb200_read_back(ctx, gene_var, ctx->gene_var.p, (size_t)ctx->G * sizeof(double)));
     ctx->have_genestats = true;
     return 0;
 }
@@ -271,24 +264,14 @@ extern "C" int cb200_fetch_logcounts_async(cb200_ctx *ctx, double *logx_out)
     CB_CHECK(ctx, ctx->have_logx, "cb200_fetch_logcounts_async: logcounts have not been computed");
     CB_CHECK(ctx, logx_out != nullptr, "cb200_fetch_logcounts_async: NULL output");
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ctx->copy_stream == nullptr) {
-        CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
-    }
-    CB_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->stream));
-    CB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
-    CB_CUDA(ctx, cudaMemcpyAsync(logx_out, ctx->logx.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost,
-                                 ctx->copy_stream));
-    return 0;
+    return cb200_copy_async(ctx, logx_out, ctx->logx.p, (size_t)ctx->nnz * sizeof(double));
 }
 
 extern "C" int cb200_wait_copies(cb200_ctx *ctx)
 {
     if (ctx == nullptr)
         return 1;
-    if (ctx->copy_stream != nullptr)
-        CB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    return 0;
+    return cb200_copies_wait(ctx);
 }
 
 extern "C" int cb200_lognorm_genestats(cb200_ctx *ctx, double *logx_out, double *gene_mean, double *gene_var)

@@ -799,7 +799,9 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
             seen[hvg_idx[h]] = 1;
         }
     }
+    CB_TRACE("gram_local: enter");
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CB_TRACE("gram_local: setdevice");
     const int H = n_hvg;
     ctx->H = H;
     // Device-side slots are numbered in ascending gene order (entries of a cell then come sorted by
@@ -821,11 +823,9 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     CB_CUDA(ctx, ctx->gram.ensure((size_t)H * H));
 
     cb_stage_begin(ctx, ST_HVG_EXTRACT);
-    CB_CUDA(ctx, cudaMemcpyAsync(ctx->hvg_idx.p, sorted_genes.data(), (size_t)H * sizeof(int32_t),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-    CB_CUDA(ctx, cudaMemcpyAsync(ctx->hvg_perm.p, perm.data(), (size_t)H * sizeof(int32_t), cudaMemcpyHostToDevice,
-                                 ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+    CB_TRY(cb200_write_small(ctx, ctx->hvg_idx.p, sorted_genes.data(), (size_t)H * sizeof(int32_t)));
+    CB_TRY(cb200_write_small(ctx, ctx->hvg_perm.p, perm.data(), (size_t)H * sizeof(int32_t)));
+    CB_TRACE("gram_local: h2d synced");
     k_fill_i32<<<(unsigned)((ctx->G + 255) / 256), 256, 0, ctx->stream>>>(ctx->slot.p, ctx->G, -1);
     CB_LAUNCH(ctx);
     k_build_slot<<<(H + 255) / 256, 256, 0, ctx->stream>>>(ctx->hvg_idx.p, H, ctx->slot.p, ctx->gene_mean.p,
@@ -836,10 +836,9 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     CB_LAUNCH(ctx);
     CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->hcnt.p, ctx->N, ctx->hptr.p));
     int64_t nnz_hvg = 0;
-    CB_CUDA(ctx, cudaMemcpyAsync(&nnz_hvg, ctx->hptr.p + ctx->N, sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(cb200_read_back(ctx, &nnz_hvg, ctx->hptr.p + ctx->N, sizeof(int64_t)));
     ctx->nnz_hvg = nnz_hvg;
+    CB_TRACE("gram_local: nnz_hvg read");
     CB_CUDA(ctx, ctx->hslot.ensure((size_t)nnz_hvg));
     CB_CUDA(ctx, ctx->hval.ensure((size_t)nnz_hvg));
     k_hvg_fill<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->logx.p, ctx->slot.p, ctx->N,
@@ -850,6 +849,7 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     k_hvg_blockptr<<<grid, 256, 0, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->N, nb, ctx->hbptr.p);
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_HVG_EXTRACT);
+    CB_TRACE("gram_local: hvg stage launched");
 
     cb_stage_begin(ctx, ST_GRAM);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->gram.p, 0, (size_t)H * H * sizeof(double), ctx->stream));
@@ -881,6 +881,7 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
         CB_LAUNCH(ctx);
     }
     cb_stage_end(ctx, ST_GRAM);
+    CB_TRACE("gram_local: gram done");
     ctx->have_gram = true;
     ctx->have_scores = false;
     return 0;
@@ -943,9 +944,7 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
     CB_LAUNCH(ctx);
     {
         std::vector<double> hv((size_t)H);
-        CB_CUDA(ctx, cudaMemcpyAsync(hv.data(), ctx->ex.p, (size_t)H * sizeof(double), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_TRY(cb200_read_back(ctx, hv.data(), ctx->ex.p, (size_t)H * sizeof(double)));
         double tv = 0.0;
         for (int h = 0; h < H; ++h)
             tv += hv[h];
@@ -981,11 +980,8 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
         // now Y1 = Ritz vectors, Y2 = C * Ritz vectors
         k_residual<<<b, 256, 0, ctx->stream>>>(Y2, Y1, ctx->etheta.p, H, b, ctx->eres.p);
         CB_LAUNCH(ctx);
-        CB_CUDA(ctx, cudaMemcpyAsync(th.data(), ctx->etheta.p, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        CB_CUDA(ctx, cudaMemcpyAsync(res.data(), ctx->eres.p, (size_t)b * sizeof(double), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_TRY(cb200_read_back(ctx, th.data(), ctx->etheta.p, (size_t)b * sizeof(double)));
+        CB_TRY(cb200_read_back(ctx, res.data(), ctx->eres.p, (size_t)b * sizeof(double)));
         double worst = 0.0;
         for (int j = 0; j < d; ++j)
             worst = res[j] > worst ? res[j] : worst;
@@ -1018,8 +1014,7 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
             // a floored Cholesky pivot means the degree-3 block was too ill-conditioned for
             // Cholesky-QR: continue with the gentler degree-2 filter
             int h_piv = 0;
-            CB_CUDA(ctx, cudaMemcpyAsync(&h_piv, ctx->flag.p + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            CB_TRY(cb200_read_back(ctx, &h_piv, ctx->flag.p + 1, sizeof(int)));
             if (h_piv != 0) {
                 degree = 2;
                 CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 1, 0, sizeof(int), ctx->stream));
@@ -1050,17 +1045,13 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
         k_rowmajor_to_colmajor<<<(unsigned)((ctx->N * d + 255) / 256), 256, 0, ctx->stream>>>(ctx->scores.p, ctx->N, d,
                                                                                              ctx->stage_d.p);
         CB_LAUNCH(ctx);
-        CB_CUDA(ctx, cudaMemcpyAsync(scores, ctx->stage_d.p, (size_t)ctx->N * d * sizeof(double),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_TRY(cb200_read_back(ctx, scores, ctx->stage_d.p, (size_t)ctx->N * d * sizeof(double)));
     }
     if (rotation != nullptr) {
         k_rotation_out<<<(unsigned)(((int64_t)H * d + 255) / 256), 256, 0, ctx->stream>>>(ctx->rot.p, ctx->hvg_perm.p,
                                                                                         H, d, ctx->stage_d.p);
         CB_LAUNCH(ctx);
-        CB_CUDA(ctx, cudaMemcpyAsync(rotation, ctx->stage_d.p, (size_t)H * d * sizeof(double), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CB_TRY(cb200_read_back(ctx, rotation, ctx->stage_d.p, (size_t)H * d * sizeof(double)));
     }
     if (scores != nullptr || rotation != nullptr)
         cb_stage_end(ctx, ST_D2H);
@@ -1071,8 +1062,7 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
     if (total_var != nullptr)
         *total_var = ctx->total_var;
     int h_flag = 0;
-    CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, ctx->flag.p + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p + 1, sizeof(int)));
     CB_CHECK(ctx, converged, "cb200_pca: eigen-solver did not converge in %d iterations (worst residual above %g)",
              max_outer, tol);
     (void)h_flag;  // floored Cholesky pivots only occur for rank-deficient blocks; residual test is the judge

@@ -258,30 +258,58 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
     }
 }
 
+// [j_begin, j_end) is a sub-range of the range the per-cell arrays (ecnt, bcnt, eptr) were sized for;
+// loc = j_begin - (first cell of that range)
 template <int MODE>
 static void launch_snn_merge(cb200_ctx *ctx, int grid, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin,
-                             int64_t j_end)
+                             int64_t j_end, int64_t loc)
 {
     const int32_t *nn = d_nn;
+    int32_t *ecnt = ctx->ecnt.p + loc, *bcnt = ctx->bcnt.p + loc * (k + 1);
+    int64_t *eptr = ctx->eptr.p + loc;
     if (k + 1 <= 32)
         k_snn_merge<MODE, 1><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ctx->ecnt.p, ctx->bcnt.p, ctx->eptr.p, ctx->efrom.p,
-                                                           ctx->eto.p, ctx->ew8.p);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p);
     else if (k + 1 <= 64)
         k_snn_merge<MODE, 2><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ctx->ecnt.p, ctx->bcnt.p, ctx->eptr.p, ctx->efrom.p,
-                                                           ctx->eto.p, ctx->ew8.p);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p);
     else
         k_snn_merge<MODE, 4><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ctx->ecnt.p, ctx->bcnt.p, ctx->eptr.p, ctx->efrom.p,
-                                                           ctx->eto.p, ctx->ew8.p);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p);
+}
+
+// cell boundaries of SNN_CHUNKS pieces with about equal numbers of edges: out[2c] = first local cell of
+// piece c, out[2c+1] = its first edge; out[2*SNN_CHUNKS..] = (nj, ne)
+#define SNN_CHUNKS 8
+__global__ void k_snn_chunk_bounds(const int64_t *__restrict__ eptr, int64_t nj, int64_t *__restrict__ out)
+{
+    const int c = threadIdx.x;
+    if (c > SNN_CHUNKS)
+        return;
+    const int64_t ne = eptr[nj];
+    int64_t j = nj;
+    if (c < SNN_CHUNKS) {
+        const int64_t target = (int64_t)(((__int128)ne * c) / SNN_CHUNKS);
+        int64_t lo = 0, hi = nj;  // first j with eptr[j] >= target
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (eptr[mid] < target)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        j = lo;
+    }
+    out[2 * c] = j;
+    out[2 * c + 1] = eptr[j];
 }
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-static int snn_core(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
-                    int64_t *n_edges)
+// reverse lists + counting pass: how many edges the cells [j_begin, j_end) emit
+static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
+                     int64_t *n_edges)
 {
     CB_CHECK(ctx, n >= 2 && n < (1LL << 24), "cb200_snn: 2 <= n < 2^24 cells supported (got %lld)", (long long)n);
     CB_CHECK(ctx, k >= 1 && k + 1 <= 32 * SNN_SLOTS, "cb200_snn: 1 <= k <= %d supported (got %d)", 32 * SNN_SLOTS - 1, k);
@@ -297,6 +325,7 @@ static int snn_core(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int t
     CB_CUDA(ctx, ctx->ecnt.ensure((size_t)nj));
     CB_CUDA(ctx, ctx->eptr.ensure((size_t)nj + 1));
     CB_CUDA(ctx, ctx->bcnt.ensure((size_t)nj * L));
+    CB_CUDA(ctx, ctx->snn_bounds.ensure(2 * (SNN_CHUNKS + 1)));
 
     cb_stage_begin(ctx, ST_SNN_REVLIST);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->rcnt.p, 0, (size_t)n * sizeof(int32_t), ctx->stream));
@@ -314,21 +343,64 @@ static int snn_core(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int t
 
     cb_stage_begin(ctx, ST_SNN_EDGES);
     const int g3 = cb_grid_for(nj, 8, ctx->num_sms * 16);
-    launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end);
+    launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0);
     CB_LAUNCH(ctx);
     CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->ecnt.p, nj, ctx->eptr.p));
-    int64_t ne = 0;
-    CB_CUDA(ctx, cudaMemcpyAsync(&ne, ctx->eptr.p + nj, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    CB_CUDA(ctx, ctx->efrom.ensure((size_t)ne));
-    CB_CUDA(ctx, ctx->eto.ensure((size_t)ne));
-    CB_CUDA(ctx, ctx->ew8.ensure((size_t)ne));
-    launch_snn_merge<1>(ctx, g3, d_nn, n, k, type, j_begin, j_end);
+    k_snn_chunk_bounds<<<1, 32, 0, ctx->stream>>>(ctx->eptr.p, nj, ctx->snn_bounds.p);
     CB_LAUNCH(ctx);
-    cb_stage_end(ctx, ST_SNN_EDGES);
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->snn_bounds_h, ctx->snn_bounds.p, 2 * (SNN_CHUNKS + 1) * sizeof(int64_t),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t ne = ctx->snn_bounds_h[2 * SNN_CHUNKS + 1];
+    ctx->snn_nn = d_nn;
+    ctx->snn_n = n;
+    ctx->snn_k = k;
+    ctx->snn_type = type;
+    ctx->snn_jbegin = j_begin;
+    ctx->snn_jend = j_end;
+    ctx->snn_counted = true;
     ctx->n_edges = ne;
     *n_edges = ne;
     return 0;
+}
+
+// emission pass of the counted range, in SNN_CHUNKS pieces of about equal size; with host outputs
+// every piece is copied out (paced background copies) while the next one is being emitted
+static int snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight)
+{
+    CB_CHECK(ctx, ctx->snn_counted, "cb200_snn_emit: no counted SNN range in the context (call cb200_snn_count_device first)");
+    const int64_t ne = ctx->n_edges;
+    CB_CUDA(ctx, ctx->efrom.ensure((size_t)ne));
+    CB_CUDA(ctx, ctx->eto.ensure((size_t)ne));
+    CB_CUDA(ctx, ctx->ew8.ensure((size_t)ne));
+    const bool out = from != nullptr && to != nullptr && weight != nullptr;
+    const int64_t *bd = ctx->snn_bounds_h;
+    for (int c = 0; c < SNN_CHUNKS; ++c) {
+        const int64_t ja = bd[2 * c], jb = bd[2 * c + 2], ea = bd[2 * c + 1], eb = bd[2 * c + 3];
+        if (jb <= ja)
+            continue;
+        const int g3 = cb_grid_for(jb - ja, 8, ctx->num_sms * 16);
+        launch_snn_merge<1>(ctx, g3, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
+                            ctx->snn_jbegin + jb, ja);
+        CB_LAUNCH(ctx);
+        if (out && eb > ea) {
+            CB_TRY(cb200_copy_async(ctx, from + ea, ctx->efrom.p + ea, (size_t)(eb - ea) * sizeof(int32_t)));
+            CB_TRY(cb200_copy_async(ctx, to + ea, ctx->eto.p + ea, (size_t)(eb - ea) * sizeof(int32_t)));
+            CB_TRY(cb200_copy_async(ctx, weight + ea, ctx->ew8.p + ea, (size_t)(eb - ea) * sizeof(double)));
+        }
+    }
+    cb_stage_end(ctx, ST_SNN_EDGES);
+    ctx->snn_counted = false;
+    if (out)
+        CB_TRY(cb200_copies_wait(ctx));
+    return 0;
+}
+
+static int snn_core(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
+                    int64_t *n_edges)
+{
+    CB_TRY(snn_count(ctx, d_nn, n, k, type, j_begin, j_end, n_edges));
+    return snn_emit(ctx, nullptr, nullptr, nullptr);
 }
 
 static int snn_fetch(cb200_ctx *ctx, int64_t ne, int32_t **from, int32_t **to, double **weight)
@@ -439,6 +511,36 @@ extern "C" int cb200_snn(cb200_ctx *ctx, const int32_t *index, int64_t n_total, 
     }
     CB_TRY(snn_core(ctx, d_nn, n_total, k, type, j_begin, j_end, n_edges));
     return snn_fetch(ctx, *n_edges, from, to, weight);
+}
+
+// Two-phase form for callers that own the result buffers (R vectors, pinned staging): count, let the
+// caller size its arrays, then emit straight into them with the copies overlapping the emission.
+extern "C" int cb200_snn_count_device(cb200_ctx *ctx, const int32_t *d_index_rowmajor0, int64_t n_total, int k,
+                                      int type, int64_t j_begin, int64_t j_end, int64_t *n_edges)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, n_edges != nullptr, "cb200_snn_count_device: NULL argument");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int32_t *d_nn = d_index_rowmajor0;
+    if (d_nn == nullptr) {
+        CB_CHECK(ctx, ctx->have_knn && ctx->knn_nq == n_total && ctx->knn_ntotal == n_total && ctx->knn_k == k,
+                 "cb200_snn_count_device: no index given and the resident kNN result does not cover all %lld cells "
+                 "with k=%d", (long long)n_total, k);
+        d_nn = ctx->knn.p;
+    }
+    return snn_count(ctx, d_nn, n_total, k, type, j_begin, j_end, n_edges);
+}
+
+extern "C" int cb200_snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CB_TRY(snn_emit(ctx, from, to, weight));
+    if (from == nullptr)
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 extern "C" int cb200_snn_resident(cb200_ctx *ctx, int k, int type, int64_t *n_edges)

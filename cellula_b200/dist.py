@@ -112,10 +112,10 @@ class CudaShard:
     def snn(self, knn_full, snn_type, j_begin, j_end, fetch=True, edge_buffers=None):
         n, k = knn_full.shape
         if fetch and edge_buffers is not None:
-            # count first, then copy straight into the caller's (pinned) arrays
-            ne = self.ctx.snn_device(knn_full.data_ptr(), n, k, snn_type, j_begin, j_end, fetch=False)
+            # count first, then emit straight into the caller's (pinned) arrays, copies behind the emission
+            ne = self.ctx.snn_count_device(knn_full.data_ptr(), n, k, snn_type, j_begin, j_end)
             f, t, w = edge_buffers(ne)
-            return self.ctx.fetch_edges(ne, f, t, w)
+            return self.ctx.snn_emit(ne, f, t, w)
         return self.ctx.snn_device(knn_full.data_ptr(), n, k, snn_type, j_begin, j_end, fetch=fetch)
 
 
@@ -154,7 +154,14 @@ class ShardedPipeline:
     # -- stages ----------------------------------------------------------------------
     def size_factors(self, sf_in=None, want=True):
         part = self._allreduce(self.shard.libsize_partial(sf_in))
-        tot = part.cpu().numpy()
+        if part.is_cuda:   # pinned landing zone: a pageable read would queue behind background copies
+            if getattr(self, "_pin2", None) is None:
+                self._pin2 = torch.empty(2, dtype=torch.float64).pin_memory()
+            self._pin2.copy_(part, non_blocking=True)
+            torch.cuda.current_stream(part.device).synchronize()
+            tot = self._pin2.numpy().copy()
+        else:
+            tot = part.cpu().numpy()
         return self.shard.finish_size_factors(float(tot[0]), int(round(float(tot[1]))), want=want)
 
     def gene_stats(self):
@@ -187,17 +194,28 @@ class ShardedPipeline:
         scores_out: optional column-major (n_local x ndims) host array (e.g. pinned) for the scores;
         edge_buffers: optional callable n_edges -> (from, to, weight) host arrays to fill;
         logx_out: optional pinned array for the logcounts, copied out behind the following stages."""
+        import time
+        marks = [("start", time.perf_counter())]
         sf = self.size_factors(sf_in, want=want_host)
+        marks.append(("size_factors", time.perf_counter()))
         mean, var = self.gene_stats()
+        marks.append(("gene_stats", time.perf_counter()))
         if logx_out is not None:
             self.shard.logcounts_async(logx_out)            # overlaps the trend fit, PCA, kNN and SNN
         stats = trendvar.model_gene_var(mean, var)          # replicated host step (R: scran::fitTrendVar)
         hvgs = trendvar.get_top_hvgs(stats, hvg_ntop)
+        marks.append(("trend_hvg", time.perf_counter()))
         pca = self.pca(hvgs, ndims, want_scores=want_host, scores_out=scores_out if want_host else None)
+        marks.append(("pca", time.perf_counter()))
         knn_full = self.knn(pca["scores_full_dev"], neighbors)
+        marks.append(("knn", time.perf_counter()))
         # (from, to, w), or the count if resident
         edges = self.snn(knn_full, snn_type, fetch=want_host, edge_buffers=edge_buffers)
+        marks.append(("snn", time.perf_counter()))
         if logx_out is not None:
             self.shard.wait_copies()
+        marks.append(("wait_copies", time.perf_counter()))
+        # host wall-clock split of this call (ms since entry; device work is asynchronous between syncs)
+        self.last_marks = {k: 1e3 * (t - marks[0][1]) for k, t in marks[1:]}
         return dict(sf=sf, mean=mean, var=var, stats=stats, hvgs=hvgs, pca=pca, knn_full=knn_full,
                     edges=edges)

@@ -181,6 +181,14 @@ int cb200_snn_device(cb200_ctx *ctx, const int32_t *d_index_rowmajor0, int64_t n
                      int32_t **to, double **weight);
 /* Device-only variant: edges stay in HBM (bench "value" leg); returns the count. */
 int cb200_snn_resident(cb200_ctx *ctx, int k, int type, int64_t *n_edges);
+/* Two-phase form for callers that own the result vectors (what the R shim does: count, allocVector,
+ * emit): cb200_snn_count_device builds the reverse lists and counts the edges of cells
+ * [j_begin, j_end) (d_index_rowmajor0 NULL = the resident kNN result); cb200_snn_emit then writes
+ * them -- into from/to/weight (host, n_edges entries each; the device->host copies overlap the
+ * emission) or, with NULL pointers, only into HBM (cb200_fetch_edges copies them later). */
+int cb200_snn_count_device(cb200_ctx *ctx, const int32_t *d_index_rowmajor0, int64_t n_total, int k,
+                           int type, int64_t j_begin, int64_t j_end, int64_t *n_edges);
+int cb200_snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight);
 int cb200_free_edges(int32_t *from, int32_t *to, double *weight);
 /* Copies the n_edges edges left in HBM by the last cb200_snn / cb200_snn_device / cb200_snn_resident
  * call into caller-owned arrays (what the R shim does with freshly allocated R vectors). */

@@ -132,10 +132,11 @@ SEXP cb200r_snn_graph(SEXP sctx, SEXP space, SEXP k, SEXP type)
     int d = Rf_ncols(space), kk = Rf_asInteger(k);
     CB_OK(ctx, cb200_knn(ctx, REAL(space), n, d, kk, 0, n, NULL));
     int64_t ne = 0;
-    CB_OK(ctx, cb200_snn_resident(ctx, kk, Rf_asInteger(type), &ne));  /* edges stay in HBM */
+    /* count, size the R vectors, emit straight into them (copies overlap the emission) */
+    CB_OK(ctx, cb200_snn_count_device(ctx, NULL, n, kk, Rf_asInteger(type), 0, n, &ne));
     SEXP sf = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)ne)), st = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)ne));
     SEXP sw = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)ne));
-    if (cb200_fetch_edges(ctx, ne, INTEGER(sf), INTEGER(st), REAL(sw)) != 0) { /* straight into the R vectors */
+    if (cb200_snn_emit(ctx, INTEGER(sf), INTEGER(st), REAL(sw)) != 0) {
         UNPROTECT(3);
         Rf_error("%s", cb200_last_error(ctx));
     }

@@ -73,6 +73,28 @@ def test_snn_resident_knn_equals_host_index(gpu_ctx):
     assert gpu_ctx.snn_resident(20, "jaccard") == len(b[0])
 
 
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_snn_two_phase_into_caller_buffers(gpu_ctx, scheme):
+    """count -> caller sizes its arrays -> emit in pieces with the copies behind the emission: same
+    edges, same order, for the whole range and for a sub-range of cells."""
+    import torch
+    emb = synth.make_embedding(20000, 20, seed=44)
+    knn = gpu_ctx.knn(emb, 20)
+    want = O.snn_edges(knn, scheme)
+    ne = gpu_ctx.snn_count_device(0, 20000, 20, scheme, 0, 20000)       # 0: the resident kNN result
+    assert ne == len(want[0])
+    f = torch.empty(ne + 5, dtype=torch.int32).pin_memory().numpy()
+    t = torch.empty(ne + 5, dtype=torch.int32).pin_memory().numpy()
+    w = torch.empty(ne + 5, dtype=torch.float64).pin_memory().numpy()
+    assert_same_edges(gpu_ctx.snn_emit(ne, f, t, w), want)
+    assert_same_edges(gpu_ctx.fetch_edges(ne), want)                     # and they are left in HBM too
+    with pytest.raises(cellula_b200.Cb200Error, match="no counted SNN range"):
+        gpu_ctx.snn_emit(ne, f, t, w)
+    full = gpu_ctx.snn(knn, scheme, j_begin=5000, j_end=12345)
+    ne2 = gpu_ctx.snn_count_device(0, 20000, 20, scheme, 5000, 12345)
+    assert_same_edges(gpu_ctx.snn_emit(ne2), full)
+
+
 def test_snn_argument_errors(gpu_ctx):
     knn = O.find_knn(synth.make_embedding(100, 5, seed=1), 5)
     bad = knn.copy()
