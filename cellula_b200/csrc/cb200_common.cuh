@@ -133,6 +133,7 @@ struct cb200_ctx {
     DevBuf<unsigned long long> maxnrm;  // [1] bit pattern of max |r|^2
     DevBuf<int32_t> cand_idx;  // [nq*KP]
     DevBuf<float> cand_tau;    // [nq]
+    DevBuf<float> cand_err;    // [nq] per-query bound of |approximate key - exact key| (tensor-core engine)
     DevBuf<int32_t> knn;       // [nq*k] row-major 0-based
     DevBuf<double> knn_dk;     // [nq] exact k-th candidate distance
     DevBuf<int32_t> fb_list;   // [nq] queries needing the exact scan

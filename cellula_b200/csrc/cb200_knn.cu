@@ -265,7 +265,8 @@ template <int KP>
 __global__ void __launch_bounds__(256)
 k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, int64_t nq, int k,
              const int32_t *__restrict__ cand_idx, const float *__restrict__ cand_tau, int ntau, const double *__restrict__ nrm2,
-             const unsigned long long *__restrict__ maxbits, double err_coef, const int32_t *__restrict__ qlist,
+             const unsigned long long *__restrict__ maxbits, double err_coef, const float *__restrict__ cand_err,
+             const int32_t *__restrict__ qlist,
              int32_t *__restrict__ knn, double *__restrict__ knn_dk, int32_t *__restrict__ fb_list,
              int *__restrict__ fb_count)
 {
@@ -309,9 +310,18 @@ k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, 
         }
         if (lane == 0) {
             knn_dk[orow] = dk;
-            const double nq2 = nrm2[grow];
-            const double ek = 0.5 * dk * dk - 0.5 * nq2;      // exact key of the k-th candidate
-            const double bound = err_coef * (nq2 + m2);       // |approx key - exact key| <= bound
+            // exact key of the k-th candidate and the bound of |approx key - exact key|: the tensor-core
+            // engine uses the canonical key 0.5 d^2 and records a bound per query, the fp32 engine the
+            // key 0.5 d^2 - 0.5 |q|^2 with an a-priori bound
+            double ek, bound;
+            if (cand_err != nullptr) {
+                ek = 0.5 * dk * dk;
+                bound = (double)cand_err[q];
+            } else {
+                const double nq2 = nrm2[grow];
+                ek = 0.5 * dk * dk - 0.5 * nq2;
+                bound = err_coef * (nq2 + m2);
+            }
             // every non-candidate has an approximate key >= the smallest of the ntau thresholds
             float tau = cand_tau[q * ntau];
             for (int u = 1; u < ntau; ++u)
@@ -411,7 +421,8 @@ static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, i
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 2, 0, sizeof(int), ctx->stream));
     const int rgrid = cb_grid_for(nq, 8, ctx->num_sms * 16);
     k_knn_rerank<KP><<<rgrid, 256, 0, ctx->stream>>>(E, lde, d, q_begin, nq, k, ctx->cand_idx.p, ctx->cand_tau.p,
-                                                     ntau, ctx->nrm2.p, ctx->maxnrm.p, err_coef, qlist, ctx->knn.p, ctx->knn_dk.p,
+                                                     ntau, ctx->nrm2.p, ctx->maxnrm.p, err_coef,
+                                                     err_coef < 0.0 ? ctx->cand_err.p : nullptr, qlist, ctx->knn.p, ctx->knn_dk.p,
                                                      ctx->fb_list.p, ctx->flag.p + 2);
     CB_LAUNCH(ctx);
     int h[2] = {0, 0};

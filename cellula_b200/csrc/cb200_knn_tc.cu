@@ -303,8 +303,9 @@ __global__ void k_knn_tc_qscatter(const int32_t *__restrict__ perm, const int32_
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, const int32_t *__restrict__ perm,
-              const float *__restrict__ rho, unsigned char *__restrict__ img, double *__restrict__ nrm2,
-              unsigned long long *__restrict__ maxbits, float *__restrict__ tile_lo, float *__restrict__ tile_hi)
+              const float *__restrict__ rho, const int32_t *__restrict__ cl, const double *__restrict__ cen,
+              unsigned char *__restrict__ img, double *__restrict__ nrm2, unsigned long long *__restrict__ maxbits,
+              float *__restrict__ tile_lo, float *__restrict__ tile_hi)
 {
     __shared__ float smin[4], smax[4];
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // sorted position
@@ -313,13 +314,14 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, co
     __half *hi_base = reinterpret_cast<__half *>(tile);
     __half *lo_base = reinterpret_cast<__half *>(tile + TC_PART_BYTES);
     const int64_t src = (int64_t)perm[i];  // -1: padding position
+    const double *cj = src >= 0 ? cen + (size_t)cl[src] * d : nullptr;   // centre of the point's cluster
     double s = 0.0, sp = 0.0;
     for (int t = 0; t < TC_K; ++t) {
         __half h = __float2half(0.f), l = __float2half(0.f);
         if (src >= 0 && t < d) {
             const double v = E[src * lde + t];
             s += v * v;
-            const double vs = v * scale;
+            const double vs = v * scale - cj[t];   // coordinates relative to the cluster centre
             sp += vs * vs;
             split_h(vs, h, l);
         }
@@ -327,7 +329,7 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, co
         *reinterpret_cast<__half *>(reinterpret_cast<unsigned char *>(hi_base) + off) = h;
         *reinterpret_cast<__half *>(reinterpret_cast<unsigned char *>(lo_base) + off) = l;
     }
-    // -0.5|r'|^2 in the three spare K columns of the hi part
+    // -0.5|r~|^2 in the three spare K columns of the hi part
     __half a1, a2, a3;
     float rlo = INFINITY, rhi = -INFINITY;  // an all-padding tile is never needed
     if (src >= 0) {
@@ -388,37 +390,38 @@ constexpr int TC_RING = 16;  // tile ids of the sequence in flight (producer -> 
 constexpr int TC_SCAN_SETS = 2;
 constexpr int TC_ACC_STAGES = 4;
 constexpr int TC_POS_BITS = 27;  // sorted positions in a ring entry
-constexpr int TC_THREADS = 64 + TC_SCAN_SETS * 128 + 128;
+constexpr int TC_THREADS = 64 + TC_SCAN_SETS * 128 + 128 + 128;  // + inserters + query-image builders
 
 template <int KP, int STAGES, int QCAP>
 struct TcSmem {
-    static constexpr size_t q_img = 0;
-    static constexpr size_t r_img = q_img + TC_TILE_BYTES;
+    static constexpr size_t q_img = 0;                                      // 2 x (Q hi | Q lo)
+    static constexpr size_t r_img = q_img + 2 * TC_TILE_BYTES;
     static constexpr size_t hk = r_img + (size_t)STAGES * TC_TILE_BYTES;    // [KP][TC_M] heap keys (T values)
     static constexpr size_t hi = hk + (size_t)TC_M * KP * 4;                // [KP][TC_M] sorted positions
     static constexpr size_t ring = hi + (size_t)TC_M * KP * 4;              // [SETS][QCAP][TC_M] uint2
     static constexpr size_t bars = ring + (size_t)TC_SCAN_SETS * QCAP * TC_M * 8;  // full/empty[STAGES], tfull/tempty[ACC]
-    static constexpr size_t thr_sh = bars + (size_t)(2 * STAGES + 2 * TC_ACC_STAGES) * 8;  // [TC_M] float
+    static constexpr size_t thr_sh = bars + (size_t)(2 * STAGES + 2 * TC_ACC_STAGES + 8) * 8;  // [TC_M] float
     static constexpr size_t qhead = thr_sh + TC_M * 4;                      // [SETS][TC_M]
     static constexpr size_t misc = qhead + TC_SCAN_SETS * TC_M * 4;         // tmem slot, scan_done
-    static constexpr size_t seq_tile = misc + 16;                           // [TC_RING]
-    static constexpr size_t bytes = seq_tile + TC_RING * 4;
+    static constexpr size_t seq_tile = misc + 16;                           // [TC_RING] tile, [TC_RING] meta
+    static constexpr size_t bytes = seq_tile + 2 * TC_RING * 4;
 };
 
 template <int KP, int STAGES, int QCAP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, const unsigned char *__restrict__ img,
                int64_t nq, const int32_t *__restrict__ qlist, const int32_t *__restrict__ qpos,
-               const int32_t *__restrict__ perm, int C, const float *__restrict__ dqc, const int32_t *__restrict__ cl,
-               const uint16_t *__restrict__ cl_order, const int32_t *__restrict__ cl_tile_begin,
-               const unsigned int *__restrict__ cl_rhomax, const float *__restrict__ tile_lo,
-               const float *__restrict__ tile_hi, float key_unscale, int cand_stride, int32_t *__restrict__ cand_idx,
-               float *__restrict__ cand_tau, int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done)
+               const int32_t *__restrict__ perm, int C, const double *__restrict__ cen, const float *__restrict__ dqc,
+               const int32_t *__restrict__ cl, const uint16_t *__restrict__ cl_order,
+               const int32_t *__restrict__ cl_tile_begin, const unsigned int *__restrict__ cl_rhomax,
+               const float *__restrict__ tile_lo, const float *__restrict__ tile_hi, float key_unscale, int cand_stride,
+               int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau, float *__restrict__ cand_err,
+               int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done)
 {
     using L = TcSmem<KP, STAGES, QCAP>;
     constexpr uint32_t TC_TMEM_COLS = TC_ACC_STAGES * TC_N;  // 512
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *q_img = smem + L::q_img;                                // 32 KB: Q hi | Q lo
+    unsigned char *q_img = smem + L::q_img;                                // 2 x 32 KB: Q hi | Q lo, per cluster visit
     unsigned char *r_img = smem + L::r_img;                                // STAGES x 32 KB
     float *hk = reinterpret_cast<float *>(smem + L::hk);
     int *hi_ = reinterpret_cast<int *>(smem + L::hi);
@@ -428,37 +431,21 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     uint64_t *empty = bars + STAGES;             // [STAGES]
     uint64_t *tfull = bars + 2 * STAGES;         // [TC_ACC_STAGES]
     uint64_t *tempty = tfull + TC_ACC_STAGES;    // [TC_ACC_STAGES]
+    uint64_t *qreq = tempty + TC_ACC_STAGES;     // [2] producer -> builders: build the image of cluster q_cluster[b]
+    uint64_t *qfull = qreq + 2;                  // [2] builders -> MMA issuer (and producer): image b is ready
+    uint64_t *qfree = qfull + 2;                 // [2] MMA issuer -> builders: image b is no longer read
+    volatile int *q_cluster = reinterpret_cast<volatile int *>(qfree + 2);  // [2]
     volatile float *thr_sh = reinterpret_cast<volatile float *>(smem + L::thr_sh);
     volatile unsigned int *qhead = reinterpret_cast<volatile unsigned int *>(smem + L::qhead);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::misc);
     unsigned int *scan_done = reinterpret_cast<unsigned int *>(smem + L::misc + 4);
     volatile int *seq_tile = reinterpret_cast<volatile int *>(smem + L::seq_tile);
+    volatile int *seq_meta = seq_tile + TC_RING;  // cluster | image buffer << 16 | first tile of a visit << 17
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ql0 = (int64_t)blockIdx.x * TC_M;   // first entry of the (sorted) query list
 
     // ---- one-time setup ------------------------------------------------------------------
-    // query operand image (generic-proxy stores, made visible to the async proxy below)
-    for (int i = tid; i < TC_M * TC_K; i += TC_THREADS) {
-        const int row = i / TC_K, t = i % TC_K;
-        const int64_t ql = ql0 + row;
-        __half h = __float2half(0.f), l = __float2half(0.f);
-        if (ql < nq) {
-            const int64_t g = qlist[ql];
-            if (t < d) {
-                split_h(E[g * lde + t] * scale, h, l);
-            } else if (t == d) {
-                h = __float2half(4096.f);
-            } else if (t == d + 1) {
-                h = __float2half(1.f);
-            } else if (t == d + 2) {
-                h = __float2half(1.0f / 4096.f);
-            }
-        }
-        const uint32_t off = swz_offset(row, t * 2);
-        *reinterpret_cast<__half *>(q_img + off) = h;
-        *reinterpret_cast<__half *>(q_img + TC_PART_BYTES + off) = l;
-    }
     for (int i = tid; i < TC_SCAN_SETS * QCAP * TC_M; i += TC_THREADS)
         ring[i] = make_uint2(0u, 0x80000000u);  // parity of lap -1
     for (int i = tid; i < TC_M; i += TC_THREADS)
@@ -476,11 +463,15 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             mbar_init(tfull + a, 1);
             mbar_init(tempty + a, 4);  // one arrival per scanner warp of the set
         }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(qreq + b, 1);
+            mbar_init(qfull + b, 4);   // one arrival per builder warp
+            mbar_init(qfree + b, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0)
         tmem_alloc(tmem_slot, TC_TMEM_COLS);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -488,58 +479,111 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 
     if (warp == 0) {
         // ===== producer: visits the clusters by ascending centre distance from the query tile's own
-        // cluster and stages only the tiles some row can still reach (whole warp: lane = 4 query rows) =====
+        // cluster and stages only the tiles some row can still reach (whole warp: lane = 4 query rows).
+        // The search for the next tile runs ahead of the wait for a free stage.  After the home cluster
+        // (thresholds exist by then) one warp-parallel pass over the distance table drops every cluster
+        // no row can reach -- a cluster out of reach stays out of reach, the thresholds only tighten --
+        // so the serial walk only touches the few candidates left. =====
         constexpr float EPS = 3e-7f;
-        int64_t g[4];
-        float qn[4], dlo[4], dhi[4], lo[4], hi[4];
+        constexpr int NW = TC_MAXC / 32;   // candidate words: bit b of word w = position w*32 + b of `order`
+        int g[4];
+        float dlo[4], dhi[4], lo[4], hi[4], dq[4], smax[4], omax[4], reach[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t ql = ql0 + u * 32 + lane;
-            g[u] = ql < nq ? (int64_t)qlist[ql] : -1;
-            qn[u] = 0.f;
-            if (g[u] >= 0) {
-                double sp = 0.0;
-                for (int t = 0; t < d; ++t) {
-                    const double vs = E[g[u] * lde + t] * scale;
-                    sp += vs * vs;
-                }
-                qn[u] = nextafterf((float)(0.5 * sp), FLT_MAX);
-            }
+            g[u] = ql < nq ? qlist[ql] : -1;
             dlo[u] = INFINITY;   // rows past the list need nothing
             dhi[u] = -INFINITY;
             lo[u] = INFINITY;
             hi[u] = -INFINITY;
+            dq[u] = 0.f;
+            reach[u] = INFINITY;
+            smax[u] = 0.f;       // largest |q~||r~| + 0.5|r~|^2 bound over the clusters scanned (error bound)
+            omax[u] = 0.f;       // largest key offset 0.5 |q~|^2 over the clusters scanned
         }
         const int64_t nvalid = nq - ql0 < TC_M ? nq - ql0 : TC_M;
         const int home = cl[qlist[ql0 + nvalid / 2]];
         const uint16_t *order = cl_order + (size_t)home * C;
+        unsigned words[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            words[w] = 0u;
+        words[0] = 1u;                 // the home cluster first
+        bool prefiltered = false;
+        int wpos = 0;
         int64_t seq = 0;
-        int oi = 0, t = 0, te = 0, tb32 = 0;
+        int t = 0, te = 0, tb32 = 0, cur_j = -1;
+        int visit = -1;               // cluster visits that staged at least one tile so far, minus one
+        bool visit_open = false;      // the current cluster already has its query image requested
         float blo = 0.f, bhi = 0.f;   // bounds of tile tb32 + lane
         float crmax = 0.f;
-        while (true) {
-            const int s = (int)(seq % STAGES);
-            if (lane == 0)
-                mbar_wait(empty + s, (uint32_t)((seq / STAGES) & 1) ^ 1u, err_flag);
-            __syncwarp();
-            // how far every row can still find a candidate: d <= sqrt(2 (key_thr + qn)), rounded up
-            float reach[4];
+
+        auto refresh = [&]() {
+            // how far every row can still find a candidate: canonical T = -0.5 d^2, rounded up
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const float thr = thr_sh[u * 32 + lane];
-                reach[u] = thr == -FLT_MAX ? INFINITY
-                                           : sqrtf(fmaxf(2.0f * (qn[u] - thr), 0.f)) * 1.000002f + 1e-30f;
+                reach[u] = thr == -FLT_MAX ? INFINITY : sqrtf(fmaxf(-2.0f * thr, 0.f)) * 1.000002f + 1e-30f;
                 if (g[u] >= 0) {
                     lo[u] = dlo[u] - reach[u];
                     hi[u] = dhi[u] + reach[u];
                 }
             }
-            bool found = false;
+        };
+        auto prefilter = [&]() {
+            // lane = 32 positions of `order` (p = w*32 + lane); rows one after the other
+            if (C > 256) {   // more clusters than the register budget below: keep them all
+                for (int w = 0; w < NW; ++w) {
+                    const int left = C - w * 32;
+                    words[w] = left >= 32 ? 0xffffffffu : (left > 0 ? ((1u << left) - 1u) : 0u);
+                }
+                words[0] &= ~1u;
+                return;
+            }
+            int jm[8];
+            float lb[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int p = w * 32 + lane;
+                jm[w] = p < C ? (int)order[p] : -1;
+                lb[w] = INFINITY;
+            }
+            for (int r = 0; r < TC_M; ++r) {
+                const int gr = __shfl_sync(0xffffffffu, g[r >> 5], r & 31);
+                const float rr = __shfl_sync(0xffffffffu, reach[r >> 5], r & 31);
+                if (gr < 0)
+                    continue;
+                const float *drow = dqc + (size_t)gr * C;
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                    if (jm[w] >= 0)
+                        lb[w] = fminf(lb[w], drow[jm[w]] * (1.f - EPS) - rr);
+            }
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const bool need = jm[w] >= 0 && lb[w] <= __uint_as_float(cl_rhomax[jm[w]]) * (1.f + EPS);
+                words[w] = __ballot_sync(0xffffffffu, need);
+            }
+            words[0] &= ~1u;   // the home cluster is done
+        };
+        // advances (t, te, cur_j, ...) to the next tile some row can reach; false when nothing is left
+        auto find_next = [&]() -> bool {
             while (true) {
-                if (t >= te) {  // next cluster
-                    if (oi >= C)
-                        break;
-                    const int j = order[oi++];
+                if (t >= te) {  // next candidate cluster
+                    while (wpos < NW && words[wpos] == 0u)
+                        ++wpos;
+                    if (wpos >= NW) {
+                        if (prefiltered)
+                            return false;
+                        prefiltered = true;
+                        refresh();
+                        prefilter();
+                        wpos = 0;
+                        continue;
+                    }
+                    const int bit = __ffs(words[wpos]) - 1;
+                    words[wpos] &= words[wpos] - 1u;
+                    const int j = order[wpos * 32 + bit];
                     t = cl_tile_begin[j];
                     te = cl_tile_begin[j + 1];
                     if (t >= te)
@@ -549,9 +593,9 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         if (g[u] >= 0) {
-                            const float dq = dqc[(size_t)g[u] * C + j];
-                            dlo[u] = dq * (1.f - EPS);
-                            dhi[u] = dq * (1.f + EPS);
+                            dq[u] = dqc[(size_t)g[u] * C + j];
+                            dlo[u] = dq[u] * (1.f - EPS);
+                            dhi[u] = dq[u] * (1.f + EPS);
                             lo[u] = dlo[u] - reach[u];
                             hi[u] = dhi[u] + reach[u];
                             need |= lo[u] <= crmax;
@@ -561,6 +605,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                         t = te;
                         continue;
                     }
+                    cur_j = j;
+                    visit_open = false;
                     tb32 = t - 32;  // forces a load of the tile bounds below
                 }
                 if (t >= tb32 + 32) {
@@ -575,34 +621,78 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     need |= (lo[u] <= b) && (hi[u] >= a);
-                if (__any_sync(0xffffffffu, need)) {
-                    found = true;
-                    break;
-                }
+                if (__any_sync(0xffffffffu, need))
+                    return true;
                 ++t;
             }
-            if (!found)
-                break;
+        };
+
+        bool have = find_next();
+        while (have) {
+            const bool first = !visit_open;
+            if (first) {
+                // first tile of this cluster: ask the builders for the query image relative to its centre
+                ++visit;
+                visit_open = true;
+                const int b = visit & 1, use = visit >> 1;
+                if (lane == 0) {
+                    if (use >= 1)   // the builders must have taken the previous request for this buffer
+                        mbar_wait(qfull + b, (uint32_t)((use - 1) & 1), err_flag);
+                    q_cluster[b] = cur_j;
+                    __threadfence_block();
+                    mbar_arrive(qreq + b);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    smax[u] = fmaxf(smax[u], dq[u] * crmax + 0.5f * crmax * crmax);
+                    omax[u] = fmaxf(omax[u], 0.5f * dq[u] * dq[u]);
+                }
+            }
+            const int s = (int)(seq % STAGES);
             if (lane == 0) {
+                mbar_wait(empty + s, (uint32_t)((seq / STAGES) & 1) ^ 1u, err_flag);
                 seq_tile[seq % TC_RING] = t;
+                seq_meta[seq % TC_RING] = cur_j | ((visit & 1) << 16) | ((first ? 1 : 0) << 17);
                 mbar_expect_tx(full + s, TC_TILE_BYTES);
                 bulk_g2s(r_img + (size_t)s * TC_TILE_BYTES, img + (int64_t)t * TC_TILE_BYTES, TC_TILE_BYTES, full + s);
             }
+            __syncwarp();
             ++t;
             ++seq;
+            refresh();
+            have = find_next();
         }
-        // end of the sequence (the empty slot of stage seq % STAGES has been waited for above)
+        // end of the sequence
         if (lane == 0) {
+            mbar_wait(empty + (int)(seq % STAGES), (uint32_t)((seq / STAGES) & 1) ^ 1u, err_flag);
             seq_tile[seq % TC_RING] = -1;
             __threadfence_block();
             mbar_arrive(full + (int)(seq % STAGES));
             atomicAdd(tiles_done, (unsigned long long)seq);
+            // stop the builders
+            const int v = visit + 1, b = v & 1, use = v >> 1;
+            if (use >= 1)
+                mbar_wait(qfull + b, (uint32_t)((use - 1) & 1), err_flag);
+            q_cluster[b] = -1;
+            __threadfence_block();
+            mbar_arrive(qreq + b);
+        }
+        // a-priori bound of |approximate key - exact key| of every reference this row was compared with
+        // (scaled^2 units -> unscaled): fp16 split + fp32 accumulation relative to |q~||r~| + 0.5|r~|^2,
+        // rounding of the key offset 0.5|q~|^2, fp16 underflow floor
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t ql = ql0 + u * 32 + lane;
+            if (ql < nq)
+                cand_err[ql] = (4.6e-5f * smax[u] + 4.8e-7f * omax[u] + 0.02f) * key_unscale;
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t qh = smem_u32(q_img), ql = smem_u32(q_img + TC_PART_BYTES);
+            int prev_b = -1;
+            uint32_t quse[2] = {0u, 0u};   // visits that used image buffer b so far
+            uint32_t qh = 0, ql = 0;
             for (int64_t seq = 0;; ++seq) {
                 const int s = (int)(seq % STAGES);
                 const uint32_t ph = (uint32_t)((seq / STAGES) & 1);
@@ -623,6 +713,18 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                         mbar_arrive(tfull + a2);
                     }
                     break;
+                }
+                const int meta = seq_meta[seq % TC_RING];
+                if (meta & (1 << 17)) {   // first tile of a cluster visit: switch to its query image
+                    const int b = (meta >> 16) & 1;
+                    if (prev_b >= 0)
+                        umma_commit(qfree + prev_b);   // every MMA reading the previous image has been issued
+                    mbar_wait(qfull + b, quse[b] & 1u, err_flag);
+                    tc_fence_after();
+                    quse[b] += 1;
+                    prev_b = b;
+                    qh = smem_u32(q_img + (size_t)b * TC_TILE_BYTES);
+                    ql = qh + TC_PART_BYTES;
                 }
                 const uint32_t rh = smem_u32(r_img + (size_t)s * TC_TILE_BYTES), rl = rh + TC_PART_BYTES;
                 const uint32_t dcol = tmem_base + (uint32_t)(a * TC_N);
@@ -650,9 +752,12 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         const int64_t myql = ql0 + row;
         const bool active = myql < nq;
         const int my_pos = active ? qpos[myql] : -1;   // sorted position of the query itself (self-exclusion)
+        const float *mydq = active ? dqc + (size_t)qlist[myql] * C : nullptr;
         const uint32_t ring_addr = smem_u32(ring + (size_t)set * QCAP * TC_M + row);  // slot s at + s*TC_M*8
         volatile unsigned int *myhead = qhead + set * TC_M + row;
         unsigned tail = 0u;
+        int cur_j = -1;
+        float off = 0.f;   // key offset of the current cluster: 0.5 |q - c_j|^2 (canonical T = T_j - off)
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
         for (int64_t seq = set;; seq += TC_SCAN_SETS) {
             const int a = (int)(seq % TC_ACC_STAGES);
@@ -661,23 +766,29 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             const int t = seq_tile[seq % TC_RING];
             if (t < 0)
                 break;
+            const int j = seq_meta[seq % TC_RING] & 0xffff;
+            if (j != cur_j) {
+                cur_j = j;
+                const float dq = active ? mydq[j] : 0.f;
+                off = 0.5f * dq * dq;
+            }
             const int r0 = t * TC_N;
             const uint32_t tcol = tbase + (uint32_t)(a * TC_N);
             uint32_t r[32];
 #pragma unroll 1
             for (int ch = 0; ch < TC_N / 32; ++ch) {
                 tmem_ld32_issue(tcol + (uint32_t)(ch * 32), r);
-                const float thr = thr_sh[row];     // stale reads only cost extra pushes
+                const float thr = thr_sh[row] + off;   // stale reads only cost extra pushes
                 tmem_ld_wait();
                 float g[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float a0 = fmaxf(fmaxf(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
-                                     __uint_as_float(r[8 * j + 2]));
-                    float a1 = fmaxf(fmaxf(__uint_as_float(r[8 * j + 3]), __uint_as_float(r[8 * j + 4])),
-                                     __uint_as_float(r[8 * j + 5]));
-                    float a2 = fmaxf(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-                    g[j] = fmaxf(fmaxf(a0, a1), a2);
+                for (int jj = 0; jj < 4; ++jj) {
+                    float a0 = fmaxf(fmaxf(__uint_as_float(r[8 * jj]), __uint_as_float(r[8 * jj + 1])),
+                                     __uint_as_float(r[8 * jj + 2]));
+                    float a1 = fmaxf(fmaxf(__uint_as_float(r[8 * jj + 3]), __uint_as_float(r[8 * jj + 4])),
+                                     __uint_as_float(r[8 * jj + 5]));
+                    float a2 = fmaxf(__uint_as_float(r[8 * jj + 6]), __uint_as_float(r[8 * jj + 7]));
+                    g[jj] = fmaxf(fmaxf(a0, a1), a2);
                 }
                 const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
                 if (!__any_sync(0xffffffffu, m > thr))
@@ -697,7 +808,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                             const unsigned meta = (((tail / QCAP) & 1u) << 31) | (unsigned)gcol;
                             asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(
                                              ring_addr + (uint32_t)((tail % QCAP) * TC_M * 8)),
-                                         "r"(r[i]), "r"(meta)
+                                         "r"(__float_as_uint(__uint_as_float(r[i]) - off)), "r"(meta)
                                          : "memory");
                             ++tail;
                         }
@@ -715,7 +826,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             __threadfence_block();
             atomicAdd(scan_done, 1u);
         }
-    } else {
+    } else if (warp < 2 + TC_SCAN_SETS * 4 + 4) {
         // ===== inserters: thread = query row; binary min-heap of the KP largest T in shared memory =====
         const int row = tid - (64 + TC_SCAN_SETS * 128);
         float *mk = hk + row;   // entry e at mk[e * TC_M]
@@ -727,7 +838,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             head[s2] = 0u;
             raddr[s2] = smem_u32(ring + (size_t)s2 * QCAP * TC_M + row);
         }
-        int cnt = 0;            // entries held; the heap is filled from the back (no sifting: parents are empty)
+        int cnt = 0;            // entries held; the heap is filled from the back, then heapified once
         float root = -FLT_MAX;
         bool done_seen = false;
         while (true) {
@@ -807,13 +918,59 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             }
         }
         // final: candidates (original indices, unsorted) and the row threshold in key space, unscaled:
-        // key = 0.5 d^2 - 0.5 |q|^2 = -T
+        // key = 0.5 d^2 = -T
         const int64_t myql = ql0 + row;
         if (myql < nq) {
             int32_t *out = cand_idx + myql * (int64_t)cand_stride;
             for (int p = 0; p < cand_stride; ++p)
                 out[p] = (p < KP && p >= KP - cnt) ? perm[mi[p * TC_M]] : -1;
             cand_tau[myql] = (cnt < KP) ? FLT_MAX : -root * key_unscale;
+        }
+    } else {
+        // ===== builders: thread = query row; the query operand image relative to the centre of the
+        // cluster being visited, into the image buffer the producer names =====
+        const int row = tid - (64 + TC_SCAN_SETS * 128 + 128);
+        const int64_t myql = ql0 + row;
+        const double *qrow = myql < nq ? E + (int64_t)qlist[myql] * lde : nullptr;
+        for (int visit = 0;; ++visit) {
+            const int b = visit & 1, use = visit >> 1;
+            mbar_wait(qreq + b, (uint32_t)(use & 1), err_flag);
+            const int j = q_cluster[b];
+            if (j < 0)
+                break;
+            if (use >= 1)
+                mbar_wait(qfree + b, (uint32_t)((use - 1) & 1), err_flag);
+            const double *cj = cen + (size_t)j * d;
+            unsigned char *qb = q_img + (size_t)b * TC_TILE_BYTES;
+#pragma unroll 1
+            for (int c8 = 0; c8 < TC_K / 8; ++c8) {   // one 16-byte chunk (8 fp16) of the row per pass
+                __align__(16) __half h8[8], l8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int t = c8 * 8 + e;
+                    __half h = __float2half(0.f), l = __float2half(0.f);
+                    if (qrow != nullptr) {
+                        if (t < d) {
+                            split_h(qrow[t] * scale - cj[t], h, l);
+                        } else if (t == d) {
+                            h = __float2half(4096.f);
+                        } else if (t == d + 1) {
+                            h = __float2half(1.f);
+                        } else if (t == d + 2) {
+                            h = __float2half(1.0f / 4096.f);
+                        }
+                    }
+                    h8[e] = h;
+                    l8[e] = l;
+                }
+                const uint32_t o = swz_offset(row, c8 * 16);
+                *reinterpret_cast<uint4 *>(qb + o) = *reinterpret_cast<const uint4 *>(h8);
+                *reinterpret_cast<uint4 *>(qb + TC_PART_BYTES + o) = *reinterpret_cast<const uint4 *>(l8);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core reads
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(qfull + b);
         }
     }
     tc_fence_before();
@@ -836,10 +993,10 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
     const unsigned grid = (unsigned)((nq + TC_M - 1) / TC_M);
     const float key_unscale = (float)(1.0 / (scale * scale));
     k_knn_tiles_tc<KP, STAGES, QCAP><<<grid, TC_THREADS, smem, ctx->stream>>>(
-        E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, C, ctx->knn_dqc.p,
-        ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p, ctx->knn_tile_lo.p,
-        ctx->knn_tile_hi.p, key_unscale, cand_stride, ctx->cand_idx.p, ctx->cand_tau.p, ctx->flag.p + 3,
-        ctx->maxnrm.p + 3);
+        E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, C, ctx->knn_cen.p,
+        ctx->knn_dqc.p, ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p,
+        ctx->knn_tile_lo.p, ctx->knn_tile_hi.p, key_unscale, cand_stride, ctx->cand_idx.p, ctx->cand_tau.p,
+        ctx->cand_err.p, ctx->flag.p + 3, ctx->maxnrm.p + 3);
     CB_LAUNCH(ctx);
     return 0;
 }
@@ -878,14 +1035,14 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     const int B = TC_BUCKETS / C;
     const int64_t n_tiles_cap = (n + TC_N - 1) / TC_N + C;  // every cluster is padded to whole tiles
     const int64_t npos = n_tiles_cap * TC_N;
-    // candidates kept per query (one list): enough beyond k for the margin proof of k_knn_rerank;
-    // the candidate records are padded to 128 entries (the re-rank sorts a power of two)
-    const int KP = k <= 24 ? 96 : 120;
-    const int CAND = 128;
+    // candidates kept per query (one list): enough beyond k for the margin proof of k_knn_rerank
+    const int KP = k <= 24 ? 32 : 64;
+    const int CAND = KP;
     CB_CUDA(ctx, ctx->knn_img.ensure((size_t)n_tiles_cap * TC_TILE_BYTES));
     CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
     CB_CUDA(ctx, ctx->cand_idx.ensure((size_t)nq * CAND));
     CB_CUDA(ctx, ctx->cand_tau.ensure((size_t)nq));
+    CB_CUDA(ctx, ctx->cand_err.ensure((size_t)nq));
     CB_CUDA(ctx, ctx->knn_perm.ensure((size_t)npos));
     CB_CUDA(ctx, ctx->knn_bkt.ensure((size_t)npos));
     CB_CUDA(ctx, ctx->knn_hist.ensure((size_t)TC_BUCKETS));
@@ -962,8 +1119,9 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     // image, norms, tile bounds (maxnrm[0] becomes max |r|^2)
     CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     k_knn_tc_prep<<<(unsigned)n_tiles_cap, 128, 0, ctx->stream>>>(E, lde, d, scale, ctx->knn_perm.p, ctx->knn_rho.p,
-                                                                  ctx->knn_img.p, ctx->nrm2.p, ctx->maxnrm.p,
-                                                                  ctx->knn_tile_lo.p, ctx->knn_tile_hi.p);
+                                                                  ctx->knn_cl.p, ctx->knn_cen.p, ctx->knn_img.p,
+                                                                  ctx->nrm2.p, ctx->maxnrm.p, ctx->knn_tile_lo.p,
+                                                                  ctx->knn_tile_hi.p);
     CB_LAUNCH(ctx);
     // the query list: the cells of [q_begin, q_end) in sorted order, with their sorted positions
     const unsigned gpos = (unsigned)((npos + 255) / 256);
@@ -978,15 +1136,16 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     cb_stage_begin(ctx, ST_KNN_TILE);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     CB_CHECK(ctx, npos < (1LL << TC_POS_BITS), "cb200_knn: at most 2^27 points on the tensor-core engine");
-    if (KP == 96)
-        CB_TRY((launch_tc<96, 2, 8>(ctx, E, lde, d, scale, nq, C, CAND)));
+    if (KP == 32)
+        CB_TRY((launch_tc<32, 3, 16>(ctx, E, lde, d, scale, nq, C, CAND)));
     else
-        CB_TRY((launch_tc<120, 2, 4>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<64, 2, 16>(ctx, E, lde, d, scale, nq, C, CAND)));
     cb_stage_end(ctx, ST_KNN_TILE);
     *kp_out = CAND;
     *ntau_out = 1;
     *qlist_out = ctx->knn_qlist.p;
-    // split (3.1 * 2^-22) + fp32 accumulation of <= 195 products (2^-23 each, truncation assumed)
-    *err_coef_out = ldexp(1.0, -15);
+    // the bound of every query is in ctx->cand_err (see the producer of k_knn_tiles_tc); a negative
+    // coefficient tells k_knn_rerank to use it with the canonical key 0.5 d^2
+    *err_coef_out = -1.0;
     return 0;
 }
