@@ -38,6 +38,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cuda_fp16.h>
+#include <cstdio>
+#include <vector>
 
 #include "cb200_common.cuh"
 #include "cb200_knn_tc.cuh"
@@ -58,11 +60,13 @@ constexpr int TC_TILE_BYTES = 2 * TC_PART_BYTES; // hi + lo
 // N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-// fp64 coordinate (already scaled) -> (hi, lo) fp16 pair
+// fp64 coordinate (already scaled and centred) -> (hi, lo) fp16 pair: hi + lo carries 22 bits of x.
+// One fp64 -> fp32 rounding (2^-24, far below the 2^-22 of the pair), then exact fp32 arithmetic.
 __device__ __forceinline__ void split_h(double x, __half &hi, __half &lo)
 {
-    hi = __double2half(x);
-    lo = __double2half(x - (double)__half2float(hi));
+    const float xf = (float)x;
+    hi = __float2half_rn(xf);
+    lo = __float2half_rn(xf - __half2float(hi));
 }
 
 }  // namespace
@@ -400,8 +404,10 @@ struct TcSmem {
     static constexpr size_t hi = hk + (size_t)TC_M * KP * 4;                // [KP][TC_M] sorted positions
     static constexpr size_t ring = hi + (size_t)TC_M * KP * 4;              // [SETS][QCAP][TC_M] uint2
     static constexpr size_t bars = ring + (size_t)TC_SCAN_SETS * QCAP * TC_M * 8;  // full/empty[STAGES], tfull/tempty[ACC]
-    static constexpr size_t thr_sh = bars + (size_t)(2 * STAGES + 2 * TC_ACC_STAGES + 8) * 8;  // [TC_M] float
-    static constexpr size_t qhead = thr_sh + TC_M * 4;                      // [SETS][TC_M]
+    static constexpr size_t thr_sh = bars + (size_t)(2 * STAGES + 2 * TC_ACC_STAGES + 10) * 8;  // [TC_M] float
+    static constexpr size_t pf_reach = thr_sh + TC_M * 4;                   // [TC_M] reach of every row (prefilter input)
+    static constexpr size_t pf_words = pf_reach + TC_M * 4;                 // [TC_MAXC / 32] clusters still in reach
+    static constexpr size_t qhead = pf_words + (TC_MAXC / 32) * 4;          // [SETS][TC_M]
     static constexpr size_t misc = qhead + TC_SCAN_SETS * TC_M * 4;         // tmem slot, scan_done
     static constexpr size_t seq_tile = misc + 16;                           // [TC_RING] tile, [TC_RING] meta
     static constexpr size_t bytes = seq_tile + 2 * TC_RING * 4;
@@ -416,9 +422,22 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                const int32_t *__restrict__ cl_tile_begin, const unsigned int *__restrict__ cl_rhomax,
                const float *__restrict__ tile_lo, const float *__restrict__ tile_hi, float key_unscale, int cand_stride,
                int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau, float *__restrict__ cand_err,
-               int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done)
+               int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done, long long *__restrict__ dbg)
 {
     using L = TcSmem<KP, STAGES, QCAP>;
+    // CB200_KNN_TIMELINE (debugging aid): the CTA in the middle of the grid records (tag, clock) pairs
+    // per role into dbg[role][TL_CAP][2]
+    constexpr int TL_CAP = 4096;
+    const bool tl_on = dbg != nullptr && blockIdx.x == gridDim.x / 2;
+    int tl_n = 0;
+    auto TL = [&](int role, long long tag) {
+        if (tl_on && tl_n < TL_CAP) {
+            long long *e = dbg + ((size_t)role * TL_CAP + tl_n) * 2;
+            e[0] = tag;
+            e[1] = clock64();
+            ++tl_n;
+        }
+    };
     constexpr uint32_t TC_TMEM_COLS = TC_ACC_STAGES * TC_N;  // 512
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *q_img = smem + L::q_img;                                // 2 x 32 KB: Q hi | Q lo, per cluster visit
@@ -435,12 +454,16 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     uint64_t *qfull = qreq + 2;                  // [2] builders -> MMA issuer (and producer): image b is ready
     uint64_t *qfree = qfull + 2;                 // [2] MMA issuer -> builders: image b is no longer read
     volatile int *q_cluster = reinterpret_cast<volatile int *>(qfree + 2);  // [2]
+    uint64_t *pfreq = qfree + 3;                 // producer -> builders: run the cluster prefilter
+    uint64_t *pfdone = qfree + 4;                // builders -> producer
+    volatile float *pf_reach = reinterpret_cast<volatile float *>(smem + L::pf_reach);
+    volatile unsigned int *pf_words = reinterpret_cast<volatile unsigned int *>(smem + L::pf_words);
     volatile float *thr_sh = reinterpret_cast<volatile float *>(smem + L::thr_sh);
     volatile unsigned int *qhead = reinterpret_cast<volatile unsigned int *>(smem + L::qhead);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::misc);
     unsigned int *scan_done = reinterpret_cast<unsigned int *>(smem + L::misc + 4);
     volatile int *seq_tile = reinterpret_cast<volatile int *>(smem + L::seq_tile);
-    volatile int *seq_meta = seq_tile + TC_RING;  // cluster | image buffer << 16 | first tile of a visit << 17
+    volatile int *seq_meta = seq_tile + TC_RING;  // cluster | first tile of a visit << 10 | visit << 11
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ql0 = (int64_t)blockIdx.x * TC_M;   // first entry of the (sorted) query list
@@ -468,6 +491,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             mbar_init(qfull + b, 4);   // one arrival per builder warp
             mbar_init(qfree + b, 1);
         }
+        mbar_init(pfreq, 1);
+        mbar_init(pfdone, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0)
@@ -476,6 +501,56 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // need[j] (bit j of the result words) = some row can still reach cluster j.  Lane = 4 rows (g4, reach4);
+    // every lane streams its rows of the distance table (128-bit loads, 4 clusters each), the minimum
+    // over the warp's rows is one redux per cluster on order-preserving integer keys.  Words [w_lo, w_hi).
+    auto prefilter_words = [&](const int (&g4)[4], const float (&reach4)[4], int w_lo, int w_hi) {
+        constexpr float EPS = 3e-7f;
+        const bool vec = (C & 3) == 0;
+        for (int w = w_lo; w < w_hi; ++w) {
+            const int j0 = w * 32;
+            unsigned wbits = 0u;
+#pragma unroll 2
+            for (int jj = 0; jj < 32; jj += 4) {
+                if (j0 + jj >= C)
+                    break;
+                float lb4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (g4[u] < 0)
+                        continue;
+                    const float *drow = dqc + (size_t)g4[u] * C + j0 + jj;
+                    float v[4];
+                    if (vec) {
+                        const float4 q4 = *reinterpret_cast<const float4 *>(drow);
+                        v[0] = q4.x; v[1] = q4.y; v[2] = q4.z; v[3] = q4.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            v[e] = j0 + jj + e < C ? drow[e] : INFINITY;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        lb4[e] = fminf(lb4[e], v[e] * (1.f - EPS) - reach4[u]);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // signed-int order of the float bits is monotone for the values that occur
+                    // (-inf .. +inf, no NaN: reach = inf gives -inf, inf - inf cannot happen)
+                    const int key = __float_as_int(lb4[e]) >= 0 ? __float_as_int(lb4[e])
+                                                                 : (int)(0x80000000u - (unsigned)__float_as_int(lb4[e]));
+                    const int mn = __reduce_min_sync(0xffffffffu, key);
+                    const float lbmin = __int_as_float(mn >= 0 ? mn : (int)(0x80000000u - (unsigned)mn));
+                    const int j = j0 + jj + e;
+                    if (j < C && lbmin <= __uint_as_float(cl_rhomax[j]) * (1.f + EPS))
+                        wbits |= 1u << (jj + e);
+                }
+            }
+            if (lane == 0)
+                pf_words[w] = wbits;
+        }
+    };
 
     if (warp == 0) {
         // ===== producer: visits the clusters by ascending centre distance from the query tile's own
@@ -504,17 +579,21 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         const int64_t nvalid = nq - ql0 < TC_M ? nq - ql0 : TC_M;
         const int home = cl[qlist[ql0 + nvalid / 2]];
         const uint16_t *order = cl_order + (size_t)home * C;
-        unsigned words[NW];
+        unsigned words[NW];            // bit j: cluster j may still hold candidates (all set until the prefilter)
 #pragma unroll
         for (int w = 0; w < NW; ++w)
-            words[w] = 0u;
-        words[0] = 1u;                 // the home cluster first
+            words[w] = 0xffffffffu;
         bool prefiltered = false;
-        int wpos = 0;
-        int64_t seq = 0;
+        int opos = 0;                  // next position of `order` to look at
+        unsigned ochunk = 0u;          // order[32 * (opos / 32) + lane]
+        uint32_t seq = 0;
         int t = 0, te = 0, tb32 = 0, cur_j = -1;
-        int visit = -1;               // cluster visits that staged at least one tile so far, minus one
-        bool visit_open = false;      // the current cluster already has its query image requested
+        int req_visit = -1;           // cluster visits requested from the builders so far, minus one
+        int cur_visit = -1;           // visit of the cluster being walked (-1: none)
+        bool cur_issued = false;      // the current visit has staged a tile
+        bool plan_valid = false, no_more = false;
+        int plan_j = -1, plan_t = 0, plan_te = 0;
+        float plan_crmax = 0.f, plan_dq[4] = {0.f, 0.f, 0.f, 0.f};
         float blo = 0.f, bhi = 0.f;   // bounds of tile tb32 + lane
         float crmax = 0.f;
 
@@ -531,82 +610,104 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             }
         };
         auto prefilter = [&]() {
-            // lane = 32 positions of `order` (p = w*32 + lane); rows one after the other
-            if (C > 256) {   // more clusters than the register budget below: keep them all
-                for (int w = 0; w < NW; ++w) {
-                    const int left = C - w * 32;
-                    words[w] = left >= 32 ? 0xffffffffu : (left > 0 ? ((1u << left) - 1u) : 0u);
+            // the four builder warps share the pass over the distance table (they are idle right now)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                pf_reach[u * 32 + lane] = reach[u];
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                mbar_arrive(pfreq);
+                mbar_wait(pfdone, 0u, err_flag);
+            }
+            __syncwarp();
+            for (int w = 0; w < NW; ++w)
+                words[w] = w * 32 < C ? pf_words[w] : 0u;
+        };
+        // Looks for the next cluster (in `order`) some row can still reach, loads its per-row distances and
+        // asks the builders for the query image relative to its centre.  Runs AHEAD: it is called right
+        // after the first tile of the current cluster has been staged, so the loads and the image build
+        // hide behind the tiles in flight.  (A cluster planned with the thresholds of that moment may
+        // turn out to need no tile later: the visit is then skipped and its image buffer released here.)
+        auto make_plan = [&]() {
+            while (opos < C) {
+                if (opos == 1 && !prefiltered) {   // the home cluster is done: thresholds exist now
+                    prefiltered = true;
+                    refresh();
+                    prefilter();
                 }
-                words[0] &= ~1u;
+                if ((opos & 31) == 0)
+                    ochunk = opos + lane < C ? (unsigned)order[opos + lane] : 0u;
+                const int j = (int)__shfl_sync(0xffffffffu, ochunk, opos & 31);
+                ++opos;
+                if (((words[j >> 5] >> (j & 31)) & 1u) == 0u)
+                    continue;
+                const int pt = cl_tile_begin[j], pte = cl_tile_begin[j + 1];
+                if (pt >= pte)
+                    continue;
+                const float pcr = __uint_as_float(cl_rhomax[j]) * (1.f + EPS);
+                bool need = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    plan_dq[u] = g[u] >= 0 ? dqc[(size_t)g[u] * C + j] : 0.f;
+                    need |= g[u] >= 0 && plan_dq[u] * (1.f - EPS) - reach[u] <= pcr;
+                }
+                if (!__any_sync(0xffffffffu, need))
+                    continue;
+                ++req_visit;
+                if (lane == 0) {
+                    const int b = req_visit & 1, use = req_visit >> 1;
+                    if (use >= 1)   // the builders must have taken the previous request for this buffer
+                        mbar_wait(qfull + b, (uint32_t)((use - 1) & 1), err_flag);
+                    q_cluster[b] = j;
+                    __threadfence_block();
+                    mbar_arrive(qreq + b);
+                }
+                plan_valid = true;
+                plan_j = j;
+                plan_t = pt;
+                plan_te = pte;
+                plan_crmax = pcr;
                 return;
             }
-            int jm[8];
-            float lb[8];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const int p = w * 32 + lane;
-                jm[w] = p < C ? (int)order[p] : -1;
-                lb[w] = INFINITY;
-            }
-            for (int r = 0; r < TC_M; ++r) {
-                const int gr = __shfl_sync(0xffffffffu, g[r >> 5], r & 31);
-                const float rr = __shfl_sync(0xffffffffu, reach[r >> 5], r & 31);
-                if (gr < 0)
-                    continue;
-                const float *drow = dqc + (size_t)gr * C;
-#pragma unroll
-                for (int w = 0; w < 8; ++w)
-                    if (jm[w] >= 0)
-                        lb[w] = fminf(lb[w], drow[jm[w]] * (1.f - EPS) - rr);
-            }
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const bool need = jm[w] >= 0 && lb[w] <= __uint_as_float(cl_rhomax[jm[w]]) * (1.f + EPS);
-                words[w] = __ballot_sync(0xffffffffu, need);
-            }
-            words[0] &= ~1u;   // the home cluster is done
+            no_more = true;
         };
         // advances (t, te, cur_j, ...) to the next tile some row can reach; false when nothing is left
         auto find_next = [&]() -> bool {
             while (true) {
-                if (t >= te) {  // next candidate cluster
-                    while (wpos < NW && words[wpos] == 0u)
-                        ++wpos;
-                    if (wpos >= NW) {
-                        if (prefiltered)
-                            return false;
-                        prefiltered = true;
-                        refresh();
-                        prefilter();
-                        wpos = 0;
-                        continue;
+                if (t >= te) {  // the current cluster is exhausted: adopt the planned one
+                    if (cur_visit >= 0 && !cur_issued && lane == 0) {
+                        // skipped visit: nobody else releases its image buffer.  Only once the image is
+                        // built: an earlier arrival would complete the release the builders are still
+                        // waiting for from the previous user of the buffer.
+                        mbar_wait(qfull + (cur_visit & 1), (uint32_t)((cur_visit >> 1) & 1), err_flag);
+                        mbar_arrive(qfree + (cur_visit & 1));
                     }
-                    const int bit = __ffs(words[wpos]) - 1;
-                    words[wpos] &= words[wpos] - 1u;
-                    const int j = order[wpos * 32 + bit];
-                    t = cl_tile_begin[j];
-                    te = cl_tile_begin[j + 1];
-                    if (t >= te)
-                        continue;
-                    crmax = __uint_as_float(cl_rhomax[j]) * (1.f + EPS);
-                    bool need = false;
+                    cur_visit = -1;
+                    if (!plan_valid) {
+                        if (no_more)
+                            return false;
+                        make_plan();
+                        if (!plan_valid)
+                            return false;
+                    }
+                    cur_j = plan_j;
+                    t = plan_t;
+                    te = plan_te;
+                    crmax = plan_crmax;
+                    cur_visit = req_visit;
+                    cur_issued = false;
+                    plan_valid = false;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
+                        dq[u] = plan_dq[u];
                         if (g[u] >= 0) {
-                            dq[u] = dqc[(size_t)g[u] * C + j];
                             dlo[u] = dq[u] * (1.f - EPS);
                             dhi[u] = dq[u] * (1.f + EPS);
                             lo[u] = dlo[u] - reach[u];
                             hi[u] = dhi[u] + reach[u];
-                            need |= lo[u] <= crmax;
                         }
                     }
-                    if (!__any_sync(0xffffffffu, need)) {
-                        t = te;
-                        continue;
-                    }
-                    cur_j = j;
-                    visit_open = false;
                     tb32 = t - 32;  // forces a load of the tile bounds below
                 }
                 if (t >= tb32 + 32) {
@@ -615,8 +716,24 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     blo = tt < te ? tile_lo[tt] : INFINITY;
                     bhi = tt < te ? tile_hi[tt] : -INFINITY;
                 }
-                const float a = __shfl_sync(0xffffffffu, blo, t - tb32);
-                const float b = __shfl_sync(0xffffffffu, bhi, t - tb32);
+                // coarse test of the 32 tiles of the block at once (lane = tile) against the hull of the
+                // rows' intervals, then the exact per-row test of the first survivor
+                float mlo = fminf(fminf(lo[0], lo[1]), fminf(lo[2], lo[3]));
+                float mhi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mlo = fminf(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+                    mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+                }
+                const unsigned cm = __ballot_sync(0xffffffffu, tb32 + lane >= t && mlo <= bhi && mhi >= blo);
+                if (cm == 0u) {
+                    t = tb32 + 32 < te ? tb32 + 32 : te;
+                    continue;
+                }
+                const int off = __ffs(cm) - 1;
+                t = tb32 + off;
+                const float a = __shfl_sync(0xffffffffu, blo, off);
+                const float b = __shfl_sync(0xffffffffu, bhi, off);
                 bool need = false;
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
@@ -627,21 +744,14 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             }
         };
 
+        TL(0, -1);
         bool have = find_next();
         while (have) {
-            const bool first = !visit_open;
+            if (lane == 0)
+                TL(0, ((long long)t << 8) | 1);   // found
+            const bool first = !cur_issued;
+            cur_issued = true;
             if (first) {
-                // first tile of this cluster: ask the builders for the query image relative to its centre
-                ++visit;
-                visit_open = true;
-                const int b = visit & 1, use = visit >> 1;
-                if (lane == 0) {
-                    if (use >= 1)   // the builders must have taken the previous request for this buffer
-                        mbar_wait(qfull + b, (uint32_t)((use - 1) & 1), err_flag);
-                    q_cluster[b] = cur_j;
-                    __threadfence_block();
-                    mbar_arrive(qreq + b);
-                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     smax[u] = fmaxf(smax[u], dq[u] * crmax + 0.5f * crmax * crmax);
@@ -652,14 +762,17 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             if (lane == 0) {
                 mbar_wait(empty + s, (uint32_t)((seq / STAGES) & 1) ^ 1u, err_flag);
                 seq_tile[seq % TC_RING] = t;
-                seq_meta[seq % TC_RING] = cur_j | ((visit & 1) << 16) | ((first ? 1 : 0) << 17);
+                seq_meta[seq % TC_RING] = cur_j | ((first ? 1 : 0) << 10) | (cur_visit << 11);
                 mbar_expect_tx(full + s, TC_TILE_BYTES);
                 bulk_g2s(r_img + (size_t)s * TC_TILE_BYTES, img + (int64_t)t * TC_TILE_BYTES, TC_TILE_BYTES, full + s);
+                TL(0, ((long long)t << 8) | 2 | (first ? 16 : 0));   // issued
             }
             __syncwarp();
             ++t;
             ++seq;
             refresh();
+            if (!plan_valid && !no_more && (opos != 1 || prefiltered))
+                make_plan();
             have = find_next();
         }
         // end of the sequence
@@ -670,7 +783,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             mbar_arrive(full + (int)(seq % STAGES));
             atomicAdd(tiles_done, (unsigned long long)seq);
             // stop the builders
-            const int v = visit + 1, b = v & 1, use = v >> 1;
+            const int v = req_visit + 1, b = v & 1, use = v >> 1;
             if (use >= 1)
                 mbar_wait(qfull + b, (uint32_t)((use - 1) & 1), err_flag);
             q_cluster[b] = -1;
@@ -691,20 +804,24 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         // ===== MMA issuer =====
         if (lane == 0) {
             int prev_b = -1;
-            uint32_t quse[2] = {0u, 0u};   // visits that used image buffer b so far
-            uint32_t qh = 0, ql = 0;
-            for (int64_t seq = 0;; ++seq) {
+            const uint64_t desc_hi = make_desc(0u);                      // everything but the start address
+            const uint32_t r_desc0 = smem_u32(r_img) >> 4;
+            uint32_t q_desc = 0u;
+            for (uint32_t seq = 0;; ++seq) {
                 const int s = (int)(seq % STAGES);
                 const uint32_t ph = (uint32_t)((seq / STAGES) & 1);
                 const int a = (int)(seq % TC_ACC_STAGES);
                 const uint32_t aph = (uint32_t)((seq / TC_ACC_STAGES) & 1);
+                TL(1, ((long long)seq << 8) | 1);
                 mbar_wait(tempty + a, aph ^ 1u, err_flag);
+                TL(1, ((long long)seq << 8) | 2);
                 mbar_wait(full + s, ph, err_flag);
+                TL(1, ((long long)seq << 8) | 3);
                 tc_fence_after();
                 if (seq_tile[seq % TC_RING] < 0) {
                     // wake every scanner set with the end marker at its next sequence slot
                     for (int j = 0; j < TC_SCAN_SETS; ++j) {
-                        const int64_t sq = seq + j;
+                        const uint32_t sq = seq + (uint32_t)j;
                         const int a2 = (int)(sq % TC_ACC_STAGES);
                         if (j > 0)
                             mbar_wait(tempty + a2, (uint32_t)((sq / TC_ACC_STAGES) & 1) ^ 1u, err_flag);
@@ -715,33 +832,36 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     break;
                 }
                 const int meta = seq_meta[seq % TC_RING];
-                if (meta & (1 << 17)) {   // first tile of a cluster visit: switch to its query image
-                    const int b = (meta >> 16) & 1;
+                if (meta & (1 << 10)) {   // first tile of a cluster visit: switch to its query image
+                    const int v = meta >> 11, b = v & 1;
                     if (prev_b >= 0)
                         umma_commit(qfree + prev_b);   // every MMA reading the previous image has been issued
-                    mbar_wait(qfull + b, quse[b] & 1u, err_flag);
+                    mbar_wait(qfull + b, (uint32_t)((v >> 1) & 1), err_flag);
+                    TL(1, ((long long)seq << 8) | 4);
                     tc_fence_after();
-                    quse[b] += 1;
                     prev_b = b;
-                    qh = smem_u32(q_img + (size_t)b * TC_TILE_BYTES);
-                    ql = qh + TC_PART_BYTES;
+                    q_desc = smem_u32(q_img + (size_t)b * TC_TILE_BYTES) >> 4;
                 }
-                const uint32_t rh = smem_u32(r_img + (size_t)s * TC_TILE_BYTES), rl = rh + TC_PART_BYTES;
+                // descriptors: only the 14-bit start-address field (bytes >> 4) changes between operands
+                const uint32_t rb = r_desc0 + (uint32_t)s * (TC_TILE_BYTES >> 4);
                 const uint32_t dcol = tmem_base + (uint32_t)(a * TC_N);
-                uint32_t acc = 0;
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
-                    const uint32_t qa = (p == 2) ? ql : qh;
-                    const uint32_t rb = (p == 1) ? rl : rh;
+                    const uint32_t qd = q_desc + ((p == 2) ? (TC_PART_BYTES >> 4) : 0u);
+                    const uint32_t rd = rb + ((p == 1) ? (TC_PART_BYTES >> 4) : 0u);
 #pragma unroll
                     for (int kk = 0; kk < TC_K / TC_UMMA_K; ++kk) {
-                        umma_f16(dcol, make_desc(qa + kk * TC_UMMA_K * 2), make_desc(rb + kk * TC_UMMA_K * 2),
-                                 TC_IDESC, acc);
-                        acc = 1;
+                        const uint64_t da = desc_hi | (uint64_t)(qd + kk * (TC_UMMA_K * 2 >> 4));
+                        const uint64_t db = desc_hi | (uint64_t)(rd + kk * (TC_UMMA_K * 2 >> 4));
+                        if (p == 0 && kk == 0)
+                            umma_f16_first(dcol, da, db, TC_IDESC);
+                        else
+                            umma_f16_acc(dcol, da, db, TC_IDESC);
                     }
                 }
                 umma_commit(empty + s);   // smem stage may be refilled once these MMAs have read it
                 umma_commit(tfull + a);   // accumulator complete
+                TL(1, ((long long)seq << 8) | 5);
             }
         }
     } else if (warp < 2 + TC_SCAN_SETS * 4) {
@@ -751,7 +871,6 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         const int row = quarter * 32 + lane;
         const int64_t myql = ql0 + row;
         const bool active = myql < nq;
-        const int my_pos = active ? qpos[myql] : -1;   // sorted position of the query itself (self-exclusion)
         const float *mydq = active ? dqc + (size_t)qlist[myql] * C : nullptr;
         const uint32_t ring_addr = smem_u32(ring + (size_t)set * QCAP * TC_M + row);  // slot s at + s*TC_M*8
         volatile unsigned int *myhead = qhead + set * TC_M + row;
@@ -759,14 +878,18 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         int cur_j = -1;
         float off = 0.f;   // key offset of the current cluster: 0.5 |q - c_j|^2 (canonical T = T_j - off)
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int64_t seq = set;; seq += TC_SCAN_SETS) {
+        for (uint32_t seq = (uint32_t)set;; seq += TC_SCAN_SETS) {
             const int a = (int)(seq % TC_ACC_STAGES);
+            if (lane == 0 && quarter == 2)
+                TL(2 + set, ((long long)seq << 8) | 1);
             mbar_wait(tfull + a, (uint32_t)((seq / TC_ACC_STAGES) & 1), err_flag);
+            if (lane == 0 && quarter == 2)
+                TL(2 + set, ((long long)seq << 8) | 2);
             tc_fence_after();
             const int t = seq_tile[seq % TC_RING];
             if (t < 0)
                 break;
-            const int j = seq_meta[seq % TC_RING] & 0xffff;
+            const int j = seq_meta[seq % TC_RING] & 1023;
             if (j != cur_j) {
                 cur_j = j;
                 const float dq = active ? mydq[j] : 0.f;
@@ -797,7 +920,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int gcol = r0 + ch * 32 + i;
-                        if (__uint_as_float(r[i]) > thr && gcol != my_pos) {
+                        if (__uint_as_float(r[i]) > thr) {
                             for (uint32_t spin = 0; (int)(tail - *myhead) >= QCAP; ++spin) {
                                 if (spin > (1u << 24)) {
                                     atomicOr(err_flag, 4);
@@ -820,6 +943,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(tempty + a);
+            if (lane == 0 && quarter == 2)
+                TL(2 + set, ((long long)seq << 8) | 3);
         }
         __syncwarp();
         if (lane == 0) {
@@ -840,6 +965,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         }
         int cnt = 0;            // entries held; the heap is filled from the back, then heapified once
         float root = -FLT_MAX;
+        const int my_pos = ql0 + row < nq ? qpos[ql0 + row] : -1;   // sorted position of the query itself
         bool done_seen = false;
         while (true) {
             bool got = false;
@@ -857,6 +983,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 qhead[s2 * TC_M + row] = head[s2];
                 const float val = __uint_as_float(ex);
                 const int pos = (int)(ey & ((1u << TC_POS_BITS) - 1u));
+                if (pos == my_pos)
+                    continue;   // the query itself
                 if (cnt < KP) {
                     const int e = KP - 1 - cnt;
                     mk[e * TC_M] = val;
@@ -927,50 +1055,95 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             cand_tau[myql] = (cnt < KP) ? FLT_MAX : -root * key_unscale;
         }
     } else {
-        // ===== builders: thread = query row; the query operand image relative to the centre of the
-        // cluster being visited, into the image buffer the producer names =====
-        const int row = tid - (64 + TC_SCAN_SETS * 128 + 128);
-        const int64_t myql = ql0 + row;
-        const double *qrow = myql < nq ? E + (int64_t)qlist[myql] * lde : nullptr;
+        // ===== builders: the query operand image relative to the centre of the cluster being visited,
+        // into the image buffer the producer names.  Warp w owns rows 32w .. 32w+31; a row is loaded by
+        // the whole warp (lane = coordinate: coalesced), several rows in flight =====
+        const int bw = warp - (2 + TC_SCAN_SETS * 4 + 4);
+        const int64_t rowq = ql0 + bw * 32 + lane;
+        const int my_g = rowq < nq ? qlist[rowq] : -1;   // lane r: original index of row 32 bw + r
+        bool pf_served = false;
         for (int visit = 0;; ++visit) {
             const int b = visit & 1, use = visit >> 1;
+            // wait for the next image request; meanwhile serve the (single) prefilter request
+            // (polling only until the prefilter is served; afterwards the hardware-suspended wait below)
+            for (uint32_t spin = 0; !pf_served && !mbar_test(qreq + b, (uint32_t)(use & 1)); ++spin) {
+                if (mbar_test(pfreq, 0u)) {
+                    pf_served = true;
+                    int g4[4];
+                    float reach4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int64_t ql = ql0 + u * 32 + lane;
+                        g4[u] = ql < nq ? qlist[ql] : -1;
+                        reach4[u] = pf_reach[u * 32 + lane];
+                    }
+                    const int nw = (C + 31) / 32, per = (nw + 3) / 4;
+                    const int w_lo = bw * per < nw ? bw * per : nw, w_hi = w_lo + per < nw ? w_lo + per : nw;
+                    prefilter_words(g4, reach4, w_lo, w_hi);
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        mbar_arrive(pfdone);
+                    }
+                    spin = 0;
+                }
+                if (spin > (1u << 24)) {
+                    atomicOr(err_flag, 4);
+                    __threadfence();
+                    asm volatile("trap;");
+                }
+                __nanosleep(200);
+            }
             mbar_wait(qreq + b, (uint32_t)(use & 1), err_flag);
             const int j = q_cluster[b];
             if (j < 0)
                 break;
+            if (bw == 0 && lane == 0)
+                TL(4, ((long long)visit << 8) | 1);
             if (use >= 1)
                 mbar_wait(qfree + b, (uint32_t)((use - 1) & 1), err_flag);
+            if (bw == 0 && lane == 0)
+                TL(4, ((long long)visit << 8) | 2);
             const double *cj = cen + (size_t)j * d;
+            const double c0 = lane < d ? cj[lane] : 0.0, c1 = lane + 32 < d ? cj[lane + 32] : 0.0;
             unsigned char *qb = q_img + (size_t)b * TC_TILE_BYTES;
+            // constants of the columns past the coordinates: [2^12, 1, 2^-12] (hi part), 0 elsewhere
+            float k0 = 0.f, k1 = 0.f;
+            if (lane == d) k0 = 4096.f; else if (lane == d + 1) k0 = 1.f; else if (lane == d + 2) k0 = 1.0f / 4096.f;
+            if (lane + 32 == d) k1 = 4096.f; else if (lane + 32 == d + 1) k1 = 1.f; else if (lane + 32 == d + 2) k1 = 1.0f / 4096.f;
 #pragma unroll 1
-            for (int c8 = 0; c8 < TC_K / 8; ++c8) {   // one 16-byte chunk (8 fp16) of the row per pass
-                __align__(16) __half h8[8], l8[8];
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                double x0[8], x1[8];
+                int gr[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int t = c8 * 8 + e;
-                    __half h = __float2half(0.f), l = __float2half(0.f);
-                    if (qrow != nullptr) {
-                        if (t < d) {
-                            split_h(qrow[t] * scale - cj[t], h, l);
-                        } else if (t == d) {
-                            h = __float2half(4096.f);
-                        } else if (t == d + 1) {
-                            h = __float2half(1.f);
-                        } else if (t == d + 2) {
-                            h = __float2half(1.0f / 4096.f);
-                        }
-                    }
-                    h8[e] = h;
-                    l8[e] = l;
+                for (int u = 0; u < 8; ++u) {
+                    gr[u] = __shfl_sync(0xffffffffu, my_g, r0 + u);
+                    const double *qrow = E + (int64_t)(gr[u] < 0 ? 0 : gr[u]) * lde;
+                    x0[u] = (gr[u] >= 0 && lane < d) ? qrow[lane] : 0.0;
+                    x1[u] = (gr[u] >= 0 && lane + 32 < d) ? qrow[lane + 32] : 0.0;
                 }
-                const uint32_t o = swz_offset(row, c8 * 16);
-                *reinterpret_cast<uint4 *>(qb + o) = *reinterpret_cast<const uint4 *>(h8);
-                *reinterpret_cast<uint4 *>(qb + TC_PART_BYTES + o) = *reinterpret_cast<const uint4 *>(l8);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int row = bw * 32 + r0 + u;
+                    __half h0 = __float2half(gr[u] >= 0 ? k0 : 0.f), l0 = __float2half(0.f);
+                    __half h1 = __float2half(gr[u] >= 0 ? k1 : 0.f), l1 = __float2half(0.f);
+                    if (gr[u] >= 0 && lane < d)
+                        split_h(x0[u] * scale - c0, h0, l0);
+                    if (gr[u] >= 0 && lane + 32 < d)
+                        split_h(x1[u] * scale - c1, h1, l1);
+                    const uint32_t o0 = swz_offset(row, lane * 2), o1 = swz_offset(row, (lane + 32) * 2);
+                    *reinterpret_cast<__half *>(qb + o0) = h0;
+                    *reinterpret_cast<__half *>(qb + TC_PART_BYTES + o0) = l0;
+                    *reinterpret_cast<__half *>(qb + o1) = h1;
+                    *reinterpret_cast<__half *>(qb + TC_PART_BYTES + o1) = l1;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core reads
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(qfull + b);
+            if (bw == 0 && lane == 0)
+                TL(4, ((long long)visit << 8) | 3);
         }
     }
     tc_fence_before();
@@ -992,12 +1165,28 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
                                       (int)smem));
     const unsigned grid = (unsigned)((nq + TC_M - 1) / TC_M);
     const float key_unscale = (float)(1.0 / (scale * scale));
+    long long *dbg = nullptr;
+    if (getenv("CB200_KNN_TIMELINE") != nullptr) {
+        CB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&dbg), (size_t)5 * 4096 * 2 * sizeof(long long)));
+        CB_CUDA(ctx, cudaMemsetAsync(dbg, 0, (size_t)5 * 4096 * 2 * sizeof(long long), ctx->stream));
+    }
     k_knn_tiles_tc<KP, STAGES, QCAP><<<grid, TC_THREADS, smem, ctx->stream>>>(
         E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, C, ctx->knn_cen.p,
         ctx->knn_dqc.p, ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p,
         ctx->knn_tile_lo.p, ctx->knn_tile_hi.p, key_unscale, cand_stride, ctx->cand_idx.p, ctx->cand_tau.p,
-        ctx->cand_err.p, ctx->flag.p + 3, ctx->maxnrm.p + 3);
+        ctx->cand_err.p, ctx->flag.p + 3, ctx->maxnrm.p + 3, dbg);
     CB_LAUNCH(ctx);
+    if (dbg != nullptr) {   // dump the timeline of the middle CTA
+        std::vector<long long> h((size_t)5 * 4096 * 2);
+        CB_CUDA(ctx, cudaMemcpyAsync(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FILE *f = fopen(getenv("CB200_KNN_TIMELINE"), "wb");
+        if (f != nullptr) {
+            fwrite(h.data(), sizeof(long long), h.size(), f);
+            fclose(f);
+        }
+        cudaFree(dbg);
+    }
     return 0;
 }
 
