@@ -160,7 +160,9 @@ struct cb200_ctx {
     const int32_t *snn_nn = nullptr;  // the counted range (between cb200_snn_count_device and cb200_snn_emit)
     int64_t snn_n = 0, snn_jbegin = 0, snn_jend = 0;
     int snn_k = 0, snn_type = 0;
-    bool snn_counted = false;
+    bool snn_counted = false, snn_use_hash = true;
+    DevBuf<int32_t> snn_cut;          // [n*(k+1)] position of (cell, rank) inside the sorted list of its neighbour
+    DevBuf<unsigned char> snn_flag;   // [nj] cells left to the merge kernel (too many partners for the hash table)
 
     // scan scratch
     DevBuf<int64_t> scan_blk;

@@ -16,6 +16,10 @@
 //                                           of list i); every distinct h < j is one edge.
 // Edges of cell j are emitted in libscran's order (first encounter while scanning
 // i = 0..k, list i in ascending cell order), i.e. sorted by (first list that holds h, h).
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 #include "cb200_common.cuh"
 
 #define SNN_SLOTS 4  // at most 4 lists per lane: supports k + 1 <= 128
@@ -62,8 +66,10 @@ __global__ void k_rev_fill(const int32_t *__restrict__ nn, int64_t n, int k, con
 }
 
 // warp per list: rank sort (entries are unique, so rank = #smaller is a permutation)
+// cut[c * L + i] = position of the entry (c, i) inside its sorted list = number of cells < c in that list
 __global__ void __launch_bounds__(256) k_rev_sort(const int64_t *__restrict__ rptr, int64_t n,
-                                                  const uint32_t *__restrict__ hosts_u, uint32_t *__restrict__ hosts)
+                                                  const uint32_t *__restrict__ hosts_u, uint32_t *__restrict__ hosts,
+                                                  int L, int32_t *__restrict__ cut)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -79,8 +85,10 @@ __global__ void __launch_bounds__(256) k_rev_sort(const int64_t *__restrict__ rp
                 const uint32_t other = __shfl_sync(0xffffffffu, mine, o);
                 rank += other < mine ? 1 : 0;
             }
-            if (lane < len)
+            if (lane < len) {
                 hosts[b + rank] = mine;
+                cut[(int64_t)(mine >> 8) * L + (mine & 0xffu)] = rank;
+            }
         } else {
             for (int e = lane; e < len; e += 32) {
                 const uint32_t mine = hosts_u[b + e];
@@ -88,6 +96,7 @@ __global__ void __launch_bounds__(256) k_rev_sort(const int64_t *__restrict__ rp
                 for (int o = 0; o < len; ++o)
                     rank += hosts_u[b + o] < mine ? 1 : 0;
                 hosts[b + rank] = mine;
+                cut[(int64_t)(mine >> 8) * L + (mine & 0xffu)] = rank;
             }
         }
     }
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(256)
 k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
             const int64_t *__restrict__ rptr, const uint32_t *__restrict__ hosts, int32_t *__restrict__ ecnt,
             int32_t *__restrict__ bcnt, const int64_t *__restrict__ eptr, int32_t *__restrict__ efrom,
-            int32_t *__restrict__ eto, double *__restrict__ ew)
+            int32_t *__restrict__ eto, double *__restrict__ ew, const unsigned char *__restrict__ only_flagged)
 {
     constexpr int CH = SnnChunk<SLOTS>::value;
     __shared__ uint32_t stage[8][SNN_SMEM_WORDS];
@@ -120,6 +129,8 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t j = j_begin + warp0; j < j_end; j += nwarps) {
         const int64_t jl = j - j_begin;
+        if (only_flagged != nullptr && only_flagged[jl] == 0)
+            continue;   // handled by k_snn_hash
         int64_t gptr[SLOTS], gend[SLOTS];   // next entry not yet staged / end of the list
         int hpos[SLOTS], hcnt[SLOTS];       // position in / size of the staged chunk
         uint32_t head[SLOTS];
@@ -258,24 +269,215 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// K7b, main path: warp per cell j with a hash table in shared memory.
+//
+// The lists hosts[L_j[0]], hosts[L_j[1]], ... are taken ONE AFTER THE OTHER (that is libscran's scan
+// order), the entries of a list 32 at a time, one per lane.  A cell h appears at most once per list,
+// so the lanes of one step touch different keys: no atomics on the values, one CAS to claim a slot.
+// A key met for the first time in list i gets the next output position (ballot + popcount keep the
+// ascending-h order inside the list), so positions come out directly in emission order -- sorted by
+// (first list that holds h, h) -- with no sort and no per-list counts; later lists only lower the
+// rank sum and raise the shared-neighbour count.  MODE 0 counts (ecnt[j]); MODE 1 repeats the scan
+// and writes the edges of j at eptr[j] + position, 32 consecutive edges per store instruction.
+// One warp-iteration handles up to 32 list entries; the merge kernel above spends one per edge.
+// A cell with more than SNN_HASH_CAP distinct partners is flagged and left to k_snn_merge.
+// ---------------------------------------------------------------------------------------
+#define SNN_HASH_SLOTS 2048
+#define SNN_HASH_CAP 1408          // dense entries per warp (load factor <= 0.69)
+#define SNN_HASH_STAGE 2048        // list entries staged per group of lists
+#define SNN_HASH_WARPS 7
+#define SNN_HASH_EMPTY 0xffffffffu
+struct SnnHashWarp {
+    uint32_t key[SNN_HASH_SLOTS];    // cell h or EMPTY
+    uint16_t idx[SNN_HASH_SLOTS];    // -> dense entry
+    uint32_t dh[SNN_HASH_CAP];       // dense, in emission order: h
+    uint32_t drc[SNN_HASH_CAP];      // dense: min rank sum | shared count << 16
+    uint32_t stage[SNN_HASH_STAGE];  // the entries (cell < j) of a group of lists, list after list
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(32 * SNN_HASH_WARPS)
+k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
+           const int64_t *__restrict__ rptr, const uint32_t *__restrict__ hosts, const int32_t *__restrict__ cut,
+           int32_t *__restrict__ ecnt, unsigned char *__restrict__ flagged, const int64_t *__restrict__ eptr,
+           int32_t *__restrict__ efrom, int32_t *__restrict__ eto, double *__restrict__ ew)
+{
+    extern __shared__ __align__(16) unsigned char snn_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    SnnHashWarp &T = reinterpret_cast<SnnHashWarp *>(snn_smem)[w];
+    const int L = k + 1;
+    const int64_t warp0 = (int64_t)blockIdx.x * SNN_HASH_WARPS + w;
+    const int64_t nwarps = (int64_t)gridDim.x * SNN_HASH_WARPS;
+    for (int64_t j = j_begin + warp0; j < j_end; j += nwarps) {
+        const int64_t jl = j - j_begin;
+        if (MODE == 1 && flagged[jl] != 0)
+            continue;
+        // clear the keys
+        for (int e = lane * 4; e < SNN_HASH_SLOTS; e += 128)
+            *reinterpret_cast<uint4 *>(&T.key[e]) = make_uint4(SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY);
+        int base = 0;        // distinct partners so far = next output position
+        bool overflow = false;
+        for (int i0 = 0; i0 < L && !overflow; i0 += 32) {
+            // lane holds list i0 + lane: start in hosts and number of entries with cell < j (the entry of
+            // j itself sits at position cut[j][i] of the list of its i-th neighbour)
+            const int il = i0 + lane;
+            int64_t lb = 0;
+            int len = 0;
+            if (il < L) {
+                const int sidx = il == 0 ? (int)j : nn[j * k + (il - 1)];
+                lb = rptr[sidx];
+                len = cut[j * L + il];
+            }
+            const int nl = L - i0 < 32 ? L - i0 : 32;
+            int li0 = 0;
+            while (li0 < nl && !overflow) {
+                // group of lists [li0, li1) whose entries fit the staging buffer (inclusive scan of len)
+                int inc = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t2 = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o)
+                        inc += t2;
+                }
+                const int before = li0 > 0 ? __shfl_sync(0xffffffffu, inc, li0 - 1) : 0;
+                const unsigned fit = __ballot_sync(0xffffffffu, lane >= li0 && lane < nl && inc - before <= SNN_HASH_STAGE);
+                // lists fit as a prefix of [li0, nl): the first lane that does not fit ends the group
+                const unsigned range = (nl == 32 ? 0xffffffffu : ((1u << nl) - 1u)) & ~((1u << li0) - 1u);
+                const unsigned nofit = range & ~fit;
+                const int li1 = nofit ? __ffs(nofit) - 1 : nl;
+                if (li1 == li0) {   // a single list longer than the buffer: hub cell, left to the merge kernel
+                    overflow = true;
+                    break;
+                }
+                // stage: asynchronous 4-byte copies, all in flight together
+                __syncwarp();
+                for (int li = li0; li < li1; ++li) {
+                    const int64_t b = __shfl_sync(0xffffffffu, lb, li);
+                    const int ln = __shfl_sync(0xffffffffu, len, li);
+                    const int off = __shfl_sync(0xffffffffu, inc - len, li) - before;   // exclusive prefix
+                    for (int e = lane; e < ln; e += 32) {
+                        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&T.stage[off + e]);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(hosts + b + e) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                // insert list after list (libscran's scan order), 32 entries per step
+                for (int li = li0; li < li1 && !overflow; ++li) {
+                    const int i = i0 + li;
+                    const int ln = __shfl_sync(0xffffffffu, len, li);
+                    const int off = __shfl_sync(0xffffffffu, inc - len, li) - before;
+                    for (int e0 = 0; e0 < ln; e0 += 32) {
+                        const int e = e0 + lane;
+                        const bool valid = e < ln;
+                        const uint32_t ent = valid ? T.stage[off + e] : 0u;
+                        const uint32_t h = ent >> 8;
+                        bool is_new = false;
+                        int slot = 0;
+                        if (valid) {
+                            slot = (int)((h * 2654435761u) >> 21);              // 11 bits
+                            while (true) {
+                                const uint32_t kc = T.key[slot];
+                                if (kc == h)
+                                    break;
+                                if (kc == SNN_HASH_EMPTY) {
+                                    const uint32_t old = atomicCAS(&T.key[slot], SNN_HASH_EMPTY, h);
+                                    if (old == SNN_HASH_EMPTY) {
+                                        is_new = true;
+                                        break;
+                                    }
+                                    if (old == h)
+                                        break;
+                                }
+                                slot = (slot + 1) & (SNN_HASH_SLOTS - 1);
+                            }
+                        }
+                        const unsigned nm = __ballot_sync(0xffffffffu, is_new);
+                        const int nnew = __popc(nm);
+                        if (base + nnew > SNN_HASH_CAP) {
+                            overflow = true;
+                            break;
+                        }
+                        const uint32_t rs = (uint32_t)i + (ent & 0xffu);
+                        if (is_new) {
+                            const int pos = base + __popc(nm & ((1u << lane) - 1u));
+                            T.idx[slot] = (uint16_t)pos;
+                            T.dh[pos] = h;
+                            T.drc[pos] = rs | (1u << 16);
+                        } else if (valid) {
+                            const int pos = T.idx[slot];
+                            const uint32_t rc = T.drc[pos];
+                            T.drc[pos] = min(rc & 0xffffu, rs) | ((rc & 0xffff0000u) + (1u << 16));
+                        }
+                        base += nnew;
+                        __syncwarp();
+                    }
+                }
+                li0 = li1;
+            }
+        }
+        if (MODE == 0) {
+            if (lane == 0) {
+                ecnt[jl] = overflow ? 0 : base;
+                flagged[jl] = overflow ? 1 : 0;
+            }
+        } else {
+            const int64_t ebase = eptr[jl];
+            for (int p = lane; p < base; p += 32) {
+                const uint32_t rc = T.drc[p];
+                const int rs = (int)(rc & 0xffffu), nmatch = (int)(rc >> 16);
+                double wgt;
+                if (type == CB200_SNN_RANK)
+                    wgt = (double)k - 0.5 * (double)rs;
+                else if (type == CB200_SNN_NUMBER)
+                    wgt = (double)nmatch;
+                else
+                    wgt = __ddiv_rn((double)nmatch, (double)(2 * L - nmatch));
+                if (wgt < 1e-6)
+                    wgt = 1e-6;
+                efrom[ebase + p] = (int32_t)(j + 1);
+                eto[ebase + p] = (int32_t)(T.dh[p] + 1);
+                ew[ebase + p] = wgt;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int MODE>
+static int launch_snn_hash(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin,
+                           int64_t j_end, int64_t loc)
+{
+    const size_t smem = sizeof(SnnHashWarp) * SNN_HASH_WARPS;
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_hash<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = cb_grid_for(j_end - j_begin, SNN_HASH_WARPS, ctx->num_sms * 8);
+    k_snn_hash<MODE><<<grid, 32 * SNN_HASH_WARPS, smem, ctx->stream>>>(
+        d_nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->ecnt.p + loc, ctx->snn_flag.p + loc,
+        ctx->eptr.p + loc, ctx->efrom.p, ctx->eto.p, ctx->ew8.p);
+    CB_LAUNCH(ctx);
+    return 0;
+}
+
 // [j_begin, j_end) is a sub-range of the range the per-cell arrays (ecnt, bcnt, eptr) were sized for;
 // loc = j_begin - (first cell of that range)
 template <int MODE>
 static void launch_snn_merge(cb200_ctx *ctx, int grid, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin,
-                             int64_t j_end, int64_t loc)
+                             int64_t j_end, int64_t loc, const unsigned char *flagged = nullptr)
 {
     const int32_t *nn = d_nn;
     int32_t *ecnt = ctx->ecnt.p + loc, *bcnt = ctx->bcnt.p + loc * (k + 1);
     int64_t *eptr = ctx->eptr.p + loc;
+    const unsigned char *flg = flagged != nullptr ? flagged + loc : nullptr;
     if (k + 1 <= 32)
         k_snn_merge<MODE, 1><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, flg);
     else if (k + 1 <= 64)
         k_snn_merge<MODE, 2><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, flg);
     else
         k_snn_merge<MODE, 4><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, flg);
 }
 
 // cell boundaries of SNN_CHUNKS pieces with about equal numbers of edges: out[2c] = first local cell of
@@ -325,6 +527,8 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
     CB_CUDA(ctx, ctx->ecnt.ensure((size_t)nj));
     CB_CUDA(ctx, ctx->eptr.ensure((size_t)nj + 1));
     CB_CUDA(ctx, ctx->bcnt.ensure((size_t)nj * L));
+    CB_CUDA(ctx, ctx->snn_flag.ensure((size_t)nj));
+    CB_CUDA(ctx, ctx->snn_cut.ensure((size_t)n * L));
     CB_CUDA(ctx, ctx->snn_bounds.ensure(2 * (SNN_CHUNKS + 1)));
 
     cb_stage_begin(ctx, ST_SNN_REVLIST);
@@ -337,14 +541,39 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
     k_rev_fill<<<g1, 256, 0, ctx->stream>>>(d_nn, n, k, ctx->rptr.p, ctx->rcur.p, ctx->hosts_u.p);
     CB_LAUNCH(ctx);
     const int g2 = cb_grid_for(n, 8, ctx->num_sms * 16);
-    k_rev_sort<<<g2, 256, 0, ctx->stream>>>(ctx->rptr.p, n, ctx->hosts_u.p, ctx->hosts.p);
+    k_rev_sort<<<g2, 256, 0, ctx->stream>>>(ctx->rptr.p, n, ctx->hosts_u.p, ctx->hosts.p, L, ctx->snn_cut.p);
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_SNN_REVLIST);
 
     cb_stage_begin(ctx, ST_SNN_EDGES);
+    // hash kernel for (nearly) every cell, merge kernel for the flagged ones (too many partners for the
+    // table); CB200_SNN_ENGINE=merge runs everything through the merge kernel (cross-check)
+    const char *seng = getenv("CB200_SNN_ENGINE");
+    ctx->snn_use_hash = !(seng != nullptr && strcmp(seng, "merge") == 0);
     const int g3 = cb_grid_for(nj, 8, ctx->num_sms * 16);
-    launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0);
+    if (ctx->snn_use_hash) {
+        CB_TRY(launch_snn_hash<0>(ctx, d_nn, n, k, type, j_begin, j_end, 0));
+        launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_flag.p);
+    } else {
+        launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0);
+    }
     CB_LAUNCH(ctx);
+    if (getenv("CB200_TRACE") != nullptr && ctx->snn_use_hash) {   // how many cells the hash table could not hold
+        std::vector<unsigned char> hf((size_t)nj);
+        std::vector<int32_t> hc((size_t)nj);
+        CB_CUDA(ctx, cudaMemcpyAsync(hf.data(), ctx->snn_flag.p, (size_t)nj, cudaMemcpyDeviceToHost, ctx->stream));
+        CB_CUDA(ctx, cudaMemcpyAsync(hc.data(), ctx->ecnt.p, (size_t)nj * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int64_t nf = 0, ef = 0, et = 0;
+        for (int64_t q = 0; q < nj; ++q) {
+            nf += hf[q];
+            et += hc[q];
+            if (hf[q])
+                ef += hc[q];
+        }
+        fprintf(stderr, "[cb200] snn: %lld of %lld cells flagged for the merge kernel, holding %lld of %lld edges\n",
+                (long long)nf, (long long)nj, (long long)ef, (long long)et);
+    }
     CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->ecnt.p, nj, ctx->eptr.p));
     k_snn_chunk_bounds<<<1, 32, 0, ctx->stream>>>(ctx->eptr.p, nj, ctx->snn_bounds.p);
     CB_LAUNCH(ctx);
@@ -380,8 +609,15 @@ static int snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight)
         if (jb <= ja)
             continue;
         const int g3 = cb_grid_for(jb - ja, 8, ctx->num_sms * 16);
-        launch_snn_merge<1>(ctx, g3, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
-                            ctx->snn_jbegin + jb, ja);
+        if (ctx->snn_use_hash) {
+            CB_TRY(launch_snn_hash<1>(ctx, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
+                                      ctx->snn_jbegin + jb, ja));
+            launch_snn_merge<1>(ctx, g3, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
+                                ctx->snn_jbegin + jb, ja, ctx->snn_flag.p);
+        } else {
+            launch_snn_merge<1>(ctx, g3, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
+                                ctx->snn_jbegin + jb, ja);
+        }
         CB_LAUNCH(ctx);
         if (out && eb > ea) {
             CB_TRY(cb200_copy_async(ctx, from + ea, ctx->efrom.p + ea, (size_t)(eb - ea) * sizeof(int32_t)));

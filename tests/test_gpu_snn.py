@@ -95,6 +95,18 @@ def test_snn_two_phase_into_caller_buffers(gpu_ctx, scheme):
     assert_same_edges(gpu_ctx.snn_emit(ne2), full)
 
 
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_snn_hash_and_merge_engines_agree(gpu_ctx, monkeypatch, scheme):
+    """The hash-table kernel (default) and the k-way merge kernel (fallback for cells with more partners
+    than the table holds; forced here with CB200_SNN_ENGINE=merge) must emit identical edge lists."""
+    knn = O.find_knn(synth.make_embedding(30000, 10, seed=3), 20)
+    a = gpu_ctx.snn(knn, scheme)
+    monkeypatch.setenv("CB200_SNN_ENGINE", "merge")
+    b = gpu_ctx.snn(knn, scheme)
+    assert_same_edges(a, b)
+    assert_same_edges(a, O.snn_edges(knn, scheme))
+
+
 def test_snn_argument_errors(gpu_ctx):
     knn = O.find_knn(synth.make_embedding(100, 5, seed=1), 5)
     bad = knn.copy()
