@@ -162,6 +162,9 @@ struct cb200_ctx {
     int snn_k = 0, snn_type = 0;
     bool snn_counted = false, snn_use_hash = true;
     DevBuf<int32_t> snn_cut;          // [n*(k+1)] position of (cell, rank) inside the sorted list of its neighbour
+    DevBuf<int32_t> snn_tcnt;         // [nj] upper bound of the partners of every cell
+    DevBuf<int64_t> snn_toff;         // [nj+1] its scan: slices of the partner store
+    DevBuf<uint32_t> snn_tmp_h, snn_tmp_rc;  // partner store written by the counting pass, read by the emission
     DevBuf<unsigned char> snn_flag;   // [nj] cells left to the merge kernel (too many partners for the hash table)
 
     // scan scratch

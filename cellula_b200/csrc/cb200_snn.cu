@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(32 * SNN_HASH_WARPS)
 k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
            const int64_t *__restrict__ rptr, const uint32_t *__restrict__ hosts, const int32_t *__restrict__ cut,
            int32_t *__restrict__ ecnt, unsigned char *__restrict__ flagged, const int64_t *__restrict__ eptr,
-           int32_t *__restrict__ efrom, int32_t *__restrict__ eto, double *__restrict__ ew)
+           int32_t *__restrict__ efrom, int32_t *__restrict__ eto, double *__restrict__ ew,
+           const int64_t *__restrict__ toff, uint32_t *__restrict__ tmp_h, uint32_t *__restrict__ tmp_rc)
 {
     extern __shared__ __align__(16) unsigned char snn_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -422,6 +423,15 @@ k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j
                 ecnt[jl] = overflow ? 0 : base;
                 flagged[jl] = overflow ? 1 : 0;
             }
+            if (!overflow && tmp_h != nullptr) {
+                // keep the partners for k_snn_compact: no second pass over the lists.  toff is the scan
+                // of an upper bound (all staged entries), so the slices never overlap.
+                const int64_t tb = toff[jl];
+                for (int p = lane; p < base; p += 32) {
+                    tmp_h[tb + p] = T.dh[p];
+                    tmp_rc[tb + p] = T.drc[p];
+                }
+            }
         } else {
             const int64_t ebase = eptr[jl];
             for (int p = lane; p < base; p += 32) {
@@ -445,6 +455,56 @@ k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j
     }
 }
 
+// upper bound of the partners of cell j: all list entries with a cell < j
+__global__ void k_snn_upper(const int32_t *__restrict__ cut, int64_t j_begin, int64_t nj, int L, int32_t *__restrict__ tcnt)
+{
+    const int64_t jl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (jl < nj) {
+        const int32_t *c = cut + (j_begin + jl) * L;
+        int t = 0;
+        for (int i = 0; i < L; ++i)
+            t += c[i];
+        tcnt[jl] = t;
+    }
+}
+
+// edges of the cells [j_begin, j_end) from the partner slices kept by k_snn_hash<0>: warp per cell,
+// 32 consecutive edges per store instruction
+__global__ void __launch_bounds__(256)
+k_snn_compact(int64_t j_begin, int64_t j_end, int k, int type, const int32_t *__restrict__ ecnt,
+              const unsigned char *__restrict__ flagged, const int64_t *__restrict__ eptr,
+              const int64_t *__restrict__ toff, const uint32_t *__restrict__ tmp_h, const uint32_t *__restrict__ tmp_rc,
+              int32_t *__restrict__ efrom, int32_t *__restrict__ eto, double *__restrict__ ew, int64_t loc0)
+{
+    const int lane = threadIdx.x & 31;
+    const int L = k + 1;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t j = j_begin + warp0; j < j_end; j += nwarps) {
+        const int64_t jl = j - loc0;
+        if (flagged[jl] != 0)
+            continue;
+        const int cnt = ecnt[jl];
+        const int64_t ebase = eptr[jl], tb = toff[jl];
+        for (int p = lane; p < cnt; p += 32) {
+            const uint32_t rc = tmp_rc[tb + p];
+            const int rs = (int)(rc & 0xffffu), nmatch = (int)(rc >> 16);
+            double wgt;
+            if (type == CB200_SNN_RANK)
+                wgt = (double)k - 0.5 * (double)rs;
+            else if (type == CB200_SNN_NUMBER)
+                wgt = (double)nmatch;
+            else
+                wgt = __ddiv_rn((double)nmatch, (double)(2 * L - nmatch));
+            if (wgt < 1e-6)
+                wgt = 1e-6;
+            efrom[ebase + p] = (int32_t)(j + 1);
+            eto[ebase + p] = (int32_t)(tmp_h[tb + p] + 1);
+            ew[ebase + p] = wgt;
+        }
+    }
+}
+
 template <int MODE>
 static int launch_snn_hash(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin,
                            int64_t j_end, int64_t loc)
@@ -454,7 +514,7 @@ static int launch_snn_hash(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k
     const int grid = cb_grid_for(j_end - j_begin, SNN_HASH_WARPS, ctx->num_sms * 8);
     k_snn_hash<MODE><<<grid, 32 * SNN_HASH_WARPS, smem, ctx->stream>>>(
         d_nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->ecnt.p + loc, ctx->snn_flag.p + loc,
-        ctx->eptr.p + loc, ctx->efrom.p, ctx->eto.p, ctx->ew8.p);
+        ctx->eptr.p + loc, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, ctx->snn_toff.p + loc, ctx->snn_tmp_h.p, ctx->snn_tmp_rc.p);
     CB_LAUNCH(ctx);
     return 0;
 }
@@ -552,6 +612,16 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
     ctx->snn_use_hash = !(seng != nullptr && strcmp(seng, "merge") == 0);
     const int g3 = cb_grid_for(nj, 8, ctx->num_sms * 16);
     if (ctx->snn_use_hash) {
+        // slices of the partner store: scan of the per-cell upper bounds
+        CB_CUDA(ctx, ctx->snn_tcnt.ensure((size_t)nj));
+        CB_CUDA(ctx, ctx->snn_toff.ensure((size_t)nj + 1));
+        k_snn_upper<<<(unsigned)((nj + 255) / 256), 256, 0, ctx->stream>>>(ctx->snn_cut.p, j_begin, nj, L, ctx->snn_tcnt.p);
+        CB_LAUNCH(ctx);
+        CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->snn_tcnt.p, nj, ctx->snn_toff.p));
+        int64_t ttot = 0;
+        CB_TRY(cb200_read_back(ctx, &ttot, ctx->snn_toff.p + nj, sizeof(int64_t)));
+        CB_CUDA(ctx, ctx->snn_tmp_h.ensure((size_t)ttot));
+        CB_CUDA(ctx, ctx->snn_tmp_rc.ensure((size_t)ttot));
         CB_TRY(launch_snn_hash<0>(ctx, d_nn, n, k, type, j_begin, j_end, 0));
         launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_flag.p);
     } else {
@@ -610,8 +680,11 @@ static int snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight)
             continue;
         const int g3 = cb_grid_for(jb - ja, 8, ctx->num_sms * 16);
         if (ctx->snn_use_hash) {
-            CB_TRY(launch_snn_hash<1>(ctx, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
-                                      ctx->snn_jbegin + jb, ja));
+            k_snn_compact<<<g3, 256, 0, ctx->stream>>>(ctx->snn_jbegin + ja, ctx->snn_jbegin + jb, ctx->snn_k, ctx->snn_type,
+                                                       ctx->ecnt.p, ctx->snn_flag.p, ctx->eptr.p, ctx->snn_toff.p,
+                                                       ctx->snn_tmp_h.p, ctx->snn_tmp_rc.p, ctx->efrom.p, ctx->eto.p,
+                                                       ctx->ew8.p, ctx->snn_jbegin);
+            CB_LAUNCH(ctx);
             launch_snn_merge<1>(ctx, g3, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
                                 ctx->snn_jbegin + jb, ja, ctx->snn_flag.p);
         } else {
