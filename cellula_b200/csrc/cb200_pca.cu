@@ -735,6 +735,69 @@ k_project(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, c
     }
 }
 
+// The same with the rotation blocked through shared memory: a CTA owns a contiguous range of cells and
+// walks the HVG slots slab by slab (a slab = as many 64-slot blocks as fit ~200 KB of V rows); the entries
+// of a cell that fall into the slab are found through the block pointers.  V is then read from shared
+// memory (400 B per entry at d = 50) instead of L2 -- k_project runs at the L2 bandwidth.  The partial
+// sums of a cell are added slab after slab by the same warp, so the result is deterministic.
+template <int NU>   // NU = ceil(d / 32) accumulators per lane
+__global__ void __launch_bounds__(1024)
+k_project_slab(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, const double *__restrict__ hval,
+               const uint16_t *__restrict__ bptr, int nb, int64_t n_cols, const double *__restrict__ rot,
+               const double *__restrict__ muv, int H, int d, int blocks_per_slab, double *__restrict__ scores)
+{
+    extern __shared__ __align__(16) double vs[];   // [slab slots][d]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t per = (n_cols + gridDim.x - 1) / gridDim.x;
+    const int64_t c0 = blockIdx.x * per, c1 = c0 + per < n_cols ? c0 + per : n_cols;
+    for (int blk0 = 0; blk0 < nb; blk0 += blocks_per_slab) {
+        const int blk1 = blk0 + blocks_per_slab < nb ? blk0 + blocks_per_slab : nb;
+        const int s0 = blk0 * GB_BS, s1 = blk1 * GB_BS < H ? blk1 * GB_BS : H;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (s1 - s0) * d; i += blockDim.x)
+            vs[i] = rot[(int64_t)s0 * d + i];
+        __syncthreads();
+        for (int64_t c = c0 + w; c < c1; c += (blockDim.x >> 5)) {
+            const int64_t b = hptr[c];
+            const int e0 = bptr[c * (nb + 1) + blk0], e1 = bptr[c * (nb + 1) + blk1];
+            double acc[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                acc[u] = 0.0;
+            for (int a0 = e0; a0 < e1; a0 += 32) {
+                const int a = a0 + lane;
+                int sl = 0;
+                double v = 0.0;
+                if (a < e1) {
+                    sl = hslot[b + a] - s0;
+                    v = hval[b + a];
+                }
+                const int cnt = e1 - a0 < 32 ? e1 - a0 : 32;
+#pragma unroll 4
+                for (int q = 0; q < cnt; ++q) {
+                    const int sq = __shfl_sync(0xffffffffu, sl, q);
+                    const double vq = __shfl_sync(0xffffffffu, v, q);
+                    const double *r = vs + sq * d;
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        const int j = u * 32 + lane;
+                        if (j < d)
+                            acc[u] = fma(vq, r[j], acc[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int j = u * 32 + lane;
+                if (j < d) {
+                    const double prev = blk0 == 0 ? -muv[j] : scores[c * d + j];
+                    scores[c * d + j] = prev + acc[u];
+                }
+            }
+        }
+    }
+}
+
 // row-major [rows x cols] -> column-major [rows x cols]
 __global__ void k_rowmajor_to_colmajor(const double *__restrict__ in, int64_t rows, int cols, double *__restrict__ out)
 {
@@ -1032,9 +1095,36 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
     cb_stage_end(ctx, ST_EIG);
 
     cb_stage_begin(ctx, ST_PROJECT);
-    const int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
-    k_project<<<grid, 256, 0, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p, ctx->N, ctx->rot.p, ctx->emuv.p,
-                                             d, ctx->scores.p);
+    {
+        // V slab in shared memory: as many 64-slot blocks as fit 200 KB (CB200_PROJECT_ENGINE=l2: V from L2)
+        const int nbp = (H + GB_BS - 1) / GB_BS;
+        int bps = (int)((200 * 1024) / ((size_t)GB_BS * d * sizeof(double)));
+        const char *peng = getenv("CB200_PROJECT_ENGINE");
+        if (bps >= 1 && !(peng != nullptr && strcmp(peng, "l2") == 0)) {
+            if (bps > nbp)
+                bps = nbp;
+            const size_t smem = (size_t)bps * GB_BS * d * sizeof(double);
+            const int pgrid = (int)(ctx->N < ctx->num_sms ? ctx->N : ctx->num_sms);
+#define CB_PROJECT_SLAB(NU)                                                                                          \
+    do {                                                                                                             \
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_project_slab<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_project_slab<NU><<<pgrid, 1024, smem, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p, ctx->hbptr.p, \
+                                                               nbp, ctx->N, ctx->rot.p, ctx->emuv.p, H, d, bps,      \
+                                                               ctx->scores.p);                                       \
+    } while (0)
+            if (d <= 32)
+                CB_PROJECT_SLAB(1);
+            else if (d <= 64)
+                CB_PROJECT_SLAB(2);
+            else
+                CB_PROJECT_SLAB(4);
+#undef CB_PROJECT_SLAB
+        } else {
+            const int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
+            k_project<<<grid, 256, 0, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p, ctx->N, ctx->rot.p,
+                                                     ctx->emuv.p, d, ctx->scores.p);
+        }
+    }
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_PROJECT);
     ctx->have_scores = true;
