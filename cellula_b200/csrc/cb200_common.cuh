@@ -103,7 +103,7 @@ struct cb200_ctx {
     DevBuf<double> gram;       // [H*H + H]: upper-triangular accumulation of X^T X, + col sums
     DevBuf<double> cov;        // [H*H]
     DevBuf<double> mu;         // [H]
-    DevBuf<double> eq, ew, ey, ex, es, et, etheta, eres, emuv;  // eigen-solver work
+    DevBuf<double> eq, ew, ey, ex, es, et, etheta, eres, emuv, egs;  // eigen-solver work (egs: split-K partials)
     DevBuf<double> rot;        // [H*d] row-major rotation (V)
     DevBuf<double> scores;     // [N*d] row-major
     DevBuf<double> varexp;     // [d]

@@ -368,6 +368,25 @@ __global__ void k_sum_partials(const double *__restrict__ part, int64_t n, int n
     }
 }
 
+// out[i] = alpha * sum_z part[z*n + i] + beta * P[i] + gamma * R[i]  (split-K epilogue, fixed order)
+__global__ void k_combine_partials(const double *__restrict__ part, int64_t n, int nz, double alpha,
+                                   const double *__restrict__ P, double beta, const double *__restrict__ R, double gamma,
+                                   double *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        double s = 0.0;
+        for (int z = 0; z < nz; ++z)
+            s += part[(int64_t)z * n + i];
+        double v = alpha * s;
+        if (P != nullptr)
+            v += beta * P[i];
+        if (R != nullptr)
+            v += gamma * R[i];
+        out[i] = v;
+    }
+}
+
 // deterministic start block: hash -> uniform(-1, 1)
 __global__ void k_init_block(double *__restrict__ Q, int64_t n, uint64_t seed)
 {
@@ -822,6 +841,20 @@ static int launch_gemm(cb200_ctx *ctx, int M, int N, int K, const double *A, int
     return 0;
 }
 
+// O(H x b) = alpha C Q + beta P + gamma R with the H x H covariance: split over K so that every SM has work
+// (the plain launch has (b/32) x (H/64) = 64 CTAs for H = 2000, b = 64), deterministic reduction
+static int launch_cq(cb200_ctx *ctx, int H, int b, const double *C, const double *Q, double alpha, const double *P,
+                     double beta, const double *R, double gamma, double *O)
+{
+    const int ksplit = 6;
+    CB_CUDA(ctx, ctx->egs.ensure((size_t)ksplit * H * b));
+    CB_TRY(launch_gemm(ctx, H, b, H, C, H, 1, Q, b, 1, 1.0, nullptr, 0.0, nullptr, 0.0, ctx->egs.p, b, ksplit));
+    k_combine_partials<<<(unsigned)(((int64_t)H * b + 255) / 256), 256, 0, ctx->stream>>>(ctx->egs.p, (int64_t)H * b, ksplit,
+                                                                                        alpha, P, beta, R, gamma, O);
+    CB_LAUNCH(ctx);
+    return 0;
+}
+
 // S(b x b) = A^T B for row-major H x b blocks, deterministic split-K
 static int launch_atb(cb200_ctx *ctx, const double *A, const double *B, int H, int b, double *S)
 {
@@ -1032,7 +1065,7 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
     bool converged = false;
     for (; it < max_outer; ++it) {
         // Rayleigh-Ritz: W = C Q, T = Q^T W, T = Y Theta Y^T, Q <- Q Y, W <- W Y
-        CB_TRY(launch_gemm(ctx, H, b, H, C, H, 1, Q, b, 1, 1.0, nullptr, 0.0, nullptr, 0.0, W, b));
+        CB_TRY(launch_cq(ctx, H, b, C, Q, 1.0, nullptr, 0.0, nullptr, 0.0, W));
         CB_TRY(launch_atb(ctx, Q, W, H, b, ctx->et.p));
         k_jacobi_eig<<<1, 1024, jac_smem, ctx->stream>>>(ctx->et.p, b, ctx->etheta.p, ctx->et.p + (size_t)b * b,
                                                          nullptr);
@@ -1062,11 +1095,11 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
         k_axpby<<<ew_grid, 256, 0, ctx->stream>>>(Y2, 1.0 / ee, Y1, -cc / ee, hb, W);
         CB_LAUNCH(ctx);
         // X2 = 2 (C X1 - c X1)/e - Q -> Q buffer
-        CB_TRY(launch_gemm(ctx, H, b, H, C, H, 1, W, b, 1, 2.0 / ee, W, -2.0 * cc / ee, Y1, -1.0, Q, b));
+        CB_TRY(launch_cq(ctx, H, b, C, W, 2.0 / ee, W, -2.0 * cc / ee, Y1, -1.0, Q));
         double *filtered = Q;
         if (degree >= 3) {
             // X3 = 2 (C X2 - c X2)/e - X1 -> Y2 buffer (C Q is no longer needed)
-            CB_TRY(launch_gemm(ctx, H, b, H, C, H, 1, Q, b, 1, 2.0 / ee, Q, -2.0 * cc / ee, W, -1.0, Y2, b));
+            CB_TRY(launch_cq(ctx, H, b, C, Q, 2.0 / ee, Q, -2.0 * cc / ee, W, -1.0, Y2));
             filtered = Y2;
         }
         k_colnorm_scale<<<b, 256, 0, ctx->stream>>>(filtered, H, b);
