@@ -903,37 +903,52 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 tmem_ld32_issue(tcol + (uint32_t)(ch * 32), r);
                 const float thr = thr_sh[row] + off;   // stale reads only cost extra pushes
                 tmem_ld_wait();
-                float g[4];
+                // max tree: 32 -> 12 partial maxima (3, 3, 2 columns) -> 4 group maxima -> 1
+                float pm[12], g[4];
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    float a0 = fmaxf(fmaxf(__uint_as_float(r[8 * jj]), __uint_as_float(r[8 * jj + 1])),
-                                     __uint_as_float(r[8 * jj + 2]));
-                    float a1 = fmaxf(fmaxf(__uint_as_float(r[8 * jj + 3]), __uint_as_float(r[8 * jj + 4])),
-                                     __uint_as_float(r[8 * jj + 5]));
-                    float a2 = fmaxf(__uint_as_float(r[8 * jj + 6]), __uint_as_float(r[8 * jj + 7]));
-                    g[jj] = fmaxf(fmaxf(a0, a1), a2);
+                    pm[3 * jj] = fmaxf(fmaxf(__uint_as_float(r[8 * jj]), __uint_as_float(r[8 * jj + 1])),
+                                       __uint_as_float(r[8 * jj + 2]));
+                    pm[3 * jj + 1] = fmaxf(fmaxf(__uint_as_float(r[8 * jj + 3]), __uint_as_float(r[8 * jj + 4])),
+                                           __uint_as_float(r[8 * jj + 5]));
+                    pm[3 * jj + 2] = fmaxf(__uint_as_float(r[8 * jj + 6]), __uint_as_float(r[8 * jj + 7]));
+                    g[jj] = fmaxf(fmaxf(pm[3 * jj], pm[3 * jj + 1]), pm[3 * jj + 2]);
                 }
                 const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
                 if (!__any_sync(0xffffffffu, m > thr))
                     continue;
+                // hit path: walk the tree down, so a single hit costs ~10 comparisons instead of 32
+                auto push = [&](int i) {
+                    const int gcol = r0 + ch * 32 + i;
+                    for (uint32_t spin = 0; (int)(tail - *myhead) >= QCAP; ++spin) {
+                        if (spin > (1u << 24)) {
+                            atomicOr(err_flag, 4);
+                            __threadfence();
+                            asm volatile("trap;");
+                        }
+                    }
+                    const unsigned meta = (((tail / QCAP) & 1u) << 31) | (unsigned)gcol;
+                    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(
+                                     ring_addr + (uint32_t)((tail % QCAP) * TC_M * 8)),
+                                 "r"(__float_as_uint(__uint_as_float(r[i]) - off)), "r"(meta)
+                                 : "memory");
+                    ++tail;
+                };
                 if (m > thr) {  // this row has at least one hit among the 32 columns
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int gcol = r0 + ch * 32 + i;
-                        if (__uint_as_float(r[i]) > thr) {
-                            for (uint32_t spin = 0; (int)(tail - *myhead) >= QCAP; ++spin) {
-                                if (spin > (1u << 24)) {
-                                    atomicOr(err_flag, 4);
-                                    __threadfence();
-                                    asm volatile("trap;");
-                                }
+                    for (int jj = 0; jj < 4; ++jj) {
+                        if (!(g[jj] > thr))
+                            continue;
+#pragma unroll
+                        for (int s3 = 0; s3 < 3; ++s3) {
+                            if (!(pm[3 * jj + s3] > thr))
+                                continue;
+#pragma unroll
+                            for (int e = 0; e < (s3 == 2 ? 2 : 3); ++e) {
+                                const int i = 8 * jj + 3 * s3 + e;
+                                if (__uint_as_float(r[i]) > thr)
+                                    push(i);
                             }
-                            const unsigned meta = (((tail / QCAP) & 1u) << 31) | (unsigned)gcol;
-                            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(
-                                             ring_addr + (uint32_t)((tail % QCAP) * TC_M * 8)),
-                                         "r"(__float_as_uint(__uint_as_float(r[i]) - off)), "r"(meta)
-                                         : "memory");
-                            ++tail;
                         }
                     }
                 }
