@@ -286,7 +286,7 @@ def main():
         peaks = read_peaks()
         stage_ms = {k: v / args.steps for k, v in stage_sum.items()}
         # dominant kernel: the kNN distance-tile kernel (k_knn_tiles_tc): ALGORITHMIC work 2 * n_query * N * d flop
-        # per launch (the full distance matrix; tiles skipped by the exact PC-1 bound still count as answered)
+        # per launch (the full distance matrix; tiles skipped by the exact triangle-inequality bound still count as answered)
         flop = 2.0 * n_local * w["cells"] * w["ndims"]
         knn_ms = stage_ms["knn_tile_ms"]
         achieved_tf = flop / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else 0.0

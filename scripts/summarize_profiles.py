@@ -41,5 +41,16 @@ with open(os.path.join(out, f"{tag}_knn_tiles_tc_ncu.txt"), "w") as f:
     for h, u, v in zip(hdr, rr[1], vals):
         if any(w in h for w in want):
             f.write(f"{h} [{u}] = {v}\n")
+# 3. DRAM traffic per launch of the dominant kernel -> profiles/traffic.json (read by bench.py)
+def num(name):
+    return float(vals[hdr.index(name)].replace(",", ""))
+unit_r, unit_w = rr[1][hdr.index("dram__bytes_read.sum")], rr[1][hdr.index("dram__bytes_write.sum")]
+mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+traffic = num("dram__bytes_read.sum") * mult[unit_r] + num("dram__bytes_write.sum") * mult[unit_w]
+json.dump({"_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture per kernel "
+                      f"(profiles/{tag}_knn_tiles_tc_ncu.txt), per launch",
+           "k_knn_tiles_tc": {"workload": "cfg3", "n_gpus": 1, "bytes_per_launch": int(traffic),
+                              "capture": f"profiles/{tag}_knn_tiles_tc_ncu.txt"}},
+          open(os.path.join(out, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out, f"{tag}_launches_summary.md")).read()[:3000])
 print(open(os.path.join(out, f"{tag}_knn_tiles_tc_ncu.txt")).read()[:5000])
