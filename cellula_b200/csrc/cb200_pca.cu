@@ -576,13 +576,31 @@ __global__ void __launch_bounds__(1024) k_jacobi_eig(const double *__restrict__ 
     __syncthreads();
     const int np = (b + 1) & ~1;  // players (one dummy when b is odd)
     const double eps = 1e-12;  // relative off-diagonal threshold: eigenvectors good to ~1e-12
+    // half-warp per column pair (all np/2 <= 64 pairs of a round at once); the squared column norms are
+    // kept in shared memory and updated in closed form by every rotation (|a_p'|^2 = |a_p|^2 - t g,
+    // |a_q'|^2 = |a_q|^2 + t g), recomputed at the start of every sweep, so a pair costs ONE reduction
+    double *nrm = lam;   // b entries, free until the eigenvalues are formed below
+    const int hw = tid >> 4, hl = tid & 15, nhw = blockDim.x >> 4;
+    const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
     int sweep = 0;
     for (; sweep < 40; ++sweep) {
         if (tid == 0)
             rotated = 0;
+        for (int j = hw; j < b; j += nhw) {
+            double s2 = 0.0;
+            for (int i = hl; i < b; i += 16) {
+                const double x = A[i + (size_t)j * ld];
+                s2 += x * x;
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1)
+                s2 += __shfl_xor_sync(hmask, s2, o);
+            if (hl == 0)
+                nrm[j] = s2;
+        }
         __syncthreads();
         for (int r = 0; r < np - 1; ++r) {
-            for (int pr = w; pr < np / 2; pr += nw) {
+            for (int pr = hw; pr < np / 2; pr += nhw) {
                 int p, q;
                 if (pr == 0) {
                     p = np - 1;
@@ -599,22 +617,19 @@ __global__ void __launch_bounds__(1024) k_jacobi_eig(const double *__restrict__ 
                 if (q >= b)
                     continue;  // dummy player
                 double *ap = A + (size_t)p * ld, *aq = A + (size_t)q * ld;
-                double al = 0.0, be = 0.0, ga = 0.0;
-                for (int i = lane; i < b; i += 32) {
-                    const double x = ap[i], y = aq[i];
-                    al += x * x;
-                    be += y * y;
-                    ga += x * y;
-                }
-                al = warp_sum(al);
-                be = warp_sum(be);
-                ga = warp_sum(ga);
+                double ga = 0.0;
+                for (int i = hl; i < b; i += 16)
+                    ga += ap[i] * aq[i];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1)
+                    ga += __shfl_xor_sync(hmask, ga, o);
+                const double al = nrm[p], be = nrm[q];
                 if (fabs(ga) > eps * sqrt(al * be) && fabs(ga) > 1e-300) {
                     const double zeta = (be - al) / (2.0 * ga);
                     const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
                     double *vp = V + (size_t)p * ld, *vq = V + (size_t)q * ld;
-                    for (int i = lane; i < b; i += 32) {
+                    for (int i = hl; i < b; i += 16) {
                         const double x = ap[i], y = aq[i];
                         ap[i] = c * x - s * y;
                         aq[i] = s * x + c * y;
@@ -622,8 +637,11 @@ __global__ void __launch_bounds__(1024) k_jacobi_eig(const double *__restrict__ 
                         vp[i] = c * u - s * v;
                         vq[i] = s * u + c * v;
                     }
-                    if (lane == 0)
+                    if (hl == 0) {
+                        nrm[p] = al - t * ga;
+                        nrm[q] = be + t * ga;
                         rotated = 1;
+                    }
                 }
             }
             __syncthreads();
@@ -1059,6 +1077,7 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
 
     const int max_outer = 300;
     const double tol = 2e-9;
+    const bool trace_sweeps = getenv("CB200_TRACE") != nullptr;
     int degree = 3;  // Chebyshev filter degree between Rayleigh-Ritz steps
     std::vector<double> th((size_t)b), res((size_t)b);
     int it = 0;
@@ -1068,8 +1087,14 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
         CB_TRY(launch_cq(ctx, H, b, C, Q, 1.0, nullptr, 0.0, nullptr, 0.0, W));
         CB_TRY(launch_atb(ctx, Q, W, H, b, ctx->et.p));
         k_jacobi_eig<<<1, 1024, jac_smem, ctx->stream>>>(ctx->et.p, b, ctx->etheta.p, ctx->et.p + (size_t)b * b,
-                                                         nullptr);
+                                                         trace_sweeps ? ctx->flag.p + 1 : nullptr);
         CB_LAUNCH(ctx);
+        if (trace_sweeps) {
+            int sw = 0;
+            CB_TRY(cb200_read_back(ctx, &sw, ctx->flag.p + 1, sizeof(int)));
+            fprintf(stderr, "[cb200] eig iteration %d: %d Jacobi sweeps (b = %d)\n", it, sw, b);
+            CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 1, 0, sizeof(int), ctx->stream));
+        }
         const double *Yr = ctx->et.p + (size_t)b * b;
         CB_TRY(launch_gemm(ctx, H, b, b, Q, b, 1, Yr, b, 1, 1.0, nullptr, 0.0, nullptr, 0.0, Y1, b));
         CB_TRY(launch_gemm(ctx, H, b, b, W, b, 1, Yr, b, 1, 1.0, nullptr, 0.0, nullptr, 0.0, Y2, b));
