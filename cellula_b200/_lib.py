@@ -60,6 +60,7 @@ SIGNATURES = {
     "cb200_fetch_logcounts_async": (c_int, [c_vp, c_vp]),
     "cb200_wait_copies": (c_int, [c_vp]),
     "cb200_lognorm_genestats": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cb200_lognorm_values": (c_int, [c_vp]),
     "cb200_pca_gram_local": (c_int, [c_vp, c_vp, c_int]),
     "cb200_pca_finish": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "cb200_pca": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -244,6 +245,10 @@ class Context:
         var = np.empty(self.n_genes) if want_stats else None
         self._ck(lib().cb200_lognorm_genestats(self._h, _ptr(logx), _ptr(mean), _ptr(var)))
         return logx, mean, var
+
+    def lognorm_values(self):
+        """Logcounts only (no gene sums yet): runs while the row indices are still being uploaded."""
+        self._ck(lib().cb200_lognorm_values(self._h))
 
     def lognorm_genestats_local(self):
         self._ck(lib().cb200_lognorm_genestats_local(self._h))

@@ -77,6 +77,9 @@ struct cb200_ctx {
     DevBuf<int32_t> rowidx;
     DevBuf<double> x;
     bool loaded = false;
+    cudaStream_t up_stream = nullptr;   // the row indices are uploaded behind the values, on their own stream ...
+    cudaEvent_t ev_x = nullptr, ev_rowidx = nullptr;
+    bool rowidx_pending = false;        // ... and the first consumer waits for them (cb200_need_rowidx)
 
     // ---- a2/a3/a4
     DevBuf<double> libsize;   // [N]
@@ -87,6 +90,7 @@ struct cb200_ctx {
     DevBuf<double> gene_acc;  // [2G] sum y, sum y^2
     DevBuf<double> gene_mean, gene_var;  // [G]
     bool have_sf = false, have_logx = false, have_genestats = false;
+    bool logx_values_only = false;      // logcounts computed by cb200_lognorm_values: gene sums still to do
 
     // ---- a7: PCA
     int H = 0, d = 0, blk = 0;
@@ -251,6 +255,9 @@ void cb200_copies_shutdown(cb200_ctx *ctx);
 // the stream idle.  Above CB200_PIN_SCRATCH/2 bytes they fall back to a plain cudaMemcpyAsync.
 int cb200_read_back(cb200_ctx *ctx, void *dst, const void *src, size_t bytes);
 int cb200_write_small(cb200_ctx *ctx, void *dev_dst, const void *src, size_t bytes);
+
+// makes ctx->stream wait for the upload of the row indices (no-op once done)
+int cb200_need_rowidx(cb200_ctx *ctx);
 
 // exclusive scan of int32 counts into int64 offsets (out has n+1 entries, out[n] = total)
 int cb200_scan_i32_to_i64(cb200_ctx *ctx, const int32_t *d_in, int64_t n, int64_t *d_out);

@@ -127,6 +127,12 @@ extern "C" int cb200_free(cb200_ctx *ctx)
         cudaEventDestroy(ctx->ev[s][1]);
     }
     cb200_copies_shutdown(ctx);
+    if (ctx->up_stream != nullptr) {
+        cudaStreamSynchronize(ctx->up_stream);
+        cudaStreamDestroy(ctx->up_stream);
+        cudaEventDestroy(ctx->ev_x);
+        cudaEventDestroy(ctx->ev_rowidx);
+    }
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -408,13 +414,34 @@ static int load_common(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, int64_t
     ctx->N_total = n_cells_total;
     CB_CUDA(ctx, ctx->rowidx.ensure((size_t)nnz));
     CB_CUDA(ctx, ctx->x.ensure((size_t)nnz));
-    CB_CUDA(ctx, cudaMemcpyAsync(ctx->rowidx.p, rowidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice,
-                                 ctx->stream));
+    // values first: size factors and log-counts need only them (and the column pointers), so that part of
+    // the path -- and the copy-out of the log-counts -- runs while the row indices are still arriving
+    if (ctx->up_stream == nullptr) {
+        CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+        CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_x, cudaEventDisableTiming));
+        CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rowidx, cudaEventDisableTiming));
+    }
     CB_CUDA(ctx, cudaMemcpyAsync(ctx->x.p, values, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice,
                                  ctx->stream));
+    CB_CUDA(ctx, cudaEventRecord(ctx->ev_x, ctx->stream));
+    CB_CUDA(ctx, cudaStreamWaitEvent(ctx->up_stream, ctx->ev_x, 0));
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->rowidx.p, rowidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                 ctx->up_stream));
+    CB_CUDA(ctx, cudaEventRecord(ctx->ev_rowidx, ctx->up_stream));
+    ctx->rowidx_pending = true;
+    ctx->logx_values_only = false;
     ctx->loaded = true;
     ctx->have_sf = ctx->have_logx = ctx->have_genestats = ctx->have_gram = ctx->have_scores = false;
     ctx->have_knn = false;
+    return 0;
+}
+
+int cb200_need_rowidx(cb200_ctx *ctx)
+{
+    if (ctx->rowidx_pending) {
+        CB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_rowidx, 0));
+        ctx->rowidx_pending = false;
+    }
     return 0;
 }
 
@@ -474,6 +501,7 @@ extern "C" int cb200_export_csc(cb200_ctx *ctx, int64_t *colptr, int32_t *rowidx
     if (colptr != nullptr)
         CB_CUDA(ctx, cudaMemcpyAsync(colptr, ctx->colptr.p, (size_t)(ctx->N + 1) * sizeof(int64_t),
                                      cudaMemcpyDeviceToHost, ctx->stream));
+    CB_TRY(cb200_need_rowidx(ctx));
     if (rowidx != nullptr)
         CB_CUDA(ctx, cudaMemcpyAsync(rowidx, ctx->rowidx.p, (size_t)ctx->nnz * sizeof(int32_t),
                                      cudaMemcpyDeviceToHost, ctx->stream));

@@ -186,6 +186,48 @@ k_lognorm_genestats(const int64_t *__restrict__ colptr, const int32_t *__restric
     }
 }
 
+// K2 alone: logcounts from the values and the column pointers only (no row indices, no gene sums)
+__global__ void __launch_bounds__(256)
+k_lognorm_values(const int64_t *__restrict__ colptr, const double *__restrict__ x, const double *__restrict__ sf,
+                 int64_t n_cols, double *__restrict__ logx)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const double ln2 = 0.693147180559945309417232121458;
+    for (int64_t c = warp0; c < n_cols; c += nwarps) {
+        const int64_t b = colptr[c], e = colptr[c + 1];
+        const double s = sf[c];
+        int64_t i = b + lane;
+        for (; i + 96 < e; i += 128) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                v[u] = ld_stream(x + i + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                st_stream(logx + i + 32 * u, log1p(v[u] / s) / ln2);
+        }
+        for (; i < e; i += 32)
+            st_stream(logx + i, log1p(ld_stream(x + i) / s) / ln2);
+    }
+}
+
+// K3 alone: per-gene sums of the logcounts already in HBM (same arithmetic as the fused kernel: the
+// values are read back bit for bit)
+__global__ void __launch_bounds__(256)
+k_genestats_from_logx(const int32_t *__restrict__ rowidx, const double *__restrict__ logx, int64_t nnz,
+                      double *__restrict__ acc_sum, double *__restrict__ acc_sq)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const double y = ld_stream(logx + i);
+        const int g = ld_stream_i(rowidx + i);
+        atomicAdd(acc_sum + g, y);
+        atomicAdd(acc_sq + g, y * y);
+    }
+}
+
 __global__ void k_genestats_finish(const double *__restrict__ acc_sum, const double *__restrict__ acc_sq, int64_t G,
                                    double n_total, double *__restrict__ mean, double *__restrict__ var)
 {
@@ -209,14 +251,42 @@ extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     CB_CUDA(ctx, ctx->logx.ensure((size_t)ctx->nnz));
     CB_CUDA(ctx, ctx->gene_acc.ensure((size_t)(2 * ctx->G)));
-    cb_stage_begin(ctx, ST_LOGNORM);
+    CB_TRY(cb200_need_rowidx(ctx));
+    if (!(ctx->have_logx && ctx->logx_values_only))
+        cb_stage_begin(ctx, ST_LOGNORM);   // (after cb200_lognorm_values the stage is already open)
     CB_CUDA(ctx, cudaMemsetAsync(ctx->gene_acc.p, 0, (size_t)(2 * ctx->G) * sizeof(double), ctx->stream));
-    int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
-    k_lognorm_genestats<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->N,
-                                                       ctx->logx.p, ctx->gene_acc.p, ctx->gene_acc.p + ctx->G);
+    if (ctx->have_logx && ctx->logx_values_only) {
+        // the logcounts exist already (cb200_lognorm_values): only the gene sums are left
+        k_genestats_from_logx<<<ctx->num_sms * 16, 256, 0, ctx->stream>>>(ctx->rowidx.p, ctx->logx.p, ctx->nnz,
+                                                                           ctx->gene_acc.p, ctx->gene_acc.p + ctx->G);
+        ctx->logx_values_only = false;
+    } else {
+        int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
+        k_lognorm_genestats<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->N,
+                                                           ctx->logx.p, ctx->gene_acc.p, ctx->gene_acc.p + ctx->G);
+    }
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_LOGNORM);
     ctx->have_logx = true;
+    return 0;
+}
+
+// Logcounts only (K2), from the values and the column pointers: callable while the row indices are still
+// being uploaded, so that cb200_fetch_logcounts_async can start early; a following
+// cb200_lognorm_genestats_local then only accumulates the gene sums.
+extern "C" int cb200_lognorm_values(cb200_ctx *ctx)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->loaded && ctx->have_sf, "cb200_lognorm_values: size factors have not been computed");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CB_CUDA(ctx, ctx->logx.ensure((size_t)ctx->nnz));
+    cb_stage_begin(ctx, ST_LOGNORM);
+    const int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
+    k_lognorm_values<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->x.p, ctx->sf.p, ctx->N, ctx->logx.p);
+    CB_LAUNCH(ctx);
+    ctx->have_logx = true;
+    ctx->logx_values_only = true;
     return 0;
 }
 

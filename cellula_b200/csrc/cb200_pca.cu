@@ -936,6 +936,7 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     CB_CUDA(ctx, ctx->hptr.ensure((size_t)ctx->N + 1));
     CB_CUDA(ctx, ctx->gram.ensure((size_t)H * H));
 
+    CB_TRY(cb200_need_rowidx(ctx));
     cb_stage_begin(ctx, ST_HVG_EXTRACT);
     CB_TRY(cb200_write_small(ctx, ctx->hvg_idx.p, sorted_genes.data(), (size_t)H * sizeof(int32_t)));
     CB_TRY(cb200_write_small(ctx, ctx->hvg_perm.p, perm.data(), (size_t)H * sizeof(int32_t)));

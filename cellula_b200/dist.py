@@ -82,6 +82,9 @@ class CudaShard:
     def finish_genestats(self):
         return self.ctx.genestats_finish(want=True)
 
+    def lognorm_values(self):
+        self.ctx.lognorm_values()
+
     def logcounts(self, out=None):
         return self.ctx.fetch_logcounts(out)
 
@@ -198,9 +201,14 @@ class ShardedPipeline:
         marks = [("start", time.perf_counter())]
         sf = self.size_factors(sf_in, want=want_host)
         marks.append(("size_factors", time.perf_counter()))
+        if logx_out is not None and hasattr(self.shard, "lognorm_values"):
+            # logcounts first (values + column pointers only) and on their way to the host while the row
+            # indices are still being uploaded; the gene sums follow
+            self.shard.lognorm_values()
+            self.shard.logcounts_async(logx_out)            # overlaps everything that follows
         mean, var = self.gene_stats()
         marks.append(("gene_stats", time.perf_counter()))
-        if logx_out is not None:
+        if logx_out is not None and not hasattr(self.shard, "lognorm_values"):
             self.shard.logcounts_async(logx_out)            # overlaps the trend fit, PCA, kNN and SNN
         stats = trendvar.model_gene_var(mean, var)          # replicated host step (R: scran::fitTrendVar)
         hvgs = trendvar.get_top_hvgs(stats, hvg_ntop)

@@ -127,6 +127,10 @@ int cb200_size_factors(cb200_ctx *ctx, const double *sf_in, double *sf_out);
 int cb200_lognorm_genestats_local(cb200_ctx *ctx);
 int cb200_genestats_finish(cb200_ctx *ctx, double *gene_mean /* nullable [G] */,
                            double *gene_var /* nullable [G] */);
+/* K2 alone: logcounts from the values and the column pointers (no gene sums yet).  The loaders send the
+ * values first and the row indices behind them, so this -- and cb200_fetch_logcounts_async -- can run while
+ * the indices are still arriving; cb200_lognorm_genestats_local afterwards only accumulates the gene sums. */
+int cb200_lognorm_values(cb200_ctx *ctx);
 int cb200_fetch_logcounts(cb200_ctx *ctx, double *logx_out /* [nnz_local] */);
 /* Same copy issued on the context's copy stream so that it overlaps the following stages;
  * logx_out should be page-locked.  cb200_wait_copies blocks until such copies have landed. */

@@ -95,3 +95,19 @@ def test_stage_order_is_enforced(gpu_ctx, small_counts):
     gpu_ctx.load_csc(d["n_genes"], d["colptr"], d["rowidx"], d["x"])
     with pytest.raises(cellula_b200.Cb200Error, match="size factors have not been computed"):
         gpu_ctx.lognorm_genestats()
+
+
+def test_values_first_split_equals_fused(gpu_ctx, small_counts):
+    """cb200_lognorm_values (logcounts from values + column pointers, while the row indices still upload)
+    followed by the gene sums must give bit-identical logcounts and statistics to the fused kernel's."""
+    d = small_counts
+    gpu_ctx.load_csc(d["n_genes"], d["colptr"], d["rowidx"], d["x"])
+    gpu_ctx.size_factors()
+    logx_f, mean_f, var_f = gpu_ctx.lognorm_genestats()
+    gpu_ctx.load_csc(d["n_genes"], d["colptr"], d["rowidx"], d["x"])
+    gpu_ctx.size_factors()
+    gpu_ctx.lognorm_values()
+    early = gpu_ctx.fetch_logcounts()                      # available before the gene sums
+    logx_s, mean_s, var_s = gpu_ctx.lognorm_genestats()
+    assert np.array_equal(early, logx_f) and np.array_equal(logx_s, logx_f)
+    assert rel(mean_s, mean_f) <= 1e-14 and rel(var_s, var_f) <= 1e-12     # summation order of the atomics
