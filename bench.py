@@ -33,6 +33,8 @@ WORKLOADS = {
     "cfg1": dict(cells=2700, genes=32738, nnz_per_cell=850.0, ndims=30, k=10, scheme="jaccard"),
     "cfg2": dict(cells=68579, genes=32738, nnz_per_cell=525.0, ndims=50, k=20, scheme="rank"),
     "cfg3": dict(cells=1306127, genes=27998, nnz_per_cell=1500.0, ndims=50, k=20, scheme="rank"),
+    # cfg4 (kNN/SNN-only sweep on a fixed 1M x 50 embedding) is scripts/knn_only.py
+    "cfg5": dict(cells=4000000, genes=30000, nnz_per_cell=1000.0, ndims=50, k=20, scheme="rank"),
 }
 HVG_NTOP = 2000
 SEED = 20261019

@@ -141,6 +141,9 @@ struct cb200_ctx {
     DevBuf<int32_t> knn;       // [nq*k] row-major 0-based
     DevBuf<double> knn_dk;     // [nq] exact k-th candidate distance
     DevBuf<int32_t> fb_list;   // [nq] queries needing the exact scan
+    DevBuf<int> fb_cnt;        // [n_fallback] hits collected per flagged query
+    DevBuf<double> fb_d;       // [n_fallback * KNN_FB_CAP] their distances
+    DevBuf<int32_t> fb_i;      // ... and indices
     DevBuf<int32_t> stage_i;   // staging for index layout conversion
     int64_t knn_nq = 0, knn_ntotal = 0, knn_qbegin = 0;
     int knn_k = 0;

@@ -113,7 +113,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->knn_cl.release(); ctx->knn_rho.release(); ctx->knn_cl_rhomax.release(); ctx->knn_cl_tile_begin.release();
     ctx->knn_pad_before.release(); ctx->knn_cl_order.release();
     ctx->nrm2.release(); ctx->maxnrm.release(); ctx->cand_idx.release(); ctx->cand_tau.release(); ctx->cand_err.release();
-    ctx->knn.release(); ctx->knn_dk.release(); ctx->fb_list.release(); ctx->stage_i.release();
+    ctx->knn.release(); ctx->knn_dk.release(); ctx->fb_list.release(); ctx->fb_cnt.release(); ctx->fb_d.release(); ctx->fb_i.release(); ctx->stage_i.release();
     ctx->index0.release(); ctx->rcnt.release(); ctx->rptr.release(); ctx->rcur.release();
     ctx->hosts_u.release(); ctx->hosts.release(); ctx->ecnt.release(); ctx->eptr.release();
     ctx->bcnt.release(); ctx->efrom.release(); ctx->eto.release(); ctx->ew8.release();

@@ -335,42 +335,53 @@ k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, 
     }
 }
 
-// Exact scan for one flagged query per block: every reference whose exact distance is
-// <= the exact distance of the k-th candidate is collected, then ranked by (distance, index).
+// Exact scan for the flagged queries: every reference whose exact distance is <= the exact distance
+// of the k-th candidate is collected, then ranked by (distance, index).  Two kernels so that a single
+// flagged query still uses the whole GPU: blockIdx.y slices the references, the hits of a query are
+// appended to its global buffer; then one block per query ranks them.
 __global__ void __launch_bounds__(256)
-k_knn_exact(const double *__restrict__ E, int64_t lde, int d, int64_t n, int64_t q_begin, int k,
-            const int32_t *__restrict__ fb_list, const double *__restrict__ knn_dk, int32_t *__restrict__ knn,
-            int *__restrict__ err_flag)
+k_knn_exact_collect(const double *__restrict__ E, int64_t lde, int d, int64_t n, int64_t q_begin,
+                    const int32_t *__restrict__ fb_list, const double *__restrict__ knn_dk, int *__restrict__ gcnt,
+                    double *__restrict__ gd, int32_t *__restrict__ gi)
 {
-    __shared__ double sd[KNN_FB_CAP];
-    __shared__ int si[KNN_FB_CAP];
-    __shared__ int cnt;
     const int64_t q = fb_list[blockIdx.x];
     const int64_t grow = q_begin + q;
     const double thr = knn_dk[q];
     const double *qa = E + grow * lde;
-    if (threadIdx.x == 0)
-        cnt = 0;
-    __syncthreads();
-    for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
+    const int64_t per = (n + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * per, r1 = r0 + per < n ? r0 + per : n;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
         if (r == grow)
             continue;
         const double dist = exact_dist(qa, E + r * lde, d);
         if (dist <= thr) {
-            const int pos = atomicAdd(&cnt, 1);
+            const int pos = atomicAdd(gcnt + blockIdx.x, 1);
             if (pos < KNN_FB_CAP) {
-                sd[pos] = dist;
-                si[pos] = (int)r;
+                gd[(size_t)blockIdx.x * KNN_FB_CAP + pos] = dist;
+                gi[(size_t)blockIdx.x * KNN_FB_CAP + pos] = (int32_t)r;
             }
         }
     }
-    __syncthreads();
-    const int c = cnt;
+}
+
+__global__ void __launch_bounds__(256)
+k_knn_exact_rank(int k, const int32_t *__restrict__ fb_list, const int *__restrict__ gcnt, const double *__restrict__ gd,
+                 const int32_t *__restrict__ gi, int32_t *__restrict__ knn, int *__restrict__ err_flag)
+{
+    __shared__ double sd[KNN_FB_CAP];
+    __shared__ int si[KNN_FB_CAP];
+    const int64_t q = fb_list[blockIdx.x];
+    const int c = gcnt[blockIdx.x];
     if (c > KNN_FB_CAP || c < k) {
         if (threadIdx.x == 0)
             atomicOr(err_flag, 1);
         return;
     }
+    for (int e = threadIdx.x; e < c; e += blockDim.x) {
+        sd[e] = gd[(size_t)blockIdx.x * KNN_FB_CAP + e];
+        si[e] = gi[(size_t)blockIdx.x * KNN_FB_CAP + e];
+    }
+    __syncthreads();
     for (int e = threadIdx.x; e < c; e += blockDim.x) {
         const double de = sd[e];
         const int ie = si[e];
@@ -438,8 +449,21 @@ static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, i
         ctx->tm.knn_tiles_scanned = ctx->tm.knn_tiles_total = ((nq + 127) / 128) * ((n + 127) / 128);
     }
     if (h[0] > 0) {
-        k_knn_exact<<<h[0], 256, 0, ctx->stream>>>(E, lde, d, n, q_begin, k, ctx->fb_list.p, ctx->knn_dk.p, ctx->knn.p,
-                                                   ctx->flag.p + 3);
+        const int nfb = h[0];
+        int slices = (ctx->num_sms * 8 + nfb - 1) / nfb;   // enough blocks to fill the GPU whatever the count
+        if ((int64_t)slices * 4096 > n)
+            slices = (int)((n + 4095) / 4096);
+        if (slices < 1)
+            slices = 1;
+        CB_CUDA(ctx, ctx->fb_cnt.ensure((size_t)nfb));
+        CB_CUDA(ctx, ctx->fb_d.ensure((size_t)nfb * KNN_FB_CAP));
+        CB_CUDA(ctx, ctx->fb_i.ensure((size_t)nfb * KNN_FB_CAP));
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->fb_cnt.p, 0, (size_t)nfb * sizeof(int), ctx->stream));
+        k_knn_exact_collect<<<dim3((unsigned)nfb, (unsigned)slices), 256, 0, ctx->stream>>>(
+            E, lde, d, n, q_begin, ctx->fb_list.p, ctx->knn_dk.p, ctx->fb_cnt.p, ctx->fb_d.p, ctx->fb_i.p);
+        CB_LAUNCH(ctx);
+        k_knn_exact_rank<<<nfb, 256, 0, ctx->stream>>>(k, ctx->fb_list.p, ctx->fb_cnt.p, ctx->fb_d.p, ctx->fb_i.p,
+                                                       ctx->knn.p, ctx->flag.p + 3);
         CB_LAUNCH(ctx);
         CB_TRY(cb200_read_back(ctx, h, ctx->flag.p + 2, 2 * sizeof(int)));
         CB_CHECK(ctx, (h[1] & 1) == 0,
