@@ -396,10 +396,10 @@ constexpr int TC_ACC_STAGES = 4;
 constexpr int TC_POS_BITS = 27;  // sorted positions in a ring entry
 constexpr int TC_THREADS = 64 + TC_SCAN_SETS * 128 + 128 + 128;  // + inserters + query-image builders
 
-template <int KP, int STAGES, int QCAP>
+template <int KP, int STAGES, int QCAP, int NQB>
 struct TcSmem {
-    static constexpr size_t q_img = 0;                                      // 2 x (Q hi | Q lo)
-    static constexpr size_t r_img = q_img + 2 * TC_TILE_BYTES;
+    static constexpr size_t q_img = 0;                                      // NQB x (Q hi | Q lo)
+    static constexpr size_t r_img = q_img + NQB * TC_TILE_BYTES;
     static constexpr size_t hk = r_img + (size_t)STAGES * TC_TILE_BYTES;    // [KP][TC_M] heap keys (T values)
     static constexpr size_t hi = hk + (size_t)TC_M * KP * 4;                // [KP][TC_M] sorted positions
     static constexpr size_t ring = hi + (size_t)TC_M * KP * 4;              // [SETS][QCAP][TC_M] uint2
@@ -413,7 +413,9 @@ struct TcSmem {
     static constexpr size_t bytes = seq_tile + 2 * TC_RING * 4;
 };
 
-template <int KP, int STAGES, int QCAP>
+// NQB = query-image buffers: 2 (the image of the next cluster is built while the current one is in use) or,
+// when the candidate heaps need the room (KP = 112), 1 (the build waits for the last MMA of the visit)
+template <int KP, int STAGES, int QCAP, int NQB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, const unsigned char *__restrict__ img,
                int64_t nq, const int32_t *__restrict__ qlist, const int32_t *__restrict__ qpos,
@@ -424,7 +426,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau, float *__restrict__ cand_err,
                int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done, long long *__restrict__ dbg)
 {
-    using L = TcSmem<KP, STAGES, QCAP>;
+    using L = TcSmem<KP, STAGES, QCAP, NQB>;
     // CB200_KNN_TIMELINE (debugging aid): the CTA in the middle of the grid records (tag, clock) pairs
     // per role into dbg[role][TL_CAP][2]
     constexpr int TL_CAP = 4096;
@@ -629,6 +631,17 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         // after the first tile of the current cluster has been staged, so the loads and the image build
         // hide behind the tiles in flight.  (A cluster planned with the thresholds of that moment may
         // turn out to need no tile later: the visit is then skipped and its image buffer released here.)
+        auto post_request = [&](int j) {
+            ++req_visit;
+            if (lane == 0) {
+                const int b = req_visit % NQB, use = req_visit / NQB;
+                if (use >= 1)   // the builders must have taken the previous request for this buffer
+                    mbar_wait(qfull + b, (uint32_t)((use - 1) & 1), err_flag);
+                q_cluster[b] = j;
+                __threadfence_block();
+                mbar_arrive(qreq + b);
+            }
+        };
         auto make_plan = [&]() {
             while (opos < C) {
                 if (opos == 1 && !prefiltered) {   // the home cluster is done: thresholds exist now
@@ -654,15 +667,11 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 }
                 if (!__any_sync(0xffffffffu, need))
                     continue;
-                ++req_visit;
-                if (lane == 0) {
-                    const int b = req_visit & 1, use = req_visit >> 1;
-                    if (use >= 1)   // the builders must have taken the previous request for this buffer
-                        mbar_wait(qfull + b, (uint32_t)((use - 1) & 1), err_flag);
-                    q_cluster[b] = j;
-                    __threadfence_block();
-                    mbar_arrive(qreq + b);
-                }
+                // with two image buffers the build is requested now, ahead of the first tile; with one buffer
+                // it waits for that tile (an early request for a visit that ends up without tiles could
+                // only be released after the MMA issuer has moved on -- which needs the next tile)
+                if (NQB == 2)
+                    post_request(j);
                 plan_valid = true;
                 plan_j = j;
                 plan_t = pt;
@@ -680,8 +689,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                         // skipped visit: nobody else releases its image buffer.  Only once the image is
                         // built: an earlier arrival would complete the release the builders are still
                         // waiting for from the previous user of the buffer.
-                        mbar_wait(qfull + (cur_visit & 1), (uint32_t)((cur_visit >> 1) & 1), err_flag);
-                        mbar_arrive(qfree + (cur_visit & 1));
+                        mbar_wait(qfull + (cur_visit % NQB), (uint32_t)((cur_visit / NQB) & 1), err_flag);
+                        mbar_arrive(qfree + (cur_visit % NQB));
                     }
                     cur_visit = -1;
                     if (!plan_valid) {
@@ -695,7 +704,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     t = plan_t;
                     te = plan_te;
                     crmax = plan_crmax;
-                    cur_visit = req_visit;
+                    cur_visit = NQB == 2 ? req_visit : -1;   // one buffer: requested with the first tile
                     cur_issued = false;
                     plan_valid = false;
 #pragma unroll
@@ -752,6 +761,10 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             const bool first = !cur_issued;
             cur_issued = true;
             if (first) {
+                if (NQB == 1) {
+                    post_request(cur_j);
+                    cur_visit = req_visit;
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     smax[u] = fmaxf(smax[u], dq[u] * crmax + 0.5f * crmax * crmax);
@@ -783,7 +796,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             mbar_arrive(full + (int)(seq % STAGES));
             atomicAdd(tiles_done, (unsigned long long)seq);
             // stop the builders
-            const int v = req_visit + 1, b = v & 1, use = v >> 1;
+            const int v = req_visit + 1, b = v % NQB, use = v / NQB;
             if (use >= 1)
                 mbar_wait(qfull + b, (uint32_t)((use - 1) & 1), err_flag);
             q_cluster[b] = -1;
@@ -833,10 +846,10 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 }
                 const int meta = seq_meta[seq % TC_RING];
                 if (meta & (1 << 10)) {   // first tile of a cluster visit: switch to its query image
-                    const int v = meta >> 11, b = v & 1;
+                    const int v = meta >> 11, b = v % NQB;
                     if (prev_b >= 0)
                         umma_commit(qfree + prev_b);   // every MMA reading the previous image has been issued
-                    mbar_wait(qfull + b, (uint32_t)((v >> 1) & 1), err_flag);
+                    mbar_wait(qfull + b, (uint32_t)((v / NQB) & 1), err_flag);
                     TL(1, ((long long)seq << 8) | 4);
                     tc_fence_after();
                     prev_b = b;
@@ -1078,7 +1091,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         const int my_g = rowq < nq ? qlist[rowq] : -1;   // lane r: original index of row 32 bw + r
         bool pf_served = false;
         for (int visit = 0;; ++visit) {
-            const int b = visit & 1, use = visit >> 1;
+            const int b = visit % NQB, use = visit / NQB;
             // wait for the next image request; meanwhile serve the (single) prefilter request
             // (polling only until the prefilter is served; afterwards the hardware-suspended wait below)
             for (uint32_t spin = 0; !pf_served && !mbar_test(qreq + b, (uint32_t)(use & 1)); ++spin) {
@@ -1170,13 +1183,13 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-template <int KP, int STAGES, int QCAP>
+template <int KP, int STAGES, int QCAP, int NQB>
 static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double scale, int64_t nq, int C,
                      int cand_stride)
 {
-    const size_t smem = TcSmem<KP, STAGES, QCAP>::bytes;
-    static_assert(TcSmem<KP, STAGES, QCAP>::bytes <= 232448, "shared memory budget");
-    CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, STAGES, QCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = TcSmem<KP, STAGES, QCAP, NQB>::bytes;
+    static_assert(TcSmem<KP, STAGES, QCAP, NQB>::bytes <= 232448, "shared memory budget");
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, STAGES, QCAP, NQB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     const unsigned grid = (unsigned)((nq + TC_M - 1) / TC_M);
     const float key_unscale = (float)(1.0 / (scale * scale));
@@ -1185,7 +1198,7 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
         CB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&dbg), (size_t)5 * 4096 * 2 * sizeof(long long)));
         CB_CUDA(ctx, cudaMemsetAsync(dbg, 0, (size_t)5 * 4096 * 2 * sizeof(long long), ctx->stream));
     }
-    k_knn_tiles_tc<KP, STAGES, QCAP><<<grid, TC_THREADS, smem, ctx->stream>>>(
+    k_knn_tiles_tc<KP, STAGES, QCAP, NQB><<<grid, TC_THREADS, smem, ctx->stream>>>(
         E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, C, ctx->knn_cen.p,
         ctx->knn_dqc.p, ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p,
         ctx->knn_tile_lo.p, ctx->knn_tile_hi.p, key_unscale, cand_stride, ctx->cand_idx.p, ctx->cand_tau.p,
@@ -1205,7 +1218,7 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
     return 0;
 }
 
-bool cb200_knn_tc_supported(int d, int k) { return d + 3 <= TC_K && k <= 52; }
+bool cb200_knn_tc_supported(int d, int k) { return d + 3 <= TC_K && k <= 100; }
 
 // number of clusters of the reference ordering: about one per 512 points (4 tiles), at most 256
 // (CB200_KNN_CLUSTERS overrides, up to TC_MAXC; any value gives the same, exact, result)
@@ -1240,8 +1253,8 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     const int64_t n_tiles_cap = (n + TC_N - 1) / TC_N + C;  // every cluster is padded to whole tiles
     const int64_t npos = n_tiles_cap * TC_N;
     // candidates kept per query (one list): enough beyond k for the margin proof of k_knn_rerank
-    const int KP = k <= 24 ? 32 : 64;
-    const int CAND = KP;
+    const int KP = k <= 24 ? 32 : (k <= 52 ? 64 : 112);
+    const int CAND = KP == 112 ? 128 : KP;   // the re-rank sorts a power of two: padded with empty entries
     CB_CUDA(ctx, ctx->knn_img.ensure((size_t)n_tiles_cap * TC_TILE_BYTES));
     CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
     CB_CUDA(ctx, ctx->cand_idx.ensure((size_t)nq * CAND));
@@ -1341,9 +1354,11 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     CB_CHECK(ctx, npos < (1LL << TC_POS_BITS), "cb200_knn: at most 2^27 points on the tensor-core engine");
     if (KP == 32)
-        CB_TRY((launch_tc<32, 3, 16>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<32, 3, 16, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
+    else if (KP == 64)
+        CB_TRY((launch_tc<64, 2, 16, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
     else
-        CB_TRY((launch_tc<64, 2, 16>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<112, 2, 4, 1>(ctx, E, lde, d, scale, nq, C, CAND)));
     cb_stage_end(ctx, ST_KNN_TILE);
     *kp_out = CAND;
     *ntau_out = 1;

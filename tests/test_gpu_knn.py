@@ -42,7 +42,19 @@ def test_knn_bit_exact_random(gpu_ctx, engine, n, d, k):
     assert bad.size == 0, (bad[:10], got[bad[:3]], want[bad[:3]])
 
 
-@pytest.mark.parametrize("n,d,k", [(2000, 50, 100), (4097, 64, 24), (900, 62, 10), (700, 20, 53)])
+@pytest.mark.parametrize("n,d,k", [(2000, 50, 100), (700, 20, 53), (5000, 30, 77)])
+def test_knn_large_k_on_the_tensor_engine(gpu_ctx, monkeypatch, n, d, k):
+    """52 < k <= 100: 112-entry heaps and a single query-image buffer (cfg4's k = 100)."""
+    monkeypatch.setenv("CB200_KNN_ENGINE", "tc")
+    for clusters in ("", "9"):
+        if clusters:
+            monkeypatch.setenv("CB200_KNN_CLUSTERS", clusters)
+        emb = synth.make_embedding(n, d, seed=n + d + k)
+        assert np.array_equal(gpu_ctx.knn(emb, k), O.find_knn(emb, k))
+        assert gpu_ctx.timings()["knn_engine"] == 2
+
+
+@pytest.mark.parametrize("n,d,k", [(4097, 64, 24), (900, 62, 10), (1500, 20, 105)])
 def test_knn_shapes_only_the_simt_engine_takes(gpu_ctx, n, d, k):
     emb = synth.make_embedding(n, d, seed=n + d + k)
     assert np.array_equal(gpu_ctx.knn(emb, k), O.find_knn(emb, k))
