@@ -1220,11 +1220,16 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
 
 bool cb200_knn_tc_supported(int d, int k) { return d + 3 <= TC_K && k <= 100; }
 
-// number of clusters of the reference ordering: about one per 512 points (4 tiles), at most 256
-// (CB200_KNN_CLUSTERS overrides, up to TC_MAXC; any value gives the same, exact, result)
+// number of clusters of the reference ordering: about one per 512 points up to 128, then one per 16 384
+// points up to 256 (measured at cfg3: 128 clusters 74 ms for ordering + tiles, 256 clusters 80 ms -- fewer
+// tiles but more cluster visits per query tile); CB200_KNN_CLUSTERS overrides, up to TC_MAXC; any value
+// gives the same, exact, result
 static int tc_num_clusters(int64_t n)
 {
     int64_t c = n / 512;
+    const int64_t hi = n / 16384 > 128 ? n / 16384 : 128;
+    if (c > hi)
+        c = hi;
     if (c > 256)
         c = 256;
     const char *e = getenv("CB200_KNN_CLUSTERS");
