@@ -7,8 +7,8 @@ plain C ABI (include/cellula_b200.h).  Importing the package never touches the G
 call does, and raises if libcellula_b200.so has not been built or no B200 is present.
 """
 from ._lib import Cb200Error, Context, build, lib  # noqa: F401
-from .api import (SerialParam, doNormAndReduce, get_context, makeGraphsAndClusters, makeSNNGraph,  # noqa: F401
-                  options, rebuildModularity, release_context)
+from .api import (SerialParam, approxSilhouette, doNormAndReduce, get_context, makeGraphsAndClusters,  # noqa: F401
+                  makeSNNGraph, options, pairwiseModularity, rebuildModularity, release_context)
 from .sce import CSC, ReducedDim, SingleCellExperiment, SNNGraph  # noqa: F401
 
 __version__ = "0.1"

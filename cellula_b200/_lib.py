@@ -74,6 +74,8 @@ SIGNATURES = {
     "cb200_snn_count_device": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_i64p]),
     "cb200_snn_emit": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cb200_free_edges": (c_int, [c_i32p, c_i32p, c_f64p]),
+    "cb200_approx_silhouette": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp]),
+    "cb200_pairwise_modularity": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "cb200_fetch_edges": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cb200_synth_counts": (c_int, [c_vp, c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_i64p]),
     "cb200_export_csc": (c_int, [c_vp, c_vp, c_vp, c_vp]),
@@ -369,6 +371,41 @@ class Context:
         weight = np.empty(n_edges, np.float64) if weight is None else weight
         self._ck(lib().cb200_fetch_edges(self._h, n_edges, _ptr(frm), _ptr(to), _ptr(weight)))
         return frm[:n_edges], to[:n_edges], weight[:n_edges]
+
+    # -- 8(f) rank 2: cluster diagnostics -------------------------------------------
+    def approx_silhouette(self, emb, labels, n_clusters, d=None):
+        """emb: N x d array or None for the resident PCA scores (first d components); labels: 0-based int32[N].
+        Returns (width float64[N], other int32[N])."""
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        n = labels.size
+        if emb is not None:
+            emb = np.asfortranarray(emb, dtype=np.float64)
+            assert emb.shape[0] == n
+            d = emb.shape[1]
+        width = np.empty(n)
+        other = np.empty(n, dtype=np.int32)
+        self._ck(lib().cb200_approx_silhouette(self._h, _ptr(emb), n, int(d), _ptr(labels), int(n_clusters),
+                                               _ptr(width), _ptr(other)))
+        return width, other
+
+    def pairwise_modularity(self, edges, labels, n_clusters):
+        """edges: (from, to, weight) 1-based arrays, or None for the edge list resident in HBM.
+        Returns (observed K x K, expected K x K, total weight); upper triangles filled."""
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        K = int(n_clusters)
+        obs, exp = np.empty((K, K)), np.empty((K, K))
+        tot = ctypes.c_double()
+        if edges is None:
+            f = t = w = None
+            ne = 0
+        else:
+            f = np.ascontiguousarray(edges[0], dtype=np.int32)
+            t = np.ascontiguousarray(edges[1], dtype=np.int32)
+            w = np.ascontiguousarray(edges[2], dtype=np.float64)
+            ne = f.size
+        self._ck(lib().cb200_pairwise_modularity(self._h, _ptr(f), _ptr(t), _ptr(w), ne, _ptr(labels), labels.size, K,
+                                                 _ptr(obs), _ptr(exp), ctypes.cast(ctypes.byref(tot), c_vp)))
+        return obs, exp, tot.value
 
     def snn_resident(self, k, snn_type="rank"):
         ne = c_i64()

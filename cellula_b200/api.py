@@ -128,6 +128,35 @@ def makeSNNGraph(space, k=10, type="rank"):
     return SNNGraph(n=space.shape[0], frm=frm, to=to, weight=w, k=int(k), type=type)
 
 
+def _label_codes(clusters):
+    """sort(unique(clusters)) and the 0-based position of every cell's label in it."""
+    clusters = np.asarray(clusters)
+    uclust = np.unique(clusters)
+    return uclust, np.searchsorted(uclust, clusters).astype(np.int32)
+
+
+def approxSilhouette(x, clusters):
+    """bluster::approxSilhouette(x, clusters) on the GPU (R/makeGraphsAndClusters.R:110, :149).
+    Returns dict(cluster, other, width) -- the columns of bluster's DataFrame."""
+    uclust, codes = _label_codes(clusters)
+    width, other = get_context().approx_silhouette(np.asarray(x, dtype=np.float64), codes, uclust.size)
+    return dict(cluster=np.asarray(clusters), other=np.where(other >= 0, uclust[np.maximum(other, 0)], uclust[0]),
+                width=width)
+
+
+def pairwiseModularity(graph, clusters, get_weights=False, as_ratio=False):
+    """bluster::pairwiseModularity(graph, clusters, get.weights, as.ratio) on the GPU
+    (R/makeGraphsAndClusters.R:105, :144, :288).  graph: what makeSNNGraph returns (SNNGraph, or a dict with
+    from / to / weight)."""
+    uclust, codes = _label_codes(clusters)
+    edges = (graph.frm, graph.to, graph.weight) if hasattr(graph, "frm") else (graph["from"], graph["to"], graph["weight"])
+    obs, expd, total = get_context().pairwise_modularity(edges, codes, uclust.size)
+    if get_weights:
+        return dict(observed=obs, expected=expd)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return obs / expd if as_ratio else (obs - expd) / total
+
+
 def _igraph_of(g):
     import igraph
     ig = igraph.Graph(n=g.n, edges=np.column_stack((g.frm - 1, g.to - 1)).tolist(), directed=False)
@@ -187,7 +216,13 @@ def makeGraphsAndClusters(sce, neighbors=10, weighting_scheme="jaccard", sweep_o
             if verbose:
                 _message(_blue("[CLU]"), "Clustering at resolution ", res, ".")
             cl = cluster(g, float(res))
-            sce.colData[f"{prefix}{res:g}"] = [str(c + 1) for c in cl]
+            gname = f"{prefix}{res:g}"
+            sce.colData[gname] = [str(c + 1) for c in cl]
+            if calculate_modularity:
+                sce.metadata[f"modularity_{gname}"] = pairwiseModularity(g, cl, as_ratio=True)
+            if calculate_silhouette:
+                sil = approxSilhouette(space, cl)
+                sce.metadata[f"silhouette_{gname}"] = sil
     elif sweep_on == "SNN" and k is not None:
         for kk in np.floor(np.asarray(k)).astype(int):
             if verbose:

@@ -174,6 +174,11 @@ struct cb200_ctx {
     DevBuf<uint32_t> snn_tmp_h, snn_tmp_rc;  // partner store written by the counting pass, read by the emission
     DevBuf<unsigned char> snn_flag;   // [nj] cells left to the merge kernel (too many partners for the hash table)
 
+    // ---- cluster diagnostics (cb200_diag.cu)
+    DevBuf<int32_t> diag_lab, diag_i, diag_ef;
+    DevBuf<double> diag_d, diag_ew;
+    DevBuf<unsigned long long> diag_cnt;
+
     // scan scratch
     DevBuf<int64_t> scan_blk;
 

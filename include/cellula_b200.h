@@ -198,6 +198,24 @@ int cb200_free_edges(int32_t *from, int32_t *to, double *weight);
  * call into caller-owned arrays (what the R shim does with freshly allocated R vectors). */
 int cb200_fetch_edges(cb200_ctx *ctx, int64_t n_edges, int32_t *from, int32_t *to, double *weight);
 
+/* ---- per-resolution cluster diagnostics -------------------------------------------
+ * Replaces: bluster::approxSilhouette(space, clusters) and bluster::pairwiseModularity(g, clusters, ...)
+ * in /root/reference/R/makeGraphsAndClusters.R:103-114 (:144-153, :288).  labels: 0-based positions in the
+ * sorted unique cluster labels, host int32[n]; a value without cells is not a cluster.
+ *
+ * cb200_approx_silhouette: emb = host column-major n x d, or NULL for the PCA scores resident in the
+ * context (first d components).  width_out[n] = (other - self) / max(other, self) with the root-mean-square
+ * distances to the own / the closest other cluster; other_out[n] = that other cluster (0-based, -1 if none). */
+int cb200_approx_silhouette(cb200_ctx *ctx, const double *emb, int64_t n, int d, const int32_t *labels,
+                            int n_clusters, double *width_out, int32_t *other_out);
+/* cb200_pairwise_modularity: edges 1-based as cb200_snn returns them (from == NULL: the edge list left in HBM
+ * by the last cb200_snn* call).  observed_out / expected_out: row-major K x K, upper triangle filled
+ * (bluster's get.weights = TRUE pair); total_weight_out (nullable) = sum of the edge weights.  The caller
+ * forms observed / expected (as.ratio = TRUE) or (observed - expected) / total. */
+int cb200_pairwise_modularity(cb200_ctx *ctx, const int32_t *from, const int32_t *to, const double *weight,
+                              int64_t n_edges, const int32_t *labels, int64_t n, int n_clusters,
+                              double *observed_out, double *expected_out, double *total_weight_out);
+
 /* ---- synthetic input (bench / test infrastructure, not part of the reference path) ---
  * Fills the context with a deterministic negative-binomial count matrix with planted
  * low-rank structure generated on the device, as if by cb200_load_csc.

@@ -543,6 +543,69 @@ def canonical_edges(frm, to, w):
 # ---------------------------------------------------------------------------------------
 # whole path (for bench cpu_baseline and the end-to-end parity tests)
 # ---------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------
+# per-resolution cluster diagnostics (R/makeGraphsAndClusters.R:103-114)
+#   bluster::approxSilhouette, bluster::pairwiseModularity -- restated from the package's
+#   definitions (bluster 1.16); bluster is not vendored in the reference: parity unpinned.
+# ---------------------------------------------------------------------------------------
+def approx_silhouette(x, clusters):
+    """bluster::approxSilhouette(x, clusters).  Returns (other, width): for every cell the closest
+    other cluster (a label) and (other.dist - self.dist) / pmax(other.dist, self.dist), where the
+    distance from cell i to cluster u is sqrt(|x_i - centroid_u|^2 + sum_dims mean sq. deviation of u)."""
+    x = np.asarray(x, dtype=np.float64)
+    clusters = np.asarray(clusters)
+    uclust = np.unique(clusters)                       # sort(unique(clusters))
+    cent, cvar = [], []
+    for u in uclust:
+        cur = x[clusters == u]
+        c = cur.mean(axis=0)
+        cent.append(c)
+        cvar.append(float(((cur - c) ** 2).mean(axis=0).sum()))
+    n = x.shape[0]
+    self_d = np.full(n, np.inf)
+    other_d = np.full(n, np.inf)
+    other_c = np.full(n, -1, dtype=np.int64)
+    for i, u in enumerate(uclust):
+        D = np.sqrt(((x - cent[i]) ** 2).sum(axis=1) + cvar[i])
+        is_self = clusters == u
+        self_d[is_self] = D[is_self]
+        better = (~is_self) & (D < other_d)
+        other_d[better] = D[better]
+        other_c[better] = i
+    with np.errstate(invalid="ignore"):
+        width = (other_d - self_d) / np.maximum(other_d, self_d)
+    other = np.where(other_c >= 0, uclust[np.maximum(other_c, 0)], uclust[0])
+    return other, width, other_c
+
+
+def pairwise_modularity(frm, to, weight, clusters, get_weights=False, as_ratio=False):
+    """bluster::pairwiseModularity(graph, clusters, get.weights, as.ratio) on an undirected weighted edge
+    list (1-based).  observed: upper-triangular K x K, [x, y] = weight of the edges between clusters x and y
+    (diagonal: within); expected: W p_x^2 on the diagonal, 2 W p_x p_y above it, p = share of the weighted
+    degree; the lower triangles are 0 (so as_ratio gives NaN there, as in R)."""
+    clusters = np.asarray(clusters)
+    uclust = np.unique(clusters)
+    K = uclust.size
+    lab = np.searchsorted(uclust, clusters)
+    a = lab[np.asarray(frm, dtype=np.int64) - 1]
+    b = lab[np.asarray(to, dtype=np.int64) - 1]
+    w = np.asarray(weight, dtype=np.float64)
+    obs = np.zeros((K, K))
+    np.add.at(obs, (np.minimum(a, b), np.maximum(a, b)), w)
+    deg = np.zeros(K)
+    np.add.at(deg, a, w)
+    np.add.at(deg, b, w)
+    W = float(w.sum())
+    prop = deg / deg.sum() if deg.sum() > 0 else deg
+    expd = np.outer(prop, prop) * W
+    expd[np.tril_indices(K, -1)] = 0.0
+    expd[np.triu_indices(K, 1)] *= 2.0
+    if get_weights:
+        return dict(observed=obs, expected=expd)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return obs / expd if as_ratio else (obs - expd) / W
+
+
 def pipeline(n_genes, colptr, rowidx, x, ndims=50, hvg_ntop=2000, neighbors=20, snn_type="rank",
              fast_pca=False):
     """counts -> SNN graph through the restated steps, in the reference's call order."""

@@ -45,11 +45,11 @@ makeGraphsAndClusters <- function(sce,
     if (verbose) message(.bluem("[CLU]"), "Found", length(unique(cl)), "clusters.")
     if (calculate_modularity) {
       if (verbose) message(.bluem("[CLU]"), "Calculating pairwise modularity.")
-      metadata(sce)[[paste0("modularity_", gname)]] <<- pairwiseModularity(g, clusters = cl, as.ratio = TRUE)
+      metadata(sce)[[paste0("modularity_", gname)]] <<- pairwiseModularityB200(g, clusters = cl, as.ratio = TRUE)
     }
     if (calculate_silhouette) {
       if (verbose) message(.bluem("[CLU]"), "Calculating approximate silhouette widths.")
-      silhouette <- as.data.frame(approxSilhouette(space, clusters = cl))
+      silhouette <- as.data.frame(approxSilhouetteB200(space, clusters = cl))
       silhouette$closest <- factor(ifelse(silhouette$width > 0, cl, silhouette$other))
       silhouette$cluster <- cl
       metadata(sce)[[paste0("silhouette_", gname)]] <<- silhouette
@@ -91,6 +91,6 @@ rebuildModularity <- function(sce, dr = "PCA", neighbors = NULL, ndims = 20,
   g <- makeSNNGraphB200(space, k = neighbors, type = weighting_scheme)
   cl <- colData(sce)[, labels]
   mlab <- paste0("modularity_", labels)
-  metadata(sce)[[mlab]] <- pairwiseModularity(g, clusters = cl, as.ratio = TRUE)
+  metadata(sce)[[mlab]] <- pairwiseModularityB200(g, clusters = cl, as.ratio = TRUE)
   sce
 }

@@ -26,3 +26,28 @@ makeSNNGraphB200 <- function(x, k = 10, type = "rank") {
   igraph::E(g)$weight <- e$weight
   g
 }
+
+#' bluster::approxSilhouette(x, clusters) on the GPU (same DataFrame columns: cluster, other, width).
+approxSilhouetteB200 <- function(x, clusters) {
+  x <- as.matrix(x)
+  storage.mode(x) <- "double"
+  uclust <- sort(unique(clusters))
+  r <- .Call("cb200r_approx_silhouette", .cb200_ctx(), x, match(clusters, uclust) - 1L, length(uclust),
+             PACKAGE = "cellulaB200")
+  S4Vectors::DataFrame(cluster = clusters, other = uclust[r$other + 1L], width = r$width, row.names = rownames(x))
+}
+
+#' bluster::pairwiseModularity(graph, clusters, get.weights, as.ratio) on the GPU.
+pairwiseModularityB200 <- function(graph, clusters, get.weights = FALSE, as.ratio = FALSE) {
+  uclust <- sort(unique(clusters))
+  el <- igraph::as_edgelist(graph, names = FALSE)
+  w <- igraph::E(graph)$weight
+  if (is.null(w)) w <- rep(1, nrow(el))
+  r <- .Call("cb200r_pairwise_modularity", .cb200_ctx(), as.integer(el[, 1]), as.integer(el[, 2]), as.numeric(w),
+             match(clusters, uclust) - 1L, length(uclust), PACKAGE = "cellulaB200")
+  obs <- t(r$observed_t); expd <- t(r$expected_t)            # the library fills row-major
+  dimnames(obs) <- dimnames(expd) <- list(uclust, uclust)
+  if (get.weights) list(observed = obs, expected = expd)
+  else if (as.ratio) obs / expd
+  else (obs - expd) / r$total
+}

@@ -166,6 +166,57 @@ SEXP cb200r_knn(SEXP sctx, SEXP space, SEXP k)
     return idx;
 }
 
+/* bluster::approxSilhouette(x, clusters): codes = 0-based position of every cell's label in
+ * sort(unique(clusters)).  Returns list(width, other) (other: 0-based code of the closest other cluster). */
+SEXP cb200r_approx_silhouette(SEXP sctx, SEXP space, SEXP codes, SEXP nclust)
+{
+    cb200_ctx *ctx = get_ctx(sctx);
+    int64_t n = Rf_nrows(space);
+    int d = Rf_ncols(space);
+    SEXP width = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)n)), other = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)n));
+    int rc = cb200_approx_silhouette(ctx, REAL(space), n, d, INTEGER(codes), Rf_asInteger(nclust), REAL(width),
+                                     INTEGER(other));
+    if (rc != 0) {
+        UNPROTECT(2);
+        Rf_error("%s", cb200_last_error(ctx));
+    }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2)), nm = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_VECTOR_ELT(out, 0, width);
+    SET_VECTOR_ELT(out, 1, other);
+    SET_STRING_ELT(nm, 0, Rf_mkChar("width"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("other"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(4);
+    return out;
+}
+
+/* bluster::pairwiseModularity(g, clusters, get.weights = TRUE): edges = as_edgelist(g) + E(g)$weight.
+ * Returns list(observed, expected, total); the K x K matrices are filled row-major by the library, so they
+ * are transposed into R's column-major layout here (lower/upper triangle swap handled by t() in R). */
+SEXP cb200r_pairwise_modularity(SEXP sctx, SEXP from, SEXP to, SEXP weight, SEXP codes, SEXP nclust)
+{
+    cb200_ctx *ctx = get_ctx(sctx);
+    int K = Rf_asInteger(nclust);
+    SEXP obs = PROTECT(Rf_allocMatrix(REALSXP, K, K)), expd = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+    SEXP tot = PROTECT(Rf_allocVector(REALSXP, 1));
+    int rc = cb200_pairwise_modularity(ctx, INTEGER(from), INTEGER(to), REAL(weight), (int64_t)XLENGTH(from), INTEGER(codes),
+                                       (int64_t)XLENGTH(codes), K, REAL(obs), REAL(expd), REAL(tot));
+    if (rc != 0) {
+        UNPROTECT(3);
+        Rf_error("%s", cb200_last_error(ctx));
+    }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)), nm = PROTECT(Rf_allocVector(STRSXP, 3));
+    SET_VECTOR_ELT(out, 0, obs);
+    SET_VECTOR_ELT(out, 1, expd);
+    SET_VECTOR_ELT(out, 2, tot);
+    SET_STRING_ELT(nm, 0, Rf_mkChar("observed_t"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("expected_t"));
+    SET_STRING_ELT(nm, 2, Rf_mkChar("total"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(5);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"cb200r_init", (DL_FUNC)&cb200r_init, 1},
     {"cb200r_load_counts", (DL_FUNC)&cb200r_load_counts, 2},
@@ -174,6 +225,8 @@ static const R_CallMethodDef call_methods[] = {
     {"cb200r_pca", (DL_FUNC)&cb200r_pca, 4},
     {"cb200r_snn_graph", (DL_FUNC)&cb200r_snn_graph, 4},
     {"cb200r_knn", (DL_FUNC)&cb200r_knn, 3},
+    {"cb200r_approx_silhouette", (DL_FUNC)&cb200r_approx_silhouette, 4},
+    {"cb200r_pairwise_modularity", (DL_FUNC)&cb200r_pairwise_modularity, 6},
     {NULL, NULL, 0}};
 
 void R_init_cellulaB200(DllInfo *dll)

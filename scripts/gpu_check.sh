@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 } > gpurun_out/env.log 2>&1
 cat gpurun_out/env.log
 echo "== build"; timeout 600 python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -3
-for f in tests/test_gpu_norm.py tests/test_gpu_snn.py tests/test_gpu_knn.py tests/test_gpu_pca.py tests/test_gpu_pipeline.py; do
+for f in tests/test_gpu_norm.py tests/test_gpu_snn.py tests/test_gpu_knn.py tests/test_gpu_pca.py tests/test_gpu_diag.py tests/test_gpu_pipeline.py; do
   n=$(basename $f .py)
   echo "== $n"
   timeout -k 10 ${TEST_TIMEOUT:-700} python -m pytest $f -m gpu -q --timeout 400 --timeout-method=thread > gpurun_out/$n.log 2>&1

@@ -123,3 +123,17 @@ def test_pca_matches_definition(small_counts):
     assert np.all(np.diff(p["var_explained"]) <= 0)
     q = O.run_pca_irlba_like(d["n_genes"], d["colptr"], d["rowidx"], lx, hv, 5)
     assert np.allclose(q["var_explained"], p["var_explained"], rtol=1e-8)
+
+
+def test_kat_cluster_diagnostics():
+    """SURVEY 8(f) rank 2 restatements (bluster::approxSilhouette / pairwiseModularity) against the
+    hand-derived vectors."""
+    s = KAT["silhouette1"]
+    other, width, _ = O.approx_silhouette(np.asarray(s["x"])[:, None], np.asarray(s["clusters"]))
+    assert other.tolist() == s["other"] and np.allclose(width, s["width"], rtol=1e-15)
+    m = KAT["modularity1"]
+    got = O.pairwise_modularity(m["from"], m["to"], m["weight"], m["clusters"], get_weights=True)
+    assert np.allclose(got["observed"], m["observed"], rtol=1e-15)
+    assert np.allclose(got["expected"], m["expected"], rtol=1e-15)
+    ratio = O.pairwise_modularity(m["from"], m["to"], m["weight"], m["clusters"], as_ratio=True)
+    assert np.isclose(ratio[0, 1], 5.0 / (2 * 6 * 35 / 144)) and np.isnan(ratio[1, 0])
