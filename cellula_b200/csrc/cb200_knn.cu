@@ -445,6 +445,8 @@ static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, i
         CB_TRY(cb200_read_back(ctx, &done, ctx->maxnrm.p + 3, sizeof(done)));
         ctx->tm.knn_tiles_scanned = (int64_t)done;
         ctx->tm.knn_tiles_total = ((nq + 127) / 128) * ((n + 127) / 128);
+        if (ctx->tm.knn_tiles_total < ctx->tm.knn_tiles_scanned)   // tiny inputs: the clusters are padded to whole tiles
+            ctx->tm.knn_tiles_total = ctx->tm.knn_tiles_scanned;
     } else {
         ctx->tm.knn_tiles_scanned = ctx->tm.knn_tiles_total = ((nq + 127) / 128) * ((n + 127) / 128);
     }
