@@ -283,30 +283,40 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
 // One warp-iteration handles up to 32 list entries; the merge kernel above spends one per edge.
 // A cell with more than SNN_HASH_CAP distinct partners is flagged and left to k_snn_merge.
 // ---------------------------------------------------------------------------------------
-#define SNN_HASH_SLOTS 2048
-#define SNN_HASH_CAP 1408          // dense entries per warp (load factor <= 0.69)
-#define SNN_HASH_STAGE 2048        // list entries staged per group of lists
-#define SNN_HASH_WARPS 7
+// Two table sizes: the small one (14 warps per SM) takes every cell first; a cell with more partners than it
+// holds is flagged 1 and retried with the large one (7 warps per SM); what still does not fit is flagged 2
+// and left to k_snn_merge.
 #define SNN_HASH_EMPTY 0xffffffffu
+template <int LOG_SLOTS, int CAP, int STAGE, int WARPS>
+struct SnnHashCfg {
+    static constexpr int log_slots = LOG_SLOTS, slots = 1 << LOG_SLOTS, cap = CAP, stage = STAGE, warps = WARPS;
+};
+using SnnHashSmall = SnnHashCfg<10, 704, 1024, 14>;    // 15.5 KB per warp
+using SnnHashLarge = SnnHashCfg<11, 1408, 2048, 7>;    // 31 KB per warp
+template <class CFG>
 struct SnnHashWarp {
-    uint32_t key[SNN_HASH_SLOTS];    // cell h or EMPTY
-    uint16_t idx[SNN_HASH_SLOTS];    // -> dense entry
-    uint32_t dh[SNN_HASH_CAP];       // dense, in emission order: h
-    uint32_t drc[SNN_HASH_CAP];      // dense: min rank sum | shared count << 16
-    uint32_t stage[SNN_HASH_STAGE];  // the entries (cell < j) of a group of lists, list after list
+    uint32_t key[CFG::slots];    // cell h or EMPTY
+    uint16_t idx[CFG::slots];    // -> dense entry
+    uint32_t dh[CFG::cap];       // dense, in emission order: h
+    uint32_t drc[CFG::cap];      // dense: min rank sum | shared count << 16
+    uint32_t stage[CFG::stage];  // the entries (cell < j) of a group of lists, list after list
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(32 * SNN_HASH_WARPS)
+// MODE 0: count (+ partner slices), MODE 1: emit directly (unused by the host code since k_snn_compact).
+// PASS 0: every cell; PASS 1: only the cells flagged 1 by the previous pass.
+template <int MODE, class CFG, int PASS>
+__global__ void __launch_bounds__(32 * CFG::warps)
 k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
            const int64_t *__restrict__ rptr, const uint32_t *__restrict__ hosts, const int32_t *__restrict__ cut,
            int32_t *__restrict__ ecnt, unsigned char *__restrict__ flagged, const int64_t *__restrict__ eptr,
            int32_t *__restrict__ efrom, int32_t *__restrict__ eto, double *__restrict__ ew,
-           const int64_t *__restrict__ toff, uint32_t *__restrict__ tmp_h, uint32_t *__restrict__ tmp_rc)
+           const int64_t *__restrict__ toff, uint32_t *__restrict__ tmp_h, uint32_t *__restrict__ tmp_rc,
+           const int32_t *__restrict__ tcnt)
 {
     extern __shared__ __align__(16) unsigned char snn_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    SnnHashWarp &T = reinterpret_cast<SnnHashWarp *>(snn_smem)[w];
+    SnnHashWarp<CFG> &T = reinterpret_cast<SnnHashWarp<CFG> *>(snn_smem)[w];
+    constexpr int SNN_HASH_SLOTS = CFG::slots, SNN_HASH_CAP = CFG::cap, SNN_HASH_STAGE = CFG::stage, SNN_HASH_WARPS = CFG::warps;
     const int L = k + 1;
     const int64_t warp0 = (int64_t)blockIdx.x * SNN_HASH_WARPS + w;
     const int64_t nwarps = (int64_t)gridDim.x * SNN_HASH_WARPS;
@@ -314,6 +324,17 @@ k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j
         const int64_t jl = j - j_begin;
         if (MODE == 1 && flagged[jl] != 0)
             continue;
+        if (MODE == 0 && PASS == 1 && flagged[jl] != 1)
+            continue;
+        if (MODE == 0 && PASS == 0 && tcnt != nullptr && tcnt[jl] > 2 * CFG::cap - CFG::cap / 8) {
+            // about half of the staged entries are distinct partners: this cell would most likely overflow
+            // the small table -- straight to the large one
+            if (lane == 0) {
+                ecnt[jl] = 0;
+                flagged[jl] = 1;
+            }
+            continue;
+        }
         // clear the keys
         for (int e = lane * 4; e < SNN_HASH_SLOTS; e += 128)
             *reinterpret_cast<uint4 *>(&T.key[e]) = make_uint4(SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY);
@@ -377,7 +398,7 @@ k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j
                         bool is_new = false;
                         int slot = 0;
                         if (valid) {
-                            slot = (int)((h * 2654435761u) >> 21);              // 11 bits
+                            slot = (int)((h * 2654435761u) >> (32 - CFG::log_slots));
                             while (true) {
                                 const uint32_t kc = T.key[slot];
                                 if (kc == h)
@@ -421,7 +442,7 @@ k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j
         if (MODE == 0) {
             if (lane == 0) {
                 ecnt[jl] = overflow ? 0 : base;
-                flagged[jl] = overflow ? 1 : 0;
+                flagged[jl] = overflow ? (unsigned char)(PASS + 1) : (unsigned char)0;
             }
             if (!overflow && tmp_h != nullptr) {
                 // keep the partners for k_snn_compact: no second pass over the lists.  toff is the scan
@@ -505,16 +526,17 @@ k_snn_compact(int64_t j_begin, int64_t j_end, int k, int type, const int32_t *__
     }
 }
 
-template <int MODE>
+template <int MODE, class CFG, int PASS>
 static int launch_snn_hash(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin,
                            int64_t j_end, int64_t loc)
 {
-    const size_t smem = sizeof(SnnHashWarp) * SNN_HASH_WARPS;
-    CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_hash<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = cb_grid_for(j_end - j_begin, SNN_HASH_WARPS, ctx->num_sms * 8);
-    k_snn_hash<MODE><<<grid, 32 * SNN_HASH_WARPS, smem, ctx->stream>>>(
+    const size_t smem = sizeof(SnnHashWarp<CFG>) * CFG::warps;
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_hash<MODE, CFG, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = cb_grid_for(j_end - j_begin, CFG::warps, ctx->num_sms * 8);
+    k_snn_hash<MODE, CFG, PASS><<<grid, 32 * CFG::warps, smem, ctx->stream>>>(
         d_nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->ecnt.p + loc, ctx->snn_flag.p + loc,
-        ctx->eptr.p + loc, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, ctx->snn_toff.p + loc, ctx->snn_tmp_h.p, ctx->snn_tmp_rc.p);
+        ctx->eptr.p + loc, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, ctx->snn_toff.p + loc, ctx->snn_tmp_h.p, ctx->snn_tmp_rc.p,
+        ctx->snn_tcnt.p + loc);
     CB_LAUNCH(ctx);
     return 0;
 }
@@ -622,7 +644,8 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
         CB_TRY(cb200_read_back(ctx, &ttot, ctx->snn_toff.p + nj, sizeof(int64_t)));
         CB_CUDA(ctx, ctx->snn_tmp_h.ensure((size_t)ttot));
         CB_CUDA(ctx, ctx->snn_tmp_rc.ensure((size_t)ttot));
-        CB_TRY(launch_snn_hash<0>(ctx, d_nn, n, k, type, j_begin, j_end, 0));
+        CB_TRY((launch_snn_hash<0, SnnHashSmall, 0>(ctx, d_nn, n, k, type, j_begin, j_end, 0)));
+        CB_TRY((launch_snn_hash<0, SnnHashLarge, 1>(ctx, d_nn, n, k, type, j_begin, j_end, 0)));
         launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_flag.p);
     } else {
         launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0);
