@@ -172,6 +172,7 @@ struct cb200_ctx {
     DevBuf<int32_t> snn_tcnt;         // [nj] upper bound of the partners of every cell
     DevBuf<int64_t> snn_toff;         // [nj+1] its scan: slices of the partner store
     DevBuf<uint32_t> snn_tmp_h, snn_tmp_rc;  // partner store written by the counting pass, read by the emission
+    DevBuf<int32_t> snn_jlist;        // [nj + 1] cells left to the merge kernel (+ their count)
     DevBuf<unsigned char> snn_flag;   // [nj] cells left to the merge kernel (too many partners for the hash table)
 
     // ---- cluster diagnostics (cb200_diag.cu)

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256)
 k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
             const int64_t *__restrict__ rptr, const uint32_t *__restrict__ hosts, int32_t *__restrict__ ecnt,
             int32_t *__restrict__ bcnt, const int64_t *__restrict__ eptr, int32_t *__restrict__ efrom,
-            int32_t *__restrict__ eto, double *__restrict__ ew, const unsigned char *__restrict__ only_flagged)
+            int32_t *__restrict__ eto, double *__restrict__ ew, const int32_t *__restrict__ jlist,
+            const int *__restrict__ nlist)
 {
     constexpr int CH = SnnChunk<SLOTS>::value;
     __shared__ uint32_t stage[8][SNN_SMEM_WORDS];
@@ -127,10 +128,11 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
     const int L = k + 1;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t j = j_begin + warp0; j < j_end; j += nwarps) {
-        const int64_t jl = j - j_begin;
-        if (only_flagged != nullptr && only_flagged[jl] == 0)
-            continue;   // handled by k_snn_hash
+    // either every cell of [j_begin, j_end), or the cells j_begin + jlist[0 .. *nlist) (the ones k_snn_hash left)
+    const int64_t n_items = jlist != nullptr ? (int64_t)*nlist : j_end - j_begin;
+    for (int64_t it = warp0; it < n_items; it += nwarps) {
+        const int64_t jl = jlist != nullptr ? (int64_t)jlist[it] : it;
+        const int64_t j = j_begin + jl;
         int64_t gptr[SLOTS], gend[SLOTS];   // next entry not yet staged / end of the list
         int hpos[SLOTS], hcnt[SLOTS];       // position in / size of the staged chunk
         uint32_t head[SLOTS];
@@ -545,21 +547,29 @@ static int launch_snn_hash(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k
 // loc = j_begin - (first cell of that range)
 template <int MODE>
 static void launch_snn_merge(cb200_ctx *ctx, int grid, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin,
-                             int64_t j_end, int64_t loc, const unsigned char *flagged = nullptr)
+                             int64_t j_end, int64_t loc, const int32_t *jlist = nullptr, const int *nlist = nullptr)
 {
     const int32_t *nn = d_nn;
     int32_t *ecnt = ctx->ecnt.p + loc, *bcnt = ctx->bcnt.p + loc * (k + 1);
     int64_t *eptr = ctx->eptr.p + loc;
-    const unsigned char *flg = flagged != nullptr ? flagged + loc : nullptr;
     if (k + 1 <= 32)
         k_snn_merge<MODE, 1><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, flg);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, jlist, nlist);
     else if (k + 1 <= 64)
         k_snn_merge<MODE, 2><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, flg);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, jlist, nlist);
     else
         k_snn_merge<MODE, 4><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
-                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, flg);
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, jlist, nlist);
+}
+
+// the cells k_snn_hash could not hold (flag 2), as a list: one warp of k_snn_merge each
+__global__ void k_snn_flag_list(const unsigned char *__restrict__ flagged, int64_t nj, int32_t *__restrict__ jlist,
+                                int *__restrict__ nlist)
+{
+    const int64_t jl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (jl < nj && flagged[jl] == 2)
+        jlist[atomicAdd(nlist, 1)] = (int32_t)jl;
 }
 
 // cell boundaries of SNN_CHUNKS pieces with about equal numbers of edges: out[2c] = first local cell of
@@ -646,7 +656,12 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
         CB_CUDA(ctx, ctx->snn_tmp_rc.ensure((size_t)ttot));
         CB_TRY((launch_snn_hash<0, SnnHashSmall, 0>(ctx, d_nn, n, k, type, j_begin, j_end, 0)));
         CB_TRY((launch_snn_hash<0, SnnHashLarge, 1>(ctx, d_nn, n, k, type, j_begin, j_end, 0)));
-        launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_flag.p);
+        CB_CUDA(ctx, ctx->snn_jlist.ensure((size_t)nj + 1));
+        int *nlist = reinterpret_cast<int *>(ctx->snn_jlist.p + nj);
+        CB_CUDA(ctx, cudaMemsetAsync(nlist, 0, sizeof(int), ctx->stream));
+        k_snn_flag_list<<<(unsigned)((nj + 255) / 256), 256, 0, ctx->stream>>>(ctx->snn_flag.p, nj, ctx->snn_jlist.p, nlist);
+        CB_LAUNCH(ctx);
+        launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_jlist.p, nlist);
     } else {
         launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0);
     }
@@ -697,6 +712,15 @@ static int snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight)
     CB_CUDA(ctx, ctx->ew8.ensure((size_t)ne));
     const bool out = from != nullptr && to != nullptr && weight != nullptr;
     const int64_t *bd = ctx->snn_bounds_h;
+    if (ctx->snn_use_hash) {
+        // the few cells left to the merge kernel first, in one launch over their list (their edges land at
+        // their final offsets); the pieces below then only compact and copy
+        const int64_t nj = ctx->snn_jend - ctx->snn_jbegin;
+        const int gm = cb_grid_for(nj, 8, ctx->num_sms * 16);
+        launch_snn_merge<1>(ctx, gm, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin, ctx->snn_jend, 0,
+                            ctx->snn_jlist.p, reinterpret_cast<int *>(ctx->snn_jlist.p + nj));
+        CB_LAUNCH(ctx);
+    }
     for (int c = 0; c < SNN_CHUNKS; ++c) {
         const int64_t ja = bd[2 * c], jb = bd[2 * c + 2], ea = bd[2 * c + 1], eb = bd[2 * c + 3];
         if (jb <= ja)
@@ -707,9 +731,6 @@ static int snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight)
                                                        ctx->ecnt.p, ctx->snn_flag.p, ctx->eptr.p, ctx->snn_toff.p,
                                                        ctx->snn_tmp_h.p, ctx->snn_tmp_rc.p, ctx->efrom.p, ctx->eto.p,
                                                        ctx->ew8.p, ctx->snn_jbegin);
-            CB_LAUNCH(ctx);
-            launch_snn_merge<1>(ctx, g3, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
-                                ctx->snn_jbegin + jb, ja, ctx->snn_flag.p);
         } else {
             launch_snn_merge<1>(ctx, g3, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
                                 ctx->snn_jbegin + jb, ja);
