@@ -207,6 +207,7 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     launches = tm["kernel_launches"]
+    resident_marks = dict(pipe.last_marks)   # host wall-clock split of the last resident step (rank 0's is printed)
     dev_ms = ev0.elapsed_time(ev1) / args.steps
     n_edges_local = int(res["edges"])
     fallback_q = tm["knn_fallback_queries"]
@@ -324,7 +325,7 @@ def main():
                                 knn_tiles_scanned_rank0=int(tiles_scanned), knn_tiles_total_rank0=int(tiles_total),
                                 engines=engines, size_factors="library"),
                     clocks=sampler.summary(), gpu_launches=launches_all // max(args.steps, 1) * args.steps,
-                    stage_ms=stage_ms, hbm_stages=hbm, roofline=roofline)
+                    stage_ms=stage_ms, host_marks_ms_last_step_rank0=resident_marks, hbm_stages=hbm, roofline=roofline)
         if e2e:
             line["e2e"] = dict(value=w["cells"] / (e2e_ms * 1e-3), unit="cells/s", ms_per_step=e2e_ms,
                                h2d_bytes_per_step=h2d_all, d2h_bytes_per_step=d2h_all,

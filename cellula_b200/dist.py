@@ -10,14 +10,17 @@ small exchanges the path needs:
     PCA            all-reduce  H x H cross-product                      (H^2 doubles)
                    all-gather  scores (N x d doubles)
     kNN            all-gather  neighbour index (N x k int32)
-    SNN            none: every rank emits the edges of its own cells j (ascending j), so the
-                   concatenation in rank order is the single-GPU edge list.
+    SNN            none: every rank emits the edges of a contiguous range of cells j (ascending j; the ranges
+                   are balanced by work, `snn_bounds`), so the concatenation in rank order is the single-GPU
+                   edge list.
 
 `ShardedPipeline` only talks to a *shard backend* (the methods of `CudaShard`) and to
 `torch.distributed`, so the same driver runs on CPU with the gloo backend and a test double as
 backend (tests/test_dist_gloo.py) -- that is how the N>1 host logic is covered without GPUs.
 """
 from __future__ import annotations
+
+import math
 
 import numpy as np
 import torch
@@ -33,6 +36,17 @@ def shard_bounds(n_total: int, world: int):
     for r in range(world):
         bounds.append(bounds[-1] + base + (1 if r < rem else 0))
     return bounds
+
+
+def snn_bounds(n_total: int, world: int):
+    """Contiguous ranges of cells j for the SNN stage with about equal WORK per rank.  A cell j is joined to
+    partners h < j only, so its edge count (and its share of the list scanning) grows like j: equal work
+    means boundaries at N sqrt(r / R), not N r / R.  Any contiguous split keeps the contract that the
+    concatenation in rank order is the single-GPU edge list."""
+    b = [int(round(int(n_total) * math.sqrt(r / world))) for r in range(world)] + [int(n_total)]
+    for r in range(1, world + 1):          # strictly increasing even for tiny inputs
+        b[r] = min(max(b[r], b[r - 1] + 1), int(n_total) - (world - r))
+    return b
 
 
 def slice_csc(colptr, rowidx, x, c0, c1):
@@ -133,6 +147,8 @@ class ShardedPipeline:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bounds = shard_bounds(self.n_total, self.world)
         self.c0, self.c1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        sb = snn_bounds(self.n_total, self.world)
+        self.j0, self.j1 = sb[self.rank], sb[self.rank + 1]     # cells whose SNN edges this rank emits
 
     # -- collectives ---------------------------------------------------------------
     def _allreduce(self, t):
@@ -186,10 +202,10 @@ class ShardedPipeline:
 
     def snn(self, knn_full, snn_type, fetch=True, edge_buffers=None):
         if fetch and edge_buffers is not None:
-            return self.shard.snn(knn_full, snn_type, self.c0, self.c1, fetch=True, edge_buffers=edge_buffers)
+            return self.shard.snn(knn_full, snn_type, self.j0, self.j1, fetch=True, edge_buffers=edge_buffers)
         if fetch:
-            return self.shard.snn(knn_full, snn_type, self.c0, self.c1)
-        return self.shard.snn(knn_full, snn_type, self.c0, self.c1, fetch=False)
+            return self.shard.snn(knn_full, snn_type, self.j0, self.j1)
+        return self.shard.snn(knn_full, snn_type, self.j0, self.j1, fetch=False)
 
     def run(self, ndims=50, hvg_ntop=2000, neighbors=20, snn_type="rank", sf_in=None, want_host=True,
             scores_out=None, edge_buffers=None, logx_out=None):
