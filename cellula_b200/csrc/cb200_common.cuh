@@ -131,6 +131,7 @@ struct cb200_ctx {
     DevBuf<int32_t> knn_cl_tile_begin;       // [C+1] first (padded) tile of every cluster
     DevBuf<int64_t> knn_pad_before;          // [C] padding positions ahead of the cluster
     DevBuf<uint16_t> knn_cl_order;           // [C*C] clusters by ascending centre distance from cluster h
+    DevBuf<double> knn_eperm;  // [npos*d] the embedding in sorted order (rows of the padding positions are 0)
     DevBuf<unsigned char> knn_img;  // tensor-core operand image of the references (cb200_knn_tc.cu)
     DevBuf<float> hnorm;       // [n_total]   0.5*|r|^2 (fp32)
     DevBuf<double> nrm2;       // [n_total]   |r|^2 (fp64)

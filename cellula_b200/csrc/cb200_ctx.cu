@@ -106,7 +106,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->mu.release(); ctx->eq.release(); ctx->ew.release(); ctx->ey.release(); ctx->ex.release();
     ctx->es.release(); ctx->et.release(); ctx->etheta.release(); ctx->eres.release();
     ctx->emuv.release(); ctx->egs.release(); ctx->rot.release(); ctx->scores.release(); ctx->varexp.release();
-    ctx->emb.release(); ctx->stage_d.release(); ctx->emb_f.release(); ctx->knn_img.release(); ctx->knn_perm.release(); ctx->knn_bkt.release(); ctx->knn_hist.release();
+    ctx->emb.release(); ctx->stage_d.release(); ctx->emb_f.release(); ctx->knn_img.release(); ctx->knn_eperm.release(); ctx->knn_perm.release(); ctx->knn_bkt.release(); ctx->knn_hist.release();
     ctx->knn_qlist.release(); ctx->knn_qpos.release(); ctx->knn_cursor.release(); ctx->knn_qoff.release();
     ctx->knn_tile_lo.release(); ctx->knn_tile_hi.release(); ctx->hnorm.release();
     ctx->knn_cen.release(); ctx->knn_km_sums.release(); ctx->knn_km_cnt.release(); ctx->knn_dqc.release();

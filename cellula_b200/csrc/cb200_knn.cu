@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(256)
 k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, int64_t nq, int k,
              const int32_t *__restrict__ cand_idx, const float *__restrict__ cand_tau, int ntau, const double *__restrict__ nrm2,
              const unsigned long long *__restrict__ maxbits, double err_coef, const float *__restrict__ cand_err,
-             const int32_t *__restrict__ qlist,
+             const int32_t *__restrict__ qlist, const double *__restrict__ eperm, const int32_t *__restrict__ perm,
+             const int32_t *__restrict__ qpos,
              int32_t *__restrict__ knn, double *__restrict__ knn_dk, int32_t *__restrict__ fb_list,
              int *__restrict__ fb_count)
 {
@@ -279,15 +280,29 @@ k_knn_rerank(const double *__restrict__ E, int64_t lde, int d, int64_t q_begin, 
         // q runs over the candidate records; the tensor-core engine orders them by PC 1 (qlist)
         const int64_t grow = qlist != nullptr ? (int64_t)qlist[q] : q_begin + q;
         const int64_t orow = grow - q_begin;   // row of the result
-        const double *qa = E + grow * lde;
+        // tensor-core engine: the candidates are sorted POSITIONS and the rows are read from the copy of the
+        // embedding in sorted order (same values; queries that follow each other share most candidates, so
+        // the gathers hit L2); the original index -- the tie-break and the result -- comes from perm
+        const double *qa = eperm != nullptr ? eperm + (int64_t)qpos[q] * d : E + grow * lde;
         double key[EPL];
         int idx[EPL];
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
-            const int ci = cand_idx[q * KP + e * 32 + lane];
+            int ci = cand_idx[q * KP + e * 32 + lane];
+            int oi = ci;
+            if (eperm != nullptr && ci >= 0) {
+                oi = perm[ci];
+                if (oi < 0)
+                    ci = -1;   // a padding position (only kept while fewer than KP references were seen)
+            }
             if (ci >= 0) {
-                key[e] = exact_dist(qa, E + (int64_t)ci * lde, d);
-                idx[e] = ci;
+                if (eperm != nullptr) {
+                    key[e] = exact_dist(qa, eperm + (int64_t)ci * d, d);
+                    idx[e] = oi;
+                } else {
+                    key[e] = exact_dist(qa, E + (int64_t)ci * lde, d);
+                    idx[e] = ci;
+                }
             } else {
                 key[e] = DBL_MAX;
                 idx[e] = 0x7fffffff;
@@ -433,7 +448,9 @@ static int run_rerank(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, i
     const int rgrid = cb_grid_for(nq, 8, ctx->num_sms * 16);
     k_knn_rerank<KP><<<rgrid, 256, 0, ctx->stream>>>(E, lde, d, q_begin, nq, k, ctx->cand_idx.p, ctx->cand_tau.p,
                                                      ntau, ctx->nrm2.p, ctx->maxnrm.p, err_coef,
-                                                     err_coef < 0.0 ? ctx->cand_err.p : nullptr, qlist, ctx->knn.p, ctx->knn_dk.p,
+                                                     err_coef < 0.0 ? ctx->cand_err.p : nullptr, qlist,
+                                                     err_coef < 0.0 ? ctx->knn_eperm.p : nullptr, ctx->knn_perm.p, ctx->knn_qpos.p,
+                                                     ctx->knn.p, ctx->knn_dk.p,
                                                      ctx->fb_list.p, ctx->flag.p + 2);
     CB_LAUNCH(ctx);
     int h[2] = {0, 0};

@@ -308,8 +308,8 @@ __global__ void k_knn_tc_qscatter(const int32_t *__restrict__ perm, const int32_
 __global__ void __launch_bounds__(128)
 k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, const int32_t *__restrict__ perm,
               const float *__restrict__ rho, const int32_t *__restrict__ cl, const double *__restrict__ cen,
-              unsigned char *__restrict__ img, double *__restrict__ nrm2, unsigned long long *__restrict__ maxbits,
-              float *__restrict__ tile_lo, float *__restrict__ tile_hi)
+              unsigned char *__restrict__ img, double *__restrict__ eperm, double *__restrict__ nrm2,
+              unsigned long long *__restrict__ maxbits, float *__restrict__ tile_lo, float *__restrict__ tile_hi)
 {
     __shared__ float smin[4], smax[4];
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // sorted position
@@ -332,6 +332,16 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, co
         const uint32_t off = swz_offset(row, t * 2);
         *reinterpret_cast<__half *>(reinterpret_cast<unsigned char *>(hi_base) + off) = h;
         *reinterpret_cast<__half *>(reinterpret_cast<unsigned char *>(lo_base) + off) = l;
+    }
+    // the embedding in sorted order (k_knn_rerank reads it): one row per warp pass, lanes over the coordinates
+    {
+        const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+        for (int r = wid * 32; r < wid * 32 + 32; ++r) {
+            const int64_t pos = blockIdx.x * (int64_t)blockDim.x + r;
+            const int64_t sr = (int64_t)__shfl_sync(0xffffffffu, (int)src, r & 31);
+            for (int t = ln; t < d; t += 32)
+                eperm[pos * d + t] = sr >= 0 ? E[sr * lde + t] : 0.0;
+        }
     }
     // -0.5|r~|^2 in the three spare K columns of the hi part
     __half a1, a2, a3;
@@ -1079,7 +1089,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         if (myql < nq) {
             int32_t *out = cand_idx + myql * (int64_t)cand_stride;
             for (int p = 0; p < cand_stride; ++p)
-                out[p] = (p < KP && p >= KP - cnt) ? perm[mi[p * TC_M]] : -1;
+                out[p] = (p < KP && p >= KP - cnt) ? mi[p * TC_M] : -1;   // sorted positions: k_knn_rerank maps them through perm
             cand_tau[myql] = (cnt < KP) ? FLT_MAX : -root * key_unscale;
         }
     } else {
@@ -1262,6 +1272,7 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     const int CAND = KP == 112 ? 128 : KP;   // the re-rank sorts a power of two: padded with empty entries
     CB_CUDA(ctx, ctx->knn_img.ensure((size_t)n_tiles_cap * TC_TILE_BYTES));
     CB_CUDA(ctx, ctx->nrm2.ensure((size_t)n));
+    CB_CUDA(ctx, ctx->knn_eperm.ensure((size_t)npos * d));
     CB_CUDA(ctx, ctx->cand_idx.ensure((size_t)nq * CAND));
     CB_CUDA(ctx, ctx->cand_tau.ensure((size_t)nq));
     CB_CUDA(ctx, ctx->cand_err.ensure((size_t)nq));
@@ -1342,7 +1353,7 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     CB_CUDA(ctx, cudaMemsetAsync(ctx->maxnrm.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     k_knn_tc_prep<<<(unsigned)n_tiles_cap, 128, 0, ctx->stream>>>(E, lde, d, scale, ctx->knn_perm.p, ctx->knn_rho.p,
                                                                   ctx->knn_cl.p, ctx->knn_cen.p, ctx->knn_img.p,
-                                                                  ctx->nrm2.p, ctx->maxnrm.p, ctx->knn_tile_lo.p,
+                                                                  ctx->knn_eperm.p, ctx->nrm2.p, ctx->maxnrm.p, ctx->knn_tile_lo.p,
                                                                   ctx->knn_tile_hi.p);
     CB_LAUNCH(ctx);
     // the query list: the cells of [q_begin, q_end) in sorted order, with their sorted positions
