@@ -216,6 +216,46 @@ static bool solve3(const double a[3][3], const double g[3], double x[3])
     return std::isfinite(x[0]) && std::isfinite(x[1]) && std::isfinite(x[2]);
 }
 
+// Grid search of scran's .get_nls_starts (fitTrendVar): rss[n][b] = sum_i (v_i - grad b m_i / (m_i^n + b))^2 over
+// the 10 x 10 grid of (n, b) values; the first minimum in expand.grid order (b fastest) is returned.
+extern "C" int cb200_host_nls_grid(int64_t n64, const double *v, const double *m, double grad, int nb, const double *bgrid,
+                                   int nn, const double *ngrid, int *ib_out, int *in_out)
+{
+    const int n = (int)n64;
+    if (n < 1 || v == nullptr || m == nullptr || bgrid == nullptr || ngrid == nullptr || nb < 1 || nn < 1 || nb > 64)
+        return 1;
+    std::vector<double> mp((size_t)n);
+    double best = 0.0;
+    int bi = -1, bn = -1;
+    for (int a = 0; a < nn; ++a) {
+        for (int i = 0; i < n; ++i)
+            mp[i] = std::pow(m[i], ngrid[a]);
+        double rss[64];
+        for (int b = 0; b < nb; ++b)
+            rss[b] = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double gm = m[i], vi = v[i], p = mp[i];
+            for (int b = 0; b < nb; ++b) {
+                const double r = vi - grad * bgrid[b] * gm / (p + bgrid[b]);
+                rss[b] += r * r;
+            }
+        }
+        for (int b = 0; b < nb; ++b) {
+            // NaN never wins; ties keep the earlier grid point (argmin over the flattened [n][b] array)
+            if (rss[b] == rss[b] && (bi < 0 || rss[b] < best)) {
+                best = rss[b];
+                bi = b;
+                bn = a;
+            }
+        }
+    }
+    if (bi < 0)
+        return 2;
+    *ib_out = bi;
+    *in_out = bn;
+    return 0;
+}
+
 // A few worker threads for the passes over the G genes (each pass is ~G exp() calls; the fit makes dozens).
 // Static partition, partial sums combined in chunk order: the result does not depend on timing.
 namespace {

@@ -62,6 +62,14 @@ def _start_values(v, m):
     grad = float(m[keep] @ v[keep]) / float(m[keep] @ m[keep])
     bgrid = 2.0 ** np.linspace(-5, 5, 10)
     ngrid = 2.0 ** np.linspace(0, 10, 10)
+    native = _native("cb200_host_nls_grid")
+    if native is not None:   # same sums in C++ (csrc/cb200_host.cu): no 10 x 10 x G temporaries
+        import ctypes
+        vc, mc = np.ascontiguousarray(v), np.ascontiguousarray(m)
+        ib, inn = ctypes.c_int(), ctypes.c_int()
+        if native(v.size, vc.ctypes.data, mc.ctypes.data, grad, 10, bgrid.ctypes.data, 10, ngrid.ctypes.data,
+                  ctypes.addressof(ib), ctypes.addressof(inn)) == 0:
+            return bgrid[ib.value] * grad, bgrid[ib.value], ngrid[inn.value]
     with np.errstate(over="ignore"):
         mp = m[None, :] ** ngrid[:, None]                                   # [n-grid, genes]
         pred = grad * bgrid[None, :, None] * m[None, None, :] / (mp[:, None, :] + bgrid[None, :, None])

@@ -236,6 +236,9 @@ int cb200_host_weighted_lowess(int64_t n, const double *x_sorted, const double *
  * v ~ exp(A) m / (m^(1+exp(N)) + exp(B)), theta = (A, B, N) updated in place from its start value. */
 int cb200_host_nls_trend(int64_t n, const double *v, const double *m, const double *w, double *theta, double tol,
                          int maxiter);
+/* grid search for the start values of the parametric trend (scran's .get_nls_starts); first minimum, b fastest */
+int cb200_host_nls_grid(int64_t n, const double *v, const double *m, double grad, int nb, const double *bgrid, int nn,
+                        const double *ngrid, int *ib_out, int *in_out);
 int cb200_host_gauss_kde(int64_t n, const double *m, double bw, double lo, double hi, int ng, double *dens_out);
 
 #ifdef __cplusplus
