@@ -78,3 +78,17 @@ def test_host_trend_agrees_with_oracle_restatement(small_counts):
     # trend properties: positive where the mean is positive, zero at zero
     tr, sd = trendvar.fit_trend_var(mean, var)
     assert sd > 0 and tr(np.array([0.0]))[0] == 0.0 and np.all(tr(np.linspace(0.01, 5, 50)) > 0)
+
+
+def test_snn_bounds_balance_and_cover():
+    """SNN cell ranges of the sharded pipeline: contiguous, strictly increasing, covering [0, N), and with
+    about equal numbers of (j, h < j) pairs per rank (work grows like j)."""
+    from cellula_b200.dist import shard_bounds, snn_bounds
+    for n, world in [(1306127, 8), (1306127, 3), (100, 4), (5, 4), (7, 1)]:
+        b = snn_bounds(n, world)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1
+        assert all(b[r] < b[r + 1] for r in range(world))
+        assert shard_bounds(n, world)[-1] == n
+    b = snn_bounds(1306127, 8)
+    work = [b[r + 1] ** 2 - b[r] ** 2 for r in range(8)]
+    assert max(work) / min(work) < 1.001
