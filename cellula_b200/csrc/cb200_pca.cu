@@ -51,7 +51,17 @@ __global__ void __launch_bounds__(256) k_hvg_count(const int64_t *__restrict__ c
     for (int64_t c = warp0; c < n_cols; c += nwarps) {
         const int64_t b = colptr[c], e = colptr[c + 1];
         int cnt = 0;
-        for (int64_t i = b + lane; i < e; i += 32)
+        int64_t i = b + lane;
+        for (; i + 96 < e; i += 128) {
+            int g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                g[u] = ld_stream_i(rowidx + i + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                cnt += (slot[g[u]] >= 0) ? 1 : 0;
+        }
+        for (; i < e; i += 32)
             cnt += (slot[rowidx[i]] >= 0) ? 1 : 0;
         cnt = warp_sum_i(cnt);
         if (lane == 0)
@@ -71,21 +81,32 @@ k_hvg_fill(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowid
     for (int64_t c = warp0; c < n_cols; c += nwarps) {
         const int64_t b = colptr[c], e = colptr[c + 1];
         int64_t out = hptr[c];
-        for (int64_t i0 = b; i0 < e; i0 += 32) {
-            const int64_t i = i0 + lane;
-            int s = -1;
-            double v = 0.0;
-            if (i < e) {
-                s = slot[rowidx[i]];
-                v = logx[i];
+        // 128 entries per pass: the four row-index loads, then the four slot look-ups, then the (few) value
+        // loads are each issued back to back; the values of non-HVG rows are never read
+        for (int64_t i0 = b; i0 < e; i0 += 128) {
+            int g[4], s[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + 32 * u + lane;
+                g[u] = i < e ? ld_stream_i(rowidx + i) : -1;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, s >= 0);
-            if (s >= 0) {
-                const int64_t o = out + __popc(m & ((1u << lane) - 1u));
-                hslot[o] = s;
-                hval[o] = v;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                s[u] = g[u] >= 0 ? slot[g[u]] : -1;
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                v[u] = s[u] >= 0 ? logx[i0 + 32 * u + lane] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned m = __ballot_sync(0xffffffffu, s[u] >= 0);
+                if (s[u] >= 0) {
+                    const int64_t o = out + __popc(m & ((1u << lane) - 1u));
+                    hslot[o] = s[u];
+                    hval[o] = v[u];
+                }
+                out += __popc(m);
             }
-            out += __popc(m);
         }
     }
 }
