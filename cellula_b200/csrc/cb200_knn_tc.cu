@@ -429,7 +429,8 @@ template <int KP, int STAGES, int QCAP, int NQB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, const unsigned char *__restrict__ img,
                int64_t nq, const int32_t *__restrict__ qlist, const int32_t *__restrict__ qpos,
-               const int32_t *__restrict__ perm, int C, const double *__restrict__ cen, const float *__restrict__ dqc,
+               const int32_t *__restrict__ perm, const double *__restrict__ eperm, int C, const double *__restrict__ cen,
+               const float *__restrict__ dqc,
                const int32_t *__restrict__ cl, const uint16_t *__restrict__ cl_order,
                const int32_t *__restrict__ cl_tile_begin, const unsigned int *__restrict__ cl_rhomax,
                const float *__restrict__ tile_lo, const float *__restrict__ tile_hi, float key_unscale, int cand_stride,
@@ -1098,7 +1099,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         // the whole warp (lane = coordinate: coalesced), several rows in flight =====
         const int bw = warp - (2 + TC_SCAN_SETS * 4 + 4);
         const int64_t rowq = ql0 + bw * 32 + lane;
-        const int my_g = rowq < nq ? qlist[rowq] : -1;   // lane r: original index of row 32 bw + r
+        const int my_p = rowq < nq ? qpos[rowq] : -1;    // lane r: sorted position of row 32 bw + r
         bool pf_served = false;
         for (int visit = 0;; ++visit) {
             const int b = visit % NQB, use = visit / NQB;
@@ -1143,37 +1144,40 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             if (bw == 0 && lane == 0)
                 TL(4, ((long long)visit << 8) | 2);
             const double *cj = cen + (size_t)j * d;
-            const double c0 = lane < d ? cj[lane] : 0.0, c1 = lane + 32 < d ? cj[lane + 32] : 0.0;
+            // lane = the column pair (2 lane, 2 lane + 1): one packed 32-bit store per part and row
+            const int t0 = 2 * lane, t1 = 2 * lane + 1;
+            const double c0 = t0 < d ? cj[t0] : 0.0, c1 = t1 < d ? cj[t1] : 0.0;
             unsigned char *qb = q_img + (size_t)b * TC_TILE_BYTES;
             // constants of the columns past the coordinates: [2^12, 1, 2^-12] (hi part), 0 elsewhere
-            float k0 = 0.f, k1 = 0.f;
-            if (lane == d) k0 = 4096.f; else if (lane == d + 1) k0 = 1.f; else if (lane == d + 2) k0 = 1.0f / 4096.f;
-            if (lane + 32 == d) k1 = 4096.f; else if (lane + 32 == d + 1) k1 = 1.f; else if (lane + 32 == d + 2) k1 = 1.0f / 4096.f;
+            auto kconst = [&](int t) { return t == d ? 4096.f : (t == d + 1 ? 1.f : (t == d + 2 ? 1.0f / 4096.f : 0.f)); };
+            const float k0 = kconst(t0), k1 = kconst(t1);
+            const uint32_t lane_chunk = (uint32_t)(lane >> 2), lane_byte = (uint32_t)((lane * 4) & 15);
 #pragma unroll 1
             for (int r0 = 0; r0 < 32; r0 += 8) {
                 double x0[8], x1[8];
-                int gr[8];
+                int ps[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    gr[u] = __shfl_sync(0xffffffffu, my_g, r0 + u);
-                    const double *qrow = E + (int64_t)(gr[u] < 0 ? 0 : gr[u]) * lde;
-                    x0[u] = (gr[u] >= 0 && lane < d) ? qrow[lane] : 0.0;
-                    x1[u] = (gr[u] >= 0 && lane + 32 < d) ? qrow[lane + 32] : 0.0;
+                    ps[u] = __shfl_sync(0xffffffffu, my_p, r0 + u);
+                    const double *qrow = eperm + (int64_t)(ps[u] < 0 ? 0 : ps[u]) * d;   // the sorted-order copy
+                    x0[u] = (ps[u] >= 0 && t0 < d) ? qrow[t0] : 0.0;
+                    x1[u] = (ps[u] >= 0 && t1 < d) ? qrow[t1] : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int row = bw * 32 + r0 + u;
-                    __half h0 = __float2half(gr[u] >= 0 ? k0 : 0.f), l0 = __float2half(0.f);
-                    __half h1 = __float2half(gr[u] >= 0 ? k1 : 0.f), l1 = __float2half(0.f);
-                    if (gr[u] >= 0 && lane < d)
+                    __half h0 = __float2half(ps[u] >= 0 ? k0 : 0.f), l0 = __float2half(0.f);
+                    __half h1 = __float2half(ps[u] >= 0 ? k1 : 0.f), l1 = __float2half(0.f);
+                    if (ps[u] >= 0 && t0 < d)
                         split_h(x0[u] * scale - c0, h0, l0);
-                    if (gr[u] >= 0 && lane + 32 < d)
+                    if (ps[u] >= 0 && t1 < d)
                         split_h(x1[u] * scale - c1, h1, l1);
-                    const uint32_t o0 = swz_offset(row, lane * 2), o1 = swz_offset(row, (lane + 32) * 2);
-                    *reinterpret_cast<__half *>(qb + o0) = h0;
-                    *reinterpret_cast<__half *>(qb + TC_PART_BYTES + o0) = l0;
-                    *reinterpret_cast<__half *>(qb + o1) = h1;
-                    *reinterpret_cast<__half *>(qb + TC_PART_BYTES + o1) = l1;
+                    const uint32_t o = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128) +
+                                       (((lane_chunk ^ (uint32_t)(row & 7)) & 7u) << 4) + lane_byte;
+                    const uint32_t hp = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    const uint32_t lp = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                    *reinterpret_cast<uint32_t *>(qb + o) = hp;
+                    *reinterpret_cast<uint32_t *>(qb + TC_PART_BYTES + o) = lp;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core reads
@@ -1209,7 +1213,8 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
         CB_CUDA(ctx, cudaMemsetAsync(dbg, 0, (size_t)5 * 4096 * 2 * sizeof(long long), ctx->stream));
     }
     k_knn_tiles_tc<KP, STAGES, QCAP, NQB><<<grid, TC_THREADS, smem, ctx->stream>>>(
-        E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, C, ctx->knn_cen.p,
+        E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, ctx->knn_eperm.p, C,
+        ctx->knn_cen.p,
         ctx->knn_dqc.p, ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p,
         ctx->knn_tile_lo.p, ctx->knn_tile_hi.p, key_unscale, cand_stride, ctx->cand_idx.p, ctx->cand_tau.p,
         ctx->cand_err.p, ctx->flag.p + 3, ctx->maxnrm.p + 3, dbg);
