@@ -226,7 +226,7 @@ class ShardedPipeline:
         marks.append(("gene_stats", time.perf_counter()))
         if logx_out is not None and not hasattr(self.shard, "lognorm_values"):
             self.shard.logcounts_async(logx_out)            # overlaps the trend fit, PCA, kNN and SNN
-        stats = trendvar.model_gene_var(mean, var)          # replicated host step (R: scran::fitTrendVar)
+        stats = trendvar.model_gene_var(mean, var, want_pvalues=False)   # replicated host step (R: scran::fitTrendVar)
         hvgs = trendvar.get_top_hvgs(stats, hvg_ntop)
         marks.append(("trend_hvg", time.perf_counter()))
         pca = self.pca(hvgs, ndims, want_scores=want_host, scores_out=scores_out if want_host else None)

@@ -251,13 +251,17 @@ def fit_trend_var(means, variances, min_mean=0.1):
     return trend, std_dev
 
 
-def model_gene_var(means, variances):
-    """scran::modelGeneVar's DataFrame columns from per-gene mean / total variance."""
+def model_gene_var(means, variances, want_pvalues=True):
+    """scran::modelGeneVar's DataFrame columns from per-gene mean / total variance.
+    want_pvalues=False skips p.value / FDR: cellula only feeds the table to getTopHVGs(), which ranks by
+    `bio` (R/doNormAndReduce.R:88-91), so the sharded pipeline does not spend host time on them."""
     means = np.asarray(means, dtype=np.float64)
     variances = np.asarray(variances, dtype=np.float64)
     trend, std_dev = fit_trend_var(means, variances)
     tech = trend(means)
     bio = variances - tech
+    if not want_pvalues:
+        return dict(mean=means, total=variances, tech=tech, bio=bio)
     with np.errstate(divide="ignore", invalid="ignore"):
         ratio = variances / tech
     p = np.where(np.isfinite(ratio), ndtr(-(ratio - 1.0) / std_dev), np.nan)
