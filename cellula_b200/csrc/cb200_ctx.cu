@@ -332,6 +332,7 @@ extern "C" int cb200_synchronize(cb200_ctx *ctx)
 {
     if (ctx == nullptr)
         return 1;
+    CB_TRY(cb200_need_rowidx(ctx));   // the upload of the row indices runs on its own stream
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
