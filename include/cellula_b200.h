@@ -101,7 +101,8 @@ int cb200_device_ptr(cb200_ctx *ctx, int which, void **ptr, int64_t *bytes);
  * colptr is int64[n_cells+1]; cb200_load_csc_i32 takes dgCMatrix's own int32 `p` slot.
  * rowidx int32[nnz] 0-based gene index, sorted within a column; values double[nnz].
  * cell_offset / n_cells_total describe the shard: this context holds global cells
- * [cell_offset, cell_offset + n_cells); single GPU: 0 and n_cells.  * The copies are asynchronous when the host arrays are page-locked (values first, row indices behind them on
+ * [cell_offset, cell_offset + n_cells); single GPU: 0 and n_cells.
+ * The copies are asynchronous when the host arrays are page-locked (values first, row indices behind them on
  * their own stream): keep the arrays valid until cb200_lognorm_genestats[_local] or cb200_synchronize has returned. */
 int cb200_load_csc(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, const int64_t *colptr,
                    const int32_t *rowidx, const double *values, int64_t cell_offset,
