@@ -311,8 +311,11 @@ def main():
                         executed_tflops=(tiles_scanned * 3 * 2.0 * 128 * 128 * 64 / (knn_ms * 1e-3) / 1e12) if knn_ms > 0 else None)
         # memory-bound stages against the measured HBM copy bandwidth (algorithmic bytes)
         hbm = {}
+        kk = w["k"]
         for key, nbytes in (("colsum_ms", 8.0 * nnz + 16.0 * n_local),
-                            ("lognorm_ms", 20.0 * nnz + 8.0 * n_local + 16.0 * w["genes"])):
+                            ("lognorm_ms", 20.0 * nnz + 8.0 * n_local + 16.0 * w["genes"]),
+                            # kNN read + reverse-list build + host-list gathers + edge write (rank 0's share)
+                            ("snn_edges_ms", 12.0 * w["cells"] * kk + 8.0 * n_local * (kk + 1) ** 2 + 16.0 * n_edges_local)):
             if stage_ms[key] > 0:
                 gbs = nbytes / (stage_ms[key] * 1e-3) / 1e9
                 hbm[key.replace("_ms", "")] = dict(achieved_gbs=gbs, frac=gbs / peaks["hbm"])
