@@ -401,7 +401,7 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, co
 // is the row's threshold, published after every change.  Candidates leave unsorted (k_knn_rerank
 // sorts by exact distance).
 constexpr int TC_RING = 16;  // tile ids of the sequence in flight (producer -> MMA -> scanners)
-constexpr int TC_SCAN_SETS = 2;
+constexpr int TC_SCAN_SETS = 3;
 constexpr int TC_ACC_STAGES = 4;
 constexpr int TC_POS_BITS = 27;  // sorted positions in a ring entry
 constexpr int TC_THREADS = 64 + TC_SCAN_SETS * 128 + 128 + 128;  // + inserters + query-image builders
@@ -1375,9 +1375,9 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     CB_CHECK(ctx, npos < (1LL << TC_POS_BITS), "cb200_knn: at most 2^27 points on the tensor-core engine");
     if (KP == 32)
-        CB_TRY((launch_tc<32, 3, 16, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<32, 3, 8, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
     else if (KP == 64)
-        CB_TRY((launch_tc<64, 2, 16, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<64, 2, 8, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
     else
         CB_TRY((launch_tc<112, 2, 4, 1>(ctx, E, lde, d, scale, nq, C, CAND)));
     cb_stage_end(ctx, ST_KNN_TILE);
