@@ -387,10 +387,10 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, co
 // ---------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------
-// Warp roles: warp 0 = bulk-copy producer (+ pruning tests), warp 1 = MMA issuer, warps 2..9 = two
-// scanner sets of 4 warps (the n-th tile of the sequence goes to set n % 2 through accumulator stage
-// n % 4; within a set warp w owns TMEM lane quarter w % 4 and a thread is one query row), warps
-// 10..13 = inserters, again one thread per query row.
+// Warp roles: warp 0 = bulk-copy producer (+ pruning tests), warp 1 = MMA issuer, then TC_SCAN_SETS (3)
+// scanner sets of 4 warps (the n-th tile of the sequence goes to set n % 3 through accumulator stage
+// n % 4; within a set warp w owns TMEM lane quarter w % 4 and a thread is one query row), 4 inserter
+// warps, again one thread per query row, and 4 builder warps (query images, cluster prefilter).
 //
 // Scanners only compare: 3-input max tree over 32 accumulator columns + one vote; a column that beats
 // the row's published threshold is pushed as (value, sorted position) into the ring of (set, row) --
