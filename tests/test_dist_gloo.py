@@ -37,8 +37,21 @@ class OracleShard:
             raise ValueError("size factors should be positive")
         return self.sf
 
-    def gene_acc(self):
+    # values-first order of the e2e path: logcounts before (and independently of) the gene sums
+    def lognorm_values(self):
         self.logx = O.log_norm_counts(self.colptr, self.x, self.sf)
+        self.values_first = True
+
+    def logcounts_async(self, out):
+        assert getattr(self, "values_first", False), "the logcounts must be requested after lognorm_values"
+        out[:] = self.logx
+
+    def wait_copies(self):
+        pass
+
+    def gene_acc(self):
+        if not getattr(self, "values_first", False):
+            self.logx = O.log_norm_counts(self.colptr, self.x, self.sf)
         s = np.bincount(self.rowidx, weights=self.logx, minlength=self.G)
         q = np.bincount(self.rowidx, weights=self.logx ** 2, minlength=self.G)
         self._acc = torch.from_numpy(np.concatenate([s, q]))
@@ -93,7 +106,10 @@ def _worker(rank, world, port, n_cells, n_genes, out):
         p, i, x = slice_csc(d["colptr"], d["rowidx"], d["x"], b[rank], b[rank + 1])
         pipe = ShardedPipeline(OracleShard(n_genes, p, i, x), n_cells)
         assert (pipe.c0, pipe.c1) == (b[rank], b[rank + 1])
-        res = pipe.run(ndims=8, hvg_ntop=300, neighbors=5, snn_type="rank")
+        logx_out = np.empty(x.size)
+        res = pipe.run(ndims=8, hvg_ntop=300, neighbors=5, snn_type="rank", logx_out=logx_out)
+        assert np.array_equal(logx_out, pipe.shard.logx)       # copied out before the gene statistics
+        assert pipe.j0 < pipe.j1                                # SNN range of this rank (balanced by work)
         gathered = [None] * world
         dist.all_gather_object(gathered, dict(sf=res["sf"], edges=res["edges"], hvgs=res["hvgs"],
                                               mean=res["mean"], var=res["var"],
