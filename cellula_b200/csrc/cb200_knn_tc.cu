@@ -425,7 +425,11 @@ struct TcSmem {
 
 // NQB = query-image buffers: 2 (the image of the next cluster is built while the current one is in use) or,
 // when the candidate heaps need the room (KP = 112), 1 (the build waits for the last MMA of the visit)
-template <int KP, int STAGES, int QCAP, int NQB>
+// NPROD = fp16 products per tile: 3 (q_h r_h + q_h r_l + q_l r_h, the default) or, experimentally
+// (CB200_KNN_PRODUCTS=2), 2: without q_l r_h the key error grows by 2^-12 |q~||r~| -- the recorded bound
+// covers it (err_rel) -- and the tensor work shrinks by a third.  Measured at cfg3: 66.2 vs 67.4 ms for the
+// tiles (the MMA issue is not the limiter) and 9 142 queries lose their margin proof: not worth it, kept off
+template <int KP, int STAGES, int QCAP, int NQB, int NPROD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, const unsigned char *__restrict__ img,
                int64_t nq, const int32_t *__restrict__ qlist, const int32_t *__restrict__ qpos,
@@ -434,7 +438,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                const int32_t *__restrict__ cl, const uint16_t *__restrict__ cl_order,
                const int32_t *__restrict__ cl_tile_begin, const unsigned int *__restrict__ cl_rhomax,
                const float *__restrict__ tile_lo, const float *__restrict__ tile_hi, float key_unscale, int cand_stride,
-               int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau, float *__restrict__ cand_err,
+               int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau, float *__restrict__ cand_err, float err_rel,
                int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done, long long *__restrict__ dbg)
 {
     using L = TcSmem<KP, STAGES, QCAP, NQB>;
@@ -821,7 +825,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         for (int u = 0; u < 4; ++u) {
             const int64_t ql = ql0 + u * 32 + lane;
             if (ql < nq)
-                cand_err[ql] = (4.6e-5f * smax[u] + 4.8e-7f * omax[u] + 0.02f) * key_unscale;
+                cand_err[ql] = (err_rel * smax[u] + 4.8e-7f * omax[u] + 0.02f) * key_unscale;
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -870,7 +874,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 const uint32_t rb = r_desc0 + (uint32_t)s * (TC_TILE_BYTES >> 4);
                 const uint32_t dcol = tmem_base + (uint32_t)(a * TC_N);
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
+                for (int p = 0; p < NPROD; ++p) {
                     const uint32_t qd = q_desc + ((p == 2) ? (TC_PART_BYTES >> 4) : 0u);
                     const uint32_t rd = rb + ((p == 1) ? (TC_PART_BYTES >> 4) : 0u);
 #pragma unroll
@@ -1197,13 +1201,13 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-template <int KP, int STAGES, int QCAP, int NQB>
+template <int KP, int STAGES, int QCAP, int NQB, int NPROD = 3>
 static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double scale, int64_t nq, int C,
                      int cand_stride)
 {
     const size_t smem = TcSmem<KP, STAGES, QCAP, NQB>::bytes;
     static_assert(TcSmem<KP, STAGES, QCAP, NQB>::bytes <= 232448, "shared memory budget");
-    CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, STAGES, QCAP, NQB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_tiles_tc<KP, STAGES, QCAP, NQB, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     const unsigned grid = (unsigned)((nq + TC_M - 1) / TC_M);
     const float key_unscale = (float)(1.0 / (scale * scale));
@@ -1212,12 +1216,12 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
         CB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&dbg), (size_t)5 * 4096 * 2 * sizeof(long long)));
         CB_CUDA(ctx, cudaMemsetAsync(dbg, 0, (size_t)5 * 4096 * 2 * sizeof(long long), ctx->stream));
     }
-    k_knn_tiles_tc<KP, STAGES, QCAP, NQB><<<grid, TC_THREADS, smem, ctx->stream>>>(
+    k_knn_tiles_tc<KP, STAGES, QCAP, NQB, NPROD><<<grid, TC_THREADS, smem, ctx->stream>>>(
         E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, ctx->knn_eperm.p, C,
         ctx->knn_cen.p,
         ctx->knn_dqc.p, ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p,
         ctx->knn_tile_lo.p, ctx->knn_tile_hi.p, key_unscale, cand_stride, ctx->cand_idx.p, ctx->cand_tau.p,
-        ctx->cand_err.p, ctx->flag.p + 3, ctx->maxnrm.p + 3, dbg);
+        ctx->cand_err.p, NPROD == 3 ? 4.6e-5f : 3.0e-4f, ctx->flag.p + 3, ctx->maxnrm.p + 3, dbg);
     CB_LAUNCH(ctx);
     if (dbg != nullptr) {   // dump the timeline of the middle CTA
         std::vector<long long> h((size_t)5 * 4096 * 2);
@@ -1374,7 +1378,10 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     cb_stage_begin(ctx, ST_KNN_TILE);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     CB_CHECK(ctx, npos < (1LL << TC_POS_BITS), "cb200_knn: at most 2^27 points on the tensor-core engine");
-    if (KP == 32)
+    const char *np_env = getenv("CB200_KNN_PRODUCTS");
+    if (KP == 32 && np_env != nullptr && atoi(np_env) == 2)
+        CB_TRY((launch_tc<32, 3, 8, 2, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
+    else if (KP == 32)
         CB_TRY((launch_tc<32, 3, 8, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
     else if (KP == 64)
         CB_TRY((launch_tc<64, 2, 8, 2>(ctx, E, lde, d, scale, nq, C, CAND)));

@@ -210,3 +210,16 @@ def test_knn_argument_errors(gpu_ctx):
         gpu_ctx.knn(synth.make_embedding(300, 5, seed=3), 120)
     with pytest.raises(cellula_b200.Cb200Error, match="ndims"):
         gpu_ctx.knn(synth.make_embedding(100, 70, seed=3), 5)
+
+
+def test_knn_two_product_mode_is_exact(gpu_ctx, monkeypatch):
+    """CB200_KNN_PRODUCTS=2 (experimental): the q_l r_h product is dropped and the recorded error bound widened;
+    the result must stay exact (margin proof or fallback)."""
+    monkeypatch.setenv("CB200_KNN_ENGINE", "tc")
+    monkeypatch.setenv("CB200_KNN_PRODUCTS", "2")
+    for n, d, k, seed in [(20000, 50, 20, 99), (3000, 12, 10, 3)]:
+        emb = synth.make_embedding(n, d, seed=seed)
+        assert np.array_equal(gpu_ctx.knn(emb, k), O.find_knn(emb, k))
+    rng = np.random.default_rng(5)
+    lat = rng.integers(-2, 3, size=(1500, 4)).astype(np.float64)
+    assert np.array_equal(gpu_ctx.knn(lat, 15), O.find_knn(lat, 15))
