@@ -137,3 +137,19 @@ def test_kat_cluster_diagnostics():
     assert np.allclose(got["expected"], m["expected"], rtol=1e-15)
     ratio = O.pairwise_modularity(m["from"], m["to"], m["weight"], m["clusters"], as_ratio=True)
     assert np.isclose(ratio[0, 1], 5.0 / (2 * 6 * 35 / 144)) and np.isnan(ratio[1, 0])
+
+
+def test_kat_pca_and_hvg_ranking():
+    """Analytic PCA (orthogonal centred columns: singular values by hand) and the getTopHVGs ordering rule."""
+    import scipy.sparse as sp
+    k = KAT["pca1"]
+    m = sp.csc_matrix(np.array([k["logcounts_geneA"], k["logcounts_geneB"]]))     # genes x cells
+    res = O.run_pca(2, m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data, np.array([0, 1], dtype=np.int32), 2)
+    assert np.allclose(res["var_explained"], k["var_explained"], rtol=1e-14)
+    assert np.allclose(res["percent_var"], k["percent_var"], rtol=1e-14)
+    assert np.allclose(np.abs(res["scores"][:, 0]), k["abs_scores_pc1"], atol=1e-14)
+    assert np.allclose(np.abs(res["scores"][:, 1]), k["abs_scores_pc2"], atol=1e-14)
+    h = KAT["hvg1"]
+    assert O.get_top_hvgs(np.array(h["bio"]), h["n"]).tolist() == h["top"]
+    from cellula_b200 import trendvar
+    assert trendvar.get_top_hvgs(np.array(h["bio"]), h["n"]).tolist() == h["top"]
