@@ -79,6 +79,10 @@ SIGNATURES = {
     "cb200_fetch_edges": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cb200_synth_counts": (c_int, [c_vp, c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_i64p]),
     "cb200_export_csc": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cb200_synth_host": (c_int, [c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_int, c_i64p,
+                                 ctypes.POINTER(c_i64p), ctypes.POINTER(c_i32p), ctypes.POINTER(c_f64p)]),
+    "cb200_synth_host_free": (None, [c_i64p, c_i32p, c_f64p]),
+    "cb200_synth_embedding_host": (c_int, [c_i64, c_int, ctypes.c_uint64, c_int, c_vp]),
     "cb200_host_weighted_lowess": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.c_double, c_int, c_int, c_vp]),
     "cb200_host_nls_trend": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, c_int]),
     "cb200_host_nls_grid": (c_int, [c_i64, c_vp, c_vp, ctypes.c_double, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),

@@ -432,3 +432,234 @@ extern "C" int cb200_host_nls_trend(int64_t n64, const double *v, const double *
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Host compilation of the synthetic-data generator (cb200_synth_core.h): bit-identical to the device
+// generator of cb200_synth.cu.  Test / bench infrastructure; no device work.
+// ---------------------------------------------------------------------------------------------------------
+#include <cstdlib>
+#include <cstring>
+
+#include "cb200_synth_core.h"
+#include "cb200_synth_host.h"
+
+void cb200_synth_params_host(int64_t G, uint64_t seed, std::vector<float> &base, std::vector<uint8_t> &wf,
+                             std::vector<float> &wv, std::vector<float> &cent)
+{
+    base.resize((size_t)G);
+    wf.resize((size_t)G * SY_NZ);
+    wv.resize((size_t)G * SY_NZ);
+    cent.resize((size_t)SY_CLUSTERS * SY_F);
+    for (int64_t g = 0; g < G; ++g) {
+        base[(size_t)g] = sy_gene_base(seed, g);
+        for (int z = 0; z < SY_NZ; ++z) {
+            wf[(size_t)g * SY_NZ + z] = (uint8_t)sy_gene_factor(seed, g, z);
+            wv[(size_t)g * SY_NZ + z] = sy_gene_loading(seed, g, z);
+        }
+    }
+    for (int i = 0; i < SY_CLUSTERS * SY_F; ++i)
+        cent[(size_t)i] = sy_centroid(seed, i);
+}
+
+// offset that gives the neutral cell (all factors 0, depth 1) ~nnz_per_cell non-zero genes: bisection
+float cb200_synth_neutral_offset(const std::vector<float> &base, double nnz_per_cell)
+{
+    float lo = -30.0f, hi = 10.0f;
+    for (int it = 0; it < 40; ++it) {
+        const float mid = sy_fmul(0.5f, sy_fadd(lo, hi));
+        double nz = 0.0;
+        for (size_t g = 0; g < base.size(); ++g) {
+            const float ll = sy_fadd(base[g], mid);
+            nz = sy_dadd(nz, (double)sy_fadd(1.0f, -sy_p0(sy_expf(ll < SY_LL_MAX ? ll : SY_LL_MAX))));
+        }
+        if (nz < nnz_per_cell)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return sy_fmul(0.5f, sy_fadd(lo, hi));
+}
+
+// one step of the realised-density correction (the neutral cell ignores factor and depth variance)
+float cb200_synth_refine_offset(float off, double nnz_per_cell, int64_t nnz_probe, int64_t n_probe)
+{
+    const double actual = sy_ddiv((double)nnz_probe, (double)n_probe);
+    return sy_fadd(off, (float)sy_dmul(1.3, sy_log(sy_ddiv(nnz_per_cell, actual))));
+}
+
+bool cb200_synth_offset_ok(double nnz_per_cell, int64_t nnz_probe, int64_t n_probe)
+{
+    const double ratio = sy_ddiv(sy_ddiv((double)nnz_probe, (double)n_probe), nnz_per_cell);
+    return ratio > 0.99 && ratio < 1.01;
+}
+
+namespace {
+struct SyBlock {
+    std::vector<int32_t> cnt, row;
+    std::vector<double> val;
+};
+
+// cells [c0, c1) of the global matrix; FILL = false only counts
+void sy_host_cells(int64_t G, int64_t c0, int64_t c1, uint64_t seed, float off, const std::vector<float> &base,
+                   const std::vector<uint8_t> &wf, const std::vector<float> &wv, const std::vector<float> &cent,
+                   bool fill, SyBlock &out)
+{
+    float zs[SY_F];
+    out.cnt.assign((size_t)(c1 - c0), 0);
+    for (int64_t c = c0; c < c1; ++c) {
+        const uint64_t cg = (uint64_t)c;
+        const int cl = sy_cell_cluster(seed, cg);
+        for (int f = 0; f < SY_F; ++f)
+            zs[f] = sy_cell_factor(seed, cg, f, cent.data(), cl);
+        const float ldepth = sy_cell_logdepth(seed, cg);
+        int total = 0;
+        for (int64_t g = 0; g < G; ++g) {
+            const int k = sy_count(seed, cg, g, base[(size_t)g], &wf[(size_t)g * SY_NZ], &wv[(size_t)g * SY_NZ], zs, off,
+                                   ldepth);
+            if (k > 0) {
+                ++total;
+                if (fill) {
+                    out.row.push_back((int32_t)g);
+                    out.val.push_back((double)k);
+                }
+            }
+        }
+        if (total == 0) {
+            total = 1;
+            if (fill) {
+                out.row.push_back((int32_t)(cg % (uint64_t)G));
+                out.val.push_back(1.0);
+            }
+        }
+        out.cnt[(size_t)(c - c0)] = total;
+    }
+}
+
+template <typename Fn>
+void sy_parallel_blocks(int64_t n_blocks, int n_threads, Fn fn)
+{
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= n_blocks)
+                return;
+            fn(b);
+        }
+    };
+    if (n_threads <= 1) {
+        work();
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back(work);
+    for (auto &t : th)
+        t.join();
+}
+}  // namespace
+
+int cb200_synth_calibrate_host(int64_t n_genes, int64_t n_cells_total, double nnz_per_cell, uint64_t seed, int n_threads,
+                               const std::vector<float> &base, const std::vector<uint8_t> &wf,
+                               const std::vector<float> &wv, const std::vector<float> &cent, float *off_out)
+{
+    float off = cb200_synth_neutral_offset(base, nnz_per_cell);
+    const int64_t n_probe = n_cells_total < CB200_SYNTH_PROBE ? n_cells_total : CB200_SYNTH_PROBE;
+    const int64_t BL = 16, nb = (n_probe + BL - 1) / BL;
+    for (int pass = 0; pass < 6; ++pass) {
+        std::vector<int64_t> part((size_t)nb, 0);
+        sy_parallel_blocks(nb, n_threads, [&](int64_t b) {
+            SyBlock blk;
+            const int64_t c0 = b * BL, c1 = std::min(n_probe, c0 + BL);
+            sy_host_cells(n_genes, c0, c1, seed, off, base, wf, wv, cent, false, blk);
+            int64_t s = 0;
+            for (int32_t v : blk.cnt)
+                s += v;
+            part[(size_t)b] = s;
+        });
+        int64_t nnz = 0;
+        for (int64_t v : part)
+            nnz += v;
+        if (cb200_synth_offset_ok(nnz_per_cell, nnz, n_probe))
+            break;
+        off = cb200_synth_refine_offset(off, nnz_per_cell, nnz, n_probe);
+    }
+    *off_out = off;
+    return 0;
+}
+
+extern "C" int cb200_synth_host(int64_t n_genes, int64_t n_cells, double nnz_per_cell, uint64_t seed, int64_t cell_offset,
+                                int64_t n_cells_total, int n_threads, int64_t *nnz_out, int64_t **colptr_out,
+                                int32_t **rowidx_out, double **values_out)
+{
+    if (n_genes < 64 || n_genes >= 2147483647LL || n_cells <= 0 || cell_offset < 0 ||
+        cell_offset + n_cells > n_cells_total || !(nnz_per_cell >= 1.0) || !(nnz_per_cell < (double)n_genes) ||
+        nnz_out == nullptr || colptr_out == nullptr || rowidx_out == nullptr || values_out == nullptr)
+        return 1;
+    if (n_threads <= 0)
+        n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<float> base, wv, cent;
+    std::vector<uint8_t> wf;
+    cb200_synth_params_host(n_genes, seed, base, wf, wv, cent);
+    float off = 0.f;
+    cb200_synth_calibrate_host(n_genes, n_cells_total, nnz_per_cell, seed, n_threads, base, wf, wv, cent, &off);
+    const int64_t BL = 32, nb = (n_cells + BL - 1) / BL;
+    std::vector<SyBlock> blocks((size_t)nb);
+    sy_parallel_blocks(nb, n_threads, [&](int64_t b) {
+        const int64_t c0 = cell_offset + b * BL, c1 = std::min(cell_offset + n_cells, c0 + BL);
+        sy_host_cells(n_genes, c0, c1, seed, off, base, wf, wv, cent, true, blocks[(size_t)b]);
+    });
+    int64_t nnz = 0;
+    for (auto &b : blocks)
+        nnz += (int64_t)b.row.size();
+    int64_t *cp = (int64_t *)malloc((size_t)(n_cells + 1) * sizeof(int64_t));
+    int32_t *ri = (int32_t *)malloc((size_t)std::max<int64_t>(nnz, 1) * sizeof(int32_t));
+    double *xv = (double *)malloc((size_t)std::max<int64_t>(nnz, 1) * sizeof(double));
+    if (cp == nullptr || ri == nullptr || xv == nullptr) {
+        free(cp);
+        free(ri);
+        free(xv);
+        return 2;
+    }
+    int64_t pos = 0, c = 0;
+    cp[0] = 0;
+    for (auto &b : blocks) {
+        memcpy(ri + pos, b.row.data(), b.row.size() * sizeof(int32_t));
+        memcpy(xv + pos, b.val.data(), b.val.size() * sizeof(double));
+        int64_t p = pos;
+        for (int32_t v : b.cnt) {
+            p += v;
+            cp[++c] = p;
+        }
+        pos += (int64_t)b.row.size();
+    }
+    *nnz_out = nnz;
+    *colptr_out = cp;
+    *rowidx_out = ri;
+    *values_out = xv;
+    return 0;
+}
+
+extern "C" void cb200_synth_host_free(int64_t *colptr, int32_t *rowidx, double *values)
+{
+    free(colptr);
+    free(rowidx);
+    free(values);
+}
+
+extern "C" int cb200_synth_embedding_host(int64_t n, int d, uint64_t seed, int n_threads, double *emb_colmajor)
+{
+    if (n <= 0 || d <= 0 || emb_colmajor == nullptr)
+        return 1;
+    if (n_threads <= 0)
+        n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int64_t BL = 4096, nb = (n + BL - 1) / BL;
+    sy_parallel_blocks(nb * d, n_threads, [&](int64_t job) {
+        const int t = (int)(job / nb);
+        const int64_t i0 = (job % nb) * BL, i1 = std::min(n, i0 + BL);
+        const double sc = sy_emb_scale(t, d);
+        for (int64_t i = i0; i < i1; ++i)
+            emb_colmajor[(size_t)t * (size_t)n + (size_t)i] = sy_emb_value(seed, i, t, sc, SY_EMB_CLUSTERS);
+    });
+    return 0;
+}

@@ -10,31 +10,8 @@
 #include <vector>
 
 #include "cb200_common.cuh"
-
-#define SY_F 64
-#define SY_NZ 4
-#define SY_CLUSTERS 40
-#define SY_SIZE 10.0f  // NB size parameter r = 1/dispersion
-
-__host__ __device__ __forceinline__ uint64_t sy_mix(uint64_t z)
-{
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
-__host__ __device__ __forceinline__ uint64_t sy_hash(uint64_t seed, uint64_t a, uint64_t b)
-{
-    return sy_mix(sy_mix(seed + 0x9E3779B97F4A7C15ULL * (a + 1)) ^ (0xD1B54A32D192ED03ULL * (b + 1)));
-}
-__host__ __device__ __forceinline__ float sy_unif(uint64_t h)  // (0, 1)
-{
-    return ((float)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);
-}
-__device__ __forceinline__ float sy_normal(uint64_t h)
-{
-    const float u1 = sy_unif(h), u2 = sy_unif(sy_mix(h + 0x632BE59BD9B4E019ULL));
-    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-}
+#include "cb200_synth_core.h"
+#include "cb200_synth_host.h"
 
 struct SyParams {
     float *base;      // [G]
@@ -42,45 +19,6 @@ struct SyParams {
     float *wv;        // [G*SY_NZ] loadings
     float *cent;      // [SY_CLUSTERS*SY_F]
 };
-
-__global__ void k_synth_params(int64_t G, uint64_t seed, float *base, uint8_t *wf, float *wv, float *cent)
-{
-    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (g < G) {
-        base[g] = 2.0f * sy_normal(sy_hash(seed, 0x1001, (uint64_t)g));
-        for (int z = 0; z < SY_NZ; ++z) {
-            const uint64_t h = sy_hash(seed, 0x2000 + z, (uint64_t)g);
-            const int f = (int)(h % SY_F);
-            wf[g * SY_NZ + z] = (uint8_t)f;
-            wv[g * SY_NZ + z] = sy_normal(sy_mix(h)) * powf(0.93f, (float)f);
-        }
-    }
-    if (g < SY_CLUSTERS * SY_F)
-        cent[g] = sy_normal(sy_hash(seed, 0x3003, (uint64_t)g));
-}
-
-__device__ __forceinline__ int sy_draw(float lam, float u)
-{
-    // NB(mean lam, size r) by inversion; normal approximation for large means
-    const float r = SY_SIZE;
-    if (lam > 30.f) {
-        const float sd = sqrtf(lam + lam * lam / r);
-        const float v = lam + sd * normcdfinvf(u);
-        return v < 0.f ? 0 : (int)(v + 0.5f);
-    }
-    const float q = lam / (r + lam);
-    float p = expf(-r * log1pf(lam / r));
-    float cum = p;
-    int kk = 0;
-    while (u > cum && kk < 4096) {
-        p *= ((float)kk + r) / ((float)kk + 1.f) * q;
-        cum += p;
-        ++kk;
-        if (p < 1e-12f)
-            break;
-    }
-    return kk;
-}
 
 // warp per cell; FILL == 0 counts the non-zeros, FILL == 1 writes them in gene order
 template <int FILL>
@@ -95,25 +33,18 @@ k_synth_cells(int64_t G, int64_t n_cells, int64_t cell_offset, uint64_t seed, fl
     const int64_t nwarps = (int64_t)gridDim.x * 8;
     for (int64_t c = warp0; c < n_cells; c += nwarps) {
         const uint64_t cg = (uint64_t)(cell_offset + c);
-        const int cl = (int)(sy_hash(seed, 0x4004, cg) % SY_CLUSTERS);
+        const int cl = sy_cell_cluster(seed, cg);
         for (int f = lane; f < SY_F; f += 32)
-            zs[w][f] = P.cent[cl * SY_F + f] + 0.3f * sy_normal(sy_hash(seed, 0x5000 + f, cg));
-        const float ldepth = 0.35f * sy_normal(sy_hash(seed, 0x6006, cg));
+            zs[w][f] = sy_cell_factor(seed, cg, f, P.cent, cl);
+        const float ldepth = sy_cell_logdepth(seed, cg);
         __syncwarp();
         int64_t out = FILL ? colptr[c] : 0;
         int total = 0;
         for (int64_t g0 = 0; g0 < G; g0 += 32) {
             const int64_t g = g0 + lane;
             int k = 0;
-            if (g < G) {
-                float ll = P.base[g] + off + ldepth;
-#pragma unroll
-                for (int z = 0; z < SY_NZ; ++z)
-                    ll = fmaf(P.wv[g * SY_NZ + z], zs[w][P.wf[g * SY_NZ + z]], ll);
-                const float lam = expf(fminf(ll, 12.f));
-                const float u = sy_unif(sy_hash(seed ^ 0x7007, cg, (uint64_t)g));
-                k = sy_draw(lam, u);
-            }
+            if (g < G)
+                k = sy_count(seed, cg, g, P.base[g], P.wf + g * SY_NZ, P.wv + g * SY_NZ, zs[w], off, ldepth);
             const unsigned m = __ballot_sync(0xffffffffu, k > 0);
             if (FILL && k > 0) {
                 const int64_t o = out + __popc(m & ((1u << lane) - 1u));
@@ -156,38 +87,26 @@ extern "C" int cb200_synth_counts(cb200_ctx *ctx, int64_t n_genes, int64_t n_cel
     P.wf = wf.p;
     P.wv = wv.p;
     P.cent = cent.p;
-    const int64_t np = n_genes > SY_CLUSTERS * SY_F ? n_genes : SY_CLUSTERS * SY_F;
-    k_synth_params<<<(unsigned)((np + 255) / 256), 256, 0, ctx->stream>>>(n_genes, seed, base.p, wf.p, wv.p, cent.p);
-    CB_LAUNCH(ctx);
-    // calibrate the global offset so that a neutral cell has ~nnz_per_cell non-zero genes
-    std::vector<float> hb((size_t)n_genes);
-    CB_CUDA(ctx, cudaMemcpyAsync(hb.data(), base.p, (size_t)n_genes * sizeof(float), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
+    // model parameters and the neutral-cell offset come from the same host code as the host generator
+    std::vector<float> hb, hwv, hcent;
+    std::vector<uint8_t> hwf;
+    cb200_synth_params_host(n_genes, seed, hb, hwf, hwv, hcent);
+    CB_CUDA(ctx, cudaMemcpyAsync(base.p, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(ctx, cudaMemcpyAsync(wv.p, hwv.data(), hwv.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(ctx, cudaMemcpyAsync(wf.p, hwf.data(), hwf.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(ctx, cudaMemcpyAsync(cent.p, hcent.data(), hcent.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    double lo = -30.0, hi = 10.0;
-    for (int it = 0; it < 60; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        double nz = 0.0;
-        for (int64_t g = 0; g < n_genes; ++g) {
-            const double lam = exp((double)hb[g] + mid);
-            nz += 1.0 - exp(-(double)SY_SIZE * log1p(lam / (double)SY_SIZE));
-        }
-        if (nz < nnz_per_cell)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    float off = (float)(0.5 * (lo + hi));
+    float off = cb200_synth_neutral_offset(hb, nnz_per_cell);
 
     ctx->G = n_genes;
     ctx->N = n_cells;
     ctx->cell_offset = cell_offset;
     ctx->N_total = n_cells_total;
     // The neutral-cell calibration ignores the factor / depth variance: correct the offset with a
-    // few count passes over a fixed probe -- the first min(N_total, 16384) cells of the *global*
+    // few count passes over a fixed probe -- the first min(N_total, CB200_SYNTH_PROBE) cells of the *global*
     // matrix -- until the realised mean is within 1% of the request.  The probe does not depend on
     // the shard, so every rank derives the same offset and the shards tile one matrix.
-    const int64_t n_probe = n_cells_total < 16384 ? n_cells_total : 16384;
+    const int64_t n_probe = n_cells_total < CB200_SYNTH_PROBE ? n_cells_total : CB200_SYNTH_PROBE;
     const int64_t n_buf = n_cells > n_probe ? n_cells : n_probe;
     CB_CUDA(ctx, ctx->colptr.ensure((size_t)n_buf + 1));
     CB_CUDA(ctx, ctx->hcnt.ensure((size_t)n_buf));
@@ -201,10 +120,9 @@ extern "C" int cb200_synth_counts(cb200_ctx *ctx, int64_t n_genes, int64_t n_cel
         CB_CUDA(ctx, cudaMemcpyAsync(&nnz, ctx->colptr.p + n_probe, sizeof(int64_t), cudaMemcpyDeviceToHost,
                                      ctx->stream));
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        const double actual = (double)nnz / (double)n_probe;
-        if (fabs(actual / nnz_per_cell - 1.0) < 0.01)
+        if (cb200_synth_offset_ok(nnz_per_cell, nnz, n_probe))
             break;
-        off += (float)(1.3 * log(nnz_per_cell / actual));
+        off = cb200_synth_refine_offset(off, nnz_per_cell, nnz, n_probe);
     }
     const int grid = cb_grid_for(n_cells, 8, ctx->num_sms * 8);
     k_synth_cells<0><<<grid, 256, 0, ctx->stream>>>(n_genes, n_cells, cell_offset, seed, off, P, ctx->hcnt.p, nullptr,

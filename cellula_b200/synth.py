@@ -1,72 +1,92 @@
-"""Synthetic scRNA-seq count matrices and embeddings (host side, numpy).
+"""Synthetic scRNA-seq count matrices and embeddings -- host side of THE generator of this repository.
 
-Deterministic negative-binomial counts with planted low-rank structure, in the
-dgCMatrix/CSC layout the reference's ``counts(sce)`` assay uses (SURVEY.md row a1,
-generator spec SURVEY.md 8d): log lambda_gc = log m_g + sum_f W_gf Z_fc + log s_c,
-F latent factors of geometrically decaying strength (clear spectral gap so the PCA
-comparison is well-posed), 40 cluster centroids plus continuous noise (no duplicate
-cells), Gamma-Poisson counts with dispersion 0.1.
+One specification (csrc/cb200_synth_core.h: integer hashing + individually rounded IEEE operations), compiled
+for the device (``Context.synth_counts`` -> ``cb200_synth_counts``, what the bench uses at 1.3 M - 4 M cells)
+and for the host (``make_counts`` -> ``cb200_synth_host``, no GPU needed).  Both give the same matrix bit for
+bit for the same (seed, shape, nnz_per_cell), and any contiguous block of cells can be generated on its own.
+``write_dataset`` stores it in the language-neutral on-disk form that
+``baseline/run_reference.R`` reads on an R host.
 
-The bench generates its (much larger) matrices on the device with
-``cb200_synth_counts`` (csrc/cb200_synth.cu); this numpy version feeds the parity tests,
-where oracle and CUDA path must see the same host arrays.
+Model: negative-binomial counts with planted low-rank structure in the dgCMatrix/CSC layout the reference's
+``counts(sce)`` assay uses: log lambda_gc = base_g + off + log depth_c + sum_z W_gz Z_fc,
+64 latent factors of geometrically decaying strength (clear spectral gap so the PCA comparison is
+well-posed), 40 cluster centroids plus continuous noise (no duplicate cells), dispersion 0.1.
 """
 from __future__ import annotations
 
+import ctypes
+import hashlib
+import json
+import os
+
 import numpy as np
 
+from . import _lib
+
 SEED = 20261019
+EMB_SEED = 20261020
 
 
-def make_counts(n_cells, n_genes, nnz_per_cell=500, seed=SEED, n_factors=64, n_clusters=40,
-                chunk=4096, dispersion=0.1):
-    """Returns dict(colptr int64[N+1], rowidx int32[nnz], x float64[nnz], n_genes, n_cells)."""
-    rng = np.random.default_rng(seed)
-    F = n_factors
-    sigma = 1.0 * 0.93 ** np.arange(F)
-    W = np.where(rng.random((n_genes, F)) < 0.05, rng.standard_normal((n_genes, F)), 0.0) * sigma
-    cent = rng.standard_normal((n_clusters, F))
-    base = rng.standard_normal(n_genes) * 2.0
-    # calibrate the base-mean offset so that the neutral cell has ~nnz_per_cell non-zeros
-    r = 1.0 / dispersion
-    lo, hi = -20.0, 10.0
-    for _ in range(60):
-        mid = 0.5 * (lo + hi)
-        lam = np.exp(base + mid)
-        nnz = np.sum(1.0 - (r / (r + lam)) ** r)
-        lo, hi = (mid, hi) if nnz < nnz_per_cell else (lo, mid)
-    base = base + 0.5 * (lo + hi)
-
-    cols, rows, vals = [0], [], []
-    total = 0
-    for c0 in range(0, n_cells, chunk):
-        c1 = min(n_cells, c0 + chunk)
-        crng = np.random.default_rng([seed, c0])
-        nc = c1 - c0
-        cl = crng.integers(0, n_clusters, nc)
-        Z = cent[cl] + 0.3 * crng.standard_normal((nc, F))
-        depth = np.exp(0.35 * crng.standard_normal(nc))
-        loglam = Z @ W.T + base[None, :] + np.log(depth)[:, None]
-        lam = np.exp(loglam)
-        gam = crng.gamma(shape=r, scale=1.0 / r, size=lam.shape)
-        cnt = crng.poisson(lam * gam)
-        for q in range(nc):  # re-draw empty cells (logNormCounts would error on them)
-            while cnt[q].sum() == 0:
-                cnt[q] = crng.poisson(lam[q] * crng.gamma(shape=r, scale=1.0 / r, size=n_genes))
-        cc, gg = np.nonzero(cnt)
-        rows.append(gg.astype(np.int32))
-        vals.append(cnt[cc, gg].astype(np.float64))
-        per = np.bincount(cc, minlength=nc)
-        cols.extend((total + np.cumsum(per)).tolist())
-        total += per.sum()
-    return dict(colptr=np.asarray(cols, dtype=np.int64), rowidx=np.concatenate(rows),
-                x=np.concatenate(vals), n_genes=int(n_genes), n_cells=int(n_cells))
+def make_counts(n_cells, n_genes, nnz_per_cell=500, seed=SEED, cell_offset=0, n_cells_total=None, n_threads=0):
+    """Returns dict(colptr int64[N+1], rowidx int32[nnz], x float64[nnz], n_genes, n_cells) for the global
+    cells [cell_offset, cell_offset + n_cells) of the (n_genes x n_cells_total) matrix."""
+    L = _lib.lib()
+    if n_cells_total is None:
+        n_cells_total = cell_offset + n_cells
+    nnz = _lib.c_i64()
+    pc, pr, px = _lib.c_i64p(), _lib.c_i32p(), _lib.c_f64p()
+    rc = L.cb200_synth_host(int(n_genes), int(n_cells), float(nnz_per_cell), int(seed), int(cell_offset),
+                            int(n_cells_total), int(n_threads), ctypes.byref(nnz), ctypes.byref(pc), ctypes.byref(pr),
+                            ctypes.byref(px))
+    if rc != 0:
+        raise ValueError(f"cb200_synth_host failed ({rc}): need n_genes >= 64, 1 <= nnz_per_cell < n_genes")
+    m = nnz.value
+    try:
+        colptr = np.ctypeslib.as_array(pc, shape=(n_cells + 1,)).copy()
+        rowidx = np.ctypeslib.as_array(pr, shape=(max(m, 1),))[:m].copy()
+        x = np.ctypeslib.as_array(px, shape=(max(m, 1),))[:m].copy()
+    finally:
+        L.cb200_synth_host_free(pc, pr, px)
+    return dict(colptr=colptr, rowidx=rowidx, x=x, n_genes=int(n_genes), n_cells=int(n_cells))
 
 
-def make_embedding(n_cells, d=50, seed=SEED + 1, n_clusters=40):
-    """cfg-4-style PC matrix: Gaussian clusters, per-PC scale decaying 20 -> 1 (N x d fp64)."""
-    rng = np.random.default_rng(seed)
-    scale = np.geomspace(20.0, 1.0, d)
-    cent = rng.standard_normal((n_clusters, d)) * scale
-    cl = rng.integers(0, n_clusters, n_cells)
-    return cent[cl] + rng.standard_normal((n_cells, d)) * (0.35 * scale)
+def make_embedding(n_cells, d=50, seed=EMB_SEED, n_threads=0):
+    """cfg-4-style PC matrix: 40 Gaussian clusters, per-PC scale decaying 20 -> 1 (N x d fp64, column-major)."""
+    emb = np.empty((n_cells, d), dtype=np.float64, order="F")
+    rc = _lib.lib().cb200_synth_embedding_host(int(n_cells), int(d), int(seed), int(n_threads),
+                                               ctypes.c_void_p(emb.ctypes.data))
+    if rc != 0:
+        raise ValueError("cb200_synth_embedding_host failed")
+    return emb
+
+
+def _sha256(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def write_dataset(path, d, **meta):
+    """On-disk form of a count matrix (little-endian raw binaries + manifest), readable from base R with
+    readBin -> new("dgCMatrix", i=, p=as.integer(p), x=, Dim=): p.i64, i.i32, x.f64, manifest.json."""
+    os.makedirs(path, exist_ok=True)
+    arrays = {"p.i64": np.asarray(d["colptr"], dtype="<i8"), "i.i32": np.asarray(d["rowidx"], dtype="<i4"),
+              "x.f64": np.asarray(d["x"], dtype="<f8")}
+    for name, a in arrays.items():
+        a.tofile(os.path.join(path, name))
+    man = dict(format="cellula_b200 dataset v1", n_genes=int(d["n_genes"]), n_cells=int(d["n_cells"]),
+               nnz=int(arrays["x.f64"].size), sha256={k: _sha256(v) for k, v in arrays.items()},
+               generator="cellula_b200/csrc/cb200_synth_core.h", **meta)
+    with open(os.path.join(path, "manifest.json"), "w") as fh:
+        json.dump(man, fh, indent=1)
+    return man
+
+
+def read_dataset(path, verify=True):
+    man = json.load(open(os.path.join(path, "manifest.json")))
+    d = dict(colptr=np.fromfile(os.path.join(path, "p.i64"), dtype="<i8"),
+             rowidx=np.fromfile(os.path.join(path, "i.i32"), dtype="<i4"),
+             x=np.fromfile(os.path.join(path, "x.f64"), dtype="<f8"), n_genes=man["n_genes"], n_cells=man["n_cells"])
+    if verify:
+        for k, a in (("p.i64", d["colptr"]), ("i.i32", d["rowidx"]), ("x.f64", d["x"])):
+            if _sha256(a) != man["sha256"][k]:
+                raise ValueError(f"{path}/{k}: sha256 does not match the manifest")
+    return d, man

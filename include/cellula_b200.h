@@ -219,13 +219,22 @@ int cb200_pairwise_modularity(cb200_ctx *ctx, const int32_t *from, const int32_t
                               double *observed_out, double *expected_out, double *total_weight_out);
 
 /* ---- synthetic input (bench / test infrastructure, not part of the reference path) ---
- * Fills the context with a deterministic negative-binomial count matrix with planted
- * low-rank structure generated on the device, as if by cb200_load_csc.
- * cb200_export_csc copies it to host buffers so that the same data can be pushed back
- * through the host-facing calls and handed to the oracle. */
+ * ONE generator specification (cellula_b200/csrc/cb200_synth_core.h) compiled for the device and for the
+ * host; both produce the same matrix bit for bit (integer hashing + individually rounded IEEE operations).
+ * cb200_synth_counts fills the context with the negative-binomial count matrix with planted low-rank
+ * structure as if by cb200_load_csc; cb200_export_csc copies it to host buffers.
+ * cb200_synth_host is the host compilation (no GPU needed): it mallocs colptr[n_cells+1], rowidx[nnz],
+ * values[nnz] for the global cells [cell_offset, cell_offset + n_cells); release with cb200_synth_host_free.
+ * cb200_synth_embedding_host: the cfg-4 style PC matrix (Gaussian clusters, per-PC scale 20 -> 1), column-major
+ * n x d doubles into a caller-owned array.  n_threads <= 0: all host cores. */
 int cb200_synth_counts(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, double nnz_per_cell,
                        uint64_t seed, int64_t cell_offset, int64_t n_cells_total,
                        int64_t *nnz_out);
+int cb200_synth_host(int64_t n_genes, int64_t n_cells, double nnz_per_cell, uint64_t seed, int64_t cell_offset,
+                     int64_t n_cells_total, int n_threads, int64_t *nnz_out, int64_t **colptr_out,
+                     int32_t **rowidx_out, double **values_out);
+void cb200_synth_host_free(int64_t *colptr, int32_t *rowidx, double *values);
+int cb200_synth_embedding_host(int64_t n, int d, uint64_t seed, int n_threads, double *emb_colmajor);
 int cb200_export_csc(cb200_ctx *ctx, int64_t *colptr, int32_t *rowidx, double *values);
 
 /* ---- host-side helper of the Python mirror (no device work, not part of the reference FFI) ----

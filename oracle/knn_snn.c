@@ -106,10 +106,10 @@ int oracle_knn(const double *emb, int64_t N, int d, int k, int32_t *index_out,
  * Edges are emitted as (from = j+1, to = h+1 with h < j, weight) in order of first
  * encounter, exactly as SURVEY.md 8c.1-7 states.  Arrays are malloc'ed here; release
  * with oracle_free(). Returns 0 / negative on error. */
-int oracle_snn(const int32_t *index, int64_t N, int k, int type, int64_t *n_edges,
-               int32_t **from_out, int32_t **to_out, double **w_out)
+int oracle_snn_range(const int32_t *index, int64_t N, int k, int type, int64_t j_begin, int64_t j_end,
+                     int64_t *n_edges, int32_t **from_out, int32_t **to_out, double **w_out)
 {
-    if (N < 1 || k < 1 || type < 0 || type > 2)
+    if (N < 1 || k < 1 || type < 0 || type > 2 || j_begin < 0 || j_end > N || j_begin > j_end)
         return -1;
     const int L = k + 1;
     /* hosts[s] = (cell, rank) of every cell whose extended list holds s; CSR layout. */
@@ -154,7 +154,7 @@ int oracle_snn(const int32_t *index, int64_t N, int k, int type, int64_t *n_edge
     for (int64_t h = 0; h < N; ++h)
         stamp[h] = -1;
 
-    for (int64_t j = 0; j < N; ++j) {
+    for (int64_t j = j_begin; j < j_end; ++j) { /* the edges of cell j depend on the lists only: any j-range */
         for (int i = 0; i < L; ++i) {
             int64_t s = (i == 0) ? j : (int64_t)index[j + N * (int64_t)(i - 1)] - 1;
             for (int64_t e = hptr[s]; e < hptr[s + 1]; ++e) {
@@ -212,7 +212,84 @@ int oracle_snn(const int32_t *index, int64_t N, int k, int type, int64_t *n_edge
     return 0;
 }
 
+int oracle_snn(const int32_t *index, int64_t N, int k, int type, int64_t *n_edges,
+               int32_t **from_out, int32_t **to_out, double **w_out)
+{
+    return oracle_snn_range(index, N, k, type, 0, N, n_edges, from_out, to_out, w_out);
+}
+
 void oracle_free(void *p) { free(p); }
+
+/* Exact kNN of selected query rows only (same arithmetic and tie rule as oracle_knn): used to check
+ * sampled rows at sizes where the full N x N scan is too slow for a test.
+ * queries: 0-based rows; index_out: row-major nq x k, 1-based; dist_out nullable, row-major nq x k. */
+int oracle_knn_queries(const double *emb, int64_t N, int d, int k, const int64_t *queries, int64_t nq,
+                       int32_t *index_out, double *dist_out)
+{
+    if (N < 2 || d < 1 || k < 1 || k > N - 1 || nq < 0)
+        return -1;
+    double *rows = (double *)malloc((size_t)N * d * sizeof(double));
+    if (!rows)
+        return -2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i)
+        for (int t = 0; t < d; ++t)
+            rows[i * d + t] = emb[i + N * (int64_t)t];
+    int bad = 0;
+#pragma omp parallel
+    {
+        double *bd = (double *)malloc((size_t)k * sizeof(double));
+        double *br = (double *)malloc((size_t)k * sizeof(double));
+        int32_t *bi = (int32_t *)malloc((size_t)k * sizeof(int32_t));
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t qi = 0; qi < nq; ++qi) {
+            const int64_t i = queries[qi];
+            if (i < 0 || i >= N) {
+                bad = 1;
+                continue;
+            }
+            const double *a = rows + i * d;
+            int cnt = 0;
+            for (int64_t j = 0; j < N; ++j) {
+                if (j == i)
+                    continue;
+                const double *b = rows + j * d;
+                double acc = 0.0;
+                for (int t = 0; t < d; ++t) {
+                    double delta = a[t] - b[t];
+                    acc += delta * delta;
+                }
+                if (cnt == k && acc > br[k - 1])
+                    continue;
+                double dist = sqrt(acc);
+                if (cnt == k && !(dist < bd[k - 1]))
+                    continue;
+                int pos = (cnt < k) ? cnt : k - 1;
+                while (pos > 0 && dist < bd[pos - 1]) {
+                    bd[pos] = bd[pos - 1];
+                    br[pos] = br[pos - 1];
+                    bi[pos] = bi[pos - 1];
+                    --pos;
+                }
+                bd[pos] = dist;
+                br[pos] = acc;
+                bi[pos] = (int32_t)j;
+                if (cnt < k)
+                    ++cnt;
+            }
+            for (int c = 0; c < k; ++c) {
+                index_out[qi * k + c] = bi[c] + 1;
+                if (dist_out)
+                    dist_out[qi * k + c] = bd[c];
+            }
+        }
+        free(bd);
+        free(br);
+        free(bi);
+    }
+    free(rows);
+    return bad ? -3 : 0;
+}
 
 /* --------------------------------------------------- normalisation + gene statistics
  * scuttle::librarySizeFactors / normalizeCounts and scran's per-gene mean/variance

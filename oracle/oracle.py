@@ -54,6 +54,11 @@ def _lib():
         lib.oracle_snn.argtypes = [i32p, i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(i64),
                                    ctypes.POINTER(i32p), ctypes.POINTER(i32p), ctypes.POINTER(f64p)]
         lib.oracle_snn.restype = ctypes.c_int
+        lib.oracle_snn_range.argtypes = [i32p, i64, ctypes.c_int, ctypes.c_int, i64, i64, ctypes.POINTER(i64),
+                                         ctypes.POINTER(i32p), ctypes.POINTER(i32p), ctypes.POINTER(f64p)]
+        lib.oracle_snn_range.restype = ctypes.c_int
+        lib.oracle_knn_queries.argtypes = [f64p, i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(i64), i64, i32p, f64p]
+        lib.oracle_knn_queries.restype = ctypes.c_int
         lib.oracle_free.argtypes = [ctypes.c_void_p]
         lib.oracle_lognorm_genestats.argtypes = [i64, i64, ctypes.POINTER(i64), i32p, f64p, f64p, f64p,
                                                  f64p, f64p]
@@ -465,6 +470,19 @@ def find_knn(emb, k, want_dist=False):
     return (idx, dist) if want_dist else idx
 
 
+def find_knn_queries(emb, queries, k):
+    """Exact kNN (same arithmetic / tie rule) of the 0-based rows `queries` only: len(queries) x k, 1-based."""
+    emb_f = np.asfortranarray(emb, dtype=np.float64)
+    n, d = emb_f.shape
+    q = np.ascontiguousarray(queries, dtype=np.int64)
+    idx = np.empty((q.size, k), dtype=np.int32)
+    rc = _lib().oracle_knn_queries(_p(emb_f, ctypes.c_double), n, d, k, _p(q, ctypes.c_int64), q.size,
+                                   _p(idx, ctypes.c_int32), None)
+    if rc != 0:
+        raise ValueError(f"oracle_knn_queries failed ({rc})")
+    return idx
+
+
 def find_knn_numpy(emb, k):
     """Same contract in numpy, for cross-checking the C oracle on small inputs:
     sequential fp64 accumulation (numpy never fuses multiply-add), sqrt, (dist, idx) order."""
@@ -489,15 +507,17 @@ def find_knn_numpy(emb, k):
 SNN_TYPES = {"rank": 0, "number": 1, "jaccard": 2}
 
 
-def snn_edges(index, snn_type="rank"):
-    """index: N x k 1-based.  Returns (from, to, weight) in emission order (1-based)."""
+def snn_edges(index, snn_type="rank", j_begin=0, j_end=None):
+    """index: N x k 1-based.  Returns (from, to, weight) in emission order (1-based); j_begin / j_end restrict
+    the emitting cells to the 0-based range [j_begin, j_end) (the edges of a cell depend on the lists only)."""
     idx = np.asfortranarray(index, dtype=np.int32)
     n, k = idx.shape
+    j_end = n if j_end is None else j_end
     ne = ctypes.c_int64(0)
     pf, pt = ctypes.POINTER(ctypes.c_int32)(), ctypes.POINTER(ctypes.c_int32)()
     pw = ctypes.POINTER(ctypes.c_double)()
-    rc = _lib().oracle_snn(_p(idx, ctypes.c_int32), n, k, SNN_TYPES[snn_type], ctypes.byref(ne),
-                           ctypes.byref(pf), ctypes.byref(pt), ctypes.byref(pw))
+    rc = _lib().oracle_snn_range(_p(idx, ctypes.c_int32), n, k, SNN_TYPES[snn_type], j_begin, j_end, ctypes.byref(ne),
+                                 ctypes.byref(pf), ctypes.byref(pt), ctypes.byref(pw))
     if rc != 0:
         raise ValueError(f"oracle_snn failed ({rc})")
     m = ne.value
