@@ -87,7 +87,13 @@ struct cb200_ctx {
     DevBuf<double> part;      // [2]  local sum, local count
     DevBuf<int> flag;         // [4]  device-side error flags
     DevBuf<double> logx;      // [nnz]
-    DevBuf<double> gene_acc;  // [2G] sum y, sum y^2
+    DevBuf<double> gene_acc;  // [2G] sum y, sum y^2 as 64-bit FIXED-POINT integers (scales 2^gs_s1, 2^gs_s2): exact,
+                              // order-independent sums -- the buffer a multi-GPU caller all-reduces as int64
+    DevBuf<int32_t> gs_split; // [N*(S-1)] cut points of the columns at the gene-slab boundaries
+    DevBuf<unsigned int> gs_queue;
+    int gs_s1 = 0, gs_s2 = 0, gs_ybits = 0;
+    bool gs_flag_pending = false, sf_from_input = false;
+    double mean_ls = 0.0;     // mean library size when the size factors are library-size factors, else 0
     DevBuf<double> gene_mean, gene_var;  // [G]
     bool have_sf = false, have_logx = false, have_genestats = false;
     bool logx_values_only = false;      // logcounts computed by cb200_lognorm_values: gene sums still to do

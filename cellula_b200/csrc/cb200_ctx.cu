@@ -100,7 +100,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->colptr.release(); ctx->rowidx.release(); ctx->x.release();
     ctx->libsize.release(); ctx->sf.release(); ctx->part.release(); ctx->flag.release();
-    ctx->logx.release(); ctx->gene_acc.release(); ctx->gene_mean.release(); ctx->gene_var.release();
+    ctx->logx.release(); ctx->gene_acc.release(); ctx->gs_split.release(); ctx->gs_queue.release(); ctx->gene_mean.release(); ctx->gene_var.release();
     ctx->hvg_idx.release(); ctx->hvg_perm.release(); ctx->hbptr.release(); ctx->gram_img.release(); ctx->slot.release(); ctx->hcnt.release(); ctx->hptr.release();
     ctx->hslot.release(); ctx->hval.release(); ctx->gram.release(); ctx->cov.release();
     ctx->mu.release(); ctx->eq.release(); ctx->ew.release(); ctx->ey.release(); ctx->ex.release();
@@ -414,8 +414,8 @@ static int load_common(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, int64_t
     ctx->nnz = nnz;
     ctx->cell_offset = cell_offset;
     ctx->N_total = n_cells_total;
-    CB_CUDA(ctx, ctx->rowidx.ensure((size_t)nnz));
-    CB_CUDA(ctx, ctx->x.ensure((size_t)nnz));
+    CB_CUDA(ctx, ctx->rowidx.ensure((size_t)nnz + 16));   // slack: the bulk copies of the gene-sum kernel round
+    CB_CUDA(ctx, ctx->x.ensure((size_t)nnz + 16));        // their source ranges out to 16 bytes
     // values first: size factors and log-counts need only them (and the column pointers), so that part of
     // the path -- and the copy-out of the log-counts -- runs while the row indices are still arriving
     if (ctx->up_stream == nullptr) {

@@ -95,6 +95,7 @@ extern "C" int cb200_size_factors_local(cb200_ctx *ctx, const double *sf_in)
     CB_CUDA(ctx, ctx->libsize.ensure((size_t)ctx->N));
     CB_CUDA(ctx, ctx->sf.ensure((size_t)ctx->N));
     cb_stage_begin(ctx, ST_COLSUM);
+    ctx->sf_from_input = sf_in != nullptr;
     if (sf_in != nullptr) {
         CB_CUDA(ctx, cudaMemcpyAsync(ctx->libsize.p, sf_in, (size_t)ctx->N * sizeof(double), cudaMemcpyHostToDevice,
                                      ctx->stream));
@@ -128,6 +129,7 @@ extern "C" int cb200_size_factors_finish(cb200_ctx *ctx, double total, int64_t n
     if (sf_out != nullptr)
         CB_TRY(cb200_read_back(ctx, sf_out, ctx->sf.p, (size_t)ctx->N * sizeof(double)));
     CB_CHECK(ctx, h_flag == 0, "size factors should be positive");
+    ctx->mean_ls = ctx->sf_from_input ? 0.0 : mean_ls;
     ctx->have_sf = true;
     return 0;
 }
@@ -145,44 +147,241 @@ extern "C" int cb200_size_factors(cb200_ctx *ctx, const double *sf_in, double *s
 // ---------------------------------------------------------------------------------------
 // K2 + K3
 // ---------------------------------------------------------------------------------------
-// One warp per column.  y = log1p(x / sf) / ln 2 is written back coalesced; the per-gene
-// sums go to L2 with fp64 reductions (RED.ADD.F64 -- no return value, so no round trip).
-__global__ void __launch_bounds__(256)
-k_lognorm_genestats(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
-                    const double *__restrict__ x, const double *__restrict__ sf, int64_t n_cols,
-                    double *__restrict__ logx, double *__restrict__ acc_sum, double *__restrict__ acc_sq)
+// Per-gene sums WITHOUT global fp64 atomics (round 1: 3.9 G RED.ADD.F64 at cfg3 = 24 ms, and a result that
+// depended on the order the reductions landed in).  Now:
+//   * the sums are 64-bit FIXED-POINT integers: Y1 = rn(y 2^s1), Y2 = rn(y^2 2^s2).  Integer addition is
+//     associative, so the result is bit-identical from run to run and for ANY split of the cells over CTAs or
+//     GPUs (the all-reduce is an int64 sum).  s1 = 63 - ceil(log2 N) - ybits, s2 = 63 - ceil(log2 N) - 2 ybits,
+//     with 2^ybits > max y (y <= log2(1 + mean library size) for library-size factors: x <= colsum);
+//   * the genes are cut into slabs of <= GS_SLAB_MAX genes whose (Y1, Y2) table lives in shared memory; the rows
+//     of a dgCMatrix column are sorted, so the slab's entries of a cell are ONE contiguous segment of the column
+//     (k_gs_splits finds the cut points once).  A CTA owns (slab, chunk of cells) work items from a queue;
+//   * one producer warp stages those segments with bulk async copies (TMA engine, mbarrier ring); 15 consumer
+//     warps process one segment at a time: the genes inside a cell are distinct, so the table is updated with
+//     plain 128-bit shared-memory loads / stores (no atomics; ATOMS costs 2 cycles per lane), and a named
+//     barrier separates consecutive cells;
+//   * when the slab changes the table is flushed with integer reductions to global memory (G / S x 2 per CTA).
+// The variance is then formed WITHOUT cancellation error: N Q - S^2 in 128-bit integers (k_genestats_finish).
+#include "cb200_tc.cuh"
+
+#define GS_THREADS 512
+#define GS_CONSUMERS 480
+#define GS_STAGE_ENTRIES 1024
+#define GS_STAGES 5
+#define GS_SLAB_MAX 9600
+#define GS_CHUNK 512          // cells per work item
+#define GS_ITEM_DATA 0
+#define GS_ITEM_FLUSH 1
+#define GS_ITEM_END 2
+
+struct GsItem {
+    int64_t beg;      // first entry of the segment (element index into x / rowidx / logx)
+    double sf;        // size factor of the cell
+    int32_t n;        // entries
+    int32_t off8;     // position of entry `beg` inside the staged 8-byte array
+    int32_t off4;     // ... inside the staged 4-byte array
+    int32_t kind;     // GS_ITEM_*
+    int32_t slab_base;
+    int32_t slab_genes;
+};
+
+// cut points of every column at the slab boundaries: split[c * (S-1) + b] = number of entries of column c with
+// row < (b+1) * slab_genes
+__global__ void k_gs_splits(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx, int64_t n_cols,
+                            int n_slabs, int slab_genes, int32_t *__restrict__ split)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const double ln2 = 0.693147180559945309417232121458;
-    for (int64_t c = warp0; c < n_cols; c += nwarps) {
-        const int64_t b = colptr[c], e = colptr[c + 1];
-        const double s = sf[c];
-        int64_t i = b + lane;
-        for (; i + 96 < e; i += 128) {
-            double v[4];
-            int g[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                v[u] = ld_stream(x + i + 32 * u);
-                g[u] = ld_stream_i(rowidx + i + 32 * u);
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int nb = n_slabs - 1;
+    if (i >= n_cols * nb)
+        return;
+    const int64_t c = i / nb;
+    const int b = (int)(i % nb);
+    const int32_t bound = (b + 1) * slab_genes;
+    const int64_t base = colptr[c];
+    int lo = 0, hi = (int)(colptr[c + 1] - base);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(rowidx + base + mid) < bound)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    split[i] = lo;
+}
+
+__device__ __forceinline__ void gs_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GS_CONSUMERS) : "memory"); }
+
+// FUSED = true : staged 8-byte array = counts; computes the logcounts (and writes them)
+// FUSED = false: staged 8-byte array = the logcounts already in HBM (cb200_lognorm_values ran first)
+template <bool FUSED>
+__global__ void __launch_bounds__(GS_THREADS, 1)
+k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx, const double *__restrict__ v8,
+                 const double *__restrict__ sf, const int32_t *__restrict__ split, int64_t n_cols, int64_t G,
+                 int n_slabs, int slab_genes, double scale1, double scale2, double y_limit,
+                 double *__restrict__ logx, unsigned long long *__restrict__ acc1, unsigned long long *__restrict__ acc2,
+                 unsigned int *__restrict__ queue, int *__restrict__ flag)
+{
+    extern __shared__ __align__(128) unsigned char gs_smem[];
+    using namespace cb200tc;
+    ulonglong2 *tab = reinterpret_cast<ulonglong2 *>(gs_smem);                       // [GS_SLAB_MAX]
+    unsigned char *stage8 = gs_smem + (size_t)GS_SLAB_MAX * 16;                      // [GS_STAGES][(E+2)*8]
+    unsigned char *stage4 = stage8 + (size_t)GS_STAGES * (GS_STAGE_ENTRIES + 2) * 8;  // [GS_STAGES][(E+4)*4]
+    GsItem *items = reinterpret_cast<GsItem *>(stage4 + (size_t)GS_STAGES * (GS_STAGE_ENTRIES + 4) * 4);
+    uint64_t *full = reinterpret_cast<uint64_t *>(items + GS_STAGES);
+    uint64_t *empty = full + GS_STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int g = tid; g < GS_SLAB_MAX; g += GS_THREADS)
+        tab[g] = make_ulonglong2(0ull, 0ull);
+    if (tid == 0) {
+        for (int s = 0; s < GS_STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t n_chunks = (n_cols + GS_CHUNK - 1) / GS_CHUNK;
+    const int64_t n_work = n_chunks * n_slabs;
+    const int nb = n_slabs - 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        int stage = 0;
+        uint32_t phase = 0;
+        int cur_slab = -1, cur_genes = 0;
+        auto next_stage = [&]() {
+            if (++stage == GS_STAGES) {
+                stage = 0;
+                phase ^= 1u;
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                double y = log1p(v[u] / s) / ln2;
-                st_stream(logx + i + 32 * u, y);
-                atomicAdd(acc_sum + g[u], y);
-                atomicAdd(acc_sq + g[u], y * y);
+        };
+        auto acquire = [&]() {            // all lanes wait (the stage's previous occupant has been consumed)
+            mbar_wait(empty + stage, phase ^ 1u, flag);
+        };
+        auto control = [&](int kind, int slab) {
+            acquire();
+            if (lane == 0) {
+                GsItem it;
+                it.beg = 0; it.sf = 1.0; it.n = 0; it.off8 = 0; it.off4 = 0; it.kind = kind;
+                it.slab_base = slab * slab_genes;
+                it.slab_genes = (int)(((int64_t)(slab + 1) * slab_genes < G ? (int64_t)(slab + 1) * slab_genes : G) - (int64_t)slab * slab_genes);
+                items[stage] = it;
+                mbar_arrive(full + stage);
+            }
+            __syncwarp();
+            next_stage();
+        };
+        for (;;) {
+            unsigned int w = 0;
+            if (lane == 0)
+                w = atomicAdd(queue, 1u);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if ((int64_t)w >= n_work)
+                break;
+            const int slab = (int)(w / n_chunks);
+            const int64_t chunk = (int64_t)w % n_chunks;
+            if (slab != cur_slab) {
+                if (cur_slab >= 0)
+                    control(GS_ITEM_FLUSH, cur_slab);
+                cur_slab = slab;
+                const int64_t hi = (int64_t)(slab + 1) * slab_genes < G ? (int64_t)(slab + 1) * slab_genes : G;
+                cur_genes = (int)(hi - (int64_t)slab * slab_genes);
+            }
+            const int64_t c0 = chunk * GS_CHUNK;
+            const int64_t c1 = c0 + GS_CHUNK < n_cols ? c0 + GS_CHUNK : n_cols;
+            for (int64_t cb = c0; cb < c1; cb += 32) {
+                const int64_t c = cb + lane;
+                int64_t beg = 0, end = 0;
+                double s = 1.0;
+                if (c < c1) {
+                    const int64_t b = colptr[c], e = colptr[c + 1];
+                    beg = slab == 0 ? b : b + split[c * nb + slab - 1];
+                    end = slab == nb ? e : b + split[c * nb + slab];
+                    s = sf[c];
+                }
+                const int ncell = (int)(c1 - cb < 32 ? c1 - cb : 32);
+                for (int j = 0; j < ncell; ++j) {
+                    int64_t jb = __shfl_sync(0xffffffffu, beg, j);
+                    const int64_t je = __shfl_sync(0xffffffffu, end, j);
+                    const double js = __shfl_sync(0xffffffffu, s, j);
+                    while (jb < je) {
+                        const int n = (int)(je - jb < GS_STAGE_ENTRIES ? je - jb : GS_STAGE_ENTRIES);
+                        acquire();
+                        if (lane == 0) {
+                            const int64_t a8 = jb & ~1LL, a4 = jb & ~3LL;        // 16-byte aligned sources
+                            const uint32_t bytes8 = (uint32_t)(((jb + n - a8 + 1) & ~1LL) * 8);
+                            const uint32_t bytes4 = (uint32_t)(((jb + n - a4 + 3) & ~3LL) * 4);
+                            GsItem it;
+                            it.beg = jb; it.sf = js; it.n = n; it.off8 = (int)(jb - a8); it.off4 = (int)(jb - a4);
+                            it.kind = GS_ITEM_DATA; it.slab_base = slab * slab_genes; it.slab_genes = cur_genes;
+                            items[stage] = it;
+                            mbar_expect_tx(full + stage, bytes8 + bytes4);
+                            bulk_g2s(stage8 + (size_t)stage * (GS_STAGE_ENTRIES + 2) * 8, v8 + a8, bytes8, full + stage);
+                            bulk_g2s(stage4 + (size_t)stage * (GS_STAGE_ENTRIES + 4) * 4, rowidx + a4, bytes4, full + stage);
+                        }
+                        __syncwarp();
+                        next_stage();
+                        jb += n;
+                    }
+                }
             }
         }
-        for (; i < e; i += 32) {
-            double y = log1p(ld_stream(x + i) / s) / ln2;
-            int g = ld_stream_i(rowidx + i);
-            st_stream(logx + i, y);
-            atomicAdd(acc_sum + g, y);
-            atomicAdd(acc_sq + g, y * y);
+        if (cur_slab >= 0)
+            control(GS_ITEM_FLUSH, cur_slab);
+        control(GS_ITEM_END, 0);
+    } else {
+        // ------------------------------------------------------------------ consumers
+        const int ct = tid - 32;
+        const double ln2 = 0.693147180559945309417232121458;
+        int stage = 0;
+        uint32_t phase = 0;
+        int bad = 0;
+        for (;;) {
+            mbar_wait(full + stage, phase, flag);
+            const GsItem it = items[stage];
+            if (it.kind == GS_ITEM_DATA) {
+                const double *s8 = reinterpret_cast<const double *>(stage8 + (size_t)stage * (GS_STAGE_ENTRIES + 2) * 8) + it.off8;
+                const int32_t *s4 = reinterpret_cast<const int32_t *>(stage4 + (size_t)stage * (GS_STAGE_ENTRIES + 4) * 4) + it.off4;
+                for (int t = ct; t < it.n; t += GS_CONSUMERS) {
+                    double y = s8[t];
+                    if (FUSED) {
+                        y = log1p(y / it.sf) / ln2;
+                        st_stream(logx + it.beg + t, y);
+                    }
+                    const int g = s4[t] - it.slab_base;
+                    if (!(y < y_limit) || g < 0 || g >= it.slab_genes) {   // out of the fixed-point range / malformed row index
+                        bad = 1;
+                        continue;
+                    }
+                    ulonglong2 a = tab[g];
+                    a.x += (unsigned long long)__double2ll_rn(y * scale1);
+                    a.y += (unsigned long long)__double2ll_rn(y * y * scale2);
+                    tab[g] = a;
+                }
+            } else if (it.kind == GS_ITEM_FLUSH) {
+                for (int g = ct; g < it.slab_genes; g += GS_CONSUMERS) {
+                    const ulonglong2 a = tab[g];
+                    if (a.x | a.y) {
+                        atomicAdd(acc1 + it.slab_base + g, a.x);
+                        atomicAdd(acc2 + it.slab_base + g, a.y);
+                        tab[g] = make_ulonglong2(0ull, 0ull);
+                    }
+                }
+            }
+            gs_consumer_sync();             // every update of this item is in the table before the next one starts
+            if (ct == 0)
+                mbar_arrive(empty + stage);
+            if (it.kind == GS_ITEM_END)
+                break;
+            if (++stage == GS_STAGES) {
+                stage = 0;
+                phase ^= 1u;
+            }
         }
+        if (bad)
+            atomicOr(flag, 2);
     }
 }
 
@@ -213,34 +412,44 @@ k_lognorm_values(const int64_t *__restrict__ colptr, const double *__restrict__ 
     }
 }
 
-// K3 alone: per-gene sums of the logcounts already in HBM (same arithmetic as the fused kernel: the
-// values are read back bit for bit)
-__global__ void __launch_bounds__(256)
-k_genestats_from_logx(const int32_t *__restrict__ rowidx, const double *__restrict__ logx, int64_t nnz,
-                      double *__restrict__ acc_sum, double *__restrict__ acc_sq)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += stride) {
-        const double y = ld_stream(logx + i);
-        const int g = ld_stream_i(rowidx + i);
-        atomicAdd(acc_sum + g, y);
-        atomicAdd(acc_sq + g, y * y);
-    }
-}
-
-__global__ void k_genestats_finish(const double *__restrict__ acc_sum, const double *__restrict__ acc_sq, int64_t G,
-                                   double n_total, double *__restrict__ mean, double *__restrict__ var)
+// mean and n-1 variance from the fixed-point sums S = sum Y1 (scale 2^s1), Q = sum Y2 (scale 2^s2):
+//   var = (N Q 2^(2 s1 - s2) - S^2) / (2^(2 s1) N (N - 1)) with the numerator formed exactly in 128-bit integers,
+// so no cancellation error enters; implicit zeros are included by construction.
+__global__ void k_genestats_finish(const unsigned long long *__restrict__ acc1, const unsigned long long *__restrict__ acc2,
+                                   int64_t G, double n_total, int s1, int s2, double *__restrict__ mean,
+                                   double *__restrict__ var)
 {
     int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (g < G) {
-        double s = acc_sum[g], q = acc_sq[g];
-        double m = s / n_total;
-        double ss = q - s * m;  // sum (y - m)^2 over all cells, implicit zeros included
-        if (ss < 0.0)
-            ss = 0.0;
-        mean[g] = m;
-        var[g] = n_total > 1.0 ? ss / (n_total - 1.0) : nan("");
+        const unsigned long long S = acc1[g], Q = acc2[g];
+        const unsigned __int128 nq = ((unsigned __int128)(unsigned long long)n_total * Q) << (2 * s1 - s2);
+        const unsigned __int128 ss = (unsigned __int128)S * S;
+        double num = 0.0;   // independent rounding of y and y^2 can leave a constant gene a hair below zero
+        if (nq > ss) {
+            const unsigned __int128 dlt = nq - ss;
+            num = ldexp((double)(unsigned long long)(dlt >> 64), 64) + (double)(unsigned long long)dlt;
+        }
+        mean[g] = ldexp((double)S, -s1) / n_total;
+        var[g] = n_total > 1.0 ? ldexp(num, -2 * s1) / (n_total * (n_total - 1.0)) : nan("");
     }
+}
+
+// fixed-point scales of the gene sums: 2^ybits > every logcount, sums over n_total cells stay below 2^63
+static void gs_scales(cb200_ctx *ctx)
+{
+    int lgn = 0;
+    while (((int64_t)1 << lgn) < ctx->N_total)
+        ++lgn;
+    int ybits = 6;   // caller-supplied size factors: no a-priori bound, the kernel checks y < 64
+    if (ctx->mean_ls > 0.0) {   // library-size factors: x <= column sum, so x / sf <= mean library size
+        const double ymax = log2(1.0 + ctx->mean_ls) * (1.0 + 1e-9) + 1e-9;
+        ybits = 1;
+        while (ldexp(1.0, ybits) <= ymax)
+            ++ybits;
+    }
+    ctx->gs_ybits = ybits;
+    ctx->gs_s1 = 63 - lgn - ybits;
+    ctx->gs_s2 = 63 - lgn - 2 * ybits;
 }
 
 extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
@@ -249,25 +458,50 @@ extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
         return 1;
     CB_CHECK(ctx, ctx->loaded && ctx->have_sf, "cb200_lognorm_genestats: size factors have not been computed");
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
-    CB_CUDA(ctx, ctx->logx.ensure((size_t)ctx->nnz));
+    CB_CUDA(ctx, ctx->logx.ensure((size_t)ctx->nnz + 16));
     CB_CUDA(ctx, ctx->gene_acc.ensure((size_t)(2 * ctx->G)));
+    CB_CUDA(ctx, ctx->gs_queue.ensure(4));
+    gs_scales(ctx);
+    CB_CHECK(ctx, ctx->gs_s2 >= 8, "cb200_lognorm_genestats: too many cells for the fixed-point gene sums");
+    const int n_slabs = (int)((ctx->G + GS_SLAB_MAX - 1) / GS_SLAB_MAX);
+    const int slab_genes = (int)((ctx->G + n_slabs - 1) / n_slabs);
     CB_TRY(cb200_need_rowidx(ctx));
-    if (!(ctx->have_logx && ctx->logx_values_only))
+    const bool from_logx = ctx->have_logx && ctx->logx_values_only;
+    if (!from_logx)
         cb_stage_begin(ctx, ST_LOGNORM);   // (after cb200_lognorm_values the stage is already open)
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->gene_acc.p, 0, (size_t)(2 * ctx->G) * sizeof(double), ctx->stream));
-    if (ctx->have_logx && ctx->logx_values_only) {
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->gene_acc.p, 0, (size_t)(2 * ctx->G) * sizeof(unsigned long long), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->gs_queue.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    if (n_slabs > 1) {
+        CB_CUDA(ctx, ctx->gs_split.ensure((size_t)ctx->N * (n_slabs - 1)));
+        const int64_t n = ctx->N * (n_slabs - 1);
+        k_gs_splits<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->N, n_slabs,
+                                                                          slab_genes, ctx->gs_split.p);
+        CB_LAUNCH(ctx);
+    }
+    const size_t smem = (size_t)GS_SLAB_MAX * 16 + (size_t)GS_STAGES * ((GS_STAGE_ENTRIES + 2) * 8 + (GS_STAGE_ENTRIES + 4) * 4) +
+                        GS_STAGES * sizeof(GsItem) + 2 * GS_STAGES * sizeof(uint64_t);
+    const int64_t n_work = ((ctx->N + GS_CHUNK - 1) / GS_CHUNK) * n_slabs;
+    const int grid = (int)(n_work < ctx->num_sms ? n_work : ctx->num_sms);
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(ctx->gene_acc.p);
+    const double sc1 = ldexp(1.0, ctx->gs_s1), sc2 = ldexp(1.0, ctx->gs_s2), ylim = ldexp(1.0, ctx->gs_ybits);
+    if (from_logx) {
         // the logcounts exist already (cb200_lognorm_values): only the gene sums are left
-        k_genestats_from_logx<<<ctx->num_sms * 16, 256, 0, ctx->stream>>>(ctx->rowidx.p, ctx->logx.p, ctx->nnz,
-                                                                           ctx->gene_acc.p, ctx->gene_acc.p + ctx->G);
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_genestats_slab<false><<<grid, GS_THREADS, smem, ctx->stream>>>(
+            ctx->colptr.p, ctx->rowidx.p, ctx->logx.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
+            sc2, ylim, nullptr, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p);
         ctx->logx_values_only = false;
     } else {
-        int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
-        k_lognorm_genestats<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->N,
-                                                           ctx->logx.p, ctx->gene_acc.p, ctx->gene_acc.p + ctx->G);
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_genestats_slab<true><<<grid, GS_THREADS, smem, ctx->stream>>>(
+            ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1, sc2,
+            ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p);
     }
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_LOGNORM);
     ctx->have_logx = true;
+    ctx->gs_flag_pending = true;
     return 0;
 }
 
@@ -280,7 +514,7 @@ extern "C" int cb200_lognorm_values(cb200_ctx *ctx)
         return 1;
     CB_CHECK(ctx, ctx->loaded && ctx->have_sf, "cb200_lognorm_values: size factors have not been computed");
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
-    CB_CUDA(ctx, ctx->logx.ensure((size_t)ctx->nnz));
+    CB_CUDA(ctx, ctx->logx.ensure((size_t)ctx->nnz + 16));
     cb_stage_begin(ctx, ST_LOGNORM);
     const int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
     k_lognorm_values<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->x.p, ctx->sf.p, ctx->N, ctx->logx.p);
@@ -298,8 +532,18 @@ extern "C" int cb200_genestats_finish(cb200_ctx *ctx, double *gene_mean, double 
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     CB_CUDA(ctx, ctx->gene_mean.ensure((size_t)ctx->G));
     CB_CUDA(ctx, ctx->gene_var.ensure((size_t)ctx->G));
+    if (ctx->gs_flag_pending) {   // malformed input is reported here, where the caller synchronises anyway
+        int h_flag = 0;
+        CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
+        ctx->gs_flag_pending = false;
+        CB_CHECK(ctx, (h_flag & 4) == 0, "cb200_lognorm_genestats: internal pipeline error (mbarrier timeout)");
+        CB_CHECK(ctx, (h_flag & 2) == 0,
+                 "cb200_lognorm_genestats: a row index is outside [0, n_genes) / rows are not sorted within a column, or a "
+                 "log-count is outside the fixed-point range (size factors far from the library sizes?)");
+    }
+    const unsigned long long *acc = reinterpret_cast<const unsigned long long *>(ctx->gene_acc.p);
     k_genestats_finish<<<(unsigned)((ctx->G + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->gene_acc.p, ctx->gene_acc.p + ctx->G, ctx->G, (double)ctx->N_total, ctx->gene_mean.p, ctx->gene_var.p);
+        acc, acc + ctx->G, ctx->G, (double)ctx->N_total, ctx->gs_s1, ctx->gs_s2, ctx->gene_mean.p, ctx->gene_var.p);
     CB_LAUNCH(ctx);
     if (gene_mean != nullptr)
         CB_TRY(cb200_read_back(ctx, gene_mean, ctx->gene_mean.p, (size_t)ctx->G * sizeof(double)));

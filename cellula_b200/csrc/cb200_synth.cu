@@ -132,8 +132,8 @@ extern "C" int cb200_synth_counts(cb200_ctx *ctx, int64_t n_genes, int64_t n_cel
     CB_CUDA(ctx, cudaMemcpyAsync(&nnz, ctx->colptr.p + n_cells, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->nnz = nnz;
-    CB_CUDA(ctx, ctx->rowidx.ensure((size_t)nnz));
-    CB_CUDA(ctx, ctx->x.ensure((size_t)nnz));
+    CB_CUDA(ctx, ctx->rowidx.ensure((size_t)nnz + 16));
+    CB_CUDA(ctx, ctx->x.ensure((size_t)nnz + 16));
     k_synth_cells<1><<<grid, 256, 0, ctx->stream>>>(n_genes, n_cells, cell_offset, seed, off, P, nullptr, ctx->colptr.p,
                                                     ctx->rowidx.p, ctx->x.p);
     CB_LAUNCH(ctx);

@@ -6,7 +6,7 @@ rank-local (libcellula_b200.so through `CudaShard`); between stages this module 
 small exchanges the path needs:
 
     size factors   all-reduce  [sum of library sizes, #cells]           (2 doubles)
-    gene stats     all-reduce  [sum y, sum y^2] per gene                (2 G doubles)
+    gene stats     all-reduce  [sum y, sum y^2] per gene                (2 G int64, fixed point: exact)
     PCA            all-reduce  H x H cross-product                      (H^2 doubles)
                    all-gather  scores (N x d doubles)
     kNN            all-gather  neighbour index (N x k int32)
@@ -65,7 +65,7 @@ class _DevView:
 
 
 def device_tensor(ptr, shape, dtype, device):
-    typestr = {torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+    typestr = {torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8"}[dtype]
     return torch.as_tensor(_DevView(ptr, shape, typestr), device=device)
 
 
@@ -91,7 +91,8 @@ class CudaShard:
     # K2 + K3
     def gene_acc(self):
         self.ctx.lognorm_genestats_local()
-        return self._view("gene_acc", (2 * self.ctx.n_genes,), torch.float64)
+        # 64-bit fixed-point sums: the all-reduce is an integer sum, exact for any number of ranks
+        return self._view("gene_acc", (2 * self.ctx.n_genes,), torch.int64)
 
     def finish_genestats(self):
         return self.ctx.genestats_finish(want=True)

@@ -43,7 +43,8 @@ enum { CB200_SNN_RANK = 0, CB200_SNN_NUMBER = 1, CB200_SNN_JACCARD = 2 };
 /* device buffers a caller may reduce / gather across GPUs (cb200_device_ptr) */
 enum {
     CB200_BUF_LIBSIZE_PARTIAL = 0, /* double[2]: local sum of library sizes, local #cells    */
-    CB200_BUF_GENE_ACC = 1,        /* double[2*G]: per-gene sum(y), sum(y^2) over local cells */
+    CB200_BUF_GENE_ACC = 1,        /* int64[2*G]: per-gene sum(y), sum(y^2) over local cells as FIXED-POINT
+                                      integers (exact, order-independent): all-reduce with an integer sum */
     CB200_BUF_GRAM = 2,            /* double[H*H]: local X^T X of the HVG log-counts (upper)  */
     CB200_BUF_SCORES = 3,          /* double[n_local*d] row-major: local PCA scores           */
     CB200_BUF_KNN = 4,             /* int32[n_query*k] row-major, 0-based global indices      */
