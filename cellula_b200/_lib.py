@@ -77,6 +77,7 @@ SIGNATURES = {
     "cb200_approx_silhouette": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_vp]),
     "cb200_pairwise_modularity": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "cb200_fetch_edges": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cb200_edges_checksum": (c_int, [c_vp, c_i64p, ctypes.POINTER(ctypes.c_uint64)]),
     "cb200_synth_counts": (c_int, [c_vp, c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_i64p]),
     "cb200_export_csc": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cb200_synth_host": (c_int, [c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_int, c_i64p,
@@ -376,6 +377,12 @@ class Context:
         weight = np.empty(n_edges, np.float64) if weight is None else weight
         self._ck(lib().cb200_fetch_edges(self._h, n_edges, _ptr(frm), _ptr(to), _ptr(weight)))
         return frm[:n_edges], to[:n_edges], weight[:n_edges]
+
+    def edges_checksum(self):
+        """(n_edges, 64-bit order-independent digest) of the edge list resident in HBM."""
+        ne, cs = c_i64(), ctypes.c_uint64()
+        self._ck(lib().cb200_edges_checksum(self._h, ctypes.byref(ne), ctypes.byref(cs)))
+        return ne.value, cs.value
 
     # -- 8(f) rank 2: cluster diagnostics -------------------------------------------
     def approx_silhouette(self, emb, labels, n_clusters, d=None):

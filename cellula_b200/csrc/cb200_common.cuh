@@ -110,7 +110,9 @@ struct cb200_ctx {
     DevBuf<int32_t> hslot;     // [nnz_hvg]
     DevBuf<double> hval;       // [nnz_hvg]
     int64_t nnz_hvg = 0;
-    DevBuf<double> gram;       // [H*H + H]: upper-triangular accumulation of X^T X, + col sums
+    DevBuf<double> gram;       // upper-triangular accumulation of X^T X: fp64 [H*H] (fp64 engines) or two planes of
+                               // 64-bit integers [2][H*H] (tensor-core engine, gram_fixed): lo, hi; value = (lo + hi 2^16) 2^-38
+    bool gram_fixed = false;
     DevBuf<double> cov;        // [H*H]
     DevBuf<double> mu;         // [H]
     DevBuf<double> eq, ew, ey, ex, es, et, etheta, eres, emuv, egs;  // eigen-solver work (egs: split-K partials)

@@ -377,7 +377,7 @@ extern "C" int cb200_device_ptr(cb200_ctx *ctx, int which, void **ptr, int64_t *
     case CB200_BUF_GENE_ACC: *ptr = ctx->gene_acc.p; *bytes = 2 * ctx->G * (int64_t)sizeof(double); break;
     case CB200_BUF_GRAM:
         *ptr = ctx->gram.p;
-        *bytes = ((int64_t)ctx->H * ctx->H) * (int64_t)sizeof(double);
+        *bytes = ((int64_t)ctx->H * ctx->H) * (int64_t)sizeof(double) * (ctx->gram_fixed ? 2 : 1);
         break;
     case CB200_BUF_SCORES: *ptr = ctx->scores.p; *bytes = ctx->N * (int64_t)ctx->d * (int64_t)sizeof(double); break;
     case CB200_BUF_KNN: *ptr = ctx->knn.p; *bytes = ctx->knn_nq * (int64_t)ctx->knn_k * (int64_t)sizeof(int32_t); break;

@@ -16,7 +16,10 @@
 // cell chunk c (128 cells) three 16 KB planes.  A CTA of k_gram_tc owns a 128 x 64 output tile (I, J)
 // for a slice of the chunks: per chunk one 48 KB + three 8 KB bulk copies, 9 digit products x 4
 // tcgen05.mma (M = 128, N = 64, K = 32).  Warp roles: 0 = bulk-copy producer, 1 = MMA issuer,
-// 2-5 = flush (TMEM -> fp64 -> RED.ADD.F64 into the H x H buffer).
+// 2-5 = flush.  The flush keeps the sums as INTEGERS: the five exact order sums are packed into two 64-bit
+// words per entry (lo = S0 + S1 2^8, hi = S2 + S3 2^8 + S4 2^16, value = (lo + hi 2^16) 2^-38) and added with
+// integer reductions, so the cross-product is bit-identical from run to run and for any split of the cells over
+// CTAs or GPUs (the multi-GPU all-reduce is an int64 sum); it is converted to fp64 once, in k_cov_from_gram.
 #include <cstdlib>
 #include <cstring>
 
@@ -111,8 +114,8 @@ k_gram_img(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, 
 }
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
-k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int H, double *__restrict__ gram,
-          int *__restrict__ err_flag)
+k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int H,
+          unsigned long long *__restrict__ gram_lo, unsigned long long *__restrict__ gram_hi, int *__restrict__ err_flag)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)GT_STAGES * GT_STAGE_BYTES);
@@ -208,35 +211,39 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
             }
         }
     } else {
-        // ===== flush: thread = output row; fp64 combination of the five exact integer sums =====
+        // ===== flush: thread = output row; the five exact integer sums packed into two 64-bit words =====
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int grow = I * GT_M + row;
-        const double unscale = 1.0 / ((double)(1 << GT_SCALE_BITS) * (double)(1 << GT_SCALE_BITS));
         for (int64_t f = 0; f < n_flush; ++f) {
             mbar_wait(tfull, (uint32_t)(f & 1), err_flag);
             tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < GT_N / 32; ++half) {
-                double acc[32];
+                unsigned long long lo[32], hi[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                    acc[c] = 0.0;
+                    lo[c] = hi[c] = 0ull;
 #pragma unroll
                 for (int o = 0; o < GT_ORDERS; ++o) {
                     uint32_t r[32];
                     tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(o * GT_N + half * 32), r);
                     tmem_ld_wait();
-                    const double wgt = (double)(1ull << (8 * o));  // 2^(8 o)
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        acc[c] += (double)(int)r[c] * wgt;
+                    for (int c = 0; c < 32; ++c) {
+                        if (o < 2)
+                            lo[c] += (unsigned long long)r[c] << (8 * o);
+                        else
+                            hi[c] += (unsigned long long)r[c] << (8 * (o - 2));
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     const int gcol = J * GT_N + half * 32 + c;
-                    if (grow < H && gcol < H && gcol >= grow && acc[c] != 0.0)
-                        atomicAdd(gram + (int64_t)grow * H + gcol, acc[c] * unscale);
+                    if (grow < H && gcol < H && gcol >= grow && (lo[c] | hi[c]) != 0ull) {
+                        atomicAdd(gram_lo + (int64_t)grow * H + gcol, lo[c]);
+                        atomicAdd(gram_hi + (int64_t)grow * H + gcol, hi[c]);
+                    }
                 }
             }
             tc_fence_before();
@@ -297,7 +304,9 @@ int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used)
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     CB_TRACE("gram_tc: img launched");
     dim3 grid((unsigned)n_pairs, (unsigned)ksplit);
-    k_gram_tc<<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, ctx->gram.p, ctx->flag.p + 3);
+    unsigned long long *glo = reinterpret_cast<unsigned long long *>(ctx->gram.p);
+    k_gram_tc<<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, glo, glo + (size_t)H * H,
+                                                       ctx->flag.p + 3);
     CB_LAUNCH(ctx);
     int h_flag = 0;
     CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p + 3, sizeof(int)));

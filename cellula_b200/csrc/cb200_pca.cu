@@ -257,15 +257,24 @@ __global__ void k_rotation_out(const double *__restrict__ rot, const int32_t *__
     }
 }
 
-// cov[i][j] = (G[min][max] - N mu_i mu_j) / (N - 1)
+// cov[i][j] = (G[min][max] - N mu_i mu_j) / (N - 1).  fixed != 0: G is the integer cross-product of the tensor-core
+// engine, two 64-bit words per entry (cb200_gram_tc.cu): value = (lo + hi 2^16) 2^-38
 __global__ void k_cov_from_gram(const double *__restrict__ gram, const double *__restrict__ mu, int H, double n_total,
-                                double *__restrict__ cov)
+                                double *__restrict__ cov, int fixed)
 {
     int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx < (int64_t)H * H) {
         int i = (int)(idx / H), j = (int)(idx % H);
         int r = i < j ? i : j, c = i < j ? j : i;
-        cov[idx] = (gram[(int64_t)r * H + c] - n_total * mu[i] * mu[j]) / (n_total - 1.0);
+        double g;
+        if (fixed) {
+            const unsigned long long *lo = reinterpret_cast<const unsigned long long *>(gram);
+            const unsigned long long *hi = lo + (int64_t)H * H;
+            g = ldexp((double)hi[(int64_t)r * H + c], 16 - 38) + ldexp((double)lo[(int64_t)r * H + c], -38);
+        } else {
+            g = gram[(int64_t)r * H + c];
+        }
+        cov[idx] = (g - n_total * mu[i] * mu[j]) / (n_total - 1.0);
     }
 }
 
@@ -955,7 +964,7 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     CB_CUDA(ctx, ctx->mu.ensure((size_t)H));
     CB_CUDA(ctx, ctx->hcnt.ensure((size_t)ctx->N));
     CB_CUDA(ctx, ctx->hptr.ensure((size_t)ctx->N + 1));
-    CB_CUDA(ctx, ctx->gram.ensure((size_t)H * H));
+    CB_CUDA(ctx, ctx->gram.ensure((size_t)2 * H * H));   // two 64-bit words per entry for the integer engine
 
     CB_TRY(cb200_need_rowidx(ctx));
     cb_stage_begin(ctx, ST_HVG_EXTRACT);
@@ -988,14 +997,16 @@ extern "C" int cb200_pca_gram_local(cb200_ctx *ctx, const int32_t *hvg_idx, int 
     CB_TRACE("gram_local: hvg stage launched");
 
     cb_stage_begin(ctx, ST_GRAM);
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->gram.p, 0, (size_t)H * H * sizeof(double), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->gram.p, 0, (size_t)2 * H * H * sizeof(double), ctx->stream));
     // engine: tensor cores (error-free int8 digit products) by default; CB200_GRAM_ENGINE=tiled|atomic
     // selects the exact fp64 kernels (also used when a value is outside the fixed-point range)
     const char *geng = getenv("CB200_GRAM_ENGINE");
     int used_tc = 0;
-    if ((geng == nullptr && ctx->N >= 1024) || (geng != nullptr && strcmp(geng, "tc") == 0))
+    // (the choice must not depend on the shard: N_total, not N, so that every rank of a multi-GPU job agrees)
+    if ((geng == nullptr && ctx->N_total >= 1024) || (geng != nullptr && strcmp(geng, "tc") == 0))
         CB_TRY(cb200_gram_tc(ctx, nb, &used_tc));
     ctx->tm.gram_engine = used_tc ? 3 : ((geng != nullptr && strcmp(geng, "atomic") == 0) ? 1 : 2);
+    ctx->gram_fixed = used_tc != 0;
     if (used_tc) {
         // done
     } else if (geng != nullptr && strcmp(geng, "atomic") == 0) {
@@ -1073,7 +1084,8 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
     cb_stage_begin(ctx, ST_EIG);
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 1, 0, sizeof(int), ctx->stream));
     k_cov_from_gram<<<(unsigned)(((int64_t)H * H + 255) / 256), 256, 0, ctx->stream>>>(ctx->gram.p, ctx->mu.p, H,
-                                                                                      (double)Nt, ctx->cov.p);
+                                                                                      (double)Nt, ctx->cov.p,
+                                                                                      ctx->gram_fixed ? 1 : 0);
     CB_LAUNCH(ctx);
     // total variance of the HVG block = sum of the K3 variances of the selected genes
     k_gather_f64<<<(H + 255) / 256, 256, 0, ctx->stream>>>(ctx->gene_var.p, ctx->hvg_idx.p, H, ctx->ex.p);

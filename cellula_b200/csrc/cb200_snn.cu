@@ -803,6 +803,52 @@ extern "C" int cb200_fetch_edges(cb200_ctx *ctx, int64_t n_edges, int32_t *from,
     return 0;
 }
 
+// order-independent digest of the edge list resident in HBM: sum over the edges of a 64-bit hash of
+// (from, to, bit pattern of the weight), modulo 2^64.  Shards add up (sum over ranks), so an N-GPU run can be
+// compared with the single-GPU run without moving 8 GB of edges.
+__device__ __forceinline__ unsigned long long cs_mix(unsigned long long z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_edge_checksum(const int32_t *__restrict__ ef, const int32_t *__restrict__ et,
+                                                       const double *__restrict__ ew, int64_t ne,
+                                                       unsigned long long *__restrict__ out)
+{
+    unsigned long long s = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += stride) {
+        const unsigned long long key = ((unsigned long long)(uint32_t)ef[e] << 32) | (unsigned long long)(uint32_t)et[e];
+        s += cs_mix(cs_mix(key) ^ (unsigned long long)__double_as_longlong(ew[e]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s != 0)
+        atomicAdd(out, s);
+}
+
+extern "C" int cb200_edges_checksum(cb200_ctx *ctx, int64_t *n_edges, uint64_t *checksum)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, n_edges != nullptr && checksum != nullptr, "cb200_edges_checksum: NULL output argument");
+    CB_CHECK(ctx, ctx->efrom.p != nullptr || ctx->n_edges == 0, "cb200_edges_checksum: no edge list in the context");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(ctx->maxnrm.p);
+    CB_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+    if (ctx->n_edges > 0) {
+        k_edge_checksum<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->efrom.p, ctx->eto.p, ctx->ew8.p, ctx->n_edges, d);
+        CB_LAUNCH(ctx);
+    }
+    unsigned long long h = 0;
+    CB_TRY(cb200_read_back(ctx, &h, d, sizeof(h)));
+    *n_edges = ctx->n_edges;
+    *checksum = (uint64_t)h;
+    return 0;
+}
+
 extern "C" int cb200_free_edges(int32_t *from, int32_t *to, double *weight)
 {
     if (from != nullptr)

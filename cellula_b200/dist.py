@@ -7,7 +7,7 @@ small exchanges the path needs:
 
     size factors   all-reduce  [sum of library sizes, #cells]           (2 doubles)
     gene stats     all-reduce  [sum y, sum y^2] per gene                (2 G int64, fixed point: exact)
-    PCA            all-reduce  H x H cross-product                      (H^2 doubles)
+    PCA            all-reduce  H x H cross-product                      (2 H^2 int64, fixed point: exact)
                    all-gather  scores (N x d doubles)
     kNN            all-gather  neighbour index (N x k int32)
     SNN            none: every rank emits the edges of a contiguous range of cells j (ascending j; the ranges
@@ -112,8 +112,11 @@ class CudaShard:
     # K5
     def gram(self, hvg_idx):
         self.ctx.pca_gram_local(hvg_idx)
+        ptr, nbytes = self.ctx.device_ptr("gram")
         h = len(hvg_idx)
-        return self._view("gram", (h * h,), torch.float64)
+        if nbytes == 2 * h * h * 8:     # tensor-core engine: 64-bit fixed-point planes, exact integer all-reduce
+            return device_tensor(ptr, (2 * h * h,), torch.int64, self.device)
+        return device_tensor(ptr, (h * h,), torch.float64, self.device)
 
     def finish_pca(self, d, n_hvg, want_scores=True, scores_out=None):
         res = self.ctx.pca_finish(d, n_hvg, want_scores=want_scores, scores_out=scores_out)

@@ -45,7 +45,8 @@ enum {
     CB200_BUF_LIBSIZE_PARTIAL = 0, /* double[2]: local sum of library sizes, local #cells    */
     CB200_BUF_GENE_ACC = 1,        /* int64[2*G]: per-gene sum(y), sum(y^2) over local cells as FIXED-POINT
                                       integers (exact, order-independent): all-reduce with an integer sum */
-    CB200_BUF_GRAM = 2,            /* double[H*H]: local X^T X of the HVG log-counts (upper)  */
+    CB200_BUF_GRAM = 2,            /* local X^T X of the HVG log-counts (upper triangle): int64[2*H*H] (fixed
+                                      point, gram_engine 3: all-reduce with an integer sum) or double[H*H]   */
     CB200_BUF_SCORES = 3,          /* double[n_local*d] row-major: local PCA scores           */
     CB200_BUF_KNN = 4,             /* int32[n_query*k] row-major, 0-based global indices      */
     CB200_BUF_SIZE_FACTORS = 5,    /* double[n_local]                                         */
@@ -200,6 +201,11 @@ int cb200_free_edges(int32_t *from, int32_t *to, double *weight);
 /* Copies the n_edges edges left in HBM by the last cb200_snn / cb200_snn_device / cb200_snn_resident
  * call into caller-owned arrays (what the R shim does with freshly allocated R vectors). */
 int cb200_fetch_edges(cb200_ctx *ctx, int64_t n_edges, int32_t *from, int32_t *to, double *weight);
+
+/* Order-independent digest of the edge list left in HBM by the last cb200_snn* call: sum over the edges of a
+ * 64-bit hash of (from, to, weight bits) modulo 2^64, and the edge count.  The digests of the shards of a
+ * multi-GPU run add up to the single-GPU digest (bench.py and the tests compare them). */
+int cb200_edges_checksum(cb200_ctx *ctx, int64_t *n_edges, uint64_t *checksum);
 
 /* ---- per-resolution cluster diagnostics -------------------------------------------
  * Replaces: bluster::approxSilhouette(space, clusters) and bluster::pairwiseModularity(g, clusters, ...)
