@@ -69,6 +69,7 @@ struct cb200_ctx {
     bool own_stream = false;
     unsigned char *pin_scratch = nullptr;  // pinned staging of cb200_read_back (CB200_PIN_SCRATCH bytes)
     struct CopyWorker *copier = nullptr;  // paced background device->host copies (cb200_ctx.cu)
+    struct StagePool *stage = nullptr;    // pinned staging ring + memcpy threads for pageable host memory (cb200_stage.cu)
     std::string err;
 
     // ---- a1: counts shard (CSC, genes x local cells)
@@ -181,7 +182,9 @@ struct cb200_ctx {
     DevBuf<int32_t> snn_tcnt;         // [nj] upper bound of the partners of every cell
     DevBuf<int64_t> snn_toff;         // [nj+1] its scan: slices of the partner store
     DevBuf<uint32_t> snn_tmp_h, snn_tmp_rc;  // partner store written by the counting pass, read by the emission
-    DevBuf<int32_t> snn_jlist;        // [nj + 1] cells left to the merge kernel (+ their count)
+    DevBuf<int32_t> snn_jlist;        // [(tiers + 1) * nj] cells of every hash-table tier, then the cells left to the merge kernel
+    DevBuf<int> snn_nlists;           // [tiers + 1] their counts
+    int snn_n_merge = 0;
     DevBuf<unsigned char> snn_flag;   // [nj] cells left to the merge kernel (too many partners for the hash table)
 
     // ---- cluster diagnostics (cb200_diag.cu)
@@ -265,6 +268,20 @@ int cb200_copy_async(cb200_ctx *ctx, void *dst, const void *src, size_t bytes);
 int cb200_copies_wait(cb200_ctx *ctx);
 void cb200_copies_shutdown(cb200_ctx *ctx);
 
+// Copies between caller memory and HBM (cb200_stage.cu).  Page-locked caller memory: one cudaMemcpyAsync.  Pageable
+// memory (R vectors): chunks through a pinned ring filled / drained by several host threads.  cb200_h2d returns when
+// the source is no longer needed by the host side (pageable) or has been queued (pinned: keep it valid until the
+// stream has passed it); cb200_d2h is complete on return for pageable destinations, asynchronous for pinned ones.
+int cb200_h2d(cb200_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes, cudaStream_t stream);
+int cb200_d2h(cb200_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes, cudaStream_t stream);
+int cb200_d2h_worker(cb200_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes, cudaStream_t stream);
+int cb200_upload_background(cb200_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes, cudaStream_t stream,
+                            cudaEvent_t done);
+int cb200_upload_join(cb200_ctx *ctx);
+void cb200_stage_shutdown(cb200_ctx *ctx);
+bool cb200_host_is_pinned(const void *p);
+int cb200_stage_thread_count(cb200_ctx *ctx);
+
 // Small synchronous transfers (flags, counters, a few KB of statistics or indices) that do NOT go
 // through the copy engines: a kernel moves the bytes between device memory and a pinned, device-
 // mapped scratch buffer over PCIe.  A copy-engine transfer issued while a background copy is in
@@ -329,6 +346,39 @@ __device__ __forceinline__ int ld_stream_i(const int *p)
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// logcount of the path: log2(1 + x / sf) with rs = 1 / sf (computed once per cell, __drcp-exact 1.0 / sf).
+// The reference evaluates log1p(x / sf) / log(2) (scuttle::normalizeCounts); this is the same function to ~1e-15
+// relative (contract: 1e-6), restated so that it costs ~40 instructions instead of the ~190 of log1p() plus two
+// fp64 divisions: at cfg3 there are 2e9 of them and the pass was instruction-bound, not HBM-bound.
+//   u = 1 + t rounded, c = t - (u - 1) its rounding error (exact);  u = 2^e m, m in [sqrt(1/2), sqrt(2));
+//   log(m) by fdlibm's atanh series in s = f / (2 + f), f = m - 1;  log2(1 + t) = e + (log(m) + c / u) / ln 2.
+// Every kernel that produces logcounts calls this one function, so all paths give identical bits.
+__device__ __forceinline__ double cb_logcount(double x, double rs)
+{
+    const double t = x * rs;
+    const double u = 1.0 + t;
+    const double c = t - (u - 1.0);
+    if (!(u > 0.0))
+        return nan("");                              // x / sf <= -1 (not a count) or NaN
+    const long long bits = __double_as_longlong(u);
+    int hi = (int)(bits >> 32);
+    int e = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int carry = (hi + 0x95f64) & 0x100000;   // mantissa >= sqrt(2): halve it, bump the exponent
+    e += carry >> 20;
+    const double m = __hiloint2double(hi | (carry ^ 0x3ff00000), (int)(unsigned int)bits);
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+    const double t2 = z * (6.666666666666735130e-01 + w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 +
+                                                                                          w * 1.479819860511658591e-01)));
+    const double hfsq = 0.5 * f * f;
+    const double lm = f - (hfsq - s * (hfsq + (t1 + t2)));          // log(m)
+    const double corr = c * (double)__frcp_rn((float)u);            // c / u: a 2^-53-sized term, fp32 reciprocal is plenty
+    return (double)e + (lm + corr) * 1.4426950408889634074;
+}
+
 __device__ __forceinline__ void st_stream(double *p, double v)
 {
     asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");

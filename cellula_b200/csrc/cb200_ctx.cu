@@ -97,6 +97,11 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     if (ctx == nullptr)
         return 0;
     cudaSetDevice(ctx->device);
+    // background work first: the copy worker and the row-index uploader still read / write the buffers freed below
+    cb200_copies_shutdown(ctx);
+    cb200_stage_shutdown(ctx);
+    if (ctx->up_stream != nullptr)
+        cudaStreamSynchronize(ctx->up_stream);
     cudaStreamSynchronize(ctx->stream);
     ctx->colptr.release(); ctx->rowidx.release(); ctx->x.release();
     ctx->libsize.release(); ctx->sf.release(); ctx->part.release(); ctx->flag.release();
@@ -118,7 +123,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->hosts_u.release(); ctx->hosts.release(); ctx->ecnt.release(); ctx->eptr.release();
     ctx->bcnt.release(); ctx->efrom.release(); ctx->eto.release(); ctx->ew8.release();
     ctx->diag_lab.release(); ctx->diag_i.release(); ctx->diag_ef.release(); ctx->diag_d.release(); ctx->diag_ew.release(); ctx->diag_cnt.release();
-    ctx->scan_blk.release(); ctx->snn_bounds.release(); ctx->snn_flag.release(); ctx->snn_jlist.release(); ctx->snn_tcnt.release(); ctx->snn_toff.release(); ctx->snn_tmp_h.release(); ctx->snn_tmp_rc.release(); ctx->snn_cut.release();
+    ctx->scan_blk.release(); ctx->snn_bounds.release(); ctx->snn_flag.release(); ctx->snn_jlist.release(); ctx->snn_nlists.release(); ctx->snn_tcnt.release(); ctx->snn_toff.release(); ctx->snn_tmp_h.release(); ctx->snn_tmp_rc.release(); ctx->snn_cut.release();
     if (ctx->snn_bounds_h != nullptr)
         cudaFreeHost(ctx->snn_bounds_h);
     if (ctx->pin_scratch != nullptr)
@@ -127,9 +132,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
         cudaEventDestroy(ctx->ev[s][0]);
         cudaEventDestroy(ctx->ev[s][1]);
     }
-    cb200_copies_shutdown(ctx);
     if (ctx->up_stream != nullptr) {
-        cudaStreamSynchronize(ctx->up_stream);
         cudaStreamDestroy(ctx->up_stream);
         cudaEventDestroy(ctx->ev_x);
         cudaEventDestroy(ctx->ev_rowidx);
@@ -169,7 +172,7 @@ int cb200_read_back(cb200_ctx *ctx, void *dst, const void *src, size_t bytes)
         memcpy(dst, ctx->pin_scratch, bytes);
         return 0;
     }
-    CB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CB_TRY(cb200_d2h(ctx, dst, src, bytes, ctx->stream));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -187,7 +190,7 @@ int cb200_write_small(cb200_ctx *ctx, void *dev_dst, const void *src, size_t byt
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return 0;
     }
-    CB_CUDA(ctx, cudaMemcpyAsync(dev_dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CB_TRY(cb200_h2d(ctx, dev_dst, src, bytes, ctx->stream));
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -210,6 +213,7 @@ struct CopyWorker {
     int pending = 0;
     cudaError_t err = cudaSuccess;
     int device = 0;
+    cb200_ctx *ctx = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
 };
@@ -243,6 +247,13 @@ static void copy_worker_main(CopyWorker *w)
         }
         cudaError_t e = cudaStreamWaitEvent(w->stream, job.after, 0);
         size_t i = 0;
+        if (e == cudaSuccess && !cb200_host_is_pinned(job.dst)) {
+            // pageable destination (an R vector): device -> pinned ring -> caller memory with the memcpy threads;
+            // chunks are 16 MB, so the short reads of the stages are not starved either
+            if (cb200_d2h_worker(w->ctx, job.dst, job.src, job.bytes, w->stream) != 0)
+                e = cudaErrorUnknown;
+            job.bytes = 0;
+        }
         for (size_t off = 0; off < job.bytes && e == cudaSuccess; off += COPY_CHUNK, ++i) {
             const size_t nb = job.bytes - off < COPY_CHUNK ? job.bytes - off : COPY_CHUNK;
             if (i >= 1)
@@ -271,6 +282,7 @@ int cb200_copy_async(cb200_ctx *ctx, void *dst, const void *src, size_t bytes)
     if (ctx->copier == nullptr) {
         CopyWorker *w = new CopyWorker();
         w->device = ctx->device;
+        w->ctx = ctx;
         cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
         for (int i = 0; i < 2 && e == cudaSuccess; ++i)
             e = cudaEventCreateWithFlags(&w->chunk_ev[i], cudaEventDisableTiming);
@@ -409,6 +421,9 @@ static int load_common(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, int64_t
     CB_CHECK(ctx, cell_offset >= 0 && cell_offset + n_cells <= n_cells_total,
              "cb200_load_csc: shard [%lld, %lld) does not fit n_cells_total=%lld", (long long)cell_offset,
              (long long)(cell_offset + n_cells), (long long)n_cells_total);
+    // a background copy-out of the previous matrix's results may still be reading buffers that are re-used below
+    CB_TRY(cb200_copies_wait(ctx));
+    CB_TRY(cb200_upload_join(ctx));
     ctx->G = n_genes;
     ctx->N = n_cells;
     ctx->nnz = nnz;
@@ -423,13 +438,18 @@ static int load_common(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, int64_t
         CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_x, cudaEventDisableTiming));
         CB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rowidx, cudaEventDisableTiming));
     }
-    CB_CUDA(ctx, cudaMemcpyAsync(ctx->x.p, values, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice,
-                                 ctx->stream));
+    // (pageable host memory -- R vectors -- goes through the pinned staging ring, cb200_stage.cu)
+    CB_TRY(cb200_h2d(ctx, ctx->x.p, values, (size_t)nnz * sizeof(double), ctx->stream));
     CB_CUDA(ctx, cudaEventRecord(ctx->ev_x, ctx->stream));
     CB_CUDA(ctx, cudaStreamWaitEvent(ctx->up_stream, ctx->ev_x, 0));
-    CB_CUDA(ctx, cudaMemcpyAsync(ctx->rowidx.p, rowidx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice,
-                                 ctx->up_stream));
-    CB_CUDA(ctx, cudaEventRecord(ctx->ev_rowidx, ctx->up_stream));
+    if ((size_t)nnz * sizeof(int32_t) >= (64u << 20) && !cb200_host_is_pinned(rowidx)) {
+        // the indices keep arriving on a thread of their own after this call has returned
+        CB_TRY(cb200_upload_background(ctx, ctx->rowidx.p, rowidx, (size_t)nnz * sizeof(int32_t), ctx->up_stream,
+                                       ctx->ev_rowidx));
+    } else {
+        CB_TRY(cb200_h2d(ctx, ctx->rowidx.p, rowidx, (size_t)nnz * sizeof(int32_t), ctx->up_stream));
+        CB_CUDA(ctx, cudaEventRecord(ctx->ev_rowidx, ctx->up_stream));
+    }
     ctx->rowidx_pending = true;
     ctx->logx_values_only = false;
     ctx->loaded = true;
@@ -441,6 +461,7 @@ static int load_common(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, int64_t
 int cb200_need_rowidx(cb200_ctx *ctx)
 {
     if (ctx->rowidx_pending) {
+        CB_TRY(cb200_upload_join(ctx));   // the event is recorded by the uploader thread when the last chunk is queued
         CB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_rowidx, 0));
         ctx->rowidx_pending = false;
     }
@@ -460,6 +481,8 @@ extern "C" int cb200_load_csc(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, 
     int64_t nnz = colptr[n_cells] - base;
     CB_CHECK(ctx, base == 0, "cb200_load_csc: colptr[0] must be 0 (rebase the shard's column pointers)");
     CB_CHECK(ctx, nnz >= 0, "cb200_load_csc: colptr is not non-decreasing");
+    for (int64_t c = 0; c < n_cells; ++c)
+        CB_CHECK(ctx, colptr[c + 1] >= colptr[c], "cb200_load_csc: colptr is not non-decreasing (column %lld)", (long long)c);
     cb_stage_begin(ctx, ST_H2D);
     CB_CUDA(ctx, ctx->colptr.ensure((size_t)n_cells + 1));
     CB_CUDA(ctx, cudaMemcpyAsync(ctx->colptr.p, colptr, (size_t)(n_cells + 1) * sizeof(int64_t),
@@ -481,6 +504,8 @@ extern "C" int cb200_load_csc_i32(cb200_ctx *ctx, int64_t n_genes, int64_t n_cel
     CB_CHECK(ctx, colptr[0] == 0, "cb200_load_csc_i32: p[0] must be 0");
     int64_t nnz = colptr[n_cells];
     CB_CHECK(ctx, nnz >= 0, "cb200_load_csc_i32: p is not non-decreasing");
+    for (int64_t c = 0; c < n_cells; ++c)
+        CB_CHECK(ctx, colptr[c + 1] >= colptr[c], "cb200_load_csc_i32: p is not non-decreasing (column %lld)", (long long)c);
     cb_stage_begin(ctx, ST_H2D);
     CB_CUDA(ctx, ctx->colptr.ensure((size_t)n_cells + 1));
     CB_CUDA(ctx, ctx->stage_i.ensure((size_t)n_cells + 1));

@@ -204,7 +204,7 @@ extern "C" int cb200_approx_silhouette(cb200_ctx *ctx, const double *emb, int64_
     } else {
         CB_CUDA(ctx, ctx->stage_d.ensure((size_t)n * d));
         CB_CUDA(ctx, ctx->emb.ensure((size_t)n * d));
-        CB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d.p, emb, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CB_TRY(cb200_h2d(ctx, ctx->stage_d.p, emb, (size_t)n * d * sizeof(double), ctx->stream));
         k_colmajor_to_rowmajor_d<<<(unsigned)((n * d + 255) / 256), 256, 0, ctx->stream>>>(ctx->stage_d.p, n, d, ctx->emb.p);
         CB_LAUNCH(ctx);
         E = ctx->emb.p;
@@ -263,9 +263,9 @@ extern "C" int cb200_pairwise_modularity(cb200_ctx *ctx, const int32_t *from, co
                      "cb200_pairwise_modularity: edge %lld out of range [1, n]", (long long)e);
         CB_CUDA(ctx, ctx->diag_ef.ensure((size_t)(2 * n_edges + 1)));
         CB_CUDA(ctx, ctx->diag_ew.ensure((size_t)n_edges + 1));
-        CB_CUDA(ctx, cudaMemcpyAsync(ctx->diag_ef.p, from, (size_t)n_edges * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        CB_CUDA(ctx, cudaMemcpyAsync(ctx->diag_ef.p + n_edges, to, (size_t)n_edges * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        CB_CUDA(ctx, cudaMemcpyAsync(ctx->diag_ew.p, weight, (size_t)n_edges * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CB_TRY(cb200_h2d(ctx, ctx->diag_ef.p, from, (size_t)n_edges * sizeof(int32_t), ctx->stream));
+        CB_TRY(cb200_h2d(ctx, ctx->diag_ef.p + n_edges, to, (size_t)n_edges * sizeof(int32_t), ctx->stream));
+        CB_TRY(cb200_h2d(ctx, ctx->diag_ew.p, weight, (size_t)n_edges * sizeof(double), ctx->stream));
         dfrom = ctx->diag_ef.p;
         dto = ctx->diag_ef.p + n_edges;
         dw = ctx->diag_ew.p;

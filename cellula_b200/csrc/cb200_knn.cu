@@ -559,8 +559,7 @@ static int knn_core(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int
         CB_CUDA(ctx, ctx->stage_i.ensure((size_t)nq * k));
         k_knn_to_r_layout<<<(unsigned)((nq * k + 255) / 256), 256, 0, ctx->stream>>>(ctx->knn.p, nq, k, ctx->stage_i.p);
         CB_LAUNCH(ctx);
-        CB_CUDA(ctx, cudaMemcpyAsync(index_out, ctx->stage_i.p, (size_t)nq * k * sizeof(int32_t),
-                                     cudaMemcpyDeviceToHost, ctx->stream));
+        CB_TRY(cb200_d2h(ctx, index_out, ctx->stage_i.p, (size_t)nq * k * sizeof(int32_t), ctx->stream));
         cb_stage_end(ctx, ST_D2H);
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -595,8 +594,7 @@ extern "C" int cb200_knn(cb200_ctx *ctx, const double *emb, int64_t n_total, int
     cb_stage_begin(ctx, ST_H2D);
     CB_CUDA(ctx, ctx->stage_d.ensure((size_t)n_total * d));
     CB_CUDA(ctx, ctx->emb.ensure((size_t)n_total * d));
-    CB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_d.p, emb, (size_t)n_total * d * sizeof(double), cudaMemcpyHostToDevice,
-                                 ctx->stream));
+    CB_TRY(cb200_h2d(ctx, ctx->stage_d.p, emb, (size_t)n_total * d * sizeof(double), ctx->stream));
     k_colmajor_to_rowmajor<<<(unsigned)((n_total * d + 255) / 256), 256, 0, ctx->stream>>>(ctx->stage_d.p, n_total, d,
                                                                                            ctx->emb.p);
     CB_LAUNCH(ctx);

@@ -97,8 +97,7 @@ extern "C" int cb200_size_factors_local(cb200_ctx *ctx, const double *sf_in)
     cb_stage_begin(ctx, ST_COLSUM);
     ctx->sf_from_input = sf_in != nullptr;
     if (sf_in != nullptr) {
-        CB_CUDA(ctx, cudaMemcpyAsync(ctx->libsize.p, sf_in, (size_t)ctx->N * sizeof(double), cudaMemcpyHostToDevice,
-                                     ctx->stream));
+        CB_TRY(cb200_h2d(ctx, ctx->libsize.p, sf_in, (size_t)ctx->N * sizeof(double), ctx->stream));
     } else {
         int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
         k_colsum_csc<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->x.p, ctx->N, ctx->libsize.p);
@@ -176,7 +175,7 @@ extern "C" int cb200_size_factors(cb200_ctx *ctx, const double *sf_in, double *s
 
 struct GsItem {
     int64_t beg;      // first entry of the segment (element index into x / rowidx / logx)
-    double sf;        // size factor of the cell
+    double sf;        // 1 / size factor of the cell
     int32_t n;        // entries
     int32_t off8;     // position of entry `beg` inside the staged 8-byte array
     int32_t off4;     // ... inside the staged 4-byte array
@@ -299,7 +298,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                     const int64_t b = colptr[c], e = colptr[c + 1];
                     beg = slab == 0 ? b : b + split[c * nb + slab - 1];
                     end = slab == nb ? e : b + split[c * nb + slab];
-                    s = sf[c];
+                    s = 1.0 / sf[c];    // the consumers multiply
                 }
                 const int ncell = (int)(c1 - cb < 32 ? c1 - cb : 32);
                 for (int j = 0; j < ncell; ++j) {
@@ -334,7 +333,6 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
     } else {
         // ------------------------------------------------------------------ consumers
         const int ct = tid - 32;
-        const double ln2 = 0.693147180559945309417232121458;
         int stage = 0;
         uint32_t phase = 0;
         int bad = 0;
@@ -347,7 +345,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                 for (int t = ct; t < it.n; t += GS_CONSUMERS) {
                     double y = s8[t];
                     if (FUSED) {
-                        y = log1p(y / it.sf) / ln2;
+                        y = cb_logcount(y, it.sf);          // it.sf carries 1 / size factor
                         st_stream(logx + it.beg + t, y);
                     }
                     const int g = s4[t] - it.slab_base;
@@ -393,10 +391,9 @@ k_lognorm_values(const int64_t *__restrict__ colptr, const double *__restrict__ 
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const double ln2 = 0.693147180559945309417232121458;
     for (int64_t c = warp0; c < n_cols; c += nwarps) {
         const int64_t b = colptr[c], e = colptr[c + 1];
-        const double s = sf[c];
+        const double rs = 1.0 / sf[c];
         int64_t i = b + lane;
         for (; i + 96 < e; i += 128) {
             double v[4];
@@ -405,10 +402,10 @@ k_lognorm_values(const int64_t *__restrict__ colptr, const double *__restrict__ 
                 v[u] = ld_stream(x + i + 32 * u);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                st_stream(logx + i + 32 * u, log1p(v[u] / s) / ln2);
+                st_stream(logx + i + 32 * u, cb_logcount(v[u], rs));
         }
         for (; i < e; i += 32)
-            st_stream(logx + i, log1p(ld_stream(x + i) / s) / ln2);
+            st_stream(logx + i, cb_logcount(ld_stream(x + i), rs));
     }
 }
 
@@ -561,8 +558,7 @@ extern "C" int cb200_fetch_logcounts(cb200_ctx *ctx, double *logx_out)
     CB_CHECK(ctx, logx_out != nullptr, "cb200_fetch_logcounts: NULL output");
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cb_stage_begin(ctx, ST_D2H);
-    CB_CUDA(ctx, cudaMemcpyAsync(logx_out, ctx->logx.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
+    CB_TRY(cb200_d2h(ctx, logx_out, ctx->logx.p, (size_t)ctx->nnz * sizeof(double), ctx->stream));
     cb_stage_end(ctx, ST_D2H);
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -272,210 +272,177 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------
-// K7b, main path: warp per cell j with a hash table in shared memory.
+// K7b, main path: warp per cell j, hash table in shared memory, NO atomics.
 //
-// The lists hosts[L_j[0]], hosts[L_j[1]], ... are taken ONE AFTER THE OTHER (that is libscran's scan
-// order), the entries of a list 32 at a time, one per lane.  A cell h appears at most once per list,
-// so the lanes of one step touch different keys: no atomics on the values, one CAS to claim a slot.
-// A key met for the first time in list i gets the next output position (ballot + popcount keep the
-// ascending-h order inside the list), so positions come out directly in emission order -- sorted by
-// (first list that holds h, h) -- with no sort and no per-list counts; later lists only lower the
-// rank sum and raise the shared-neighbour count.  MODE 0 counts (ecnt[j]); MODE 1 repeats the scan
-// and writes the edges of j at eptr[j] + position, 32 consecutive edges per store instruction.
-// One warp-iteration handles up to 32 list entries; the merge kernel above spends one per edge.
-// A cell with more than SNN_HASH_CAP distinct partners is flagged and left to k_snn_merge.
+// The entries (cell < j) of the lists hosts[L_j[0]], hosts[L_j[1]], ... are taken as ONE flat sequence -- list after
+// list, ascending cell inside a list: libscran's scan order -- 32 consecutive entries per step, one per lane, read
+// straight from global memory (the entry of the next step is in flight while this one is inserted).  Per step:
+//   * __match_any_sync groups the lanes that hold the same cell h (it sits in several of the lists); the lowest
+//     lane of a group acts for it with the group's count / smallest rank sum,
+//   * the acting lanes probe the table (keys in shared memory).  The keys of one step are distinct, so a free slot
+//     is claimed by WRITE-THEN-VERIFY (store, __syncwarp, re-read) instead of a CAS, and the per-partner value is
+//     updated with plain shared-memory loads / stores,
+//   * a key met for the first time gets the next output position (ballot + popcount keep the flat order), which IS
+//     the emission order -- sorted by (first list that holds h, h) -- so no sort and no per-list counts are needed.
+// Only ONE 16-bit value per partner is kept: the smallest rank sum (type rank) or the number of shared
+// neighbours (number / jaccard).  The partners (h: 4 bytes, value: 2 bytes) go to the cell's slice of the partner
+// store; k_snn_compact expands them into (from, to, weight) at their final offsets once the counts are scanned.
+// Table sizes come in tiers (1 Ki ... 16 Ki slots); a cell goes to the smallest tier whose capacity covers the
+// LENGTH of its flat sequence (an upper bound of its partners, so a table never overflows), and every tier is one
+// launch over its own list of cells.  Cells beyond the largest tier are left to k_snn_merge.
 // ---------------------------------------------------------------------------------------
-// Two table sizes: the small one (14 warps per SM) takes every cell first; a cell with more partners than it
-// holds is flagged 1 and retried with the large one (7 warps per SM); what still does not fit is flagged 2
-// and left to k_snn_merge.
 #define SNN_HASH_EMPTY 0xffffffffu
-template <int LOG_SLOTS, int CAP, int STAGE, int WARPS>
-struct SnnHashCfg {
-    static constexpr int log_slots = LOG_SLOTS, slots = 1 << LOG_SLOTS, cap = CAP, stage = STAGE, warps = WARPS;
-};
-using SnnHashSmall = SnnHashCfg<10, 704, 1024, 14>;    // 15.5 KB per warp
-using SnnHashLarge = SnnHashCfg<11, 1408, 2048, 7>;    // 31 KB per warp
-template <class CFG>
-struct SnnHashWarp {
-    uint32_t key[CFG::slots];    // cell h or EMPTY
-    uint16_t idx[CFG::slots];    // -> dense entry
-    uint32_t dh[CFG::cap];       // dense, in emission order: h
-    uint32_t drc[CFG::cap];      // dense: min rank sum | shared count << 16
-    uint32_t stage[CFG::stage];  // the entries (cell < j) of a group of lists, list after list
+#define SNN_TIERS 5
+#define SNN_MAXL 128
+template <int LOG_SLOTS>
+struct SnnTier {
+    static constexpr int log_slots = LOG_SLOTS, slots = 1 << LOG_SLOTS;
+    static constexpr int cap = slots / 16 * 11;                        // load factor <= 0.6875
+    static constexpr int bytes = slots * 6 + cap * 2 + SNN_MAXL * 8 + 16;   // keys, positions, values, list table
+    // small tables: two CTAs per SM (<= 110 KB each); larger ones: one CTA with as many warps as fit 225 KB
+    static constexpr int w2 = (110 * 1024) / bytes > 16 ? 16 : (110 * 1024) / bytes;
+    static constexpr int w1 = (225 * 1024) / bytes > 16 ? 16 : ((225 * 1024) / bytes < 1 ? 1 : (225 * 1024) / bytes);
+    static constexpr int ctas_per_sm = w2 >= 8 ? 2 : 1;
+    static constexpr int warps = w2 >= 8 ? w2 : w1;
 };
 
-// MODE 0: count (+ partner slices), MODE 1: emit directly (unused by the host code since k_snn_compact).
-// PASS 0: every cell; PASS 1: only the cells flagged 1 by the previous pass.
-template <int MODE, class CFG, int PASS>
-__global__ void __launch_bounds__(32 * CFG::warps)
-k_snn_hash(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t j_begin, int64_t j_end,
-           const int64_t *__restrict__ rptr, const uint32_t *__restrict__ hosts, const int32_t *__restrict__ cut,
-           int32_t *__restrict__ ecnt, unsigned char *__restrict__ flagged, const int64_t *__restrict__ eptr,
-           int32_t *__restrict__ efrom, int32_t *__restrict__ eto, double *__restrict__ ew,
-           const int64_t *__restrict__ toff, uint32_t *__restrict__ tmp_h, uint32_t *__restrict__ tmp_rc,
-           const int32_t *__restrict__ tcnt)
+template <int LOG_SLOTS>
+__global__ void __launch_bounds__(32 * SnnTier<LOG_SLOTS>::warps)
+k_snn_flat(const int32_t *__restrict__ nn, int k, int type, int64_t j_begin, const int64_t *__restrict__ rptr,
+           const uint32_t *__restrict__ hosts, const int32_t *__restrict__ cut, const int32_t *__restrict__ jlist,
+           const int *__restrict__ nlist, int32_t *__restrict__ ecnt, const int64_t *__restrict__ toff,
+           uint32_t *__restrict__ tmp_h, uint16_t *__restrict__ tmp_v)
 {
+    using T = SnnTier<LOG_SLOTS>;
     extern __shared__ __align__(16) unsigned char snn_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    SnnHashWarp<CFG> &T = reinterpret_cast<SnnHashWarp<CFG> *>(snn_smem)[w];
-    constexpr int SNN_HASH_SLOTS = CFG::slots, SNN_HASH_CAP = CFG::cap, SNN_HASH_STAGE = CFG::stage, SNN_HASH_WARPS = CFG::warps;
+    unsigned char *mine = snn_smem + (size_t)w * T::bytes;
+    uint32_t *key = reinterpret_cast<uint32_t *>(mine);                          // [slots]
+    uint32_t *lstart = key + T::slots;                                            // [SNN_MAXL] first entry of list i in hosts
+    uint32_t *lpre = lstart + SNN_MAXL;                                           // [SNN_MAXL] entries of the lists before i
+    uint16_t *idx = reinterpret_cast<uint16_t *>(lpre + SNN_MAXL);                // [slots] slot -> output position
+    uint16_t *val = idx + T::slots;                                               // [cap]   position -> value
     const int L = k + 1;
-    const int64_t warp0 = (int64_t)blockIdx.x * SNN_HASH_WARPS + w;
-    const int64_t nwarps = (int64_t)gridDim.x * SNN_HASH_WARPS;
-    for (int64_t j = j_begin + warp0; j < j_end; j += nwarps) {
-        const int64_t jl = j - j_begin;
-        if (MODE == 1 && flagged[jl] != 0)
-            continue;
-        if (MODE == 0 && PASS == 1 && flagged[jl] != 1)
-            continue;
-        if (MODE == 0 && PASS == 0 && tcnt != nullptr && tcnt[jl] > 2 * CFG::cap - CFG::cap / 8) {
-            // about half of the staged entries are distinct partners: this cell would most likely overflow
-            // the small table -- straight to the large one
-            if (lane == 0) {
-                ecnt[jl] = 0;
-                flagged[jl] = 1;
-            }
-            continue;
-        }
-        // clear the keys
-        for (int e = lane * 4; e < SNN_HASH_SLOTS; e += 128)
-            *reinterpret_cast<uint4 *>(&T.key[e]) = make_uint4(SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY);
-        int base = 0;        // distinct partners so far = next output position
-        bool overflow = false;
-        for (int i0 = 0; i0 < L && !overflow; i0 += 32) {
-            // lane holds list i0 + lane: start in hosts and number of entries with cell < j (the entry of
-            // j itself sits at position cut[j][i] of the list of its i-th neighbour)
-            const int il = i0 + lane;
-            int64_t lb = 0;
+    const bool want_min = type == CB200_SNN_RANK;
+    const int n_items = *nlist;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int it = blockIdx.x * T::warps + w; it < n_items; it += gridDim.x * T::warps) {
+        const int64_t jl = jlist[it];
+        const int64_t j = j_begin + jl;
+        // the lists: start in hosts, number of entries with cell < j (the entry of j itself sits at position
+        // cut[j][i] of the list of its i-th neighbour), exclusive prefix = start in the flat sequence
+        int total = 0;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
             int len = 0;
-            if (il < L) {
-                const int sidx = il == 0 ? (int)j : nn[j * k + (il - 1)];
-                lb = rptr[sidx];
-                len = cut[j * L + il];
+            uint32_t lb = 0;
+            if (i < L) {
+                const int sidx = i == 0 ? (int)j : nn[j * k + (i - 1)];
+                lb = (uint32_t)rptr[sidx];
+                len = cut[j * L + i];
             }
-            const int nl = L - i0 < 32 ? L - i0 : 32;
-            int li0 = 0;
-            while (li0 < nl && !overflow) {
-                // group of lists [li0, li1) whose entries fit the staging buffer (inclusive scan of len)
-                int inc = len;
+            int inc = len;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t2 = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o)
-                        inc += t2;
-                }
-                const int before = li0 > 0 ? __shfl_sync(0xffffffffu, inc, li0 - 1) : 0;
-                const unsigned fit = __ballot_sync(0xffffffffu, lane >= li0 && lane < nl && inc - before <= SNN_HASH_STAGE);
-                // lists fit as a prefix of [li0, nl): the first lane that does not fit ends the group
-                const unsigned range = (nl == 32 ? 0xffffffffu : ((1u << nl) - 1u)) & ~((1u << li0) - 1u);
-                const unsigned nofit = range & ~fit;
-                const int li1 = nofit ? __ffs(nofit) - 1 : nl;
-                if (li1 == li0) {   // a single list longer than the buffer: hub cell, left to the merge kernel
-                    overflow = true;
-                    break;
-                }
-                // stage: asynchronous 4-byte copies, all in flight together
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += t2;
+            }
+            if (i < L) {
+                lstart[i] = lb;
+                lpre[i] = (uint32_t)(total + inc - len);
+            }
+            total += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        for (int e = lane * 4; e < T::slots; e += 128)
+            *reinterpret_cast<uint4 *>(&key[e]) = make_uint4(SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY);
+        __syncwarp();
+        const int64_t tb = toff[jl];
+        int base = 0;       // distinct partners so far = next output position
+        int cur = 0;        // list that holds this lane's flat index (advances monotonically)
+        auto fetch = [&](int f, uint32_t &ent, int &li) {
+            ent = 0u;
+            li = 0;
+            if (f < total) {
+                while (cur + 1 < L && lpre[cur + 1] <= (uint32_t)f)
+                    ++cur;
+                li = cur;
+                ent = __ldg(hosts + lstart[cur] + ((uint32_t)f - lpre[cur]));
+            }
+        };
+        uint32_t ent_n;
+        int li_n;
+        fetch(lane, ent_n, li_n);
+        for (int f0 = 0; f0 < total; f0 += 32) {
+            const uint32_t ent = ent_n;
+            const int li = li_n;
+            const bool valid = f0 + lane < total;
+            fetch(f0 + 32 + lane, ent_n, li_n);              // next step's entry: in flight during the insertion
+            const uint32_t h = valid ? (ent >> 8) : (0xff000000u | (uint32_t)lane);   // invalid lanes: unique dummies
+            const int rs = li + (int)(ent & 0xffu);
+            const unsigned grp = __match_any_sync(0xffffffffu, h);
+            const bool leader = valid && (grp & lt_mask) == 0u;
+            int v = want_min ? rs : __popc(grp);
+            if (want_min && (grp & (grp - 1u)) != 0u)
+                v = __reduce_min_sync(grp, rs);
+            // probe; free slots are claimed by write-then-verify (the keys of the acting lanes are distinct)
+            bool pending = leader, is_new = false;
+            int slot = (int)((h * 2654435761u) >> (32 - T::log_slots));
+            while (__any_sync(0xffffffffu, pending)) {
+                const uint32_t kc = pending ? key[slot] : 0u;
+                const bool tent = pending && kc == SNN_HASH_EMPTY;
+                if (tent)
+                    key[slot] = h;
                 __syncwarp();
-                for (int li = li0; li < li1; ++li) {
-                    const int64_t b = __shfl_sync(0xffffffffu, lb, li);
-                    const int ln = __shfl_sync(0xffffffffu, len, li);
-                    const int off = __shfl_sync(0xffffffffu, inc - len, li) - before;   // exclusive prefix
-                    for (int e = lane; e < ln; e += 32) {
-                        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&T.stage[off + e]);
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(hosts + b + e) : "memory");
+                if (pending) {
+                    if (kc == h) {
+                        pending = false;
+                    } else if (tent && key[slot] == h) {
+                        pending = false;
+                        is_new = true;
+                    } else {
+                        slot = (slot + 1) & (T::slots - 1);
                     }
                 }
-                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                // insert list after list (libscran's scan order), 32 entries per step
-                for (int li = li0; li < li1 && !overflow; ++li) {
-                    const int i = i0 + li;
-                    const int ln = __shfl_sync(0xffffffffu, len, li);
-                    const int off = __shfl_sync(0xffffffffu, inc - len, li) - before;
-                    for (int e0 = 0; e0 < ln; e0 += 32) {
-                        const int e = e0 + lane;
-                        const bool valid = e < ln;
-                        const uint32_t ent = valid ? T.stage[off + e] : 0u;
-                        const uint32_t h = ent >> 8;
-                        bool is_new = false;
-                        int slot = 0;
-                        if (valid) {
-                            slot = (int)((h * 2654435761u) >> (32 - CFG::log_slots));
-                            while (true) {
-                                const uint32_t kc = T.key[slot];
-                                if (kc == h)
-                                    break;
-                                if (kc == SNN_HASH_EMPTY) {
-                                    const uint32_t old = atomicCAS(&T.key[slot], SNN_HASH_EMPTY, h);
-                                    if (old == SNN_HASH_EMPTY) {
-                                        is_new = true;
-                                        break;
-                                    }
-                                    if (old == h)
-                                        break;
-                                }
-                                slot = (slot + 1) & (SNN_HASH_SLOTS - 1);
-                            }
-                        }
-                        const unsigned nm = __ballot_sync(0xffffffffu, is_new);
-                        const int nnew = __popc(nm);
-                        if (base + nnew > SNN_HASH_CAP) {
-                            overflow = true;
-                            break;
-                        }
-                        const uint32_t rs = (uint32_t)i + (ent & 0xffu);
-                        if (is_new) {
-                            const int pos = base + __popc(nm & ((1u << lane) - 1u));
-                            T.idx[slot] = (uint16_t)pos;
-                            T.dh[pos] = h;
-                            T.drc[pos] = rs | (1u << 16);
-                        } else if (valid) {
-                            const int pos = T.idx[slot];
-                            const uint32_t rc = T.drc[pos];
-                            T.drc[pos] = min(rc & 0xffffu, rs) | ((rc & 0xffff0000u) + (1u << 16));
-                        }
-                        base += nnew;
-                        __syncwarp();
-                    }
-                }
-                li0 = li1;
             }
+            const unsigned nm = __ballot_sync(0xffffffffu, is_new);
+            if (is_new) {
+                const int pos = base + __popc(nm & lt_mask);
+                idx[slot] = (uint16_t)pos;
+                val[pos] = (uint16_t)v;
+                tmp_h[tb + pos] = h;
+            } else if (leader) {
+                const int pos = idx[slot];
+                const int c = val[pos];
+                val[pos] = (uint16_t)(want_min ? min(c, v) : c + v);
+            }
+            base += __popc(nm);
+            __syncwarp();
         }
-        if (MODE == 0) {
-            if (lane == 0) {
-                ecnt[jl] = overflow ? 0 : base;
-                flagged[jl] = overflow ? (unsigned char)(PASS + 1) : (unsigned char)0;
-            }
-            if (!overflow && tmp_h != nullptr) {
-                // keep the partners for k_snn_compact: no second pass over the lists.  toff is the scan
-                // of an upper bound (all staged entries), so the slices never overlap.
-                const int64_t tb = toff[jl];
-                for (int p = lane; p < base; p += 32) {
-                    tmp_h[tb + p] = T.dh[p];
-                    tmp_rc[tb + p] = T.drc[p];
-                }
-            }
-        } else {
-            const int64_t ebase = eptr[jl];
-            for (int p = lane; p < base; p += 32) {
-                const uint32_t rc = T.drc[p];
-                const int rs = (int)(rc & 0xffffu), nmatch = (int)(rc >> 16);
-                double wgt;
-                if (type == CB200_SNN_RANK)
-                    wgt = (double)k - 0.5 * (double)rs;
-                else if (type == CB200_SNN_NUMBER)
-                    wgt = (double)nmatch;
-                else
-                    wgt = __ddiv_rn((double)nmatch, (double)(2 * L - nmatch));
-                if (wgt < 1e-6)
-                    wgt = 1e-6;
-                efrom[ebase + p] = (int32_t)(j + 1);
-                eto[ebase + p] = (int32_t)(T.dh[p] + 1);
-                ew[ebase + p] = wgt;
-            }
-        }
+        if (lane == 0)
+            ecnt[jl] = base;
+        for (int p = lane; p < base; p += 32)
+            tmp_v[tb + p] = val[p];
         __syncwarp();
     }
+}
+
+// tier of every cell from the length of its flat sequence; tier SNN_TIERS = left to the merge kernel
+__global__ void k_snn_tiers(const int32_t *__restrict__ tcnt, const int64_t *__restrict__ rptr, const int32_t *__restrict__ nn,
+                            int64_t j_begin, int64_t nj, int k, int32_t *__restrict__ lists, int *__restrict__ nlists,
+                            unsigned char *__restrict__ flagged, int32_t *__restrict__ ecnt)
+{
+    const int64_t jl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (jl >= nj)
+        return;
+    const int t = tcnt[jl];
+    int tier = 0;
+    while (tier < SNN_TIERS && t > ((1 << (10 + tier)) / 16) * 11)
+        ++tier;
+    flagged[jl] = tier == SNN_TIERS ? (unsigned char)2 : (unsigned char)0;
+    if (tier == SNN_TIERS)
+        ecnt[jl] = 0;
+    lists[(int64_t)tier * nj + atomicAdd(nlists + tier, 1)] = (int32_t)jl;
 }
 
 // upper bound of the partners of cell j: all list entries with a cell < j
@@ -491,12 +458,12 @@ __global__ void k_snn_upper(const int32_t *__restrict__ cut, int64_t j_begin, in
     }
 }
 
-// edges of the cells [j_begin, j_end) from the partner slices kept by k_snn_hash<0>: warp per cell,
-// 32 consecutive edges per store instruction
+// edges of the cells [j_begin, j_end) from the partner slices kept by k_snn_flat: warp per cell, 32 consecutive
+// edges per store instruction; the 2-byte value (smallest rank sum / shared count) becomes the fp64 weight here
 __global__ void __launch_bounds__(256)
 k_snn_compact(int64_t j_begin, int64_t j_end, int k, int type, const int32_t *__restrict__ ecnt,
               const unsigned char *__restrict__ flagged, const int64_t *__restrict__ eptr,
-              const int64_t *__restrict__ toff, const uint32_t *__restrict__ tmp_h, const uint32_t *__restrict__ tmp_rc,
+              const int64_t *__restrict__ toff, const uint32_t *__restrict__ tmp_h, const uint16_t *__restrict__ tmp_v,
               int32_t *__restrict__ efrom, int32_t *__restrict__ eto, double *__restrict__ ew, int64_t loc0)
 {
     const int lane = threadIdx.x & 31;
@@ -510,15 +477,14 @@ k_snn_compact(int64_t j_begin, int64_t j_end, int k, int type, const int32_t *__
         const int cnt = ecnt[jl];
         const int64_t ebase = eptr[jl], tb = toff[jl];
         for (int p = lane; p < cnt; p += 32) {
-            const uint32_t rc = tmp_rc[tb + p];
-            const int rs = (int)(rc & 0xffffu), nmatch = (int)(rc >> 16);
+            const int v = tmp_v[tb + p];
             double wgt;
             if (type == CB200_SNN_RANK)
-                wgt = (double)k - 0.5 * (double)rs;
+                wgt = (double)k - 0.5 * (double)v;
             else if (type == CB200_SNN_NUMBER)
-                wgt = (double)nmatch;
+                wgt = (double)v;
             else
-                wgt = __ddiv_rn((double)nmatch, (double)(2 * L - nmatch));
+                wgt = __ddiv_rn((double)v, (double)(2 * L - v));
             if (wgt < 1e-6)
                 wgt = 1e-6;
             efrom[ebase + p] = (int32_t)(j + 1);
@@ -528,17 +494,17 @@ k_snn_compact(int64_t j_begin, int64_t j_end, int k, int type, const int32_t *__
     }
 }
 
-template <int MODE, class CFG, int PASS>
-static int launch_snn_hash(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int type, int64_t j_begin,
-                           int64_t j_end, int64_t loc)
+template <int LOG_SLOTS>
+static int launch_snn_flat(cb200_ctx *ctx, const int32_t *d_nn, int k, int type, int64_t j_begin, int64_t nj, int tier)
 {
-    const size_t smem = sizeof(SnnHashWarp<CFG>) * CFG::warps;
-    CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_hash<MODE, CFG, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = cb_grid_for(j_end - j_begin, CFG::warps, ctx->num_sms * 8);
-    k_snn_hash<MODE, CFG, PASS><<<grid, 32 * CFG::warps, smem, ctx->stream>>>(
-        d_nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->ecnt.p + loc, ctx->snn_flag.p + loc,
-        ctx->eptr.p + loc, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, ctx->snn_toff.p + loc, ctx->snn_tmp_h.p, ctx->snn_tmp_rc.p,
-        ctx->snn_tcnt.p + loc);
+    using T = SnnTier<LOG_SLOTS>;
+    const size_t smem = (size_t)T::bytes * T::warps;
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_flat<LOG_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = ctx->num_sms * T::ctas_per_sm;
+    k_snn_flat<LOG_SLOTS><<<grid, 32 * T::warps, smem, ctx->stream>>>(
+        d_nn, k, type, j_begin, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->snn_jlist.p + (int64_t)tier * nj,
+        ctx->snn_nlists.p + tier, ctx->ecnt.p, ctx->snn_toff.p, ctx->snn_tmp_h.p,
+        reinterpret_cast<uint16_t *>(ctx->snn_tmp_rc.p));
     CB_LAUNCH(ctx);
     return 0;
 }
@@ -561,15 +527,6 @@ static void launch_snn_merge(cb200_ctx *ctx, int grid, const int32_t *d_nn, int6
     else
         k_snn_merge<MODE, 4><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
                                                            ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, jlist, nlist);
-}
-
-// the cells k_snn_hash could not hold (flag 2), as a list: one warp of k_snn_merge each
-__global__ void k_snn_flag_list(const unsigned char *__restrict__ flagged, int64_t nj, int32_t *__restrict__ jlist,
-                                int *__restrict__ nlist)
-{
-    const int64_t jl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (jl < nj && flagged[jl] == 2)
-        jlist[atomicAdd(nlist, 1)] = (int32_t)jl;
 }
 
 // cell boundaries of SNN_CHUNKS pieces with about equal numbers of edges: out[2c] = first local cell of
@@ -644,24 +601,33 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
     ctx->snn_use_hash = !(seng != nullptr && strcmp(seng, "merge") == 0);
     const int g3 = cb_grid_for(nj, 8, ctx->num_sms * 16);
     if (ctx->snn_use_hash) {
-        // slices of the partner store: scan of the per-cell upper bounds
+        // slices of the partner store: scan of the per-cell upper bounds (= lengths of the flat sequences)
         CB_CUDA(ctx, ctx->snn_tcnt.ensure((size_t)nj));
         CB_CUDA(ctx, ctx->snn_toff.ensure((size_t)nj + 1));
         k_snn_upper<<<(unsigned)((nj + 255) / 256), 256, 0, ctx->stream>>>(ctx->snn_cut.p, j_begin, nj, L, ctx->snn_tcnt.p);
         CB_LAUNCH(ctx);
         CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->snn_tcnt.p, nj, ctx->snn_toff.p));
-        int64_t ttot = 0;
-        CB_TRY(cb200_read_back(ctx, &ttot, ctx->snn_toff.p + nj, sizeof(int64_t)));
-        CB_CUDA(ctx, ctx->snn_tmp_h.ensure((size_t)ttot));
-        CB_CUDA(ctx, ctx->snn_tmp_rc.ensure((size_t)ttot));
-        CB_TRY((launch_snn_hash<0, SnnHashSmall, 0>(ctx, d_nn, n, k, type, j_begin, j_end, 0)));
-        CB_TRY((launch_snn_hash<0, SnnHashLarge, 1>(ctx, d_nn, n, k, type, j_begin, j_end, 0)));
-        CB_CUDA(ctx, ctx->snn_jlist.ensure((size_t)nj + 1));
-        int *nlist = reinterpret_cast<int *>(ctx->snn_jlist.p + nj);
-        CB_CUDA(ctx, cudaMemsetAsync(nlist, 0, sizeof(int), ctx->stream));
-        k_snn_flag_list<<<(unsigned)((nj + 255) / 256), 256, 0, ctx->stream>>>(ctx->snn_flag.p, nj, ctx->snn_jlist.p, nlist);
+        // one list of cells per table tier (+ one for the merge kernel)
+        CB_CUDA(ctx, ctx->snn_jlist.ensure((size_t)nj * (SNN_TIERS + 1)));
+        CB_CUDA(ctx, ctx->snn_nlists.ensure(SNN_TIERS + 1));
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->snn_nlists.p, 0, (SNN_TIERS + 1) * sizeof(int), ctx->stream));
+        k_snn_tiers<<<(unsigned)((nj + 255) / 256), 256, 0, ctx->stream>>>(ctx->snn_tcnt.p, ctx->rptr.p, d_nn, j_begin, nj, k,
+                                                                         ctx->snn_jlist.p, ctx->snn_nlists.p, ctx->snn_flag.p,
+                                                                         ctx->ecnt.p);
         CB_LAUNCH(ctx);
-        launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_jlist.p, nlist);
+        struct { int64_t ttot; int nl[SNN_TIERS + 1]; } hs;
+        CB_TRY(cb200_read_back(ctx, &hs.ttot, ctx->snn_toff.p + nj, sizeof(int64_t)));
+        CB_TRY(cb200_read_back(ctx, hs.nl, ctx->snn_nlists.p, sizeof(hs.nl)));
+        CB_CUDA(ctx, ctx->snn_tmp_h.ensure((size_t)hs.ttot));
+        CB_CUDA(ctx, ctx->snn_tmp_rc.ensure((size_t)(hs.ttot + 1) / 2));        // 2-byte values
+        if (hs.nl[0] > 0) CB_TRY((launch_snn_flat<10>(ctx, d_nn, k, type, j_begin, nj, 0)));
+        if (hs.nl[1] > 0) CB_TRY((launch_snn_flat<11>(ctx, d_nn, k, type, j_begin, nj, 1)));
+        if (hs.nl[2] > 0) CB_TRY((launch_snn_flat<12>(ctx, d_nn, k, type, j_begin, nj, 2)));
+        if (hs.nl[3] > 0) CB_TRY((launch_snn_flat<13>(ctx, d_nn, k, type, j_begin, nj, 3)));
+        if (hs.nl[4] > 0) CB_TRY((launch_snn_flat<14>(ctx, d_nn, k, type, j_begin, nj, 4)));
+        ctx->snn_n_merge = hs.nl[SNN_TIERS];
+        launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_jlist.p + (int64_t)SNN_TIERS * nj,
+                            ctx->snn_nlists.p + SNN_TIERS);
     } else {
         launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0);
     }
@@ -718,7 +684,7 @@ static int snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight)
         const int64_t nj = ctx->snn_jend - ctx->snn_jbegin;
         const int gm = cb_grid_for(nj, 8, ctx->num_sms * 16);
         launch_snn_merge<1>(ctx, gm, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin, ctx->snn_jend, 0,
-                            ctx->snn_jlist.p, reinterpret_cast<int *>(ctx->snn_jlist.p + nj));
+                            ctx->snn_jlist.p + (int64_t)SNN_TIERS * nj, ctx->snn_nlists.p + SNN_TIERS);
         CB_LAUNCH(ctx);
     }
     for (int c = 0; c < SNN_CHUNKS; ++c) {
@@ -729,8 +695,8 @@ static int snn_emit(cb200_ctx *ctx, int32_t *from, int32_t *to, double *weight)
         if (ctx->snn_use_hash) {
             k_snn_compact<<<g3, 256, 0, ctx->stream>>>(ctx->snn_jbegin + ja, ctx->snn_jbegin + jb, ctx->snn_k, ctx->snn_type,
                                                        ctx->ecnt.p, ctx->snn_flag.p, ctx->eptr.p, ctx->snn_toff.p,
-                                                       ctx->snn_tmp_h.p, ctx->snn_tmp_rc.p, ctx->efrom.p, ctx->eto.p,
-                                                       ctx->ew8.p, ctx->snn_jbegin);
+                                                       ctx->snn_tmp_h.p, reinterpret_cast<const uint16_t *>(ctx->snn_tmp_rc.p),
+                                                       ctx->efrom.p, ctx->eto.p, ctx->ew8.p, ctx->snn_jbegin);
         } else {
             launch_snn_merge<1>(ctx, g3, ctx->snn_nn, ctx->snn_n, ctx->snn_k, ctx->snn_type, ctx->snn_jbegin + ja,
                                 ctx->snn_jbegin + jb, ja);
@@ -767,12 +733,9 @@ static int snn_fetch(cb200_ctx *ctx, int64_t ne, int32_t **from, int32_t **to, d
     CB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void **>(weight), cnt * sizeof(double)));
     cb_stage_begin(ctx, ST_D2H);
     if (ne > 0) {
-        CB_CUDA(ctx, cudaMemcpyAsync(*from, ctx->efrom.p, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        CB_CUDA(ctx, cudaMemcpyAsync(*to, ctx->eto.p, (size_t)ne * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        CB_CUDA(ctx, cudaMemcpyAsync(*weight, ctx->ew8.p, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
+        CB_TRY(cb200_d2h(ctx, *from, ctx->efrom.p, (size_t)ne * sizeof(int32_t), ctx->stream));
+        CB_TRY(cb200_d2h(ctx, *to, ctx->eto.p, (size_t)ne * sizeof(int32_t), ctx->stream));
+        CB_TRY(cb200_d2h(ctx, *weight, ctx->ew8.p, (size_t)ne * sizeof(double), ctx->stream));
     }
     cb_stage_end(ctx, ST_D2H);
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -791,12 +754,9 @@ extern "C" int cb200_fetch_edges(cb200_ctx *ctx, int64_t n_edges, int32_t *from,
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cb_stage_begin(ctx, ST_D2H);
     if (n_edges > 0) {
-        CB_CUDA(ctx, cudaMemcpyAsync(from, ctx->efrom.p, (size_t)n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        CB_CUDA(ctx, cudaMemcpyAsync(to, ctx->eto.p, (size_t)n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-        CB_CUDA(ctx, cudaMemcpyAsync(weight, ctx->ew8.p, (size_t)n_edges * sizeof(double), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
+        CB_TRY(cb200_d2h(ctx, from, ctx->efrom.p, (size_t)n_edges * sizeof(int32_t), ctx->stream));
+        CB_TRY(cb200_d2h(ctx, to, ctx->eto.p, (size_t)n_edges * sizeof(int32_t), ctx->stream));
+        CB_TRY(cb200_d2h(ctx, weight, ctx->ew8.p, (size_t)n_edges * sizeof(double), ctx->stream));
     }
     cb_stage_end(ctx, ST_D2H);
     CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -895,8 +855,7 @@ extern "C" int cb200_snn(cb200_ctx *ctx, const int32_t *index, int64_t n_total, 
         cb_stage_begin(ctx, ST_H2D);
         CB_CUDA(ctx, ctx->stage_i.ensure((size_t)n_total * k));
         CB_CUDA(ctx, ctx->index0.ensure((size_t)n_total * k));
-        CB_CUDA(ctx, cudaMemcpyAsync(ctx->stage_i.p, index, (size_t)n_total * k * sizeof(int32_t),
-                                     cudaMemcpyHostToDevice, ctx->stream));
+        CB_TRY(cb200_h2d(ctx, ctx->stage_i.p, index, (size_t)n_total * k * sizeof(int32_t), ctx->stream));
         CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
         k_index_to_rowmajor0<<<(unsigned)((n_total * k + 255) / 256), 256, 0, ctx->stream>>>(
             ctx->stage_i.p, n_total, k, ctx->index0.p, ctx->flag.p);
