@@ -165,23 +165,31 @@ extern "C" int cb200_size_factors(cb200_ctx *ctx, const double *sf_in, double *s
 
 #define GS_THREADS 512
 #define GS_CONSUMERS 480
-#define GS_STAGE_ENTRIES 1024
-#define GS_STAGES 5
+#define GS_STAGE_ENTRIES 1024   // entries per stage: several column segments are packed into one stage
+#define GS_MAXSUB 8             // ... at most this many
+#define GS_STAGES 6
 #define GS_SLAB_MAX 9600
-#define GS_CHUNK 512          // cells per work item
+#define GS_CHUNK 512            // cells per work item
 #define GS_ITEM_DATA 0
 #define GS_ITEM_FLUSH 1
 #define GS_ITEM_END 2
+#define GS_CAP8 (GS_STAGE_ENTRIES + 2 * GS_MAXSUB)   // staged 8-byte elements (every segment starts 16-byte aligned)
+#define GS_CAP4 (GS_STAGE_ENTRIES + 8 * GS_MAXSUB)   // 4-byte elements: up to 3 before + 3 after every segment
 
-struct GsItem {
+struct GsSub {
     int64_t beg;      // first entry of the segment (element index into x / rowidx / logx)
-    double sf;        // 1 / size factor of the cell
+    double rs;        // 1 / size factor of the cell
     int32_t n;        // entries
-    int32_t off8;     // position of entry `beg` inside the staged 8-byte array
-    int32_t off4;     // ... inside the staged 4-byte array
+    int32_t pos8;     // position of entry `beg` inside the stage's 8-byte array
+    int32_t pos4;     // ... inside the 4-byte array
+    int32_t pad;
+};
+struct GsItem {
     int32_t kind;     // GS_ITEM_*
+    int32_t nsub;
     int32_t slab_base;
     int32_t slab_genes;
+    GsSub sub[GS_MAXSUB];
 };
 
 // cut points of every column at the slab boundaries: split[c * (S-1) + b] = number of entries of column c with
@@ -223,9 +231,9 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
     extern __shared__ __align__(128) unsigned char gs_smem[];
     using namespace cb200tc;
     ulonglong2 *tab = reinterpret_cast<ulonglong2 *>(gs_smem);                       // [GS_SLAB_MAX]
-    unsigned char *stage8 = gs_smem + (size_t)GS_SLAB_MAX * 16;                      // [GS_STAGES][(E+2)*8]
-    unsigned char *stage4 = stage8 + (size_t)GS_STAGES * (GS_STAGE_ENTRIES + 2) * 8;  // [GS_STAGES][(E+4)*4]
-    GsItem *items = reinterpret_cast<GsItem *>(stage4 + (size_t)GS_STAGES * (GS_STAGE_ENTRIES + 4) * 4);
+    unsigned char *stage8 = gs_smem + (size_t)GS_SLAB_MAX * 16;                      // [GS_STAGES][GS_CAP8 * 8]
+    unsigned char *stage4 = stage8 + (size_t)GS_STAGES * GS_CAP8 * 8;                 // [GS_STAGES][GS_CAP4 * 4]
+    GsItem *items = reinterpret_cast<GsItem *>(stage4 + (size_t)GS_STAGES * GS_CAP4 * 4);
     uint64_t *full = reinterpret_cast<uint64_t *>(items + GS_STAGES);
     uint64_t *empty = full + GS_STAGES;
 
@@ -250,6 +258,9 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
         int stage = 0;
         uint32_t phase = 0;
         int cur_slab = -1, cur_genes = 0;
+        bool open = false;          // a data stage is being packed
+        int fill = 0, nsub = 0;     // its entries and segments so far
+        int cur8 = 0, cur4 = 0;     // next free (16-byte aligned) position of the stage's 8- / 4-byte array
         auto next_stage = [&]() {
             if (++stage == GS_STAGES) {
                 stage = 0;
@@ -259,14 +270,47 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
         auto acquire = [&]() {            // all lanes wait (the stage's previous occupant has been consumed)
             mbar_wait(empty + stage, phase ^ 1u, flag);
         };
+        auto close = [&]() {              // publishes the packed stage: one expect_tx, two bulk copies per segment
+            if (!open)
+                return;
+            if (lane == 0) {
+                GsItem &it = items[stage];
+                it.kind = GS_ITEM_DATA;
+                it.nsub = nsub;
+                it.slab_base = cur_slab * slab_genes;
+                it.slab_genes = cur_genes;
+                uint32_t total = 0;
+                for (int q = 0; q < nsub; ++q) {
+                    const GsSub &sb = it.sub[q];
+                    const int64_t a8 = sb.beg & ~1LL, a4 = sb.beg & ~3LL;        // 16-byte aligned sources
+                    total += (uint32_t)(((sb.beg + sb.n - a8 + 1) & ~1LL) * 8) + (uint32_t)(((sb.beg + sb.n - a4 + 3) & ~3LL) * 4);
+                }
+                mbar_expect_tx(full + stage, total);
+                for (int q = 0; q < nsub; ++q) {
+                    const GsSub &sb = it.sub[q];
+                    const int64_t a8 = sb.beg & ~1LL, a4 = sb.beg & ~3LL;
+                    const uint32_t bytes8 = (uint32_t)(((sb.beg + sb.n - a8 + 1) & ~1LL) * 8);
+                    const uint32_t bytes4 = (uint32_t)(((sb.beg + sb.n - a4 + 3) & ~3LL) * 4);
+                    bulk_g2s(stage8 + ((size_t)stage * GS_CAP8 + (size_t)(sb.pos8 - (int)(sb.beg - a8))) * 8, v8 + a8, bytes8,
+                             full + stage);
+                    bulk_g2s(stage4 + ((size_t)stage * GS_CAP4 + (size_t)(sb.pos4 - (int)(sb.beg - a4))) * 4, rowidx + a4, bytes4,
+                             full + stage);
+                }
+            }
+            __syncwarp();
+            next_stage();
+            open = false;
+        };
         auto control = [&](int kind, int slab) {
+            close();
             acquire();
             if (lane == 0) {
-                GsItem it;
-                it.beg = 0; it.sf = 1.0; it.n = 0; it.off8 = 0; it.off4 = 0; it.kind = kind;
+                GsItem &it = items[stage];
+                it.kind = kind;
+                it.nsub = 0;
                 it.slab_base = slab * slab_genes;
-                it.slab_genes = (int)(((int64_t)(slab + 1) * slab_genes < G ? (int64_t)(slab + 1) * slab_genes : G) - (int64_t)slab * slab_genes);
-                items[stage] = it;
+                it.slab_genes = (int)(((int64_t)(slab + 1) * slab_genes < G ? (int64_t)(slab + 1) * slab_genes : G) -
+                                      (int64_t)slab * slab_genes);
                 mbar_arrive(full + stage);
             }
             __syncwarp();
@@ -306,22 +350,31 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                     const int64_t je = __shfl_sync(0xffffffffu, end, j);
                     const double js = __shfl_sync(0xffffffffu, s, j);
                     while (jb < je) {
-                        const int n = (int)(je - jb < GS_STAGE_ENTRIES ? je - jb : GS_STAGE_ENTRIES);
-                        acquire();
-                        if (lane == 0) {
-                            const int64_t a8 = jb & ~1LL, a4 = jb & ~3LL;        // 16-byte aligned sources
-                            const uint32_t bytes8 = (uint32_t)(((jb + n - a8 + 1) & ~1LL) * 8);
-                            const uint32_t bytes4 = (uint32_t)(((jb + n - a4 + 3) & ~3LL) * 4);
-                            GsItem it;
-                            it.beg = jb; it.sf = js; it.n = n; it.off8 = (int)(jb - a8); it.off4 = (int)(jb - a4);
-                            it.kind = GS_ITEM_DATA; it.slab_base = slab * slab_genes; it.slab_genes = cur_genes;
-                            items[stage] = it;
-                            mbar_expect_tx(full + stage, bytes8 + bytes4);
-                            bulk_g2s(stage8 + (size_t)stage * (GS_STAGE_ENTRIES + 2) * 8, v8 + a8, bytes8, full + stage);
-                            bulk_g2s(stage4 + (size_t)stage * (GS_STAGE_ENTRIES + 4) * 4, rowidx + a4, bytes4, full + stage);
+                        if (open && (fill >= GS_STAGE_ENTRIES || nsub >= GS_MAXSUB))
+                            close();
+                        if (!open) {
+                            acquire();
+                            open = true;
+                            fill = 0;
+                            nsub = 0;
+                            cur8 = 0;
+                            cur4 = 0;
                         }
-                        __syncwarp();
-                        next_stage();
+                        const int room = GS_STAGE_ENTRIES - fill;
+                        const int n = (int)(je - jb < room ? je - jb : room);
+                        if (lane == 0) {
+                            GsSub &sb = items[stage].sub[nsub];
+                            sb.beg = jb;
+                            sb.rs = js;
+                            sb.n = n;
+                            // the segment's 16-byte aligned image starts at an aligned position of the stage arrays
+                            sb.pos8 = cur8 + (int)(jb & 1);
+                            sb.pos4 = cur4 + (int)(jb & 3);
+                        }
+                        cur8 += (int)(((jb & 1) + n + 1) & ~1LL);
+                        cur4 += (int)(((jb & 3) + n + 3) & ~3LL);
+                        fill += n;
+                        nsub += 1;
                         jb += n;
                     }
                 }
@@ -338,40 +391,47 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
         int bad = 0;
         for (;;) {
             mbar_wait(full + stage, phase, flag);
-            const GsItem it = items[stage];
-            if (it.kind == GS_ITEM_DATA) {
-                const double *s8 = reinterpret_cast<const double *>(stage8 + (size_t)stage * (GS_STAGE_ENTRIES + 2) * 8) + it.off8;
-                const int32_t *s4 = reinterpret_cast<const int32_t *>(stage4 + (size_t)stage * (GS_STAGE_ENTRIES + 4) * 4) + it.off4;
-                for (int t = ct; t < it.n; t += GS_CONSUMERS) {
-                    double y = s8[t];
-                    if (FUSED) {
-                        y = cb_logcount(y, it.sf);          // it.sf carries 1 / size factor
-                        st_stream(logx + it.beg + t, y);
+            const GsItem &it = items[stage];
+            const int kind = it.kind, nsub = it.nsub, slab_base = it.slab_base, sgenes = it.slab_genes;
+            if (kind == GS_ITEM_DATA) {
+                const double *base8 = reinterpret_cast<const double *>(stage8) + (size_t)stage * GS_CAP8;
+                const int32_t *base4 = reinterpret_cast<const int32_t *>(stage4) + (size_t)stage * GS_CAP4;
+                for (int q = 0; q < nsub; ++q) {
+                    const GsSub sb = it.sub[q];
+                    const double *s8 = base8 + sb.pos8;
+                    const int32_t *s4 = base4 + sb.pos4;
+                    for (int t = ct; t < sb.n; t += GS_CONSUMERS) {
+                        double y = s8[t];
+                        if (FUSED) {
+                            y = cb_logcount(y, sb.rs);
+                            st_stream(logx + sb.beg + t, y);
+                        }
+                        const int g = s4[t] - slab_base;
+                        if (!(y < y_limit) || g < 0 || g >= sgenes) {   // out of the fixed-point range / malformed row index
+                            bad = 1;
+                            continue;
+                        }
+                        ulonglong2 a = tab[g];
+                        a.x += (unsigned long long)__double2ll_rn(y * scale1);
+                        a.y += (unsigned long long)__double2ll_rn(y * y * scale2);
+                        tab[g] = a;
                     }
-                    const int g = s4[t] - it.slab_base;
-                    if (!(y < y_limit) || g < 0 || g >= it.slab_genes) {   // out of the fixed-point range / malformed row index
-                        bad = 1;
-                        continue;
-                    }
-                    ulonglong2 a = tab[g];
-                    a.x += (unsigned long long)__double2ll_rn(y * scale1);
-                    a.y += (unsigned long long)__double2ll_rn(y * y * scale2);
-                    tab[g] = a;
+                    gs_consumer_sync();     // the next segment belongs to another cell and may hit the same genes
                 }
-            } else if (it.kind == GS_ITEM_FLUSH) {
-                for (int g = ct; g < it.slab_genes; g += GS_CONSUMERS) {
+            } else if (kind == GS_ITEM_FLUSH) {
+                for (int g = ct; g < sgenes; g += GS_CONSUMERS) {
                     const ulonglong2 a = tab[g];
                     if (a.x | a.y) {
-                        atomicAdd(acc1 + it.slab_base + g, a.x);
-                        atomicAdd(acc2 + it.slab_base + g, a.y);
+                        atomicAdd(acc1 + slab_base + g, a.x);
+                        atomicAdd(acc2 + slab_base + g, a.y);
                         tab[g] = make_ulonglong2(0ull, 0ull);
                     }
                 }
+                gs_consumer_sync();
             }
-            gs_consumer_sync();             // every update of this item is in the table before the next one starts
             if (ct == 0)
-                mbar_arrive(empty + stage);
-            if (it.kind == GS_ITEM_END)
+                mbar_arrive(empty + stage);     // (the named barrier above ordered every reader of the stage before this)
+            if (kind == GS_ITEM_END)
                 break;
             if (++stage == GS_STAGES) {
                 stage = 0;
@@ -476,8 +536,8 @@ extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
                                                                           slab_genes, ctx->gs_split.p);
         CB_LAUNCH(ctx);
     }
-    const size_t smem = (size_t)GS_SLAB_MAX * 16 + (size_t)GS_STAGES * ((GS_STAGE_ENTRIES + 2) * 8 + (GS_STAGE_ENTRIES + 4) * 4) +
-                        GS_STAGES * sizeof(GsItem) + 2 * GS_STAGES * sizeof(uint64_t);
+    const size_t smem = (size_t)GS_SLAB_MAX * 16 + (size_t)GS_STAGES * (GS_CAP8 * 8 + GS_CAP4 * 4) + GS_STAGES * sizeof(GsItem) +
+                        2 * GS_STAGES * sizeof(uint64_t);
     const int64_t n_work = ((ctx->N + GS_CHUNK - 1) / GS_CHUNK) * n_slabs;
     const int grid = (int)(n_work < ctx->num_sms ? n_work : ctx->num_sms);
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(ctx->gene_acc.p);

@@ -618,6 +618,9 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
         struct { int64_t ttot; int nl[SNN_TIERS + 1]; } hs;
         CB_TRY(cb200_read_back(ctx, &hs.ttot, ctx->snn_toff.p + nj, sizeof(int64_t)));
         CB_TRY(cb200_read_back(ctx, hs.nl, ctx->snn_nlists.p, sizeof(hs.nl)));
+        if (getenv("CB200_TRACE") != nullptr)
+            fprintf(stderr, "[cb200] snn: flat entries %lld, cells per tier %d %d %d %d %d, merge kernel %d\n", (long long)hs.ttot,
+                    hs.nl[0], hs.nl[1], hs.nl[2], hs.nl[3], hs.nl[4], hs.nl[5]);
         CB_CUDA(ctx, ctx->snn_tmp_h.ensure((size_t)hs.ttot));
         CB_CUDA(ctx, ctx->snn_tmp_rc.ensure((size_t)(hs.ttot + 1) / 2));        // 2-byte values
         if (hs.nl[0] > 0) CB_TRY((launch_snn_flat<10>(ctx, d_nn, k, type, j_begin, nj, 0)));
