@@ -78,6 +78,20 @@ SIGNATURES = {
     "cb200_pairwise_modularity": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "cb200_fetch_edges": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cb200_edges_checksum": (c_int, [c_vp, c_i64p, ctypes.POINTER(ctypes.c_uint64)]),
+    "cb200_multi_init": (c_int, [c_int, ctypes.POINTER(c_vp)]),
+    "cb200_multi_free": (c_int, [c_vp]),
+    "cb200_multi_last_error": (ctypes.c_char_p, [c_vp]),
+    "cb200_multi_n_gpus": (c_int, [c_vp]),
+    "cb200_multi_stage_timings": (c_int, [c_vp, c_int, ctypes.POINTER(Timing)]),
+    "cb200_multi_load_csc": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "cb200_multi_load_csc_i32": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "cb200_multi_size_factors": (c_int, [c_vp, c_vp, c_vp]),
+    "cb200_multi_lognorm_genestats": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cb200_multi_pca": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "cb200_multi_knn": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
+    "cb200_multi_snn_count": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_i64p]),
+    "cb200_multi_snn_emit": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cb200_multi_edges_checksum": (c_int, [c_vp, c_i64p, ctypes.POINTER(ctypes.c_uint64)]),
     "cb200_synth_counts": (c_int, [c_vp, c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_i64p]),
     "cb200_export_csc": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cb200_synth_host": (c_int, [c_i64, c_i64, ctypes.c_double, ctypes.c_uint64, c_i64, c_i64, c_int, c_i64p,
@@ -423,3 +437,100 @@ class Context:
         ne = c_i64()
         self._ck(lib().cb200_snn_resident(self._h, k, SNN_TYPES[snn_type], ctypes.byref(ne)))
         return ne.value
+
+
+class MultiContext:
+    """All GPUs of one node from this one process: the binding of cb200_multi_* (what the R shim calls when
+    options(cellula.b200.gpus = n) asks for more than one GPU).  Same array layouts as `Context`, covering all cells."""
+
+    def __init__(self, n_gpus: int = 0):
+        self._h = c_vp()
+        L = lib()
+        if L.cb200_multi_init(int(n_gpus), ctypes.byref(self._h)) != 0:
+            raise Cb200Error(L.cb200_multi_last_error(None).decode())
+        self.n_gpus = L.cb200_multi_n_gpus(self._h)
+        self.n_genes = self.n_cells = self.nnz = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise Cb200Error(lib().cb200_multi_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value is not None:
+            lib().cb200_multi_free(self._h)
+            self._h = c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def timings(self, rank=0) -> dict:
+        t = Timing()
+        self._ck(lib().cb200_multi_stage_timings(self._h, rank, ctypes.byref(t)))
+        return t.as_dict()
+
+    def load_csc(self, n_genes, colptr, rowidx, values):
+        colptr = np.ascontiguousarray(colptr)
+        rowidx = np.ascontiguousarray(rowidx, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        n_cells = colptr.size - 1
+        if colptr.dtype == np.int32:
+            fn = lib().cb200_multi_load_csc_i32
+        else:
+            colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+            fn = lib().cb200_multi_load_csc
+        self._ck(fn(self._h, n_genes, n_cells, _ptr(colptr), _ptr(rowidx), _ptr(values)))
+        self._keep = (colptr, rowidx, values)    # the upload of the row indices may still be running
+        self.n_genes, self.n_cells, self.nnz = int(n_genes), int(n_cells), int(values.size)
+
+    def size_factors(self, sf_in=None, want=True):
+        sf_in = None if sf_in is None else np.ascontiguousarray(sf_in, dtype=np.float64)
+        out = np.empty(self.n_cells) if want else None
+        self._ck(lib().cb200_multi_size_factors(self._h, _ptr(sf_in), _ptr(out)))
+        return out
+
+    def lognorm_genestats(self, want_logx=True):
+        logx = np.empty(self.nnz) if want_logx else None
+        mean, var = np.empty(self.n_genes), np.empty(self.n_genes)
+        self._ck(lib().cb200_multi_lognorm_genestats(self._h, _ptr(logx), _ptr(mean), _ptr(var)))
+        return logx, mean, var
+
+    def pca(self, hvg_idx, d, want_scores=True):
+        hvg_idx = np.ascontiguousarray(hvg_idx, dtype=np.int32)
+        h = len(hvg_idx)
+        scores = np.empty((self.n_cells, d), order="F") if want_scores else None
+        rotation = np.empty((h, d), order="F")
+        varexp = np.empty(d)
+        total = ctypes.c_double()
+        self._ck(lib().cb200_multi_pca(self._h, _ptr(hvg_idx), h, d, _ptr(scores), _ptr(rotation), _ptr(varexp),
+                                       ctypes.cast(ctypes.byref(total), c_vp)))
+        return dict(scores=scores, rotation=rotation, var_explained=varexp, total_var=total.value,
+                    percent_var=100.0 * varexp / total.value)
+
+    def knn(self, emb, k, want=True, n_total=None, d=None):
+        if emb is not None:
+            emb = np.asfortranarray(emb, dtype=np.float64)
+            n_total, d = emb.shape
+        idx = np.empty((n_total, k), dtype=np.int32, order="F") if want else None
+        self._ck(lib().cb200_multi_knn(self._h, _ptr(emb), n_total, d, k, _ptr(idx)))
+        return idx
+
+    def snn(self, index, snn_type="rank", n_total=None, k=None, fetch=True):
+        if index is not None:
+            index = np.asfortranarray(index, dtype=np.int32)
+            n_total, k = index.shape
+        ne = c_i64()
+        self._ck(lib().cb200_multi_snn_count(self._h, _ptr(index), n_total, k, SNN_TYPES[snn_type], ctypes.byref(ne)))
+        if not fetch:
+            self._ck(lib().cb200_multi_snn_emit(self._h, None, None, None))
+            return ne.value
+        f, t, w = np.empty(ne.value, np.int32), np.empty(ne.value, np.int32), np.empty(ne.value)
+        self._ck(lib().cb200_multi_snn_emit(self._h, _ptr(f), _ptr(t), _ptr(w)))
+        return f, t, w
+
+    def edges_checksum(self):
+        ne, cs = c_i64(), ctypes.c_uint64()
+        self._ck(lib().cb200_multi_edges_checksum(self._h, ctypes.byref(ne), ctypes.byref(cs)))
+        return ne.value, cs.value

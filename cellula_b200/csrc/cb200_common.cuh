@@ -91,7 +91,11 @@ struct cb200_ctx {
     DevBuf<double> gene_acc;  // [2G] sum y, sum y^2 as 64-bit FIXED-POINT integers (scales 2^gs_s1, 2^gs_s2): exact,
                               // order-independent sums -- the buffer a multi-GPU caller all-reduces as int64
     DevBuf<int32_t> gs_split; // [N*(S-1)] cut points of the columns at the gene-slab boundaries
-    DevBuf<unsigned int> gs_queue;
+    DevBuf<unsigned int> gs_queue;   // [0] work queue of the slab kernel, [2..3] 64-bit length of the overflow list
+    DevBuf<double> gs_tab_y;          // [N*32] logcount of the counts 1..32 of every cell
+    DevBuf<unsigned long long> gs_tab_q;  // [N*32*2] its fixed-point images
+    DevBuf<int64_t> gs_ovf_entry;     // entries the table does not cover
+    DevBuf<int32_t> gs_ovf_cell;
     int gs_s1 = 0, gs_s2 = 0, gs_ybits = 0;
     bool gs_flag_pending = false, sf_from_input = false;
     double mean_ls = 0.0;     // mean library size when the size factors are library-size factors, else 0

@@ -173,6 +173,7 @@ extern "C" int cb200_size_factors(cb200_ctx *ctx, const double *sf_in, double *s
 #define GS_ITEM_DATA 0
 #define GS_ITEM_FLUSH 1
 #define GS_ITEM_END 2
+#define GS_TABLE 32             // counts 1 .. GS_TABLE come from the per-cell logcount table
 #define GS_CAP8 (GS_STAGE_ENTRIES + 2 * GS_MAXSUB)   // staged 8-byte elements (every segment starts 16-byte aligned)
 #define GS_CAP4 (GS_STAGE_ENTRIES + 8 * GS_MAXSUB)   // 4-byte elements: up to 3 before + 3 after every segment
 
@@ -182,7 +183,7 @@ struct GsSub {
     int32_t n;        // entries
     int32_t pos8;     // position of entry `beg` inside the stage's 8-byte array
     int32_t pos4;     // ... inside the 4-byte array
-    int32_t pad;
+    int32_t cell;     // local column of the segment
 };
 struct GsItem {
     int32_t kind;     // GS_ITEM_*
@@ -226,7 +227,9 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                  const double *__restrict__ sf, const int32_t *__restrict__ split, int64_t n_cols, int64_t G,
                  int n_slabs, int slab_genes, double scale1, double scale2, double y_limit,
                  double *__restrict__ logx, unsigned long long *__restrict__ acc1, unsigned long long *__restrict__ acc2,
-                 unsigned int *__restrict__ queue, int *__restrict__ flag)
+                 unsigned int *__restrict__ queue, int *__restrict__ flag, const double *__restrict__ tab_y,
+                 const ulonglong2 *__restrict__ tab_q, int64_t *__restrict__ ovf_entry, int32_t *__restrict__ ovf_cell,
+                 unsigned long long ovf_cap)
 {
     extern __shared__ __align__(128) unsigned char gs_smem[];
     using namespace cb200tc;
@@ -367,6 +370,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                             sb.beg = jb;
                             sb.rs = js;
                             sb.n = n;
+                            sb.cell = (int32_t)(cb + j);
                             // the segment's 16-byte aligned image starts at an aligned position of the stage arrays
                             sb.pos8 = cur8 + (int)(jb & 1);
                             sb.pos4 = cur4 + (int)(jb & 3);
@@ -402,18 +406,41 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                     const int32_t *s4 = base4 + sb.pos4;
                     for (int t = ct; t < sb.n; t += GS_CONSUMERS) {
                         double y = s8[t];
-                        if (FUSED) {
-                            y = cb_logcount(y, sb.rs);
-                            st_stream(logx + sb.beg + t, y);
-                        }
                         const int g = s4[t] - slab_base;
-                        if (!(y < y_limit) || g < 0 || g >= sgenes) {   // out of the fixed-point range / malformed row index
-                            bad = 1;
-                            continue;
+                        ulonglong2 add;
+                        if (FUSED) {
+                            // counts are small integers: the logcount and its two fixed-point images come from the
+                            // cell's table (k_gs_tables); anything else is left to k_gs_overflow
+                            const int xi = __double2int_rz(y);
+                            if (xi < 1 || xi > GS_TABLE || (double)xi != y) {
+                                const unsigned long long o = atomicAdd(reinterpret_cast<unsigned long long *>(queue + 2), 1ull);
+                                if (o < ovf_cap) {
+                                    ovf_entry[o] = sb.beg + t;
+                                    ovf_cell[o] = sb.cell;
+                                } else {
+                                    bad |= 8;
+                                }
+                                continue;
+                            }
+                            const int64_t ti = (int64_t)sb.cell * GS_TABLE + (xi - 1);
+                            y = __ldg(tab_y + ti);
+                            add = __ldg(tab_q + ti);
+                            st_stream(logx + sb.beg + t, y);
+                            if (g < 0 || g >= sgenes) {
+                                bad |= 2;
+                                continue;
+                            }
+                        } else {
+                            if (!(y < y_limit) || g < 0 || g >= sgenes) {   // out of the fixed-point range / malformed row index
+                                bad |= 2;
+                                continue;
+                            }
+                            add.x = (unsigned long long)__double2ll_rn(y * scale1);
+                            add.y = (unsigned long long)__double2ll_rn(y * y * scale2);
                         }
                         ulonglong2 a = tab[g];
-                        a.x += (unsigned long long)__double2ll_rn(y * scale1);
-                        a.y += (unsigned long long)__double2ll_rn(y * y * scale2);
+                        a.x += add.x;
+                        a.y += add.y;
                         tab[g] = a;
                     }
                     gs_consumer_sync();     // the next segment belongs to another cell and may hit the same genes
@@ -439,7 +466,57 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
             }
         }
         if (bad)
+            atomicOr(flag, bad);
+    }
+}
+
+// per cell: logcount of the counts 1 .. GS_TABLE and its fixed-point images (y 2^s1, y^2 2^s2); a table entry whose
+// logcount is outside the fixed-point range is reported
+__global__ void __launch_bounds__(256)
+k_gs_tables(const double *__restrict__ sf, int64_t n_cols, double scale1, double scale2, double y_limit,
+            double *__restrict__ tab_y, ulonglong2 *__restrict__ tab_q, int *__restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_cols * GS_TABLE)
+        return;
+    const int64_t c = i / GS_TABLE;
+    const int x = (int)(i % GS_TABLE) + 1;
+    const double y = cb_logcount((double)x, 1.0 / sf[c]);
+    tab_y[i] = y;
+    ulonglong2 q = make_ulonglong2(0ull, 0ull);
+    if (y < y_limit) {
+        q.x = (unsigned long long)__double2ll_rn(y * scale1);
+        q.y = (unsigned long long)__double2ll_rn(y * y * scale2);
+    } else if (x == 1) {
+        atomicOr(flag, 2);    // even a single count is out of range: the size factors are far from the library sizes
+    }
+    tab_q[i] = q;
+}
+
+// the entries the table does not cover (counts above GS_TABLE, non-integer values): direct evaluation, integer
+// reductions straight into the global sums
+__global__ void __launch_bounds__(256)
+k_gs_overflow(const int64_t *__restrict__ ovf_entry, const int32_t *__restrict__ ovf_cell, const unsigned int *__restrict__ queue,
+              unsigned long long ovf_cap, const int32_t *__restrict__ rowidx, const double *__restrict__ x,
+              const double *__restrict__ sf, int64_t G, double scale1, double scale2, double y_limit,
+              double *__restrict__ logx, unsigned long long *__restrict__ acc1, unsigned long long *__restrict__ acc2,
+              int *__restrict__ flag)
+{
+    unsigned long long n = *reinterpret_cast<const unsigned long long *>(queue + 2);
+    if (n > ovf_cap)
+        n = ovf_cap;
+    for (unsigned long long o = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; o < n;
+         o += (unsigned long long)gridDim.x * blockDim.x) {
+        const int64_t e = ovf_entry[o];
+        const double y = cb_logcount(x[e], 1.0 / sf[ovf_cell[o]]);
+        logx[e] = y;
+        const int g = rowidx[e];
+        if (!(y < y_limit) || g < 0 || g >= G) {
             atomicOr(flag, 2);
+            continue;
+        }
+        atomicAdd(acc1 + g, (unsigned long long)__double2ll_rn(y * scale1));
+        atomicAdd(acc2 + g, (unsigned long long)__double2ll_rn(y * y * scale2));
     }
 }
 
@@ -547,15 +624,33 @@ extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
         CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_genestats_slab<false><<<grid, GS_THREADS, smem, ctx->stream>>>(
             ctx->colptr.p, ctx->rowidx.p, ctx->logx.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
-            sc2, ylim, nullptr, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p);
+            sc2, ylim, nullptr, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, nullptr, nullptr, nullptr, nullptr, 0ull);
+        CB_LAUNCH(ctx);
         ctx->logx_values_only = false;
     } else {
+        // per-cell tables of the logcounts of the counts 1 .. GS_TABLE, then the slab kernel; what the tables do not
+        // cover (a few percent of the entries) goes through an overflow list
+        const unsigned long long ovf_cap = (unsigned long long)ctx->nnz / 4 + 4096;
+        CB_CUDA(ctx, ctx->gs_tab_y.ensure((size_t)ctx->N * GS_TABLE));
+        CB_CUDA(ctx, ctx->gs_tab_q.ensure((size_t)ctx->N * GS_TABLE * 2));
+        CB_CUDA(ctx, ctx->gs_ovf_entry.ensure((size_t)ovf_cap));
+        CB_CUDA(ctx, ctx->gs_ovf_cell.ensure((size_t)ovf_cap));
+        const int64_t nt = ctx->N * GS_TABLE;
+        k_gs_tables<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->sf.p, ctx->N, sc1, sc2, ylim, ctx->gs_tab_y.p,
+                                                                          reinterpret_cast<ulonglong2 *>(ctx->gs_tab_q.p),
+                                                                          ctx->flag.p);
+        CB_LAUNCH(ctx);
         CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_genestats_slab<true><<<grid, GS_THREADS, smem, ctx->stream>>>(
             ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1, sc2,
-            ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p);
+            ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, ctx->gs_tab_y.p,
+            reinterpret_cast<const ulonglong2 *>(ctx->gs_tab_q.p), ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ovf_cap);
+        CB_LAUNCH(ctx);
+        k_gs_overflow<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ctx->gs_queue.p, ovf_cap,
+                                                                ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->G, sc1, sc2, ylim,
+                                                                ctx->logx.p, acc, acc + ctx->G, ctx->flag.p);
+        CB_LAUNCH(ctx);
     }
-    CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_LOGNORM);
     ctx->have_logx = true;
     ctx->gs_flag_pending = true;
@@ -594,6 +689,9 @@ extern "C" int cb200_genestats_finish(cb200_ctx *ctx, double *gene_mean, double 
         CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
         ctx->gs_flag_pending = false;
         CB_CHECK(ctx, (h_flag & 4) == 0, "cb200_lognorm_genestats: internal pipeline error (mbarrier timeout)");
+        CB_CHECK(ctx, (h_flag & 8) == 0,
+                 "cb200_lognorm_genestats: more than a quarter of the values are not integer counts in [1, 32]: this path "
+                 "expects a count matrix");
         CB_CHECK(ctx, (h_flag & 2) == 0,
                  "cb200_lognorm_genestats: a row index is outside [0, n_genes) / rows are not sorted within a column, or a "
                  "log-count is outside the fixed-point range (size factors far from the library sizes?)");

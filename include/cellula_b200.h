@@ -225,6 +225,41 @@ int cb200_pairwise_modularity(cb200_ctx *ctx, const int32_t *from, const int32_t
                               int64_t n_edges, const int32_t *labels, int64_t n, int n_clusters,
                               double *observed_out, double *expected_out, double *total_weight_out);
 
+/* ---- several GPUs of one node from ONE host process (what an R session needs: SURVEY.md 8b) -----------------
+ * cb200_multi_init(n_gpus) opens devices 0 .. n_gpus-1 (n_gpus <= 0: all), one cb200_ctx each, and an NCCL
+ * communicator over them (ncclCommInitAll; NCCL is loaded with dlopen here, the single-GPU path does not need it).
+ * Every call below fans out over one host thread per GPU: GPU r holds the contiguous block of cells
+ * [r N / R, (r+1) N / R) and the stages exchange what SURVEY.md 8e lists (all-reduce of the library-size total,
+ * of the fixed-point gene sums and of the fixed-point cross-product -- integer sums, so the results are
+ * bit-identical to the single-GPU ones --, all-gather of the scores and of the neighbour index).  Host arrays
+ * have the same layouts as in the single-GPU calls and cover ALL cells; pageable memory is staged through pinned
+ * rings by each GPU's thread.  Errors: non-zero return, message from cb200_multi_last_error (m == NULL: of the
+ * last failed cb200_multi_init).
+ *   cb200_multi_knn: emb NULL = the scores left by cb200_multi_pca.  cb200_multi_snn_count / _emit: the two-phase
+ *   form of cb200_snn (index NULL = the resident kNN result); the edges of GPU r land behind those of GPU r-1,
+ *   which is the single-GPU emission order; from == NULL keeps them in HBM. */
+typedef struct cb200_multi cb200_multi;
+int cb200_multi_init(int n_gpus, cb200_multi **out);
+int cb200_multi_free(cb200_multi *m);
+const char *cb200_multi_last_error(const cb200_multi *m);
+int cb200_multi_n_gpus(const cb200_multi *m);
+int cb200_multi_stage_timings(cb200_multi *m, int rank, cb200_timing *out);
+int cb200_multi_load_csc(cb200_multi *m, int64_t n_genes, int64_t n_cells, const int64_t *colptr, const int32_t *rowidx,
+                         const double *values);
+int cb200_multi_load_csc_i32(cb200_multi *m, int64_t n_genes, int64_t n_cells, const int32_t *colptr,
+                             const int32_t *rowidx, const double *values);
+int cb200_multi_size_factors(cb200_multi *m, const double *sf_in /* nullable [N] */, double *sf_out /* nullable [N] */);
+int cb200_multi_lognorm_genestats(cb200_multi *m, double *logx_out /* nullable [nnz] */, double *gene_mean /* [G] */,
+                                  double *gene_var /* [G] */);
+int cb200_multi_pca(cb200_multi *m, const int32_t *hvg_idx, int n_hvg, int d, double *scores /* nullable N x d */,
+                    double *rotation, double *var_explained, double *total_var);
+int cb200_multi_knn(cb200_multi *m, const double *emb /* nullable */, int64_t n_total, int d, int k,
+                    int32_t *index_out /* nullable N x k */);
+int cb200_multi_snn_count(cb200_multi *m, const int32_t *index /* nullable */, int64_t n_total, int k, int type,
+                          int64_t *n_edges);
+int cb200_multi_snn_emit(cb200_multi *m, int32_t *from, int32_t *to, double *weight);
+int cb200_multi_edges_checksum(cb200_multi *m, int64_t *n_edges, uint64_t *checksum);
+
 /* ---- synthetic input (bench / test infrastructure, not part of the reference path) ---
  * ONE generator specification (cellula_b200/csrc/cb200_synth_core.h) compiled for the device and for the
  * host; both produce the same matrix bit for bit (integer hashing + individually rounded IEEE operations).
