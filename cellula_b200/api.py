@@ -82,6 +82,11 @@ def doNormAndReduce(sce, batch=None, name=None, ndims=20, hvg_ntop=2000, umap_se
     # here library-size factors are the default and a pre-set sizeFactor column (e.g. deconvolution
     # factors computed elsewhere) is re-centred exactly as logNormCounts would.
     sf_in = sce.colData.get("sizeFactor") if options["size_factors"] != "library" else None
+    if verbose and sf_in is None:
+        # the R drop-in (r-pkg/) runs the reference's own quickCluster + computeSumFactors by default; this mirror
+        # has no scran, so its default is the library-size fast path -- announced, because the numbers differ
+        _message(_blue("[NORM] "), "   Library-size factors: cellula's default is scran deconvolution (set colData['sizeFactor'] "
+                 "and options['size_factors'] = 'given' to pass such factors in); results differ from that default.")
     if verbose:
         _message(_blue("[NORM] "), "   Log-normalization.")
     sf = ctx.size_factors(sf_in)
@@ -200,6 +205,16 @@ def makeGraphsAndClusters(sce, neighbors=10, weighting_scheme="jaccard", sweep_o
         return ig.community_leiden(objective_function="modularity", weights="weight",
                                    n_iterations=leiden_iterations, resolution=resolution).membership
 
+    def record(g, cl, gname):
+        """colData labels + the per-resolution diagnostics of R/makeGraphsAndClusters.R:98-114 (both sweeps)."""
+        sce.colData[gname] = [str(c + 1) for c in cl]
+        if calculate_modularity:
+            sce.metadata[f"modularity_{gname}"] = pairwiseModularity(g, cl, as_ratio=True)
+        if calculate_silhouette:
+            sil = approxSilhouette(space, cl)
+            sil["closest"] = np.where(sil["width"] > 0, np.asarray(cl), sil["other"])
+            sce.metadata[f"silhouette_{gname}"] = sil
+
     if sweep_on == "clustering" and neighbors is not None:
         if verbose:
             _message(_blue("[CLU]"), "Creating SNN graph.")
@@ -215,14 +230,7 @@ def makeGraphsAndClusters(sce, neighbors=10, weighting_scheme="jaccard", sweep_o
         for res in k:
             if verbose:
                 _message(_blue("[CLU]"), "Clustering at resolution ", res, ".")
-            cl = cluster(g, float(res))
-            gname = f"{prefix}{res:g}"
-            sce.colData[gname] = [str(c + 1) for c in cl]
-            if calculate_modularity:
-                sce.metadata[f"modularity_{gname}"] = pairwiseModularity(g, cl, as_ratio=True)
-            if calculate_silhouette:
-                sil = approxSilhouette(space, cl)
-                sce.metadata[f"silhouette_{gname}"] = sil
+            record(g, cluster(g, float(res)), f"{prefix}{res:g}")
     elif sweep_on == "SNN" and k is not None:
         for kk in np.floor(np.asarray(k)).astype(int):
             if verbose:
@@ -231,14 +239,13 @@ def makeGraphsAndClusters(sce, neighbors=10, weighting_scheme="jaccard", sweep_o
             if save_graphs or not have_igraph:
                 sce.metadata[f"SNN_{kk}_{weighting_scheme}"] = g
             if have_igraph:
-                cl = cluster(g, 1.0)
-                sce.colData[f"{prefix}{kk}"] = [str(c + 1) for c in cl]
+                record(g, cluster(g, 1.0), f"{prefix}{kk}")
     return sce
 
 
 def rebuildModularity(sce, dr="PCA", neighbors=None, ndims=20, labels=None, weighting_scheme="jaccard"):
-    """Graph half of cellula::rebuildModularity: the same makeSNNGraph call with
-    k = round(sqrt(N)) by default; the pairwise modularity itself stays with bluster/igraph."""
+    """cellula::rebuildModularity: the same makeSNNGraph call with k = round(sqrt(N)) by default, then the pairwise
+    modularity of colData[labels] on that graph (as.ratio = TRUE), stored as metadata['modularity_<labels>']."""
     ep = _red("{cellula::rebuildModularity} - ")
     if dr not in sce.reducedDims:
         raise ValueError(ep + "the dr name supplied was not found in the SingleCellExperiment object")
@@ -249,4 +256,6 @@ def rebuildModularity(sce, dr="PCA", neighbors=None, ndims=20, labels=None, weig
         neighbors = int(round(math.sqrt(space.shape[0])))
     g = makeSNNGraph(space, k=neighbors, type=weighting_scheme)
     sce.metadata[f"SNN_{neighbors}_{weighting_scheme}"] = g
+    if labels is not None:     # R/makeGraphsAndClusters.R:286-288
+        sce.metadata[f"modularity_{labels}"] = pairwiseModularity(g, np.asarray(sce.colData[labels]), as_ratio=True)
     return sce

@@ -96,6 +96,7 @@ struct cb200_ctx {
     DevBuf<unsigned long long> gs_tab_q;  // [N*32*2] its fixed-point images
     DevBuf<int64_t> gs_ovf_entry;     // entries the table does not cover
     DevBuf<int32_t> gs_ovf_cell;
+    DevBuf<int32_t> gs_ovf_count;     // entries in every warp's region of the list
     int gs_s1 = 0, gs_s2 = 0, gs_ybits = 0;
     bool gs_flag_pending = false, sf_from_input = false;
     double mean_ls = 0.0;     // mean library size when the size factors are library-size factors, else 0

@@ -105,7 +105,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->colptr.release(); ctx->rowidx.release(); ctx->x.release();
     ctx->libsize.release(); ctx->sf.release(); ctx->part.release(); ctx->flag.release();
-    ctx->logx.release(); ctx->gene_acc.release(); ctx->gs_split.release(); ctx->gs_queue.release(); ctx->gs_tab_y.release(); ctx->gs_tab_q.release(); ctx->gs_ovf_entry.release(); ctx->gs_ovf_cell.release(); ctx->gene_mean.release(); ctx->gene_var.release();
+    ctx->logx.release(); ctx->gene_acc.release(); ctx->gs_split.release(); ctx->gs_queue.release(); ctx->gs_tab_y.release(); ctx->gs_tab_q.release(); ctx->gs_ovf_entry.release(); ctx->gs_ovf_cell.release(); ctx->gs_ovf_count.release(); ctx->gene_mean.release(); ctx->gene_var.release();
     ctx->hvg_idx.release(); ctx->hvg_perm.release(); ctx->hbptr.release(); ctx->gram_img.release(); ctx->slot.release(); ctx->hcnt.release(); ctx->hptr.release();
     ctx->hslot.release(); ctx->hval.release(); ctx->gram.release(); ctx->cov.release();
     ctx->mu.release(); ctx->eq.release(); ctx->ew.release(); ctx->ey.release(); ctx->ex.release();

@@ -9,6 +9,9 @@
 //
 // Algorithmic bytes: K1 8 B/nnz (+16 B/cell); K2+K3 20 B/nnz (read x 8, read i 4,
 // write logcounts 8) + 8 B/cell + 16 B/gene.
+#include <cstdlib>
+#include <cstring>
+
 #include "cb200_common.cuh"
 
 // One warp per column (cell).  Interior of the column is read with 128-bit loads.
@@ -219,9 +222,11 @@ __global__ void k_gs_splits(const int64_t *__restrict__ colptr, const int32_t *_
 
 __device__ __forceinline__ void gs_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GS_CONSUMERS) : "memory"); }
 
-// FUSED = true : staged 8-byte array = counts; computes the logcounts (and writes them)
-// FUSED = false: staged 8-byte array = the logcounts already in HBM (cb200_lognorm_values ran first)
-template <bool FUSED>
+// MODE 0: staged 8-byte array = the logcounts already in HBM (cb200_lognorm_values ran first): gene sums only
+// MODE 1: staged 8-byte array = counts; logcount and fixed-point images of the counts 1 .. GS_TABLE from the cell's
+//         table, everything else appended to the warp's region of the overflow list (k_gs_overflow finishes them)
+// MODE 2: staged 8-byte array = counts; every logcount evaluated in place (matrices that are not small counts)
+template <int MODE>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx, const double *__restrict__ v8,
                  const double *__restrict__ sf, const int32_t *__restrict__ split, int64_t n_cols, int64_t G,
@@ -229,7 +234,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                  double *__restrict__ logx, unsigned long long *__restrict__ acc1, unsigned long long *__restrict__ acc2,
                  unsigned int *__restrict__ queue, int *__restrict__ flag, const double *__restrict__ tab_y,
                  const ulonglong2 *__restrict__ tab_q, int64_t *__restrict__ ovf_entry, int32_t *__restrict__ ovf_cell,
-                 unsigned long long ovf_cap)
+                 int32_t *__restrict__ ovf_count, int64_t ovf_region)
 {
     extern __shared__ __align__(128) unsigned char gs_smem[];
     using namespace cb200tc;
@@ -393,6 +398,9 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
         int stage = 0;
         uint32_t phase = 0;
         int bad = 0;
+        // this warp's region of the overflow list (MODE 1): no atomics, the fill level is a register
+        const int64_t ovf_base = ((int64_t)blockIdx.x * (GS_CONSUMERS / 32) + (warp - 1)) * ovf_region;
+        int64_t ovf_n = 0;
         for (;;) {
             mbar_wait(full + stage, phase, flag);
             const GsItem &it = items[stage];
@@ -404,24 +412,32 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                     const GsSub sb = it.sub[q];
                     const double *s8 = base8 + sb.pos8;
                     const int32_t *s4 = base4 + sb.pos4;
-                    for (int t = ct; t < sb.n; t += GS_CONSUMERS) {
-                        double y = s8[t];
-                        const int g = s4[t] - slab_base;
+                    for (int t0 = ct - lane; t0 < sb.n; t0 += GS_CONSUMERS) {   // uniform trip count per warp (ballot below)
+                        const int t = t0 + lane;
+                        const bool in = t < sb.n;
+                        double y = in ? s8[t] : 1.0;
+                        const int g = in ? s4[t] - slab_base : 0;
                         ulonglong2 add;
-                        if (FUSED) {
+                        if (MODE == 1) {
                             // counts are small integers: the logcount and its two fixed-point images come from the
-                            // cell's table (k_gs_tables); anything else is left to k_gs_overflow
+                            // cell's table (k_gs_tables); anything else goes to this warp's region of the overflow list
                             const int xi = __double2int_rz(y);
-                            if (xi < 1 || xi > GS_TABLE || (double)xi != y) {
-                                const unsigned long long o = atomicAdd(reinterpret_cast<unsigned long long *>(queue + 2), 1ull);
-                                if (o < ovf_cap) {
-                                    ovf_entry[o] = sb.beg + t;
-                                    ovf_cell[o] = sb.cell;
-                                } else {
-                                    bad |= 8;
+                            const bool ovf = in && (xi < 1 || xi > GS_TABLE || (double)xi != y);
+                            const unsigned om = __ballot_sync(0xffffffffu, ovf);
+                            if (om != 0u) {
+                                if (ovf) {
+                                    const int64_t o = ovf_n + __popc(om & ((1u << lane) - 1u));
+                                    if (o < ovf_region) {
+                                        ovf_entry[ovf_base + o] = sb.beg + t;
+                                        ovf_cell[ovf_base + o] = sb.cell;
+                                    } else {
+                                        bad |= 8;
+                                    }
                                 }
-                                continue;
+                                ovf_n += __popc(om);
                             }
+                            if (ovf || !in)
+                                continue;
                             const int64_t ti = (int64_t)sb.cell * GS_TABLE + (xi - 1);
                             y = __ldg(tab_y + ti);
                             add = __ldg(tab_q + ti);
@@ -431,6 +447,12 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                                 continue;
                             }
                         } else {
+                            if (!in)
+                                continue;
+                            if (MODE == 2) {
+                                y = cb_logcount(y, sb.rs);
+                                st_stream(logx + sb.beg + t, y);
+                            }
                             if (!(y < y_limit) || g < 0 || g >= sgenes) {   // out of the fixed-point range / malformed row index
                                 bad |= 2;
                                 continue;
@@ -467,6 +489,8 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
         }
         if (bad)
             atomicOr(flag, bad);
+        if (MODE == 1 && lane == 0)
+            ovf_count[blockIdx.x * (GS_CONSUMERS / 32) + (warp - 1)] = (int32_t)(ovf_n < ovf_region ? ovf_n : ovf_region);
     }
 }
 
@@ -493,30 +517,30 @@ k_gs_tables(const double *__restrict__ sf, int64_t n_cols, double scale1, double
     tab_q[i] = q;
 }
 
-// the entries the table does not cover (counts above GS_TABLE, non-integer values): direct evaluation, integer
-// reductions straight into the global sums
+// the entries the table does not cover (counts above GS_TABLE, non-integer values), region by region of the
+// overflow list: direct evaluation, integer reductions straight into the global sums
 __global__ void __launch_bounds__(256)
-k_gs_overflow(const int64_t *__restrict__ ovf_entry, const int32_t *__restrict__ ovf_cell, const unsigned int *__restrict__ queue,
-              unsigned long long ovf_cap, const int32_t *__restrict__ rowidx, const double *__restrict__ x,
+k_gs_overflow(const int64_t *__restrict__ ovf_entry, const int32_t *__restrict__ ovf_cell, const int32_t *__restrict__ ovf_count,
+              int n_regions, int64_t ovf_region, const int32_t *__restrict__ rowidx, const double *__restrict__ x,
               const double *__restrict__ sf, int64_t G, double scale1, double scale2, double y_limit,
               double *__restrict__ logx, unsigned long long *__restrict__ acc1, unsigned long long *__restrict__ acc2,
               int *__restrict__ flag)
 {
-    unsigned long long n = *reinterpret_cast<const unsigned long long *>(queue + 2);
-    if (n > ovf_cap)
-        n = ovf_cap;
-    for (unsigned long long o = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; o < n;
-         o += (unsigned long long)gridDim.x * blockDim.x) {
-        const int64_t e = ovf_entry[o];
-        const double y = cb_logcount(x[e], 1.0 / sf[ovf_cell[o]]);
-        logx[e] = y;
-        const int g = rowidx[e];
-        if (!(y < y_limit) || g < 0 || g >= G) {
-            atomicOr(flag, 2);
-            continue;
+    for (int r = blockIdx.x; r < n_regions; r += gridDim.x) {
+        const int n = ovf_count[r];
+        const int64_t base = (int64_t)r * ovf_region;
+        for (int o = threadIdx.x; o < n; o += blockDim.x) {
+            const int64_t e = ovf_entry[base + o];
+            const double y = cb_logcount(x[e], 1.0 / sf[ovf_cell[base + o]]);
+            logx[e] = y;
+            const int g = rowidx[e];
+            if (!(y < y_limit) || g < 0 || g >= G) {
+                atomicOr(flag, 2);
+                continue;
+            }
+            atomicAdd(acc1 + g, (unsigned long long)__double2ll_rn(y * scale1));
+            atomicAdd(acc2 + g, (unsigned long long)__double2ll_rn(y * y * scale2));
         }
-        atomicAdd(acc1 + g, (unsigned long long)__double2ll_rn(y * scale1));
-        atomicAdd(acc2 + g, (unsigned long long)__double2ll_rn(y * y * scale2));
     }
 }
 
@@ -619,37 +643,65 @@ extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
     const int grid = (int)(n_work < ctx->num_sms ? n_work : ctx->num_sms);
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(ctx->gene_acc.p);
     const double sc1 = ldexp(1.0, ctx->gs_s1), sc2 = ldexp(1.0, ctx->gs_s2), ylim = ldexp(1.0, ctx->gs_ybits);
+    auto zero_acc = [&]() -> int {
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->gene_acc.p, 0, (size_t)(2 * ctx->G) * sizeof(unsigned long long), ctx->stream));
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->gs_queue.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+        return 0;
+    };
     if (from_logx) {
         // the logcounts exist already (cb200_lognorm_values): only the gene sums are left
-        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_genestats_slab<false><<<grid, GS_THREADS, smem, ctx->stream>>>(
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_genestats_slab<0><<<grid, GS_THREADS, smem, ctx->stream>>>(
             ctx->colptr.p, ctx->rowidx.p, ctx->logx.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
-            sc2, ylim, nullptr, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, nullptr, nullptr, nullptr, nullptr, 0ull);
+            sc2, ylim, nullptr, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
         CB_LAUNCH(ctx);
         ctx->logx_values_only = false;
     } else {
-        // per-cell tables of the logcounts of the counts 1 .. GS_TABLE, then the slab kernel; what the tables do not
-        // cover (a few percent of the entries) goes through an overflow list
-        const unsigned long long ovf_cap = (unsigned long long)ctx->nnz / 4 + 4096;
-        CB_CUDA(ctx, ctx->gs_tab_y.ensure((size_t)ctx->N * GS_TABLE));
-        CB_CUDA(ctx, ctx->gs_tab_q.ensure((size_t)ctx->N * GS_TABLE * 2));
-        CB_CUDA(ctx, ctx->gs_ovf_entry.ensure((size_t)ovf_cap));
-        CB_CUDA(ctx, ctx->gs_ovf_cell.ensure((size_t)ovf_cap));
-        const int64_t nt = ctx->N * GS_TABLE;
-        k_gs_tables<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->sf.p, ctx->N, sc1, sc2, ylim, ctx->gs_tab_y.p,
-                                                                          reinterpret_cast<ulonglong2 *>(ctx->gs_tab_q.p),
-                                                                          ctx->flag.p);
-        CB_LAUNCH(ctx);
-        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_genestats_slab<true><<<grid, GS_THREADS, smem, ctx->stream>>>(
-            ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1, sc2,
-            ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, ctx->gs_tab_y.p,
-            reinterpret_cast<const ulonglong2 *>(ctx->gs_tab_q.p), ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ovf_cap);
-        CB_LAUNCH(ctx);
-        k_gs_overflow<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ctx->gs_queue.p, ovf_cap,
-                                                                ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->G, sc1, sc2, ylim,
-                                                                ctx->logx.p, acc, acc + ctx->G, ctx->flag.p);
-        CB_LAUNCH(ctx);
+        const char *genv = getenv("CB200_LOGNORM_ENGINE");   // "direct": evaluate every logcount in place (cross-check)
+        bool direct = genv != nullptr && strcmp(genv, "direct") == 0;
+        if (!direct) {
+            // per-cell tables of the logcounts of the counts 1 .. GS_TABLE, then the slab kernel; what the tables do
+            // not cover (a few percent of the entries of a count matrix) goes through the overflow list
+            const int n_regions = grid * (GS_CONSUMERS / 32);
+            const int64_t region = (ctx->nnz / 8 + n_regions - 1) / n_regions + 256;
+            CB_CUDA(ctx, ctx->gs_tab_y.ensure((size_t)ctx->N * GS_TABLE));
+            CB_CUDA(ctx, ctx->gs_tab_q.ensure((size_t)ctx->N * GS_TABLE * 2));
+            CB_CUDA(ctx, ctx->gs_ovf_entry.ensure((size_t)region * n_regions));
+            CB_CUDA(ctx, ctx->gs_ovf_cell.ensure((size_t)region * n_regions));
+            CB_CUDA(ctx, ctx->gs_ovf_count.ensure((size_t)n_regions));
+            const int64_t nt = ctx->N * GS_TABLE;
+            k_gs_tables<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->sf.p, ctx->N, sc1, sc2, ylim, ctx->gs_tab_y.p,
+                                                                              reinterpret_cast<ulonglong2 *>(ctx->gs_tab_q.p),
+                                                                              ctx->flag.p);
+            CB_LAUNCH(ctx);
+            CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_genestats_slab<1><<<grid, GS_THREADS, smem, ctx->stream>>>(
+                ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
+                sc2, ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, ctx->gs_tab_y.p,
+                reinterpret_cast<const ulonglong2 *>(ctx->gs_tab_q.p), ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p,
+                ctx->gs_ovf_count.p, region);
+            CB_LAUNCH(ctx);
+            k_gs_overflow<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ctx->gs_ovf_count.p,
+                                                                    n_regions, region, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->G,
+                                                                    sc1, sc2, ylim, ctx->logx.p, acc, acc + ctx->G, ctx->flag.p);
+            CB_LAUNCH(ctx);
+            // a matrix that is not made of small counts overflows its list: evaluate everything in place instead
+            int h_flag = 0;
+            CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
+            if (h_flag & 8) {
+                direct = true;
+                CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+                CB_TRY(zero_acc());
+            }
+        }
+        if (direct) {
+            CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_genestats_slab<2><<<grid, GS_THREADS, smem, ctx->stream>>>(
+                ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
+                sc2, ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, nullptr, nullptr, nullptr, nullptr,
+                nullptr, 0);
+            CB_LAUNCH(ctx);
+        }
     }
     cb_stage_end(ctx, ST_LOGNORM);
     ctx->have_logx = true;
@@ -689,9 +741,6 @@ extern "C" int cb200_genestats_finish(cb200_ctx *ctx, double *gene_mean, double 
         CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
         ctx->gs_flag_pending = false;
         CB_CHECK(ctx, (h_flag & 4) == 0, "cb200_lognorm_genestats: internal pipeline error (mbarrier timeout)");
-        CB_CHECK(ctx, (h_flag & 8) == 0,
-                 "cb200_lognorm_genestats: more than a quarter of the values are not integer counts in [1, 32]: this path "
-                 "expects a count matrix");
         CB_CHECK(ctx, (h_flag & 2) == 0,
                  "cb200_lognorm_genestats: a row index is outside [0, n_genes) / rows are not sorted within a column, or a "
                  "log-count is outside the fixed-point range (size factors far from the library sizes?)");

@@ -27,11 +27,16 @@ doNormAndReduce <- function(sce, batch = NULL, name = NULL,
 
   if (verbose) message(.bluem("[NORM] "), "Calculating size factors and normalizing.")
   .Call("cb200r_load_counts", ctx, cnt, PACKAGE = "cellulaB200")
-  # Size factors: library-size factors on the GPU by default.  With
-  # options(cellula.b200.sizefactors = "deconvolution") the reference's own pre-clustering and
-  # pooled factors (cellula R/doNormAndReduce.R:57-71) run unchanged in R and are only re-centred.
+  # Size factors.  DEFAULT = what the reference does: its own pre-clustering and pooled (deconvolution) factors
+  # (cellula R/doNormAndReduce.R:57-71) run unchanged in R -- they are the only calls that receive `parallel_param`
+  # -- and the GPU re-centres the vector exactly as logNormCounts would, so that a default call returns the
+  # reference's sizeFactors / logcounts / HVGs.  options(cellula.b200.sizefactors = "library") is the explicit
+  # fast path (library-size factors computed on the GPU, no scran pre-clustering): different numbers, announced.
   sf_in <- NULL
-  if (identical(getOption("cellula.b200.sizefactors", "library"), "deconvolution")) {
+  if (identical(getOption("cellula.b200.sizefactors", "deconvolution"), "library")) {
+    if (verbose) message(.bluem("[NORM] "), "   Library-size factors (options(cellula.b200.sizefactors = \"library\")): ",
+                         "results differ from cellula's deconvolution factors.")
+  } else {
     if (verbose) message(.bluem("[NORM] "), "   Preclustering.")
     cl <- scran::quickCluster(sce, min.size = floor(sqrt(ncol(sce))), BPPARAM = parallel_param)
     if (verbose) message(.bluem("[NORM] "), "   Calculating pooled factors.")
@@ -40,9 +45,11 @@ doNormAndReduce <- function(sce, batch = NULL, name = NULL,
   if (verbose) message(.bluem("[NORM] "), "   Log-normalization.")
   sf <- .Call("cb200r_size_factors", ctx, sf_in, ncol(sce), PACKAGE = "cellulaB200")
   sizeFactors(sce) <- sf
-  st <- .Call("cb200r_lognorm_genestats", ctx, as.numeric(length(cnt@x)), nrow(sce), PACKAGE = "cellulaB200")
-  assay(sce, "logcounts") <- new("dgCMatrix", i = cnt@i, p = cnt@p, x = st$x, Dim = cnt@Dim,
-                                 Dimnames = cnt@Dimnames)
+  # Single GPU: the logcounts leave the GPU in the background (8 B per non-zero) while the trend fit and the PCA
+  # run; the vector is handed out by cb200r_logcounts_wait below.  Several GPUs: everything on return.
+  async <- .cb200_gpus() <= 1L
+  st <- if (async) .Call("cb200r_lognorm_begin", ctx, as.numeric(length(cnt@x)), nrow(sce), PACKAGE = "cellulaB200")
+        else .Call("cb200r_lognorm_genestats", ctx, as.numeric(length(cnt@x)), nrow(sce), PACKAGE = "cellulaB200")
 
   if (verbose) message(.bluem("[DR] "), "Selecting HVGs.")
   # trend fit and decomposition stay R code on G points (scran::fitTrendVar is exported)
@@ -67,6 +74,10 @@ doNormAndReduce <- function(sce, batch = NULL, name = NULL,
   attr(scores, "percentVar") <- 100 * pca$varExplained / pca$totalVar
   attr(scores, "rotation") <- rot
   reducedDim(sce, "PCA") <- scores
+
+  lx <- if (async) .Call("cb200r_logcounts_wait", ctx, st$pending, PACKAGE = "cellulaB200") else st$x
+  assay(sce, "logcounts") <- new("dgCMatrix", i = cnt@i, p = cnt@p, x = lx, Dim = cnt@Dim,
+                                 Dimnames = cnt@Dimnames)
 
   if (!isTRUE(getOption("cellula.b200.skip_umap", FALSE))) {
     if (verbose) message(.bluem("[DR] "), "Running UMAP on uncorrected PCA.")

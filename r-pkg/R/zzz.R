@@ -1,11 +1,16 @@
-# Device context shared by the wrappers (an external pointer with a finalizer that calls
-# cb200_free).  options(cellula.b200.device = 0L) selects the GPU.
+# Device context shared by the wrappers (an external pointer with a finalizer that calls cb200_free /
+# cb200_multi_free).  options(cellula.b200.device = 0L) selects the GPU of the single-GPU form;
+# options(cellula.b200.gpus = 8L) drives that many GPUs of the node from this one R process (cells sharded by
+# column inside the library, NCCL between the GPUs; results identical to the single-GPU ones).
 .cb200_env <- new.env(parent = emptyenv())
 
+.cb200_gpus <- function() as.integer(getOption("cellula.b200.gpus", 1L))
+
 .cb200_ctx <- function() {
-  if (is.null(.cb200_env$ctx))
-    .cb200_env$ctx <- .Call("cb200r_init", as.integer(getOption("cellula.b200.device", 0L)),
-                            PACKAGE = "cellulaB200")
+  if (is.null(.cb200_env$ctx)) {
+    device <- as.integer(getOption("cellula.b200.device", 0L))
+    .cb200_env$ctx <- .Call("cb200r_init", device, .cb200_gpus(), PACKAGE = "cellulaB200")
+  }
   .cb200_env$ctx
 }
 

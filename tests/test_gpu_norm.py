@@ -175,3 +175,23 @@ def test_gene_slab_boundaries(gpu_ctx, n_genes):
     x = rng.integers(1, 60, colptr[-1]).astype(np.float64)
     dd = dict(n_genes=n_genes, colptr=colptr, rowidx=rowidx, x=x)
     check_against_oracle(dd, *run_norm(gpu_ctx, dd))
+
+
+def test_table_and_direct_logcount_engines_agree_bit_for_bit(gpu_ctx, small_counts, monkeypatch):
+    """The per-cell logcount tables (counts 1..32) + overflow list and the evaluate-everything-in-place kernel call
+    the same device function: identical logcounts and identical (integer) gene sums."""
+    a = run_norm(gpu_ctx, small_counts)
+    monkeypatch.setenv("CB200_LOGNORM_ENGINE", "direct")
+    b = run_norm(gpu_ctx, small_counts)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+
+
+def test_matrix_of_large_counts_falls_back_to_direct_evaluation(gpu_ctx):
+    rng = np.random.default_rng(8)
+    lens = rng.integers(50, 400, 800)
+    colptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    rowidx = np.concatenate([np.sort(rng.choice(3000, n, replace=False)) for n in lens]).astype(np.int32)
+    x = rng.integers(100, 5000, colptr[-1]).astype(np.float64)           # nothing the 1..32 table covers
+    d = dict(n_genes=3000, colptr=colptr, rowidx=rowidx, x=x)
+    check_against_oracle(d, *run_norm(gpu_ctx, d))
