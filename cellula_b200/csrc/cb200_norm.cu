@@ -170,7 +170,7 @@ extern "C" int cb200_size_factors(cb200_ctx *ctx, const double *sf_in, double *s
 #define GS_CONSUMERS 480
 #define GS_STAGE_ENTRIES 1024   // entries per stage: several column segments are packed into one stage
 #define GS_MAXSUB 8             // ... at most this many
-#define GS_STAGES 6
+#define GS_STAGES 5
 #define GS_SLAB_MAX 9600
 #define GS_CHUNK 512            // cells per work item
 #define GS_ITEM_DATA 0
@@ -241,7 +241,8 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
     ulonglong2 *tab = reinterpret_cast<ulonglong2 *>(gs_smem);                       // [GS_SLAB_MAX]
     unsigned char *stage8 = gs_smem + (size_t)GS_SLAB_MAX * 16;                      // [GS_STAGES][GS_CAP8 * 8]
     unsigned char *stage4 = stage8 + (size_t)GS_STAGES * GS_CAP8 * 8;                 // [GS_STAGES][GS_CAP4 * 4]
-    GsItem *items = reinterpret_cast<GsItem *>(stage4 + (size_t)GS_STAGES * GS_CAP4 * 4);
+    double *stageT = reinterpret_cast<double *>(stage4 + (size_t)GS_STAGES * GS_CAP4 * 4);   // [GS_STAGES][GS_MAXSUB][GS_TABLE]
+    GsItem *items = reinterpret_cast<GsItem *>(stageT + (size_t)GS_STAGES * GS_MAXSUB * GS_TABLE);
     uint64_t *full = reinterpret_cast<uint64_t *>(items + GS_STAGES);
     uint64_t *empty = full + GS_STAGES;
 
@@ -292,6 +293,8 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                     const GsSub &sb = it.sub[q];
                     const int64_t a8 = sb.beg & ~1LL, a4 = sb.beg & ~3LL;        // 16-byte aligned sources
                     total += (uint32_t)(((sb.beg + sb.n - a8 + 1) & ~1LL) * 8) + (uint32_t)(((sb.beg + sb.n - a4 + 3) & ~3LL) * 4);
+                    if (MODE == 1)
+                        total += GS_TABLE * 8;
                 }
                 mbar_expect_tx(full + stage, total);
                 for (int q = 0; q < nsub; ++q) {
@@ -303,6 +306,9 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                              full + stage);
                     bulk_g2s(stage4 + ((size_t)stage * GS_CAP4 + (size_t)(sb.pos4 - (int)(sb.beg - a4))) * 4, rowidx + a4, bytes4,
                              full + stage);
+                    if (MODE == 1)   // the cell's logcount table rides along (256 bytes)
+                        bulk_g2s(stageT + ((size_t)stage * GS_MAXSUB + q) * GS_TABLE, tab_y + (int64_t)sb.cell * GS_TABLE,
+                                 GS_TABLE * 8, full + stage);
                 }
             }
             __syncwarp();
@@ -412,6 +418,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                     const GsSub sb = it.sub[q];
                     const double *s8 = base8 + sb.pos8;
                     const int32_t *s4 = base4 + sb.pos4;
+                    const double *ty = stageT + ((size_t)stage * GS_MAXSUB + q) * GS_TABLE;
                     for (int t0 = ct - lane; t0 < sb.n; t0 += GS_CONSUMERS) {   // uniform trip count per warp (ballot below)
                         const int t = t0 + lane;
                         const bool in = t < sb.n;
@@ -438,14 +445,14 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                             }
                             if (ovf || !in)
                                 continue;
-                            const int64_t ti = (int64_t)sb.cell * GS_TABLE + (xi - 1);
-                            y = __ldg(tab_y + ti);
-                            add = __ldg(tab_q + ti);
+                            y = ty[xi - 1];
                             st_stream(logx + sb.beg + t, y);
-                            if (g < 0 || g >= sgenes) {
+                            if (!(y < y_limit) || g < 0 || g >= sgenes) {
                                 bad |= 2;
                                 continue;
                             }
+                            add.x = (unsigned long long)__double2ll_rn(y * scale1);
+                            add.y = (unsigned long long)__double2ll_rn(y * y * scale2);
                         } else {
                             if (!in)
                                 continue;
@@ -494,27 +501,14 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
     }
 }
 
-// per cell: logcount of the counts 1 .. GS_TABLE and its fixed-point images (y 2^s1, y^2 2^s2); a table entry whose
-// logcount is outside the fixed-point range is reported
+// per cell: logcount of the counts 1 .. GS_TABLE (256 bytes; staged with the cell's segments by the slab kernel)
 __global__ void __launch_bounds__(256)
-k_gs_tables(const double *__restrict__ sf, int64_t n_cols, double scale1, double scale2, double y_limit,
-            double *__restrict__ tab_y, ulonglong2 *__restrict__ tab_q, int *__restrict__ flag)
+k_gs_tables(const double *__restrict__ sf, int64_t n_cols, double *__restrict__ tab_y)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_cols * GS_TABLE)
         return;
-    const int64_t c = i / GS_TABLE;
-    const int x = (int)(i % GS_TABLE) + 1;
-    const double y = cb_logcount((double)x, 1.0 / sf[c]);
-    tab_y[i] = y;
-    ulonglong2 q = make_ulonglong2(0ull, 0ull);
-    if (y < y_limit) {
-        q.x = (unsigned long long)__double2ll_rn(y * scale1);
-        q.y = (unsigned long long)__double2ll_rn(y * y * scale2);
-    } else if (x == 1) {
-        atomicOr(flag, 2);    // even a single count is out of range: the size factors are far from the library sizes
-    }
-    tab_q[i] = q;
+    tab_y[i] = cb_logcount((double)((int)(i % GS_TABLE) + 1), 1.0 / sf[i / GS_TABLE]);
 }
 
 // the entries the table does not cover (counts above GS_TABLE, non-integer values), region by region of the
@@ -637,8 +631,8 @@ extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
                                                                           slab_genes, ctx->gs_split.p);
         CB_LAUNCH(ctx);
     }
-    const size_t smem = (size_t)GS_SLAB_MAX * 16 + (size_t)GS_STAGES * (GS_CAP8 * 8 + GS_CAP4 * 4) + GS_STAGES * sizeof(GsItem) +
-                        2 * GS_STAGES * sizeof(uint64_t);
+    const size_t smem = (size_t)GS_SLAB_MAX * 16 + (size_t)GS_STAGES * (GS_CAP8 * 8 + GS_CAP4 * 4 + GS_MAXSUB * GS_TABLE * 8) +
+                        GS_STAGES * sizeof(GsItem) + 2 * GS_STAGES * sizeof(uint64_t);
     const int64_t n_work = ((ctx->N + GS_CHUNK - 1) / GS_CHUNK) * n_slabs;
     const int grid = (int)(n_work < ctx->num_sms ? n_work : ctx->num_sms);
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(ctx->gene_acc.p);
@@ -665,20 +659,17 @@ extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
             const int n_regions = grid * (GS_CONSUMERS / 32);
             const int64_t region = (ctx->nnz / 8 + n_regions - 1) / n_regions + 256;
             CB_CUDA(ctx, ctx->gs_tab_y.ensure((size_t)ctx->N * GS_TABLE));
-            CB_CUDA(ctx, ctx->gs_tab_q.ensure((size_t)ctx->N * GS_TABLE * 2));
             CB_CUDA(ctx, ctx->gs_ovf_entry.ensure((size_t)region * n_regions));
             CB_CUDA(ctx, ctx->gs_ovf_cell.ensure((size_t)region * n_regions));
             CB_CUDA(ctx, ctx->gs_ovf_count.ensure((size_t)n_regions));
             const int64_t nt = ctx->N * GS_TABLE;
-            k_gs_tables<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->sf.p, ctx->N, sc1, sc2, ylim, ctx->gs_tab_y.p,
-                                                                              reinterpret_cast<ulonglong2 *>(ctx->gs_tab_q.p),
-                                                                              ctx->flag.p);
+            k_gs_tables<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->sf.p, ctx->N, ctx->gs_tab_y.p);
             CB_LAUNCH(ctx);
             CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_genestats_slab<1><<<grid, GS_THREADS, smem, ctx->stream>>>(
                 ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
                 sc2, ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, ctx->gs_tab_y.p,
-                reinterpret_cast<const ulonglong2 *>(ctx->gs_tab_q.p), ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p,
+                nullptr, ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p,
                 ctx->gs_ovf_count.p, region);
             CB_LAUNCH(ctx);
             k_gs_overflow<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ctx->gs_ovf_count.p,
