@@ -24,7 +24,7 @@ c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_vp = ctypes.c_void_p
 
 SNN_TYPES = {"rank": 0, "number": 1, "jaccard": 2}
-BUF = dict(libsize_partial=0, gene_acc=1, gram=2, scores=3, knn=4, size_factors=5, logcounts=6)
+BUF = dict(libsize_partial=0, gene_acc=1, gram=2, scores=3, knn=4, size_factors=5, logcounts=6, block_part=7, block_acc=8)
 
 
 class Timing(ctypes.Structure):
@@ -61,6 +61,15 @@ SIGNATURES = {
     "cb200_wait_copies": (c_int, [c_vp]),
     "cb200_lognorm_genestats": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cb200_lognorm_values": (c_int, [c_vp]),
+    "cb200_set_blocks": (c_int, [c_vp, c_vp, c_int]),
+    "cb200_block_prepare_local": (c_int, [c_vp]),
+    "cb200_block_averages_local": (c_int, [c_vp, ctypes.c_double]),
+    "cb200_block_averages_finish": (c_int, [c_vp, c_vp, c_vp]),
+    "cb200_block_averages": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "cb200_size_factors_given": (c_int, [c_vp, c_vp]),
+    "cb200_lognorm_genestats_blocked_local": (c_int, [c_vp]),
+    "cb200_genestats_blocked_finish": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cb200_lognorm_genestats_blocked": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cb200_pca_gram_local": (c_int, [c_vp, c_vp, c_int]),
     "cb200_pca_finish": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     "cb200_pca": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -291,6 +300,38 @@ class Context:
 
     def wait_copies(self):
         self._ck(lib().cb200_wait_copies(self._h))
+
+    # -- 8(f)-3: batch-aware branch ----------------------------------------------------
+    def block_averages(self, block, n_blocks):
+        """Per-batch gene averages of x / (sf centred within the batch): (ave B x G, mean sf per batch, cells per batch)."""
+        block = np.ascontiguousarray(block, dtype=np.int32)
+        assert block.size == self.n_cells
+        ave = np.empty((n_blocks, self.n_genes))
+        sfm = np.empty(n_blocks)
+        nb = np.empty(n_blocks, dtype=np.int64)
+        self._ck(lib().cb200_block_averages(self._h, _ptr(block), int(n_blocks), _ptr(ave), _ptr(sfm), _ptr(nb)))
+        self.n_blocks = int(n_blocks)
+        return ave, sfm, nb
+
+    def set_blocks(self, block, n_blocks):
+        block = np.ascontiguousarray(block, dtype=np.int32)
+        assert block.size == self.n_cells
+        self._ck(lib().cb200_set_blocks(self._h, _ptr(block), int(n_blocks)))
+        self.n_blocks = int(n_blocks)
+
+    def size_factors_given(self, sf):
+        """Size factors used as they are (multiBatchNorm's rescaled factors): no centring."""
+        sf = np.ascontiguousarray(sf, dtype=np.float64)
+        assert sf.size == self.n_cells
+        self._ck(lib().cb200_size_factors_given(self._h, _ptr(sf)))
+
+    def lognorm_genestats_blocked(self, want_logx=True):
+        """(logcounts, mean B x G, var B x G): statistics within every block set by set_blocks / block_averages."""
+        logx = np.empty(self.nnz) if want_logx else None
+        mean = np.empty((self.n_blocks, self.n_genes))
+        var = np.empty((self.n_blocks, self.n_genes))
+        self._ck(lib().cb200_lognorm_genestats_blocked(self._h, _ptr(logx), _ptr(mean), _ptr(var)))
+        return logx, mean, var
 
     # -- a7 -------------------------------------------------------------------------
     def pca(self, hvg_idx, d, want_scores=True, scores_out=None):

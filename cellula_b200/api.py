@@ -67,11 +67,6 @@ def doNormAndReduce(sce, batch=None, name=None, ndims=20, hvg_ntop=2000, umap_se
             raise ValueError(ep + "batch column not found in the colData of the object")
     if hvg_ntop > sce.nrow():
         raise ValueError(ep + "hvg_ntop cannot be higher than the number of features (nrow) in the object")
-    if batch is not None:
-        # R/doNormAndReduce.R:58-62,74-76,84-86 (multiBatchNorm, blocked modelGeneVar): not on the
-        # accelerated path yet.  No silent CPU fallback.
-        raise NotImplementedError(ep + "the batch-aware path is not implemented on the B200 backend")
-
     ctx = get_context()
     counts = sce.counts
     n_genes, n_cells = counts.shape
@@ -90,15 +85,27 @@ def doNormAndReduce(sce, batch=None, name=None, ndims=20, hvg_ntop=2000, umap_se
     if verbose:
         _message(_blue("[NORM] "), "   Log-normalization.")
     sf = ctx.size_factors(sf_in)
-    logx, mean, var = ctx.lognorm_genestats(want_logx=True, want_stats=True)
+    if batch is None:
+        logx, mean, var = ctx.lognorm_genestats(want_logx=True, want_stats=True)
+    else:
+        # batch-aware branch (R/doNormAndReduce.R:74-76, :84-86): multiBatchNorm rescales the size factors so that the
+        # batches are comparable (per-batch gene averages on the GPU, the B x B median ratios on the host), then
+        # modelGeneVar(block=) fits one trend per batch on the per-batch statistics
+        levels, codes = np.unique(np.asarray(sce.colData[batch]), return_inverse=True)
+        codes = codes.astype(np.int32)
+        ave, _, n_per = ctx.block_averages(codes, levels.size)
+        sf = trendvar.rescale_size_factors(ave, sf, codes)
+        ctx.size_factors_given(sf)
+        logx, mean_b, var_b = ctx.lognorm_genestats_blocked(want_logx=True)
     sce.colData["sizeFactor"] = sf
     sce.assays["logcounts"] = CSC(counts.p, counts.i, logx, counts.shape)  # shares i/p like R
 
     if verbose:
         _message(_blue("[DR] "), "Selecting HVGs.")
-    stats = trendvar.model_gene_var(mean, var)
+    stats = trendvar.model_gene_var(mean, var) if batch is None else trendvar.model_gene_var_blocked(mean_b, var_b, n_per)
     for key in ("mean", "total", "tech", "bio", "p_value", "FDR"):
-        sce.rowData[key] = stats[key]
+        if key in stats:
+            sce.rowData[key] = stats[key]
     hvg_idx = trendvar.get_top_hvgs(stats, hvg_ntop)
     hvgs = [sce.rownames[i] for i in hvg_idx] if sce.rownames is not None else hvg_idx.copy()
     sce.metadata["hvgs"] = hvgs

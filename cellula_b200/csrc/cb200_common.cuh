@@ -99,6 +99,17 @@ struct cb200_ctx {
     DevBuf<int32_t> gs_ovf_count;     // entries in every warp's region of the list
     int gs_s1 = 0, gs_s2 = 0, gs_ybits = 0;
     bool gs_flag_pending = false, sf_from_input = false;
+    bool gs_split_ready = false;      // cut points valid for the loaded matrix
+    bool gs_tables_ready = false;     // logcount tables valid for the current size factors
+    // ---- 8(f)-3: blocks (batches) of cells
+    int n_blocks = 0;
+    DevBuf<int32_t> blk_id;           // [N] block of every local cell
+    DevBuf<int32_t> blk_cells;        // [N] local cells grouped by block
+    DevBuf<int64_t> blk_ptr;          // [B+1] their offsets (device)
+    std::vector<int64_t> blk_ptr_h;   // [B+1] their offsets (host)
+    DevBuf<double> blk_part;          // [2B+1] per block: sum of the size factors, #cells; then max_c colsum_c / sf_c
+    DevBuf<double> blk_w;             // [N] scratch: column sums / weights
+    int blk_s = 0;                    // fixed-point shift of the per-block sums of x / sf
     double mean_ls = 0.0;     // mean library size when the size factors are library-size factors, else 0
     DevBuf<double> gene_mean, gene_var;  // [G]
     bool have_sf = false, have_logx = false, have_genestats = false;

@@ -105,7 +105,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->colptr.release(); ctx->rowidx.release(); ctx->x.release();
     ctx->libsize.release(); ctx->sf.release(); ctx->part.release(); ctx->flag.release();
-    ctx->logx.release(); ctx->gene_acc.release(); ctx->gs_split.release(); ctx->gs_queue.release(); ctx->gs_tab_y.release(); ctx->gs_tab_q.release(); ctx->gs_ovf_entry.release(); ctx->gs_ovf_cell.release(); ctx->gs_ovf_count.release(); ctx->gene_mean.release(); ctx->gene_var.release();
+    ctx->logx.release(); ctx->gene_acc.release(); ctx->gs_split.release(); ctx->gs_queue.release(); ctx->gs_tab_y.release(); ctx->gs_tab_q.release(); ctx->gs_ovf_entry.release(); ctx->gs_ovf_cell.release(); ctx->gs_ovf_count.release(); ctx->blk_id.release(); ctx->blk_cells.release(); ctx->blk_ptr.release(); ctx->blk_part.release(); ctx->blk_w.release(); ctx->gene_mean.release(); ctx->gene_var.release();
     ctx->hvg_idx.release(); ctx->hvg_perm.release(); ctx->hbptr.release(); ctx->gram_img.release(); ctx->slot.release(); ctx->hcnt.release(); ctx->hptr.release();
     ctx->hslot.release(); ctx->hval.release(); ctx->gram.release(); ctx->cov.release();
     ctx->mu.release(); ctx->eq.release(); ctx->ew.release(); ctx->ey.release(); ctx->ex.release();
@@ -395,6 +395,8 @@ extern "C" int cb200_device_ptr(cb200_ctx *ctx, int which, void **ptr, int64_t *
     case CB200_BUF_KNN: *ptr = ctx->knn.p; *bytes = ctx->knn_nq * (int64_t)ctx->knn_k * (int64_t)sizeof(int32_t); break;
     case CB200_BUF_SIZE_FACTORS: *ptr = ctx->sf.p; *bytes = ctx->N * (int64_t)sizeof(double); break;
     case CB200_BUF_LOGCOUNTS: *ptr = ctx->logx.p; *bytes = ctx->nnz * (int64_t)sizeof(double); break;
+    case CB200_BUF_BLOCK_PART: *ptr = ctx->blk_part.p; *bytes = (2 * (int64_t)ctx->n_blocks + 1) * (int64_t)sizeof(double); break;
+    case CB200_BUF_BLOCK_ACC: *ptr = ctx->gene_acc.p; *bytes = 2 * ctx->G * (int64_t)ctx->n_blocks * (int64_t)sizeof(double); break;
     default: return cb200_fail(ctx, "cb200_device_ptr: unknown buffer id %d", which);
     }
     if (*ptr == nullptr)
@@ -453,6 +455,8 @@ static int load_common(cb200_ctx *ctx, int64_t n_genes, int64_t n_cells, int64_t
     ctx->rowidx_pending = true;
     ctx->logx_values_only = false;
     ctx->loaded = true;
+    ctx->gs_split_ready = ctx->gs_tables_ready = false;
+    ctx->n_blocks = 0;
     ctx->have_sf = ctx->have_logx = ctx->have_genestats = ctx->have_gram = ctx->have_scores = false;
     ctx->have_knn = false;
     return 0;

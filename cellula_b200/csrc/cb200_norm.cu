@@ -133,6 +133,7 @@ extern "C" int cb200_size_factors_finish(cb200_ctx *ctx, double total, int64_t n
     CB_CHECK(ctx, h_flag == 0, "size factors should be positive");
     ctx->mean_ls = ctx->sf_from_input ? 0.0 : mean_ls;
     ctx->have_sf = true;
+    ctx->gs_tables_ready = false;
     return 0;
 }
 
@@ -226,6 +227,9 @@ __device__ __forceinline__ void gs_consumer_sync() { asm volatile("bar.sync 1, %
 // MODE 1: staged 8-byte array = counts; logcount and fixed-point images of the counts 1 .. GS_TABLE from the cell's
 //         table, everything else appended to the warp's region of the overflow list (k_gs_overflow finishes them)
 // MODE 2: staged 8-byte array = counts; every logcount evaluated in place (matrices that are not small counts)
+// MODE 3: staged 8-byte array = counts; sums of x / sf per gene (batchelor::multiBatchNorm's per-batch averages):
+//         first accumulator only, nothing written
+// cell_list != NULL: the columns cell_list[0 .. n_cols) instead of 0 .. n_cols (the cells of one block / batch)
 template <int MODE>
 __global__ void __launch_bounds__(GS_THREADS, 1)
 k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx, const double *__restrict__ v8,
@@ -234,7 +238,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                  double *__restrict__ logx, unsigned long long *__restrict__ acc1, unsigned long long *__restrict__ acc2,
                  unsigned int *__restrict__ queue, int *__restrict__ flag, const double *__restrict__ tab_y,
                  const ulonglong2 *__restrict__ tab_q, int64_t *__restrict__ ovf_entry, int32_t *__restrict__ ovf_cell,
-                 int32_t *__restrict__ ovf_count, int64_t ovf_region)
+                 int32_t *__restrict__ ovf_count, int64_t ovf_region, const int32_t *__restrict__ cell_list)
 {
     extern __shared__ __align__(128) unsigned char gs_smem[];
     using namespace cb200tc;
@@ -349,10 +353,12 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
             const int64_t c0 = chunk * GS_CHUNK;
             const int64_t c1 = c0 + GS_CHUNK < n_cols ? c0 + GS_CHUNK : n_cols;
             for (int64_t cb = c0; cb < c1; cb += 32) {
-                const int64_t c = cb + lane;
+                int64_t c = cb + lane;
                 int64_t beg = 0, end = 0;
                 double s = 1.0;
                 if (c < c1) {
+                    if (cell_list != nullptr)
+                        c = cell_list[c];
                     const int64_t b = colptr[c], e = colptr[c + 1];
                     beg = slab == 0 ? b : b + split[c * nb + slab - 1];
                     end = slab == nb ? e : b + split[c * nb + slab];
@@ -363,6 +369,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                     int64_t jb = __shfl_sync(0xffffffffu, beg, j);
                     const int64_t je = __shfl_sync(0xffffffffu, end, j);
                     const double js = __shfl_sync(0xffffffffu, s, j);
+                    const int jc = __shfl_sync(0xffffffffu, (int)c, j);
                     while (jb < je) {
                         if (open && (fill >= GS_STAGE_ENTRIES || nsub >= GS_MAXSUB))
                             close();
@@ -381,7 +388,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                             sb.beg = jb;
                             sb.rs = js;
                             sb.n = n;
-                            sb.cell = (int32_t)(cb + j);
+                            sb.cell = jc;
                             // the segment's 16-byte aligned image starts at an aligned position of the stage arrays
                             sb.pos8 = cur8 + (int)(jb & 1);
                             sb.pos4 = cur4 + (int)(jb & 3);
@@ -460,12 +467,14 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                                 y = cb_logcount(y, sb.rs);
                                 st_stream(logx + sb.beg + t, y);
                             }
+                            if (MODE == 3)
+                                y = y * sb.rs;
                             if (!(y < y_limit) || g < 0 || g >= sgenes) {   // out of the fixed-point range / malformed row index
                                 bad |= 2;
                                 continue;
                             }
                             add.x = (unsigned long long)__double2ll_rn(y * scale1);
-                            add.y = (unsigned long long)__double2ll_rn(y * y * scale2);
+                            add.y = MODE == 3 ? 0ull : (unsigned long long)__double2ll_rn(y * y * scale2);
                         }
                         ulonglong2 a = tab[g];
                         a.x += add.x;
@@ -604,100 +613,128 @@ static void gs_scales(cb200_ctx *ctx)
     ctx->gs_s2 = 63 - lgn - 2 * ybits;
 }
 
-extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
+// One run of the slab kernel over the columns cell_list[0 .. n_items) (NULL: all N columns) into the accumulators
+// acc1 / acc2.  mode as in k_genestats_slab; mode 1 is followed by the overflow kernel.
+static int gs_launch(cb200_ctx *ctx, int mode, const int32_t *cell_list, int64_t n_items, unsigned long long *acc1,
+                     unsigned long long *acc2, double sc1, double sc2, double ylim, const double *weights)
 {
-    if (ctx == nullptr)
-        return 1;
-    CB_CHECK(ctx, ctx->loaded && ctx->have_sf, "cb200_lognorm_genestats: size factors have not been computed");
-    CB_CUDA(ctx, cudaSetDevice(ctx->device));
-    CB_CUDA(ctx, ctx->logx.ensure((size_t)ctx->nnz + 16));
-    CB_CUDA(ctx, ctx->gene_acc.ensure((size_t)(2 * ctx->G)));
-    CB_CUDA(ctx, ctx->gs_queue.ensure(4));
-    gs_scales(ctx);
-    CB_CHECK(ctx, ctx->gs_s2 >= 8, "cb200_lognorm_genestats: too many cells for the fixed-point gene sums");
+    if (n_items <= 0)
+        return 0;
     const int n_slabs = (int)((ctx->G + GS_SLAB_MAX - 1) / GS_SLAB_MAX);
     const int slab_genes = (int)((ctx->G + n_slabs - 1) / n_slabs);
-    CB_TRY(cb200_need_rowidx(ctx));
-    const bool from_logx = ctx->have_logx && ctx->logx_values_only;
-    if (!from_logx)
-        cb_stage_begin(ctx, ST_LOGNORM);   // (after cb200_lognorm_values the stage is already open)
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->gene_acc.p, 0, (size_t)(2 * ctx->G) * sizeof(unsigned long long), ctx->stream));
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->gs_queue.p, 0, 4 * sizeof(unsigned int), ctx->stream));
-    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
-    if (n_slabs > 1) {
+    if (n_slabs > 1 && !ctx->gs_split_ready) {
         CB_CUDA(ctx, ctx->gs_split.ensure((size_t)ctx->N * (n_slabs - 1)));
         const int64_t n = ctx->N * (n_slabs - 1);
         k_gs_splits<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->N, n_slabs,
                                                                           slab_genes, ctx->gs_split.p);
         CB_LAUNCH(ctx);
+        ctx->gs_split_ready = true;
     }
     const size_t smem = (size_t)GS_SLAB_MAX * 16 + (size_t)GS_STAGES * (GS_CAP8 * 8 + GS_CAP4 * 4 + GS_MAXSUB * GS_TABLE * 8) +
                         GS_STAGES * sizeof(GsItem) + 2 * GS_STAGES * sizeof(uint64_t);
-    const int64_t n_work = ((ctx->N + GS_CHUNK - 1) / GS_CHUNK) * n_slabs;
+    const int64_t n_work = ((n_items + GS_CHUNK - 1) / GS_CHUNK) * n_slabs;
     const int grid = (int)(n_work < ctx->num_sms ? n_work : ctx->num_sms);
+    CB_CUDA(ctx, ctx->gs_queue.ensure(4));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->gs_queue.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+    const double *sfp = weights != nullptr ? weights : ctx->sf.p;
+#define GS_ARGS(V8, LOGX, TABY, OE, OC, ON, REG)                                                                         \
+    ctx->colptr.p, ctx->rowidx.p, V8, sfp, ctx->gs_split.p, n_items, ctx->G, n_slabs, slab_genes, sc1, sc2, ylim, LOGX,    \
+        acc1, acc2, ctx->gs_queue.p, ctx->flag.p, TABY, nullptr, OE, OC, ON, REG, cell_list
+    if (mode == 0) {
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_genestats_slab<0><<<grid, GS_THREADS, smem, ctx->stream>>>(GS_ARGS(ctx->logx.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0));
+        CB_LAUNCH(ctx);
+    } else if (mode == 1) {
+        const int n_regions = grid * (GS_CONSUMERS / 32);
+        const int64_t region = (ctx->nnz / 8 + n_regions - 1) / n_regions + 256;
+        CB_CUDA(ctx, ctx->gs_ovf_entry.ensure((size_t)region * n_regions));
+        CB_CUDA(ctx, ctx->gs_ovf_cell.ensure((size_t)region * n_regions));
+        CB_CUDA(ctx, ctx->gs_ovf_count.ensure((size_t)n_regions));
+        if (!ctx->gs_tables_ready) {   // logcounts of the counts 1 .. GS_TABLE of every cell
+            CB_CUDA(ctx, ctx->gs_tab_y.ensure((size_t)ctx->N * GS_TABLE));
+            const int64_t nt = ctx->N * GS_TABLE;
+            k_gs_tables<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->sf.p, ctx->N, ctx->gs_tab_y.p);
+            CB_LAUNCH(ctx);
+            ctx->gs_tables_ready = true;
+        }
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_genestats_slab<1><<<grid, GS_THREADS, smem, ctx->stream>>>(
+            GS_ARGS(ctx->x.p, ctx->logx.p, ctx->gs_tab_y.p, ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ctx->gs_ovf_count.p, region));
+        CB_LAUNCH(ctx);
+        k_gs_overflow<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ctx->gs_ovf_count.p,
+                                                                n_regions, region, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->G, sc1,
+                                                                sc2, ylim, ctx->logx.p, acc1, acc2, ctx->flag.p);
+        CB_LAUNCH(ctx);
+    } else if (mode == 2) {
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_genestats_slab<2><<<grid, GS_THREADS, smem, ctx->stream>>>(GS_ARGS(ctx->x.p, ctx->logx.p, nullptr, nullptr, nullptr, nullptr, 0));
+        CB_LAUNCH(ctx);
+    } else {
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_genestats_slab<3><<<grid, GS_THREADS, smem, ctx->stream>>>(GS_ARGS(ctx->x.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0));
+        CB_LAUNCH(ctx);
+    }
+#undef GS_ARGS
+    return 0;
+}
+
+// logcounts + fixed-point gene sums of the whole shard (n_blocks == 0) or of every block of cells separately
+// (acc = [block][2][G]); table engine first, everything in place when the matrix is not made of small counts
+static int gs_lognorm_sums(cb200_ctx *ctx, int n_blocks)
+{
+    CB_CUDA(ctx, ctx->logx.ensure((size_t)ctx->nnz + 16));
+    const int nb = n_blocks > 0 ? n_blocks : 1;
+    CB_CUDA(ctx, ctx->gene_acc.ensure((size_t)nb * 2 * ctx->G));
+    gs_scales(ctx);
+    CB_CHECK(ctx, ctx->gs_s2 >= 8, "cb200_lognorm_genestats: too many cells for the fixed-point gene sums");
+    CB_TRY(cb200_need_rowidx(ctx));
+    const bool from_logx = ctx->have_logx && ctx->logx_values_only;
+    if (!from_logx)
+        cb_stage_begin(ctx, ST_LOGNORM);   // (after cb200_lognorm_values the stage is already open)
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
     unsigned long long *acc = reinterpret_cast<unsigned long long *>(ctx->gene_acc.p);
     const double sc1 = ldexp(1.0, ctx->gs_s1), sc2 = ldexp(1.0, ctx->gs_s2), ylim = ldexp(1.0, ctx->gs_ybits);
-    auto zero_acc = [&]() -> int {
-        CB_CUDA(ctx, cudaMemsetAsync(ctx->gene_acc.p, 0, (size_t)(2 * ctx->G) * sizeof(unsigned long long), ctx->stream));
-        CB_CUDA(ctx, cudaMemsetAsync(ctx->gs_queue.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+    auto run = [&](int mode) -> int {
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->gene_acc.p, 0, (size_t)nb * 2 * ctx->G * sizeof(unsigned long long), ctx->stream));
+        if (n_blocks <= 0)
+            return gs_launch(ctx, mode, nullptr, ctx->N, acc, acc + ctx->G, sc1, sc2, ylim, nullptr);
+        for (int b = 0; b < n_blocks; ++b)
+            CB_TRY(gs_launch(ctx, mode, ctx->blk_cells.p + ctx->blk_ptr_h[(size_t)b], ctx->blk_ptr_h[(size_t)b + 1] - ctx->blk_ptr_h[(size_t)b],
+                             acc + (size_t)b * 2 * ctx->G, acc + (size_t)b * 2 * ctx->G + ctx->G, sc1, sc2, ylim, nullptr));
         return 0;
     };
     if (from_logx) {
-        // the logcounts exist already (cb200_lognorm_values): only the gene sums are left
-        CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_genestats_slab<0><<<grid, GS_THREADS, smem, ctx->stream>>>(
-            ctx->colptr.p, ctx->rowidx.p, ctx->logx.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
-            sc2, ylim, nullptr, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
-        CB_LAUNCH(ctx);
+        CB_TRY(run(0));   // the logcounts exist already (cb200_lognorm_values): only the gene sums are left
         ctx->logx_values_only = false;
     } else {
         const char *genv = getenv("CB200_LOGNORM_ENGINE");   // "direct": evaluate every logcount in place (cross-check)
         bool direct = genv != nullptr && strcmp(genv, "direct") == 0;
         if (!direct) {
-            // per-cell tables of the logcounts of the counts 1 .. GS_TABLE, then the slab kernel; what the tables do
-            // not cover (a few percent of the entries of a count matrix) goes through the overflow list
-            const int n_regions = grid * (GS_CONSUMERS / 32);
-            const int64_t region = (ctx->nnz / 8 + n_regions - 1) / n_regions + 256;
-            CB_CUDA(ctx, ctx->gs_tab_y.ensure((size_t)ctx->N * GS_TABLE));
-            CB_CUDA(ctx, ctx->gs_ovf_entry.ensure((size_t)region * n_regions));
-            CB_CUDA(ctx, ctx->gs_ovf_cell.ensure((size_t)region * n_regions));
-            CB_CUDA(ctx, ctx->gs_ovf_count.ensure((size_t)n_regions));
-            const int64_t nt = ctx->N * GS_TABLE;
-            k_gs_tables<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->sf.p, ctx->N, ctx->gs_tab_y.p);
-            CB_LAUNCH(ctx);
-            CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_genestats_slab<1><<<grid, GS_THREADS, smem, ctx->stream>>>(
-                ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
-                sc2, ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, ctx->gs_tab_y.p,
-                nullptr, ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p,
-                ctx->gs_ovf_count.p, region);
-            CB_LAUNCH(ctx);
-            k_gs_overflow<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gs_ovf_entry.p, ctx->gs_ovf_cell.p, ctx->gs_ovf_count.p,
-                                                                    n_regions, region, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->G,
-                                                                    sc1, sc2, ylim, ctx->logx.p, acc, acc + ctx->G, ctx->flag.p);
-            CB_LAUNCH(ctx);
+            CB_TRY(run(1));
             // a matrix that is not made of small counts overflows its list: evaluate everything in place instead
             int h_flag = 0;
             CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
             if (h_flag & 8) {
                 direct = true;
                 CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
-                CB_TRY(zero_acc());
             }
         }
-        if (direct) {
-            CB_CUDA(ctx, cudaFuncSetAttribute(k_genestats_slab<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_genestats_slab<2><<<grid, GS_THREADS, smem, ctx->stream>>>(
-                ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->sf.p, ctx->gs_split.p, ctx->N, ctx->G, n_slabs, slab_genes, sc1,
-                sc2, ylim, ctx->logx.p, acc, acc + ctx->G, ctx->gs_queue.p, ctx->flag.p, nullptr, nullptr, nullptr, nullptr,
-                nullptr, 0);
-            CB_LAUNCH(ctx);
-        }
+        if (direct)
+            CB_TRY(run(2));
     }
     cb_stage_end(ctx, ST_LOGNORM);
     ctx->have_logx = true;
     ctx->gs_flag_pending = true;
     return 0;
+}
+
+extern "C" int cb200_lognorm_genestats_local(cb200_ctx *ctx)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->loaded && ctx->have_sf, "cb200_lognorm_genestats: size factors have not been computed");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return gs_lognorm_sums(ctx, 0);
 }
 
 // Logcounts only (K2), from the values and the column pointers: callable while the row indices are still
@@ -788,6 +825,364 @@ extern "C" int cb200_lognorm_genestats(cb200_ctx *ctx, double *logx_out, double 
         return 1;
     CB_TRY(cb200_lognorm_genestats_local(ctx));
     CB_TRY(cb200_genestats_finish(ctx, gene_mean, gene_var));
+    if (logx_out != nullptr)
+        CB_TRY(cb200_fetch_logcounts(ctx, logx_out));
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// the batch-aware branch of doNormAndReduce (R/doNormAndReduce.R:58-62, :74-76, :84-86)
+//   batchelor::multiBatchNorm(sce, batch = ...)   -> per-batch averages of x / sf on the GPU (cb200_block_averages);
+//                                                     the B x B median-ratio rescaling is G-sized host code
+//   scran::modelGeneVar(sce, block = ...)         -> per-block mean / variance of the logcounts
+//                                                     (cb200_lognorm_genestats_blocked); trend fits stay host code
+// The per-block sums use the same fixed-point slab kernel, run once per block over that block's list of cells.
+// ---------------------------------------------------------------------------------------
+__global__ void k_blk_hist(const int32_t *__restrict__ blk, int64_t n, int B, int *__restrict__ cnt, int *__restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int b = blk[i];
+        if (b < 0 || b >= B)
+            atomicOr(flag, 1);
+        else
+            atomicAdd(cnt + b, 1);
+    }
+}
+// cells of every block in ascending order (one thread per block: B is small, the lists feed whole kernels)
+__global__ void k_blk_fill(const int32_t *__restrict__ blk, int64_t n, int B, const int64_t *__restrict__ ptr,
+                           int32_t *__restrict__ cells)
+{
+    const int b = blockIdx.x;
+    __shared__ int base;
+    if (threadIdx.x == 0)
+        base = 0;
+    __syncthreads();
+    for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool mine = i < n && blk[i] == b;
+        // ordered compaction: ballot per warp, warp offsets through shared memory
+        __shared__ int wcnt[32];
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0)
+            wcnt[w] = __popc(m);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
+            if (q < w)
+                off += wcnt[q];
+            tot += wcnt[q];
+        }
+        if (mine)
+            cells[ptr[b] + base + off + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            base += tot;
+        __syncthreads();
+    }
+}
+
+extern "C" int cb200_set_blocks(cb200_ctx *ctx, const int32_t *block, int n_blocks)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->loaded, "cb200_set_blocks: no count matrix loaded");
+    CB_CHECK(ctx, block != nullptr && n_blocks >= 1 && n_blocks <= 4096, "cb200_set_blocks: need 1 <= n_blocks <= 4096");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int B = n_blocks;
+    CB_CUDA(ctx, ctx->blk_id.ensure((size_t)ctx->N));
+    CB_CUDA(ctx, ctx->blk_cells.ensure((size_t)ctx->N));
+    CB_CUDA(ctx, ctx->hcnt.ensure((size_t)(ctx->N > B ? ctx->N : B)));
+    CB_CUDA(ctx, ctx->hptr.ensure((size_t)(ctx->N > B ? ctx->N : B) + 1));
+    CB_TRY(cb200_h2d(ctx, ctx->blk_id.p, block, (size_t)ctx->N * sizeof(int32_t), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->hcnt.p, 0, (size_t)B * sizeof(int32_t), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    k_blk_hist<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(ctx->blk_id.p, ctx->N, B, ctx->hcnt.p, ctx->flag.p);
+    CB_LAUNCH(ctx);
+    CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->hcnt.p, B, ctx->hptr.p));
+    CB_CUDA(ctx, ctx->blk_ptr.ensure((size_t)B + 1));
+    CB_CUDA(ctx, cudaMemcpyAsync(ctx->blk_ptr.p, ctx->hptr.p, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    k_blk_fill<<<B, 256, 0, ctx->stream>>>(ctx->blk_id.p, ctx->N, B, ctx->blk_ptr.p, ctx->blk_cells.p);
+    CB_LAUNCH(ctx);
+    ctx->blk_ptr_h.assign((size_t)B + 1, 0);
+    CB_TRY(cb200_read_back(ctx, ctx->blk_ptr_h.data(), ctx->blk_ptr.p, (size_t)(B + 1) * sizeof(int64_t)));
+    int h_flag = 0;
+    CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
+    CB_CHECK(ctx, h_flag == 0, "cb200_set_blocks: block ids must be in [0, n_blocks)");
+    ctx->n_blocks = B;
+    ctx->have_gram = ctx->have_scores = false;
+    return 0;
+}
+
+// per block: [sum of the size factors, #cells], then max over the cells of colsum / sf (bounds x / sf)
+__global__ void __launch_bounds__(256)
+k_blk_part(const int32_t *__restrict__ cells, const int64_t *__restrict__ ptr, int B, const double *__restrict__ sf,
+           const double *__restrict__ colsum, double *__restrict__ part)
+{
+    const int b = blockIdx.x;
+    __shared__ double ssum[8], smax[8];
+    double s = 0.0, mx = 0.0;
+    for (int64_t i = ptr[b] + threadIdx.x; i < ptr[b + 1]; i += blockDim.x) {   // fixed assignment: deterministic
+        const int c = cells[i];
+        s += sf[c];
+        mx = fmax(mx, colsum[c] / sf[c]);
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) {
+        ssum[threadIdx.x >> 5] = s;
+        smax[threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0, m = 0.0;
+        for (int q = 0; q < 8; ++q) {
+            t += ssum[q];
+            m = fmax(m, smax[q]);
+        }
+        part[2 * b] = t;
+        part[2 * b + 1] = (double)(ptr[b + 1] - ptr[b]);
+        atomicMax(reinterpret_cast<unsigned long long *>(part + 2 * B), (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+// Phase 1 (rank-local): fills CB200_BUF_BLOCK_PART = double[2B + 1]: per block the sum of its cells' size factors and its
+// cell count (a multi-GPU caller SUM-reduces these 2B numbers), then the largest colsum / sf (MAX-reduce).
+extern "C" int cb200_block_prepare_local(cb200_ctx *ctx)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->loaded && ctx->have_sf && ctx->n_blocks > 0, "cb200_block_averages: call cb200_size_factors and cb200_set_blocks first");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int B = ctx->n_blocks;
+    CB_CUDA(ctx, ctx->blk_part.ensure((size_t)2 * B + 1));
+    CB_CUDA(ctx, ctx->blk_w.ensure((size_t)ctx->N));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->blk_part.p, 0, (size_t)(2 * B + 1) * sizeof(double), ctx->stream));
+    const int grid = cb_grid_for(ctx->N, 8, ctx->num_sms * 8);
+    k_colsum_csc<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->x.p, ctx->N, ctx->blk_w.p);
+    CB_LAUNCH(ctx);
+    k_blk_part<<<B, 256, 0, ctx->stream>>>(ctx->blk_cells.p, ctx->blk_ptr.p, B, ctx->sf.p, ctx->blk_w.p, ctx->blk_part.p);
+    CB_LAUNCH(ctx);
+    return 0;
+}
+
+// Phase 2 (rank-local): per block and gene the fixed-point sum of x / sf over the block's local cells into
+// CB200_BUF_GENE_ACC = int64[B][2][G] (second plane unused); max_ratio = the (reduced) last entry of the part buffer
+extern "C" int cb200_block_averages_local(cb200_ctx *ctx, double max_ratio)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->n_blocks > 0 && ctx->blk_part.p != nullptr, "cb200_block_averages: call cb200_block_prepare_local first");
+    CB_CHECK(ctx, max_ratio > 0.0 && max_ratio < 1e300, "cb200_block_averages: size factors should be positive");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int B = ctx->n_blocks;
+    int lgn = 0, rbits = 1;
+    while (((int64_t)1 << lgn) < ctx->N_total)
+        ++lgn;
+    while (ldexp(1.0, rbits) <= max_ratio * (1.0 + 1e-9))
+        ++rbits;
+    ctx->blk_s = 62 - lgn - rbits;
+    CB_CHECK(ctx, ctx->blk_s >= -60, "cb200_block_averages: counts / size factors too large for the fixed-point sums");
+    CB_CUDA(ctx, ctx->gene_acc.ensure((size_t)B * 2 * ctx->G));
+    CB_TRY(cb200_need_rowidx(ctx));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->gene_acc.p, 0, (size_t)B * 2 * ctx->G * sizeof(unsigned long long), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(ctx->gene_acc.p);
+    for (int b = 0; b < B; ++b)
+        CB_TRY(gs_launch(ctx, 3, ctx->blk_cells.p + ctx->blk_ptr_h[(size_t)b], ctx->blk_ptr_h[(size_t)b + 1] - ctx->blk_ptr_h[(size_t)b],
+                         acc + (size_t)b * 2 * ctx->G, acc + (size_t)b * 2 * ctx->G + ctx->G, ldexp(1.0, ctx->blk_s), 0.0,
+                         ldexp(1.0, rbits), nullptr));
+    ctx->gs_flag_pending = true;
+    return 0;
+}
+
+__global__ void k_blk_ave_finish(const unsigned long long *__restrict__ acc, int64_t G, int B, int s, const double *__restrict__ part,
+                                 double *__restrict__ ave)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < (int64_t)B * G) {
+        const int b = (int)(i / G);
+        const int64_t g = i % G;
+        const double n = part[2 * b + 1], sfmean = n > 0.0 ? part[2 * b] / n : 1.0;
+        // mean over the block of x / (sf / mean_block(sf)): scuttle::calculateAverage with block-centred factors
+        ave[i] = n > 0.0 ? ldexp((double)acc[((size_t)b * 2) * G + g], -s) * sfmean / n : 0.0;
+    }
+}
+
+// Phase 3: part_global = the reduced double[2B] (sums of the size factors, cell counts).  ave_out: row-major B x G.
+extern "C" int cb200_block_averages_finish(cb200_ctx *ctx, const double *part_global, double *ave_out)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->n_blocks > 0 && part_global != nullptr && ave_out != nullptr, "cb200_block_averages_finish: bad arguments");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int B = ctx->n_blocks;
+    if (ctx->gs_flag_pending) {
+        int h_flag = 0;
+        CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
+        ctx->gs_flag_pending = false;
+        CB_CHECK(ctx, (h_flag & 6) == 0, "cb200_block_averages: a row index is outside [0, n_genes) or a count / size factor is out of range");
+    }
+    CB_TRY(cb200_write_small(ctx, ctx->blk_part.p, part_global, (size_t)2 * B * sizeof(double)));
+    CB_CUDA(ctx, ctx->stage_d.ensure((size_t)B * ctx->G));
+    const int64_t n = (int64_t)B * ctx->G;
+    k_blk_ave_finish<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(ctx->gene_acc.p),
+                                                                         ctx->G, B, ctx->blk_s, ctx->blk_part.p, ctx->stage_d.p);
+    CB_LAUNCH(ctx);
+    return cb200_read_back(ctx, ave_out, ctx->stage_d.p, (size_t)n * sizeof(double));
+}
+
+extern "C" int cb200_block_averages(cb200_ctx *ctx, const int32_t *block, int n_blocks, double *ave_out, double *sf_mean_out,
+                                    int64_t *n_out)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_TRY(cb200_set_blocks(ctx, block, n_blocks));
+    CB_TRY(cb200_block_prepare_local(ctx));
+    std::vector<double> part((size_t)2 * n_blocks + 1);
+    CB_TRY(cb200_read_back(ctx, part.data(), ctx->blk_part.p, part.size() * sizeof(double)));
+    CB_TRY(cb200_block_averages_local(ctx, part[(size_t)2 * n_blocks]));
+    CB_TRY(cb200_block_averages_finish(ctx, part.data(), ave_out));
+    for (int b = 0; b < n_blocks; ++b) {
+        if (sf_mean_out != nullptr)
+            sf_mean_out[b] = part[(size_t)2 * b + 1] > 0.0 ? part[(size_t)2 * b] / part[(size_t)2 * b + 1] : 0.0;
+        if (n_out != nullptr)
+            n_out[b] = (int64_t)llround(part[(size_t)2 * b + 1]);
+    }
+    return 0;
+}
+
+// multiBatchNorm's rescaled size factors are used as they are (logNormCounts(center.size.factors = FALSE))
+extern "C" int cb200_size_factors_given(cb200_ctx *ctx, const double *sf)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->loaded && sf != nullptr, "cb200_size_factors_given: no count matrix loaded / NULL input");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CB_CUDA(ctx, ctx->sf.ensure((size_t)ctx->N));
+    CB_CUDA(ctx, ctx->libsize.ensure((size_t)ctx->N));
+    CB_TRY(cb200_h2d(ctx, ctx->libsize.p, sf, (size_t)ctx->N * sizeof(double), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    k_sf_finish<<<(unsigned)((ctx->N + 255) / 256), 256, 0, ctx->stream>>>(ctx->libsize.p, ctx->N, 1.0, ctx->sf.p, ctx->flag.p);
+    CB_LAUNCH(ctx);
+    int h_flag = 0;
+    CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
+    CB_CHECK(ctx, h_flag == 0, "size factors should be positive");
+    ctx->sf_from_input = true;
+    ctx->mean_ls = 0.0;
+    ctx->have_sf = true;
+    ctx->gs_tables_ready = false;
+    ctx->have_logx = ctx->have_genestats = false;
+    return 0;
+}
+
+extern "C" int cb200_lognorm_genestats_blocked_local(cb200_ctx *ctx)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->loaded && ctx->have_sf && ctx->n_blocks > 0,
+             "cb200_lognorm_genestats_blocked: size factors and blocks (cb200_set_blocks) must be set first");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return gs_lognorm_sums(ctx, ctx->n_blocks);
+}
+
+__global__ void k_genestats_blocked_finish(const unsigned long long *__restrict__ acc, int64_t G, int B, const double *__restrict__ nb,
+                                           int s1, int s2, double *__restrict__ mean, double *__restrict__ var,
+                                           double *__restrict__ mean_all, double *__restrict__ var_all, double n_all)
+{
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= G)
+        return;
+    unsigned long long St = 0, Qt = 0;
+    for (int b = 0; b < B; ++b) {
+        const unsigned long long S = acc[((size_t)b * 2) * G + g], Q = acc[((size_t)b * 2 + 1) * G + g];
+        St += S;
+        Qt += Q;
+        const double n = nb[b];
+        double m = nan(""), v = nan("");
+        if (n >= 1.0) {
+            m = ldexp((double)S, -s1) / n;
+            if (n >= 2.0) {
+                const unsigned __int128 nq = ((unsigned __int128)(unsigned long long)n * Q) << (2 * s1 - s2);
+                const unsigned __int128 ss = (unsigned __int128)S * S;
+                double num = 0.0;
+                if (nq > ss) {
+                    const unsigned __int128 dlt = nq - ss;
+                    num = ldexp((double)(unsigned long long)(dlt >> 64), 64) + (double)(unsigned long long)dlt;
+                }
+                v = ldexp(num, -2 * s1) / (n * (n - 1.0));
+            }
+        }
+        mean[(size_t)b * G + g] = m;
+        var[(size_t)b * G + g] = v;
+    }
+    // the statistics over all cells (what the PCA centres with) from the same integer sums
+    const unsigned __int128 nq = ((unsigned __int128)(unsigned long long)n_all * Qt) << (2 * s1 - s2);
+    const unsigned __int128 ss = (unsigned __int128)St * St;
+    double num = 0.0;
+    if (nq > ss) {
+        const unsigned __int128 dlt = nq - ss;
+        num = ldexp((double)(unsigned long long)(dlt >> 64), 64) + (double)(unsigned long long)dlt;
+    }
+    mean_all[g] = ldexp((double)St, -s1) / n_all;
+    var_all[g] = n_all > 1.0 ? ldexp(num, -2 * s1) / (n_all * (n_all - 1.0)) : nan("");
+}
+
+// n_per_block: total cells of every block over all ranks.  gene_mean / gene_var: row-major B x G (NaN where a block has
+// fewer than 1 / 2 cells, like scran).  The context also keeps the all-cell statistics for the PCA.
+extern "C" int cb200_genestats_blocked_finish(cb200_ctx *ctx, const int64_t *n_per_block, double *gene_mean, double *gene_var)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->have_logx && ctx->n_blocks > 0 && n_per_block != nullptr, "cb200_genestats_blocked_finish: call cb200_lognorm_genestats_blocked_local first");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int B = ctx->n_blocks;
+    if (ctx->gs_flag_pending) {
+        int h_flag = 0;
+        CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
+        ctx->gs_flag_pending = false;
+        CB_CHECK(ctx, (h_flag & 4) == 0, "cb200_lognorm_genestats: internal pipeline error (mbarrier timeout)");
+        CB_CHECK(ctx, (h_flag & 2) == 0,
+                 "cb200_lognorm_genestats: a row index is outside [0, n_genes) / rows are not sorted within a column, or a "
+                 "log-count is outside the fixed-point range (size factors far from the library sizes?)");
+    }
+    std::vector<double> nb((size_t)B);
+    double n_all = 0.0;
+    for (int b = 0; b < B; ++b) {
+        nb[(size_t)b] = (double)n_per_block[b];
+        n_all += nb[(size_t)b];
+    }
+    CB_CHECK(ctx, (int64_t)n_all == ctx->N_total, "cb200_genestats_blocked_finish: the block sizes do not add up to the number of cells");
+    CB_CUDA(ctx, ctx->blk_part.ensure((size_t)2 * B + 1));
+    CB_TRY(cb200_write_small(ctx, ctx->blk_part.p, nb.data(), (size_t)B * sizeof(double)));
+    CB_CUDA(ctx, ctx->gene_mean.ensure((size_t)ctx->G));
+    CB_CUDA(ctx, ctx->gene_var.ensure((size_t)ctx->G));
+    CB_CUDA(ctx, ctx->stage_d.ensure((size_t)2 * B * ctx->G));
+    k_genestats_blocked_finish<<<(unsigned)((ctx->G + 255) / 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const unsigned long long *>(ctx->gene_acc.p), ctx->G, B, ctx->blk_part.p, ctx->gs_s1, ctx->gs_s2, ctx->stage_d.p,
+        ctx->stage_d.p + (size_t)B * ctx->G, ctx->gene_mean.p, ctx->gene_var.p, n_all);
+    CB_LAUNCH(ctx);
+    if (gene_mean != nullptr)
+        CB_TRY(cb200_read_back(ctx, gene_mean, ctx->stage_d.p, (size_t)B * ctx->G * sizeof(double)));
+    if (gene_var != nullptr)
+        CB_TRY(cb200_read_back(ctx, gene_var, ctx->stage_d.p + (size_t)B * ctx->G, (size_t)B * ctx->G * sizeof(double)));
+    ctx->have_genestats = true;
+    return 0;
+}
+
+extern "C" int cb200_lognorm_genestats_blocked(cb200_ctx *ctx, double *logx_out, double *gene_mean, double *gene_var)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_TRY(cb200_lognorm_genestats_blocked_local(ctx));
+    std::vector<int64_t> nb((size_t)ctx->n_blocks);
+    for (int b = 0; b < ctx->n_blocks; ++b)
+        nb[(size_t)b] = ctx->blk_ptr_h[(size_t)b + 1] - ctx->blk_ptr_h[(size_t)b];
+    CB_TRY(cb200_genestats_blocked_finish(ctx, nb.data(), gene_mean, gene_var));
     if (logx_out != nullptr)
         CB_TRY(cb200_fetch_logcounts(ctx, logx_out));
     return 0;

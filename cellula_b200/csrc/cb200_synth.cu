@@ -143,6 +143,8 @@ extern "C" int cb200_synth_counts(cb200_ctx *ctx, int64_t n_genes, int64_t n_cel
     wf.release();
     cent.release();
     ctx->loaded = true;
+    ctx->gs_split_ready = ctx->gs_tables_ready = false;
+    ctx->n_blocks = 0;
     ctx->have_sf = ctx->have_logx = ctx->have_genestats = ctx->have_gram = ctx->have_scores = false;
     ctx->have_knn = false;
     if (nnz_out != nullptr)

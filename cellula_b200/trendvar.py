@@ -277,6 +277,45 @@ def model_gene_var(means, variances, want_pvalues=True):
     return dict(mean=means, total=variances, tech=tech, bio=bio, p_value=p, FDR=fdr)
 
 
+def model_gene_var_blocked(means, variances, n_per_block):
+    """scran::modelGeneVar(block=) from per-block statistics (rows = blocks): one trend per block with >= 2 cells,
+    then the unweighted average of mean / total / tech / bio over those blocks (equiweight = TRUE)."""
+    means = np.asarray(means, dtype=np.float64)
+    variances = np.asarray(variances, dtype=np.float64)
+    use = [b for b in range(means.shape[0]) if n_per_block[b] >= 2]
+    if not use:
+        raise ValueError("no block with at least 2 cells")
+    per = [model_gene_var(means[b], variances[b], want_pvalues=False) for b in use]
+    return {k: np.mean([p[k] for p in per], axis=0) for k in ("mean", "total", "tech", "bio")}
+
+
+def rescale_size_factors(ave, sf, block, min_mean=1.0):
+    """batchelor:::.rescale_size_factors on the GPU-computed batch averages (rows = batches): pairwise median ratios
+    over the genes with grand mean >= min_mean; every batch is scaled down to the batch of lowest coverage."""
+    ave = np.asarray(ave, dtype=np.float64)
+    sf = np.asarray(sf, dtype=np.float64)
+    block = np.asarray(block)
+    nb = ave.shape[0]
+    ratios = np.ones((nb, nb))
+    sums = ave.sum(axis=1)
+    for a in range(nb - 1):
+        for b in range(a + 1, nb):
+            grand = (ave[a] / sums[a] + ave[b] / sums[b]) / 2 * (sums[a] + sums[b]) / 2
+            keep = grand >= min_mean
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cur = np.median(ave[b][keep] / ave[a][keep]) if keep.any() else np.nan
+            if not np.isfinite(cur) or cur == 0:
+                raise ValueError("median ratio of averages between batches is not finite")
+            ratios[a, b] = cur
+            ratios[b, a] = 1.0 / cur
+    smallest = int(np.argmin(ratios.min(axis=0)))
+    out = np.empty_like(sf)
+    for b in range(nb):
+        cells = block == b
+        out[cells] = sf[cells] / sf[cells].mean() / ratios[b, smallest]
+    return out
+
+
 def get_top_hvgs(stats, n):
     bio = np.asarray(stats["bio"] if isinstance(stats, dict) else stats)
     keep = np.flatnonzero(np.isfinite(bio) & (bio > 0))

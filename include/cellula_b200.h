@@ -51,7 +51,9 @@ enum {
     CB200_BUF_KNN = 4,             /* int32[n_query*k] row-major, 0-based global indices      */
     CB200_BUF_SIZE_FACTORS = 5,    /* double[n_local]                                         */
     CB200_BUF_LOGCOUNTS = 6,       /* double[nnz_local]                                       */
-    CB200_BUF_COUNT_ = 7
+    CB200_BUF_BLOCK_PART = 7,      /* double[2B+1]: per block sum of size factors, #cells (SUM-reduce); max colsum/sf (MAX)  */
+    CB200_BUF_BLOCK_ACC = 8,       /* int64[B][2][G]: per-block fixed-point gene sums (integer SUM-reduce)                 */
+    CB200_BUF_COUNT_ = 9
 };
 
 /* per-stage device times of the most recent call of each stage, milliseconds (CUDA events
@@ -142,6 +144,33 @@ int cb200_fetch_logcounts_async(cb200_ctx *ctx, double *logx_out /* [nnz_local] 
 int cb200_wait_copies(cb200_ctx *ctx);
 int cb200_lognorm_genestats(cb200_ctx *ctx, double *logx_out /* nullable */, double *gene_mean,
                             double *gene_var);
+
+/* ---- the batch-aware branch -------------------------------------------------------------------
+ * Replaces the arithmetic of batchelor::multiBatchNorm(sce, batch = ) and scran::modelGeneVar(sce, block = ) in
+ * /root/reference/R/doNormAndReduce.R:74-76 and :84-86 (reached from cellula(batch = ...), R/cellula.r:145-150).
+ * block: host int32[n_local], 0-based ids in [0, n_blocks) (levels of the batch factor).
+ *   cb200_block_averages: per batch b and gene g the mean over the batch's cells of x / (sf / mean_b(sf)) --
+ *     scuttle::calculateAverage with batch-centred size factors, what multiBatchNorm compares between batches.
+ *     ave_out row-major B x G; sf_mean_out[B] = mean_b(sf); n_out[B] = cells per batch.  The B x B median-ratio
+ *     rescaling (batchelor:::.rescale_size_factors) is G-sized host code (r-pkg/R, cellula_b200/api.py); its result
+ *     comes back through cb200_size_factors_given, which takes the factors AS THEY ARE (no centring), like
+ *     logNormCounts(center.size.factors = FALSE) inside multiBatchNorm.
+ *   cb200_lognorm_genestats_blocked: logcounts as usual; mean / variance per gene WITHIN every block (row-major
+ *     B x G, NaN where a block has < 1 / < 2 cells); the trend fits per block and their combination stay host code.
+ * _local / _finish forms for multi-GPU callers: cb200_block_prepare_local fills CB200_BUF_BLOCK_PART (SUM-reduce the
+ * first 2B doubles, MAX-reduce the last), cb200_block_averages_local / cb200_lognorm_genestats_blocked_local fill
+ * CB200_BUF_BLOCK_ACC (integer SUM-reduce), the _finish calls take the reduced block sizes. */
+int cb200_set_blocks(cb200_ctx *ctx, const int32_t *block, int n_blocks);
+int cb200_block_prepare_local(cb200_ctx *ctx);
+int cb200_block_averages_local(cb200_ctx *ctx, double max_ratio);
+int cb200_block_averages_finish(cb200_ctx *ctx, const double *part_global /* [2B] */, double *ave_out /* [B*G] */);
+int cb200_block_averages(cb200_ctx *ctx, const int32_t *block, int n_blocks, double *ave_out, double *sf_mean_out /* nullable */,
+                         int64_t *n_out /* nullable */);
+int cb200_size_factors_given(cb200_ctx *ctx, const double *sf /* [n_local], used as they are */);
+int cb200_lognorm_genestats_blocked_local(cb200_ctx *ctx);
+int cb200_genestats_blocked_finish(cb200_ctx *ctx, const int64_t *n_per_block /* [B], all ranks */, double *gene_mean /* nullable [B*G] */,
+                                   double *gene_var /* nullable [B*G] */);
+int cb200_lognorm_genestats_blocked(cb200_ctx *ctx, double *logx_out /* nullable */, double *gene_mean, double *gene_var);
 
 /* ---- a7: PCA on the HVG subset -------------------------------------------------------
  * Replaces: scater::runPCA(sce, subset_row=hvgs, exprs_values="logcounts",

@@ -415,6 +415,80 @@ def model_gene_var(means, vars_):
     return dict(mean=means, total=vars_, tech=tech, bio=bio, p_value=p, FDR=fdr, std_dev=fit.std_dev)
 
 
+# ---------------------------------------------------------------------------------------
+# batch-aware branch (R/doNormAndReduce.R:74-76, :84-86) -- batchelor::multiBatchNorm and
+# scran::modelGeneVar(block=), restated from the packages' definitions (un-vendored: parity unpinned)
+# ---------------------------------------------------------------------------------------
+def batch_averages(n_genes, colptr, rowidx, x, sf, block, n_blocks):
+    """Per batch: scuttle::calculateAverage(counts_b, size.factors = sf_b) = rowMeans(t(t(counts_b) / (sf_b / mean(sf_b))))."""
+    colptr = np.asarray(colptr, dtype=np.int64)
+    col_of = np.repeat(np.arange(colptr.size - 1), np.diff(colptr))
+    ave = np.zeros((n_blocks, n_genes))
+    for b in range(n_blocks):
+        cells = np.flatnonzero(block == b)
+        if cells.size == 0:
+            continue
+        sfc = sf / sf[cells].mean()
+        sel = block[col_of] == b
+        ave[b] = np.bincount(rowidx[sel], weights=x[sel] / sfc[col_of[sel]], minlength=n_genes) / cells.size
+    return ave
+
+
+def rescale_size_factors(ave, sf, block, min_mean=1.0):
+    """batchelor:::.rescale_size_factors: pairwise median ratio of the batch averages over the genes whose grand mean
+    is >= min_mean; every batch is scaled down to the batch of lowest coverage.  Returns the per-cell factors
+    multiBatchNorm hands to logNormCounts(center.size.factors = FALSE)."""
+    nb = ave.shape[0]
+    ratios = np.ones((nb, nb))
+    for first in range(nb - 1):
+        fa = ave[first]
+        fs = fa.sum()
+        for second in range(first + 1, nb):
+            sa = ave[second]
+            ss = sa.sum()
+            grand = (fa / fs + sa / ss) / 2 * (fs + ss) / 2
+            keep = grand >= min_mean
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cur = np.median(sa[keep] / fa[keep])
+            if not np.isfinite(cur) or cur == 0:
+                raise ValueError("median ratio of averages between batches is not finite")
+            ratios[first, second] = cur
+            ratios[second, first] = 1.0 / cur
+    smallest = int(np.argmin(ratios.min(axis=0)))
+    out = np.empty_like(sf)
+    for b in range(nb):
+        cells = block == b
+        out[cells] = sf[cells] / sf[cells].mean() / ratios[b, smallest]
+    return out
+
+
+def gene_mean_var_blocked(n_genes, colptr, rowidx, y, block, n_blocks):
+    colptr = np.asarray(colptr, dtype=np.int64)
+    col_of = np.repeat(np.arange(colptr.size - 1), np.diff(colptr))
+    mean = np.full((n_blocks, n_genes), np.nan)
+    var = np.full((n_blocks, n_genes), np.nan)
+    for b in range(n_blocks):
+        n = int((block == b).sum())
+        if n == 0:
+            continue
+        sel = block[col_of] == b
+        m, v = gene_mean_var(n_genes, n, rowidx[sel], y[sel])
+        mean[b] = m
+        if n >= 2:
+            var[b] = v
+    return mean, var
+
+
+def model_gene_var_blocked(means, vars_, n_per_block):
+    """scran::modelGeneVar(block=): a trend per block, then the unweighted average of the per-block mean / total /
+    tech / bio over the blocks with at least 2 cells (equiweight = TRUE); getTopHVGs ranks by that `bio`."""
+    use = [b for b in range(means.shape[0]) if n_per_block[b] >= 2]
+    per = [model_gene_var(means[b], vars_[b]) for b in use]
+    out = {k: np.mean([p[k] for p in per], axis=0) for k in ("mean", "total", "tech", "bio")}
+    out["per_block"] = per
+    return out
+
+
 def get_top_hvgs(bio, n):
     """scran::getTopHVGs(stats, n=n): keep bio > 0, order(bio, decreasing=TRUE) (ties by
     row index), first n.  Returns 0-based row indices (row a6)."""

@@ -18,8 +18,8 @@ doNormAndReduce <- function(sce, batch = NULL, name = NULL,
   }
   if (hvg_ntop > nrow(sce))
     stop(ep, "hvg_ntop cannot be higher than the number of features (nrow) in the object")
-  if (!is.null(batch))
-    stop(ep, "the batch-aware path is not implemented on the B200 backend")  # no CPU fallback
+  if (!is.null(batch) && .cb200_gpus() > 1L)
+    stop(ep, "the batch-aware path runs on one GPU: set options(cellula.b200.gpus = 1)")  # no CPU fallback
 
   ctx <- .cb200_ctx()
   cnt <- counts(sce)
@@ -38,27 +38,60 @@ doNormAndReduce <- function(sce, batch = NULL, name = NULL,
                          "results differ from cellula's deconvolution factors.")
   } else {
     if (verbose) message(.bluem("[NORM] "), "   Preclustering.")
-    cl <- scran::quickCluster(sce, min.size = floor(sqrt(ncol(sce))), BPPARAM = parallel_param)
+    cl <- if (!is.null(batch))
+      scran::quickCluster(sce, block = colData(sce)[, batch],
+                          min.size = floor(sqrt(min(table(colData(sce)[, batch])))), BPPARAM = parallel_param)
+    else scran::quickCluster(sce, min.size = floor(sqrt(ncol(sce))), BPPARAM = parallel_param)
     if (verbose) message(.bluem("[NORM] "), "   Calculating pooled factors.")
     sf_in <- sizeFactors(scran::computeSumFactors(sce, clusters = cl, BPPARAM = parallel_param))
   }
   if (verbose) message(.bluem("[NORM] "), "   Log-normalization.")
   sf <- .Call("cb200r_size_factors", ctx, sf_in, ncol(sce), PACKAGE = "cellulaB200")
   sizeFactors(sce) <- sf
+  if (!is.null(batch)) {
+    # multiBatchNorm (cellula R/doNormAndReduce.R:74-76): per-batch gene averages on the GPU, then the B x B
+    # median-ratio rescaling of batchelor:::.rescale_size_factors in R (G-sized), factors handed back as they are
+    bf <- factor(colData(sce)[, batch])
+    codes <- as.integer(bf) - 1L
+    av <- .Call("cb200r_block_averages", ctx, codes, nlevels(bf), nrow(sce), PACKAGE = "cellulaB200")
+    sf <- .rescale_size_factors_b200(av$ave, sf, codes)
+    .Call("cb200r_size_factors_given", ctx, sf, PACKAGE = "cellulaB200")
+    sizeFactors(sce) <- sf
+  }
   # Single GPU: the logcounts leave the GPU in the background (8 B per non-zero) while the trend fit and the PCA
   # run; the vector is handed out by cb200r_logcounts_wait below.  Several GPUs: everything on return.
-  async <- .cb200_gpus() <= 1L
-  st <- if (async) .Call("cb200r_lognorm_begin", ctx, as.numeric(length(cnt@x)), nrow(sce), PACKAGE = "cellulaB200")
+  async <- .cb200_gpus() <= 1L && is.null(batch)
+  st <- if (!is.null(batch))
+          .Call("cb200r_lognorm_genestats_blocked", ctx, as.numeric(length(cnt@x)), nrow(sce), nlevels(bf),
+                PACKAGE = "cellulaB200")
+        else if (async) .Call("cb200r_lognorm_begin", ctx, as.numeric(length(cnt@x)), nrow(sce), PACKAGE = "cellulaB200")
         else .Call("cb200r_lognorm_genestats", ctx, as.numeric(length(cnt@x)), nrow(sce), PACKAGE = "cellulaB200")
 
   if (verbose) message(.bluem("[DR] "), "Selecting HVGs.")
   # trend fit and decomposition stay R code on G points (scran::fitTrendVar is exported)
-  fit <- scran::fitTrendVar(st$mean, st$var)
-  tech <- fit$trend(st$mean)
-  vargenes <- DataFrame(mean = st$mean, total = st$var, tech = tech, bio = st$var - tech,
-                        row.names = rownames(sce))
-  vargenes$p.value <- pnorm(vargenes$total / vargenes$tech, mean = 1, sd = fit$std.dev, lower.tail = FALSE)
-  vargenes$FDR <- p.adjust(vargenes$p.value, method = "BH")
+  if (is.null(batch)) {
+    fit <- scran::fitTrendVar(st$mean, st$var)
+    tech <- fit$trend(st$mean)
+    vargenes <- DataFrame(mean = st$mean, total = st$var, tech = tech, bio = st$var - tech,
+                          row.names = rownames(sce))
+    vargenes$p.value <- pnorm(vargenes$total / vargenes$tech, mean = 1, sd = fit$std.dev, lower.tail = FALSE)
+    vargenes$FDR <- p.adjust(vargenes$p.value, method = "BH")
+  } else {
+    # modelGeneVar(block = ): one trend per batch with >= 2 cells, unweighted average of the per-batch columns
+    # (equiweight = TRUE); p-values combined with Stouffer's method like scran (metapod::parallelStouffer)
+    per <- lapply(which(av$n >= 2), function(b) {
+      fit <- scran::fitTrendVar(st$mean[, b], st$var[, b])
+      tech <- fit$trend(st$mean[, b])
+      list(mean = st$mean[, b], total = st$var[, b], tech = tech, bio = st$var[, b] - tech,
+           p = pnorm(st$var[, b] / tech, mean = 1, sd = fit$std.dev, lower.tail = FALSE))
+    })
+    avg <- function(k) rowMeans(do.call(cbind, lapply(per, `[[`, k)))
+    vargenes <- DataFrame(mean = avg("mean"), total = avg("total"), tech = avg("tech"), bio = avg("bio"),
+                          row.names = rownames(sce))
+    z <- rowSums(do.call(cbind, lapply(per, function(p) qnorm(p$p, lower.tail = FALSE)))) / sqrt(length(per))
+    vargenes$p.value <- pnorm(z, lower.tail = FALSE)
+    vargenes$FDR <- p.adjust(vargenes$p.value, method = "BH")
+  }
   rowData(sce)[, colnames(vargenes)] <- vargenes
   hvgs <- getTopHVGs(vargenes, n = hvg_ntop)
   metadata(sce)$hvgs <- hvgs
@@ -88,4 +121,31 @@ doNormAndReduce <- function(sce, batch = NULL, name = NULL,
                                     min_dist = 0.7)
   }
   sce
+}
+
+
+# batchelor:::.rescale_size_factors on the GPU-computed batch averages (ave: G x B): pairwise median ratio of the
+# averages over the genes whose grand mean is >= min.mean; every batch is scaled down to the lowest-coverage one.
+.rescale_size_factors_b200 <- function(ave, sf, codes, min.mean = 1) {
+  nb <- ncol(ave)
+  ratios <- matrix(1, nb, nb)
+  for (first in seq_len(nb - 1L)) {
+    fa <- ave[, first]; fs <- sum(fa)
+    for (second in first + seq_len(nb - first)) {
+      sa <- ave[, second]; ss <- sum(sa)
+      grand <- (fa / fs + sa / ss) / 2 * (fs + ss) / 2
+      keep <- grand >= min.mean
+      cur <- median(sa[keep] / fa[keep])
+      if (!is.finite(cur) || cur == 0) stop("median ratio of averages between batches is not finite")
+      ratios[first, second] <- cur
+      ratios[second, first] <- 1 / cur
+    }
+  }
+  smallest <- which.min(apply(ratios, 2, min, na.rm = TRUE))
+  out <- sf
+  for (b in seq_len(nb)) {
+    cells <- codes == (b - 1L)
+    out[cells] <- sf[cells] / mean(sf[cells]) / ratios[b, smallest]
+  }
+  out
 }

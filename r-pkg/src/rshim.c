@@ -176,6 +176,60 @@ SEXP cb200r_logcounts_wait(SEXP sctx, SEXP pending)
     return R_ExternalPtrProtected(pending);
 }
 
+/* ---- batch-aware branch (cellula R/doNormAndReduce.R:74-76, :84-86); single-GPU form ---- */
+static cb200_ctx *one_ctx(cb200r_handle *h, const char *what)
+{
+    if (h->one == NULL)
+        Rf_error("cellulaB200: %s is available with options(cellula.b200.gpus = 1)", what);
+    return h->one;
+}
+
+/* codes: 0-based integer batch of every cell.  Returns list(ave = G x B matrix of the per-batch averages of
+ * counts / batch-centred size factors, sfmean = mean size factor per batch, n = cells per batch). */
+SEXP cb200r_block_averages(SEXP sctx, SEXP codes, SEXP n_blocks, SEXP n_genes)
+{
+    cb200r_handle *h = get_handle(sctx);
+    cb200_ctx *ctx = one_ctx(h, "the batch-aware path");
+    int B = Rf_asInteger(n_blocks), G = Rf_asInteger(n_genes);
+    SEXP ave = PROTECT(Rf_allocMatrix(REALSXP, G, B)), sfm = PROTECT(Rf_allocVector(REALSXP, B));
+    SEXP nn = PROTECT(Rf_allocVector(REALSXP, B));
+    int64_t *nb = (int64_t *)R_alloc((size_t)B, sizeof(int64_t));
+    if (cb200_block_averages(ctx, INTEGER(codes), B, REAL(ave), REAL(sfm), nb) != 0) {
+        UNPROTECT(3);
+        Rf_error("%s", last_error(h));
+    }
+    for (int b = 0; b < B; ++b)
+        REAL(nn)[b] = (double)nb[b];
+    SEXP out = named_list3(ave, "ave", sfm, "sfmean", nn, "n");
+    UNPROTECT(3);
+    return out;
+}
+
+/* size factors used as they are (multiBatchNorm's rescaled factors; no centring) */
+SEXP cb200r_size_factors_given(SEXP sctx, SEXP sf)
+{
+    cb200r_handle *h = get_handle(sctx);
+    CB_OK(h, cb200_size_factors_given(one_ctx(h, "the batch-aware path"), REAL(sf)));
+    return R_NilValue;
+}
+
+/* returns list(x = logcounts@x, mean = G x B, var = G x B): statistics within every batch */
+SEXP cb200r_lognorm_genestats_blocked(SEXP sctx, SEXP nnz, SEXP n_genes, SEXP n_blocks)
+{
+    cb200r_handle *h = get_handle(sctx);
+    cb200_ctx *ctx = one_ctx(h, "the batch-aware path");
+    int B = Rf_asInteger(n_blocks), G = Rf_asInteger(n_genes);
+    SEXP lx = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)Rf_asReal(nnz)));
+    SEXP mean = PROTECT(Rf_allocMatrix(REALSXP, G, B)), var = PROTECT(Rf_allocMatrix(REALSXP, G, B));
+    if (cb200_lognorm_genestats_blocked(ctx, REAL(lx), REAL(mean), REAL(var)) != 0) {
+        UNPROTECT(3);
+        Rf_error("%s", last_error(h));
+    }
+    SEXP out = named_list3(lx, "x", mean, "mean", var, "var");
+    UNPROTECT(3);
+    return out;
+}
+
 /* hvg_idx: 0-based integer rows in getTopHVGs order.  returns list(scores, rotation, varExplained, totalVar) */
 SEXP cb200r_pca(SEXP sctx, SEXP hvg_idx, SEXP ndims, SEXP n_cells)
 {
@@ -315,6 +369,9 @@ static const R_CallMethodDef call_methods[] = {
     {"cb200r_lognorm_genestats", (DL_FUNC)&cb200r_lognorm_genestats, 3},
     {"cb200r_lognorm_begin", (DL_FUNC)&cb200r_lognorm_begin, 3},
     {"cb200r_logcounts_wait", (DL_FUNC)&cb200r_logcounts_wait, 2},
+    {"cb200r_block_averages", (DL_FUNC)&cb200r_block_averages, 4},
+    {"cb200r_size_factors_given", (DL_FUNC)&cb200r_size_factors_given, 2},
+    {"cb200r_lognorm_genestats_blocked", (DL_FUNC)&cb200r_lognorm_genestats_blocked, 4},
     {"cb200r_pca", (DL_FUNC)&cb200r_pca, 4},
     {"cb200r_snn_graph", (DL_FUNC)&cb200r_snn_graph, 4},
     {"cb200r_knn", (DL_FUNC)&cb200r_knn, 3},

@@ -6,6 +6,7 @@
 #include <stddef.h>
 void *R_chk_calloc(size_t, size_t);
 void R_chk_free(void *);
+char *R_alloc(size_t, int);
 #define R_Calloc(n, t) ((t *)R_chk_calloc((size_t)(n), sizeof(t)))
 #define R_Free(p) (R_chk_free((void *)(p)), (p) = NULL)
 #endif

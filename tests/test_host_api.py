@@ -20,10 +20,7 @@ def test_donormandreduce_validation():
         cb.doNormAndReduce(tiny_sce(), batch="nope")
     with pytest.raises(ValueError, match="hvg_ntop cannot be higher than the number of features"):
         cb.doNormAndReduce(tiny_sce(), hvg_ntop=10)
-    sce = tiny_sce()
-    sce.colData["batch"] = ["a", "b"]
-    with pytest.raises(NotImplementedError, match="batch-aware path is not implemented"):
-        cb.doNormAndReduce(sce, batch="batch", hvg_ntop=2)
+    # (the batch-aware branch itself runs on the GPU: tests/test_gpu_batch.py)
 
 
 def test_makegraphsandclusters_validation():
