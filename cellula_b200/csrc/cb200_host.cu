@@ -16,6 +16,35 @@
 
 #include "../../include/cellula_b200.h"
 
+// static split of [0, n) over a few host threads (G-sized loops of the trend fit; every index is handled by
+// exactly one thread with the same arithmetic as the serial loop, so results do not depend on the thread count)
+template <typename Fn>
+static void host_parallel_for(int n, Fn fn)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw > 8 ? 8 : (hw < 1 ? 1 : hw));
+    if (nt > n)
+        nt = n;
+    if (n < 8 || nt <= 1) {
+        for (int i = 0; i < n; ++i)
+            fn(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int per = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const int a = t * per, b = std::min(n, a + per);
+        if (a >= b)
+            break;
+        th.emplace_back([=] {
+            for (int i = a; i < b; ++i)
+                fn(i);
+        });
+    }
+    for (auto &t : th)
+        t.join();
+}
+
 static double weighted_median(const std::vector<double> &x, const double *w, std::vector<int> &order)
 {
     const int n = (int)x.size();
@@ -84,7 +113,7 @@ extern "C" int cb200_host_weighted_lowess(int64_t n64, const double *xs, const d
     for (int i = 0; i < n; ++i)
         fitted_out[i] = ys[i];
     for (int it = 0; it < iterations; ++it) {
-        for (int q = 0; q < ns; ++q) {
+        host_parallel_for(ns, [&](int q) {
             const int s = seeds[q];
             const double d = dist[q];
             double tw = 0.0, sx = 0.0, sy = 0.0;
@@ -101,7 +130,7 @@ extern "C" int cb200_host_weighted_lowess(int64_t n64, const double *xs, const d
             }
             if (!(tw > 0.0)) {
                 sv[q] = ys[s];
-                continue;
+                return;
             }
             const double xm = sx / tw, ym = sy / tw;
             double sxx = 0.0, sxy = 0.0;
@@ -120,7 +149,7 @@ extern "C" int cb200_host_weighted_lowess(int64_t n64, const double *xs, const d
                 sv[q] = ym;
             else
                 sv[q] = ym + sxy / sxx * (xs[s] - xm);
-        }
+        });
         // linear interpolation between the seeds (xs[seeds] is strictly increasing except for ties)
         int q = 0;
         for (int i = 0; i < n; ++i) {
@@ -163,17 +192,25 @@ extern "C" int cb200_host_gauss_kde(int64_t n, const double *m, double bw, doubl
     const double step = (hi - lo) / (ng - 1);
     std::vector<double> acc((size_t)ng, 0.0);
     const double inv = 1.0 / bw;
+    // grid ranges of every data point (exp(-0.5 z^2) < 2e-16 beyond |z| = 8.5: those terms cannot change a
+    // double-precision sum), then one thread per slice of the grid, data points in ascending index order
+    std::vector<int> r0((size_t)n), r1((size_t)n);
     for (int64_t j = 0; j < n; ++j) {
-        const double mj = m[j];
-        // exp(-0.5 z^2) < 2e-16 beyond |z| = 8.5: those terms cannot change a double-precision sum
-        int i0 = (int)std::floor((mj - 8.5 * bw - lo) / step), i1 = (int)std::ceil((mj + 8.5 * bw - lo) / step);
-        i0 = i0 < 0 ? 0 : i0;
-        i1 = i1 > ng - 1 ? ng - 1 : i1;
-        for (int i = i0; i <= i1; ++i) {
-            const double z = ((lo + step * i) - mj) * inv;
-            acc[i] += std::exp(-0.5 * z * z);
-        }
+        int i0 = (int)std::floor((m[j] - 8.5 * bw - lo) / step), i1 = (int)std::ceil((m[j] + 8.5 * bw - lo) / step);
+        r0[(size_t)j] = i0 < 0 ? 0 : i0;
+        r1[(size_t)j] = i1 > ng - 1 ? ng - 1 : i1;
     }
+    host_parallel_for(ng, [&](int i) {
+        double a = 0.0;
+        const double gx = lo + step * i;
+        for (int64_t j = 0; j < n; ++j) {
+            if (i < r0[(size_t)j] || i > r1[(size_t)j])
+                continue;
+            const double z = (gx - m[j]) * inv;
+            a += std::exp(-0.5 * z * z);
+        }
+        acc[(size_t)i] = a;
+    });
     const double norm = 1.0 / ((double)n * bw * 2.5066282746310002);  // sqrt(2 pi)
     for (int i = 0; i < ng; ++i)
         dens_out[i] = acc[i] * norm;
@@ -224,26 +261,30 @@ extern "C" int cb200_host_nls_grid(int64_t n64, const double *v, const double *m
     const int n = (int)n64;
     if (n < 1 || v == nullptr || m == nullptr || bgrid == nullptr || ngrid == nullptr || nb < 1 || nn < 1 || nb > 64)
         return 1;
-    std::vector<double> mp((size_t)n);
-    double best = 0.0;
-    int bi = -1, bn = -1;
-    for (int a = 0; a < nn; ++a) {
-        for (int i = 0; i < n; ++i)
-            mp[i] = std::pow(m[i], ngrid[a]);
+    // one thread per exponent of the grid; the winner is picked afterwards in grid order (same tie rule)
+    std::vector<double> rss_all((size_t)nn * 64, 0.0);
+    host_parallel_for(nn, [&](int a) {
         double rss[64];
         for (int b = 0; b < nb; ++b)
             rss[b] = 0.0;
         for (int i = 0; i < n; ++i) {
-            const double gm = m[i], vi = v[i], p = mp[i];
+            const double gm = m[i], vi = v[i], p = std::pow(m[i], ngrid[a]);
             for (int b = 0; b < nb; ++b) {
                 const double r = vi - grad * bgrid[b] * gm / (p + bgrid[b]);
                 rss[b] += r * r;
             }
         }
+        for (int b = 0; b < nb; ++b)
+            rss_all[(size_t)a * 64 + b] = rss[b];
+    });
+    double best = 0.0;
+    int bi = -1, bn = -1;
+    for (int a = 0; a < nn; ++a) {
         for (int b = 0; b < nb; ++b) {
             // NaN never wins; ties keep the earlier grid point (argmin over the flattened [n][b] array)
-            if (rss[b] == rss[b] && (bi < 0 || rss[b] < best)) {
-                best = rss[b];
+            const double r = rss_all[(size_t)a * 64 + b];
+            if (r == r && (bi < 0 || r < best)) {
+                best = r;
                 bi = b;
                 bn = a;
             }

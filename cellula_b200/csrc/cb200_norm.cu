@@ -283,37 +283,39 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
         auto acquire = [&]() {            // all lanes wait (the stage's previous occupant has been consumed)
             mbar_wait(empty + stage, phase ^ 1u, flag);
         };
-        auto close = [&]() {              // publishes the packed stage: one expect_tx, two bulk copies per segment
+        auto close = [&]() {   // publishes the packed stage: lane q issues the bulk copies of segment q, one expect_tx
             if (!open)
                 return;
+            __syncwarp();      // the segment descriptors written by lane 0 are visible to the other lanes
+            GsItem &it = items[stage];
+            uint32_t mine = 0;
+            int64_t a8 = 0, a4 = 0;
+            uint32_t bytes8 = 0, bytes4 = 0;
+            GsSub sb;
+            if (lane < nsub) {
+                sb = it.sub[lane];
+                a8 = sb.beg & ~1LL;                                               // 16-byte aligned sources
+                a4 = sb.beg & ~3LL;
+                bytes8 = (uint32_t)(((sb.beg + sb.n - a8 + 1) & ~1LL) * 8);
+                bytes4 = (uint32_t)(((sb.beg + sb.n - a4 + 3) & ~3LL) * 4);
+                mine = bytes8 + bytes4 + (MODE == 1 ? GS_TABLE * 8 : 0);
+            }
+            const uint32_t total = __reduce_add_sync(0xffffffffu, mine);
             if (lane == 0) {
-                GsItem &it = items[stage];
                 it.kind = GS_ITEM_DATA;
                 it.nsub = nsub;
                 it.slab_base = cur_slab * slab_genes;
                 it.slab_genes = cur_genes;
-                uint32_t total = 0;
-                for (int q = 0; q < nsub; ++q) {
-                    const GsSub &sb = it.sub[q];
-                    const int64_t a8 = sb.beg & ~1LL, a4 = sb.beg & ~3LL;        // 16-byte aligned sources
-                    total += (uint32_t)(((sb.beg + sb.n - a8 + 1) & ~1LL) * 8) + (uint32_t)(((sb.beg + sb.n - a4 + 3) & ~3LL) * 4);
-                    if (MODE == 1)
-                        total += GS_TABLE * 8;
-                }
-                mbar_expect_tx(full + stage, total);
-                for (int q = 0; q < nsub; ++q) {
-                    const GsSub &sb = it.sub[q];
-                    const int64_t a8 = sb.beg & ~1LL, a4 = sb.beg & ~3LL;
-                    const uint32_t bytes8 = (uint32_t)(((sb.beg + sb.n - a8 + 1) & ~1LL) * 8);
-                    const uint32_t bytes4 = (uint32_t)(((sb.beg + sb.n - a4 + 3) & ~3LL) * 4);
-                    bulk_g2s(stage8 + ((size_t)stage * GS_CAP8 + (size_t)(sb.pos8 - (int)(sb.beg - a8))) * 8, v8 + a8, bytes8,
-                             full + stage);
-                    bulk_g2s(stage4 + ((size_t)stage * GS_CAP4 + (size_t)(sb.pos4 - (int)(sb.beg - a4))) * 4, rowidx + a4, bytes4,
-                             full + stage);
-                    if (MODE == 1)   // the cell's logcount table rides along (256 bytes)
-                        bulk_g2s(stageT + ((size_t)stage * GS_MAXSUB + q) * GS_TABLE, tab_y + (int64_t)sb.cell * GS_TABLE,
-                                 GS_TABLE * 8, full + stage);
-                }
+                mbar_expect_tx(full + stage, total);    // (a copy may land before this: the phase cannot complete without it)
+            }
+            if (lane < nsub) {
+                bulk_g2s(stage8 + ((size_t)stage * GS_CAP8 + (size_t)(sb.pos8 - (int)(sb.beg - a8))) * 8, v8 + a8, bytes8,
+                         full + stage);
+                bulk_g2s(stage4 + ((size_t)stage * GS_CAP4 + (size_t)(sb.pos4 - (int)(sb.beg - a4))) * 4, rowidx + a4, bytes4,
+                         full + stage);
+                if (MODE == 1)   // the cell's logcount table rides along (256 bytes)
+                    bulk_g2s(stageT + ((size_t)stage * GS_MAXSUB + lane) * GS_TABLE, tab_y + (int64_t)sb.cell * GS_TABLE,
+                             GS_TABLE * 8, full + stage);
             }
             __syncwarp();
             next_stage();

@@ -319,4 +319,7 @@ def rescale_size_factors(ave, sf, block, min_mean=1.0):
 def get_top_hvgs(stats, n):
     bio = np.asarray(stats["bio"] if isinstance(stats, dict) else stats)
     keep = np.flatnonzero(np.isfinite(bio) & (bio > 0))
+    if keep.size > 4 * n:   # only the top of the list is needed: cut at the n-th value (ties kept), then the stable sort
+        cut = np.partition(bio[keep], keep.size - n)[keep.size - n]
+        keep = keep[bio[keep] >= cut]
     return keep[np.argsort(-bio[keep], kind="stable")][:n].astype(np.int32)
