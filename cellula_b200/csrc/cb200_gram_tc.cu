@@ -258,6 +258,171 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
         tmem_dealloc(tmem_base, GT_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cluster version: 8 CTAs (2 row tiles x 4 column tiles = a 256 x 256 block of the cross-product) share their
+// operand loads.  k_gram_tc above is bound by L2 -> shared-memory traffic (72 KB per CTA and chunk for 9.4 M MACs);
+// here CTA (r, c) fetches only a quarter of its row's A tile and half of its column's B tile (24 KB) and the TMA
+// engine MULTICASTS each piece to the CTAs of the row / column that need it, so every byte leaves L2 once per
+// cluster instead of once per CTA (3x less).  A stage may be overwritten when every CTA it is multicast INTO has
+// finished reading it: the MMA-completion arrival is multicast to the `empty` barriers of the row- and column-mates.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int GT_CL_R = 2, GT_CL_C = 4, GT_CL = GT_CL_R * GT_CL_C;
+constexpr int GT_SLICE = 4096;   // 32 operand rows of one plane
+
+__global__ void __cluster_dims__(GT_CL, 1, 1) __launch_bounds__(GT_THREADS, 1)
+k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, int H,
+             unsigned long long *__restrict__ gram_lo, unsigned long long *__restrict__ gram_hi, int *__restrict__ err_flag)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)GT_STAGES * GT_STAGE_BYTES);
+    uint64_t *full = bars;                 // [GT_STAGES]
+    uint64_t *empty = bars + GT_STAGES;    // [GT_STAGES]
+    uint64_t *tfull = bars + 2 * GT_STAGES;
+    uint64_t *tempty = tfull + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 1);
+
+    // super-tile (SI, SJ), SI <= SJ, of 256 x 256; CTA (r, c) of the cluster owns rows I = 2 SI + r (128), columns
+    // J = 4 SJ + c (64)
+    const uint32_t rank = cluster_ctarank();
+    const int r = (int)(rank / GT_CL_C), c = (int)(rank % GT_CL_C);
+    int SI = 0, rem = (int)(blockIdx.x / GT_CL);
+    while (rem >= n_st - SI) {
+        rem -= n_st - SI;
+        ++SI;
+    }
+    const int SJ = SI + rem;
+    const int I = GT_CL_R * SI + r, J = GT_CL_C * SJ + c;
+    const int gtB = J / 2, halfB = J & 1;
+    const uint16_t row_mask = (uint16_t)(((1u << GT_CL_C) - 1u) << (r * GT_CL_C));      // CTAs that share my A tile
+    const uint16_t col_mask = (uint16_t)((1u << c) | (1u << (GT_CL_C + c)));            // CTAs that share my B tile
+    const int64_t per = (n_chunks + gridDim.y - 1) / gridDim.y;
+    const int64_t kc0 = (int64_t)blockIdx.y * per;
+    const int64_t kc1 = kc0 + per < n_chunks ? kc0 + per : n_chunks;
+    const int64_t nk = kc1 > kc0 ? kc1 - kc0 : 0;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < GT_STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, GT_CL_C + GT_CL_R - 1);   // row-mates and column-mates (myself once)
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0)
+        tmem_alloc(tmem_slot, GT_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();            // every CTA's barriers exist before anything is multicast into it
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_flush = (nk + GT_FLUSH_CHUNKS - 1) / GT_FLUSH_CHUNKS;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int64_t t = 0; t < nk; ++t) {
+                const int s = (int)(t % GT_STAGES);
+                const uint32_t ph = (uint32_t)((t / GT_STAGES) & 1);
+                mbar_wait(empty + s, ph ^ 1u, err_flag);       // everyone I multicast into has released the stage
+                mbar_expect_tx(full + s, GT_STAGE_BYTES);      // 4 x 12 KB of A + 2 x 12 KB of B will land here
+                unsigned char *st = smem + (size_t)s * GT_STAGE_BYTES;
+                const unsigned char *a = img + ((size_t)I * n_chunks + (kc0 + t)) * GT_TILE_BYTES + (size_t)c * GT_SLICE;
+                const unsigned char *b = img + ((size_t)gtB * n_chunks + (kc0 + t)) * GT_TILE_BYTES + halfB * GT_B_BYTES +
+                                         (size_t)r * GT_SLICE;
+#pragma unroll
+                for (int p = 0; p < GT_PLANES; ++p) {
+                    bulk_g2s_multicast(st + p * GT_PLANE_BYTES + c * GT_SLICE, a + (size_t)p * GT_PLANE_BYTES, GT_SLICE, full + s,
+                                       row_mask);
+                    bulk_g2s_multicast(st + GT_TILE_BYTES + p * GT_B_BYTES + r * GT_SLICE, b + (size_t)p * GT_PLANE_BYTES, GT_SLICE,
+                                       full + s, col_mask);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int64_t f = 0; f < n_flush; ++f) {
+                mbar_wait(tempty, (uint32_t)((f & 1) ^ 1), err_flag);
+                tc_fence_after();
+                uint32_t accf[GT_ORDERS];
+#pragma unroll
+                for (int o = 0; o < GT_ORDERS; ++o)
+                    accf[o] = 0;
+                const int64_t t0 = f * GT_FLUSH_CHUNKS;
+                const int64_t t1 = t0 + GT_FLUSH_CHUNKS < nk ? t0 + GT_FLUSH_CHUNKS : nk;
+                for (int64_t t = t0; t < t1; ++t) {
+                    const int s = (int)(t % GT_STAGES);
+                    const uint32_t ph = (uint32_t)((t / GT_STAGES) & 1);
+                    mbar_wait(full + s, ph, err_flag);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * GT_STAGE_BYTES);
+                    const uint32_t sb = sa + GT_TILE_BYTES;
+#pragma unroll
+                    for (int p = 0; p < GT_PLANES; ++p) {
+#pragma unroll
+                        for (int q = 0; q < GT_PLANES; ++q) {
+#pragma unroll
+                            for (int kk = 0; kk < GT_KC / 32; ++kk) {
+                                umma_i8(tmem_base + (uint32_t)((p + q) * GT_N), make_desc(sa + p * GT_PLANE_BYTES + kk * 32),
+                                        make_desc(sb + q * GT_B_BYTES + kk * 32), GT_IDESC, accf[p + q]);
+                                accf[p + q] = 1;
+                            }
+                        }
+                    }
+                    // the stage may be refilled by its writers (row- and column-mates, me included) once these MMAs have read it
+                    umma_commit_multicast(empty + s, (uint16_t)(row_mask | col_mask));
+                }
+                umma_commit(tfull);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int grow = I * GT_M + row;
+        for (int64_t f = 0; f < n_flush; ++f) {
+            mbar_wait(tfull, (uint32_t)(f & 1), err_flag);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < GT_N / 32; ++half) {
+                unsigned long long lo[32], hi[32];
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc)
+                    lo[cc] = hi[cc] = 0ull;
+#pragma unroll
+                for (int o = 0; o < GT_ORDERS; ++o) {
+                    uint32_t rr[32];
+                    tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(o * GT_N + half * 32), rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int cc = 0; cc < 32; ++cc) {
+                        if (o < 2)
+                            lo[cc] += (unsigned long long)rr[cc] << (8 * o);
+                        else
+                            hi[cc] += (unsigned long long)rr[cc] << (8 * (o - 2));
+                    }
+                }
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc) {
+                    const int gcol = J * GT_N + half * 32 + cc;
+                    if (grow < H && gcol < H && gcol >= grow && (lo[cc] | hi[cc]) != 0ull) {
+                        atomicAdd(gram_lo + (int64_t)grow * H + gcol, lo[cc]);
+                        atomicAdd(gram_hi + (int64_t)grow * H + gcol, hi[cc]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();            // nobody leaves while a cluster-mate may still signal its barriers
+    if (warp == 0)
+        tmem_dealloc(tmem_base, GT_TMEM_COLS);
+}
+
 // Adds the local X^T X (upper triangle) of the HVG sub-matrix held by the context into ctx->gram,
 // which the caller has zeroed.  Returns 1 in *used when the tensor-core path applied (all values
 // below 32), 0 when the caller has to use the fp64 kernels instead.
@@ -278,8 +443,12 @@ int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used)
     if (!(mx < 31.99))
         return 0;  // outside the fixed-point range: fp64 path
     const int n_gt = (H + GT_M - 1) / GT_M;
+    const int n_st = (n_gt + GT_CL_R - 1) / GT_CL_R;          // 256-row super tiles (cluster kernel)
     const int64_t n_chunks = (ctx->N + GT_KC - 1) / GT_KC;
-    CB_CUDA(ctx, ctx->gram_img.ensure((size_t)n_gt * n_chunks * GT_TILE_BYTES));
+    CB_CUDA(ctx, ctx->gram_img.ensure((size_t)n_st * GT_CL_R * n_chunks * GT_TILE_BYTES));
+    if (n_st * GT_CL_R > n_gt)   // the padding gene tile of the last super tile: zeros
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->gram_img.p + (size_t)n_gt * n_chunks * GT_TILE_BYTES, 0,
+                                     (size_t)(n_st * GT_CL_R - n_gt) * n_chunks * GT_TILE_BYTES, ctx->stream));
     CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_img, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       GT_QUAD * GT_TILE_BYTES));
     dim3 igrid((unsigned)n_chunks, (unsigned)((n_gt + GT_QUAD - 1) / GT_QUAD));
@@ -303,10 +472,26 @@ int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used)
     CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     CB_TRACE("gram_tc: img launched");
-    dim3 grid((unsigned)n_pairs, (unsigned)ksplit);
     unsigned long long *glo = reinterpret_cast<unsigned long long *>(ctx->gram.p);
-    k_gram_tc<<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, glo, glo + (size_t)H * H,
-                                                       ctx->flag.p + 3);
+    const char *genv = getenv("CB200_GRAM_CLUSTER");
+    const bool use_cluster = !(genv != nullptr && strcmp(genv, "0") == 0) && n_chunks >= 64;
+    if (use_cluster) {
+        // 8-CTA clusters with multicast operand loads; enough k-slices to fill the 18 cluster slots a few times
+        const int n_sp = n_st * (n_st + 1) / 2;
+        int64_t ks = (3LL * (ctx->num_sms / GT_CL) + n_sp - 1) / n_sp;
+        if (ks > max_split)
+            ks = max_split;
+        if (ks < 1)
+            ks = 1;
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 cgrid((unsigned)(n_sp * GT_CL), (unsigned)ks);
+        k_gram_tc_cl<<<cgrid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_st, H, glo, glo + (size_t)H * H,
+                                                              ctx->flag.p + 3);
+    } else {
+        dim3 grid((unsigned)n_pairs, (unsigned)ksplit);
+        k_gram_tc<<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, glo, glo + (size_t)H * H,
+                                                           ctx->flag.p + 3);
+    }
     CB_LAUNCH(ctx);
     int h_flag = 0;
     CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p + 3, sizeof(int)));

@@ -256,7 +256,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
     if (tid == 0) {
         for (int s = 0; s < GS_STAGES; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, GS_CONSUMERS / 32);   // one arrival per consumer warp
+            mbar_init(empty + s, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -409,34 +409,17 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
         control(GS_ITEM_END, 0);
     } else {
         // ------------------------------------------------------------------ consumers
-        // Every consumer warp OWNS a contiguous range of the slab's genes.  The rows of a column are sorted, so the
-        // warp's entries of a segment are a contiguous sub-range, found with two warp-wide probes of the staged row
-        // indices.  No two warps ever touch the same table entry: no atomics and no barrier between segments; the
-        // warps run through the ring independently (a stage is released when all of them have arrived).
-        constexpr int NW = GS_CONSUMERS / 32;
-        const int cw = warp - 1;
+        const int ct = tid - 32;
         int stage = 0;
         uint32_t phase = 0;
         int bad = 0;
         // this warp's region of the overflow list (MODE 1): no atomics, the fill level is a register
-        const int64_t ovf_base = ((int64_t)blockIdx.x * NW + cw) * ovf_region;
+        const int64_t ovf_base = ((int64_t)blockIdx.x * (GS_CONSUMERS / 32) + (warp - 1)) * ovf_region;
         int64_t ovf_n = 0;
-        // lower bound of `key` in the sorted array a[0 .. n), n <= 1024: 32 probes, then the 32 elements of one block
-        auto lower_bound_warp = [&](const int32_t *a, int n, int bs, int key, int probe) -> int {
-            const int c = __popc(__ballot_sync(0xffffffffu, probe < key));     // blocks entirely below the key
-            if (c >= 32 || c * bs >= n)
-                return c * bs < n ? c * bs : n;
-            const int p = c * bs + lane;
-            const int end = (c + 1) * bs < n ? (c + 1) * bs : n;
-            const bool below = lane < bs && p < end && a[p] < key;
-            return c * bs + __popc(__ballot_sync(0xffffffffu, below));
-        };
         for (;;) {
             mbar_wait(full + stage, phase, flag);
             const GsItem &it = items[stage];
             const int kind = it.kind, nsub = it.nsub, slab_base = it.slab_base, sgenes = it.slab_genes;
-            const int gw = (sgenes + NW - 1) / NW;
-            const int g_lo = cw * gw, g_hi = (cw + 1) * gw < sgenes ? (cw + 1) * gw : sgenes;   // my genes (slab-local)
             if (kind == GS_ITEM_DATA) {
                 const double *base8 = reinterpret_cast<const double *>(stage8) + (size_t)stage * GS_CAP8;
                 const int32_t *base4 = reinterpret_cast<const int32_t *>(stage4) + (size_t)stage * GS_CAP4;
@@ -445,27 +428,18 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                     const double *s8 = base8 + sb.pos8;
                     const int32_t *s4 = base4 + sb.pos4;
                     const double *ty = stageT + ((size_t)stage * GS_MAXSUB + q) * GS_TABLE;
-                    const int bs = (sb.n + 31) >> 5;
-                    const int pi = (lane + 1) * bs - 1;
-                    const int probe = lane * bs < sb.n ? s4[pi < sb.n ? pi : sb.n - 1] : 0x7fffffff;
-                    const int lo = cw == 0 ? 0 : lower_bound_warp(s4, sb.n, bs, slab_base + g_lo, probe);
-                    const int hi = cw == NW - 1 ? sb.n : lower_bound_warp(s4, sb.n, bs, slab_base + g_hi, probe);
-                    for (int t0 = lo; t0 < hi; t0 += 32) {     // uniform trip count per warp (ballot below)
+                    for (int t0 = ct - lane; t0 < sb.n; t0 += GS_CONSUMERS) {   // uniform trip count per warp (ballot below)
                         const int t = t0 + lane;
-                        const bool in = t < hi;
+                        const bool in = t < sb.n;
                         double y = in ? s8[t] : 1.0;
-                        const int g = in ? s4[t] - slab_base : g_lo;
-                        if (in && (g < g_lo || g >= g_hi)) {    // outside [0, n_genes) or rows not sorted within the column
-                            bad |= 2;
-                            continue;
-                        }
+                        const int g = in ? s4[t] - slab_base : 0;
                         ulonglong2 add;
                         if (MODE == 1) {
-                            // counts are small integers: the logcount comes from the cell's table (k_gs_tables); anything
-                            // else goes to this warp's region of the overflow list
+                            // counts are small integers: the logcount and its two fixed-point images come from the
+                            // cell's table (k_gs_tables); anything else goes to this warp's region of the overflow list
                             const int xi = __double2int_rz(y);
                             const bool ovf = in && (xi < 1 || xi > GS_TABLE || (double)xi != y);
-                            const unsigned om = __ballot_sync(__activemask(), ovf);
+                            const unsigned om = __ballot_sync(0xffffffffu, ovf);
                             if (om != 0u) {
                                 if (ovf) {
                                     const int64_t o = ovf_n + __popc(om & ((1u << lane) - 1u));
@@ -482,6 +456,12 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                                 continue;
                             y = ty[xi - 1];
                             st_stream(logx + sb.beg + t, y);
+                            if (!(y < y_limit) || g < 0 || g >= sgenes) {
+                                bad |= 2;
+                                continue;
+                            }
+                            add.x = (unsigned long long)__double2ll_rn(y * scale1);
+                            add.y = (unsigned long long)__double2ll_rn(y * y * scale2);
                         } else {
                             if (!in)
                                 continue;
@@ -491,22 +471,22 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                             }
                             if (MODE == 3)
                                 y = y * sb.rs;
+                            if (!(y < y_limit) || g < 0 || g >= sgenes) {   // out of the fixed-point range / malformed row index
+                                bad |= 2;
+                                continue;
+                            }
+                            add.x = (unsigned long long)__double2ll_rn(y * scale1);
+                            add.y = MODE == 3 ? 0ull : (unsigned long long)__double2ll_rn(y * y * scale2);
                         }
-                        if (!(y < y_limit)) {   // out of the fixed-point range
-                            bad |= 2;
-                            continue;
-                        }
-                        add.x = (unsigned long long)__double2ll_rn(y * scale1);
-                        add.y = MODE == 3 ? 0ull : (unsigned long long)__double2ll_rn(y * y * scale2);
                         ulonglong2 a = tab[g];
                         a.x += add.x;
                         a.y += add.y;
                         tab[g] = a;
                     }
-                    __syncwarp();   // the next segment is another cell and may hit the same genes (same warp: ordered)
+                    gs_consumer_sync();     // the next segment belongs to another cell and may hit the same genes
                 }
             } else if (kind == GS_ITEM_FLUSH) {
-                for (int g = g_lo + lane; g < g_hi; g += 32) {
+                for (int g = ct; g < sgenes; g += GS_CONSUMERS) {
                     const ulonglong2 a = tab[g];
                     if (a.x | a.y) {
                         atomicAdd(acc1 + slab_base + g, a.x);
@@ -514,10 +494,10 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
                         tab[g] = make_ulonglong2(0ull, 0ull);
                     }
                 }
+                gs_consumer_sync();
             }
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(empty + stage);     // one arrival per consumer warp
+            if (ct == 0)
+                mbar_arrive(empty + stage);     // (the named barrier above ordered every reader of the stage before this)
             if (kind == GS_ITEM_END)
                 break;
             if (++stage == GS_STAGES) {
@@ -528,7 +508,7 @@ k_genestats_slab(const int64_t *__restrict__ colptr, const int32_t *__restrict__
         if (bad)
             atomicOr(flag, bad);
         if (MODE == 1 && lane == 0)
-            ovf_count[blockIdx.x * NW + cw] = (int32_t)(ovf_n < ovf_region ? ovf_n : ovf_region);
+            ovf_count[blockIdx.x * (GS_CONSUMERS / 32) + (warp - 1)] = (int32_t)(ovf_n < ovf_region ? ovf_n : ovf_region);
     }
 }
 

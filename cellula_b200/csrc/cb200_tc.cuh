@@ -72,6 +72,37 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// ---- thread-block clusters: multicast bulk copies and multicast MMA-completion arrivals ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// global -> the SAME shared-memory offset of every CTA of the cluster named in cta_mask; each destination CTA's
+// mbarrier (same offset) receives the complete_tx of the bytes that landed in it
+__device__ __forceinline__ void bulk_g2s_multicast(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                                   uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
