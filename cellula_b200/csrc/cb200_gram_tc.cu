@@ -179,10 +179,6 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
                 // the flush warps must have drained the accumulators of the previous period
                 mbar_wait(tempty, (uint32_t)((f & 1) ^ 1), err_flag);
                 tc_fence_after();
-                uint32_t accf[GT_ORDERS];
-#pragma unroll
-                for (int o = 0; o < GT_ORDERS; ++o)
-                    accf[o] = 0;
                 const int64_t t0 = f * GT_FLUSH_CHUNKS;
                 const int64_t t1 = t0 + GT_FLUSH_CHUNKS < nk ? t0 + GT_FLUSH_CHUNKS : nk;
                 for (int64_t t = t0; t < t1; ++t) {
@@ -192,16 +188,23 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)s * GT_STAGE_BYTES);
                     const uint32_t sb = sa + GT_TILE_BYTES;
+                    // descriptors: only the 14-bit start-address field (bytes >> 4) differs between the 36 MMAs of a
+                    // chunk, so it is ONE 64-bit add per operand (the issuing thread was the limiter: two full
+                    // descriptor constructions per MMA cost more than the 32 cycles the MMA keeps the tensor pipe busy)
+                    const uint64_t da0 = make_desc(sa), db0 = make_desc(sb);
+                    const uint32_t not_first = t != t0 ? 1u : 0u;   // first chunk of a flush period overwrites
 #pragma unroll
                     for (int p = 0; p < GT_PLANES; ++p) {
 #pragma unroll
                         for (int q = 0; q < GT_PLANES; ++q) {
 #pragma unroll
                             for (int kk = 0; kk < GT_KC / 32; ++kk) {
+                                // (p, q, kk) is the first product of its order o = p + q iff kk == 0 and p == max(0, o - 2)
+                                const bool first_of_order = kk == 0 && p == ((p + q) > 2 ? (p + q) - 2 : 0);
                                 umma_i8(tmem_base + (uint32_t)((p + q) * GT_N),
-                                        make_desc(sa + p * GT_PLANE_BYTES + kk * 32),
-                                        make_desc(sb + q * GT_B_BYTES + kk * 32), GT_IDESC, accf[p + q]);
-                                accf[p + q] = 1;
+                                        da0 + (uint64_t)((p * GT_PLANE_BYTES + kk * 32) >> 4),
+                                        db0 + (uint64_t)((q * GT_B_BYTES + kk * 32) >> 4), GT_IDESC,
+                                        first_of_order ? not_first : 1u);
                             }
                         }
                     }
@@ -344,10 +347,6 @@ k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, 
             for (int64_t f = 0; f < n_flush; ++f) {
                 mbar_wait(tempty, (uint32_t)((f & 1) ^ 1), err_flag);
                 tc_fence_after();
-                uint32_t accf[GT_ORDERS];
-#pragma unroll
-                for (int o = 0; o < GT_ORDERS; ++o)
-                    accf[o] = 0;
                 const int64_t t0 = f * GT_FLUSH_CHUNKS;
                 const int64_t t1 = t0 + GT_FLUSH_CHUNKS < nk ? t0 + GT_FLUSH_CHUNKS : nk;
                 for (int64_t t = t0; t < t1; ++t) {
@@ -357,15 +356,23 @@ k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, 
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)s * GT_STAGE_BYTES);
                     const uint32_t sb = sa + GT_TILE_BYTES;
+                    // descriptors: only the 14-bit start-address field (bytes >> 4) differs between the 36 MMAs of a
+                    // chunk, so it is ONE 64-bit add per operand (the issuing thread was the limiter: two full
+                    // descriptor constructions per MMA cost more than the 32 cycles the MMA keeps the tensor pipe busy)
+                    const uint64_t da0 = make_desc(sa), db0 = make_desc(sb);
+                    const uint32_t not_first = t != t0 ? 1u : 0u;   // first chunk of a flush period overwrites
 #pragma unroll
                     for (int p = 0; p < GT_PLANES; ++p) {
 #pragma unroll
                         for (int q = 0; q < GT_PLANES; ++q) {
 #pragma unroll
                             for (int kk = 0; kk < GT_KC / 32; ++kk) {
-                                umma_i8(tmem_base + (uint32_t)((p + q) * GT_N), make_desc(sa + p * GT_PLANE_BYTES + kk * 32),
-                                        make_desc(sb + q * GT_B_BYTES + kk * 32), GT_IDESC, accf[p + q]);
-                                accf[p + q] = 1;
+                                // (p, q, kk) is the first product of its order o = p + q iff kk == 0 and p == max(0, o - 2)
+                                const bool first_of_order = kk == 0 && p == ((p + q) > 2 ? (p + q) - 2 : 0);
+                                umma_i8(tmem_base + (uint32_t)((p + q) * GT_N),
+                                        da0 + (uint64_t)((p * GT_PLANE_BYTES + kk * 32) >> 4),
+                                        db0 + (uint64_t)((q * GT_B_BYTES + kk * 32) >> 4), GT_IDESC,
+                                        first_of_order ? not_first : 1u);
                             }
                         }
                     }
