@@ -64,7 +64,7 @@ __global__ void k_gram_maxval(const double *__restrict__ v, int64_t n, unsigned 
 // Digit planes of GT_QUAD gene tiles for one chunk of 128 cells, built in shared memory and written
 // out with coalesced 16-byte stores.  bptr: block boundaries (blocks of 64 slots) of the per-cell
 // entries, as produced by k_hvg_blockptr.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_gram_img(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, const double *__restrict__ hval,
            const uint16_t *__restrict__ bptr, int64_t n_cells, int nb, int n_gt, int64_t n_chunks,
            unsigned char *__restrict__ img)
@@ -82,7 +82,7 @@ k_gram_img(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, 
     if (blk1 > nb)
         blk1 = nb;
     const double scale = (double)(1 << GT_SCALE_BITS);
-    for (int cc = w; cc < GT_KC; cc += 8) {
+    for (int cc = w; cc < GT_KC; cc += (int)(blockDim.x >> 5)) {   // warp per cell: 32 warps keep the gathers in flight
         const int64_t c = kc * GT_KC + cc;
         if (c >= n_cells)
             break;
@@ -459,7 +459,7 @@ int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used)
     CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_img, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       GT_QUAD * GT_TILE_BYTES));
     dim3 igrid((unsigned)n_chunks, (unsigned)((n_gt + GT_QUAD - 1) / GT_QUAD));
-    k_gram_img<<<igrid, 256, GT_QUAD * GT_TILE_BYTES, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p,
+    k_gram_img<<<igrid, 1024, GT_QUAD * GT_TILE_BYTES, ctx->stream>>>(ctx->hptr.p, ctx->hslot.p, ctx->hval.p,
                                                                       ctx->hbptr.p, ctx->N, nb, n_gt, n_chunks,
                                                                       ctx->gram_img.p);
     CB_LAUNCH(ctx);

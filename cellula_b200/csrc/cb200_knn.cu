@@ -408,6 +408,133 @@ k_knn_exact_rank(int k, const int32_t *__restrict__ fb_list, const int *__restri
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// General path for shapes the tile engines do not take (k > 112 -- rebuildModularity's default k = round(sqrt(N)),
+// uwot's n_neighbors = floor(sqrt(N)) -- or more than 64 dimensions): exact, slow, any k <= KNN_BIG_MAXK.
+// One block per query: the distances (reference arithmetic) to a strided sample give a radius that holds a few more
+// than k references; all references within it are collected and ranked by (distance, index).  The radius is
+// widened / narrowed until the count is in [k, KNN_BIG_CAP], so the result does not depend on the sample.
+// ---------------------------------------------------------------------------------------
+#define KNN_BIG_CAP 4096
+#define KNN_BIG_MAXK 2048
+__global__ void __launch_bounds__(256)
+k_knn_bigk(const double *__restrict__ E, int64_t lde, int d, int64_t n, int64_t q_begin, int64_t nq, int k,
+           int32_t *__restrict__ knn, int *__restrict__ err_flag)
+{
+    extern __shared__ __align__(16) unsigned char bk_smem[];
+    double *sd = reinterpret_cast<double *>(bk_smem);                               // [KNN_BIG_CAP] sorted sample distances
+    double *hd = sd + KNN_BIG_CAP;                                                   // [KNN_BIG_CAP] hits: distance
+    int32_t *hx = reinterpret_cast<int32_t *>(hd + KNN_BIG_CAP);                     // [KNN_BIG_CAP] hits: index
+    __shared__ int s_cnt, s_state;     // s_state: 0 = retry with s_tau, 1 = done, 2 = failed
+    __shared__ double s_tau;
+    const int tid = threadIdx.x;
+    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        const int64_t grow = q_begin + q;
+        const double *qa = E + grow * lde;
+        // sample: S points at equal strides (all of them when n - 1 <= KNN_BIG_CAP)
+        const int S = (int)(n - 1 < KNN_BIG_CAP ? n - 1 : KNN_BIG_CAP);
+        for (int s = tid; s < KNN_BIG_CAP; s += blockDim.x) {
+            double v = 1.0 / 0.0;
+            if (s < S) {
+                int64_t r = S == n - 1 ? s : (int64_t)(((__int128)s * (n - 1)) / S);
+                if (r >= grow)
+                    ++r;       // skip the query itself
+                v = exact_dist(qa, E + r * lde, d);
+            }
+            sd[s] = v;
+        }
+        __syncthreads();
+        // bitonic sort of the KNN_BIG_CAP sample distances (ascending)
+        for (int size = 2; size <= KNN_BIG_CAP; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = tid; i < KNN_BIG_CAP / 2; i += blockDim.x) {
+                    const int lo = 2 * i - (i & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const double a = sd[lo], b = sd[hi];
+                    if ((a > b) == up) {
+                        sd[lo] = b;
+                        sd[hi] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // thread 0 steers the radius: sample rank m, bracketed by ranks known to give too few / too many hits
+        int m_lo = -1, m_hi = S, m = 0;
+        if (tid == 0) {
+            m = S == n - 1 ? k - 1 : (int)(((double)k * S) / (double)(n - 1) * 1.3) + 8;
+            if (m > S - 1)
+                m = S - 1;
+            s_tau = sd[m];
+            s_state = 0;
+        }
+        __syncthreads();
+        for (int attempt = 0; attempt < 40; ++attempt) {
+            const double tau = s_tau;
+            if (tid == 0)
+                s_cnt = 0;
+            __syncthreads();
+            for (int64_t r = tid; r < n; r += blockDim.x) {
+                if (r == grow)
+                    continue;
+                const double dist = exact_dist(qa, E + r * lde, d);
+                if (dist <= tau) {
+                    const int pos = atomicAdd(&s_cnt, 1);
+                    if (pos < KNN_BIG_CAP) {
+                        hd[pos] = dist;
+                        hx[pos] = (int32_t)r;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const int c = s_cnt;
+                if (c >= k && c <= KNN_BIG_CAP) {
+                    s_state = 1;
+                } else {
+                    int m2;
+                    if (c < k) {
+                        m_lo = m;
+                        m2 = m_hi == S ? (2 * m + 1 < S - 1 ? 2 * m + 1 : S - 1) : (m + m_hi + 1) / 2;
+                    } else {
+                        m_hi = m;
+                        m2 = (m_lo + m) / 2;
+                    }
+                    if (m2 == m || m2 < 0 || m2 >= S || m2 <= m_lo || m2 >= m_hi) {
+                        // the sample cannot separate k from KNN_BIG_CAP: the whole data set as a last resort, else ties
+                        if (c < k && tau < 1.0 / 0.0 && n - 1 <= KNN_BIG_CAP)
+                            s_tau = 1.0 / 0.0;
+                        else
+                            s_state = 2;
+                    } else {
+                        m = m2;
+                        s_tau = sd[m];
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_state != 0)
+                break;
+        }
+        if (s_state == 1) {
+            const int c = s_cnt;
+            for (int e = tid; e < c; e += blockDim.x) {
+                const double de = hd[e];
+                const int ie = hx[e];
+                int rank = 0;
+                for (int o = 0; o < c; ++o)
+                    rank += pair_less<double>(hd[o], hx[o], de, ie) ? 1 : 0;
+                if (rank < k)
+                    knn[q * k + rank] = ie;
+            }
+        } else if (tid == 0) {
+            atomicOr(err_flag, 1);
+        }
+        __syncthreads();
+    }
+}
+
 // knn (row-major, 0-based) -> column-major 1-based (R layout)
 __global__ void k_knn_to_r_layout(const int32_t *__restrict__ knn, int64_t nq, int k, int32_t *__restrict__ out)
 {
@@ -497,12 +624,44 @@ static int knn_core(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int
 {
     CB_CHECK(ctx, n >= 2, "cb200_knn: need at least 2 points");
     CB_CHECK(ctx, n < 2147483647LL, "cb200_knn: at most 2^31-2 points");
-    CB_CHECK(ctx, d >= 1 && d <= KNN_MAX_DP, "cb200_knn: 1 <= ndims <= %d required (got %d)", KNN_MAX_DP, d);
+    CB_CHECK(ctx, d >= 1 && d <= 4096, "cb200_knn: 1 <= ndims <= 4096 required (got %d)", d);
     CB_CHECK(ctx, k >= 1 && (int64_t)k <= n - 1, "cb200_knn: need 1 <= k <= n-1 (k=%d, n=%lld)", k, (long long)n);
-    CB_CHECK(ctx, k <= 112, "cb200_knn: k <= 112 supported (got %d)", k);
+    CB_CHECK(ctx, k <= KNN_BIG_MAXK, "cb200_knn: k <= %d supported (got %d)", KNN_BIG_MAXK, k);
     CB_CHECK(ctx, q_begin >= 0 && q_begin < q_end && q_end <= n, "cb200_knn: bad query range");
     const int64_t nq = q_end - q_begin;
     CB_CUDA(ctx, ctx->knn.ensure((size_t)nq * k));
+    if (k > 112 || d > KNN_MAX_DP) {
+        // shapes outside the tile engines (rebuildModularity's k = round(sqrt(N)), wide embeddings): exact general path
+        cb_stage_begin(ctx, ST_KNN_TILE);
+        CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
+        const size_t smem = (size_t)KNN_BIG_CAP * 20;
+        CB_CUDA(ctx, cudaFuncSetAttribute(k_knn_bigk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)(nq < (int64_t)ctx->num_sms * 2 ? nq : (int64_t)ctx->num_sms * 2);
+        k_knn_bigk<<<grid, 256, smem, ctx->stream>>>(E, lde, d, n, q_begin, nq, k, ctx->knn.p, ctx->flag.p + 3);
+        CB_LAUNCH(ctx);
+        cb_stage_end(ctx, ST_KNN_TILE);
+        int h_flag = 0;
+        CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p + 3, sizeof(int)));
+        CB_CHECK(ctx, h_flag == 0, "cb200_knn: more than %d references tie at the k-th distance of a query", KNN_BIG_CAP);
+        ctx->tm.knn_engine = 3;
+        ctx->tm.knn_fallback_queries = 0;
+        ctx->tm.knn_tiles_scanned = ctx->tm.knn_tiles_total = 0;
+        ctx->knn_nq = nq;
+        ctx->knn_k = k;
+        ctx->knn_ntotal = n;
+        ctx->knn_qbegin = q_begin;
+        ctx->have_knn = true;
+        if (index_out != nullptr) {
+            cb_stage_begin(ctx, ST_D2H);
+            CB_CUDA(ctx, ctx->stage_i.ensure((size_t)nq * k));
+            k_knn_to_r_layout<<<(unsigned)((nq * k + 255) / 256), 256, 0, ctx->stream>>>(ctx->knn.p, nq, k, ctx->stage_i.p);
+            CB_LAUNCH(ctx);
+            CB_TRY(cb200_d2h(ctx, index_out, ctx->stage_i.p, (size_t)nq * k * sizeof(int32_t), ctx->stream));
+            cb_stage_end(ctx, ST_D2H);
+            CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        return 0;
+    }
     CB_CUDA(ctx, ctx->knn_dk.ensure((size_t)nq));
     CB_CUDA(ctx, ctx->fb_list.ensure((size_t)nq));
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));

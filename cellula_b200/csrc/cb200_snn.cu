@@ -22,7 +22,7 @@
 
 #include "cb200_common.cuh"
 
-#define SNN_SLOTS 4  // at most 4 lists per lane: supports k + 1 <= 128
+#define SNN_SLOTS 8  // at most 8 lists per lane: supports k + 1 <= 256 (ranks are 8 bits of a reverse-list entry)
 #define SNN_INF 0xffffffffu
 
 __global__ void k_index_to_rowmajor0(const int32_t *__restrict__ in, int64_t n, int k, int32_t *__restrict__ out,
@@ -293,22 +293,27 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
 // ---------------------------------------------------------------------------------------
 #define SNN_HASH_EMPTY 0xffffffffu
 #define SNN_TIERS 5
-#define SNN_MAXL 128
+#define SNN_MAXL 256
 template <int LOG_SLOTS>
 struct SnnTier {
     static constexpr int log_slots = LOG_SLOTS, slots = 1 << LOG_SLOTS;
     static constexpr int cap = slots / 16 * 11;                        // load factor <= 0.6875
-    static constexpr int bytes = slots * 6 + cap * 2 + SNN_MAXL * 8 + 16;   // keys, positions, values, list table
+    // per warp: keys, positions, values, and the table of the k + 1 lists (start, prefix) padded to 32 lists
+    __host__ __device__ static int bytes(int lpad) { return slots * 6 + cap * 2 + lpad * 8 + 16; }
     // small tables: two CTAs per SM (<= 110 KB each); larger ones: one CTA with as many warps as fit 225 KB
-    static constexpr int w2 = (110 * 1024) / bytes > 16 ? 16 : (110 * 1024) / bytes;
-    static constexpr int w1 = (225 * 1024) / bytes > 16 ? 16 : ((225 * 1024) / bytes < 1 ? 1 : (225 * 1024) / bytes);
-    static constexpr int ctas_per_sm = w2 >= 8 ? 2 : 1;
-    static constexpr int warps = w2 >= 8 ? w2 : w1;
+    static int warps(int lpad, int *ctas_per_sm)
+    {
+        const int b = bytes(lpad);
+        const int w2 = (110 * 1024) / b > 16 ? 16 : (110 * 1024) / b;
+        const int w1 = (225 * 1024) / b > 16 ? 16 : ((225 * 1024) / b < 1 ? 1 : (225 * 1024) / b);
+        *ctas_per_sm = w2 >= 8 ? 2 : 1;
+        return w2 >= 8 ? w2 : w1;
+    }
 };
 
 template <int LOG_SLOTS>
-__global__ void __launch_bounds__(32 * SnnTier<LOG_SLOTS>::warps)
-k_snn_flat(const int32_t *__restrict__ nn, int k, int type, int64_t j_begin, const int64_t *__restrict__ rptr,
+__global__ void __launch_bounds__(512)
+k_snn_flat(const int32_t *__restrict__ nn, int k, int type, int lpad, int64_t j_begin, const int64_t *__restrict__ rptr,
            const uint32_t *__restrict__ hosts, const int32_t *__restrict__ cut, const int32_t *__restrict__ jlist,
            const int *__restrict__ nlist, int32_t *__restrict__ ecnt, const int64_t *__restrict__ toff,
            uint32_t *__restrict__ tmp_h, uint16_t *__restrict__ tmp_v)
@@ -316,17 +321,18 @@ k_snn_flat(const int32_t *__restrict__ nn, int k, int type, int64_t j_begin, con
     using T = SnnTier<LOG_SLOTS>;
     extern __shared__ __align__(16) unsigned char snn_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned char *mine = snn_smem + (size_t)w * T::bytes;
+    const int n_warps = blockDim.x >> 5;
+    unsigned char *mine = snn_smem + (size_t)w * T::bytes(lpad);
     uint32_t *key = reinterpret_cast<uint32_t *>(mine);                          // [slots]
-    uint32_t *lstart = key + T::slots;                                            // [SNN_MAXL] first entry of list i in hosts
-    uint32_t *lpre = lstart + SNN_MAXL;                                           // [SNN_MAXL] entries of the lists before i
-    uint16_t *idx = reinterpret_cast<uint16_t *>(lpre + SNN_MAXL);                // [slots] slot -> output position
+    uint32_t *lstart = key + T::slots;                                            // [lpad] first entry of list i in hosts
+    uint32_t *lpre = lstart + lpad;                                               // [lpad] entries of the lists before i
+    uint16_t *idx = reinterpret_cast<uint16_t *>(lpre + lpad);                    // [slots] slot -> output position
     uint16_t *val = idx + T::slots;                                               // [cap]   position -> value
     const int L = k + 1;
     const bool want_min = type == CB200_SNN_RANK;
     const int n_items = *nlist;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int it = blockIdx.x * T::warps + w; it < n_items; it += gridDim.x * T::warps) {
+    for (int it = blockIdx.x * n_warps + w; it < n_items; it += gridDim.x * n_warps) {
         const int64_t jl = jlist[it];
         const int64_t j = j_begin + jl;
         // the lists: start in hosts, number of entries with cell < j (the entry of j itself sits at position
@@ -498,11 +504,14 @@ template <int LOG_SLOTS>
 static int launch_snn_flat(cb200_ctx *ctx, const int32_t *d_nn, int k, int type, int64_t j_begin, int64_t nj, int tier)
 {
     using T = SnnTier<LOG_SLOTS>;
-    const size_t smem = (size_t)T::bytes * T::warps;
+    const int lpad = (k + 1 + 31) & ~31;
+    int ctas_per_sm = 1;
+    const int warps = T::warps(lpad, &ctas_per_sm);
+    const size_t smem = (size_t)T::bytes(lpad) * warps;
     CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_flat<LOG_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = ctx->num_sms * T::ctas_per_sm;
-    k_snn_flat<LOG_SLOTS><<<grid, 32 * T::warps, smem, ctx->stream>>>(
-        d_nn, k, type, j_begin, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->snn_jlist.p + (int64_t)tier * nj,
+    const int grid = ctx->num_sms * ctas_per_sm;
+    k_snn_flat<LOG_SLOTS><<<grid, 32 * warps, smem, ctx->stream>>>(
+        d_nn, k, type, lpad, j_begin, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->snn_jlist.p + (int64_t)tier * nj,
         ctx->snn_nlists.p + tier, ctx->ecnt.p, ctx->snn_toff.p, ctx->snn_tmp_h.p,
         reinterpret_cast<uint16_t *>(ctx->snn_tmp_rc.p));
     CB_LAUNCH(ctx);
@@ -524,8 +533,11 @@ static void launch_snn_merge(cb200_ctx *ctx, int grid, const int32_t *d_nn, int6
     else if (k + 1 <= 64)
         k_snn_merge<MODE, 2><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
                                                            ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, jlist, nlist);
-    else
+    else if (k + 1 <= 128)
         k_snn_merge<MODE, 4><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
+                                                           ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, jlist, nlist);
+    else
+        k_snn_merge<MODE, 8><<<grid, 256, 0, ctx->stream>>>(nn, n, k, type, j_begin, j_end, ctx->rptr.p, ctx->hosts.p,
                                                            ecnt, bcnt, eptr, ctx->efrom.p, ctx->eto.p, ctx->ew8.p, jlist, nlist);
 }
 

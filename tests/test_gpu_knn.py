@@ -206,10 +206,25 @@ def test_knn_argument_errors(gpu_ctx):
     emb = synth.make_embedding(50, 5, seed=3)
     with pytest.raises(cellula_b200.Cb200Error, match="k <= n-1"):
         gpu_ctx.knn(emb, 50)
-    with pytest.raises(cellula_b200.Cb200Error, match="k <= 112"):
-        gpu_ctx.knn(synth.make_embedding(300, 5, seed=3), 120)
-    with pytest.raises(cellula_b200.Cb200Error, match="ndims"):
-        gpu_ctx.knn(synth.make_embedding(100, 70, seed=3), 5)
+    with pytest.raises(cellula_b200.Cb200Error, match="k <= 2048"):
+        gpu_ctx.knn(synth.make_embedding(3000, 5, seed=3), 2500)
+
+
+@pytest.mark.parametrize("n,d,k", [(300, 5, 120), (100, 70, 5), (5000, 20, 113), (12544, 30, 112), (9000, 16, 255),
+                                   (4500, 100, 67), (2500, 8, 600)])
+def test_knn_general_path_for_large_k_and_wide_embeddings(gpu_ctx, n, d, k):
+    """Shapes outside the tile engines: k > 112 (rebuildModularity's default k = round(sqrt(N)), uwot's
+    n_neighbors = floor(sqrt(N))) and more than 64 dimensions go through the exact general kernel."""
+    emb = synth.make_embedding(n, d, seed=n + d + k)
+    assert np.array_equal(gpu_ctx.knn(emb, k), O.find_knn(emb, k))
+    if k > 112 or d > 64:
+        assert gpu_ctx.timings()["knn_engine"] == 3
+
+
+def test_knn_general_path_with_ties(gpu_ctx):
+    rng = np.random.default_rng(11)
+    lat = rng.integers(-3, 4, size=(4000, 3)).astype(np.float64)       # hundreds of exact ties per query
+    assert np.array_equal(gpu_ctx.knn(lat, 150), O.find_knn(lat, 150))
 
 
 def test_knn_two_product_mode_is_exact(gpu_ctx, monkeypatch):

@@ -115,3 +115,15 @@ def test_snn_argument_errors(gpu_ctx):
         gpu_ctx.snn(bad, "rank")
     with pytest.raises(KeyError):
         gpu_ctx.snn(knn, "cosine")
+
+
+@pytest.mark.parametrize("n,k", [(3000, 127), (2500, 200), (1500, 255)])
+def test_snn_large_k_as_rebuild_modularity_uses(gpu_ctx, n, k):
+    """k up to 255 (rebuildModularity's round(sqrt(N)) for up to 65 025 cells): every cell goes to the largest table
+    tiers or the merge kernel; edges, weights and emission order stay bit-exact."""
+    emb = synth.make_embedding(n, 10, seed=n + k)
+    knn = O.find_knn(emb, k)
+    for scheme in ("rank", "jaccard"):
+        got = gpu_ctx.snn(knn, scheme, j_begin=n - 300, j_end=n)
+        want = O.snn_edges(knn, scheme, j_begin=n - 300, j_end=n)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), (k, scheme)
