@@ -1142,11 +1142,11 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             if (j < 0)
                 break;
             if (bw == 0 && lane == 0)
-                TL(4, ((long long)visit << 8) | 1);
+                TL(5, ((long long)visit << 8) | 1);
             if (use >= 1)
                 mbar_wait(qfree + b, (uint32_t)((use - 1) & 1), err_flag);
             if (bw == 0 && lane == 0)
-                TL(4, ((long long)visit << 8) | 2);
+                TL(5, ((long long)visit << 8) | 2);
             const double *cj = cen + (size_t)j * d;
             // lane = the column pair (2 lane, 2 lane + 1): one packed 32-bit store per part and row
             const int t0 = 2 * lane, t1 = 2 * lane + 1;
@@ -1189,7 +1189,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             if (lane == 0)
                 mbar_arrive(qfull + b);
             if (bw == 0 && lane == 0)
-                TL(4, ((long long)visit << 8) | 3);
+                TL(5, ((long long)visit << 8) | 3);
         }
     }
     tc_fence_before();
@@ -1213,8 +1213,8 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
     const float key_unscale = (float)(1.0 / (scale * scale));
     long long *dbg = nullptr;
     if (getenv("CB200_KNN_TIMELINE") != nullptr) {
-        CB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&dbg), (size_t)5 * 4096 * 2 * sizeof(long long)));
-        CB_CUDA(ctx, cudaMemsetAsync(dbg, 0, (size_t)5 * 4096 * 2 * sizeof(long long), ctx->stream));
+        CB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&dbg), (size_t)6 * 4096 * 2 * sizeof(long long)));
+        CB_CUDA(ctx, cudaMemsetAsync(dbg, 0, (size_t)6 * 4096 * 2 * sizeof(long long), ctx->stream));
     }
     k_knn_tiles_tc<KP, STAGES, QCAP, NQB, NPROD><<<grid, TC_THREADS, smem, ctx->stream>>>(
         E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, ctx->knn_eperm.p, C,
@@ -1224,7 +1224,7 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
         ctx->cand_err.p, NPROD == 3 ? 4.6e-5f : 3.0e-4f, ctx->flag.p + 3, ctx->maxnrm.p + 3, dbg);
     CB_LAUNCH(ctx);
     if (dbg != nullptr) {   // dump the timeline of the middle CTA
-        std::vector<long long> h((size_t)5 * 4096 * 2);
+        std::vector<long long> h((size_t)6 * 4096 * 2);
         CB_CUDA(ctx, cudaMemcpyAsync(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         FILE *f = fopen(getenv("CB200_KNN_TIMELINE"), "wb");
