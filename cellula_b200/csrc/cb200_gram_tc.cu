@@ -174,7 +174,7 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int64_t f = 0; f < n_flush; ++f) {
                 // the flush warps must have drained the accumulators of the previous period
                 mbar_wait(tempty, (uint32_t)((f & 1) ^ 1), err_flag);
@@ -343,7 +343,7 @@ k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int64_t f = 0; f < n_flush; ++f) {
                 mbar_wait(tempty, (uint32_t)((f & 1) ^ 1), err_flag);
                 tc_fence_after();

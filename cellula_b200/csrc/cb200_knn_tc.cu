@@ -402,14 +402,15 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, co
 // sorts by exact distance).
 constexpr int TC_RING = 16;  // tile ids of the sequence in flight (producer -> MMA -> scanners)
 constexpr int TC_SCAN_SETS = 3;
-constexpr int TC_ACC_STAGES = 4;
+constexpr int TC_ACC_STAGES = 3;   // = scanner sets: set s reads accumulator s
+constexpr uint32_t TC_Q_COL0 = TC_ACC_STAGES * TC_N;   // TMEM columns of the query operand: 2 buffers x (32 hi + 32 lo)
 constexpr int TC_POS_BITS = 27;  // sorted positions in a ring entry
 constexpr int TC_THREADS = 64 + TC_SCAN_SETS * 128 + 128 + 128;  // + inserters + query-image builders
 
 template <int KP, int STAGES, int QCAP, int NQB>
 struct TcSmem {
-    static constexpr size_t q_img = 0;                                      // NQB x (Q hi | Q lo)
-    static constexpr size_t r_img = q_img + NQB * TC_TILE_BYTES;
+    static constexpr size_t q_img = 0;                                      // transit of the query image (Q hi | Q lo) on its way to TMEM
+    static constexpr size_t r_img = q_img + TC_TILE_BYTES;
     static constexpr size_t hk = r_img + (size_t)STAGES * TC_TILE_BYTES;    // [KP][TC_M] heap keys (T values)
     static constexpr size_t hi = hk + (size_t)TC_M * KP * 4;                // [KP][TC_M] sorted positions
     static constexpr size_t ring = hi + (size_t)TC_M * KP * 4;              // [SETS][QCAP][TC_M] uint2
@@ -455,9 +456,9 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             ++tl_n;
         }
     };
-    constexpr uint32_t TC_TMEM_COLS = TC_ACC_STAGES * TC_N;  // 512
+    constexpr uint32_t TC_TMEM_COLS = 512;  // 3 accumulators of 128 columns + 2 query-operand buffers of 64
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *q_img = smem + L::q_img;                                // 2 x 32 KB: Q hi | Q lo, per cluster visit
+    unsigned char *q_img = smem + L::q_img;                                // 32 KB transit: Q hi | Q lo of the visit being built
     unsigned char *r_img = smem + L::r_img;                                // STAGES x 32 KB
     float *hk = reinterpret_cast<float *>(smem + L::hk);
     int *hi_ = reinterpret_cast<int *>(smem + L::hi);
@@ -830,11 +831,11 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (elect_one()) {
             int prev_b = -1;
             const uint64_t desc_hi = make_desc(0u);                      // everything but the start address
             const uint32_t r_desc0 = smem_u32(r_img) >> 4;
-            uint32_t q_desc = 0u;
+            uint32_t q_tmem = 0u;
             for (uint32_t seq = 0;; ++seq) {
                 const int s = (int)(seq % STAGES);
                 const uint32_t ph = (uint32_t)((seq / STAGES) & 1);
@@ -868,23 +869,23 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     TL(1, ((long long)seq << 8) | 4);
                     tc_fence_after();
                     prev_b = b;
-                    q_desc = smem_u32(q_img + (size_t)b * TC_TILE_BYTES) >> 4;
+                    q_tmem = tmem_base + TC_Q_COL0 + (uint32_t)b * 64u;
                 }
-                // descriptors: only the 14-bit start-address field (bytes >> 4) changes between operands
+                // B descriptors: only the 14-bit start-address field (bytes >> 4) changes between operands; the A operand
+                // (query image) is read from TMEM: row = lane, 8 columns (16 fp16) per K step, hi part then lo part
                 const uint32_t rb = r_desc0 + (uint32_t)s * (TC_TILE_BYTES >> 4);
                 const uint32_t dcol = tmem_base + (uint32_t)(a * TC_N);
 #pragma unroll
                 for (int p = 0; p < NPROD; ++p) {
-                    const uint32_t qd = q_desc + ((p == 2) ? (TC_PART_BYTES >> 4) : 0u);
+                    const uint32_t qa = q_tmem + ((p == 2) ? 32u : 0u);
                     const uint32_t rd = rb + ((p == 1) ? (TC_PART_BYTES >> 4) : 0u);
 #pragma unroll
                     for (int kk = 0; kk < TC_K / TC_UMMA_K; ++kk) {
-                        const uint64_t da = desc_hi | (uint64_t)(qd + kk * (TC_UMMA_K * 2 >> 4));
                         const uint64_t db = desc_hi | (uint64_t)(rd + kk * (TC_UMMA_K * 2 >> 4));
                         if (p == 0 && kk == 0)
-                            umma_f16_first(dcol, da, db, TC_IDESC);
+                            umma_f16_ts_first(dcol, qa + (uint32_t)(kk * 8), db, TC_IDESC);
                         else
-                            umma_f16_acc(dcol, da, db, TC_IDESC);
+                            umma_f16_ts_acc(dcol, qa + (uint32_t)(kk * 8), db, TC_IDESC);
                     }
                 }
                 umma_commit(empty + s);   // smem stage may be refilled once these MMAs have read it
@@ -995,7 +996,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             atomicAdd(scan_done, 1u);
         }
     } else if (warp < 2 + TC_SCAN_SETS * 4 + 4) {
-        // ===== inserters: thread = query row; binary min-heap of the KP largest T in shared memory =====
+        // ===== inserters: thread = query row; the KP largest T in shared memory, worst entry tracked =====
         const int row = tid - (64 + TC_SCAN_SETS * 128);
         float *mk = hk + row;   // entry e at mk[e * TC_M]
         int *mi = hi_ + row;
@@ -1006,86 +1007,107 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             head[s2] = 0u;
             raddr[s2] = smem_u32(ring + (size_t)s2 * QCAP * TC_M + row);
         }
-        int cnt = 0;            // entries held; the heap is filled from the back, then heapified once
-        float root = -FLT_MAX;
+        // The KP best candidates of a row are kept UNSORTED in shared memory ([entry][row]: a lane always hits its own
+        // bank) in groups of 8; the smallest key of every group and its slot live in registers.  An accepted value
+        // overwrites the row's worst entry, only that group is rescanned (8 independent loads instead of the
+        // dependent load chain of a heap sift) and the new worst is the minimum over the group minima.
+        constexpr int NG = KP / 8;
+        static_assert(KP % 8 == 0, "candidate groups of 8");
+        float gmin[NG];
+        int gslot[NG];
+#pragma unroll
+        for (int g2 = 0; g2 < NG; ++g2) {
+            gmin[g2] = FLT_MAX;
+            gslot[g2] = g2 * 8;
+        }
+        int cnt = 0;            // entries held
+        int worst = 0;          // slot of the smallest key once the list is full
+        float root = -FLT_MAX;  // its key = the row's threshold
         const int my_pos = ql0 + row < nq ? qpos[ql0 + row] : -1;   // sorted position of the query itself
         bool done_seen = false;
+        unsigned idle_ns = 32u;
+        auto rescan_group = [&](int g2) {
+            float m = FLT_MAX;
+            int ws = g2 * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float v = mk[(g2 * 8 + e) * TC_M];
+                if (v < m) {
+                    m = v;
+                    ws = g2 * 8 + e;
+                }
+            }
+#pragma unroll
+            for (int gg = 0; gg < NG; ++gg) {
+                if (gg == g2) {
+                    gmin[gg] = m;
+                    gslot[gg] = ws;
+                }
+            }
+        };
+        auto find_worst = [&]() {
+            root = gmin[0];
+            worst = gslot[0];
+#pragma unroll
+            for (int gg = 1; gg < NG; ++gg) {
+                if (gmin[gg] < root) {
+                    root = gmin[gg];
+                    worst = gslot[gg];
+                }
+            }
+        };
         while (true) {
             bool got = false;
 #pragma unroll
             for (int s2 = 0; s2 < TC_SCAN_SETS; ++s2) {
-                unsigned ex, ey;
-                asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];"
-                             : "=r"(ex), "=r"(ey)
-                             : "r"(raddr[s2] + (uint32_t)((head[s2] % QCAP) * TC_M * 8))
-                             : "memory");
-                if ((ey >> 31) != ((head[s2] / QCAP) & 1u))
-                    continue;
-                got = true;
-                ++head[s2];
-                qhead[s2 * TC_M + row] = head[s2];
-                const float val = __uint_as_float(ex);
-                const int pos = (int)(ey & ((1u << TC_POS_BITS) - 1u));
-                if (pos == my_pos)
-                    continue;   // the query itself
-                if (cnt < KP) {
-                    const int e = KP - 1 - cnt;
-                    mk[e * TC_M] = val;
-                    mi[e * TC_M] = pos;
-                    if (++cnt == KP) {
-                        // heapify: Floyd, parents from the last one down
-                        for (int st = KP / 2 - 1; st >= 0; --st) {
-                            float v = mk[st * TC_M];
-                            int vp = mi[st * TC_M];
-                            int i = st;
-                            while (true) {
-                                const int l = 2 * i + 1;
-                                if (l >= KP)
-                                    break;
-                                const float kl = mk[l * TC_M];
-                                const float kr = (l + 1 < KP) ? mk[(l + 1) * TC_M] : FLT_MAX;
-                                const int c = kl <= kr ? l : l + 1;
-                                const float kc = fminf(kl, kr);
-                                if (v <= kc)
-                                    break;
-                                mk[i * TC_M] = kc;
-                                mi[i * TC_M] = mi[c * TC_M];
-                                i = c;
-                            }
-                            mk[i * TC_M] = v;
-                            mi[i * TC_M] = vp;
+                const unsigned h0 = head[s2];
+#pragma unroll 1
+                for (int rep = 0; rep < QCAP; ++rep) {   // drain what the set has pushed for this row
+                    unsigned ex, ey;
+                    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];"
+                                 : "=r"(ex), "=r"(ey)
+                                 : "r"(raddr[s2] + (uint32_t)((head[s2] % QCAP) * TC_M * 8))
+                                 : "memory");
+                    if ((ey >> 31) != ((head[s2] / QCAP) & 1u))
+                        break;
+                    ++head[s2];
+                    const float val = __uint_as_float(ex);
+                    const int pos = (int)(ey & ((1u << TC_POS_BITS) - 1u));
+                    if (pos == my_pos)
+                        continue;   // the query itself
+                    if (cnt < KP) {
+                        mk[cnt * TC_M] = val;
+                        mi[cnt * TC_M] = pos;
+                        if (++cnt == KP) {
+#pragma unroll 1
+                            for (int g2 = 0; g2 < NG; ++g2)
+                                rescan_group(g2);
+                            find_worst();
+                            thr_sh[row] = root;
                         }
-                        root = mk[0];
+                    } else if (val > root) {
+                        mk[worst * TC_M] = val;
+                        mi[worst * TC_M] = pos;
+                        rescan_group(worst >> 3);
+                        find_worst();
                         thr_sh[row] = root;
                     }
-                } else if (val > root) {
-                    int i = 0;
-                    while (true) {  // sift the new value down from the root
-                        const int l = 2 * i + 1;
-                        if (l >= KP)
-                            break;
-                        const float kl = mk[l * TC_M];
-                        const float kr = (l + 1 < KP) ? mk[(l + 1) * TC_M] : FLT_MAX;
-                        const int c = kl <= kr ? l : l + 1;
-                        const float kc = fminf(kl, kr);
-                        if (val <= kc)
-                            break;
-                        mk[i * TC_M] = kc;
-                        mi[i * TC_M] = mi[c * TC_M];
-                        i = c;
-                    }
-                    mk[i * TC_M] = val;
-                    mi[i * TC_M] = pos;
-                    root = mk[0];
-                    thr_sh[row] = root;
+                }
+                if (head[s2] != h0) {
+                    got = true;
+                    qhead[s2 * TC_M + row] = head[s2];
                 }
             }
             if (!__any_sync(0xffffffffu, got)) {
                 if (done_seen)
                     break;
                 done_seen = *reinterpret_cast<volatile unsigned int *>(scan_done) == (unsigned)(TC_SCAN_SETS * 4);
-                if (!done_seen)
-                    __nanosleep(32);
+                if (!done_seen) {
+                    __nanosleep(idle_ns);   // every poll is shared-memory traffic the tensor core competes with
+                    idle_ns = idle_ns < 256u ? idle_ns * 2u : 256u;
+                }
+            } else {
+                idle_ns = 32u;
             }
         }
         // final: candidates (original indices, unsorted) and the row threshold in key space, unscaled:
@@ -1094,16 +1116,17 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         if (myql < nq) {
             int32_t *out = cand_idx + myql * (int64_t)cand_stride;
             for (int p = 0; p < cand_stride; ++p)
-                out[p] = (p < KP && p >= KP - cnt) ? mi[p * TC_M] : -1;   // sorted positions: k_knn_rerank maps them through perm
+                out[p] = p < cnt ? mi[p * TC_M] : -1;   // sorted positions: k_knn_rerank maps them through perm
             cand_tau[myql] = (cnt < KP) ? FLT_MAX : -root * key_unscale;
         }
     } else {
         // ===== builders: the query operand image relative to the centre of the cluster being visited,
         // into the image buffer the producer names.  Warp w owns rows 32w .. 32w+31; a row is loaded by
         // the whole warp (lane = coordinate: coalesced), several rows in flight =====
-        const int bw = warp - (2 + TC_SCAN_SETS * 4 + 4);
-        const int64_t rowq = ql0 + bw * 32 + lane;
-        const int my_p = rowq < nq ? qpos[rowq] : -1;    // lane r: sorted position of row 32 bw + r
+        const int bw = warp - (2 + TC_SCAN_SETS * 4 + 4);   // share of the prefilter pass
+        const int bq = warp & 3;                             // TMEM lane quarter this warp may write = its 32 query rows
+        const int64_t rowq = ql0 + bq * 32 + lane;
+        const int my_p = rowq < nq ? qpos[rowq] : -1;    // lane r: sorted position of row 32 bq + r
         bool pf_served = false;
         for (int visit = 0;; ++visit) {
             const int b = visit % NQB, use = visit / NQB;
@@ -1151,7 +1174,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             // lane = the column pair (2 lane, 2 lane + 1): one packed 32-bit store per part and row
             const int t0 = 2 * lane, t1 = 2 * lane + 1;
             const double c0 = t0 < d ? cj[t0] : 0.0, c1 = t1 < d ? cj[t1] : 0.0;
-            unsigned char *qb = q_img + (size_t)b * TC_TILE_BYTES;
+            unsigned char *qb = q_img;   // transit: this warp's 32 rows, then row-wise into TMEM buffer b
             // constants of the columns past the coordinates: [2^12, 1, 2^-12] (hi part), 0 elsewhere
             auto kconst = [&](int t) { return t == d ? 4096.f : (t == d + 1 ? 1.f : (t == d + 2 ? 1.0f / 4096.f : 0.f)); };
             const float k0 = kconst(t0), k1 = kconst(t1);
@@ -1169,7 +1192,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int row = bw * 32 + r0 + u;
+                    const int row = bq * 32 + r0 + u;
                     __half h0 = __float2half(ps[u] >= 0 ? k0 : 0.f), l0 = __float2half(0.f);
                     __half h1 = __float2half(ps[u] >= 0 ? k1 : 0.f), l1 = __float2half(0.f);
                     if (ps[u] >= 0 && t0 < d)
@@ -1184,7 +1207,30 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     *reinterpret_cast<uint32_t *>(qb + TC_PART_BYTES + o) = lp;
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core reads
+            __syncwarp();
+            // transit -> TMEM: thread = query row (TMEM lane); its 128-byte hi row and lo row, chunks un-swizzled,
+            // are 32 + 32 columns of query buffer b
+            {
+                const int row = bq * 32 + lane;
+                const unsigned char *rp = qb + (size_t)((row >> 3) * 1024 + (row & 7) * 128);
+                const uint32_t tq = tmem_base + ((uint32_t)(bq * 32) << 16) + TC_Q_COL0 + (uint32_t)b * 64u;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 q4 = *reinterpret_cast<const uint4 *>(rp + (size_t)part * TC_PART_BYTES +
+                                                                          (size_t)(((c ^ (row & 7)) & 7) << 4));
+                        v[4 * c] = q4.x;
+                        v[4 * c + 1] = q4.y;
+                        v[4 * c + 2] = q4.z;
+                        v[4 * c + 3] = q4.w;
+                    }
+                    tmem_st32(tq + (uint32_t)(part * 32), v);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before();
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(qfull + b);
@@ -1380,13 +1426,13 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
     CB_CHECK(ctx, npos < (1LL << TC_POS_BITS), "cb200_knn: at most 2^27 points on the tensor-core engine");
     const char *np_env = getenv("CB200_KNN_PRODUCTS");
     if (KP == 32 && np_env != nullptr && atoi(np_env) == 2)
-        CB_TRY((launch_tc<32, 3, 8, 2, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<32, 4, 8, 2, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
     else if (KP == 32)
-        CB_TRY((launch_tc<32, 3, 8, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<32, 4, 8, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
     else if (KP == 64)
-        CB_TRY((launch_tc<64, 2, 8, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<64, 3, 8, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
     else
-        CB_TRY((launch_tc<112, 2, 4, 1>(ctx, E, lde, d, scale, nq, C, CAND)));
+        CB_TRY((launch_tc<112, 2, 4, 2>(ctx, E, lde, d, scale, nq, C, CAND)));
     cb_stage_end(ctx, ST_KNN_TILE);
     *kp_out = CAND;
     *ntau_out = 1;

@@ -103,6 +103,19 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t ct
                  : "memory");
 }
 
+// One lane of a converged warp (elect.sync): a region guarded by this predicate is known to the assembler to run in a
+// single thread, so tcgen05.mma / tcgen05.commit are emitted once instead of inside a per-active-lane ELECT loop
+__device__ __forceinline__ uint32_t elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -151,6 +164,40 @@ __device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t desc_a, u
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand is read from tensor memory (row = lane, 16-bit elements packed two per
+// 32-bit column, K-major), which leaves the shared-memory read port to the B operand alone
+__device__ __forceinline__ void umma_f16_ts_first(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_acc(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+// register -> TMEM store of 32 consecutive 32-bit columns of this thread's lane; complete after tmem_st_wait()
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
 // start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B
 // between 8-row groups | version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64)
