@@ -447,6 +447,15 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     // per role into dbg[role][TL_CAP][2]
     constexpr int TL_CAP = 4096;
     const bool tl_on = dbg != nullptr && blockIdx.x == gridDim.x / 2;
+    long long *cta_log = dbg != nullptr ? dbg + (size_t)7 * TL_CAP * 2 + (size_t)blockIdx.x * 4 : nullptr;
+    if (cta_log != nullptr && threadIdx.x == 0) {
+        unsigned long long t_ns;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ns));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        cta_log[0] = (long long)t_ns;
+        cta_log[3] = (long long)smid;
+    }
     int tl_n = 0;
     auto TL = [&](int role, long long tag) {
         if (tl_on && tl_n < TL_CAP) {
@@ -614,6 +623,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         float plan_crmax = 0.f, plan_dq[4] = {0.f, 0.f, 0.f, 0.f};
         float blo = 0.f, bhi = 0.f;   // bounds of tile tb32 + lane
         float crmax = 0.f;
+        unsigned cm = 0u;             // tiles of the current block that pass the coarse test (bit = tile - tb32)
+        bool cm_valid = false;
 
         auto refresh = [&]() {
             // how far every row can still find a candidate: canonical T = -0.5 d^2, rounded up
@@ -740,32 +751,42 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     const int tt = t + lane;
                     blo = tt < te ? tile_lo[tt] : INFINITY;
                     bhi = tt < te ? tile_hi[tt] : -INFINITY;
+                    cm_valid = false;
                 }
-                // coarse test of the 32 tiles of the block at once (lane = tile) against the hull of the
-                // rows' intervals, then the exact per-row test of the first survivor
-                float mlo = fminf(fminf(lo[0], lo[1]), fminf(lo[2], lo[3]));
-                float mhi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+                // coarse test of the 32 tiles of the block at once (lane = tile) against the hull of the rows'
+                // intervals -- kept until the thresholds are refreshed or the block changes -- then the exact
+                // per-row test of its survivors, one at a time, up to the first tile that is needed
+                if (!cm_valid) {
+                    float mlo = fminf(fminf(lo[0], lo[1]), fminf(lo[2], lo[3]));
+                    float mhi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    mlo = fminf(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
-                    mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+                    for (int o = 16; o > 0; o >>= 1) {
+                        mlo = fminf(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+                        mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+                    }
+                    cm = __ballot_sync(0xffffffffu, tb32 + lane >= t && mlo <= bhi && mhi >= blo);
+                    cm_valid = true;
                 }
-                const unsigned cm = __ballot_sync(0xffffffffu, tb32 + lane >= t && mlo <= bhi && mhi >= blo);
-                if (cm == 0u) {
-                    t = tb32 + 32 < te ? tb32 + 32 : te;
-                    continue;
-                }
-                const int off = __ffs(cm) - 1;
-                t = tb32 + off;
-                const float a = __shfl_sync(0xffffffffu, blo, off);
-                const float b = __shfl_sync(0xffffffffu, bhi, off);
-                bool need = false;
+                cm &= 0xffffffffu << (t - tb32);   // t - tb32 in [0, 32): tiles before t are done
+                bool found = false;
+                while (cm != 0u) {
+                    const int off = __ffs(cm) - 1;
+                    const float a = __shfl_sync(0xffffffffu, blo, off);
+                    const float b = __shfl_sync(0xffffffffu, bhi, off);
+                    bool need = false;
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    need |= (lo[u] <= b) && (hi[u] >= a);
-                if (__any_sync(0xffffffffu, need))
+                    for (int u = 0; u < 4; ++u)
+                        need |= (lo[u] <= b) && (hi[u] >= a);
+                    if (__any_sync(0xffffffffu, need)) {
+                        t = tb32 + off;
+                        found = true;
+                        break;
+                    }
+                    cm &= cm - 1u;
+                }
+                if (found)
                     return true;
-                ++t;
+                t = tb32 + 32 < te ? tb32 + 32 : te;
             }
         };
 
@@ -799,7 +820,12 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             __syncwarp();
             ++t;
             ++seq;
-            refresh();
+            // the thresholds move fast while the first tiles of the sequence are scanned, slowly afterwards: the rows'
+            // intervals are refreshed after every tile at first, then after every second one
+            if (seq < 96u || (seq & 1u) == 0u) {
+                refresh();
+                cm_valid = false;
+            }
             if (!plan_valid && !no_more && (opos != 1 || prefiltered))
                 make_plan();
             have = find_next();
@@ -811,6 +837,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             __threadfence_block();
             mbar_arrive(full + (int)(seq % STAGES));
             atomicAdd(tiles_done, (unsigned long long)seq);
+            if (cta_log != nullptr)
+                cta_log[2] = (long long)seq;
             // stop the builders
             const int v = req_visit + 1, b = v % NQB, use = v / NQB;
             if (use >= 1)
@@ -996,7 +1024,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             atomicAdd(scan_done, 1u);
         }
     } else if (warp < 2 + TC_SCAN_SETS * 4 + 4) {
-        // ===== inserters: thread = query row; the KP largest T in shared memory, worst entry tracked =====
+        // ===== inserters: thread = query row; binary min-heap of the KP largest T in shared memory =====
         const int row = tid - (64 + TC_SCAN_SETS * 128);
         float *mk = hk + row;   // entry e at mk[e * TC_M]
         int *mi = hi_ + row;
@@ -1007,107 +1035,86 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             head[s2] = 0u;
             raddr[s2] = smem_u32(ring + (size_t)s2 * QCAP * TC_M + row);
         }
-        // The KP best candidates of a row are kept UNSORTED in shared memory ([entry][row]: a lane always hits its own
-        // bank) in groups of 8; the smallest key of every group and its slot live in registers.  An accepted value
-        // overwrites the row's worst entry, only that group is rescanned (8 independent loads instead of the
-        // dependent load chain of a heap sift) and the new worst is the minimum over the group minima.
-        constexpr int NG = KP / 8;
-        static_assert(KP % 8 == 0, "candidate groups of 8");
-        float gmin[NG];
-        int gslot[NG];
-#pragma unroll
-        for (int g2 = 0; g2 < NG; ++g2) {
-            gmin[g2] = FLT_MAX;
-            gslot[g2] = g2 * 8;
-        }
-        int cnt = 0;            // entries held
-        int worst = 0;          // slot of the smallest key once the list is full
-        float root = -FLT_MAX;  // its key = the row's threshold
+        int cnt = 0;            // entries held; the heap is filled from the back, then heapified once
+        float root = -FLT_MAX;
         const int my_pos = ql0 + row < nq ? qpos[ql0 + row] : -1;   // sorted position of the query itself
         bool done_seen = false;
-        unsigned idle_ns = 32u;
-        auto rescan_group = [&](int g2) {
-            float m = FLT_MAX;
-            int ws = g2 * 8;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float v = mk[(g2 * 8 + e) * TC_M];
-                if (v < m) {
-                    m = v;
-                    ws = g2 * 8 + e;
-                }
-            }
-#pragma unroll
-            for (int gg = 0; gg < NG; ++gg) {
-                if (gg == g2) {
-                    gmin[gg] = m;
-                    gslot[gg] = ws;
-                }
-            }
-        };
-        auto find_worst = [&]() {
-            root = gmin[0];
-            worst = gslot[0];
-#pragma unroll
-            for (int gg = 1; gg < NG; ++gg) {
-                if (gmin[gg] < root) {
-                    root = gmin[gg];
-                    worst = gslot[gg];
-                }
-            }
-        };
         while (true) {
             bool got = false;
 #pragma unroll
             for (int s2 = 0; s2 < TC_SCAN_SETS; ++s2) {
-                const unsigned h0 = head[s2];
-#pragma unroll 1
-                for (int rep = 0; rep < QCAP; ++rep) {   // drain what the set has pushed for this row
-                    unsigned ex, ey;
-                    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];"
-                                 : "=r"(ex), "=r"(ey)
-                                 : "r"(raddr[s2] + (uint32_t)((head[s2] % QCAP) * TC_M * 8))
-                                 : "memory");
-                    if ((ey >> 31) != ((head[s2] / QCAP) & 1u))
-                        break;
-                    ++head[s2];
-                    const float val = __uint_as_float(ex);
-                    const int pos = (int)(ey & ((1u << TC_POS_BITS) - 1u));
-                    if (pos == my_pos)
-                        continue;   // the query itself
-                    if (cnt < KP) {
-                        mk[cnt * TC_M] = val;
-                        mi[cnt * TC_M] = pos;
-                        if (++cnt == KP) {
-#pragma unroll 1
-                            for (int g2 = 0; g2 < NG; ++g2)
-                                rescan_group(g2);
-                            find_worst();
-                            thr_sh[row] = root;
+                unsigned ex, ey;
+                asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(ex), "=r"(ey)
+                             : "r"(raddr[s2] + (uint32_t)((head[s2] % QCAP) * TC_M * 8))
+                             : "memory");
+                if ((ey >> 31) != ((head[s2] / QCAP) & 1u))
+                    continue;
+                got = true;
+                ++head[s2];
+                qhead[s2 * TC_M + row] = head[s2];
+                const float val = __uint_as_float(ex);
+                const int pos = (int)(ey & ((1u << TC_POS_BITS) - 1u));
+                if (pos == my_pos)
+                    continue;   // the query itself
+                if (cnt < KP) {
+                    const int e = KP - 1 - cnt;
+                    mk[e * TC_M] = val;
+                    mi[e * TC_M] = pos;
+                    if (++cnt == KP) {
+                        // heapify: Floyd, parents from the last one down
+                        for (int st = KP / 2 - 1; st >= 0; --st) {
+                            float v = mk[st * TC_M];
+                            int vp = mi[st * TC_M];
+                            int i = st;
+                            while (true) {
+                                const int l = 2 * i + 1;
+                                if (l >= KP)
+                                    break;
+                                const float kl = mk[l * TC_M];
+                                const float kr = (l + 1 < KP) ? mk[(l + 1) * TC_M] : FLT_MAX;
+                                const int c = kl <= kr ? l : l + 1;
+                                const float kc = fminf(kl, kr);
+                                if (v <= kc)
+                                    break;
+                                mk[i * TC_M] = kc;
+                                mi[i * TC_M] = mi[c * TC_M];
+                                i = c;
+                            }
+                            mk[i * TC_M] = v;
+                            mi[i * TC_M] = vp;
                         }
-                    } else if (val > root) {
-                        mk[worst * TC_M] = val;
-                        mi[worst * TC_M] = pos;
-                        rescan_group(worst >> 3);
-                        find_worst();
+                        root = mk[0];
                         thr_sh[row] = root;
                     }
-                }
-                if (head[s2] != h0) {
-                    got = true;
-                    qhead[s2 * TC_M + row] = head[s2];
+                } else if (val > root) {
+                    int i = 0;
+                    while (true) {  // sift the new value down from the root
+                        const int l = 2 * i + 1;
+                        if (l >= KP)
+                            break;
+                        const float kl = mk[l * TC_M];
+                        const float kr = (l + 1 < KP) ? mk[(l + 1) * TC_M] : FLT_MAX;
+                        const int c = kl <= kr ? l : l + 1;
+                        const float kc = fminf(kl, kr);
+                        if (val <= kc)
+                            break;
+                        mk[i * TC_M] = kc;
+                        mi[i * TC_M] = mi[c * TC_M];
+                        i = c;
+                    }
+                    mk[i * TC_M] = val;
+                    mi[i * TC_M] = pos;
+                    root = mk[0];
+                    thr_sh[row] = root;
                 }
             }
             if (!__any_sync(0xffffffffu, got)) {
                 if (done_seen)
                     break;
                 done_seen = *reinterpret_cast<volatile unsigned int *>(scan_done) == (unsigned)(TC_SCAN_SETS * 4);
-                if (!done_seen) {
-                    __nanosleep(idle_ns);   // every poll is shared-memory traffic the tensor core competes with
-                    idle_ns = idle_ns < 256u ? idle_ns * 2u : 256u;
-                }
-            } else {
-                idle_ns = 32u;
+                if (!done_seen)
+                    __nanosleep(32);
             }
         }
         // final: candidates (original indices, unsorted) and the row threshold in key space, unscaled:
@@ -1116,7 +1123,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         if (myql < nq) {
             int32_t *out = cand_idx + myql * (int64_t)cand_stride;
             for (int p = 0; p < cand_stride; ++p)
-                out[p] = p < cnt ? mi[p * TC_M] : -1;   // sorted positions: k_knn_rerank maps them through perm
+                out[p] = (p < KP && p >= KP - cnt) ? mi[p * TC_M] : -1;   // sorted positions: k_knn_rerank maps them through perm
             cand_tau[myql] = (cnt < KP) ? FLT_MAX : -root * key_unscale;
         }
     } else {
@@ -1240,6 +1247,11 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     }
     tc_fence_before();
     __syncthreads();
+    if (cta_log != nullptr && threadIdx.x == 0) {
+        unsigned long long t_ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ns));
+        cta_log[1] = (long long)t_ns;
+    }
     if (warp == 0)
         tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
@@ -1259,8 +1271,8 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
     const float key_unscale = (float)(1.0 / (scale * scale));
     long long *dbg = nullptr;
     if (getenv("CB200_KNN_TIMELINE") != nullptr) {
-        CB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&dbg), (size_t)6 * 4096 * 2 * sizeof(long long)));
-        CB_CUDA(ctx, cudaMemsetAsync(dbg, 0, (size_t)6 * 4096 * 2 * sizeof(long long), ctx->stream));
+        CB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&dbg), ((size_t)7 * 4096 * 2 + (size_t)grid * 4) * sizeof(long long)));
+        CB_CUDA(ctx, cudaMemsetAsync(dbg, 0, ((size_t)7 * 4096 * 2 + (size_t)grid * 4) * sizeof(long long), ctx->stream));
     }
     k_knn_tiles_tc<KP, STAGES, QCAP, NQB, NPROD><<<grid, TC_THREADS, smem, ctx->stream>>>(
         E, lde, d, scale, ctx->knn_img.p, nq, ctx->knn_qlist.p, ctx->knn_qpos.p, ctx->knn_perm.p, ctx->knn_eperm.p, C,
@@ -1270,7 +1282,7 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
         ctx->cand_err.p, NPROD == 3 ? 4.6e-5f : 3.0e-4f, ctx->flag.p + 3, ctx->maxnrm.p + 3, dbg);
     CB_LAUNCH(ctx);
     if (dbg != nullptr) {   // dump the timeline of the middle CTA
-        std::vector<long long> h((size_t)6 * 4096 * 2);
+        std::vector<long long> h((size_t)7 * 4096 * 2 + (size_t)grid * 4);   // role timelines of the middle CTA, then [start ns, end ns, tiles, SM] of every CTA
         CB_CUDA(ctx, cudaMemcpyAsync(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         FILE *f = fopen(getenv("CB200_KNN_TIMELINE"), "wb");

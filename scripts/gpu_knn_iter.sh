@@ -18,3 +18,4 @@ if [ "${TIMELINE:-1}" = "1" ]; then
 CB200_KNN_TIMELINE=gpurun_out/${TAG}_timeline.bin timeout 300 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-verify > gpurun_out/${TAG}_tl.log 2>&1
 python scripts/timeline_summary.py gpurun_out/${TAG}_timeline.bin
 fi
+if [ "${TIMELINE:-1}" = "1" ]; then python scripts/cta_log_summary.py gpurun_out/${TAG}_timeline.bin | head -4; fi

@@ -2,7 +2,7 @@
 import sys
 import numpy as np
 path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.bin"
-a = np.fromfile(path, dtype=np.int64).reshape(-1, 4096, 2)
+a = np.fromfile(path, dtype=np.int64)[:7 * 4096 * 2].reshape(-1, 4096, 2)
 ev = {r: a[r][:int((a[r][:, 1] != 0).sum())] for r in range(a.shape[0])}
 t0 = ev[0][0, 1]
 d = {}
