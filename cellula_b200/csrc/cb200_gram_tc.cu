@@ -43,7 +43,7 @@ constexpr uint32_t GT_TMEM_COLS = 512;                    // 5 x 64 = 320 -> nex
 constexpr int GT_FLUSH_CHUNKS = 80;                       // 3 * 255^2 * 128 * 80 < 2^31
 constexpr int GT_THREADS = 192;
 constexpr int GT_SCALE_BITS = 19;                         // q = round(y 2^19) < 2^24 for y < 32
-constexpr int GT_QUAD = 4;                                // gene tiles built per CTA of k_gram_img
+constexpr int GT_QUAD = 2;                                // gene tiles built per CTA of k_gram_img (96 KB: two CTAs per SM overlap their zero / scatter / write-out phases)
 // instruction descriptor: c = S32 (2) at [4,6), a = b = unsigned 8 bit (0), K-major, N>>3, M>>4
 constexpr uint32_t GT_IDESC = (2u << 4) | ((uint32_t)(GT_N >> 3) << 17) | ((uint32_t)(GT_M >> 4) << 24);
 }  // namespace
@@ -113,6 +113,10 @@ k_gram_img(const int64_t *__restrict__ hptr, const int32_t *__restrict__ hslot, 
     }
 }
 
+// A_TMEM: the A planes of a chunk are copied shared -> tensor memory (12 tcgen05.cp per chunk, two buffers of 96 columns
+// behind the 320 accumulator columns) and the 36 MMAs read A from there: with both operands in shared memory an
+// M = 128, N = 64, K = 32 int8 MMA needs 6 KB of operands per 32 tensor cycles = 192 B/clk of a 128 B/clk port.
+template <bool A_TMEM>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int H,
           unsigned long long *__restrict__ gram_lo, unsigned long long *__restrict__ gram_hi, int *__restrict__ err_flag)
@@ -193,6 +197,15 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
                     // descriptor constructions per MMA cost more than the 32 cycles the MMA keeps the tensor pipe busy)
                     const uint64_t da0 = make_desc(sa), db0 = make_desc(sb);
                     const uint32_t not_first = t != t0 ? 1u : 0u;   // first chunk of a flush period overwrites
+                    const uint32_t a_tm = tmem_base + GT_ORDERS * GT_N + (uint32_t)(t & 1) * (GT_PLANES * 32);
+                    if (A_TMEM) {
+#pragma unroll
+                        for (int p = 0; p < GT_PLANES; ++p)
+#pragma unroll
+                            for (int kk = 0; kk < GT_KC / 32; ++kk)
+                                tmem_cp_128x256b(a_tm + (uint32_t)(p * 32 + kk * 8),
+                                                 da0 + (uint64_t)((p * GT_PLANE_BYTES + kk * 32) >> 4));
+                    }
 #pragma unroll
                     for (int p = 0; p < GT_PLANES; ++p) {
 #pragma unroll
@@ -201,10 +214,15 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
                             for (int kk = 0; kk < GT_KC / 32; ++kk) {
                                 // (p, q, kk) is the first product of its order o = p + q iff kk == 0 and p == max(0, o - 2)
                                 const bool first_of_order = kk == 0 && p == ((p + q) > 2 ? (p + q) - 2 : 0);
-                                umma_i8(tmem_base + (uint32_t)((p + q) * GT_N),
-                                        da0 + (uint64_t)((p * GT_PLANE_BYTES + kk * 32) >> 4),
-                                        db0 + (uint64_t)((q * GT_B_BYTES + kk * 32) >> 4), GT_IDESC,
-                                        first_of_order ? not_first : 1u);
+                                if (A_TMEM)
+                                    umma_i8_ts(tmem_base + (uint32_t)((p + q) * GT_N), a_tm + (uint32_t)(p * 32 + kk * 8),
+                                               db0 + (uint64_t)((q * GT_B_BYTES + kk * 32) >> 4), GT_IDESC,
+                                               first_of_order ? not_first : 1u);
+                                else
+                                    umma_i8(tmem_base + (uint32_t)((p + q) * GT_N),
+                                            da0 + (uint64_t)((p * GT_PLANE_BYTES + kk * 32) >> 4),
+                                            db0 + (uint64_t)((q * GT_B_BYTES + kk * 32) >> 4), GT_IDESC,
+                                            first_of_order ? not_first : 1u);
                             }
                         }
                     }
@@ -214,13 +232,18 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
             }
         }
     } else {
-        // ===== flush: thread = output row; the five exact integer sums packed into two 64-bit words =====
+        // ===== flush: the five exact integer sums of an entry packed into two 64-bit words.  A CTA holds one flush period
+        // (the host sizes the k-slices so), so when the accumulators are complete the operand stages are idle: the rows
+        // (thread = TMEM lane = output row) go through shared memory and leave as COALESCED 64-bit reductions, a warp
+        // covering 32 consecutive columns of one row -- with thread = row every lane hit its own 32-byte sector and the
+        // 570 M scattered reductions of a step cost ~12 ms =====
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int grow = I * GT_M + row;
+        constexpr int FL_STRIDE = GT_N * 16 + 16;   // bytes per staged row; odd multiple of 16: no bank conflicts
         for (int64_t f = 0; f < n_flush; ++f) {
             mbar_wait(tfull, (uint32_t)(f & 1), err_flag);
             tc_fence_after();
+            const bool staged = n_flush == 1;
 #pragma unroll 1
             for (int half = 0; half < GT_N / 32; ++half) {
                 unsigned long long lo[32], hi[32];
@@ -240,12 +263,37 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
                             hi[c] += (unsigned long long)r[c] << (8 * (o - 2));
                     }
                 }
+                if (staged) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int gcol = J * GT_N + half * 32 + c;
-                    if (grow < H && gcol < H && gcol >= grow && (lo[c] | hi[c]) != 0ull) {
-                        atomicAdd(gram_lo + (int64_t)grow * H + gcol, lo[c]);
-                        atomicAdd(gram_hi + (int64_t)grow * H + gcol, hi[c]);
+                    for (int c = 0; c < 32; ++c)
+                        *reinterpret_cast<ulonglong2 *>(smem + (size_t)row * FL_STRIDE + (size_t)(half * 32 + c) * 16) =
+                            make_ulonglong2(lo[c], hi[c]);
+                } else {
+                    const int grow = I * GT_M + row;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int gcol = J * GT_N + half * 32 + c;
+                        if (grow < H && gcol < H && gcol >= grow && (lo[c] | hi[c]) != 0ull) {
+                            atomicAdd(gram_lo + (int64_t)grow * H + gcol, lo[c]);
+                            atomicAdd(gram_hi + (int64_t)grow * H + gcol, hi[c]);
+                        }
+                    }
+                }
+            }
+            if (staged) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // the four flush warps
+                for (int r2 = warp - 2; r2 < GT_M; r2 += 4) {
+                    const int grow = I * GT_M + r2;
+                    if (grow >= H)
+                        break;
+#pragma unroll
+                    for (int cc = lane; cc < GT_N; cc += 32) {
+                        const int gcol = J * GT_N + cc;
+                        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(smem + (size_t)r2 * FL_STRIDE + (size_t)cc * 16);
+                        if (gcol < H && gcol >= grow && (v.x | v.y) != 0ull) {
+                            atomicAdd(gram_lo + (int64_t)grow * H + gcol, v.x);
+                            atomicAdd(gram_hi + (int64_t)grow * H + gcol, v.y);
+                        }
                     }
                 }
             }
@@ -269,8 +317,12 @@ k_gram_tc(const unsigned char *__restrict__ img, int64_t n_chunks, int n_gt, int
 // cluster instead of once per CTA (3x less).  A stage may be overwritten when every CTA it is multicast INTO has
 // finished reading it: the MMA-completion arrival is multicast to the `empty` barriers of the row- and column-mates.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int GT_CL_R = 2, GT_CL_C = 4, GT_CL = GT_CL_R * GT_CL_C;
-constexpr int GT_SLICE = 4096;   // 32 operand rows of one plane
+#ifndef CB200_GRAM_CL_R
+#define CB200_GRAM_CL_R 1
+#endif
+constexpr int GT_CL_R = CB200_GRAM_CL_R, GT_CL_C = 2 * GT_CL_R, GT_CL = GT_CL_R * GT_CL_C;   // square super tile: R x 128 = C x 64
+constexpr int GT_A_SLICE = GT_PLANE_BYTES / GT_CL_C;   // the part of an A plane CTA (r, c) fetches for its row-mates
+constexpr int GT_B_SLICE = GT_B_BYTES / GT_CL_R;       // the part of a B half-plane it fetches for its column-mates
 
 __global__ void __cluster_dims__(GT_CL, 1, 1) __launch_bounds__(GT_THREADS, 1)
 k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, int H,
@@ -297,7 +349,10 @@ k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, 
     const int I = GT_CL_R * SI + r, J = GT_CL_C * SJ + c;
     const int gtB = J / 2, halfB = J & 1;
     const uint16_t row_mask = (uint16_t)(((1u << GT_CL_C) - 1u) << (r * GT_CL_C));      // CTAs that share my A tile
-    const uint16_t col_mask = (uint16_t)((1u << c) | (1u << (GT_CL_C + c)));            // CTAs that share my B tile
+    uint16_t col_mask = 0;                                                              // CTAs that share my B tile
+#pragma unroll
+    for (int rr = 0; rr < GT_CL_R; ++rr)
+        col_mask |= (uint16_t)(1u << (rr * GT_CL_C + c));
     const int64_t per = (n_chunks + gridDim.y - 1) / gridDim.y;
     const int64_t kc0 = (int64_t)blockIdx.y * per;
     const int64_t kc1 = kc0 + per < n_chunks ? kc0 + per : n_chunks;
@@ -328,16 +383,16 @@ k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, 
                 const int s = (int)(t % GT_STAGES);
                 const uint32_t ph = (uint32_t)((t / GT_STAGES) & 1);
                 mbar_wait(empty + s, ph ^ 1u, err_flag);       // everyone I multicast into has released the stage
-                mbar_expect_tx(full + s, GT_STAGE_BYTES);      // 4 x 12 KB of A + 2 x 12 KB of B will land here
+                mbar_expect_tx(full + s, GT_STAGE_BYTES);      // the row-mates' parts of A and the column-mates' parts of B land here
                 unsigned char *st = smem + (size_t)s * GT_STAGE_BYTES;
-                const unsigned char *a = img + ((size_t)I * n_chunks + (kc0 + t)) * GT_TILE_BYTES + (size_t)c * GT_SLICE;
+                const unsigned char *a = img + ((size_t)I * n_chunks + (kc0 + t)) * GT_TILE_BYTES + (size_t)c * GT_A_SLICE;
                 const unsigned char *b = img + ((size_t)gtB * n_chunks + (kc0 + t)) * GT_TILE_BYTES + halfB * GT_B_BYTES +
-                                         (size_t)r * GT_SLICE;
+                                         (size_t)r * GT_B_SLICE;
 #pragma unroll
                 for (int p = 0; p < GT_PLANES; ++p) {
-                    bulk_g2s_multicast(st + p * GT_PLANE_BYTES + c * GT_SLICE, a + (size_t)p * GT_PLANE_BYTES, GT_SLICE, full + s,
+                    bulk_g2s_multicast(st + p * GT_PLANE_BYTES + c * GT_A_SLICE, a + (size_t)p * GT_PLANE_BYTES, GT_A_SLICE, full + s,
                                        row_mask);
-                    bulk_g2s_multicast(st + GT_TILE_BYTES + p * GT_B_BYTES + r * GT_SLICE, b + (size_t)p * GT_PLANE_BYTES, GT_SLICE,
+                    bulk_g2s_multicast(st + GT_TILE_BYTES + p * GT_B_BYTES + r * GT_B_SLICE, b + (size_t)p * GT_PLANE_BYTES, GT_B_SLICE,
                                        full + s, col_mask);
                 }
             }
@@ -361,6 +416,13 @@ k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, 
                     // descriptor constructions per MMA cost more than the 32 cycles the MMA keeps the tensor pipe busy)
                     const uint64_t da0 = make_desc(sa), db0 = make_desc(sb);
                     const uint32_t not_first = t != t0 ? 1u : 0u;   // first chunk of a flush period overwrites
+                    // A planes: shared -> tensor memory (12 copies, in issue order with the MMAs), two buffers behind the accumulators
+                    const uint32_t a_tm = tmem_base + GT_ORDERS * GT_N + (uint32_t)(t & 1) * (GT_PLANES * 32);
+#pragma unroll
+                    for (int p = 0; p < GT_PLANES; ++p)
+#pragma unroll
+                        for (int kk = 0; kk < GT_KC / 32; ++kk)
+                            tmem_cp_128x256b(a_tm + (uint32_t)(p * 32 + kk * 8), da0 + (uint64_t)((p * GT_PLANE_BYTES + kk * 32) >> 4));
 #pragma unroll
                     for (int p = 0; p < GT_PLANES; ++p) {
 #pragma unroll
@@ -369,10 +431,9 @@ k_gram_tc_cl(const unsigned char *__restrict__ img, int64_t n_chunks, int n_st, 
                             for (int kk = 0; kk < GT_KC / 32; ++kk) {
                                 // (p, q, kk) is the first product of its order o = p + q iff kk == 0 and p == max(0, o - 2)
                                 const bool first_of_order = kk == 0 && p == ((p + q) > 2 ? (p + q) - 2 : 0);
-                                umma_i8(tmem_base + (uint32_t)((p + q) * GT_N),
-                                        da0 + (uint64_t)((p * GT_PLANE_BYTES + kk * 32) >> 4),
-                                        db0 + (uint64_t)((q * GT_B_BYTES + kk * 32) >> 4), GT_IDESC,
-                                        first_of_order ? not_first : 1u);
+                                umma_i8_ts(tmem_base + (uint32_t)((p + q) * GT_N), a_tm + (uint32_t)(p * 32 + kk * 8),
+                                           db0 + (uint64_t)((q * GT_B_BYTES + kk * 32) >> 4), GT_IDESC,
+                                           first_of_order ? not_first : 1u);
                             }
                         }
                     }
@@ -468,36 +529,60 @@ int cb200_gram_tc(cb200_ctx *ctx, int nb, int *used)
     int n_pairs = 0;
     for (int i = 0; i < n_gt; ++i)
         n_pairs += n_gn - 2 * i;
-    // enough CTAs to fill the machine a few times, but at least ~32 chunks per CTA
-    int64_t ksplit = (6LL * ctx->num_sms + n_pairs - 1) / n_pairs;
+    // k-slices of one flush period (80 chunks): the CTAs that run at the same time then work on the SAME slice of cells for
+    // different tile pairs (grid x = pair runs fastest), and the digit planes of that slice -- 16 gene tiles x 80 chunks x
+    // 48 KB = 61 MB -- stay in the 126 MB L2 while all 272 pairs pass over them.  With 4 long slices every CTA streamed
+    // its own part of the 7.8 GB image and the kernel read 111 GB from DRAM (14 passes); CB200_GRAM_SLICE overrides
+    int64_t slice_chunks = GT_FLUSH_CHUNKS;
+    if (const char *senv = getenv("CB200_GRAM_SLICE"))
+        if (atoi(senv) > 0)
+            slice_chunks = atoi(senv);
+    int64_t ksplit = (n_chunks + slice_chunks - 1) / slice_chunks;
     const int64_t max_split = (n_chunks + 31) / 32;
     if (ksplit > max_split)
         ksplit = max_split;
+    if (ksplit > 65535)
+        ksplit = 65535;
     if (ksplit < 1)
         ksplit = 1;
     const size_t smem = (size_t)GT_STAGES * GT_STAGE_BYTES + (2 * GT_STAGES + 2) * 8 + 16;
-    CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
     CB_TRACE("gram_tc: img launched");
     unsigned long long *glo = reinterpret_cast<unsigned long long *>(ctx->gram.p);
     const char *genv = getenv("CB200_GRAM_CLUSTER");
-    const bool use_cluster = !(genv != nullptr && strcmp(genv, "0") == 0) && n_chunks >= 64;
+    const bool use_cluster = genv != nullptr && strcmp(genv, "1") == 0 && n_chunks >= 64;   // measured slower: opt-in
     if (use_cluster) {
-        // 8-CTA clusters with multicast operand loads; enough k-slices to fill the 18 cluster slots a few times
+        // clusters with multicast operand loads.  k-slices: the split that minimises (waves of clusters) x (chunks per
+        // slice + the cost of one flush, ~24 chunks), so that the last wave is full
         const int n_sp = n_st * (n_st + 1) / 2;
-        int64_t ks = (3LL * (ctx->num_sms / GT_CL) + n_sp - 1) / n_sp;
-        if (ks > max_split)
-            ks = max_split;
-        if (ks < 1)
-            ks = 1;
+        const int slots = ctx->num_sms / GT_CL;
+        int64_t ks = 1;
+        double best = 1e300;
+        for (int64_t cand = 1; cand <= max_split && cand <= 64; ++cand) {
+            const int64_t waves = (n_sp * cand + slots - 1) / slots;
+            const double cost = (double)waves * ((double)((n_chunks + cand - 1) / cand) + 24.0);
+            if (cost < best) {
+                best = cost;
+                ks = cand;
+            }
+        }
         CB_CUDA(ctx, cudaFuncSetAttribute(k_gram_tc_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 cgrid((unsigned)(n_sp * GT_CL), (unsigned)ks);
         k_gram_tc_cl<<<cgrid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_st, H, glo, glo + (size_t)H * H,
                                                               ctx->flag.p + 3);
     } else {
         dim3 grid((unsigned)n_pairs, (unsigned)ksplit);
-        k_gram_tc<<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, glo, glo + (size_t)H * H,
-                                                           ctx->flag.p + 3);
+        // CB200_GRAM_A=tmem: A planes copied to tensor memory (tcgen05.cp) and read from there -- measured 1.3 ms slower than
+        // both operands from shared memory once the flush was fixed (27.0 vs 25.6 ms for the stage at cfg3)
+        const char *aenv = getenv("CB200_GRAM_A");
+        if (!(aenv != nullptr && strcmp(aenv, "tmem") == 0))
+            k_gram_tc<false><<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, glo,
+                                                                      glo + (size_t)H * H, ctx->flag.p + 3);
+        else
+            k_gram_tc<true><<<grid, GT_THREADS, smem, ctx->stream>>>(ctx->gram_img.p, n_chunks, n_gt, H, glo,
+                                                                     glo + (size_t)H * H, ctx->flag.p + 3);
     }
     CB_LAUNCH(ctx);
     int h_flag = 0;

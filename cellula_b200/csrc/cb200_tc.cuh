@@ -241,4 +241,21 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T, unsigned 8-bit inputs: A from tensor memory (row = lane, four K elements per column)
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory -> tensor memory copy of a 128-row x 32-byte operand slice (tcgen05.cp.128x256b): same matrix descriptor as
+// the MMA would use for the slice; executes in issue order with the tcgen05.mma of the issuing thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t desc_src)
+{
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(desc_src) : "memory");
+}
+
 }  // namespace cb200tc
