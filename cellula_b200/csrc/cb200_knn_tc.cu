@@ -384,6 +384,29 @@ k_knn_tc_prep(const double *__restrict__ E, int64_t lde, int d, double scale, co
     }
 }
 
+// Tile bounds made monotone inside every cluster (thread = cluster): hi'[t] = max hi[<= t], lo'[t] = min lo[>= t].
+// The counting sort orders by rho BIN, so a bin that straddles tiles can leave hi[t] > hi[t + 1]; the widened
+// bounds still contain every point of the tile, and with both sequences non-decreasing the tiles a query row can
+// reach form ONE interval of the cluster -- the producer of the tile kernel finds it by binary search.
+__global__ void k_knn_tc_monotone(int C, const int32_t *__restrict__ cl_tile_begin, float *__restrict__ tile_lo,
+                                  float *__restrict__ tile_hi)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C)
+        return;
+    const int t0 = cl_tile_begin[c], t1 = cl_tile_begin[c + 1];
+    float m = -INFINITY;
+    for (int t = t0; t < t1; ++t) {
+        m = fmaxf(m, tile_hi[t]);
+        tile_hi[t] = m;
+    }
+    m = INFINITY;
+    for (int t = t1 - 1; t >= t0; --t) {
+        m = fminf(m, tile_lo[t]);
+        tile_lo[t] = m;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------
@@ -440,9 +463,11 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                const int32_t *__restrict__ cl_tile_begin, const unsigned int *__restrict__ cl_rhomax,
                const float *__restrict__ tile_lo, const float *__restrict__ tile_hi, float key_unscale, int cand_stride,
                int32_t *__restrict__ cand_idx, float *__restrict__ cand_tau, float *__restrict__ cand_err, float err_rel,
-               int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done, long long *__restrict__ dbg)
+               int *__restrict__ err_flag, unsigned long long *__restrict__ tiles_done, int seed_max,
+               long long *__restrict__ dbg)
 {
     using L = TcSmem<KP, STAGES, QCAP, NQB>;
+    static_assert(TC_SCAN_SETS == 3, "the seed exchange below is written for three scanner sets");
     // CB200_KNN_TIMELINE (debugging aid): the CTA in the middle of the grid records (tag, clock) pairs
     // per role into dbg[role][TL_CAP][2]
     constexpr int TL_CAP = 4096;
@@ -465,6 +490,14 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             ++tl_n;
         }
     };
+    auto TLV = [&](int role, long long tag, long long val) {   // a value instead of the clock
+        if (tl_on && tl_n < TL_CAP) {
+            long long *e = dbg + ((size_t)role * TL_CAP + tl_n) * 2;
+            e[0] = tag;
+            e[1] = val;
+            ++tl_n;
+        }
+    };
     constexpr uint32_t TC_TMEM_COLS = 512;  // 3 accumulators of 128 columns + 2 query-operand buffers of 64
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *q_img = smem + L::q_img;                                // 32 KB transit: Q hi | Q lo of the visit being built
@@ -483,6 +516,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     volatile int *q_cluster = reinterpret_cast<volatile int *>(qfree + 2);  // [2]
     uint64_t *pfreq = qfree + 3;                 // producer -> builders: run the cluster prefilter
     uint64_t *pfdone = qfree + 4;                // builders -> producer
+    uint64_t *seeded = qfree + 5;                // scanners -> producer: the seed thresholds are published
     volatile float *pf_reach = reinterpret_cast<volatile float *>(smem + L::pf_reach);
     volatile unsigned int *pf_words = reinterpret_cast<volatile unsigned int *>(smem + L::pf_words);
     volatile float *thr_sh = reinterpret_cast<volatile float *>(smem + L::thr_sh);
@@ -520,6 +554,7 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         }
         mbar_init(pfreq, 1);
         mbar_init(pfdone, 4);
+        mbar_init(seeded, TC_SCAN_SETS * 4);   // one arrival per scanner warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0)
@@ -528,6 +563,36 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // Threshold seed (pass A).  Streaming a top-KP selection over n references in arbitrary order costs about
+    // KP (1 + ln(n / KP)) heap insertions per row, and most of them fall on the first tiles, where every column
+    // still beats the threshold (measured at cfg3: the first 58 of ~490 tiles took 45 % of a CTA's time, all of
+    // it scanners waiting for the inserters).  So the tiles [sb, se) of the home cluster first run through the
+    // tensor core in a cheap mode: a scanner thread only keeps 32 running maxima of T, one per column residue
+    // class mod 32 -- no compare against a threshold, no ring, no heap.  The 3 x 32 class maxima of a row belong
+    // to DISTINCT references, so their KP-th largest is a lower bound of the row's KP-th best T: a valid
+    // threshold, near the 39th best of the seed set for KP = 32.  The regular pass then starts with ~40
+    // insertions per row instead of several hundred.  Everything the seed rejects has T <= seed <= final
+    // threshold, so the margin proof of k_knn_rerank is unchanged.  The range is a pure function of the tile's
+    // position: producer, scanners and inserters compute it on their own.  seed_max < 0: the first |seed_max|
+    // tiles of the cluster (its core) instead of a window around the query tile's own position.
+    auto seed_range = [&](int &sb, int &se, int &home_j) {
+        const int64_t nv = nq - ql0 < TC_M ? nq - ql0 : TC_M;
+        const int64_t mid = ql0 + nv / 2;
+        home_j = cl[qlist[mid]];
+        const int pt = cl_tile_begin[home_j], pte = cl_tile_begin[home_j + 1];
+        const int smax_t = KP > 96 ? 0 : (seed_max < 0 ? -seed_max : seed_max);
+        sb = pt;
+        se = smax_t > 0 ? pte : pt;
+        if (se - sb > smax_t) {
+            if (seed_max > 0) {   // a window of seed_max tiles around the query tile's own position
+                const int own = qpos[mid] >> 7;
+                sb = own - smax_t / 2;
+                sb = sb < pt ? pt : (sb > pte - smax_t ? pte - smax_t : sb);
+            }
+            se = sb + smax_t;
+        }
+    };
 
     // need[j] (bit j of the result words) = some row can still reach cluster j.  Lane = 4 rows (g4, reach4);
     // every lane streams its rows of the distance table (128-bit loads, 4 clusters each), the minimum
@@ -614,17 +679,19 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         int opos = 0;                  // next position of `order` to look at
         unsigned ochunk = 0u;          // order[32 * (opos / 32) + lane]
         uint32_t seq = 0;
-        int t = 0, te = 0, tb32 = 0, cur_j = -1;
-        int req_visit = -1;           // cluster visits requested from the builders so far, minus one
-        int cur_visit = -1;           // visit of the cluster being walked (-1: none)
-        bool cur_issued = false;      // the current visit has staged a tile
-        bool plan_valid = false, no_more = false;
-        int plan_j = -1, plan_t = 0, plan_te = 0;
-        float plan_crmax = 0.f, plan_dq[4] = {0.f, 0.f, 0.f, 0.f};
-        float blo = 0.f, bhi = 0.f;   // bounds of tile tb32 + lane
+        int req_visit = -1;            // cluster visits requested from the builders so far, minus one
+        // current cluster: tiles [.., te), walked in blocks of 32 (lane = tile bt0 + lane)
+        int cur_j = -1, te = 0, bt0 = 0;
+        int cur_visit = -1;            // visit of the cluster being walked (-1: none)
+        bool cur_issued = false;       // the current visit has staged a tile
         float crmax = 0.f;
-        unsigned cm = 0u;             // tiles of the current block that pass the coarse test (bit = tile - tb32)
-        bool cm_valid = false;
+        float blo = INFINITY, bhi = INFINITY;     // (monotone) bounds of tile bt0 + lane; +inf past the cluster
+        float nblo = INFINITY, nbhi = INFINITY;   // the same for the next block of the cluster, loaded a block ahead
+        unsigned mask = 0u;            // tiles of the block still to stage
+        // the next cluster, looked up ahead of its use: 0 nothing, 1 its loads are in flight, 2 confirmed (image requested)
+        int pl_state = 0, pl_j = -1, pl_t = 0, pl_te = 0;
+        float pl_crmax = 0.f, pl_dq[4] = {0.f, 0.f, 0.f, 0.f}, pl_blo = INFINITY, pl_bhi = INFINITY;
+        bool no_more = false;
 
         auto refresh = [&]() {
             // how far every row can still find a candidate: canonical T = -0.5 d^2, rounded up
@@ -653,11 +720,6 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             for (int w = 0; w < NW; ++w)
                 words[w] = w * 32 < C ? pf_words[w] : 0u;
         };
-        // Looks for the next cluster (in `order`) some row can still reach, loads its per-row distances and
-        // asks the builders for the query image relative to its centre.  Runs AHEAD: it is called right
-        // after the first tile of the current cluster has been staged, so the loads and the image build
-        // hide behind the tiles in flight.  (A cluster planned with the thresholds of that moment may
-        // turn out to need no tile later: the visit is then skipped and its image buffer released here.)
         auto post_request = [&](int j) {
             ++req_visit;
             if (lane == 0) {
@@ -669,7 +731,37 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 mbar_arrive(qreq + b);
             }
         };
-        auto make_plan = [&]() {
+        // The tiles of the current block some row can reach, all 32 at once.  Row u needs tile t iff
+        // hi'[t] >= lo[u] and lo'[t] <= hi[u]; both bound sequences are non-decreasing (k_knn_tc_monotone), so the
+        // row's tiles are [#(hi' < lo[u]), #(lo' <= hi[u])) -- two binary searches over the lanes' bounds (shuffles
+        // with a per-lane source), four rows per lane, one OR-reduction over the warp.
+        auto block_mask = [&]() -> unsigned {
+            refresh();
+            unsigned m = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int a = 0, b = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const float va = __shfl_sync(0xffffffffu, bhi, a + step - 1);
+                    const float vb = __shfl_sync(0xffffffffu, blo, b + step - 1);
+                    a += (va < lo[u]) ? step : 0;
+                    b += (vb <= hi[u]) ? step : 0;
+                }
+                const float va = __shfl_sync(0xffffffffu, bhi, 31);
+                const float vb = __shfl_sync(0xffffffffu, blo, 31);
+                a += (a == 31 && va < lo[u]) ? 1 : 0;
+                b += (b == 31 && vb <= hi[u]) ? 1 : 0;
+                if (b > a)   // a < 32 here
+                    m |= (b >= 32 ? 0xffffffffu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
+            }
+            m = __reduce_or_sync(0xffffffffu, m);
+            return m & __ballot_sync(0xffffffffu, bt0 + lane < te);
+        };
+        // Next position of `order` whose cluster is still marked: issues the loads of everything the visit will
+        // need (per-row centre distances, tile range, bounds of its first block) and returns without touching
+        // them -- confirm_plan() consumes them one tile later, so their latency hides behind the tiles in flight.
+        auto pick_candidate = [&]() -> bool {
             while (opos < C) {
                 if (opos == 1 && !prefiltered) {   // the home cluster is done: thresholds exist now
                     prefiltered = true;
@@ -685,114 +777,126 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 const int pt = cl_tile_begin[j], pte = cl_tile_begin[j + 1];
                 if (pt >= pte)
                     continue;
-                const float pcr = __uint_as_float(cl_rhomax[j]) * (1.f + EPS);
-                bool need = false;
+                pl_j = j;
+                pl_t = pt;
+                pl_te = pte;
+                pl_crmax = __uint_as_float(cl_rhomax[j]) * (1.f + EPS);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    plan_dq[u] = g[u] >= 0 ? dqc[(size_t)g[u] * C + j] : 0.f;
-                    need |= g[u] >= 0 && plan_dq[u] * (1.f - EPS) - reach[u] <= pcr;
-                }
-                if (!__any_sync(0xffffffffu, need))
-                    continue;
+                for (int u = 0; u < 4; ++u)
+                    pl_dq[u] = g[u] >= 0 ? dqc[(size_t)g[u] * C + j] : 0.f;
+                pl_blo = pt + lane < pte ? tile_lo[pt + lane] : INFINITY;
+                pl_bhi = pt + lane < pte ? tile_hi[pt + lane] : INFINITY;
+                pl_state = 1;
+                return true;
+            }
+            no_more = true;
+            return false;
+        };
+        auto confirm_plan = [&]() {
+            bool need = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                need |= g[u] >= 0 && pl_dq[u] * (1.f - EPS) - reach[u] <= pl_crmax;
+            if (__any_sync(0xffffffffu, need)) {
                 // with two image buffers the build is requested now, ahead of the first tile; with one buffer
                 // it waits for that tile (an early request for a visit that ends up without tiles could
                 // only be released after the MMA issuer has moved on -- which needs the next tile)
                 if (NQB == 2)
-                    post_request(j);
-                plan_valid = true;
-                plan_j = j;
-                plan_t = pt;
-                plan_te = pte;
-                plan_crmax = pcr;
-                return;
+                    post_request(pl_j);
+                pl_state = 2;
+            } else {
+                pl_state = 0;
             }
-            no_more = true;
         };
-        // advances (t, te, cur_j, ...) to the next tile some row can reach; false when nothing is left
+        // between two tiles: one step of the look-ahead, never waiting on a load issued in the same call
+        auto advance_plan = [&]() {
+            if (pl_state == 1)
+                confirm_plan();
+            else if (pl_state == 0 && !no_more && (opos != 1 || prefiltered))
+                pick_candidate();
+        };
+        // moves to the next tile some row can reach (block, cluster) -> next_t; false when nothing is left
+        int next_t = 0, cur_t0 = 0;
         auto find_next = [&]() -> bool {
-            while (true) {
-                if (t >= te) {  // the current cluster is exhausted: adopt the planned one
-                    if (cur_visit >= 0 && !cur_issued && lane == 0) {
-                        // skipped visit: nobody else releases its image buffer.  Only once the image is
-                        // built: an earlier arrival would complete the release the builders are still
-                        // waiting for from the previous user of the buffer.
-                        mbar_wait(qfull + (cur_visit % NQB), (uint32_t)((cur_visit / NQB) & 1), err_flag);
-                        mbar_arrive(qfree + (cur_visit % NQB));
+            while (mask == 0u) {
+                if (bt0 + 32 < te) {   // next block of the cluster (its bounds were loaded a block ago)
+                    bt0 += 32;
+                    blo = nblo;
+                    bhi = nbhi;
+                } else {
+                    if (cur_visit >= 0 && !cur_issued) {
+                        // The image of this visit was requested ahead (two buffers), but by now no row reaches any of
+                        // its tiles.  One tile is staged anyway: the MMA issuer then releases the image buffers in
+                        // visit order like for every other visit.  (Releasing a skipped visit from here needs its
+                        // image to be built first, and the builders may be waiting for the buffer of the visit before
+                        // the last, which the MMA issuer only frees when the NEXT visit starts: two skipped visits in
+                        // a row would deadlock.)  An extra tile costs ~1 k cycles and changes nothing in the result.
+                        next_t = cur_t0;
+                        bt0 = te;
+                        return true;
                     }
                     cur_visit = -1;
-                    if (!plan_valid) {
-                        if (no_more)
-                            return false;
-                        make_plan();
-                        if (!plan_valid)
+                    while (pl_state != 2) {
+                        if (pl_state == 1)
+                            confirm_plan();
+                        else if (!pick_candidate())
                             return false;
                     }
-                    cur_j = plan_j;
-                    t = plan_t;
-                    te = plan_te;
-                    crmax = plan_crmax;
+                    cur_j = pl_j;
+                    te = pl_te;
+                    bt0 = pl_t;
+                    cur_t0 = pl_t;
+                    crmax = pl_crmax;
+                    blo = pl_blo;
+                    bhi = pl_bhi;
                     cur_visit = NQB == 2 ? req_visit : -1;   // one buffer: requested with the first tile
                     cur_issued = false;
-                    plan_valid = false;
+                    pl_state = 0;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        dq[u] = plan_dq[u];
+                        dq[u] = pl_dq[u];
                         if (g[u] >= 0) {
                             dlo[u] = dq[u] * (1.f - EPS);
                             dhi[u] = dq[u] * (1.f + EPS);
-                            lo[u] = dlo[u] - reach[u];
-                            hi[u] = dhi[u] + reach[u];
                         }
                     }
-                    tb32 = t - 32;  // forces a load of the tile bounds below
                 }
-                if (t >= tb32 + 32) {
-                    tb32 = t;
-                    const int tt = t + lane;
-                    blo = tt < te ? tile_lo[tt] : INFINITY;
-                    bhi = tt < te ? tile_hi[tt] : -INFINITY;
-                    cm_valid = false;
-                }
-                // coarse test of the 32 tiles of the block at once (lane = tile) against the hull of the rows'
-                // intervals -- kept until the thresholds are refreshed or the block changes -- then the exact
-                // per-row test of its survivors, one at a time, up to the first tile that is needed
-                if (!cm_valid) {
-                    float mlo = fminf(fminf(lo[0], lo[1]), fminf(lo[2], lo[3]));
-                    float mhi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        mlo = fminf(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
-                        mhi = fmaxf(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
-                    }
-                    cm = __ballot_sync(0xffffffffu, tb32 + lane >= t && mlo <= bhi && mhi >= blo);
-                    cm_valid = true;
-                }
-                cm &= 0xffffffffu << (t - tb32);   // t - tb32 in [0, 32): tiles before t are done
-                bool found = false;
-                while (cm != 0u) {
-                    const int off = __ffs(cm) - 1;
-                    const float a = __shfl_sync(0xffffffffu, blo, off);
-                    const float b = __shfl_sync(0xffffffffu, bhi, off);
-                    bool need = false;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        need |= (lo[u] <= b) && (hi[u] >= a);
-                    if (__any_sync(0xffffffffu, need)) {
-                        t = tb32 + off;
-                        found = true;
-                        break;
-                    }
-                    cm &= cm - 1u;
-                }
-                if (found)
-                    return true;
-                t = tb32 + 32 < te ? tb32 + 32 : te;
+                const int nt = bt0 + 32 + lane;
+                nblo = nt < te ? tile_lo[nt] : INFINITY;
+                nbhi = nt < te ? tile_hi[nt] : INFINITY;
+                mask = block_mask();
             }
+            next_t = bt0 + __ffs(mask) - 1;
+            mask &= mask - 1u;
+            return true;
         };
 
         TL(0, -1);
-        bool have = find_next();
-        while (have) {
+        {   // pass A: the seed tiles of the home cluster, all of them, no tests
+            int sb, se, hj;
+            seed_range(sb, se, hj);
+            if (se > sb) {
+                post_request(hj);
+                for (int ts = sb; ts < se; ++ts) {
+                    if (lane == 0) {
+                        const int s = (int)(seq % STAGES);
+                        mbar_wait(empty + s, (uint32_t)((seq / STAGES) & 1) ^ 1u, err_flag);
+                        seq_tile[seq % TC_RING] = ts;
+                        seq_meta[seq % TC_RING] = hj | ((ts == sb ? 1 : 0) << 10) | (req_visit << 11);
+                        mbar_expect_tx(full + s, TC_TILE_BYTES);
+                        bulk_g2s(r_img + (size_t)s * TC_TILE_BYTES, img + (int64_t)ts * TC_TILE_BYTES, TC_TILE_BYTES, full + s);
+                        TL(0, ((long long)ts << 8) | 2 | (ts == sb ? 16 : 0));
+                    }
+                    __syncwarp();
+                    ++seq;
+                }
+                if (lane == 0)
+                    mbar_wait(seeded, 0u, err_flag);   // the regular pass is planned with the seeded thresholds
+                __syncwarp();
+            }
+        }
+        while (find_next()) {
+            const int t = next_t;
             if (lane == 0)
                 TL(0, ((long long)t << 8) | 1);   // found
             const bool first = !cur_issued;
@@ -818,17 +922,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 TL(0, ((long long)t << 8) | 2 | (first ? 16 : 0));   // issued
             }
             __syncwarp();
-            ++t;
             ++seq;
-            // the thresholds move fast while the first tiles of the sequence are scanned, slowly afterwards: the rows'
-            // intervals are refreshed after every tile at first, then after every second one
-            if (seq < 96u || (seq & 1u) == 0u) {
-                refresh();
-                cm_valid = false;
-            }
-            if (!plan_valid && !no_more && (opos != 1 || prefiltered))
-                make_plan();
-            have = find_next();
+            advance_plan();
         }
         // end of the sequence
         if (lane == 0) {
@@ -935,7 +1030,127 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
         int cur_j = -1;
         float off = 0.f;   // key offset of the current cluster: 0.5 |q - c_j|^2 (canonical T = T_j - off)
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (uint32_t seq = (uint32_t)set;; seq += TC_SCAN_SETS) {
+        uint32_t seq = (uint32_t)set;
+        {   // pass A (see seed_range): 32 running maxima per row, exchanged between the sets through the (still unused)
+            // heap arrays, minimum of the 32 published as the row's first threshold
+            int sb, se, hj;
+            seed_range(sb, se, hj);
+            if (se > sb) {
+                float gm[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    gm[i] = -INFINITY;
+                const int mypos = active ? qpos[myql] : -1;   // the query itself is not a neighbour
+                for (; seq < (uint32_t)(se - sb); seq += TC_SCAN_SETS) {
+                    const int a = (int)(seq % TC_ACC_STAGES);
+                    if (lane == 0 && quarter == 2)
+                        TL(2 + set, ((long long)seq << 8) | 1);
+                    mbar_wait(tfull + a, (uint32_t)((seq / TC_ACC_STAGES) & 1), err_flag);
+                    if (lane == 0 && quarter == 2)
+                        TL(2 + set, ((long long)seq << 8) | 2);
+                    tc_fence_after();
+                    const int t = sb + (int)seq;
+                    const uint32_t tcol = tbase + (uint32_t)(a * TC_N);
+                    const int selfcol = (mypos >> 7) == t ? (mypos & 127) : -1;
+                    uint32_t ra[16];   // 16 columns at a time: 16 + 32 live registers with the maxima (no spills here)
+#pragma unroll 1
+                    for (int ch = 0; ch < TC_N / 16; ++ch) {
+                        tmem_ld16_sync(tcol + (uint32_t)(ch * 16), ra);
+                        if ((selfcol >> 4) == ch) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                ra[i] = (i == (selfcol & 15)) ? 0xff800000u : ra[i];   // -inf
+                        }
+                        if (ch & 1) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                gm[16 + i] = fmaxf(gm[16 + i], __uint_as_float(ra[i]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                gm[i] = fmaxf(gm[i], __uint_as_float(ra[i]));
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(tempty + a);
+                    if (lane == 0 && quarter == 2)
+                        TL(2 + set, ((long long)seq << 8) | 3);
+                }
+                // The 96 class maxima of a row (32 per set) belong to 96 distinct references: their KP-th largest is a
+                // valid threshold (KP references beat or equal it).  Every thread sorts its 32 in registers (bitonic
+                // network, descending), the three sorted runs meet in shared memory -- the heap arrays and the rings,
+                // unused until the seed is out: the inserters wait for it -- and every thread ranks its own run
+                // against the other two.  With classes of m references the result sits near the
+                // 96 ln(96 / (96 - KP)) -th best of the seed set (KP = 32: the 39th).
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int l = i ^ jj;
+                            if (l > i) {
+                                const float x0 = gm[i], x1 = gm[l];
+                                const bool desc = (i & kk) == 0;   // descending overall
+                                gm[i] = desc ? fmaxf(x0, x1) : fminf(x0, x1);
+                                gm[l] = desc ? fminf(x0, x1) : fmaxf(x0, x1);
+                            }
+                        }
+                    }
+                }
+                float *X = reinterpret_cast<float *>(smem + L::hk) + row;   // [3][32][TC_M]
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    X[(set * 32 + i) * TC_M] = gm[i];
+                __syncwarp();   // bar.sync is the .aligned form: the warp must arrive converged (the loops above diverge per row)
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_SCAN_SETS * 128) : "memory");
+                if (KP <= 96) {
+                    // rank of every own value in the union = its index in the own run + the number of larger values in
+                    // the other two runs (binary searches; ties: the run of the lower set counts as larger), so the
+                    // ranks are a permutation of 0..95 and exactly one of the three threads of a row holds rank KP-1
+                    const int s1 = (set + 1) % TC_SCAN_SETS, s2 = (set + 2) % TC_SCAN_SETS;
+                    const float *X1 = X + s1 * 32 * TC_M, *X2 = X + s2 * 32 * TC_M;
+                    float m = 0.f;
+                    bool mine = false;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = gm[i];
+                        int c1 = 0, c2 = 0;
+#pragma unroll
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            const float w1 = X1[(c1 + step - 1) * TC_M], w2 = X2[(c2 + step - 1) * TC_M];
+                            c1 += (s1 < set ? w1 >= v : w1 > v) ? step : 0;
+                            c2 += (s2 < set ? w2 >= v : w2 > v) ? step : 0;
+                        }
+                        const float w1 = X1[31 * TC_M], w2 = X2[31 * TC_M];
+                        c1 += (c1 == 31 && (s1 < set ? w1 >= v : w1 > v)) ? 1 : 0;
+                        c2 += (c2 == 31 && (s2 < set ? w2 >= v : w2 > v)) ? 1 : 0;
+                        if (i + c1 + c2 == KP - 1) {
+                            m = v;
+                            mine = true;
+                        }
+                    }
+                    if (mine && active && m > -1e30f) {   // (fewer than KP real references in the seed tiles: no seed)
+                        const float dqh = mydq[hj];
+                        const float offh = 0.5f * dqh * dqh;
+                        // canonical T, a few ulps down: the KP references at or above m must pass `T > thr + off`
+                        thr_sh[row] = (m - offh) - ((fabsf(m) + offh) * 4.8e-7f + 1e-30f);   // strictly below, also at m = offh = 0
+                    }
+                }
+                __syncwarp();   // bar.sync is the .aligned form: the warp must arrive converged (the loops above diverge per row)
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_SCAN_SETS * 128) : "memory");
+                for (int e = 0; e < QCAP; ++e)   // the exchange overwrote the rings: empty again (parity of lap -1)
+                    ring[((size_t)set * QCAP + e) * TC_M + row] = make_uint2(0u, 0x80000000u);
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    mbar_arrive(seeded);
+                }
+            }
+        }
+        for (;; seq += TC_SCAN_SETS) {
             const int a = (int)(seq % TC_ACC_STAGES);
             if (lane == 0 && quarter == 2)
                 TL(2 + set, ((long long)seq << 8) | 1);
@@ -1015,9 +1230,13 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(tempty + a);
-            if (lane == 0 && quarter == 2)
+            if (lane == 0 && quarter == 2) {
                 TL(2 + set, ((long long)seq << 8) | 3);
+                TLV(2 + set, ((long long)seq << 8) | 6, (long long)tail);   // pushes of this row so far
+            }
         }
+        if (tl_on)   // pushes of every row (summed over the sets)
+            atomicAdd(reinterpret_cast<unsigned long long *>(dbg + ((size_t)6 * TL_CAP + row) * 2), (unsigned long long)tail);
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
@@ -1035,10 +1254,25 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             head[s2] = 0u;
             raddr[s2] = smem_u32(ring + (size_t)s2 * QCAP * TC_M + row);
         }
-        int cnt = 0;            // entries held; the heap is filled from the back, then heapified once
         float root = -FLT_MAX;
+        long long n_ins = 0;
         const int my_pos = ql0 + row < nq ? qpos[ql0 + row] : -1;   // sorted position of the query itself
         bool done_seen = false;
+        {   // the rings carry the scanners' seed exchange first (pass A): nothing to read before it is over
+            int sb, se, hj;
+            seed_range(sb, se, hj);
+            if (se > sb)
+                mbar_wait(seeded, 0u, err_flag);
+        }
+        // The heap starts FULL of placeholders (no reference, key = the seeded threshold, or -FLT_MAX without a
+        // seed): every insertion is the same sift-down from the root, and rows that reach KP real candidates at
+        // different moments never run a divergent heapify (measured: that serialised the inserter warps for
+        // ~100 k cycles per CTA once the seed spread the fill over many tiles).
+        root = ql0 + row < nq ? thr_sh[row] : FLT_MAX;
+        for (int e = 0; e < KP; ++e) {
+            mk[e * TC_M] = root;
+            mi[e * TC_M] = -1;
+        }
         while (true) {
             bool got = false;
 #pragma unroll
@@ -1057,37 +1291,8 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 const int pos = (int)(ey & ((1u << TC_POS_BITS) - 1u));
                 if (pos == my_pos)
                     continue;   // the query itself
-                if (cnt < KP) {
-                    const int e = KP - 1 - cnt;
-                    mk[e * TC_M] = val;
-                    mi[e * TC_M] = pos;
-                    if (++cnt == KP) {
-                        // heapify: Floyd, parents from the last one down
-                        for (int st = KP / 2 - 1; st >= 0; --st) {
-                            float v = mk[st * TC_M];
-                            int vp = mi[st * TC_M];
-                            int i = st;
-                            while (true) {
-                                const int l = 2 * i + 1;
-                                if (l >= KP)
-                                    break;
-                                const float kl = mk[l * TC_M];
-                                const float kr = (l + 1 < KP) ? mk[(l + 1) * TC_M] : FLT_MAX;
-                                const int c = kl <= kr ? l : l + 1;
-                                const float kc = fminf(kl, kr);
-                                if (v <= kc)
-                                    break;
-                                mk[i * TC_M] = kc;
-                                mi[i * TC_M] = mi[c * TC_M];
-                                i = c;
-                            }
-                            mk[i * TC_M] = v;
-                            mi[i * TC_M] = vp;
-                        }
-                        root = mk[0];
-                        thr_sh[row] = root;
-                    }
-                } else if (val > root) {
+                if (val > root) {
+                    ++n_ins;
                     int i = 0;
                     while (true) {  // sift the new value down from the root
                         const int l = 2 * i + 1;
@@ -1117,14 +1322,17 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                     __nanosleep(32);
             }
         }
-        // final: candidates (original indices, unsorted) and the row threshold in key space, unscaled:
-        // key = 0.5 d^2 = -T
+        // final: candidates (sorted positions, unsorted order, -1 where a placeholder survived) and the row
+        // threshold in key space, unscaled: key = 0.5 d^2 = -T.  Every reference that is not a candidate was
+        // pruned or rejected against a threshold <= root.
         const int64_t myql = ql0 + row;
+        if (tl_on)
+            dbg[((size_t)6 * TL_CAP + row) * 2 + 1] = n_ins;
         if (myql < nq) {
             int32_t *out = cand_idx + myql * (int64_t)cand_stride;
             for (int p = 0; p < cand_stride; ++p)
-                out[p] = (p < KP && p >= KP - cnt) ? mi[p * TC_M] : -1;   // sorted positions: k_knn_rerank maps them through perm
-            cand_tau[myql] = (cnt < KP) ? FLT_MAX : -root * key_unscale;
+                out[p] = p < KP ? mi[p * TC_M] : -1;   // k_knn_rerank maps the positions through perm
+            cand_tau[myql] = root == -FLT_MAX ? FLT_MAX : -root * key_unscale;
         }
     } else {
         // ===== builders: the query operand image relative to the centre of the cluster being visited,
@@ -1269,6 +1477,9 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
                                       (int)smem));
     const unsigned grid = (unsigned)((nq + TC_M - 1) / TC_M);
     const float key_unscale = (float)(1.0 / (scale * scale));
+    // tiles of the home cluster used for the threshold seed (0: off)
+    const char *seed_env = getenv("CB200_KNN_SEED");
+    const int seed_max = seed_env != nullptr ? atoi(seed_env) : 64;
     long long *dbg = nullptr;
     if (getenv("CB200_KNN_TIMELINE") != nullptr) {
         CB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&dbg), ((size_t)7 * 4096 * 2 + (size_t)grid * 4) * sizeof(long long)));
@@ -1279,7 +1490,7 @@ static int launch_tc(cb200_ctx *ctx, const double *E, int64_t lde, int d, double
         ctx->knn_cen.p,
         ctx->knn_dqc.p, ctx->knn_cl.p, ctx->knn_cl_order.p, ctx->knn_cl_tile_begin.p, ctx->knn_cl_rhomax.p,
         ctx->knn_tile_lo.p, ctx->knn_tile_hi.p, key_unscale, cand_stride, ctx->cand_idx.p, ctx->cand_tau.p,
-        ctx->cand_err.p, NPROD == 3 ? 4.6e-5f : 3.0e-4f, ctx->flag.p + 3, ctx->maxnrm.p + 3, dbg);
+        ctx->cand_err.p, NPROD == 3 ? 4.6e-5f : 3.0e-4f, ctx->flag.p + 3, ctx->maxnrm.p + 3, seed_max, dbg);
     CB_LAUNCH(ctx);
     if (dbg != nullptr) {   // dump the timeline of the middle CTA
         std::vector<long long> h((size_t)7 * 4096 * 2 + (size_t)grid * 4);   // role timelines of the middle CTA, then [start ns, end ns, tiles, SM] of every CTA
@@ -1422,6 +1633,9 @@ int cb200_knn_tiles_tc(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, 
                                                                   ctx->knn_cl.p, ctx->knn_cen.p, ctx->knn_img.p,
                                                                   ctx->knn_eperm.p, ctx->nrm2.p, ctx->maxnrm.p, ctx->knn_tile_lo.p,
                                                                   ctx->knn_tile_hi.p);
+    CB_LAUNCH(ctx);
+    k_knn_tc_monotone<<<(unsigned)((C + 127) / 128), 128, 0, ctx->stream>>>(C, ctx->knn_cl_tile_begin.p, ctx->knn_tile_lo.p,
+                                                                         ctx->knn_tile_hi.p);
     CB_LAUNCH(ctx);
     // the query list: the cells of [q_begin, q_end) in sorted order, with their sorted positions
     const unsigned gpos = (unsigned)((npos + 255) / 256);
