@@ -1170,11 +1170,19 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
             const int r0 = t * TC_N;
             const uint32_t tcol = tbase + (uint32_t)(a * TC_N);
             uint32_t r[32];
+            long long tl_ld = 0, tl_hit = 0, tl_nhit = 0, tl_c0 = 0, tl_c1 = 0;
+            const bool tl_me = tl_on && lane == 0 && quarter == 2;
 #pragma unroll 1
             for (int ch = 0; ch < TC_N / 32; ++ch) {
+                if (tl_me)
+                    tl_c0 = clock64();
                 tmem_ld32_issue(tcol + (uint32_t)(ch * 32), r);
                 const float thr = thr_sh[row] + off;   // stale reads only cost extra pushes
                 tmem_ld_wait();
+                if (tl_me) {
+                    tl_c1 = clock64();
+                    tl_ld += tl_c1 - tl_c0;
+                }
                 // max tree: 32 -> 12 partial maxima (3, 3, 2 columns) -> 4 group maxima -> 1
                 float pm[12], g[4];
 #pragma unroll
@@ -1189,42 +1197,58 @@ k_knn_tiles_tc(const double *__restrict__ E, int64_t lde, int d, double scale, c
                 const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
                 if (!__any_sync(0xffffffffu, m > thr))
                     continue;
-                // hit path: walk the tree down, so a single hit costs ~10 comparisons instead of 32
-                auto push = [&](int i) {
-                    const int gcol = r0 + ch * 32 + i;
-                    for (uint32_t spin = 0; (int)(tail - *myhead) >= QCAP; ++spin) {
-                        if (spin > (1u << 24)) {
-                            atomicOr(err_flag, 4);
-                            __threadfence();
-                            asm volatile("trap;");
-                        }
-                    }
-                    const unsigned meta = (((tail / QCAP) & 1u) << 31) | (unsigned)gcol;
-                    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(
-                                     ring_addr + (uint32_t)((tail % QCAP) * TC_M * 8)),
-                                 "r"(__float_as_uint(__uint_as_float(r[i]) - off)), "r"(meta)
-                                 : "memory");
-                    ++tail;
-                };
-                if (m > thr) {  // this row has at least one hit among the 32 columns
+                // hit path, branch-free per lane: a 32-bit mask of the columns that beat the threshold, then one warp-
+                // uniform loop that takes the lowest set bit of every lane, fetches its value with a 5-level select
+                // tree (registers cannot be indexed) and pushes it.  The earlier tree walk (descend only into the
+                // groups with a hit) executed ~10 comparisons per hit but diverged per lane: measured 1 200 - 3 700
+                // cycles per chunk with a hit, 70 % of a scanner warp's time.
+                unsigned hm = 0u;
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        if (!(g[jj] > thr))
-                            continue;
+                for (int i = 0; i < 32; ++i)
+                    hm |= (__uint_as_float(r[i]) > thr ? 1u : 0u) << i;
+                while (__any_sync(0xffffffffu, hm != 0u)) {
+                    const int i = hm != 0u ? __ffs(hm) - 1 : 0;
+                    uint32_t s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-                        for (int s3 = 0; s3 < 3; ++s3) {
-                            if (!(pm[3 * jj + s3] > thr))
-                                continue;
+                    for (int q = 0; q < 16; ++q)
+                        s16[q] = (i & 1) ? r[2 * q + 1] : r[2 * q];
 #pragma unroll
-                            for (int e = 0; e < (s3 == 2 ? 2 : 3); ++e) {
-                                const int i = 8 * jj + 3 * s3 + e;
-                                if (__uint_as_float(r[i]) > thr)
-                                    push(i);
+                    for (int q = 0; q < 8; ++q)
+                        s8[q] = (i & 2) ? s16[2 * q + 1] : s16[2 * q];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        s4[q] = (i & 4) ? s8[2 * q + 1] : s8[2 * q];
+                    s2[0] = (i & 8) ? s4[1] : s4[0];
+                    s2[1] = (i & 8) ? s4[3] : s4[2];
+                    const uint32_t vbits = (i & 16) ? s2[1] : s2[0];
+                    if (hm != 0u) {
+                        const int gcol = r0 + ch * 32 + i;
+                        for (uint32_t spin = 0; (int)(tail - *myhead) >= QCAP; ++spin) {
+                            if (spin > (1u << 24)) {
+                                atomicOr(err_flag, 4);
+                                __threadfence();
+                                asm volatile("trap;");
                             }
                         }
+                        const unsigned meta = (((tail / QCAP) & 1u) << 31) | (unsigned)gcol;
+                        asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(
+                                         ring_addr + (uint32_t)((tail % QCAP) * TC_M * 8)),
+                                     "r"(__float_as_uint(__uint_as_float(vbits) - off)), "r"(meta)
+                                     : "memory");
+                        ++tail;
+                        hm &= hm - 1u;
                     }
                 }
                 __syncwarp();
+                if (tl_me) {
+                    tl_hit += clock64() - tl_c1;
+                    ++tl_nhit;
+                }
+            }
+            if (tl_me) {
+                TLV(2 + set, ((long long)seq << 8) | 7, tl_ld);
+                TLV(2 + set, ((long long)seq << 8) | 8, tl_hit);
+                TLV(2 + set, ((long long)seq << 8) | 9, tl_nhit);
             }
             tc_fence_before();
             __syncwarp();
