@@ -87,6 +87,9 @@ SIGNATURES = {
     "cb200_pairwise_modularity": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "cb200_fetch_edges": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cb200_edges_checksum": (c_int, [c_vp, c_i64p, ctypes.POINTER(ctypes.c_uint64)]),
+    "cb200_pooled_size_factors": (c_int, [c_vp, c_vp, c_vp, c_int, ctypes.c_double, c_i64, c_vp, c_i64p, c_vp]),
+    "cb200_qc_metrics": (c_int, [c_vp, c_int, c_vp, c_vp, ctypes.c_double, c_vp, c_vp, c_vp, c_vp]),
+    "cb200_knn_distances": (c_int, [c_vp, c_vp]),
     "cb200_multi_init": (c_int, [c_int, ctypes.POINTER(c_vp)]),
     "cb200_multi_free": (c_int, [c_vp]),
     "cb200_multi_last_error": (ctypes.c_char_p, [c_vp]),
@@ -301,6 +304,50 @@ class Context:
     def wait_copies(self):
         self._ck(lib().cb200_wait_copies(self._h))
 
+    # -- 8(f)-1: deconvolution size factors ----------------------------------------------
+    def pooled_size_factors(self, clusters=None, sizes=None, min_mean=None, max_cluster_size=3000):
+        """scran::computeSumFactors(clusters=...) on the resident matrix.  Returns (sf scaled to unit mean over the
+        positive factors, number of non-positive factors); stage times in self.pool_ms."""
+        cl = None if clusters is None else np.ascontiguousarray(clusters, dtype=np.int32)
+        assert cl is None or cl.size == self.n_cells
+        sz = None if sizes is None else np.ascontiguousarray(sorted(sizes), dtype=np.int32)
+        out = np.empty(self.n_cells)
+        nneg = c_i64()
+        ms = np.zeros(5)
+        self._ck(lib().cb200_pooled_size_factors(self._h, _ptr(cl), _ptr(sz), 0 if sz is None else int(sz.size),
+                                                 -1.0 if min_mean is None else float(min_mean),
+                                                 0 if max_cluster_size is None else int(max_cluster_size), _ptr(out),
+                                                 ctypes.byref(nneg), _ptr(ms)))
+        self.pool_ms = dict(zip(("pseudo_cells_ms", "pool_medians_ms", "solve_ms", "host_rescale_ms", "total_host_ms"),
+                                ms.tolist()))
+        return out, int(nneg.value)
+
+    # -- 8(f)-4: per-cell QC metrics, kNN distances ---------------------------------------
+    def qc_metrics(self, subsets=(), threshold=0.0):
+        """scuttle::perCellQCMetrics: dict(sum, detected, subsets=[dict(sum, detected, percent), ...])."""
+        subsets = [np.ascontiguousarray(g, dtype=np.int32) for g in subsets]
+        S = len(subsets)
+        ptr = np.zeros(S + 1, dtype=np.int32)
+        if S:
+            ptr[1:] = np.cumsum([g.size for g in subsets])
+        genes = np.concatenate(subsets).astype(np.int32) if S and ptr[-1] > 0 else np.zeros(1, dtype=np.int32)
+        n = self.n_cells
+        tot, det = np.empty(n), np.empty(n, dtype=np.int32)
+        ssum = np.empty((max(S, 1), n))
+        sdet = np.empty((max(S, 1), n), dtype=np.int32)
+        self._ck(lib().cb200_qc_metrics(self._h, S, _ptr(ptr), _ptr(genes), float(threshold), _ptr(tot), _ptr(det),
+                                        _ptr(ssum), _ptr(sdet)))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            subs = [dict(sum=ssum[s], detected=sdet[s], percent=100.0 * ssum[s] / tot) for s in range(S)]
+        return dict(sum=tot, detected=det, subsets=subs)
+
+    def knn_distances(self):
+        """Distances of the resident kNN result (n_queries x k, findKNN(get.distance=TRUE)$distance)."""
+        nq, k = self._knn_shape
+        out = np.empty((nq, k), order="F")
+        self._ck(lib().cb200_knn_distances(self._h, _ptr(out)))
+        return out
+
     # -- 8(f)-3: batch-aware branch ----------------------------------------------------
     def block_averages(self, block, n_blocks):
         """Per-batch gene averages of x / (sf centred within the batch): (ave B x G, mean sf per batch, cells per batch)."""
@@ -363,11 +410,13 @@ class Context:
         q_end = n_total if q_end is None else q_end
         idx = out if out is not None else (np.empty((q_end - q_begin, k), dtype=np.int32, order="F") if want else None)
         self._ck(lib().cb200_knn(self._h, _ptr(emb), n_total, d, k, q_begin, q_end, _ptr(idx)))
+        self._knn_shape = (q_end - q_begin, k)
         return idx
 
     def knn_device(self, d_emb_ptr, n_total, d, k, q_begin, q_end, want=True):
         idx = np.empty((q_end - q_begin, k), dtype=np.int32, order="F") if want else None
         self._ck(lib().cb200_knn_device(self._h, c_vp(d_emb_ptr), n_total, d, k, q_begin, q_end, _ptr(idx)))
+        self._knn_shape = (q_end - q_begin, k)
         return idx
 
     # -- a10 ------------------------------------------------------------------------

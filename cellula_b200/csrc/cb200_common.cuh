@@ -174,6 +174,9 @@ struct cb200_ctx {
     int64_t knn_nq = 0, knn_ntotal = 0, knn_qbegin = 0;
     int knn_k = 0;
     bool have_knn = false;
+    const double *knn_E = nullptr;   // embedding the resident kNN result was computed from (row-major, stride knn_lde) ...
+    int64_t knn_lde = 0;             // ... kept for cb200_knn_distances
+    int knn_d = 0;
 
     // ---- a10: SNN
     DevBuf<int32_t> index0;    // [n_total*k] row-major 0-based (when given from host)
@@ -202,6 +205,11 @@ struct cb200_ctx {
     DevBuf<int> snn_nlists;           // [tiers + 1] their counts
     int snn_n_merge = 0;
     DevBuf<unsigned char> snn_flag;   // [nj] cells left to the merge kernel (too many partners for the hash table)
+
+    // ---- 8(f)-4: per-cell QC metrics, kNN distances (cb200_qc.cu)
+    DevBuf<uint32_t> qc_mask;          // [G] bit s set = gene belongs to subset s
+    DevBuf<double> qc_sum;             // [(1 + S) * N] total, then per subset
+    DevBuf<int32_t> qc_det;            // [(1 + S) * N]
 
     // ---- cluster diagnostics (cb200_diag.cu)
     DevBuf<int32_t> diag_lab, diag_i, diag_ef;

@@ -122,6 +122,7 @@ extern "C" int cb200_free(cb200_ctx *ctx)
     ctx->index0.release(); ctx->rcnt.release(); ctx->rptr.release(); ctx->rcur.release();
     ctx->hosts_u.release(); ctx->hosts.release(); ctx->ecnt.release(); ctx->eptr.release();
     ctx->bcnt.release(); ctx->efrom.release(); ctx->eto.release(); ctx->ew8.release();
+    ctx->qc_mask.release(); ctx->qc_sum.release(); ctx->qc_det.release();
     ctx->diag_lab.release(); ctx->diag_i.release(); ctx->diag_ef.release(); ctx->diag_d.release(); ctx->diag_ew.release(); ctx->diag_cnt.release();
     ctx->scan_blk.release(); ctx->snn_bounds.release(); ctx->snn_flag.release(); ctx->snn_jlist.release(); ctx->snn_nlists.release(); ctx->snn_tcnt.release(); ctx->snn_toff.release(); ctx->snn_tmp_h.release(); ctx->snn_tmp_rc.release(); ctx->snn_cut.release();
     if (ctx->snn_bounds_h != nullptr)

@@ -630,6 +630,10 @@ static int knn_core(cb200_ctx *ctx, const double *E, int64_t lde, int64_t n, int
     CB_CHECK(ctx, q_begin >= 0 && q_begin < q_end && q_end <= n, "cb200_knn: bad query range");
     const int64_t nq = q_end - q_begin;
     CB_CUDA(ctx, ctx->knn.ensure((size_t)nq * k));
+    ctx->have_knn = false;
+    ctx->knn_E = E;   // for cb200_knn_distances
+    ctx->knn_lde = lde;
+    ctx->knn_d = d;
     if (k > 112 || d > KNN_MAX_DP) {
         // shapes outside the tile engines (rebuildModularity's k = round(sqrt(N)), wide embeddings): exact general path
         cb_stage_begin(ctx, ST_KNN_TILE);

@@ -1,0 +1,871 @@
+// cb200_pool.cu -- SURVEY 8(f) rank 1: deconvolution ("pooled") size factors on the GPU.
+//
+// Replaces: scran::computeSumFactors(sce, clusters = ...) = scuttle::pooledSizeFactors, called by
+// /root/reference/R/doNormAndReduce.R:66-71 between quickCluster (:57-65; its walktrap clustering stays igraph,
+// the cluster labels are an INPUT here) and logNormCounts (:78).  Published algorithm: Lun, Bach & Marioni,
+// Genome Biology 17:75 (2016); package internals restated from memory (un-vendored: parity unpinned), the same
+// restatement as oracle/oracle.py:pooled_size_factors, which the GPU tests compare against.
+//
+// Per cluster (clusters above max_cluster_size are dealt round-robin into sub-clusters first):
+//   1. y_gc = x_gc / lib_c; pseudo-cell ave_g = mean_c(y_gc) * mean(lib); genes with ave_g >= min_mean are kept.
+//   2. cells are placed on a ring by library size (odd ranks ascending, even ranks descending).
+//   3. for every ring position p and pool size s (21, 26, ... 101 <= n): b_s[p] = median over the kept genes of
+//      (sum of y over the s cells starting at p) / ave_g; plus b_1[p] with weight sqrt(1e-6).
+//   4. least squares for the per-cell factors theta: every pool says sum_{c in pool} theta_c = b.
+//   5. nf_c = theta_c * lib_c; clusters are brought to one scale by the median ratio of their pseudo-cells to a
+//      reference cluster's (host, G-sized), and the vector is scaled to unit mean over the positive factors.
+//
+// B200 design.
+//   * Step 3 is the cost (N x 18 medians over ~5 000 genes; minutes on a CPU).  k_pool_medians: one CTA owns a run
+//     of consecutive ring positions for ONE pool size and keeps the pooled profile of the current window in shared
+//     memory as 64-bit FIXED-POINT integers (2^s2 * y, exact integer adds), so sliding the window -- add the entering
+//     cell's column, subtract the leaving one's -- is exact and drift-free, and an empty gene is exactly zero.
+//     The median is a bucket selection in shared memory: zeros are counted apart, the non-zero ratios are
+//     histogrammed on fp32 keys into 2 048 buckets spanning [0, 4 x previous median), the bucket holding the
+//     wanted rank is gathered (a handful of genes) and ranked exactly in fp64 on (ratio, gene).  The range adapts
+//     (widen / narrow) until the bucket is small, so any distribution terminates; ties collapse to one value.
+//     fp32 keys only decide bucket membership: a gene within 1e-7 relative of a bucket edge may be ranked across
+//     it, which moves the median by <= 1e-7 relative (contract: size factors within 1e-6 relative).
+//   * Step 4: in ring coordinates every position carries one pool of every size, so A^T A is CIRCULANT:
+//     eigenvalues lambda_k = w + sum_s (sin(pi k s / n) / sin(pi k / n))^2, solved exactly by one DFT pair per
+//     cluster (O(n^2) fp64 with a twiddle table; n <= 3 000).  lambda_min ~ 3, so the normal equations lose
+//     nothing (checked against numpy lstsq: 3e-12).
+//   * Step 1: RED.ADD.U64 of fixed-point y into a [clusters][genes] table (order-independent, exact), then an
+//     ordered compaction of the kept genes per cluster (gene -> slot map, fp64 ave, fp32 reciprocal).
+// Single context only: the clusters are arbitrary cell subsets, so the matrix has to be resident on one GPU.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <functional>
+#include <thread>
+
+#include "cb200_common.cuh"
+
+#define POOL_THREADS 512
+#define POOL_NB 2048
+#define POOL_CAP 512
+#define POOL_LOWWEIGHT 1e-6
+
+struct PoolItem {
+    int32_t cluster, size, p0, p1;
+    int64_t out_off;   // index of ring position 0 of this (cluster, size) in the output array
+};
+
+// library sizes: warp per cell (counts are integers in fp64: the sum is exact whatever the order)
+__global__ void __launch_bounds__(256)
+k_pool_colsum(const int64_t *__restrict__ colptr, const double *__restrict__ x, int64_t n_cols, double *__restrict__ lib)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = warp0; c < n_cols; c += nwarps) {
+        double s = 0.0;
+        for (int64_t i = colptr[c] + lane; i < colptr[c + 1]; i += 32)
+            s += ld_stream(x + i);
+        s = warp_sum(s);
+        if (lane == 0)
+            lib[c] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// step 1: per-cluster gene sums of x / lib in fixed point, then the kept genes of every cluster
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pool_gene_sums(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx, const double *__restrict__ x,
+                 const double *__restrict__ lib, const int32_t *__restrict__ cl_of, int64_t n_cols, int64_t G, double scale,
+                 unsigned long long *__restrict__ acc, int *__restrict__ flag)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = warp0; c < n_cols; c += nwarps) {
+        const int64_t b = colptr[c], e = colptr[c + 1];
+        const double r = scale / lib[c];
+        unsigned long long *row = acc + (int64_t)cl_of[c] * G;
+        for (int64_t i = b + lane; i < e; i += 32) {
+            const double v = ld_stream(x + i);
+            const int g = ld_stream_i(rowidx + i);
+            if (g < 0 || g >= G || !(v >= 0.0)) {
+                atomicOr(flag, 1);
+                continue;
+            }
+            atomicAdd(row + g, (unsigned long long)__double2ll_rn(v * r));
+        }
+    }
+}
+
+// one CTA per cluster: ave = (sum / n) * meanlib; ordered compaction of the genes with ave >= min_mean
+__global__ void __launch_bounds__(256)
+k_pool_filter(const unsigned long long *__restrict__ acc, const int64_t *__restrict__ cl_ptr, const double *__restrict__ meanlib,
+              int64_t G, double inv_scale1, double inv_scale2, double min_mean, int32_t *__restrict__ pslot,
+              double *__restrict__ pave, float *__restrict__ pinv, double *__restrict__ ave_full, int32_t *__restrict__ gf_out)
+{
+    const int c = blockIdx.x;
+    const double nc = (double)(cl_ptr[c + 1] - cl_ptr[c]);
+    const double ml = meanlib[c];
+    __shared__ int wcnt[8];
+    __shared__ int base;
+    if (threadIdx.x == 0)
+        base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t g0 = 0; g0 < G; g0 += blockDim.x) {
+        const int64_t g = g0 + threadIdx.x;
+        double ave = 0.0;
+        bool keep = false;
+        if (g < G) {
+            ave = ((double)acc[(int64_t)c * G + g] * inv_scale1 / nc) * ml;
+            ave_full[(int64_t)c * G + g] = ave;
+            keep = ave >= min_mean;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0)
+            wcnt[w] = __popc(m);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int q = 0; q < 8; ++q) {
+            if (q < w)
+                off += wcnt[q];
+            tot += wcnt[q];
+        }
+        if (g < G) {
+            int slot = -1;
+            if (keep) {
+                slot = base + off + __popc(m & ((1u << lane) - 1u));
+                pave[(int64_t)c * G + slot] = ave;
+                pinv[(int64_t)c * G + slot] = (float)(inv_scale2 / ave);
+            }
+            pslot[(int64_t)c * G + g] = slot;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        gf_out[c] = base;
+}
+
+// ---------------------------------------------------------------------------------------
+// step 3: pool medians
+// ---------------------------------------------------------------------------------------
+struct PoolShared {
+    unsigned int hist[POOL_NB];
+    double list_v[POOL_CAP];
+    int list_s[POOL_CAP];
+    unsigned long long next_min;   // bit pattern of the smallest exact ratio beyond the gathered bucket
+    double res[2];
+    int n_zero, n_below, n_list, n_in;
+    int bucket, cum, cnt, tie_slot;
+};
+
+// all threads of the CTA add (sign = +1) or subtract (sign = -1) one cell's column to the window W
+__device__ __forceinline__ void pool_apply_column(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                                  const double *__restrict__ x, const double *__restrict__ lib,
+                                                  const int32_t *__restrict__ slot_of, int cell, double scale, int sign,
+                                                  unsigned long long *W, int tid, int nthreads)
+{
+    const int64_t b = colptr[cell], e = colptr[cell + 1];
+    const double r = scale / lib[cell];
+    for (int64_t i = b + tid; i < e; i += nthreads) {
+        const int s = __ldg(slot_of + __ldg(rowidx + i));
+        if (s >= 0) {
+            const long long q = __double2ll_rn(__ldg(x + i) * r);
+            atomicAdd(W + s, (unsigned long long)(sign > 0 ? q : -q));
+        }
+    }
+}
+
+__device__ __forceinline__ float pool_key(unsigned long long w, float inv)
+{
+    return (float)(long long)w * inv;
+}
+
+// Element of 0-based rank r among the NON-ZERO ratios of the window (and the next one when want_next), exact in fp64
+// up to the bucket-edge caveat in the header.  Results in sh->res[0..1].  All threads must call it.
+__device__ void pool_select(PoolShared *sh, const unsigned long long *W, const float *inv, const double *__restrict__ ave, int gf,
+                            int r, bool want_next, float &guess, double inv_scale2, int *__restrict__ flag)
+{
+    const int tid = threadIdx.x;
+    float lo = 0.f, hi = 4.f * guess;
+    if (!(hi > 0.f) || isinf(hi))
+        hi = 1.f;
+    for (int round = 0; round < 96; ++round) {
+        for (int b = tid; b < POOL_NB; b += POOL_THREADS)
+            sh->hist[b] = 0;
+        if (tid == 0) {
+            sh->n_below = 0;
+            sh->n_in = 0;
+            sh->n_list = 0;
+            sh->tie_slot = 0x7fffffff;
+            sh->next_min = ~0ULL;
+        }
+        __syncthreads();
+        const float scale = (float)POOL_NB / (hi - lo);
+        int below = 0, in = 0;
+        for (int g = tid; g < gf; g += POOL_THREADS) {
+            const unsigned long long w = W[g];
+            if (w == 0ULL)
+                continue;
+            const float key = pool_key(w, inv[g]);
+            if (key < lo) {
+                ++below;
+            } else if (key < hi) {
+                int b = (int)((key - lo) * scale);
+                b = b > POOL_NB - 1 ? POOL_NB - 1 : b;
+                atomicAdd(&sh->hist[b], 1u);
+                ++in;
+            }
+        }
+        below = warp_sum_i(below);
+        in = warp_sum_i(in);
+        if ((tid & 31) == 0) {
+            if (below)
+                atomicAdd(&sh->n_below, below);
+            if (in)
+                atomicAdd(&sh->n_in, in);
+        }
+        __syncthreads();
+        const int n_below = sh->n_below, n_in = sh->n_in;
+        if (r < n_below) {   // the range starts too high (only after a narrowing step met a rounding edge)
+            const float wd = hi - lo;
+            hi = lo;
+            lo = fmaxf(0.f, lo - 4.f * wd);
+            __syncthreads();
+            continue;
+        }
+        if (r >= n_below + n_in) {   // beyond the range: widen upwards
+            const float wd = hi - lo;
+            lo = hi;
+            hi = hi + 16.f * wd;
+            if (isinf(hi))
+                hi = 3.0e38f;
+            __syncthreads();
+            continue;
+        }
+        // the wanted rank is inside [lo, hi): find its bucket (warp 0: 64 buckets per lane, then a warp scan)
+        if (tid < 32) {
+            int s = 0;
+            for (int q = 0; q < POOL_NB / 32; ++q)
+                s += (int)sh->hist[tid * (POOL_NB / 32) + q];
+            int incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o)
+                    incl += t;
+            }
+            const int excl = incl - s;
+            const int want = r - n_below;
+            if (want >= excl && want < incl) {
+                int cum = excl;
+                for (int q = 0; q < POOL_NB / 32; ++q) {
+                    const int h = (int)sh->hist[tid * (POOL_NB / 32) + q];
+                    if (want < cum + h) {
+                        sh->bucket = tid * (POOL_NB / 32) + q;
+                        sh->cum = cum;
+                        sh->cnt = h;
+                        break;
+                    }
+                    cum += h;
+                }
+            }
+        }
+        __syncthreads();
+        const int bucket = sh->bucket, cnt = sh->cnt;
+        const int want = r - n_below - sh->cum;   // rank inside the bucket
+        const float blo = lo + (float)bucket / scale, bhi = lo + (float)(bucket + 1) / scale;
+        const bool degenerate = !(bhi > blo);   // the bucket cannot be split further in fp32: its keys are one value
+        if (cnt > POOL_CAP && !degenerate && round < 90) {   // narrow to this bucket (membership is recounted next round)
+            lo = blo;
+            hi = bhi;
+            __syncthreads();
+            continue;
+        }
+        // gather the bucket; beyond it, the smallest exact ratio (the "next" element when the bucket ends at the wanted rank)
+        const bool need_outside = want_next && want == cnt - 1;
+        for (int g = tid; g < gf; g += POOL_THREADS) {
+            const unsigned long long w = W[g];
+            if (w == 0ULL)
+                continue;
+            const float key = pool_key(w, inv[g]);
+            if (key < lo)
+                continue;
+            int b = POOL_NB;   // beyond the range
+            if (key < hi) {
+                b = (int)((key - lo) * scale);
+                b = b > POOL_NB - 1 ? POOL_NB - 1 : b;
+            }
+            if (b == bucket) {
+                if (cnt <= POOL_CAP) {
+                    const int pos = atomicAdd(&sh->n_list, 1);
+                    if (pos < POOL_CAP) {
+                        sh->list_s[pos] = g;
+                        sh->list_v[pos] = ((double)(long long)w * inv_scale2) / ave[g];
+                    }
+                } else {
+                    atomicMin(&sh->tie_slot, g);   // more equal keys than the list holds: they are one value
+                }
+            } else if (b > bucket && need_outside) {
+                const double v = ((double)(long long)w * inv_scale2) / ave[g];
+                atomicMin(&sh->next_min, (unsigned long long)__double_as_longlong(v));
+            }
+        }
+        __syncthreads();
+        if (cnt > POOL_CAP) {
+            if (tid == 0) {
+                const int g = sh->tie_slot;
+                const double v = ((double)(long long)W[g] * inv_scale2) / ave[g];
+                sh->res[0] = v;
+                sh->res[1] = v;
+            }
+            __syncthreads();
+            return;
+        }
+        const int nl = sh->n_list < POOL_CAP ? sh->n_list : POOL_CAP;
+        if (tid < nl) {
+            const double v = sh->list_v[tid];
+            const int s = sh->list_s[tid];
+            int rank = 0;
+            for (int j = 0; j < nl; ++j) {
+                const double u = sh->list_v[j];
+                rank += (u < v || (u == v && sh->list_s[j] < s)) ? 1 : 0;
+            }
+            if (rank == want)
+                sh->res[0] = v;
+            if (want_next && rank == want + 1)
+                sh->res[1] = v;
+        }
+        if (tid == 0 && sh->n_list != cnt)
+            atomicOr(flag, 8);   // histogram and gather disagree: internal error
+        __syncthreads();
+        if (need_outside && tid == 0)
+            sh->res[1] = __longlong_as_double((long long)sh->next_min);
+        __syncthreads();
+        guess = (float)sh->res[0];
+        return;
+    }
+    if (tid == 0)
+        atomicOr(flag, 4);   // no convergence of the bucket search (not expected)
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(POOL_THREADS)
+k_pool_medians(const PoolItem *__restrict__ items, int n_items, const int64_t *__restrict__ colptr,
+               const int32_t *__restrict__ rowidx, const double *__restrict__ x, const double *__restrict__ lib,
+               const int32_t *__restrict__ ring, const int64_t *__restrict__ cl_ptr, const int32_t *__restrict__ pslot,
+               const float *__restrict__ pinv, const double *__restrict__ pave, const int32_t *__restrict__ gf_of,
+               const double *__restrict__ meanlib, int64_t G, int gf_max, double scale2, double inv_scale2,
+               double *__restrict__ bvals, int *__restrict__ flag)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *W = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *inv = reinterpret_cast<float *>(W + gf_max);
+    PoolShared *sh = reinterpret_cast<PoolShared *>(smem_raw + (((size_t)gf_max * 12 + 15) & ~(size_t)15));
+    const int tid = threadIdx.x;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const PoolItem item = items[it];
+        const int c = item.cluster, size = item.size;
+        const int64_t base = cl_ptr[c];
+        const int n = (int)(cl_ptr[c + 1] - base);
+        const int gf = gf_of[c];
+        const int32_t *slot_of = pslot + (int64_t)c * G;
+        const double *ave = pave + (int64_t)c * G;
+        __syncthreads();   // previous item fully done with W / sh
+        for (int g = tid; g < gf; g += POOL_THREADS) {
+            W[g] = 0ULL;
+            inv[g] = pinv[(int64_t)c * G + g];
+        }
+        __syncthreads();
+        // window of the first position: warps take the cells round-robin
+        {
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int t = warp; t < size; t += POOL_THREADS / 32)
+                pool_apply_column(colptr, rowidx, x, lib, slot_of, ring[base + (item.p0 + t) % n], scale2, +1, W, lane, 32);
+        }
+        __syncthreads();
+        float guess = (float)(0.5 * (double)size / meanlib[c]);
+        const int half = gf / 2;
+        const bool even = (gf & 1) == 0;
+        for (int p = item.p0; p < item.p1; ++p) {
+            // zeros of the window
+            if (tid == 0)
+                sh->n_zero = 0;
+            __syncthreads();
+            int z = 0;
+            for (int g = tid; g < gf; g += POOL_THREADS)
+                z += W[g] == 0ULL ? 1 : 0;
+            z = warp_sum_i(z);
+            if ((tid & 31) == 0 && z)
+                atomicAdd(&sh->n_zero, z);
+            __syncthreads();
+            const int nz = sh->n_zero;
+            double med;
+            if (!even) {
+                if (half < nz) {
+                    med = 0.0;
+                } else {
+                    pool_select(sh, W, inv, ave, gf, half - nz, false, guess, inv_scale2, flag);
+                    med = sh->res[0];
+                }
+            } else {
+                if (half < nz) {
+                    med = 0.0;
+                } else if (half - 1 < nz) {   // lower middle is a zero, upper middle the smallest non-zero ratio
+                    pool_select(sh, W, inv, ave, gf, 0, false, guess, inv_scale2, flag);
+                    med = (0.0 + sh->res[0]) / 2.0;
+                } else {
+                    pool_select(sh, W, inv, ave, gf, half - 1 - nz, true, guess, inv_scale2, flag);
+                    med = (sh->res[1] + sh->res[0]) / 2.0;
+                }
+            }
+            if (tid == 0)
+                bvals[item.out_off + p] = med;
+            __syncthreads();   // res consumed before the next selection rewrites it
+            if (p + 1 < item.p1 && size < n) {
+                // slide: the cell at ring position p leaves, the one at p + size enters (half a CTA each)
+                const int halfT = POOL_THREADS / 2;
+                if (tid < halfT)
+                    pool_apply_column(colptr, rowidx, x, lib, slot_of, ring[base + p % n], scale2, -1, W, tid, halfT);
+                else
+                    pool_apply_column(colptr, rowidx, x, lib, slot_of, ring[base + (p + size) % n], scale2, +1, W, tid - halfT, halfT);
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// step 4: circulant least squares per cluster (one CTA each)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+k_pool_solve(const int64_t *__restrict__ cl_ptr, const int32_t *__restrict__ sizes, const int32_t *__restrict__ ns_of,
+             int n_sizes_all, int64_t N, const double *__restrict__ bvals, const int32_t *__restrict__ ring,
+             const double *__restrict__ lib, double *__restrict__ rhs, double *__restrict__ tw_re, double *__restrict__ tw_im,
+             double *__restrict__ F_re, double *__restrict__ F_im, double *__restrict__ nf)
+{
+    const int c = blockIdx.x;
+    const int64_t base = cl_ptr[c];
+    const int n = (int)(cl_ptr[c + 1] - base);
+    const int ns = ns_of[c];
+    const double w = POOL_LOWWEIGHT;
+    // right-hand side A^T b in ring coordinates and the twiddle table
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double acc = w * bvals[(int64_t)n_sizes_all * N + base + j];
+        for (int si = 0; si < ns; ++si) {
+            const int s = sizes[si];
+            const double *b = bvals + (int64_t)si * N + base;
+            int idx = j;
+            for (int t = 0; t < s; ++t) {
+                acc += b[idx];
+                idx = idx == 0 ? n - 1 : idx - 1;
+            }
+        }
+        rhs[base + j] = acc;
+        double sn, cs;
+        sincospi(2.0 * (double)j / (double)n, &sn, &cs);
+        tw_re[base + j] = cs;
+        tw_im[base + j] = -sn;
+    }
+    __syncthreads();
+    // forward DFT, divided by the eigenvalues of A^T A
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double fr = 0.0, fi = 0.0;
+        int idx = 0;
+        for (int j = 0; j < n; ++j) {
+            const double v = rhs[base + j];
+            fr += v * tw_re[base + idx];
+            fi += v * tw_im[base + idx];
+            idx += k;
+            if (idx >= n)
+                idx -= n;
+        }
+        double lam = w;
+        for (int si = 0; si < ns; ++si) {
+            const int s = sizes[si];
+            if (k == 0) {
+                lam += (double)s * (double)s;
+            } else {
+                const double a = sinpi((double)(((int64_t)k * s) % n) / (double)n);
+                const double b = sinpi((double)k / (double)n);
+                lam += (a / b) * (a / b);
+            }
+        }
+        F_re[base + k] = fr / lam;
+        F_im[base + k] = fi / lam;
+    }
+    __syncthreads();
+    // inverse DFT (real part), times the library size, scattered to the cell
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double acc = 0.0;
+        int idx = 0;
+        for (int k = 0; k < n; ++k) {
+            acc += F_re[base + k] * tw_re[base + idx] + F_im[base + k] * tw_im[base + idx];
+            idx += j;
+            if (idx >= n)
+                idx -= n;
+        }
+        const int cell = ring[base + j];
+        nf[cell] = (acc / (double)n) * lib[cell];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+template <typename F>
+static void pool_parallel_for(int n, F f)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw == 0 ? 4 : hw > 32 ? 32 : hw);
+    if (nt > n)
+        nt = n;
+    if (nt <= 1) {
+        for (int i = 0; i < n; ++i)
+            f(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([=]() {
+            for (int i = t; i < n; i += nt)
+                f(i);
+        });
+    for (auto &t : th)
+        t.join();
+}
+
+static double pool_median(std::vector<double> &v)
+{
+    const size_t n = v.size();
+    if (n == 0)
+        return NAN;
+    const size_t h = n / 2;
+    std::nth_element(v.begin(), v.begin() + h, v.end());
+    const double hi = v[h];
+    if (n & 1)
+        return hi;
+    const double lo = *std::max_element(v.begin(), v.begin() + h);
+    return (lo + hi) / 2.0;
+}
+
+extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters, const int32_t *sizes, int n_sizes,
+                                         double min_mean, int64_t max_cluster_size, double *sf_out, int64_t *n_nonpositive,
+                                         double *stage_ms_out)
+{
+    if (ctx == nullptr)
+        return 1;
+    CB_CHECK(ctx, ctx->loaded, "cb200_pooled_size_factors: no count matrix loaded");
+    CB_CHECK(ctx, ctx->N == ctx->N_total, "cb200_pooled_size_factors: the whole matrix has to be resident on one GPU "
+                                           "(clusters are arbitrary cell subsets)");
+    CB_CHECK(ctx, sf_out != nullptr, "cb200_pooled_size_factors: NULL output");
+    static const int32_t default_sizes[17] = {21, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 81, 86, 91, 96, 101};
+    if (sizes == nullptr) {
+        sizes = default_sizes;
+        n_sizes = 17;
+    }
+    CB_CHECK(ctx, n_sizes >= 1 && n_sizes <= 64, "cb200_pooled_size_factors: 1 <= number of pool sizes <= 64");
+    std::vector<int32_t> sz(sizes, sizes + n_sizes);
+    std::sort(sz.begin(), sz.end());
+    for (int i = 0; i < n_sizes; ++i) {
+        CB_CHECK(ctx, sz[i] >= 2, "cb200_pooled_size_factors: pool sizes must be >= 2");
+        CB_CHECK(ctx, i == 0 || sz[i] != sz[i - 1], "cb200_pooled_size_factors: 'sizes' are not unique");
+    }
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t N = ctx->N, G = ctx->G;
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    cudaEvent_t ev[4];
+    for (auto &e : ev)
+        CB_CUDA(ctx, cudaEventCreate(&e));
+    struct EvGuard {
+        cudaEvent_t *e;
+        ~EvGuard()
+        {
+            for (int i = 0; i < 4; ++i)
+                cudaEventDestroy(e[i]);
+        }
+    } ev_guard{ev};
+
+    // ---- library sizes (K1) -> host
+    CB_CUDA(ctx, ctx->blk_w.ensure((size_t)N));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    {
+        const int grid = cb_grid_for(N, 8, ctx->num_sms * 8);
+        k_pool_colsum<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->x.p, N, ctx->blk_w.p);
+        CB_LAUNCH(ctx);
+    }
+    std::vector<double> lib((size_t)N);
+    CB_TRY(cb200_d2h(ctx, lib.data(), ctx->blk_w.p, (size_t)N * sizeof(double), ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < N; ++i)
+        CB_CHECK(ctx, lib[(size_t)i] > 0.0 && std::isfinite(lib[(size_t)i]), "cb200_pooled_size_factors: cells should have non-zero library sizes");
+    if (!(min_mean > 0.0)) {   // scuttle:::.guessMinMean
+        std::vector<double> tmp(lib);
+        min_mean = pool_median(tmp) <= 50000.0 ? 0.1 : 1.0;
+    }
+    if (min_mean < 1e-8)
+        min_mean = 1e-8;
+
+    // ---- clusters: size limit (round-robin split, ids by first appearance), members, ring order
+    std::vector<int32_t> cl((size_t)N, 0);
+    int C = 0;
+    {
+        int32_t maxc = 0;
+        if (clusters != nullptr)
+            for (int64_t i = 0; i < N; ++i) {
+                CB_CHECK(ctx, clusters[i] >= 0, "cb200_pooled_size_factors: cluster codes must be >= 0");
+                maxc = clusters[i] > maxc ? clusters[i] : maxc;
+            }
+        std::vector<int64_t> cnt((size_t)maxc + 1, 0), seen((size_t)maxc + 1, 0);
+        std::vector<int32_t> first_id((size_t)maxc + 1, -1), mult((size_t)maxc + 1, 1);
+        for (int64_t i = 0; i < N; ++i)
+            cnt[(size_t)(clusters ? clusters[i] : 0)] += 1;
+        for (int64_t i = 0; i < N; ++i) {
+            const size_t o = (size_t)(clusters ? clusters[i] : 0);
+            if (first_id[o] < 0) {
+                first_id[o] = C;
+                mult[o] = (max_cluster_size > 0 && cnt[o] > max_cluster_size) ? (int32_t)((cnt[o] + max_cluster_size - 1) / max_cluster_size) : 1;
+                C += mult[o];
+            }
+            cl[(size_t)i] = first_id[o] + (int32_t)(seen[o] % mult[o]);
+            seen[o] += 1;
+        }
+    }
+    std::vector<int64_t> cl_ptr((size_t)C + 1, 0);
+    for (int64_t i = 0; i < N; ++i)
+        cl_ptr[(size_t)cl[(size_t)i] + 1] += 1;
+    for (int c = 0; c < C; ++c)
+        cl_ptr[(size_t)c + 1] += cl_ptr[(size_t)c];
+    std::vector<int32_t> members((size_t)N), ring((size_t)N), ns_of((size_t)C);
+    {
+        std::vector<int64_t> cur(cl_ptr.begin(), cl_ptr.end() - 1);
+        for (int64_t i = 0; i < N; ++i)
+            members[(size_t)cur[(size_t)cl[(size_t)i]]++] = (int32_t)i;
+    }
+    std::vector<double> meanlib((size_t)C);
+    int n_max = 0;
+    for (int c = 0; c < C; ++c) {
+        const int64_t n = cl_ptr[(size_t)c + 1] - cl_ptr[(size_t)c];
+        int ns = 0;
+        while (ns < n_sizes && sz[(size_t)ns] <= n)
+            ++ns;
+        CB_CHECK(ctx, ns >= 1, "cb200_pooled_size_factors: not enough cells in at least one cluster for some 'sizes' "
+                               "(%lld cells, smallest pool %d)", (long long)n, sz[0]);
+        CB_CHECK(ctx, n < (1 << 30), "cb200_pooled_size_factors: cluster too large");
+        ns_of[(size_t)c] = ns;
+        n_max = n > n_max ? (int)n : n_max;
+    }
+    pool_parallel_for(C, [&](int c) {
+        const int64_t b = cl_ptr[(size_t)c], e = cl_ptr[(size_t)c + 1];
+        std::vector<int32_t> o(members.begin() + b, members.begin() + e);
+        std::stable_sort(o.begin(), o.end(), [&](int32_t a, int32_t bb) { return lib[(size_t)a] < lib[(size_t)bb]; });
+        const int64_t n = e - b;
+        int64_t w = b;
+        for (int64_t i = 0; i < n; i += 2)
+            ring[(size_t)w++] = o[(size_t)i];
+        for (int64_t i = (n & 1) ? n - 2 : n - 1; i >= 1; i -= 2)
+            ring[(size_t)w++] = o[(size_t)i];
+        double s = 0.0;
+        for (int64_t i = b; i < e; ++i)
+            s += lib[(size_t)members[(size_t)i]];
+        meanlib[(size_t)c] = s / (double)n;
+    });
+
+    // ---- device buffers
+    DevBuf<int32_t> d_cl, d_ring, d_sizes, d_ns, d_pslot, d_gf;
+    DevBuf<int64_t> d_clptr;
+    DevBuf<double> d_meanlib, d_pave, d_avefull, d_bvals, d_work, d_nf;
+    DevBuf<float> d_pinv;
+    DevBuf<unsigned long long> d_acc;
+    DevBuf<PoolItem> d_items;
+    struct BufGuard {
+        std::vector<std::function<void()>> f;
+        ~BufGuard()
+        {
+            for (auto &g : f)
+                g();
+        }
+    } guard;
+#define POOL_OWN(b) guard.f.push_back([&]() { b.release(); })
+    POOL_OWN(d_cl); POOL_OWN(d_ring); POOL_OWN(d_sizes); POOL_OWN(d_ns); POOL_OWN(d_pslot); POOL_OWN(d_gf); POOL_OWN(d_clptr);
+    POOL_OWN(d_meanlib); POOL_OWN(d_pave); POOL_OWN(d_avefull); POOL_OWN(d_bvals); POOL_OWN(d_work); POOL_OWN(d_nf);
+    POOL_OWN(d_pinv); POOL_OWN(d_acc); POOL_OWN(d_items);
+#undef POOL_OWN
+    const size_t CG = (size_t)C * (size_t)G;
+    CB_CUDA(ctx, d_cl.ensure((size_t)N));
+    CB_CUDA(ctx, d_ring.ensure((size_t)N));
+    CB_CUDA(ctx, d_sizes.ensure((size_t)n_sizes));
+    CB_CUDA(ctx, d_ns.ensure((size_t)C));
+    CB_CUDA(ctx, d_clptr.ensure((size_t)C + 1));
+    CB_CUDA(ctx, d_meanlib.ensure((size_t)C));
+    CB_CUDA(ctx, d_acc.ensure(CG));
+    CB_CUDA(ctx, d_pslot.ensure(CG));
+    CB_CUDA(ctx, d_pave.ensure(CG));
+    CB_CUDA(ctx, d_pinv.ensure(CG));
+    CB_CUDA(ctx, d_avefull.ensure(CG));
+    CB_CUDA(ctx, d_gf.ensure((size_t)C));
+    CB_CUDA(ctx, d_bvals.ensure((size_t)(n_sizes + 1) * N));
+    CB_CUDA(ctx, d_work.ensure((size_t)5 * N));
+    CB_CUDA(ctx, d_nf.ensure((size_t)N));
+    CB_TRY(cb200_h2d(ctx, d_cl.p, cl.data(), (size_t)N * sizeof(int32_t), ctx->stream));
+    CB_TRY(cb200_h2d(ctx, d_ring.p, ring.data(), (size_t)N * sizeof(int32_t), ctx->stream));
+    CB_TRY(cb200_h2d(ctx, d_sizes.p, sz.data(), (size_t)n_sizes * sizeof(int32_t), ctx->stream));
+    CB_TRY(cb200_h2d(ctx, d_ns.p, ns_of.data(), (size_t)C * sizeof(int32_t), ctx->stream));
+    CB_TRY(cb200_h2d(ctx, d_clptr.p, cl_ptr.data(), (size_t)(C + 1) * sizeof(int64_t), ctx->stream));
+    CB_TRY(cb200_h2d(ctx, d_meanlib.p, meanlib.data(), (size_t)C * sizeof(double), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(d_acc.p, 0, CG * sizeof(unsigned long long), ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(d_bvals.p, 0, (size_t)(n_sizes + 1) * N * sizeof(double), ctx->stream));
+    CB_TRY(cb200_need_rowidx(ctx));
+
+    // fixed-point scales: y <= 1; sums over at most n_max cells (pseudo-cell) / the largest pool (windows)
+    int bits1 = 1, bits2 = 1;
+    while ((1LL << bits1) <= (long long)n_max)
+        ++bits1;
+    while ((1LL << bits2) <= (long long)sz[(size_t)n_sizes - 1])
+        ++bits2;
+    const int s1 = 62 - bits1, s2 = 62 - bits2;
+
+    // ---- step 1
+    CB_CUDA(ctx, cudaEventRecord(ev[0], ctx->stream));
+    {
+        const int grid = cb_grid_for(N, 8, ctx->num_sms * 8);
+        k_pool_gene_sums<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->blk_w.p, d_cl.p, N, G,
+                                                        ldexp(1.0, s1), d_acc.p, ctx->flag.p);
+        CB_LAUNCH(ctx);
+        k_pool_filter<<<C, 256, 0, ctx->stream>>>(d_acc.p, d_clptr.p, d_meanlib.p, G, ldexp(1.0, -s1), ldexp(1.0, -s2), min_mean,
+                                                  d_pslot.p, d_pave.p, d_pinv.p, d_avefull.p, d_gf.p);
+        CB_LAUNCH(ctx);
+    }
+    CB_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
+    std::vector<int32_t> gf((size_t)C);
+    CB_TRY(cb200_d2h(ctx, gf.data(), d_gf.p, (size_t)C * sizeof(int32_t), ctx->stream));
+    int h_flag = 0;
+    CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
+    CB_CHECK(ctx, (h_flag & 1) == 0, "cb200_pooled_size_factors: a row index is outside [0, n_genes) or a count is negative / NaN");
+    int gf_max = 0;
+    for (int c = 0; c < C; ++c) {
+        CB_CHECK(ctx, gf[(size_t)c] >= 1, "cb200_pooled_size_factors: no gene of cluster %d reaches min.mean = %g", c, min_mean);
+        gf_max = gf[(size_t)c] > gf_max ? gf[(size_t)c] : gf_max;
+    }
+    const size_t smem = (((size_t)gf_max * 12 + 15) & ~(size_t)15) + sizeof(PoolShared);
+    CB_CHECK(ctx, smem <= 200 * 1024, "cb200_pooled_size_factors: %d genes pass min.mean in one cluster; the shared-memory "
+                                      "window holds at most %d (raise min.mean)", gf_max, (int)((200 * 1024 - sizeof(PoolShared)) / 12));
+
+    // ---- step 3: work items = (cluster, size, run of ring positions)
+    int64_t pairs = 0;
+    for (int c = 0; c < C; ++c)
+        pairs += (cl_ptr[(size_t)c + 1] - cl_ptr[(size_t)c]) * (ns_of[(size_t)c] + 1);
+    int L = (int)(pairs / ((int64_t)ctx->num_sms * 24));
+    L = L < 8 ? 8 : L > 64 ? 64 : L;
+    std::vector<PoolItem> items;
+    items.reserve((size_t)(pairs / L + (int64_t)C * (n_sizes + 1) + 16));
+    for (int c = 0; c < C; ++c) {
+        const int n = (int)(cl_ptr[(size_t)c + 1] - cl_ptr[(size_t)c]);
+        for (int si = -1; si < ns_of[(size_t)c]; ++si) {
+            const int size = si < 0 ? 1 : sz[(size_t)si];
+            const int64_t off = (int64_t)(si < 0 ? n_sizes : si) * N + cl_ptr[(size_t)c];
+            for (int p0 = 0; p0 < n; p0 += L)
+                items.push_back(PoolItem{c, size, p0, p0 + L < n ? p0 + L : n, off});
+        }
+    }
+    CB_CHECK(ctx, items.size() < (size_t)2147483647, "cb200_pooled_size_factors: too many work items");
+    CB_CUDA(ctx, d_items.ensure(items.size()));
+    CB_TRY(cb200_h2d(ctx, d_items.p, items.data(), items.size() * sizeof(PoolItem), ctx->stream));
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_pool_medians, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        per_sm = per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm;
+        int64_t grid = (int64_t)ctx->num_sms * per_sm;
+        if (grid > (int64_t)items.size())
+            grid = (int64_t)items.size();
+        k_pool_medians<<<(unsigned)grid, POOL_THREADS, smem, ctx->stream>>>(
+            d_items.p, (int)items.size(), ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->blk_w.p, d_ring.p, d_clptr.p, d_pslot.p,
+            d_pinv.p, d_pave.p, d_gf.p, d_meanlib.p, G, gf_max, ldexp(1.0, s2), ldexp(1.0, -s2), d_bvals.p, ctx->flag.p);
+        CB_LAUNCH(ctx);
+    }
+    CB_CUDA(ctx, cudaEventRecord(ev[2], ctx->stream));
+
+    // ---- step 4
+    k_pool_solve<<<C, 512, 0, ctx->stream>>>(d_clptr.p, d_sizes.p, d_ns.p, n_sizes, N, d_bvals.p, d_ring.p, ctx->blk_w.p,
+                                             d_work.p, d_work.p + N, d_work.p + 2 * N, d_work.p + 3 * N, d_work.p + 4 * N, d_nf.p);
+    CB_LAUNCH(ctx);
+    CB_CUDA(ctx, cudaEventRecord(ev[3], ctx->stream));
+    std::vector<double> nf((size_t)N), ave(CG);
+    CB_TRY(cb200_d2h(ctx, nf.data(), d_nf.p, (size_t)N * sizeof(double), ctx->stream));
+    CB_TRY(cb200_d2h(ctx, ave.data(), d_avefull.p, CG * sizeof(double), ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CB_TRY(cb200_read_back(ctx, &h_flag, ctx->flag.p, sizeof(int)));
+    CB_CHECK(ctx, (h_flag & 12) == 0, "cb200_pooled_size_factors: internal error in the median selection (flag %d)", h_flag);
+    const auto t_host = clk::now();
+
+    // ---- step 5 (host, G-sized): reference cluster, median ratios of the pseudo-cells, final scaling
+    int ref = 0;
+    {
+        std::vector<int64_t> nzc((size_t)C, 0);
+        pool_parallel_for(C, [&](int c) {
+            int64_t k = 0;
+            for (int64_t g = 0; g < G; ++g)
+                k += ave[(size_t)c * G + g] > 0.0 ? 1 : 0;
+            nzc[(size_t)c] = k;
+        });
+        for (int c = 1; c < C; ++c)
+            if (nzc[(size_t)c] > nzc[(size_t)ref])
+                ref = c;
+    }
+    std::vector<double> resc((size_t)C, 1.0);
+    std::vector<int> bad((size_t)C, 0);
+    pool_parallel_for(C, [&](int c) {
+        const double *cur = ave.data() + (size_t)c * G, *rp = ave.data() + (size_t)ref * G;
+        double cs = 0.0, rs = 0.0;
+        for (int64_t g = 0; g < G; ++g) {
+            cs += cur[g];
+            rs += rp[g];
+        }
+        std::vector<double> ratio;
+        ratio.reserve((size_t)G);
+        for (int64_t g = 0; g < G; ++g) {
+            const double grand = (cur[g] / cs + rp[g] / rs) / 2.0 * (cs + rs) / 2.0;
+            if (grand >= min_mean) {
+                const double q = cur[g] / rp[g];
+                if (q == q)   // na.rm
+                    ratio.push_back(q);
+            }
+        }
+        const double m = pool_median(ratio);
+        if (!(m > 0.0) || !std::isfinite(m))
+            bad[(size_t)c] = 1;
+        resc[(size_t)c] = m;
+    });
+    for (int c = 0; c < C; ++c)
+        CB_CHECK(ctx, bad[(size_t)c] == 0, "cb200_pooled_size_factors: inter-cluster rescaling factor for cluster %d is not strictly positive", c);
+    double pos_sum = 0.0;
+    int64_t n_pos = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        const double v = nf[(size_t)i] * resc[(size_t)cl[(size_t)i]];
+        sf_out[i] = v;
+        if (v > 0.0) {
+            pos_sum += v;
+            ++n_pos;
+        }
+    }
+    CB_CHECK(ctx, n_pos > 0, "cb200_pooled_size_factors: no positive size factor");
+    const double scale = (double)n_pos / pos_sum;
+    for (int64_t i = 0; i < N; ++i)
+        sf_out[i] *= scale;
+    if (n_nonpositive != nullptr)
+        *n_nonpositive = N - n_pos;
+    if (stage_ms_out != nullptr) {
+        float a = 0.f, b = 0.f, c2 = 0.f;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        cudaEventElapsedTime(&c2, ev[2], ev[3]);
+        stage_ms_out[0] = a;    // pseudo-cells + gene filter
+        stage_ms_out[1] = b;    // pool medians
+        stage_ms_out[2] = c2;   // circulant solves
+        stage_ms_out[3] = std::chrono::duration<double, std::milli>(clk::now() - t_host).count();   // host rescaling
+        stage_ms_out[4] = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();  // whole call
+    }
+    return 0;
+}

@@ -254,6 +254,38 @@ int cb200_pairwise_modularity(cb200_ctx *ctx, const int32_t *from, const int32_t
                               int64_t n_edges, const int32_t *labels, int64_t n, int n_clusters,
                               double *observed_out, double *expected_out, double *total_weight_out);
 
+/* ---- deconvolution (pooled) size factors ---------------------------------------------
+ * Replaces: scran::computeSumFactors(sce, clusters = sce_cl) = scuttle::pooledSizeFactors in
+ * /root/reference/R/doNormAndReduce.R:66-71 (the quickCluster call above it, :57-65, keeps its igraph walktrap;
+ * its labels are the `clusters` input).  Needs the whole count matrix resident in this context (cb200_load_csc
+ * with all cells).  clusters: host int32[N] codes >= 0, or NULL for one cluster; sizes: pool sizes (NULL =
+ * seq(21, 101, 5)), sizes above a cluster's cell count are dropped for that cluster; min_mean <= 0 = scuttle's
+ * guess (0.1 when the median library size is <= 50000, else 1); max_cluster_size <= 0 = no limit (scuttle's
+ * default is 3000).  sf_out[N]: the factors, scaled to unit mean over the positive ones; the count of
+ * non-positive factors (scuttle would warn and, with positive = TRUE, call cleanSizeFactors -- that repair stays
+ * with the caller) goes to n_nonpositive.  stage_ms_out (nullable, 5 doubles): pseudo-cells + gene filter, pool
+ * medians, least-squares solves (device ms), host rescaling, whole call (host ms). */
+int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters /* nullable */, const int32_t *sizes /* nullable */,
+                              int n_sizes, double min_mean, int64_t max_cluster_size, double *sf_out,
+                              int64_t *n_nonpositive /* nullable */, double *stage_ms_out /* nullable */);
+
+/* ---- the callers either side of the path that re-use its kernels ---------------------
+ * cb200_qc_metrics replaces scuttle::perCellQCMetrics(sce, subsets = list(mito =, Malat1 =, Ribo =)) in
+ * /root/reference/R/doQC.R:106-108: per cell the total count and the number of genes above detection_limit
+ * (scuttle's threshold = 0), and the same pair over each of n_subsets <= 8 gene subsets given CSR-style
+ * (subset_ptr[n_subsets + 1], subset_genes 0-based).  Outputs (host, nullable): sum_out[N], detected_out[N],
+ * subset_sum_out / subset_detected_out [n_subsets x N], subset s at offset s * N; subsets_*_percent is
+ * 100 * subset sum / sum, formed by the caller. */
+int cb200_qc_metrics(cb200_ctx *ctx, int n_subsets, const int32_t *subset_ptr, const int32_t *subset_genes,
+                     double detection_limit, double *sum_out, int32_t *detected_out, double *subset_sum_out,
+                     int32_t *subset_detected_out);
+/* cb200_knn_distances: the distance matrix findKNN(get.distance = TRUE) returns beside the index, for the kNN
+ * result left in HBM by the last cb200_knn / cb200_knn_device call (whose device embedding must still be alive):
+ * dist_out column-major n_queries x k, sqrt of the sequential fp64 sum of squares.  Lets
+ * uwot::umap(n_neighbors = floor(sqrt(N)), nn_method = list(idx, dist)) in
+ * /root/reference/R/doNormAndReduce.R:102-106 re-use the exact search instead of running its own. */
+int cb200_knn_distances(cb200_ctx *ctx, double *dist_out);
+
 /* ---- several GPUs of one node from ONE host process (what an R session needs: SURVEY.md 8b) -----------------
  * cb200_multi_init(n_gpus) opens devices 0 .. n_gpus-1 (n_gpus <= 0: all), one cb200_ctx each, and an NCCL
  * communicator over them (ncclCommInitAll; NCCL is loaded with dlopen here, the single-GPU path does not need it).

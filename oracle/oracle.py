@@ -489,6 +489,176 @@ def model_gene_var_blocked(means, vars_, n_per_block):
     return out
 
 
+# ---------------------------------------------------------------------------------------
+# deconvolution size factors (R/doNormAndReduce.R:66-71 -> scran::computeSumFactors =
+# scuttle::pooledSizeFactors), restated from the published algorithm (Lun, Bach & Marioni 2016, Genome Biol. 17:75,
+# and the package sources as recalled: un-vendored, parity unpinned).  quickCluster's walktrap stays igraph;
+# the clusters are an input here.
+# ---------------------------------------------------------------------------------------
+POOL_SIZES = tuple(range(21, 102, 5))
+POOL_LOWWEIGHT = 1e-6
+
+
+def limit_cluster_size(clusters, max_size=3000):
+    """scuttle:::.limit_cluster_size: a cluster with more than max_size cells is dealt round-robin into
+    ceiling(n / max_size) sub-clusters; new ids are numbered in order of first appearance."""
+    clusters = np.asarray(clusters)
+    out = np.zeros(clusters.size, dtype=np.int32)
+    counter = 0
+    _, first = np.unique(clusters, return_index=True)
+    for cid in clusters[np.sort(first)]:
+        cur = np.flatnonzero(clusters == cid)
+        if max_size is None or cur.size <= max_size:
+            out[cur] = counter
+            counter += 1
+            continue
+        mult = -(-cur.size // max_size)
+        out[cur] = counter + (np.arange(cur.size) % mult)
+        counter += mult
+    return out, counter
+
+
+def guess_min_mean(libsizes):
+    """scuttle:::.guessMinMean: UMI-like data (median library size <= 50000) -> 0.1, else 1."""
+    return 0.1 if float(np.median(libsizes)) <= 50000 else 1.0
+
+
+def pool_ring(libsizes):
+    """scuttle:::.generateSphere: cells by ascending library size (stable), odd ranks ascending then even ranks
+    descending, so that neighbours on the ring have similar library sizes."""
+    o = np.argsort(libsizes, kind="stable")
+    return np.concatenate([o[0::2], o[1::2][::-1]])
+
+
+def pooled_factors_one_cluster(dense_counts, sizes=POOL_SIZES, min_mean=0.1):
+    """scuttle:::.per_cluster_normalize on a dense genes x cells block.  Returns (final.nf, ave.cell)."""
+    x = np.asarray(dense_counts, dtype=np.float64)
+    n = x.shape[1]
+    lib = x.sum(axis=0)
+    if np.any(lib == 0):
+        raise ValueError("cells should have non-zero library sizes")
+    y = x / lib
+    ave = y.mean(axis=1) * lib.mean()
+    keep = ave >= min_mean
+    yk, avek = y[keep], ave[keep]
+    ring = pool_ring(lib)
+    sizes = [int(s) for s in sorted(sizes) if s <= n]
+    if not sizes:
+        raise ValueError("not enough cells in at least one cluster for some 'sizes'")
+    rows, cols, vals, rhs = [], [], [], []
+    r = 0
+    for s in sizes:
+        for i in range(n):
+            members = ring[(i + np.arange(s)) % n]
+            pooled = np.zeros(yk.shape[0])
+            for c in members:                     # sequential fp64 sum in ring order (pool_size_factors C++)
+                pooled = pooled + yk[:, c]
+            rhs.append(np.median(pooled / avek))
+            rows += [r] * s
+            cols += members.tolist()
+            vals += [1.0] * s
+            r += 1
+    lw = np.sqrt(POOL_LOWWEIGHT)
+    for i in range(n):
+        c = ring[i]
+        rhs.append(lw * np.median(yk[:, c] / avek))
+        rows.append(r)
+        cols.append(int(c))
+        vals.append(lw)
+        r += 1
+    design = np.zeros((r, n))
+    design[rows, cols] = vals
+    nf, *_ = np.linalg.lstsq(design, np.asarray(rhs), rcond=None)   # Matrix::qr + qr.coef in the package
+    return nf * lib, ave
+
+
+def rescale_clusters(profiles, ref, min_mean):
+    """scuttle:::.rescale_clusters: median ratio of every cluster's pseudo-cell to the reference cluster's over the
+    genes whose grand mean passes min_mean."""
+    out = np.zeros(len(profiles))
+    refp = profiles[ref]
+    for c, cur in enumerate(profiles):
+        cl, rl = cur.sum(), refp.sum()
+        use = (cur / cl + refp / rl) / 2 * (cl + rl) / 2 >= min_mean
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = cur[use] / refp[use]
+        val = float(np.median(ratio[~np.isnan(ratio)])) if np.any(~np.isnan(ratio)) else np.nan
+        if not np.isfinite(val) or val <= 0:
+            raise ValueError("inter-cluster rescaling factor is not strictly positive")
+        out[c] = val
+    return out
+
+
+def pooled_size_factors(n_genes, colptr, rowidx, x, clusters=None, sizes=POOL_SIZES, min_mean=None,
+                        max_cluster_size=3000):
+    """scuttle::pooledSizeFactors(counts, clusters = ...) for a CSC count matrix: per-cluster pooled factors, then
+    rescaling between clusters (reference = the cluster whose pseudo-cell has most non-zero genes), scaled to unit
+    mean over the positive factors.  No cleanSizeFactors step: non-positive factors are returned as they are."""
+    colptr = np.asarray(colptr, dtype=np.int64)
+    n = colptr.size - 1
+    clusters = np.zeros(n, dtype=np.int32) if clusters is None else np.asarray(clusters)
+    cl, ncl = limit_cluster_size(clusters, max_cluster_size)
+    lib_all = np.add.reduceat(np.asarray(x, dtype=np.float64), colptr[:-1]) if n else np.zeros(0)
+    lib_all[np.diff(colptr) == 0] = 0.0
+    if min_mean is None:
+        min_mean = guess_min_mean(lib_all)
+    min_mean = max(min_mean, 1e-8)
+    nfs, profiles, members = [], [], []
+    for c in range(ncl):
+        cells = np.flatnonzero(cl == c)
+        dense = np.zeros((n_genes, cells.size))
+        for j, cell in enumerate(cells):
+            sl = slice(colptr[cell], colptr[cell + 1])
+            dense[rowidx[sl], j] = x[sl]
+        nf, ave = pooled_factors_one_cluster(dense, sizes, min_mean)
+        nfs.append(nf)
+        profiles.append(ave)
+        members.append(cells)
+    ref = int(np.argmax([int((p > 0).sum()) for p in profiles]))
+    resc = rescale_clusters(profiles, ref, min_mean)
+    sf = np.full(n, np.nan)
+    for c in range(ncl):
+        sf[members[c]] = nfs[c] * resc[c]
+    pos = sf > 0
+    return sf / sf[pos].mean()
+
+
+# ---------------------------------------------------------------------------------------
+# SURVEY 8(f)-4: scuttle::perCellQCMetrics as doQC calls it (R/doQC.R:106-108); findKNN(get.distance = TRUE)
+# ---------------------------------------------------------------------------------------
+def per_cell_qc_metrics(n_genes, colptr, rowidx, x, subsets=(), threshold=0.0):
+    """sum, detected (count > threshold) and per subset: sum, detected, percent = 100 * subset sum / sum."""
+    colptr = np.asarray(colptr, dtype=np.int64)
+    n = colptr.size - 1
+    col_of = np.repeat(np.arange(n), np.diff(colptr))
+    x = np.asarray(x, dtype=np.float64)
+    out = dict(sum=np.bincount(col_of, weights=x, minlength=n),
+               detected=np.bincount(col_of, weights=(x > threshold), minlength=n).astype(np.int32), subsets=[])
+    for genes in subsets:
+        m = np.zeros(n_genes, dtype=bool)
+        m[np.asarray(genes, dtype=np.int64)] = True
+        sel = m[rowidx]
+        ssum = np.bincount(col_of[sel], weights=x[sel], minlength=n)
+        sdet = np.bincount(col_of[sel], weights=(x[sel] > threshold), minlength=n).astype(np.int32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out["subsets"].append(dict(sum=ssum, detected=sdet, percent=100.0 * ssum / out["sum"]))
+    return out
+
+
+def knn_distances(emb, index1):
+    """Distances of the neighbours in a 1-based index matrix, in the search's arithmetic (sequential fp64)."""
+    emb = np.asarray(emb, dtype=np.float64)
+    n, k = index1.shape
+    out = np.empty((n, k))
+    for c in range(k):
+        diff = emb - emb[index1[:, c] - 1]
+        s = np.zeros(n)
+        for t in range(emb.shape[1]):
+            s = s + diff[:, t] * diff[:, t]
+        out[:, c] = np.sqrt(s)
+    return out
+
+
 def get_top_hvgs(bio, n):
     """scran::getTopHVGs(stats, n=n): keep bio > 0, order(bio, decreasing=TRUE) (ties by
     row index), first n.  Returns 0-based row indices (row a6)."""

@@ -43,7 +43,20 @@ doNormAndReduce <- function(sce, batch = NULL, name = NULL,
                           min.size = floor(sqrt(min(table(colData(sce)[, batch])))), BPPARAM = parallel_param)
     else scran::quickCluster(sce, min.size = floor(sqrt(ncol(sce))), BPPARAM = parallel_param)
     if (verbose) message(.bluem("[NORM] "), "   Calculating pooled factors.")
-    sf_in <- sizeFactors(scran::computeSumFactors(sce, clusters = cl, BPPARAM = parallel_param))
+    if (identical(getOption("cellula.b200.sizefactors", "deconvolution"), "deconvolution_gpu") && .cb200_gpus() <= 1L) {
+      # SURVEY 8(f)-1: the pooling itself (N x 18 medians over the expressed genes + one least-squares solve per
+      # cluster) on the GPU; quickCluster's labels go in as integer codes.  Opt-in: scran's own call stays the default
+      # until an R host has pinned the two against each other (baseline/run_reference.R dumps both).
+      r <- .Call("cb200r_pooled_size_factors", ctx, as.integer(factor(cl)) - 1L, NULL, NA_real_, 3000, ncol(sce),
+                 PACKAGE = "cellulaB200")
+      sf_in <- r$sf
+      if (r$nonpositive > 0) {                       # scuttle: warning + cleanSizeFactors when positive = TRUE
+        warning("encountered non-positive size factor estimates")
+        sf_in <- scuttle::cleanSizeFactors(sf_in, num.detected = Matrix::colSums(cnt > 0))
+      }
+    } else {
+      sf_in <- sizeFactors(scran::computeSumFactors(sce, clusters = cl, BPPARAM = parallel_param))
+    }
   }
   if (verbose) message(.bluem("[NORM] "), "   Log-normalization.")
   sf <- .Call("cb200r_size_factors", ctx, sf_in, ncol(sce), PACKAGE = "cellulaB200")
@@ -115,8 +128,18 @@ doNormAndReduce <- function(sce, batch = NULL, name = NULL,
   if (!isTRUE(getOption("cellula.b200.skip_umap", FALSE))) {
     if (verbose) message(.bluem("[DR] "), "Running UMAP on uncorrected PCA.")
     neighbor_n <- floor(sqrt(ncol(sce)))
-    reducedDim(sce, "UMAP") <- umap(reducedDim(sce, "PCA")[, seq_len(ndims)],
+    space <- reducedDim(sce, "PCA")[, seq_len(ndims)]
+    nn <- NULL
+    if (isTRUE(getOption("cellula.b200.umap_knn", FALSE))) {
+      # SURVEY 8(f)-4: uwot searches neighbor_n neighbours (self included) with Annoy; hand it the exact GPU search
+      # instead (same kernel as makeSNNGraph's, k = neighbor_n - 1 others + the cell itself in column 1)
+      storage.mode(space) <- "double"
+      r <- .Call("cb200r_knn_with_distance", .cb200_ctx(), space, as.integer(neighbor_n - 1L), PACKAGE = "cellulaB200")
+      nn <- list(idx = cbind(seq_len(nrow(space)), r$index), dist = cbind(0, r$distance))
+    }
+    reducedDim(sce, "UMAP") <- umap(space,
                                     n_neighbors = neighbor_n,
+                                    nn_method = nn,
                                     seed = umap_seed,
                                     min_dist = 0.7)
   }

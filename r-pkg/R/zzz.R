@@ -56,3 +56,30 @@ pairwiseModularityB200 <- function(graph, clusters, get.weights = FALSE, as.rati
   else if (as.ratio) obs / expd
   else (obs - expd) / r$total
 }
+
+#' scuttle::perCellQCMetrics(sce, subsets = list(...)) on the GPU, as doQC() calls it (cellula R/doQC.R:106-108):
+#' same DataFrame columns (sum, detected, subsets_<name>_sum / _detected / _percent, total).
+perCellQCMetricsB200 <- function(sce, subsets = NULL, threshold = 0) {
+  cnt <- SingleCellExperiment::counts(sce)
+  if (!is(cnt, "dgCMatrix")) cnt <- as(cnt, "CsparseMatrix")
+  ctx <- .cb200_ctx()
+  .Call("cb200r_load_counts", ctx, cnt, PACKAGE = "cellulaB200")
+  idx <- lapply(subsets, function(s) {
+    if (is.character(s)) match(s, rownames(sce)) - 1L
+    else if (is.logical(s)) which(s) - 1L
+    else as.integer(s) - 1L
+  })
+  if (any(vapply(idx, anyNA, TRUE))) stop("subsets contain genes that are not rows of the object")
+  ptr <- as.integer(c(0L, cumsum(lengths(idx))))
+  r <- .Call("cb200r_qc_metrics", ctx, if (length(idx)) ptr else integer(0), as.integer(unlist(idx)), as.numeric(threshold),
+             ncol(sce), PACKAGE = "cellulaB200")
+  out <- S4Vectors::DataFrame(sum = r$sum, detected = r$detected, row.names = colnames(sce))
+  for (s in seq_along(idx)) {
+    nm <- names(subsets)[s]
+    out[[paste0("subsets_", nm, "_sum")]] <- r$subsets$sum[, s]
+    out[[paste0("subsets_", nm, "_detected")]] <- r$subsets$detected[, s]
+    out[[paste0("subsets_", nm, "_percent")]] <- r$subsets$sum[, s] / r$sum * 100
+  }
+  out$total <- r$sum
+  out
+}

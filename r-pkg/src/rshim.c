@@ -313,6 +313,71 @@ static cb200_ctx *single_ctx(cb200r_handle *h)
     return h->one;
 }
 
+/* scran::computeSumFactors(sce, clusters = cl) (cellula R/doNormAndReduce.R:66-71) on the resident counts.
+ * codes: 0-based integer cluster codes or NULL; sizes: integer pool sizes or NULL (seq(21, 101, 5)); min_mean: NA = guess.
+ * Returns list(sf, nonpositive, ms).  Single-GPU form only (the clusters are arbitrary cell subsets). */
+SEXP cb200r_pooled_size_factors(SEXP sctx, SEXP codes, SEXP sizes, SEXP min_mean, SEXP max_cluster_size, SEXP n_cells)
+{
+    cb200r_handle *h = get_handle(sctx);
+    if (h->one == NULL)
+        Rf_error("cellulaB200: pooled size factors need the single-GPU form (options(cellula.b200.gpus = 1L))");
+    SEXP sf = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(n_cells)));
+    SEXP ms = PROTECT(Rf_allocVector(REALSXP, 5));
+    SEXP nn = PROTECT(Rf_allocVector(REALSXP, 1));
+    int64_t nonpos = 0;
+    double mm = Rf_asReal(min_mean);
+    int rc = cb200_pooled_size_factors(h->one, Rf_isNull(codes) ? NULL : INTEGER(codes), Rf_isNull(sizes) ? NULL : INTEGER(sizes),
+                                       Rf_isNull(sizes) ? 0 : Rf_length(sizes), ISNAN(mm) ? -1.0 : mm,
+                                       (int64_t)Rf_asReal(max_cluster_size), REAL(sf), &nonpos, REAL(ms));
+    REAL(nn)[0] = (double)nonpos;
+    SEXP out = named_list3(sf, "sf", nn, "nonpositive", ms, "ms");
+    UNPROTECT(3);
+    if (rc != 0)
+        Rf_error("%s", last_error(h));
+    return out;
+}
+
+/* scuttle::perCellQCMetrics(sce, subsets) (cellula R/doQC.R:106-108) on the resident counts.  subset_ptr / subset_genes:
+ * CSR-style 0-based gene lists.  Returns list(sum, detected, subsets = list(sum = S x N by row, detected = ...)). */
+SEXP cb200r_qc_metrics(SEXP sctx, SEXP subset_ptr, SEXP subset_genes, SEXP threshold, SEXP n_cells)
+{
+    cb200r_handle *h = get_handle(sctx);
+    if (h->one == NULL)
+        Rf_error("cellulaB200: QC metrics need the single-GPU form (options(cellula.b200.gpus = 1L))");
+    int n = Rf_asInteger(n_cells), S = Rf_length(subset_ptr) - 1;
+    if (S < 0)
+        S = 0;
+    SEXP sum = PROTECT(Rf_allocVector(REALSXP, n)), det = PROTECT(Rf_allocVector(INTSXP, n));
+    SEXP ssum = PROTECT(Rf_allocMatrix(REALSXP, n, S)), sdet = PROTECT(Rf_allocMatrix(INTSXP, n, S));
+    int rc = cb200_qc_metrics(h->one, S, S > 0 ? INTEGER(subset_ptr) : NULL, S > 0 ? INTEGER(subset_genes) : NULL,
+                              Rf_asReal(threshold), REAL(sum), INTEGER(det), S > 0 ? REAL(ssum) : NULL,
+                              S > 0 ? INTEGER(sdet) : NULL);
+    SEXP sub = PROTECT(named_list3(ssum, "sum", sdet, "detected", R_NilValue, "unused"));
+    SEXP out = named_list3(sum, "sum", det, "detected", sub, "subsets");
+    UNPROTECT(5);
+    if (rc != 0)
+        Rf_error("%s", last_error(h));
+    return out;
+}
+
+/* findKNN(space, k, get.distance = TRUE): list(index, distance), both n x k -- what uwot::umap(nn_method = ) takes
+ * (cellula R/doNormAndReduce.R:102-106 with n_neighbors = floor(sqrt(N))). */
+SEXP cb200r_knn_with_distance(SEXP sctx, SEXP space, SEXP k)
+{
+    cb200_ctx *ctx = single_ctx(get_handle(sctx));
+    int64_t n = Rf_nrows(space);
+    int d = Rf_ncols(space), kk = Rf_asInteger(k);
+    SEXP idx = PROTECT(Rf_allocMatrix(INTSXP, (int)n, kk)), dist = PROTECT(Rf_allocMatrix(REALSXP, (int)n, kk));
+    int rc = cb200_knn(ctx, REAL(space), n, d, kk, 0, n, INTEGER(idx));
+    if (rc == 0)
+        rc = cb200_knn_distances(ctx, REAL(dist));
+    SEXP out = named_list3(idx, "index", dist, "distance", R_NilValue, "unused");
+    UNPROTECT(2);
+    if (rc != 0)
+        Rf_error("%s", cb200_last_error(ctx));
+    return out;
+}
+
 SEXP cb200r_approx_silhouette(SEXP sctx, SEXP space, SEXP codes, SEXP nclust)
 {
     cb200_ctx *ctx = single_ctx(get_handle(sctx));
@@ -375,6 +440,9 @@ static const R_CallMethodDef call_methods[] = {
     {"cb200r_pca", (DL_FUNC)&cb200r_pca, 4},
     {"cb200r_snn_graph", (DL_FUNC)&cb200r_snn_graph, 4},
     {"cb200r_knn", (DL_FUNC)&cb200r_knn, 3},
+    {"cb200r_pooled_size_factors", (DL_FUNC)&cb200r_pooled_size_factors, 6},
+    {"cb200r_qc_metrics", (DL_FUNC)&cb200r_qc_metrics, 5},
+    {"cb200r_knn_with_distance", (DL_FUNC)&cb200r_knn_with_distance, 3},
     {"cb200r_approx_silhouette", (DL_FUNC)&cb200r_approx_silhouette, 4},
     {"cb200r_pairwise_modularity", (DL_FUNC)&cb200r_pairwise_modularity, 6},
     {NULL, NULL, 0}};

@@ -31,6 +31,9 @@ int Rf_asInteger(SEXP);
 double Rf_asReal(SEXP);
 Rboolean Rf_isNull(SEXP);
 int Rf_nrows(SEXP);
+int Rf_length(SEXP);
+int R_IsNA(double);
+#define ISNAN(x) ((x) != (x))   /* R_ext/Arith.h: true for NA_real_ and NaN */
 int Rf_ncols(SEXP);
 void Rf_error(const char *, ...) __attribute__((noreturn));
 SEXP R_MakeExternalPtr(void *, SEXP, SEXP);

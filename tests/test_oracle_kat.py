@@ -153,3 +153,45 @@ def test_kat_pca_and_hvg_ranking():
     assert O.get_top_hvgs(np.array(h["bio"]), h["n"]).tolist() == h["top"]
     from cellula_b200 import trendvar
     assert trendvar.get_top_hvgs(np.array(h["bio"]), h["n"]).tolist() == h["top"]
+
+
+# ---- SURVEY 8(f)-1 / 8(f)-4 restatements -------------------------------------------------------------------
+def test_pool_ring_and_cluster_limit_known_answers():
+    from oracle import oracle as O
+    # libsizes ranks: cell 3 smallest ... ; odd ranks ascending, even ranks descending (scuttle:::.generateSphere)
+    lib = np.array([50.0, 20.0, 40.0, 10.0, 30.0, 20.0])
+    # order (stable): 3, 1, 5, 4, 2, 0 -> odd ranks (1st, 3rd, 5th) 3, 5, 2 then even ranks reversed 0, 4, 1
+    assert O.pool_ring(lib).tolist() == [3, 5, 2, 0, 4, 1]
+    cl = np.array([5, 5, 2, 5, 2, 5, 5, 5, 5])                      # 7 cells of cluster 5 -> ceil(7 / 3) = 3 parts
+    lim, n = O.limit_cluster_size(cl, 3)
+    assert n == 4 and lim.tolist() == [0, 1, 3, 2, 3, 0, 1, 2, 0]
+    assert O.guess_min_mean(np.array([100.0, 60000.0, 200.0])) == 0.1
+    assert O.guess_min_mean(np.array([100000.0, 60000.0, 200.0])) == 1.0
+
+
+def test_pooled_size_factors_recover_planted_scale():
+    from oracle import oracle as O
+    import scipy.sparse as sp
+    rng = np.random.default_rng(1)
+    G, N = 400, 150
+    lam = rng.gamma(2.0, 2.0, size=G)
+    s = np.exp(rng.normal(0, 0.4, size=N))
+    m = sp.csc_matrix(rng.poisson(lam[:, None] * s[None, :]).astype(float))
+    sf = O.pooled_size_factors(G, m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data, None)
+    assert abs(sf.mean() - 1) < 1e-12 and np.corrcoef(sf, s)[0, 1] > 0.99
+    # identical cells scaled by known factors: every pool ratio is exact, so the factors are the scales
+    base = rng.poisson(lam * 3).astype(float) + 1.0
+    scales = np.tile([1.0, 2.0, 4.0], 10)
+    m = sp.csc_matrix(base[:, None] * scales[None, :])
+    sf = O.pooled_size_factors(G, m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data, None, sizes=(5, 10))
+    assert np.allclose(sf, scales / scales.mean(), rtol=1e-9)
+
+
+def test_per_cell_qc_metrics_known_answer():
+    from oracle import oracle as O
+    # genes x cells = [[1, 0], [0, 3], [2, 5]]
+    colptr, rowidx, x = np.array([0, 2, 4]), np.array([0, 2, 1, 2]), np.array([1.0, 2.0, 3.0, 5.0])
+    q = O.per_cell_qc_metrics(3, colptr, rowidx, x, subsets=[[2], [0, 1]])
+    assert q["sum"].tolist() == [3.0, 8.0] and q["detected"].tolist() == [2, 2]
+    assert q["subsets"][0]["sum"].tolist() == [2.0, 5.0] and q["subsets"][1]["detected"].tolist() == [1, 1]
+    assert np.allclose(q["subsets"][0]["percent"], [200 / 3, 62.5])
