@@ -313,12 +313,13 @@ class Context:
         sz = None if sizes is None else np.ascontiguousarray(sorted(sizes), dtype=np.int32)
         out = np.empty(self.n_cells)
         nneg = c_i64()
-        ms = np.zeros(5)
+        ms = np.zeros(8)
         self._ck(lib().cb200_pooled_size_factors(self._h, _ptr(cl), _ptr(sz), 0 if sz is None else int(sz.size),
                                                  -1.0 if min_mean is None else float(min_mean),
                                                  0 if max_cluster_size is None else int(max_cluster_size), _ptr(out),
                                                  ctypes.byref(nneg), _ptr(ms)))
-        self.pool_ms = dict(zip(("pseudo_cells_ms", "pool_medians_ms", "solve_ms", "host_rescale_ms", "total_host_ms"),
+        self.pool_ms = dict(zip(("pseudo_cells_ms", "pool_medians_ms", "solve_ms", "host_rescale_ms", "total_host_ms", "kept_genes_max",
+                                 "clusters", "kept_entries"),
                                 ms.tolist()))
         return out, int(nneg.value)
 

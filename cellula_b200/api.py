@@ -76,12 +76,24 @@ def doNormAndReduce(sce, batch=None, name=None, ndims=20, hvg_ntop=2000, umap_se
     # Size factors.  The reference runs scran deconvolution first (R/doNormAndReduce.R:57-71);
     # here library-size factors are the default and a pre-set sizeFactor column (e.g. deconvolution
     # factors computed elsewhere) is re-centred exactly as logNormCounts would.
-    sf_in = sce.colData.get("sizeFactor") if options["size_factors"] != "library" else None
+    sf_in = sce.colData.get("sizeFactor") if options["size_factors"] == "given" else None
+    if options["size_factors"] == "deconvolution":
+        # scran::computeSumFactors on the GPU (R/doNormAndReduce.R:66-71).  quickCluster's walktrap is
+        # igraph code that stays outside this library: its labels are read from colData["quickCluster"]; without them
+        # the pooling runs on one cluster dealt into parts of <= 3000 cells (computeSumFactors(clusters = NULL)).
+        if verbose:
+            _message(_blue("[NORM] "), "   Calculating pooled factors.")
+        cl = sce.colData.get("quickCluster")
+        codes = None if cl is None else np.unique(np.asarray(cl), return_inverse=True)[1].astype(np.int32)
+        sf_in, n_bad = ctx.pooled_size_factors(codes)
+        if n_bad:
+            raise ValueError(ep + f"{n_bad} non-positive size factor estimates (scuttle::cleanSizeFactors is not part of "
+                             "this mirror)")
     if verbose and sf_in is None:
         # the R drop-in (r-pkg/) runs the reference's own quickCluster + computeSumFactors by default; this mirror
         # has no scran, so its default is the library-size fast path -- announced, because the numbers differ
-        _message(_blue("[NORM] "), "   Library-size factors: cellula's default is scran deconvolution (set colData['sizeFactor'] "
-                 "and options['size_factors'] = 'given' to pass such factors in); results differ from that default.")
+        _message(_blue("[NORM] "), "   Library-size factors: cellula's default is scran deconvolution (options['size_factors'] = "
+                 "'deconvolution' computes it on the GPU, 'given' takes colData['sizeFactor']); results differ from that default.")
     if verbose:
         _message(_blue("[NORM] "), "   Log-normalization.")
     sf = ctx.size_factors(sf_in)

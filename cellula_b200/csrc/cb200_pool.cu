@@ -21,7 +21,7 @@
 //     memory as 64-bit FIXED-POINT integers (2^s2 * y, exact integer adds), so sliding the window -- add the entering
 //     cell's column, subtract the leaving one's -- is exact and drift-free, and an empty gene is exactly zero.
 //     The median is a bucket selection in shared memory: zeros are counted apart, the non-zero ratios are
-//     histogrammed on fp32 keys into 2 048 buckets spanning [0, 4 x previous median), the bucket holding the
+//     histogrammed on fp32 keys into 1 024 buckets spanning [0, 4 x previous median), the bucket holding the
 //     wanted rank is gathered (a handful of genes) and ranked exactly in fp64 on (ratio, gene).  The range adapts
 //     (widen / narrow) until the bucket is small, so any distribution terminates; ties collapse to one value.
 //     fp32 keys only decide bucket membership: a gene within 1e-7 relative of a bucket edge may be ranked across
@@ -41,9 +41,10 @@
 
 #include "cb200_common.cuh"
 
-#define POOL_THREADS 512
-#define POOL_NB 2048
-#define POOL_CAP 512
+#define POOL_THREADS 256
+#define POOL_NB 1024
+#define POOL_CAP 256
+#define POOL_BYTES_PER_GENE 14   // window int64 + reciprocal fp32 + bucket id uint16
 #define POOL_LOWWEIGHT 1e-6
 
 struct PoolItem {
@@ -156,24 +157,72 @@ struct PoolShared {
     int list_s[POOL_CAP];
     unsigned long long next_min;   // bit pattern of the smallest exact ratio beyond the gathered bucket
     double res[2];
+    int wsum[POOL_THREADS / 32];
     int n_zero, n_below, n_list, n_in;
     int bucket, cum, cnt, tie_slot;
 };
+#define POOL_BKT_NONE 0xffffu    // zero entry, or below the range
+#define POOL_BKT_ABOVE 0xfffeu   // beyond the range
 
-// all threads of the CTA add (sign = +1) or subtract (sign = -1) one cell's column to the window W
-__device__ __forceinline__ void pool_apply_column(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
-                                                  const double *__restrict__ x, const double *__restrict__ lib,
-                                                  const int32_t *__restrict__ slot_of, int cell, double scale, int sign,
-                                                  unsigned long long *W, int tid, int nthreads)
+// Compact store of the kept entries, in RING order: position r of the ring (clusters concatenated) owns the entries
+// [cptr[r], cptr[r + 1]) = (slot of the gene among its cluster's kept genes, fixed-point y).  The cells of a window are
+// consecutive ring positions, so a window is one contiguous range (two at the wrap-around) and a slide touches two
+// short contiguous ranges: no dependent gene -> slot look-ups on the way.
+__global__ void __launch_bounds__(256)
+k_pool_compact(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx, const double *__restrict__ x,
+               const double *__restrict__ lib, const int32_t *__restrict__ ring, const int32_t *__restrict__ cl_of,
+               const int32_t *__restrict__ pslot, int64_t n_cols, int64_t G, double scale, const int64_t *__restrict__ cptr,
+               int32_t *__restrict__ kcnt, uint16_t *__restrict__ eslot, long long *__restrict__ eq)
 {
-    const int64_t b = colptr[cell], e = colptr[cell + 1];
-    const double r = scale / lib[cell];
-    for (int64_t i = b + tid; i < e; i += nthreads) {
-        const int s = __ldg(slot_of + __ldg(rowidx + i));
-        if (s >= 0) {
-            const long long q = __double2ll_rn(__ldg(x + i) * r);
-            atomicAdd(W + s, (unsigned long long)(sign > 0 ? q : -q));
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp0; r < n_cols; r += nwarps) {
+        const int cell = ring[r];
+        const int64_t b = colptr[cell], e = colptr[cell + 1];
+        const int32_t *slot_of = pslot + (int64_t)cl_of[cell] * G;
+        const double sc = scale / lib[cell];
+        int64_t out = cptr != nullptr ? cptr[r] : 0;
+        int total = 0;
+        for (int64_t i0 = b; i0 < e; i0 += 32) {
+            const int64_t i = i0 + lane;
+            int sl = -1;
+            if (i < e)
+                sl = __ldg(slot_of + ld_stream_i(rowidx + i));
+            const unsigned m = __ballot_sync(0xffffffffu, sl >= 0);
+            if (cptr != nullptr && sl >= 0) {
+                const int64_t o = out + __popc(m & ((1u << lane) - 1u));
+                eslot[o] = (uint16_t)sl;
+                eq[o] = __double2ll_rn(ld_stream(x + i) * sc);
+            }
+            out += __popc(m);
+            total += __popc(m);
         }
+        if (cptr == nullptr && lane == 0)
+            kcnt[r] = total;
+    }
+}
+
+// all threads of the CTA add (sign = +1) or subtract (sign = -1) the entries [b, e) of the compact store
+__device__ __forceinline__ void pool_apply_range(const uint16_t *__restrict__ eslot, const long long *__restrict__ eq, int64_t b,
+                                                 int64_t e, int sign, unsigned long long *W, int tid)
+{
+    int64_t i = b + tid;
+    for (; i + 3 * POOL_THREADS < e; i += 4 * POOL_THREADS) {   // four independent loads in flight per thread
+        long long q[4];
+        uint16_t sl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            q[u] = __ldg(eq + i + u * POOL_THREADS);
+            sl[u] = __ldg(eslot + i + u * POOL_THREADS);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            atomicAdd(W + sl[u], (unsigned long long)(sign > 0 ? q[u] : -q[u]));
+    }
+    for (; i < e; i += POOL_THREADS) {
+        const long long q = __ldg(eq + i);
+        atomicAdd(W + __ldg(eslot + i), (unsigned long long)(sign > 0 ? q : -q));
     }
 }
 
@@ -182,19 +231,45 @@ __device__ __forceinline__ float pool_key(unsigned long long w, float inv)
     return (float)(long long)w * inv;
 }
 
-// Element of 0-based rank r among the NON-ZERO ratios of the window (and the next one when want_next), exact in fp64
-// up to the bucket-edge caveat in the header.  Results in sh->res[0..1].  All threads must call it.
-__device__ void pool_select(PoolShared *sh, const unsigned long long *W, const float *inv, const double *__restrict__ ave, int gf,
-                            int r, bool want_next, float &guess, double inv_scale2, int *__restrict__ flag)
+// bucket code of one window entry for the range [lo, hi); counts it and, inside the range, adds it to the histogram
+__device__ __forceinline__ unsigned int pool_classify(unsigned long long w, float iv, float lo, float hi, float scale,
+                                                      unsigned int *hist, int &zero, int &below, int &in)
 {
-    const int tid = threadIdx.x;
+    const float key = pool_key(w, iv);
+    const bool z = w == 0ULL;
+    const bool bl = !z && key < lo;
+    const bool inr = !z && !bl && key < hi;
+    int bb = (int)((key - lo) * scale);   // only used inside the range
+    bb = bb > POOL_NB - 1 ? POOL_NB - 1 : bb;
+    bb = bb < 0 ? 0 : bb;
+    if (inr)
+        atomicAdd(hist + bb, 1u);
+    zero += z ? 1 : 0;
+    below += bl ? 1 : 0;
+    in += inr ? 1 : 0;
+    return inr ? (unsigned int)bb : ((z || bl) ? POOL_BKT_NONE : POOL_BKT_ABOVE);
+}
+
+// Median of the gf ratios W[g] * inv[g] of the window (zeros included), exact in fp64 up to the bucket-edge caveat in
+// the header.  All threads of the CTA must call it; every thread returns the same value.  `guess` carries the scale
+// of the previous median from one ring position to the next.
+__device__ double pool_median_select(PoolShared *sh, const unsigned long long *W, const float *inv, uint16_t *bkt,
+                                     const double *__restrict__ ave, int gf, float &guess, double inv_scale2, int *__restrict__ flag)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = gf / 2;
+    const bool even = (gf & 1) == 0;
     float lo = 0.f, hi = 4.f * guess;
     if (!(hi > 0.f) || isinf(hi))
         hi = 1.f;
     for (int round = 0; round < 96; ++round) {
-        for (int b = tid; b < POOL_NB; b += POOL_THREADS)
-            sh->hist[b] = 0;
+        {
+            uint4 *h4 = reinterpret_cast<uint4 *>(sh->hist);
+            for (int b = tid; b < POOL_NB / 4; b += POOL_THREADS)
+                h4[b] = make_uint4(0u, 0u, 0u, 0u);
+        }
         if (tid == 0) {
+            sh->n_zero = 0;
             sh->n_below = 0;
             sh->n_in = 0;
             sh->n_list = 0;
@@ -202,32 +277,47 @@ __device__ void pool_select(PoolShared *sh, const unsigned long long *W, const f
             sh->next_min = ~0ULL;
         }
         __syncthreads();
+        // pass A: zeros, entries below the range, histogram of the entries inside it; the bucket of every gene is kept
         const float scale = (float)POOL_NB / (hi - lo);
-        int below = 0, in = 0;
-        for (int g = tid; g < gf; g += POOL_THREADS) {
-            const unsigned long long w = W[g];
-            if (w == 0ULL)
-                continue;
-            const float key = pool_key(w, inv[g]);
-            if (key < lo) {
-                ++below;
-            } else if (key < hi) {
-                int b = (int)((key - lo) * scale);
-                b = b > POOL_NB - 1 ? POOL_NB - 1 : b;
-                atomicAdd(&sh->hist[b], 1u);
-                ++in;
+        int zero = 0, below = 0, in = 0;
+        {
+            // two entries per thread and step: one 128-bit + one 64-bit shared load, one 32-bit store of both bucket ids
+            const ulonglong2 *W2 = reinterpret_cast<const ulonglong2 *>(W);
+            const float2 *inv2 = reinterpret_cast<const float2 *>(inv);
+            unsigned int *bkt2 = reinterpret_cast<unsigned int *>(bkt);
+            const int npair = gf >> 1;
+#pragma unroll 2
+            for (int i = tid; i < npair; i += POOL_THREADS) {
+                const ulonglong2 w = W2[i];
+                const float2 iv = inv2[i];
+                const unsigned int b0 = pool_classify(w.x, iv.x, lo, hi, scale, sh->hist, zero, below, in);
+                const unsigned int b1 = pool_classify(w.y, iv.y, lo, hi, scale, sh->hist, zero, below, in);
+                bkt2[i] = b0 | (b1 << 16);
             }
+            if ((gf & 1) && tid == 0)
+                bkt[gf - 1] = (uint16_t)pool_classify(W[gf - 1], inv[gf - 1], lo, hi, scale, sh->hist, zero, below, in);
         }
+        zero = warp_sum_i(zero);
         below = warp_sum_i(below);
         in = warp_sum_i(in);
-        if ((tid & 31) == 0) {
+        if (lane == 0) {
+            if (zero)
+                atomicAdd(&sh->n_zero, zero);
             if (below)
                 atomicAdd(&sh->n_below, below);
             if (in)
                 atomicAdd(&sh->n_in, in);
         }
         __syncthreads();
-        const int n_below = sh->n_below, n_in = sh->n_in;
+        const int nz = sh->n_zero, n_below = sh->n_below, n_in = sh->n_in;
+        // the wanted rank(s) among the non-zero ratios
+        if (half < nz) {
+            __syncthreads();   // counters read by everybody before the next call resets them
+            return 0.0;
+        }
+        const bool lower_is_zero = even && half - 1 < nz;                     // lower middle is a zero
+        const int r = even ? (lower_is_zero ? 0 : half - 1 - nz) : half - nz;   // first wanted non-zero rank
+        const bool want_next = even && !lower_is_zero;
         if (r < n_below) {   // the range starts too high (only after a narrowing step met a rounding edge)
             const float wd = hi - lo;
             hi = lo;
@@ -244,37 +334,53 @@ __device__ void pool_select(PoolShared *sh, const unsigned long long *W, const f
             __syncthreads();
             continue;
         }
-        // the wanted rank is inside [lo, hi): find its bucket (warp 0: 64 buckets per lane, then a warp scan)
-        if (tid < 32) {
-            int s = 0;
-            for (int q = 0; q < POOL_NB / 32; ++q)
-                s += (int)sh->hist[tid * (POOL_NB / 32) + q];
-            int incl = s;
+        // bucket of the wanted rank: block-wide scan of the histogram, POOL_NB / POOL_THREADS buckets per thread
+        constexpr int BPT = POOL_NB / POOL_THREADS;
+        unsigned int hv[BPT];
+        {
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(sh->hist + tid * BPT);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (tid >= o)
-                    incl += t;
+            for (int q = 0; q < BPT / 4; ++q) {
+                const uint4 v = h4[q];
+                hv[4 * q] = v.x;
+                hv[4 * q + 1] = v.y;
+                hv[4 * q + 2] = v.z;
+                hv[4 * q + 3] = v.w;
             }
-            const int excl = incl - s;
-            const int want = r - n_below;
-            if (want >= excl && want < incl) {
-                int cum = excl;
-                for (int q = 0; q < POOL_NB / 32; ++q) {
-                    const int h = (int)sh->hist[tid * (POOL_NB / 32) + q];
-                    if (want < cum + h) {
-                        sh->bucket = tid * (POOL_NB / 32) + q;
-                        sh->cum = cum;
-                        sh->cnt = h;
-                        break;
-                    }
-                    cum += h;
+        }
+        int mine = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q)
+            mine += (int)hv[q];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            sh->wsum[warp] = incl;
+        __syncthreads();
+        int excl = incl - mine;
+        for (int q = 0; q < warp; ++q)
+            excl += sh->wsum[q];
+        const int want_in = r - n_below;
+        if (want_in >= excl && want_in < excl + mine) {
+            int cum = excl;
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) {
+                if (want_in >= cum && want_in < cum + (int)hv[q]) {
+                    sh->bucket = tid * BPT + q;
+                    sh->cum = cum;
+                    sh->cnt = (int)hv[q];
                 }
+                cum += (int)hv[q];
             }
         }
         __syncthreads();
         const int bucket = sh->bucket, cnt = sh->cnt;
-        const int want = r - n_below - sh->cum;   // rank inside the bucket
+        const int want = want_in - sh->cum;   // rank inside the bucket
         const float blo = lo + (float)bucket / scale, bhi = lo + (float)(bucket + 1) / scale;
         const bool degenerate = !(bhi > blo);   // the bucket cannot be split further in fp32: its keys are one value
         if (cnt > POOL_CAP && !degenerate && round < 90) {   // narrow to this bucket (membership is recounted next round)
@@ -285,84 +391,87 @@ __device__ void pool_select(PoolShared *sh, const unsigned long long *W, const f
         }
         // gather the bucket; beyond it, the smallest exact ratio (the "next" element when the bucket ends at the wanted rank)
         const bool need_outside = want_next && want == cnt - 1;
-        for (int g = tid; g < gf; g += POOL_THREADS) {
-            const unsigned long long w = W[g];
-            if (w == 0ULL)
-                continue;
-            const float key = pool_key(w, inv[g]);
-            if (key < lo)
-                continue;
-            int b = POOL_NB;   // beyond the range
-            if (key < hi) {
-                b = (int)((key - lo) * scale);
-                b = b > POOL_NB - 1 ? POOL_NB - 1 : b;
-            }
-            if (b == bucket) {
-                if (cnt <= POOL_CAP) {
-                    const int pos = atomicAdd(&sh->n_list, 1);
-                    if (pos < POOL_CAP) {
-                        sh->list_s[pos] = g;
-                        sh->list_v[pos] = ((double)(long long)w * inv_scale2) / ave[g];
+        {
+            // eight bucket ids per thread and step (the ids beyond gf are POOL_BKT_NONE)
+            const uint4 *b4 = reinterpret_cast<const uint4 *>(bkt);
+            const int n8 = (gf + 7) >> 3;
+            for (int i = tid; i < n8; i += POOL_THREADS) {
+                const uint4 v = b4[i];
+                const unsigned int word[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    const unsigned int b = (word[h >> 1] >> (16 * (h & 1))) & 0xffffu;
+                    const int g = 8 * i + h;
+                    if (b == (unsigned int)bucket) {
+                        if (cnt <= POOL_CAP) {
+                            const int pos = atomicAdd(&sh->n_list, 1);
+                            if (pos < POOL_CAP) {
+                                sh->list_s[pos] = g;
+                                sh->list_v[pos] = ((double)(long long)W[g] * inv_scale2) / ave[g];
+                            }
+                        } else {
+                            atomicMin(&sh->tie_slot, g);   // more equal keys than the list holds: they are one value
+                        }
+                    } else if (need_outside && b > (unsigned int)bucket && b != POOL_BKT_NONE) {
+                        const double vv = ((double)(long long)W[g] * inv_scale2) / ave[g];
+                        atomicMin(&sh->next_min, (unsigned long long)__double_as_longlong(vv));
                     }
-                } else {
-                    atomicMin(&sh->tie_slot, g);   // more equal keys than the list holds: they are one value
                 }
-            } else if (b > bucket && need_outside) {
-                const double v = ((double)(long long)w * inv_scale2) / ave[g];
-                atomicMin(&sh->next_min, (unsigned long long)__double_as_longlong(v));
             }
         }
         __syncthreads();
+        double v0, v1;
         if (cnt > POOL_CAP) {
-            if (tid == 0) {
-                const int g = sh->tie_slot;
-                const double v = ((double)(long long)W[g] * inv_scale2) / ave[g];
-                sh->res[0] = v;
-                sh->res[1] = v;
+            const int g = sh->tie_slot;
+            v0 = v1 = ((double)(long long)W[g] * inv_scale2) / ave[g];
+        } else {
+            const int nl = sh->n_list < POOL_CAP ? sh->n_list : POOL_CAP;
+            if (tid < nl) {
+                const double v = sh->list_v[tid];
+                const int sl = sh->list_s[tid];
+                int rank = 0;
+                for (int j = 0; j < nl; ++j) {
+                    const double u = sh->list_v[j];
+                    rank += (u < v || (u == v && sh->list_s[j] < sl)) ? 1 : 0;
+                }
+                if (rank == want)
+                    sh->res[0] = v;
+                if (want_next && rank == want + 1)
+                    sh->res[1] = v;
             }
+            if (tid == 0 && sh->n_list != cnt)
+                atomicOr(flag, 8);   // histogram and gather disagree: internal error
             __syncthreads();
-            return;
+            v0 = sh->res[0];
+            v1 = need_outside ? __longlong_as_double((long long)sh->next_min) : sh->res[1];
         }
-        const int nl = sh->n_list < POOL_CAP ? sh->n_list : POOL_CAP;
-        if (tid < nl) {
-            const double v = sh->list_v[tid];
-            const int s = sh->list_s[tid];
-            int rank = 0;
-            for (int j = 0; j < nl; ++j) {
-                const double u = sh->list_v[j];
-                rank += (u < v || (u == v && sh->list_s[j] < s)) ? 1 : 0;
-            }
-            if (rank == want)
-                sh->res[0] = v;
-            if (want_next && rank == want + 1)
-                sh->res[1] = v;
-        }
-        if (tid == 0 && sh->n_list != cnt)
-            atomicOr(flag, 8);   // histogram and gather disagree: internal error
-        __syncthreads();
-        if (need_outside && tid == 0)
-            sh->res[1] = __longlong_as_double((long long)sh->next_min);
-        __syncthreads();
-        guess = (float)sh->res[0];
-        return;
+        guess = (float)v0;
+        __syncthreads();   // res / counters consumed before the next call rewrites them
+        if (!even)
+            return v0;
+        return lower_is_zero ? (0.0 + v0) / 2.0 : (v1 + v0) / 2.0;
     }
     if (tid == 0)
         atomicOr(flag, 4);   // no convergence of the bucket search (not expected)
     __syncthreads();
+    return 0.0;
 }
 
-__global__ void __launch_bounds__(POOL_THREADS)
-k_pool_medians(const PoolItem *__restrict__ items, int n_items, const int64_t *__restrict__ colptr,
-               const int32_t *__restrict__ rowidx, const double *__restrict__ x, const double *__restrict__ lib,
-               const int32_t *__restrict__ ring, const int64_t *__restrict__ cl_ptr, const int32_t *__restrict__ pslot,
+#define POOL_PREF 4   // entries per thread and column prefetched into registers ahead of a slide
+
+__global__ void __launch_bounds__(POOL_THREADS, 4)
+k_pool_medians(const PoolItem *__restrict__ items, int n_items, const int64_t *__restrict__ cptr,
+               const uint16_t *__restrict__ eslot, const long long *__restrict__ eq, const int64_t *__restrict__ cl_ptr,
                const float *__restrict__ pinv, const double *__restrict__ pave, const int32_t *__restrict__ gf_of,
-               const double *__restrict__ meanlib, int64_t G, int gf_max, double scale2, double inv_scale2,
-               double *__restrict__ bvals, int *__restrict__ flag)
+               const double *__restrict__ meanlib, int64_t G, int gf_max, double inv_scale2, double *__restrict__ bvals,
+               int *__restrict__ flag)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int gfp = (gf_max + 7) & ~7;   // array strides: multiples of 8 genes keep every array 16-byte aligned
     unsigned long long *W = reinterpret_cast<unsigned long long *>(smem_raw);
-    float *inv = reinterpret_cast<float *>(W + gf_max);
-    PoolShared *sh = reinterpret_cast<PoolShared *>(smem_raw + (((size_t)gf_max * 12 + 15) & ~(size_t)15));
+    float *inv = reinterpret_cast<float *>(W + gfp);
+    uint16_t *bkt = reinterpret_cast<uint16_t *>(inv + gfp);
+    PoolShared *sh = reinterpret_cast<PoolShared *>(smem_raw + (size_t)gfp * POOL_BYTES_PER_GENE);
     const int tid = threadIdx.x;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const PoolItem item = items[it];
@@ -370,66 +479,63 @@ k_pool_medians(const PoolItem *__restrict__ items, int n_items, const int64_t *_
         const int64_t base = cl_ptr[c];
         const int n = (int)(cl_ptr[c + 1] - base);
         const int gf = gf_of[c];
-        const int32_t *slot_of = pslot + (int64_t)c * G;
         const double *ave = pave + (int64_t)c * G;
+        const int64_t *cp = cptr + base;   // cp[r] .. cp[r + 1]: entries of ring position r of this cluster
         __syncthreads();   // previous item fully done with W / sh
         for (int g = tid; g < gf; g += POOL_THREADS) {
             W[g] = 0ULL;
             inv[g] = pinv[(int64_t)c * G + g];
         }
+        if ((gf & 7) != 0 && tid < 8 && (gf & ~7) + tid >= gf)
+            bkt[(gf & ~7) + tid] = (uint16_t)POOL_BKT_NONE;   // ids beyond gf in the last group of 8
         __syncthreads();
-        // window of the first position: warps take the cells round-robin
+        // window of the first position: ring positions p0 .. p0 + size - 1 (mod n) = one or two contiguous ranges
+        int po = item.p0 % n;             // ring position that leaves at the next slide ...
+        int pi = (item.p0 + size) % n;    // ... and the one that enters
         {
-            const int warp = tid >> 5, lane = tid & 31;
-            for (int t = warp; t < size; t += POOL_THREADS / 32)
-                pool_apply_column(colptr, rowidx, x, lib, slot_of, ring[base + (item.p0 + t) % n], scale2, +1, W, lane, 32);
+            const int first = po + size <= n ? size : n - po;
+            pool_apply_range(eslot, eq, cp[po], cp[po + first], +1, W, tid);
+            if (first < size)
+                pool_apply_range(eslot, eq, cp[0], cp[size - first], +1, W, tid);
         }
         __syncthreads();
         float guess = (float)(0.5 * (double)size / meanlib[c]);
-        const int half = gf / 2;
-        const bool even = (gf & 1) == 0;
         for (int p = item.p0; p < item.p1; ++p) {
-            // zeros of the window
-            if (tid == 0)
-                sh->n_zero = 0;
-            __syncthreads();
-            int z = 0;
-            for (int g = tid; g < gf; g += POOL_THREADS)
-                z += W[g] == 0ULL ? 1 : 0;
-            z = warp_sum_i(z);
-            if ((tid & 31) == 0 && z)
-                atomicAdd(&sh->n_zero, z);
-            __syncthreads();
-            const int nz = sh->n_zero;
-            double med;
-            if (!even) {
-                if (half < nz) {
-                    med = 0.0;
-                } else {
-                    pool_select(sh, W, inv, ave, gf, half - nz, false, guess, inv_scale2, flag);
-                    med = sh->res[0];
-                }
-            } else {
-                if (half < nz) {
-                    med = 0.0;
-                } else if (half - 1 < nz) {   // lower middle is a zero, upper middle the smallest non-zero ratio
-                    pool_select(sh, W, inv, ave, gf, 0, false, guess, inv_scale2, flag);
-                    med = (0.0 + sh->res[0]) / 2.0;
-                } else {
-                    pool_select(sh, W, inv, ave, gf, half - 1 - nz, true, guess, inv_scale2, flag);
-                    med = (sh->res[1] + sh->res[0]) / 2.0;
+            // the two columns of the coming slide are requested now and applied after the median
+            const bool slide = p + 1 < item.p1 && size < n;
+            int64_t ob = 0, oe = 0, ib = 0, ie = 0;
+            uint16_t os[POOL_PREF], is[POOL_PREF];
+            long long oq[POOL_PREF], iq[POOL_PREF];
+            if (slide) {
+                ob = cp[po];
+                oe = cp[po + 1];
+                ib = cp[pi];
+                ie = cp[pi + 1];
+#pragma unroll
+                for (int u = 0; u < POOL_PREF; ++u) {
+                    const int64_t i = ob + tid + u * POOL_THREADS, j = ib + tid + u * POOL_THREADS;
+                    os[u] = i < oe ? __ldg(eslot + i) : (uint16_t)0;
+                    oq[u] = i < oe ? __ldg(eq + i) : 0LL;
+                    is[u] = j < ie ? __ldg(eslot + j) : (uint16_t)0;
+                    iq[u] = j < ie ? __ldg(eq + j) : 0LL;
                 }
             }
+            const double med = pool_median_select(sh, W, inv, bkt, ave, gf, guess, inv_scale2, flag);
             if (tid == 0)
                 bvals[item.out_off + p] = med;
-            __syncthreads();   // res consumed before the next selection rewrites it
-            if (p + 1 < item.p1 && size < n) {
-                // slide: the cell at ring position p leaves, the one at p + size enters (half a CTA each)
-                const int halfT = POOL_THREADS / 2;
-                if (tid < halfT)
-                    pool_apply_column(colptr, rowidx, x, lib, slot_of, ring[base + p % n], scale2, -1, W, tid, halfT);
-                else
-                    pool_apply_column(colptr, rowidx, x, lib, slot_of, ring[base + (p + size) % n], scale2, +1, W, tid - halfT, halfT);
+            if (slide) {
+#pragma unroll
+                for (int u = 0; u < POOL_PREF; ++u) {
+                    if (oq[u] != 0LL)
+                        atomicAdd(W + os[u], (unsigned long long)(-oq[u]));
+                    if (iq[u] != 0LL)
+                        atomicAdd(W + is[u], (unsigned long long)iq[u]);
+                }
+                // columns longer than the prefetch window
+                pool_apply_range(eslot, eq, ob + (int64_t)POOL_PREF * POOL_THREADS, oe, -1, W, tid);
+                pool_apply_range(eslot, eq, ib + (int64_t)POOL_PREF * POOL_THREADS, ie, +1, W, tid);
+                po = po + 1 == n ? 0 : po + 1;
+                pi = pi + 1 == n ? 0 : pi + 1;
                 __syncthreads();
             }
         }
@@ -738,7 +844,6 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
                                                   d_pslot.p, d_pave.p, d_pinv.p, d_avefull.p, d_gf.p);
         CB_LAUNCH(ctx);
     }
-    CB_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
     std::vector<int32_t> gf((size_t)C);
     CB_TRY(cb200_d2h(ctx, gf.data(), d_gf.p, (size_t)C * sizeof(int32_t), ctx->stream));
     int h_flag = 0;
@@ -749,16 +854,39 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
         CB_CHECK(ctx, gf[(size_t)c] >= 1, "cb200_pooled_size_factors: no gene of cluster %d reaches min.mean = %g", c, min_mean);
         gf_max = gf[(size_t)c] > gf_max ? gf[(size_t)c] : gf_max;
     }
-    const size_t smem = (((size_t)gf_max * 12 + 15) & ~(size_t)15) + sizeof(PoolShared);
-    CB_CHECK(ctx, smem <= 200 * 1024, "cb200_pooled_size_factors: %d genes pass min.mean in one cluster; the shared-memory "
-                                      "window holds at most %d (raise min.mean)", gf_max, (int)((200 * 1024 - sizeof(PoolShared)) / 12));
+    const size_t smem = (size_t)((gf_max + 7) & ~7) * POOL_BYTES_PER_GENE + sizeof(PoolShared);
+    CB_CHECK(ctx, smem <= 200 * 1024 && gf_max <= 65535, "cb200_pooled_size_factors: %d genes pass min.mean in one cluster; the shared-memory "
+                                      "window holds at most %d (raise min.mean)", gf_max, (int)((200 * 1024 - sizeof(PoolShared)) / POOL_BYTES_PER_GENE));
+
+    // ---- compact ring-ordered store of the kept entries
+    DevBuf<int32_t> d_kcnt;
+    DevBuf<int64_t> d_cptr;
+    DevBuf<uint16_t> d_eslot;
+    DevBuf<long long> d_eq;
+    guard.f.push_back([&]() { d_kcnt.release(); d_cptr.release(); d_eslot.release(); d_eq.release(); });
+    CB_CUDA(ctx, d_kcnt.ensure((size_t)N));
+    CB_CUDA(ctx, d_cptr.ensure((size_t)N + 1));
+    int64_t n_kept = 0;
+    {
+        const int grid = cb_grid_for(N, 8, ctx->num_sms * 8);
+        k_pool_compact<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->blk_w.p, d_ring.p, d_cl.p,
+                                                      d_pslot.p, N, G, ldexp(1.0, s2), nullptr, d_kcnt.p, nullptr, nullptr);
+        CB_LAUNCH(ctx);
+        CB_TRY(cb200_scan_i32_to_i64(ctx, d_kcnt.p, N, d_cptr.p));
+        CB_TRY(cb200_read_back(ctx, &n_kept, d_cptr.p + N, sizeof(int64_t)));
+        CB_CUDA(ctx, d_eslot.ensure((size_t)n_kept + 8));
+        CB_CUDA(ctx, d_eq.ensure((size_t)n_kept + 8));
+        k_pool_compact<<<grid, 256, 0, ctx->stream>>>(ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->blk_w.p, d_ring.p, d_cl.p,
+                                                      d_pslot.p, N, G, ldexp(1.0, s2), d_cptr.p, nullptr, d_eslot.p, d_eq.p);
+        CB_LAUNCH(ctx);
+    }
 
     // ---- step 3: work items = (cluster, size, run of ring positions)
     int64_t pairs = 0;
     for (int c = 0; c < C; ++c)
         pairs += (cl_ptr[(size_t)c + 1] - cl_ptr[(size_t)c]) * (ns_of[(size_t)c] + 1);
     int L = (int)(pairs / ((int64_t)ctx->num_sms * 24));
-    L = L < 8 ? 8 : L > 64 ? 64 : L;
+    L = L < 8 ? 8 : L > 128 ? 128 : L;
     std::vector<PoolItem> items;
     items.reserve((size_t)(pairs / L + (int64_t)C * (n_sizes + 1) + 16));
     for (int c = 0; c < C; ++c) {
@@ -774,15 +902,17 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
     CB_CUDA(ctx, d_items.ensure(items.size()));
     CB_TRY(cb200_h2d(ctx, d_items.p, items.data(), items.size() * sizeof(PoolItem), ctx->stream));
     CB_CUDA(ctx, cudaFuncSetAttribute(k_pool_medians, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(ctx, cudaEventRecord(ev[1], ctx->stream));
     {
-        int per_sm = (int)((220 * 1024) / (smem + 1024));
-        per_sm = per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm;
+        int per_sm = 1;
+        CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pool_medians, POOL_THREADS, smem));
+        per_sm = per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm;
         int64_t grid = (int64_t)ctx->num_sms * per_sm;
         if (grid > (int64_t)items.size())
             grid = (int64_t)items.size();
         k_pool_medians<<<(unsigned)grid, POOL_THREADS, smem, ctx->stream>>>(
-            d_items.p, (int)items.size(), ctx->colptr.p, ctx->rowidx.p, ctx->x.p, ctx->blk_w.p, d_ring.p, d_clptr.p, d_pslot.p,
-            d_pinv.p, d_pave.p, d_gf.p, d_meanlib.p, G, gf_max, ldexp(1.0, s2), ldexp(1.0, -s2), d_bvals.p, ctx->flag.p);
+            d_items.p, (int)items.size(), d_cptr.p, d_eslot.p, d_eq.p, d_clptr.p, d_pinv.p, d_pave.p, d_gf.p, d_meanlib.p, G,
+            gf_max, ldexp(1.0, -s2), d_bvals.p, ctx->flag.p);
         CB_LAUNCH(ctx);
     }
     CB_CUDA(ctx, cudaEventRecord(ev[2], ctx->stream));
@@ -861,7 +991,10 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
         cudaEventElapsedTime(&a, ev[0], ev[1]);
         cudaEventElapsedTime(&b, ev[1], ev[2]);
         cudaEventElapsedTime(&c2, ev[2], ev[3]);
-        stage_ms_out[0] = a;    // pseudo-cells + gene filter
+        stage_ms_out[5] = (double)gf_max;
+        stage_ms_out[6] = (double)C;
+        stage_ms_out[7] = (double)n_kept;
+        stage_ms_out[0] = a;    // pseudo-cells + gene filter + compact store
         stage_ms_out[1] = b;    // pool medians
         stage_ms_out[2] = c2;   // circulant solves
         stage_ms_out[3] = std::chrono::duration<double, std::milli>(clk::now() - t_host).count();   // host rescaling

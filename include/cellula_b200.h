@@ -263,8 +263,9 @@ int cb200_pairwise_modularity(cb200_ctx *ctx, const int32_t *from, const int32_t
  * guess (0.1 when the median library size is <= 50000, else 1); max_cluster_size <= 0 = no limit (scuttle's
  * default is 3000).  sf_out[N]: the factors, scaled to unit mean over the positive ones; the count of
  * non-positive factors (scuttle would warn and, with positive = TRUE, call cleanSizeFactors -- that repair stays
- * with the caller) goes to n_nonpositive.  stage_ms_out (nullable, 5 doubles): pseudo-cells + gene filter, pool
- * medians, least-squares solves (device ms), host rescaling, whole call (host ms). */
+ * with the caller) goes to n_nonpositive.  stage_ms_out (nullable, 8 doubles): pseudo-cells + gene filter +
+ * compact store, pool medians, least-squares solves (device ms), host rescaling, whole call (host ms), then the
+ * largest number of kept genes of a cluster, the number of clusters after the size limit, the kept entries. */
 int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters /* nullable */, const int32_t *sizes /* nullable */,
                               int n_sizes, double min_mean, int64_t max_cluster_size, double *sf_out,
                               int64_t *n_nonpositive /* nullable */, double *stage_ms_out /* nullable */);

@@ -322,7 +322,7 @@ SEXP cb200r_pooled_size_factors(SEXP sctx, SEXP codes, SEXP sizes, SEXP min_mean
     if (h->one == NULL)
         Rf_error("cellulaB200: pooled size factors need the single-GPU form (options(cellula.b200.gpus = 1L))");
     SEXP sf = PROTECT(Rf_allocVector(REALSXP, Rf_asInteger(n_cells)));
-    SEXP ms = PROTECT(Rf_allocVector(REALSXP, 5));
+    SEXP ms = PROTECT(Rf_allocVector(REALSXP, 8));
     SEXP nn = PROTECT(Rf_allocVector(REALSXP, 1));
     int64_t nonpos = 0;
     double mm = Rf_asReal(min_mean);

@@ -105,3 +105,22 @@ def test_deconvolution_factors_feed_logcounts(gpu_ctx):
         d["n_genes"], d["colptr"], d["rowidx"], d["x"]))
     assert np.allclose(sf, o_sf, rtol=RTOL)
     assert np.allclose(logx, O.log_norm_counts(d["colptr"], d["x"], o_sf), rtol=1e-6, atol=1e-9)
+
+
+def test_mirror_default_order_with_deconvolution_option(gpu_ctx):
+    """cellula_b200.doNormAndReduce(options size_factors = 'deconvolution'): pooled factors -> centred -> logcounts."""
+    import cellula_b200 as cb
+    from cellula_b200.sce import SingleCellExperiment
+    d, _, grp = planted(700, 400, seed=8, groups=2)
+    old = dict(cb.options)
+    try:
+        cb.options.update(skip_umap=True, size_factors="deconvolution")
+        sce = SingleCellExperiment.from_counts(d["colptr"], d["rowidx"], d["x"], 700)
+        sce.colData["quickCluster"] = np.array(["b", "a"])[grp]
+        sce = cb.doNormAndReduce(sce, ndims=5, hvg_ntop=200, verbose=False)
+    finally:
+        cb.options.update(old)
+    codes = np.unique(np.array(["b", "a"])[grp], return_inverse=True)[1]
+    want = O.pooled_size_factors(700, d["colptr"], d["rowidx"], d["x"], codes)
+    want = want / want.mean()
+    assert np.allclose(sce.colData["sizeFactor"], want, rtol=RTOL)
