@@ -169,6 +169,9 @@ class Context:
         if rc != 0:
             raise Cb200Error(L.cb200_last_error(None).decode())
         self.device = device
+        # the cudaStream_t the context runs on when the caller supplied one (None: a private non-blocking stream made by
+        # the library -- note that handle 0, the legacy default stream, cannot be requested through this ABI)
+        self.stream_handle = int(stream) if stream else None
         self.n_genes = self.n_cells = self.nnz = 0
         self.cell_offset = 0
         self.n_cells_total = 0

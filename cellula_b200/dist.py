@@ -75,6 +75,24 @@ class CudaShard:
     def __init__(self, ctx, device):
         self.ctx = ctx
         self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        self.check_stream()
+
+    def check_stream(self):
+        """STREAM CONTRACT.  torch.distributed orders its collectives against torch's *current* stream only, while the
+        library launches its kernels on the context's stream.  The collectives of ShardedPipeline run directly on the
+        library's buffers, so the two must be the same stream: build the context with
+        ``Context(device, stream=torch.cuda.current_stream(device).cuda_stream)`` on a ``torch.cuda.Stream`` that is
+        current (``torch.cuda.set_stream``) whenever the pipeline is driven, as bench.py and tests/dist_worker.py do.
+        Anything else (a context with its own private stream, or torch's legacy default stream, handle 0, which the C
+        ABI cannot be asked to use) would let a collective read a buffer before the kernel that fills it has finished:
+        refused here instead of producing silently wrong output."""
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        mine = getattr(self.ctx, "stream_handle", None)
+        if mine is None or int(mine) != int(cur):
+            raise RuntimeError(
+                "CudaShard: the cb200 context does not run on torch's current CUDA stream (context stream "
+                f"{mine}, torch current stream {cur}); create it as Context(device, stream=s.cuda_stream) for a "
+                "torch.cuda.Stream s and make s current (torch.cuda.set_stream(s)) while the pipeline runs")
 
     def _view(self, which, shape, dtype):
         ptr, _ = self.ctx.device_ptr(which)
@@ -157,6 +175,8 @@ class ShardedPipeline:
     # -- collectives ---------------------------------------------------------------
     def _allreduce(self, t):
         if self.world > 1:
+            if hasattr(self.shard, "check_stream"):
+                self.shard.check_stream()
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
@@ -164,6 +184,8 @@ class ShardedPipeline:
         """Concatenate row blocks of unequal height in rank order."""
         if self.world == 1:
             return local
+        if hasattr(self.shard, "check_stream"):
+            self.shard.check_stream()
         sizes = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
         mx = max(sizes)
         pad = local

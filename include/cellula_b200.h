@@ -86,6 +86,12 @@ typedef struct cb200_timing {
 /* Create a context on CUDA device `device`.  `stream` is a cudaStream_t to run on (e.g.
  * the caller's current stream so that its own events bracket the work) or NULL to let the
  * library create one. */
+/* STREAM CONTRACT for callers that run their own collectives on the library's buffers (cb200_device_ptr) between the
+ * *_local and *_finish halves: the library's kernels are asynchronous on the context's stream, so such a caller must
+ * issue its collectives on THAT stream (pass it here), or bracket them with cb200_synchronize().  A NULL `stream`
+ * gives a private cudaStreamNonBlocking stream that nothing else is ordered against; handle 0 (the legacy default
+ * stream) cannot be requested.  cellula_b200/dist.py:CudaShard refuses a context that is not on torch's current
+ * stream; cb200_multi_* runs NCCL on each context's own stream and needs nothing from the caller. */
 int cb200_init(int device, void *stream, cb200_ctx **out);
 int cb200_free(cb200_ctx *ctx);
 /* Message of the last failure on this context ("" if none); ctx == NULL returns the

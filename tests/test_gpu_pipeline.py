@@ -128,3 +128,22 @@ def test_cfg2_sized_properties(gpu_ctx):
         for h in knn[j]:
             a, b = int(max(j + 1, h)), int(min(j + 1, h))
             assert a * (n + 1) + b in have
+
+
+def test_cuda_shard_refuses_a_context_on_another_stream(gpu_ctx):
+    """NCCL collectives are ordered against torch's current stream only, so CudaShard accepts nothing but a
+    context that runs on it (a private library stream would let an all-reduce read a buffer that is still being written)."""
+    import torch
+    import cellula_b200
+    from cellula_b200.dist import CudaShard
+    with pytest.raises(RuntimeError, match="torch's current CUDA stream"):
+        CudaShard(gpu_ctx, 0)                       # session context: private stream made by the library
+    s = torch.cuda.Stream(device=0)
+    ctx = cellula_b200.Context(0, stream=s.cuda_stream)
+    try:
+        with pytest.raises(RuntimeError, match="torch's current CUDA stream"):
+            CudaShard(ctx, 0)                       # right stream, but not current
+        with torch.cuda.stream(s):
+            CudaShard(ctx, 0)                       # accepted
+    finally:
+        ctx.close()
