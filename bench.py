@@ -308,13 +308,17 @@ def main():
             emb_h = res["emb"].cpu().numpy()
             knn_h = res["knn_full"].cpu().numpy()
             sb = snn_bounds(n_total, world)
-            verified.update(verify_results(ctx, emb_h, knn_h, w["k"], w["scheme"], sb[0], sb[1]))
+            try:
+                verified.update(verify_results(ctx, emb_h, knn_h, w["k"], w["scheme"], sb[0], sb[1]))
+            except cellula_b200.Cb200Error as e:   # e.g. cfg5 on ONE GPU: no HBM left for the checker's own upload
+                verified.update(knn_rows_wrong=None, snn_edges_identical=None, check_error=str(e)[:200])
             gold = golden_digest(args.workload, w["k"], w["scheme"])
             verified["single_gpu_digest"] = gold["edge_digest"] if gold else None
             verified["matches_single_gpu"] = (gold["edge_digest"] == verified["edge_digest"] and
                                               gold["n_edges"] == verified["n_edges"]) if gold else None
-            verified["ok"] = bool(verified["knn_rows_wrong"] == 0 and verified["snn_edges_identical"] and
-                                  verified["matches_single_gpu"] is not False)
+            verified["ok"] = None if "check_error" in verified else bool(
+                verified["knn_rows_wrong"] == 0 and verified["snn_edges_identical"] and
+                verified["matches_single_gpu"] is not False)
             if args.write_golden and world == 1:
                 allg = json.load(open(GOLDEN_DIGESTS)) if os.path.exists(GOLDEN_DIGESTS) else {}
                 allg[f"{args.workload}:k{w['k']}:{w['scheme']}"] = dict(n_edges=verified["n_edges"],

@@ -1112,7 +1112,12 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
     const int max_outer = 300;
     const double tol = 2e-9;
     const bool trace_sweeps = getenv("CB200_TRACE") != nullptr;
-    int degree = 3;  // Chebyshev filter degree between Rayleigh-Ritz steps
+    int degree_hi = 6;  // Chebyshev filter degree between Rayleigh-Ritz steps once the block has settled (CB200_EIG_DEGREE)
+    if (const char *ed = getenv("CB200_EIG_DEGREE")) {
+        const int v = atoi(ed);
+        if (v >= 2 && v <= 16)
+            degree_hi = v;
+    }
     std::vector<double> th((size_t)b), res((size_t)b);
     int it = 0;
     bool converged = false;
@@ -1145,33 +1150,38 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
             converged = true;
             break;
         }
-        // Chebyshev filter (degree 3, or 2) damping [0, cut]; cut = smallest Ritz value of the block
+        // Chebyshev filter damping [0, cut]; cut = smallest Ritz value of the block.  Degree schedule: 3 while the
+        // Ritz vectors are still rough, then `degree_hi` (default 6): the products are cheap next to the
+        // Rayleigh-Ritz / QR work of an outer iteration, and once the columns are close to eigenvectors every column is
+        // amplified by its own factor, so the column-normalised block stays well conditioned for Cholesky-QR.
         double cut = th[b - 1];
         if (!(cut > 1e-12 * th[0]))
             cut = 1e-12 * th[0];
         const double cc = 0.5 * cut, ee = 0.5 * cut;
-        // X1 = (C Q - c Q)/e  (Q, C Q are the Ritz blocks Y1, Y2) -> W
+        const int degree = it < 2 ? (degree_hi < 3 ? degree_hi : 3) : degree_hi;
+        // X_k lives in bufs[k mod 4]: X0 = Ritz vectors (Y1), X1 -> W, X2 -> Q, X3 -> Y2, X4 -> Y1, ...
+        double *bufs[4] = {Y1, W, Q, Y2};
+        // X1 = (C X0 - c X0) / e  (C X0 is the Ritz block Y2)
         k_axpby<<<ew_grid, 256, 0, ctx->stream>>>(Y2, 1.0 / ee, Y1, -cc / ee, hb, W);
         CB_LAUNCH(ctx);
-        // X2 = 2 (C X1 - c X1)/e - Q -> Q buffer
-        CB_TRY(launch_cq(ctx, H, b, C, W, 2.0 / ee, W, -2.0 * cc / ee, Y1, -1.0, Q));
-        double *filtered = Q;
-        if (degree >= 3) {
-            // X3 = 2 (C X2 - c X2)/e - X1 -> Y2 buffer (C Q is no longer needed)
-            CB_TRY(launch_cq(ctx, H, b, C, Q, 2.0 / ee, Q, -2.0 * cc / ee, W, -1.0, Y2));
-            filtered = Y2;
+        for (int m = 2; m <= degree; ++m) {
+            // X_m = 2 (C X_{m-1} - c X_{m-1}) / e - X_{m-2}
+            double *xm1 = bufs[(m - 1) & 3], *xm2 = bufs[(m - 2) & 3], *xm = bufs[m & 3];
+            CB_TRY(launch_cq(ctx, H, b, C, xm1, 2.0 / ee, xm1, -2.0 * cc / ee, xm2, -1.0, xm));
         }
+        double *filtered = bufs[degree & 3];
         k_colnorm_scale<<<b, 256, 0, ctx->stream>>>(filtered, H, b);
         CB_LAUNCH(ctx);
-        CB_TRY(chol_qr(ctx, filtered, H, b, W));
-        CB_TRY(chol_qr(ctx, W, H, b, Q));
+        double *tmp = filtered == W ? Y1 : W;
+        CB_TRY(chol_qr(ctx, filtered, H, b, tmp));
+        CB_TRY(chol_qr(ctx, tmp, H, b, Q));
         if (degree >= 3) {
-            // a floored Cholesky pivot means the degree-3 block was too ill-conditioned for
-            // Cholesky-QR: continue with the gentler degree-2 filter
+            // a floored Cholesky pivot means the filtered block was too ill-conditioned for Cholesky-QR:
+            // continue with a gentler filter (6 -> 3 -> 2)
             int h_piv = 0;
             CB_TRY(cb200_read_back(ctx, &h_piv, ctx->flag.p + 1, sizeof(int)));
             if (h_piv != 0) {
-                degree = 2;
+                degree_hi = degree_hi > 3 ? 3 : 2;
                 CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 1, 0, sizeof(int), ctx->stream));
             }
         }
@@ -1219,7 +1229,7 @@ extern "C" int cb200_pca_finish(cb200_ctx *ctx, int d, double *scores, double *r
     }
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_PROJECT);
-    ctx->have_scores = true;
+    ctx->have_scores = converged;   // scores of an unconverged solve are never handed to cb200_knn(NULL)
 
     if (scores != nullptr || rotation != nullptr)
         cb_stage_begin(ctx, ST_D2H);

@@ -39,7 +39,25 @@ __global__ void k_index_to_rowmajor0(const int32_t *__restrict__ in, int64_t n, 
     }
 }
 
-__global__ void k_rev_count(const int32_t *__restrict__ nn, int64_t n, int k, int32_t *__restrict__ rcnt)
+// A neighbour index handed in by a caller (device pointer or host matrix) is not trusted: an entry outside [0, n) or
+// equal to its own row would index out of bounds / break the one-entry-per-list invariant of the hash kernel.  Such
+// entries are skipped by both passes (so everything stays in bounds) and reported through `flag` (1: range, 2: self).
+__device__ __forceinline__ bool snn_entry_ok(int s, int64_t j, int i, int64_t n, int *__restrict__ flag)
+{
+    if (i == 0)
+        return true;
+    if (s < 0 || s >= n) {
+        atomicOr(flag, 1);
+        return false;
+    }
+    if (s == j) {
+        atomicOr(flag, 2);
+        return false;
+    }
+    return true;
+}
+
+__global__ void k_rev_count(const int32_t *__restrict__ nn, int64_t n, int k, int32_t *__restrict__ rcnt, int *__restrict__ flag)
 {
     int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int L = k + 1;
@@ -47,12 +65,31 @@ __global__ void k_rev_count(const int32_t *__restrict__ nn, int64_t n, int k, in
         int64_t j = idx / L;
         int i = (int)(idx % L);
         int s = i == 0 ? (int)j : nn[j * k + (i - 1)];
-        atomicAdd(rcnt + s, 1);
+        if (snn_entry_ok(s, j, i, n, flag))
+            atomicAdd(rcnt + s, 1);
+    }
+}
+
+// duplicates inside a row of a caller-supplied index (thread per entry, compared with the entries before it)
+__global__ void k_snn_check_dups(const int32_t *__restrict__ nn, int64_t n, int k, int *__restrict__ flag)
+{
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx < n * k) {
+        const int64_t j = idx / k;
+        const int i = (int)(idx % k);
+        const int v = nn[idx];
+        if (v == (int)j)
+            atomicOr(flag, 2);
+        for (int t = 0; t < i; ++t)
+            if (nn[j * k + t] == v) {
+                atomicOr(flag, 4);
+                break;
+            }
     }
 }
 
 __global__ void k_rev_fill(const int32_t *__restrict__ nn, int64_t n, int k, const int64_t *__restrict__ rptr,
-                           int32_t *__restrict__ rcur, uint32_t *__restrict__ hosts_u)
+                           int32_t *__restrict__ rcur, uint32_t *__restrict__ hosts_u, int *__restrict__ flag)
 {
     int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int L = k + 1;
@@ -60,6 +97,8 @@ __global__ void k_rev_fill(const int32_t *__restrict__ nn, int64_t n, int k, con
         int64_t j = idx / L;
         int i = (int)(idx % L);
         int s = i == 0 ? (int)j : nn[j * k + (i - 1)];
+        if (!snn_entry_ok(s, j, i, n, flag))
+            return;
         int pos = atomicAdd(rcur + s, 1);
         hosts_u[rptr[s] + pos] = ((uint32_t)j << 8) | (uint32_t)i;
     }
@@ -596,15 +635,22 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
     CB_CUDA(ctx, cudaMemsetAsync(ctx->rcnt.p, 0, (size_t)n * sizeof(int32_t), ctx->stream));
     CB_CUDA(ctx, cudaMemsetAsync(ctx->rcur.p, 0, (size_t)n * sizeof(int32_t), ctx->stream));
     const unsigned g1 = (unsigned)((n * L + 255) / 256);
-    k_rev_count<<<g1, 256, 0, ctx->stream>>>(d_nn, n, k, ctx->rcnt.p);
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flag.p + 3, 0, sizeof(int), ctx->stream));
+    k_rev_count<<<g1, 256, 0, ctx->stream>>>(d_nn, n, k, ctx->rcnt.p, ctx->flag.p + 3);
     CB_LAUNCH(ctx);
     CB_TRY(cb200_scan_i32_to_i64(ctx, ctx->rcnt.p, n, ctx->rptr.p));
-    k_rev_fill<<<g1, 256, 0, ctx->stream>>>(d_nn, n, k, ctx->rptr.p, ctx->rcur.p, ctx->hosts_u.p);
+    k_rev_fill<<<g1, 256, 0, ctx->stream>>>(d_nn, n, k, ctx->rptr.p, ctx->rcur.p, ctx->hosts_u.p, ctx->flag.p + 3);
     CB_LAUNCH(ctx);
     const int g2 = cb_grid_for(n, 8, ctx->num_sms * 16);
     k_rev_sort<<<g2, 256, 0, ctx->stream>>>(ctx->rptr.p, n, ctx->hosts_u.p, ctx->hosts.p, L, ctx->snn_cut.p);
     CB_LAUNCH(ctx);
     cb_stage_end(ctx, ST_SNN_REVLIST);
+    {   // the edge kernels index the reverse lists with the entries of d_nn: stop here if any is unusable
+        int h_bad = 0;
+        CB_TRY(cb200_read_back(ctx, &h_bad, ctx->flag.p + 3, sizeof(int)));
+        CB_CHECK(ctx, (h_bad & 1) == 0, "cb200_snn: neighbour index out of range [0, n)");
+        CB_CHECK(ctx, (h_bad & 2) == 0, "cb200_snn: a row of the neighbour index names its own cell");
+    }
 
     cb_stage_begin(ctx, ST_SNN_EDGES);
     // hash kernel for (nearly) every cell, merge kernel for the flagged ones (too many partners for the
@@ -875,11 +921,14 @@ extern "C" int cb200_snn(cb200_ctx *ctx, const int32_t *index, int64_t n_total, 
         k_index_to_rowmajor0<<<(unsigned)((n_total * k + 255) / 256), 256, 0, ctx->stream>>>(
             ctx->stage_i.p, n_total, k, ctx->index0.p, ctx->flag.p);
         CB_LAUNCH(ctx);
+        k_snn_check_dups<<<(unsigned)((n_total * k + 255) / 256), 256, 0, ctx->stream>>>(ctx->index0.p, n_total, k, ctx->flag.p);
+        CB_LAUNCH(ctx);
         cb_stage_end(ctx, ST_H2D);
         int h_flag = 0;
         CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        CB_CHECK(ctx, h_flag == 0, "cb200_snn: neighbour index out of range [1, n]");
+        CB_CHECK(ctx, (h_flag & 1) == 0, "cb200_snn: neighbour index out of range [1, n]");
+        CB_CHECK(ctx, (h_flag & 6) == 0, "cb200_snn: a row of the neighbour index names its own cell or the same cell twice");
         d_nn = ctx->index0.p;
     }
     CB_TRY(snn_core(ctx, d_nn, n_total, k, type, j_begin, j_end, n_edges));

@@ -127,3 +127,26 @@ def test_snn_large_k_as_rebuild_modularity_uses(gpu_ctx, n, k):
         got = gpu_ctx.snn(knn, scheme, j_begin=n - 300, j_end=n)
         want = O.snn_edges(knn, scheme, j_begin=n - 300, j_end=n)
         assert all(np.array_equal(a, b) for a, b in zip(got, want)), (k, scheme)
+
+
+def test_untrusted_index_is_validated(gpu_ctx):
+    """a malformed neighbour index (out of range, own cell, repeated cell) is refused, never indexed with."""
+    import cellula_b200
+    emb = synth.make_embedding(600, 5, seed=3)
+    good = O.find_knn(emb, 8)
+    for bad_value, pattern in ((601, "out of range"), (0, "out of range")):
+        bad = good.copy()
+        bad[17, 3] = bad_value
+        with pytest.raises(cellula_b200.Cb200Error, match=pattern):
+            gpu_ctx.snn(bad, "rank")
+    bad = good.copy()
+    bad[40, 2] = 41                      # 1-based: row 40 is cell 41
+    with pytest.raises(cellula_b200.Cb200Error, match="own cell"):
+        gpu_ctx.snn(bad, "rank")
+    bad = good.copy()
+    bad[5, 7] = bad[5, 0]
+    with pytest.raises(cellula_b200.Cb200Error, match="twice"):
+        gpu_ctx.snn(bad, "number")
+    got = O.canonical_edges(*gpu_ctx.snn(good, "rank"))          # the context is still usable afterwards
+    want = O.canonical_edges(*O.snn_edges(good, "rank"))
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
