@@ -19,5 +19,7 @@ rm -f gpurun_out/${TAG}_stages_full.ncu-rep
 ncu --set full --clock-control none --import-source on -k regex:k_knn_tiles_tc -c 1 -o gpurun_out/${TAG}_knn_tiles_full -f \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-verify > gpurun_out/${TAG}_ncu_knn.log 2>&1
 echo "knn capture exit $?"; ls -la gpurun_out/*.ncu-rep
+python scripts/summarize_ncu.py gpurun_out/${TAG}_knn_tiles_full.ncu-rep gpurun_out/${TAG}_knn_tiles_tc_ncu.txt \
+  "ncu --set full --clock-control none --import-source on -k regex:k_knn_tiles_tc -c 1 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-verify (cfg3, 1 B200)" > /dev/null
 CB200_KNN_TIMELINE=gpurun_out/${TAG}_timeline.bin python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-verify > gpurun_out/${TAG}_tl.log 2>&1
 python scripts/timeline_summary.py gpurun_out/${TAG}_timeline.bin
