@@ -472,6 +472,199 @@ k_snn_flat(const int32_t *__restrict__ nn, int k, int type, int lpad, int64_t j_
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// K7b for the two largest table tiers: ONE table per CTA, all warps of the CTA work on the same cell.
+// The warp-per-cell kernel above needs a private table per warp; at 8 Ki / 16 Ki slots that leaves 3 / 1 warps per
+// SM (k = 100: every cell).  Here the 32 warps of a CTA take the 32-entry steps of the cell's flat sequence in
+// turn.  Pass 1 inserts with atomicCAS on the key and records per partner the SMALLEST flat index it occurs at
+// (atomicMin) and its value (atomicMin of the rank sum / atomicAdd of the count).  Pass 2 walks the flat sequence
+// again: an entry is a partner's first occurrence iff its flat index equals that minimum; the first occurrences are
+// compacted in flat order (per-step ballots + a prefix over the steps), which is libscran's emission order -- the
+// same output, bit for bit, as the warp kernel's running counter.
+// ---------------------------------------------------------------------------------------
+#define SNN_CTA_THREADS 1024
+template <int LOG_SLOTS>
+struct SnnCtaTier {
+    static constexpr int slots = 1 << LOG_SLOTS;
+    static constexpr int cap = slots / 16 * 11;
+    static constexpr int nsteps_max = (cap + 31) / 32;
+    static constexpr int steps_per_warp = (nsteps_max + SNN_CTA_THREADS / 32 - 1) / (SNN_CTA_THREADS / 32);
+    __host__ __device__ static int bytes(int lpad) { return slots * 12 + lpad * 8 + (nsteps_max + 8) * 4; }
+};
+
+template <int LOG_SLOTS>
+__global__ void __launch_bounds__(SNN_CTA_THREADS)
+k_snn_flat_cta(const int32_t *__restrict__ nn, int k, int type, int lpad, int64_t j_begin, const int64_t *__restrict__ rptr,
+               const uint32_t *__restrict__ hosts, const int32_t *__restrict__ cut, const int32_t *__restrict__ jlist,
+               const int *__restrict__ nlist, int32_t *__restrict__ ecnt, const int64_t *__restrict__ toff,
+               uint32_t *__restrict__ tmp_h, uint16_t *__restrict__ tmp_v)
+{
+    using T = SnnCtaTier<LOG_SLOTS>;
+    extern __shared__ __align__(16) unsigned char snn_smem[];
+    uint32_t *key = reinterpret_cast<uint32_t *>(snn_smem);      // [slots]
+    uint32_t *first = key + T::slots;                             // [slots] smallest flat index of the partner
+    uint32_t *val = first + T::slots;                             // [slots] smallest rank sum / number of shared neighbours
+    uint32_t *lstart = val + T::slots;                            // [lpad]
+    uint32_t *lpre = lstart + lpad;                               // [lpad]
+    int *cnt = reinterpret_cast<int *>(lpre + lpad);              // [nsteps_max + 1] first occurrences per step, then offsets
+    int *misc = cnt + T::nsteps_max + 1;                          // [0] total
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NW = SNN_CTA_THREADS / 32;
+    const int L = k + 1;
+    const bool want_min = type == CB200_SNN_RANK;
+    const int n_items = *nlist;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int64_t jl = jlist[it];
+        const int64_t j = j_begin + jl;
+        __syncthreads();   // the previous cell is completely written out
+        if (w == 0) {
+            int total = 0;
+            for (int i0 = 0; i0 < L; i0 += 32) {
+                const int i = i0 + lane;
+                int len = 0;
+                uint32_t lb = 0;
+                if (i < L) {
+                    const int sidx = i == 0 ? (int)j : nn[j * k + (i - 1)];
+                    lb = (uint32_t)rptr[sidx];
+                    len = cut[j * L + i];
+                }
+                int inc = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t2 = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o)
+                        inc += t2;
+                }
+                if (i < L) {
+                    lstart[i] = lb;
+                    lpre[i] = (uint32_t)(total + inc - len);
+                }
+                total += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0)
+                misc[0] = total;
+        }
+        {
+            const uint32_t vinit = want_min ? 0xffffffffu : 0u;
+            uint4 *k4 = reinterpret_cast<uint4 *>(key), *f4 = reinterpret_cast<uint4 *>(first), *v4 = reinterpret_cast<uint4 *>(val);
+            for (int e = tid; e < T::slots / 4; e += SNN_CTA_THREADS) {
+                k4[e] = make_uint4(SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY);
+                f4[e] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                v4[e] = make_uint4(vinit, vinit, vinit, vinit);
+            }
+        }
+        __syncthreads();
+        const int total = misc[0];
+        const int nsteps = (total + 31) >> 5;
+        // pass 1a: every thread requests all its entries of the flat sequence first (independent loads in flight) ...
+        uint32_t hreg[T::steps_per_warp];
+        int sreg[T::steps_per_warp];
+#pragma unroll
+        for (int t = 0; t < T::steps_per_warp; ++t) {
+            const int st = w + t * NW;
+            const int f = st * 32 + lane;
+            hreg[t] = 0u;
+            sreg[t] = -1;
+            if (st < nsteps && f < total) {
+                int lo = 0, hi = L - 1;   // largest i with lpre[i] <= f (lists may be empty: equal prefixes)
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (lpre[mid] <= (uint32_t)f)
+                        lo = mid;
+                    else
+                        hi = mid - 1;
+                }
+                hreg[t] = __ldg(hosts + lstart[lo] + ((uint32_t)f - lpre[lo]));   // raw entry: cell << 8 | rank
+                sreg[t] = lo;                                                      // its list
+            }
+        }
+        // ... pass 1b: then inserts them
+#pragma unroll
+        for (int t = 0; t < T::steps_per_warp; ++t) {
+            if (sreg[t] >= 0) {
+                const int f = (w + t * NW) * 32 + lane;
+                const uint32_t h = hreg[t] >> 8;
+                const int rs = sreg[t] + (int)(hreg[t] & 0xffu);
+                int slot = (int)((h * 2654435761u) >> (32 - LOG_SLOTS));
+                while (true) {
+                    const uint32_t old = atomicCAS(key + slot, SNN_HASH_EMPTY, h);
+                    if (old == SNN_HASH_EMPTY || old == h)
+                        break;
+                    slot = (slot + 1) & (T::slots - 1);
+                }
+                atomicMin(first + slot, (uint32_t)f);
+                if (want_min)
+                    atomicMin(val + slot, (uint32_t)rs);
+                else
+                    atomicAdd(val + slot, 1u);
+                hreg[t] = h;
+                sreg[t] = slot;
+            }
+        }
+        __syncthreads();
+        // pass 2a: first occurrences per step
+        unsigned firstbits = 0u;
+#pragma unroll
+        for (int t = 0; t < T::steps_per_warp; ++t) {
+            const int st = w + t * NW;
+            const int f = st * 32 + lane;
+            const bool isf = sreg[t] >= 0 && first[sreg[t]] == (uint32_t)f;
+            const unsigned m = __ballot_sync(0xffffffffu, isf);
+            if (isf)
+                firstbits |= 1u << t;
+            if (lane == 0 && st < nsteps)
+                cnt[st] = __popc(m);
+        }
+        __syncthreads();
+        // exclusive prefix over the steps (warp 0)
+        if (w == 0) {
+            constexpr int PER = (T::nsteps_max + 31) / 32;
+            int loc[PER];
+            int sum = 0;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int st = lane * PER + q;
+                loc[q] = st < nsteps ? cnt[st] : 0;
+                sum += loc[q];
+            }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += t2;
+            }
+            int run = inc - sum;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int st = lane * PER + q;
+                if (st < nsteps)
+                    cnt[st] = run;
+                run += loc[q];
+            }
+            if (lane == 31)
+                misc[1] = inc;   // distinct partners
+        }
+        __syncthreads();
+        // pass 2b: write the partners at their emission positions
+        const int64_t tb = toff[jl];
+#pragma unroll
+        for (int t = 0; t < T::steps_per_warp; ++t) {
+            const int st = w + t * NW;
+            const bool isf = (firstbits >> t) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, isf);
+            if (isf) {
+                const int pos = cnt[st] + __popc(m & lt_mask);
+                tmp_h[tb + pos] = hreg[t];
+                tmp_v[tb + pos] = (uint16_t)val[sreg[t]];
+            }
+        }
+        if (tid == 0)
+            ecnt[jl] = misc[1];
+    }
+}
+
 // tier of every cell from the length of its flat sequence; tier SNN_TIERS = left to the merge kernel
 __global__ void k_snn_tiers(const int32_t *__restrict__ tcnt, const int64_t *__restrict__ rptr, const int32_t *__restrict__ nn,
                             int64_t j_begin, int64_t nj, int k, int32_t *__restrict__ lists, int *__restrict__ nlists,
@@ -550,6 +743,24 @@ static int launch_snn_flat(cb200_ctx *ctx, const int32_t *d_nn, int k, int type,
     CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_flat<LOG_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = ctx->num_sms * ctas_per_sm;
     k_snn_flat<LOG_SLOTS><<<grid, 32 * warps, smem, ctx->stream>>>(
+        d_nn, k, type, lpad, j_begin, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->snn_jlist.p + (int64_t)tier * nj,
+        ctx->snn_nlists.p + tier, ctx->ecnt.p, ctx->snn_toff.p, ctx->snn_tmp_h.p,
+        reinterpret_cast<uint16_t *>(ctx->snn_tmp_rc.p));
+    CB_LAUNCH(ctx);
+    return 0;
+}
+
+template <int LOG_SLOTS>
+static int launch_snn_flat_cta(cb200_ctx *ctx, const int32_t *d_nn, int k, int type, int64_t j_begin, int64_t nj, int tier)
+{
+    using T = SnnCtaTier<LOG_SLOTS>;
+    const int lpad = (k + 1 + 31) & ~31;
+    const size_t smem = (size_t)T::bytes(lpad);
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_flat_cta<LOG_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_snn_flat_cta<LOG_SLOTS>, SNN_CTA_THREADS, smem));
+    const int grid = ctx->num_sms * (per_sm < 1 ? 1 : per_sm);
+    k_snn_flat_cta<LOG_SLOTS><<<grid, SNN_CTA_THREADS, smem, ctx->stream>>>(
         d_nn, k, type, lpad, j_begin, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->snn_jlist.p + (int64_t)tier * nj,
         ctx->snn_nlists.p + tier, ctx->ecnt.p, ctx->snn_toff.p, ctx->snn_tmp_h.p,
         reinterpret_cast<uint16_t *>(ctx->snn_tmp_rc.p));
@@ -684,8 +895,14 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
         if (hs.nl[0] > 0) CB_TRY((launch_snn_flat<10>(ctx, d_nn, k, type, j_begin, nj, 0)));
         if (hs.nl[1] > 0) CB_TRY((launch_snn_flat<11>(ctx, d_nn, k, type, j_begin, nj, 1)));
         if (hs.nl[2] > 0) CB_TRY((launch_snn_flat<12>(ctx, d_nn, k, type, j_begin, nj, 2)));
-        if (hs.nl[3] > 0) CB_TRY((launch_snn_flat<13>(ctx, d_nn, k, type, j_begin, nj, 3)));
-        if (hs.nl[4] > 0) CB_TRY((launch_snn_flat<14>(ctx, d_nn, k, type, j_begin, nj, 4)));
+        // the two largest tiers: one table per CTA (the warp-per-cell kernel has room for 3 / 1 tables per SM there);
+        // CB200_SNN_CTA=0 keeps the warp-per-cell kernel (cross-check)
+        const char *scta = getenv("CB200_SNN_CTA");
+        const bool use_cta = !(scta != nullptr && strcmp(scta, "0") == 0);
+        if (hs.nl[3] > 0) CB_TRY(use_cta ? (launch_snn_flat_cta<13>(ctx, d_nn, k, type, j_begin, nj, 3))
+                                         : (launch_snn_flat<13>(ctx, d_nn, k, type, j_begin, nj, 3)));
+        if (hs.nl[4] > 0) CB_TRY(use_cta ? (launch_snn_flat_cta<14>(ctx, d_nn, k, type, j_begin, nj, 4))
+                                         : (launch_snn_flat<14>(ctx, d_nn, k, type, j_begin, nj, 4)));
         ctx->snn_n_merge = hs.nl[SNN_TIERS];
         launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_jlist.p + (int64_t)SNN_TIERS * nj,
                             ctx->snn_nlists.p + SNN_TIERS);

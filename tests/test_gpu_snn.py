@@ -150,3 +150,17 @@ def test_untrusted_index_is_validated(gpu_ctx):
     got = O.canonical_edges(*gpu_ctx.snn(good, "rank"))          # the context is still usable afterwards
     want = O.canonical_edges(*O.snn_edges(good, "rank"))
     assert all(np.array_equal(a, b) for a, b in zip(got, want))
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_snn_cta_tables_equal_warp_tables(gpu_ctx, monkeypatch, scheme):
+    """Cells whose flat sequence needs the 8 Ki / 16 Ki-slot tables run on the CTA-per-cell kernel (one shared table,
+    atomic insertion, emission order rebuilt from the smallest flat index of every partner); CB200_SNN_CTA=0 keeps the
+    warp-per-cell kernel.  Same edges, weights and order, and both equal the oracle."""
+    knn = O.find_knn(synth.make_embedding(4000, 12, seed=17), 90)
+    a = gpu_ctx.snn(knn, scheme)
+    monkeypatch.setenv("CB200_SNN_CTA", "0")
+    b = gpu_ctx.snn(knn, scheme)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    want = O.snn_edges(knn, scheme)
+    assert all(np.array_equal(x, y) for x, y in zip(a, want))
