@@ -121,11 +121,33 @@ if (opt$variant %in% c("both", "A")) {
   dump_path(sce, "A")
 }
 
+# ---- SURVEY 8(f)-1 / 8(f)-4: the calls either side of the path, on the same counts ------------------------------
+# quickCluster + computeSumFactors exactly as doNormAndReduce.R:57-71 calls them (the labels are dumped too: they are
+# the INPUT of cb200_pooled_size_factors, whose output is compared with F1_pooled_sf); perCellQCMetrics as
+# doQC.R:106-108 calls it, with three deterministic gene subsets; findKNN(get.distance = TRUE) for cb200_knn_distances.
+if (opt$variant %in% c("both", "A", "F")) {
+  sce <- SingleCellExperiment(assays = list(counts = counts))
+  cl <- tick("F1_quickCluster", quickCluster(sce, min.size = floor(sqrt(ncol(sce))), BPPARAM = bp))
+  write_vec(as.integer(factor(cl)) - 1L, "F1_quickcluster_codes.i32", "integer")
+  sce <- tick("F1_computeSumFactors", computeSumFactors(sce, clusters = cl, BPPARAM = bp))
+  write_vec(sizeFactors(sce), "F1_pooled_sf.f64")
+  subsets <- list(first = seq(1, G, by = 97), second = seq(5, G, by = 1013), third = seq_len(min(G, 50)))
+  qc <- tick("F4_perCellQCMetrics", perCellQCMetrics(sce, subsets = subsets, BPPARAM = bp))
+  write_vec(qc$sum, "F4_qc_sum.f64"); write_vec(qc$detected, "F4_qc_detected.i32", "integer")
+  for (nm in names(subsets)) {
+    write_vec(subsets[[nm]] - 1L, paste0("F4_subset_", nm, "_genes.i32"), "integer")
+    write_vec(qc[[paste0("subsets_", nm, "_sum")]], paste0("F4_qc_", nm, "_sum.f64"))
+    write_vec(qc[[paste0("subsets_", nm, "_detected")]], paste0("F4_qc_", nm, "_detected.i32"), "integer")
+    write_vec(qc[[paste0("subsets_", nm, "_percent")]], paste0("F4_qc_", nm, "_percent.f64"))
+  }
+}
+
 # ---- SURVEY 8c.2 checklist: the upstream behaviours the oracle assumes ---------------------------------------------
 chk <- list()
 lat <- as.matrix(expand.grid(0:9, 0:9, 0:4)) * 1.0                # integer lattice: exact distance ties everywhere
 kl <- findKNN(lat, k = 7, BNPARAM = KmknnParam(), get.distance = TRUE)
 write_vec(as.vector(lat), "check_lattice_x.f64"); write_vec(as.vector(kl$index), "check_lattice_knn.i32", "integer")
+write_vec(as.vector(kl$distance), "check_lattice_dist.f64")       # 8(f)-4: cb200_knn_distances
 dup <- rbind(matrix(rnorm(200 * 5), 200), matrix(1.5, 30, 5))     # 30 identical rows: self-exclusion with duplicates
 kd <- findKNN(dup, k = 10, BNPARAM = KmknnParam(), get.distance = FALSE)
 write_vec(as.vector(dup), "check_dup_x.f64"); write_vec(as.vector(kd$index), "check_dup_knn.i32", "integer")

@@ -786,7 +786,11 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
     DevBuf<float> d_pinv;
     DevBuf<unsigned long long> d_acc;
     DevBuf<PoolItem> d_items;
-    struct BufGuard {
+    DevBuf<int32_t> d_kcnt;          // compact ring-ordered store of the kept entries (step 3)
+    DevBuf<int64_t> d_cptr;
+    DevBuf<uint16_t> d_eslot;
+    DevBuf<long long> d_eq;
+    struct BufGuard {   // declared after every buffer it releases
         std::vector<std::function<void()>> f;
         ~BufGuard()
         {
@@ -798,6 +802,7 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
     POOL_OWN(d_cl); POOL_OWN(d_ring); POOL_OWN(d_sizes); POOL_OWN(d_ns); POOL_OWN(d_pslot); POOL_OWN(d_gf); POOL_OWN(d_clptr);
     POOL_OWN(d_meanlib); POOL_OWN(d_pave); POOL_OWN(d_avefull); POOL_OWN(d_bvals); POOL_OWN(d_work); POOL_OWN(d_nf);
     POOL_OWN(d_pinv); POOL_OWN(d_acc); POOL_OWN(d_items);
+    POOL_OWN(d_kcnt); POOL_OWN(d_cptr); POOL_OWN(d_eslot); POOL_OWN(d_eq);
 #undef POOL_OWN
     const size_t CG = (size_t)C * (size_t)G;
     CB_CUDA(ctx, d_cl.ensure((size_t)N));
@@ -859,11 +864,6 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
                                       "window holds at most %d (raise min.mean)", gf_max, (int)((200 * 1024 - sizeof(PoolShared)) / POOL_BYTES_PER_GENE));
 
     // ---- compact ring-ordered store of the kept entries
-    DevBuf<int32_t> d_kcnt;
-    DevBuf<int64_t> d_cptr;
-    DevBuf<uint16_t> d_eslot;
-    DevBuf<long long> d_eq;
-    guard.f.push_back([&]() { d_kcnt.release(); d_cptr.release(); d_eslot.release(); d_eq.release(); });
     CB_CUDA(ctx, d_kcnt.ensure((size_t)N));
     CB_CUDA(ctx, d_cptr.ensure((size_t)N + 1));
     int64_t n_kept = 0;

@@ -103,6 +103,48 @@ def gpu_results(d, ref, ndims, k, scheme, sf_in):
                 knn_on_ref_pca=knn, edges_on_ref_knn=edges)
 
 
+def compare_side_calls(dump, d, use_gpu):
+    """SURVEY 8(f)-1 / 8(f)-4 dumps (F1_*, F4_*, check_lattice_dist): pooled size factors on the reference's own
+    quickCluster labels, per-cell QC metrics, neighbour distances.  Skipped when the dump predates them."""
+    from oracle import oracle as O
+    rows = []
+    path = lambda name: os.path.join(dump, name)  # noqa: E731
+    if not os.path.exists(path("F1_pooled_sf.f64")):
+        return rows
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))  # noqa: E731
+    codes = np.fromfile(path("F1_quickcluster_codes.i32"), dtype="<i4")
+    ref_sf = np.fromfile(path("F1_pooled_sf.f64"), dtype="<f8")
+    ref_sf = ref_sf / ref_sf[ref_sf > 0].mean()            # both sides on the unit-mean scale logNormCounts would use
+    subsets = [np.fromfile(path(f"F4_subset_{nm}_genes.i32"), dtype="<i4") for nm in ("first", "second", "third")]
+    arms = [("oracle", lambda: O.pooled_size_factors(d["n_genes"], d["colptr"], d["rowidx"], d["x"], codes),
+             lambda: O.per_cell_qc_metrics(d["n_genes"], d["colptr"], d["rowidx"], d["x"], subsets))]
+    if use_gpu:
+        import cellula_b200 as cb
+        ctx = cb.Context(0)
+        ctx.load_csc(d["n_genes"], d["colptr"], d["rowidx"], d["x"])
+        arms.append(("cellula_b200", lambda: ctx.pooled_size_factors(codes)[0], lambda: ctx.qc_metrics(subsets)))
+    for name, pooled, qc in arms:
+        sf = pooled()
+        v = rel(sf / sf[sf > 0].mean(), ref_sf)
+        rows.append((f"{name}: pooled size factors on the reference's quickCluster labels, max rel", v, 1e-6, v <= 1e-6))
+        q = qc()
+        ok = (np.array_equal(q["sum"], np.fromfile(path("F4_qc_sum.f64"), dtype="<f8")) and
+              np.array_equal(q["detected"], np.fromfile(path("F4_qc_detected.i32"), dtype="<i4")))
+        for s_i, nm in enumerate(("first", "second", "third")):
+            ok = ok and np.array_equal(q["subsets"][s_i]["sum"], np.fromfile(path(f"F4_qc_{nm}_sum.f64"), dtype="<f8"))
+            ok = ok and np.array_equal(q["subsets"][s_i]["detected"], np.fromfile(path(f"F4_qc_{nm}_detected.i32"), dtype="<i4"))
+            pr = np.fromfile(path(f"F4_qc_{nm}_percent.f64"), dtype="<f8")
+            ok = ok and np.allclose(q["subsets"][s_i]["percent"], pr, rtol=1e-14, atol=0, equal_nan=True)
+        rows.append((f"{name}: perCellQCMetrics (sum, detected, 3 subsets) identical", 0 if ok else 1, 0, ok))
+    if os.path.exists(path("check_lattice_dist.f64")):
+        lat = np.fromfile(path("check_lattice_x.f64"), dtype="<f8").reshape((-1, 3), order="F")
+        idx = np.fromfile(path("check_lattice_knn.i32"), dtype="<i4").reshape((lat.shape[0], -1), order="F")
+        dist = np.fromfile(path("check_lattice_dist.f64"), dtype="<f8").reshape(idx.shape, order="F")
+        same = np.array_equal(O.knn_distances(lat, idx), dist)
+        rows.append(("oracle: findKNN(get.distance = TRUE) distances on the tie lattice identical", 0 if same else 1, 0, same))
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--data", required=True)
@@ -120,6 +162,7 @@ def main():
     if a.gpu:
         rows += compare("cellula_b200", gpu_results(d, ref, rep["ndims"], rep["k"], rep["scheme"], sf_in), ref, d,
                         a.variant == "B")
+    rows += compare_side_calls(a.dump, d, a.gpu)
     width = max(len(r[0]) for r in rows)
     for check, value, bound, ok in rows:
         print(f"{'ok  ' if ok else 'FAIL'} {check:<{width}}  {value:.3e}  (bound {bound:g})")

@@ -23,6 +23,7 @@ def _run(dump, compute):
     ref = C.load_dump(dump, "B", d["n_cells"])
     rep = ref["report"]
     rows = C.compare(compute.__name__, compute(d, ref, rep["ndims"], rep["k"], rep["scheme"], None), ref, d, True)
+    rows += C.compare_side_calls(dump, d, compute is C.gpu_results)    # SURVEY 8(f)-1 / 8(f)-4 dumps, when present
     bad = [r for r in rows if not r[3]]
     assert not bad, bad
 
