@@ -331,7 +331,8 @@ k_snn_merge(const int32_t *__restrict__ nn, int64_t n, int k, int type, int64_t 
 // launch over its own list of cells.  Cells beyond the largest tier are left to k_snn_merge.
 // ---------------------------------------------------------------------------------------
 #define SNN_HASH_EMPTY 0xffffffffu
-#define SNN_TIERS 5
+#define SNN_TIERS 6       // 0..4: tables of 1 Ki .. 16 Ki slots chosen by the flat length; 5: 16 Ki-slot CTA table for longer sequences
+#define SNN_LONG_MAXFLAT 65536
 #define SNN_MAXL 256
 template <int LOG_SLOTS>
 struct SnnTier {
@@ -668,15 +669,19 @@ k_snn_flat_cta(const int32_t *__restrict__ nn, int k, int type, int lpad, int64_
 // tier of every cell from the length of its flat sequence; tier SNN_TIERS = left to the merge kernel
 __global__ void k_snn_tiers(const int32_t *__restrict__ tcnt, const int64_t *__restrict__ rptr, const int32_t *__restrict__ nn,
                             int64_t j_begin, int64_t nj, int k, int32_t *__restrict__ lists, int *__restrict__ nlists,
-                            unsigned char *__restrict__ flagged, int32_t *__restrict__ ecnt)
+                            unsigned char *__restrict__ flagged, int32_t *__restrict__ ecnt, int long_max)
 {
     const int64_t jl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (jl >= nj)
         return;
     const int t = tcnt[jl];
     int tier = 0;
-    while (tier < SNN_TIERS && t > ((1 << (10 + tier)) / 16) * 11)
+    while (tier < 5 && t > ((1 << (10 + tier)) / 16) * 11)
         ++tier;
+    // beyond the 16 Ki-slot capacity: the long CTA tier when the sequence is short enough for it (its DISTINCT partners
+    // almost always fit the table; the kernel hands the cell to the merge kernel if they do not), else the merge kernel
+    if (tier == 5 && t > long_max)
+        tier = SNN_TIERS;
     flagged[jl] = tier == SNN_TIERS ? (unsigned char)2 : (unsigned char)0;
     if (tier == SNN_TIERS)
         ecnt[jl] = 0;
@@ -746,6 +751,228 @@ static int launch_snn_flat(cb200_ctx *ctx, const int32_t *d_nn, int k, int type,
         d_nn, k, type, lpad, j_begin, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->snn_jlist.p + (int64_t)tier * nj,
         ctx->snn_nlists.p + tier, ctx->ecnt.p, ctx->snn_toff.p, ctx->snn_tmp_h.p,
         reinterpret_cast<uint16_t *>(ctx->snn_tmp_rc.p));
+    CB_LAUNCH(ctx);
+    return 0;
+}
+
+// The same CTA-per-cell scheme for sequences LONGER than the largest table's capacity (k = 100: 28 % of the cells,
+// half of the edges; the k-way merge kernel spends one warp-iteration per edge on them).  The capacity bounds the
+// DISTINCT partners, which are a fraction of the flat length (duplicates: a partner sits in several lists), so the
+// 16 Ki-slot table nearly always suffices; the kernel counts the distinct keys while inserting and hands the cell to
+// the merge kernel's list if they exceed the capacity.  Nothing is cached in registers (up to 2 048 steps per cell):
+// pass 2 re-reads the entries (L1/L2 hits) and re-probes; the first-occurrence masks of the steps are kept in shared
+// memory so that only first occurrences are visited by the write-out pass.
+__global__ void __launch_bounds__(SNN_CTA_THREADS)
+k_snn_flat_cta_long(const int32_t *__restrict__ nn, int k, int type, int lpad, int64_t j_begin, const int64_t *__restrict__ rptr,
+                    const uint32_t *__restrict__ hosts, const int32_t *__restrict__ cut, const int32_t *__restrict__ jlist,
+                    const int *__restrict__ nlist, int32_t *__restrict__ ecnt, const int64_t *__restrict__ toff,
+                    uint32_t *__restrict__ tmp_h, uint16_t *__restrict__ tmp_v, int32_t *__restrict__ merge_list,
+                    int *__restrict__ merge_count, unsigned char *__restrict__ flagged, int cap)
+{
+    constexpr int LOG_SLOTS = 14, SLOTS = 1 << LOG_SLOTS;   // cap <= SLOTS / 16 * 11 distinct partners
+    constexpr int MAXSTEPS = SNN_LONG_MAXFLAT / 32;
+    extern __shared__ __align__(16) unsigned char snn_smem[];
+    uint32_t *key = reinterpret_cast<uint32_t *>(snn_smem);
+    uint32_t *first = key + SLOTS;
+    uint32_t *val = first + SLOTS;
+    uint32_t *lstart = val + SLOTS;
+    uint32_t *lpre = lstart + lpad;
+    int *cnt = reinterpret_cast<int *>(lpre + lpad);              // [MAXSTEPS + 1]
+    uint32_t *fmask = reinterpret_cast<uint32_t *>(cnt + MAXSTEPS + 1);   // [MAXSTEPS] first-occurrence lanes of every step
+    int *misc = reinterpret_cast<int *>(fmask + MAXSTEPS);        // [0] total, [1] distinct (final), [2] overflow, [3] distinct (running)
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NW = SNN_CTA_THREADS / 32;
+    const int L = k + 1;
+    const bool want_min = type == CB200_SNN_RANK;
+    const int n_items = *nlist;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int64_t jl = jlist[it];
+        const int64_t j = j_begin + jl;
+        __syncthreads();
+        if (w == 0) {
+            int total = 0;
+            for (int i0 = 0; i0 < L; i0 += 32) {
+                const int i = i0 + lane;
+                int len = 0;
+                uint32_t lb = 0;
+                if (i < L) {
+                    const int sidx = i == 0 ? (int)j : nn[j * k + (i - 1)];
+                    lb = (uint32_t)rptr[sidx];
+                    len = cut[j * L + i];
+                }
+                int inc = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t2 = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o)
+                        inc += t2;
+                }
+                if (i < L) {
+                    lstart[i] = lb;
+                    lpre[i] = (uint32_t)(total + inc - len);
+                }
+                total += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) {
+                misc[0] = total;
+                misc[2] = 0;
+                misc[3] = 0;
+            }
+        }
+        {
+            const uint32_t vinit = want_min ? 0xffffffffu : 0u;
+            uint4 *k4 = reinterpret_cast<uint4 *>(key), *f4 = reinterpret_cast<uint4 *>(first), *v4 = reinterpret_cast<uint4 *>(val);
+            for (int e = tid; e < SLOTS / 4; e += SNN_CTA_THREADS) {
+                k4[e] = make_uint4(SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY, SNN_HASH_EMPTY);
+                f4[e] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                v4[e] = make_uint4(vinit, vinit, vinit, vinit);
+            }
+        }
+        __syncthreads();
+        const int total = misc[0];
+        const int nsteps = (total + 31) >> 5;
+        // entry f of the flat sequence: (cell << 8 | rank, list)
+        auto entry = [&](int f, int &li) -> uint32_t {
+            int lo = 0, hi = L - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (lpre[mid] <= (uint32_t)f)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            li = lo;
+            return __ldg(hosts + lstart[lo] + ((uint32_t)f - lpre[lo]));
+        };
+        // pass 1: insert, counting the distinct keys
+        for (int st = w; st < nsteps; st += NW) {
+            if (*reinterpret_cast<volatile int *>(misc + 2) != 0)
+                break;
+            const int f = st * 32 + lane;
+            bool is_new = false;
+            if (f < total) {
+                int li;
+                const uint32_t ent = entry(f, li);
+                const uint32_t h = ent >> 8;
+                const int rs = li + (int)(ent & 0xffu);
+                int slot = (int)((h * 2654435761u) >> (32 - LOG_SLOTS));
+                while (true) {
+                    const uint32_t old = atomicCAS(key + slot, SNN_HASH_EMPTY, h);
+                    if (old == SNN_HASH_EMPTY) {
+                        is_new = true;
+                        break;
+                    }
+                    if (old == h)
+                        break;
+                    slot = (slot + 1) & (SLOTS - 1);
+                }
+                atomicMin(first + slot, (uint32_t)f);
+                if (want_min)
+                    atomicMin(val + slot, (uint32_t)rs);
+                else
+                    atomicAdd(val + slot, 1u);
+            }
+            const unsigned nm = __ballot_sync(0xffffffffu, is_new);
+            if (lane == 0 && nm != 0u) {
+                const int c = __popc(nm);
+                if (atomicAdd(misc + 3, c) + c > cap)
+                    *reinterpret_cast<volatile int *>(misc + 2) = 1;   // at most 32 warps x 32 keys land after this: the table holds them
+            }
+        }
+        __syncthreads();
+        if (misc[2] != 0) {   // more distinct partners than the table may hold: the merge kernel takes the cell
+            if (tid == 0) {
+                merge_list[atomicAdd(merge_count, 1)] = (int32_t)jl;
+                flagged[jl] = (unsigned char)2;
+                ecnt[jl] = 0;
+            }
+            continue;
+        }
+        // pass 2a: first occurrences per step
+        for (int st = w; st < nsteps; st += NW) {
+            const int f = st * 32 + lane;
+            bool isf = false;
+            if (f < total) {
+                int li;
+                const uint32_t h = entry(f, li) >> 8;
+                int slot = (int)((h * 2654435761u) >> (32 - LOG_SLOTS));
+                while (key[slot] != h)
+                    slot = (slot + 1) & (SLOTS - 1);
+                isf = first[slot] == (uint32_t)f;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, isf);
+            if (lane == 0) {
+                cnt[st] = __popc(m);
+                fmask[st] = m;
+            }
+        }
+        __syncthreads();
+        if (w == 0) {   // exclusive prefix over the steps
+            constexpr int PER = MAXSTEPS / 32;
+            int sum = 0;
+            for (int q = 0; q < PER; ++q) {
+                const int st = lane * PER + q;
+                sum += st < nsteps ? cnt[st] : 0;
+            }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += t2;
+            }
+            int run = inc - sum;
+            for (int q = 0; q < PER; ++q) {
+                const int st = lane * PER + q;
+                if (st < nsteps) {
+                    const int c = cnt[st];
+                    cnt[st] = run;
+                    run += c;
+                }
+            }
+            if (lane == 31)
+                misc[1] = inc;
+        }
+        __syncthreads();
+        // pass 2b: the first occurrences go to their emission positions
+        const int64_t tb = toff[jl];
+        for (int st = w; st < nsteps; st += NW) {
+            const unsigned m = fmask[st];
+            if ((m >> lane) & 1u) {
+                const int f = st * 32 + lane;
+                int li;
+                const uint32_t h = entry(f, li) >> 8;
+                int slot = (int)((h * 2654435761u) >> (32 - LOG_SLOTS));
+                while (key[slot] != h)
+                    slot = (slot + 1) & (SLOTS - 1);
+                const int pos = cnt[st] + __popc(m & lt_mask);
+                tmp_h[tb + pos] = h;
+                tmp_v[tb + pos] = (uint16_t)val[slot];
+            }
+        }
+        if (tid == 0)
+            ecnt[jl] = misc[1];
+    }
+}
+
+static int launch_snn_flat_cta_long(cb200_ctx *ctx, const int32_t *d_nn, int k, int type, int64_t j_begin, int64_t nj, int tier)
+{
+    const int lpad = (k + 1 + 31) & ~31;
+    const size_t smem = (size_t)(1 << 14) * 12 + (size_t)lpad * 8 + (size_t)(SNN_LONG_MAXFLAT / 32 + 1) * 4 +
+                        (size_t)(SNN_LONG_MAXFLAT / 32) * 4 + 32;
+    CB_CUDA(ctx, cudaFuncSetAttribute(k_snn_flat_cta_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int cap = (1 << 14) / 16 * 11;
+    if (const char *ec = getenv("CB200_SNN_LONG_CAP")) {   // tests: force the hand-over to the merge kernel
+        const int v = atoi(ec);
+        if (v >= 1 && v < cap)
+            cap = v;
+    }
+    k_snn_flat_cta_long<<<ctx->num_sms, SNN_CTA_THREADS, smem, ctx->stream>>>(
+        d_nn, k, type, lpad, j_begin, ctx->rptr.p, ctx->hosts.p, ctx->snn_cut.p, ctx->snn_jlist.p + (int64_t)tier * nj,
+        ctx->snn_nlists.p + tier, ctx->ecnt.p, ctx->snn_toff.p, ctx->snn_tmp_h.p,
+        reinterpret_cast<uint16_t *>(ctx->snn_tmp_rc.p), ctx->snn_jlist.p + (int64_t)SNN_TIERS * nj,
+        ctx->snn_nlists.p + SNN_TIERS, ctx->snn_flag.p, cap);
     CB_LAUNCH(ctx);
     return 0;
 }
@@ -880,29 +1107,30 @@ static int snn_count(cb200_ctx *ctx, const int32_t *d_nn, int64_t n, int k, int 
         CB_CUDA(ctx, ctx->snn_jlist.ensure((size_t)nj * (SNN_TIERS + 1)));
         CB_CUDA(ctx, ctx->snn_nlists.ensure(SNN_TIERS + 1));
         CB_CUDA(ctx, cudaMemsetAsync(ctx->snn_nlists.p, 0, (SNN_TIERS + 1) * sizeof(int), ctx->stream));
+        // the two largest tiers and the long tier: one table per CTA (the warp-per-cell kernel has room for 3 / 1 tables per
+        // SM there); CB200_SNN_CTA=0 keeps the warp-per-cell kernel and leaves the long sequences to the merge kernel
+        const char *scta = getenv("CB200_SNN_CTA");
+        const bool use_cta = !(scta != nullptr && strcmp(scta, "0") == 0);
         k_snn_tiers<<<(unsigned)((nj + 255) / 256), 256, 0, ctx->stream>>>(ctx->snn_tcnt.p, ctx->rptr.p, d_nn, j_begin, nj, k,
                                                                          ctx->snn_jlist.p, ctx->snn_nlists.p, ctx->snn_flag.p,
-                                                                         ctx->ecnt.p);
+                                                                         ctx->ecnt.p, use_cta ? SNN_LONG_MAXFLAT : 0);
         CB_LAUNCH(ctx);
         struct { int64_t ttot; int nl[SNN_TIERS + 1]; } hs;
         CB_TRY(cb200_read_back(ctx, &hs.ttot, ctx->snn_toff.p + nj, sizeof(int64_t)));
         CB_TRY(cb200_read_back(ctx, hs.nl, ctx->snn_nlists.p, sizeof(hs.nl)));
         if (getenv("CB200_TRACE") != nullptr)
-            fprintf(stderr, "[cb200] snn: flat entries %lld, cells per tier %d %d %d %d %d, merge kernel %d\n", (long long)hs.ttot,
-                    hs.nl[0], hs.nl[1], hs.nl[2], hs.nl[3], hs.nl[4], hs.nl[5]);
+            fprintf(stderr, "[cb200] snn: flat entries %lld, cells per tier %d %d %d %d %d, long tier %d, merge kernel %d\n",
+                    (long long)hs.ttot, hs.nl[0], hs.nl[1], hs.nl[2], hs.nl[3], hs.nl[4], hs.nl[5], hs.nl[6]);
         CB_CUDA(ctx, ctx->snn_tmp_h.ensure((size_t)hs.ttot));
         CB_CUDA(ctx, ctx->snn_tmp_rc.ensure((size_t)(hs.ttot + 1) / 2));        // 2-byte values
         if (hs.nl[0] > 0) CB_TRY((launch_snn_flat<10>(ctx, d_nn, k, type, j_begin, nj, 0)));
         if (hs.nl[1] > 0) CB_TRY((launch_snn_flat<11>(ctx, d_nn, k, type, j_begin, nj, 1)));
         if (hs.nl[2] > 0) CB_TRY((launch_snn_flat<12>(ctx, d_nn, k, type, j_begin, nj, 2)));
-        // the two largest tiers: one table per CTA (the warp-per-cell kernel has room for 3 / 1 tables per SM there);
-        // CB200_SNN_CTA=0 keeps the warp-per-cell kernel (cross-check)
-        const char *scta = getenv("CB200_SNN_CTA");
-        const bool use_cta = !(scta != nullptr && strcmp(scta, "0") == 0);
         if (hs.nl[3] > 0) CB_TRY(use_cta ? (launch_snn_flat_cta<13>(ctx, d_nn, k, type, j_begin, nj, 3))
                                          : (launch_snn_flat<13>(ctx, d_nn, k, type, j_begin, nj, 3)));
         if (hs.nl[4] > 0) CB_TRY(use_cta ? (launch_snn_flat_cta<14>(ctx, d_nn, k, type, j_begin, nj, 4))
                                          : (launch_snn_flat<14>(ctx, d_nn, k, type, j_begin, nj, 4)));
+        if (hs.nl[5] > 0) CB_TRY(launch_snn_flat_cta_long(ctx, d_nn, k, type, j_begin, nj, 5));   // only filled when use_cta
         ctx->snn_n_merge = hs.nl[SNN_TIERS];
         launch_snn_merge<0>(ctx, g3, d_nn, n, k, type, j_begin, j_end, 0, ctx->snn_jlist.p + (int64_t)SNN_TIERS * nj,
                             ctx->snn_nlists.p + SNN_TIERS);

@@ -164,3 +164,24 @@ def test_snn_cta_tables_equal_warp_tables(gpu_ctx, monkeypatch, scheme):
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     want = O.snn_edges(knn, scheme)
     assert all(np.array_equal(x, y) for x, y in zip(a, want))
+
+
+def test_snn_long_sequences_and_their_hand_over_to_the_merge_kernel(gpu_ctx, monkeypatch):
+    """Cells whose flat sequence exceeds the largest table's capacity run on the long CTA tier (distinct partners are
+    counted while inserting); with a forced tiny capacity every such cell is handed to the merge kernel's list from
+    inside the kernel.  All three routes (long tier, hand-over, CB200_SNN_CTA=0 = merge kernel directly) emit the
+    oracle's edge list."""
+    knn = O.find_knn(synth.make_embedding(2600, 8, seed=23), 180)      # flat sequences of up to ~30 000 entries
+    want = O.snn_edges(knn, "rank", j_begin=2300, j_end=2600)
+    a = gpu_ctx.snn(knn, "rank", j_begin=2300, j_end=2600)
+    assert all(np.array_equal(x, y) for x, y in zip(a, want))
+    monkeypatch.setenv("CB200_SNN_LONG_CAP", "200")
+    b = gpu_ctx.snn(knn, "rank", j_begin=2300, j_end=2600)
+    assert all(np.array_equal(x, y) for x, y in zip(b, want))
+    monkeypatch.delenv("CB200_SNN_LONG_CAP")
+    monkeypatch.setenv("CB200_SNN_CTA", "0")
+    c = gpu_ctx.snn(knn, "number", j_begin=2300, j_end=2600)
+    monkeypatch.delenv("CB200_SNN_CTA")
+    d = gpu_ctx.snn(knn, "number", j_begin=2300, j_end=2600)
+    assert all(np.array_equal(x, y) for x, y in zip(c, d))
+    assert all(np.array_equal(x, y) for x, y in zip(d, O.snn_edges(knn, "number", j_begin=2300, j_end=2600)))
