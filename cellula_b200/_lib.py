@@ -113,6 +113,7 @@ SIGNATURES = {
     "cb200_host_weighted_lowess": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.c_double, c_int, c_int, c_vp]),
     "cb200_host_nls_trend": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, c_int]),
     "cb200_host_nls_grid": (c_int, [c_i64, c_vp, c_vp, ctypes.c_double, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
+    "cb200_host_pool_layout": (c_int, [c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cb200_host_gauss_kde": (c_int, [c_i64, c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_int, c_vp]),
 }
 

@@ -656,6 +656,92 @@ static double pool_median(std::vector<double> &v)
     return (lo + hi) / 2.0;
 }
 
+// Host layout of the pooling (scuttle:::.limit_cluster_size + .generateSphere): clusters above max_cluster_size are dealt
+// round-robin into ceil(n / max) parts, new ids in order of first appearance; per cluster the member cells (ascending),
+// the ring order by library size (stable sort; odd ranks ascending, then even ranks descending) and the mean library
+// size.  Returns false when a cluster code is negative.
+static bool pool_layout(int64_t N, const int32_t *clusters, const double *lib, int64_t max_cluster_size, std::vector<int32_t> &cl,
+                        int &C, std::vector<int64_t> &cl_ptr, std::vector<int32_t> &members, std::vector<int32_t> &ring,
+                        std::vector<double> &meanlib)
+{
+    cl.assign((size_t)N, 0);
+    C = 0;
+    {
+        int32_t maxc = 0;
+        if (clusters != nullptr)
+            for (int64_t i = 0; i < N; ++i) {
+                if (clusters[i] < 0)
+                    return false;
+                maxc = clusters[i] > maxc ? clusters[i] : maxc;
+            }
+        std::vector<int64_t> cnt((size_t)maxc + 1, 0), seen((size_t)maxc + 1, 0);
+        std::vector<int32_t> first_id((size_t)maxc + 1, -1), mult((size_t)maxc + 1, 1);
+        for (int64_t i = 0; i < N; ++i)
+            cnt[(size_t)(clusters ? clusters[i] : 0)] += 1;
+        for (int64_t i = 0; i < N; ++i) {
+            const size_t o = (size_t)(clusters ? clusters[i] : 0);
+            if (first_id[o] < 0) {
+                first_id[o] = C;
+                mult[o] = (max_cluster_size > 0 && cnt[o] > max_cluster_size) ? (int32_t)((cnt[o] + max_cluster_size - 1) / max_cluster_size) : 1;
+                C += mult[o];
+            }
+            cl[(size_t)i] = first_id[o] + (int32_t)(seen[o] % mult[o]);
+            seen[o] += 1;
+        }
+    }
+    cl_ptr.assign((size_t)C + 1, 0);
+    for (int64_t i = 0; i < N; ++i)
+        cl_ptr[(size_t)cl[(size_t)i] + 1] += 1;
+    for (int c = 0; c < C; ++c)
+        cl_ptr[(size_t)c + 1] += cl_ptr[(size_t)c];
+    members.assign((size_t)N, 0);
+    ring.assign((size_t)N, 0);
+    meanlib.assign((size_t)C, 0.0);
+    {
+        std::vector<int64_t> cur(cl_ptr.begin(), cl_ptr.end() - 1);
+        for (int64_t i = 0; i < N; ++i)
+            members[(size_t)cur[(size_t)cl[(size_t)i]]++] = (int32_t)i;
+    }
+    pool_parallel_for(C, [&](int c) {
+        const int64_t b = cl_ptr[(size_t)c], e = cl_ptr[(size_t)c + 1];
+        std::vector<int32_t> o(members.begin() + b, members.begin() + e);
+        std::stable_sort(o.begin(), o.end(), [&](int32_t a, int32_t bb) { return lib[(size_t)a] < lib[(size_t)bb]; });
+        const int64_t n = e - b;
+        int64_t w = b;
+        for (int64_t i = 0; i < n; i += 2)
+            ring[(size_t)w++] = o[(size_t)i];
+        for (int64_t i = (n & 1) ? n - 2 : n - 1; i >= 1; i -= 2)
+            ring[(size_t)w++] = o[(size_t)i];
+        double s = 0.0;
+        for (int64_t i = b; i < e; ++i)
+            s += lib[(size_t)members[(size_t)i]];
+        meanlib[(size_t)c] = s / (double)n;
+    });
+    return true;
+}
+
+// the same layout for host-side tests (no device work): cl_out[n], ring_out[n], cl_ptr_out[n + 1] (first n_clusters + 1 used)
+extern "C" int cb200_host_pool_layout(int64_t n, const int32_t *clusters, const double *lib, int64_t max_cluster_size,
+                                      int32_t *cl_out, int32_t *ring_out, int64_t *cl_ptr_out, double *meanlib_out,
+                                      int32_t *n_clusters_out)
+{
+    if (n < 1 || lib == nullptr || cl_out == nullptr || ring_out == nullptr || cl_ptr_out == nullptr || n_clusters_out == nullptr)
+        return 1;
+    std::vector<int32_t> cl, members, ring;
+    std::vector<int64_t> cl_ptr;
+    std::vector<double> meanlib;
+    int C = 0;
+    if (!pool_layout(n, clusters, lib, max_cluster_size, cl, C, cl_ptr, members, ring, meanlib))
+        return 2;
+    std::copy(cl.begin(), cl.end(), cl_out);
+    std::copy(ring.begin(), ring.end(), ring_out);
+    std::copy(cl_ptr.begin(), cl_ptr.end(), cl_ptr_out);
+    if (meanlib_out != nullptr)
+        std::copy(meanlib.begin(), meanlib.end(), meanlib_out);
+    *n_clusters_out = C;
+    return 0;
+}
+
 extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters, const int32_t *sizes, int n_sizes,
                                          double min_mean, int64_t max_cluster_size, double *sf_out, int64_t *n_nonpositive,
                                          double *stage_ms_out)
@@ -714,43 +800,14 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
     if (min_mean < 1e-8)
         min_mean = 1e-8;
 
-    // ---- clusters: size limit (round-robin split, ids by first appearance), members, ring order
-    std::vector<int32_t> cl((size_t)N, 0);
+    // ---- clusters: size limit (round-robin split, ids by first appearance), members, ring order (host: pool_layout)
+    std::vector<int32_t> cl, members, ring;
+    std::vector<int64_t> cl_ptr;
+    std::vector<double> meanlib;
     int C = 0;
-    {
-        int32_t maxc = 0;
-        if (clusters != nullptr)
-            for (int64_t i = 0; i < N; ++i) {
-                CB_CHECK(ctx, clusters[i] >= 0, "cb200_pooled_size_factors: cluster codes must be >= 0");
-                maxc = clusters[i] > maxc ? clusters[i] : maxc;
-            }
-        std::vector<int64_t> cnt((size_t)maxc + 1, 0), seen((size_t)maxc + 1, 0);
-        std::vector<int32_t> first_id((size_t)maxc + 1, -1), mult((size_t)maxc + 1, 1);
-        for (int64_t i = 0; i < N; ++i)
-            cnt[(size_t)(clusters ? clusters[i] : 0)] += 1;
-        for (int64_t i = 0; i < N; ++i) {
-            const size_t o = (size_t)(clusters ? clusters[i] : 0);
-            if (first_id[o] < 0) {
-                first_id[o] = C;
-                mult[o] = (max_cluster_size > 0 && cnt[o] > max_cluster_size) ? (int32_t)((cnt[o] + max_cluster_size - 1) / max_cluster_size) : 1;
-                C += mult[o];
-            }
-            cl[(size_t)i] = first_id[o] + (int32_t)(seen[o] % mult[o]);
-            seen[o] += 1;
-        }
-    }
-    std::vector<int64_t> cl_ptr((size_t)C + 1, 0);
-    for (int64_t i = 0; i < N; ++i)
-        cl_ptr[(size_t)cl[(size_t)i] + 1] += 1;
-    for (int c = 0; c < C; ++c)
-        cl_ptr[(size_t)c + 1] += cl_ptr[(size_t)c];
-    std::vector<int32_t> members((size_t)N), ring((size_t)N), ns_of((size_t)C);
-    {
-        std::vector<int64_t> cur(cl_ptr.begin(), cl_ptr.end() - 1);
-        for (int64_t i = 0; i < N; ++i)
-            members[(size_t)cur[(size_t)cl[(size_t)i]]++] = (int32_t)i;
-    }
-    std::vector<double> meanlib((size_t)C);
+    CB_CHECK(ctx, pool_layout(N, clusters, lib.data(), max_cluster_size, cl, C, cl_ptr, members, ring, meanlib),
+             "cb200_pooled_size_factors: cluster codes must be >= 0");
+    std::vector<int32_t> ns_of((size_t)C);
     int n_max = 0;
     for (int c = 0; c < C; ++c) {
         const int64_t n = cl_ptr[(size_t)c + 1] - cl_ptr[(size_t)c];
@@ -763,22 +820,6 @@ extern "C" int cb200_pooled_size_factors(cb200_ctx *ctx, const int32_t *clusters
         ns_of[(size_t)c] = ns;
         n_max = n > n_max ? (int)n : n_max;
     }
-    pool_parallel_for(C, [&](int c) {
-        const int64_t b = cl_ptr[(size_t)c], e = cl_ptr[(size_t)c + 1];
-        std::vector<int32_t> o(members.begin() + b, members.begin() + e);
-        std::stable_sort(o.begin(), o.end(), [&](int32_t a, int32_t bb) { return lib[(size_t)a] < lib[(size_t)bb]; });
-        const int64_t n = e - b;
-        int64_t w = b;
-        for (int64_t i = 0; i < n; i += 2)
-            ring[(size_t)w++] = o[(size_t)i];
-        for (int64_t i = (n & 1) ? n - 2 : n - 1; i >= 1; i -= 2)
-            ring[(size_t)w++] = o[(size_t)i];
-        double s = 0.0;
-        for (int64_t i = b; i < e; ++i)
-            s += lib[(size_t)members[(size_t)i]];
-        meanlib[(size_t)c] = s / (double)n;
-    });
-
     // ---- device buffers
     DevBuf<int32_t> d_cl, d_ring, d_sizes, d_ns, d_pslot, d_gf;
     DevBuf<int64_t> d_clptr;

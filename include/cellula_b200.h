@@ -360,6 +360,13 @@ int cb200_host_nls_trend(int64_t n, const double *v, const double *m, const doub
 /* grid search for the start values of the parametric trend (scran's .get_nls_starts); first minimum, b fastest */
 int cb200_host_nls_grid(int64_t n, const double *v, const double *m, double grad, int nb, const double *bgrid, int nn,
                         const double *ngrid, int *ib_out, int *in_out);
+/* Host layout of cb200_pooled_size_factors (no device work; exported so that the CPU test suite can check it against the
+ * oracle): scuttle:::.limit_cluster_size + .generateSphere.  cl_out[n] = cluster codes after the size limit, ring_out[n] =
+ * cells in ring order (clusters concatenated), cl_ptr_out[n + 1] (first *n_clusters_out + 1 entries used), meanlib_out[n]
+ * (nullable; first *n_clusters_out used) = mean library size per cluster. */
+int cb200_host_pool_layout(int64_t n, const int32_t *clusters /* nullable */, const double *lib, int64_t max_cluster_size,
+                           int32_t *cl_out, int32_t *ring_out, int64_t *cl_ptr_out, double *meanlib_out,
+                           int32_t *n_clusters_out);
 int cb200_host_gauss_kde(int64_t n, const double *m, double bw, double lo, double hi, int ng, double *dens_out);
 
 #ifdef __cplusplus

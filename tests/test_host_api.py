@@ -89,3 +89,35 @@ def test_snn_bounds_balance_and_cover():
     b = snn_bounds(1306127, 8)
     work = [b[r + 1] ** 2 - b[r] ** 2 for r in range(8)]
     assert max(work) / min(work) < 1.001
+
+
+def test_pool_layout_matches_the_oracle():
+    """Host half of cb200_pooled_size_factors (cluster size limit + ring order) against the oracle restatement of
+    scuttle:::.limit_cluster_size / .generateSphere -- no GPU needed (cb200_host_pool_layout does no device work)."""
+    import ctypes
+    import numpy as np
+    from cellula_b200 import _lib
+    from oracle import oracle as O
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    for n, ncl, max_size in ((1, 1, 3000), (50, 1, 0), (997, 4, 100), (3000, 7, 250), (400, 3, 3000)):
+        clusters = (rng.integers(0, ncl, n) * 3 + 2).astype(np.int32)          # arbitrary non-contiguous codes
+        lib = rng.integers(5, 40, n).astype(np.float64)                         # many ties: the sort must be stable
+        cl, ring = np.empty(n, np.int32), np.empty(n, np.int32)
+        ptr, ml = np.empty(n + 1, np.int64), np.empty(n)
+        nc = ctypes.c_int32()
+        rc = L.cb200_host_pool_layout(n, clusters.ctypes.data, lib.ctypes.data, max_size, cl.ctypes.data, ring.ctypes.data,
+                                      ptr.ctypes.data, ml.ctypes.data, ctypes.cast(ctypes.byref(nc), ctypes.c_void_p))
+        assert rc == 0
+        o_cl, o_n = O.limit_cluster_size(clusters, max_size if max_size > 0 else None)
+        assert nc.value == o_n and np.array_equal(cl, o_cl)
+        for c in range(o_n):
+            cells = np.flatnonzero(o_cl == c)
+            assert ptr[c + 1] - ptr[c] == cells.size
+            assert np.array_equal(ring[ptr[c]:ptr[c + 1]], cells[O.pool_ring(lib[cells])])
+            assert ml[c] == lib[cells].sum() / cells.size
+    bad = np.array([0, -1, 2], dtype=np.int32)
+    rc = L.cb200_host_pool_layout(3, bad.ctypes.data, np.ones(3).ctypes.data, 0, np.empty(3, np.int32).ctypes.data,
+                                  np.empty(3, np.int32).ctypes.data, np.empty(4, np.int64).ctypes.data, None,
+                                  ctypes.cast(ctypes.byref(ctypes.c_int32()), ctypes.c_void_p))
+    assert rc == 2
