@@ -121,3 +121,58 @@ def test_pool_layout_matches_the_oracle():
                                   np.empty(3, np.int32).ctypes.data, np.empty(4, np.int64).ctypes.data, None,
                                   ctypes.cast(ctypes.byref(ctypes.c_int32()), ctypes.c_void_p))
     assert rc == 2
+
+
+def test_deconvolution_option_routes_cluster_labels_to_the_pooling(monkeypatch):
+    """options['size_factors'] = 'deconvolution' (R/doNormAndReduce.R:57-71 order): the labels of colData['quickCluster']
+    become 0-based codes for cb200_pooled_size_factors, its vector is what logNormCounts re-centres, and non-positive
+    estimates stop the call.  Driven with a recording stand-in for the device context (no GPU here)."""
+    import cellula_b200.api as api
+
+    class Stop(Exception):
+        pass
+
+    class FakeCtx:
+        def __init__(self, n_bad):
+            self.calls, self.n_bad = [], n_bad
+
+        def load_csc(self, *a, **k):
+            self.calls.append("load")
+
+        def pooled_size_factors(self, codes):
+            self.calls.append(("pool", None if codes is None else codes.copy()))
+            return np.array([2.0, 4.0]), self.n_bad
+
+        def size_factors(self, sf_in):
+            self.calls.append(("sf", None if sf_in is None else np.asarray(sf_in).copy()))
+            raise Stop()
+
+    old = dict(api.options)
+    try:
+        api.options.update(size_factors="deconvolution", skip_umap=True)
+        sce = tiny_sce()
+        sce.colData["quickCluster"] = np.array(["z", "a"])
+        fake = FakeCtx(0)
+        monkeypatch.setattr(api, "get_context", lambda: fake)
+        with pytest.raises(Stop):
+            api.doNormAndReduce(sce, hvg_ntop=2, verbose=False)
+        assert fake.calls[0] == "load" and fake.calls[1][0] == "pool" and fake.calls[1][1].tolist() == [1, 0]
+        assert fake.calls[2][0] == "sf" and fake.calls[2][1].tolist() == [2.0, 4.0]
+        fake = FakeCtx(0)
+        monkeypatch.setattr(api, "get_context", lambda: fake)
+        with pytest.raises(Stop):
+            api.doNormAndReduce(tiny_sce(), hvg_ntop=2, verbose=False)          # no labels: one cluster
+        assert fake.calls[1] == ("pool", None)
+        fake = FakeCtx(1)
+        monkeypatch.setattr(api, "get_context", lambda: fake)
+        with pytest.raises(ValueError, match="non-positive size factor"):
+            api.doNormAndReduce(tiny_sce(), hvg_ntop=2, verbose=False)
+        api.options.update(size_factors="library")
+        fake = FakeCtx(0)
+        monkeypatch.setattr(api, "get_context", lambda: fake)
+        with pytest.raises(Stop):
+            api.doNormAndReduce(tiny_sce(), hvg_ntop=2, verbose=False)
+        assert fake.calls[1] == ("sf", None)                                      # library-size factors: no pooling
+    finally:
+        api.options.clear()
+        api.options.update(old)
